@@ -1,0 +1,66 @@
+import gzip
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def _ensure_built():
+    """Build the checkers (and the product library) if they are not there yet.
+    On the GPU box the prebuilt .so files travel with the snapshot."""
+    from sregex_b200 import capi
+    if not os.path.exists(capi.ORACLE_LIB):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
+    if not os.path.exists(capi.REF_LIB) and os.path.isdir("/root/reference/src/sregex"):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    if not os.path.exists(capi.CUDA_LIB) and os.path.exists(
+            os.path.join(ROOT, "sregex_b200", "csrc", "Makefile")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "sregex_b200", "csrc")])
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built():
+    _ensure_built()
+
+
+@pytest.fixture(scope="session")
+def golden():
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "t_suite.json.gz")) as f:
+        g = json.load(f)
+    for b in g["blocks"]:
+        b["regexes_b"] = [bytes.fromhex(r) for r in b["regexes"]]
+        b["subject_b"] = bytes.fromhex(b["subject"])
+    return g
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from sregex_b200 import capi
+    return capi.load("oracle")
+
+
+@pytest.fixture(scope="session")
+def ref():
+    from sregex_b200 import capi
+    if not os.path.exists(capi.REF_LIB):
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    return capi.load("ref")
+
+
+@pytest.fixture(scope="session")
+def cuda():
+    from sregex_b200 import capi
+    return capi.load("cuda")
+
+
+def runnable(golden):
+    return [b for b in golden["blocks"] if "skip" not in b and "error" not in b]

@@ -1,0 +1,75 @@
+"""The CPU oracle (oracle/sre_oracle.c + the host front end) against the
+reference's golden vectors: every runnable block of the reference's t/ suite,
+answers recorded from the unmodified reference by tests/golden/gen_golden.py."""
+import random
+
+from conftest import runnable
+from sregex_b200 import capi
+
+
+def test_golden_has_whole_corpus(golden):
+    st = golden["stats"]
+    assert st["blocks"] == 1999 and st["runnable"] >= 1918 and st["explicit_checked"] >= 70
+    assert all(b.get("modes_agree", True) for b in golden["blocks"])
+
+
+def test_thompson_against_golden(golden, oracle):
+    for b in runnable(golden):
+        p = oracle.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        assert oracle.thompson(p, b["subject_b"]) == b["thompson"], (b["file"], b["name"])
+        p.close()
+
+
+def test_thompson_streaming_against_golden(golden, oracle):
+    """1-byte chunks: the whole rc sequence, incl. the interpreter's
+    one-step-late SRE_OK (sre_vm_thompson.c:233-235)."""
+    for b in runnable(golden):
+        p = oracle.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        got = oracle.thompson(p, b["subject_b"], capi.split_chunks(b["subject_b"]))
+        assert got == b["thompson_split"], (b["file"], b["name"])
+        p.close()
+
+
+def test_pike_against_golden(golden, oracle):
+    for b in runnable(golden):
+        p = oracle.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        rc, ov = oracle.pike(p, b["subject_b"])
+        assert (rc, ov) == (b["pike"]["rc"], b["pike"]["ov"]), (b["file"], b["name"])
+        p.close()
+
+
+def test_pike_streaming_against_golden(golden, oracle):
+    """1-byte chunks: final rc/ovector plus the temp-capture / pending-match
+    trace after every call (sre_vm_pike.c:640-658, 692-735)."""
+    for b in runnable(golden):
+        p = oracle.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        trace, rc, ov = oracle.pike(p, b["subject_b"], capi.split_chunks(b["subject_b"]))
+        want = b["pike_split"]
+        assert (rc, ov) == (want["rc"], want["ov"]), (b["file"], b["name"])
+        assert [list(t) for t in trace] == want["trace"], (b["file"], b["name"])
+        p.close()
+
+
+def _random_subject(rng, alphabet, n):
+    return bytes(rng.choice(alphabet) for _ in range(n))
+
+
+def test_oracle_against_live_reference_fuzz(golden, oracle, ref):
+    """Seeded random subjects over the corpus regexes, oracle vs the reference
+    itself (only where oracle/_ref exists, i.e. not required on the GPU box)."""
+    rng = random.Random(0x5EED)
+    blocks = runnable(golden)
+    for b in rng.sample(blocks, 400):
+        po = oracle.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        pr = ref.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        alphabet = list(set(b["subject_b"]) | set(b"ab \n_")) or list(b"ab")
+        for _ in range(6):
+            s = _random_subject(rng, alphabet, rng.randrange(0, 40))
+            assert oracle.thompson(po, s) == ref.thompson(pr, s), (b["name"], s)
+            assert oracle.pike(po, s) == ref.pike(pr, s), (b["name"], s)
+            cuts = sorted(rng.sample(range(len(s) + 1), min(len(s) + 1, 2)))
+            chunks = [(s[:cuts[0]], False), (s[cuts[0]:cuts[-1]], False), (s[cuts[-1]:], True)]
+            assert oracle.thompson(po, s, chunks) == ref.thompson(pr, s, chunks), (b["name"], s)
+            assert oracle.pike(po, s, chunks) == ref.pike(pr, s, chunks), (b["name"], s, chunks)
+        po.close()
+        pr.close()
