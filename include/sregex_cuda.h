@@ -1,0 +1,127 @@
+/*
+ * sregex_cuda.h -- batch / device-pointer extension of the sregex C API.
+ *
+ * New in this build.  The reference's executors take one buffer per call
+ * (sre_vm_thompson_exec, sregex.h:147-148; sre_vm_pike_exec, sregex.h:133-134;
+ * the JIT handler type, sregex.h:158-159); a kernel launch per 1 KB line would
+ * cap throughput at launch rate, so the GPU library adds entry points that take
+ * a whole corpus.  Each function below names the reference call it is the batch
+ * form of.  Plain C ABI: pointers and sizes only.  Pointers named dev_* are CUDA
+ * device pointers; `stream` is a cudaStream_t passed as void* (NULL = default
+ * stream).  Functions returning int give SRE_OK or SRE_ERROR unless noted; there
+ * is no CPU fallback -- without a usable CUDA device they return SRE_ERROR.
+ */
+#ifndef SREGEX_B200_SREGEX_CUDA_H
+#define SREGEX_B200_SREGEX_CUDA_H
+
+#include <sregex/sregex.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* GPU tables lowered from a compiled program; cached inside the program and
+ * released with the pool that owns the program. */
+typedef struct sre_cuda_program_s  sre_cuda_program_t;
+
+enum {
+    SRE_CUDA_ENGINE_AUTO        = 0,    /* best tier available                       */
+    SRE_CUDA_ENGINE_DFA_TILED   = 1,    /* smem-staged thread-per-line DFA           */
+    SRE_CUDA_ENGINE_DFA_GENERIC = 2,    /* thread-per-line DFA, any alignment        */
+    SRE_CUDA_ENGINE_NFA         = 3     /* warp-per-line bit-parallel NFA            */
+};
+
+typedef struct {
+    uint32_t  prog_len;         /* bytecode instructions                            */
+    uint32_t  nfa_states;       /* lowered (pc, look-ahead) states                  */
+    uint32_t  nfa_classes;      /* byte classes                                     */
+    uint32_t  nfa_kinds;        /* 3 if look-behind assertions are present          */
+    uint32_t  nfa_shift_states; /* states handled by the shift path                 */
+    uint32_t  dfa_states;       /* 0: subset construction gave up                   */
+    uint32_t  dfa_classes;
+    uint32_t  dfa_byte_table;   /* 1: [state][byte] u8 table (<= 256 states)        */
+    uint32_t  nregexes;
+    uint32_t  pike_slots;       /* capture slots of the whole set                   */
+    uint64_t  pike_ctx_bytes;   /* device scratch per concurrent Pike context       */
+} sre_cuda_info_t;
+
+/* Lowering pass (host) + upload.  The batch analogue of
+ * sre_vm_thompson_jit_compile (sregex.h:162-163): done once per program. */
+SRE_API sre_cuda_program_t *sre_cuda_program_create(sre_program_t *prog);
+SRE_API int sre_cuda_program_info(sre_cuda_program_t *cp, sre_cuda_info_t *info);
+
+/*
+ * Batch form of sre_vm_thompson_exec(ctx, line, len, eof=1) with a fresh ctx per
+ * line (how bench/sregex.c:224-228 and the nginx module use it).  Line i is
+ * dev_buf[i*pitch, i*pitch + linelen).  dev_rc[i] = SRE_OK or SRE_DECLINED.
+ */
+SRE_API int sre_cuda_thompson_exec_lines(sre_cuda_program_t *cp,
+    const uint8_t *dev_buf, size_t nlines, size_t pitch, size_t linelen,
+    int32_t *dev_rc, int engine, void *stream);
+
+/* Same with ragged lines: line i is dev_buf[dev_offsets[i], dev_offsets[i+1]). */
+SRE_API int sre_cuda_thompson_exec_ragged(sre_cuda_program_t *cp,
+    const uint8_t *dev_buf, const int64_t *dev_offsets, size_t nlines,
+    int32_t *dev_rc, int engine, void *stream);
+
+/*
+ * Batch form of sre_vm_pike_exec(ctx, line, len, eof=1, NULL) with a fresh ctx
+ * per line.  dev_rc[i] = matched regex id (>= 0), SRE_DECLINED or SRE_ERROR;
+ * dev_ovec[i*ovec_slots ..] = what the reference leaves in the caller's ovector
+ * (matched regex's groups, -1 fill; all -1 when there is no match).
+ * dev_offsets may be NULL (fixed pitch).  dev_select may be NULL; otherwise only
+ * lines with dev_select[i] == SRE_OK are run (others: rc = dev_select[i]), which
+ * lets a Thompson pass gate the capture pass.
+ */
+SRE_API int sre_cuda_pike_exec_lines(sre_cuda_program_t *cp,
+    const uint8_t *dev_buf, const int64_t *dev_offsets, size_t nlines,
+    size_t pitch, size_t linelen, const int32_t *dev_select, int32_t *dev_rc,
+    int64_t *dev_ovec, size_t ovec_slots, void *stream);
+
+/*
+ * Chunk-parallel form of a sequence of sre_vm_thompson_exec(ctx, chunk_k,
+ * chunk_bytes, eof) calls over one long stream resident on the device.
+ * *state_io carries the automaton state across calls (set it to
+ * SRE_CUDA_STATE_INIT before the first call).  Returns SRE_OK / SRE_AGAIN /
+ * SRE_DECLINED like the reference would after the last chunk; on SRE_OK
+ * *match_chunk (if not NULL) is the index of the chunk_bytes-sized chunk in
+ * which the reference's call sequence first returns SRE_OK.
+ */
+#define SRE_CUDA_STATE_INIT  0xffffffffu
+SRE_API int sre_cuda_thompson_exec_stream(sre_cuda_program_t *cp,
+    const uint8_t *dev_buf, size_t len, size_t chunk_bytes, unsigned eof,
+    uint32_t *state_io, int64_t *match_chunk, void *stream);
+
+/*
+ * Pieces of the stream scan, exposed for multi-GPU sharding: each
+ * rank reduces its shard to one transfer function (nstates bytes, host), the
+ * functions are all-gathered, composed in rank order, and each rank then
+ * resolves its own first match with the entry state it was given.
+ */
+SRE_API int sre_cuda_thompson_stream_reduce(sre_cuda_program_t *cp,
+    const uint8_t *dev_buf, size_t len, uint8_t *host_fn /* [dfa_states] */,
+    void *stream);
+SRE_API int sre_cuda_thompson_stream_resolve(sre_cuda_program_t *cp,
+    uint32_t entry_state, uint32_t *exit_state, int64_t *first_match_offset,
+    void *stream);
+
+/* Host-buffer conveniences (the end-to-end path: H2D + kernels + D2H inside) */
+SRE_API int sre_cuda_thompson_exec_lines_host(sre_cuda_program_t *cp,
+    const uint8_t *host_buf, size_t nlines, size_t pitch, size_t linelen,
+    int32_t *host_rc, int engine);
+SRE_API int sre_cuda_pike_exec_lines_host(sre_cuda_program_t *cp,
+    const uint8_t *host_buf, size_t nlines, size_t pitch, size_t linelen,
+    int gate_with_thompson, int32_t *host_rc, int64_t *host_ovec,
+    size_t ovec_slots);
+
+/* Tuning / introspection */
+SRE_API void sre_cuda_set_variant(int variant);     /* tile shape of DFA_TILED   */
+SRE_API long sre_cuda_launch_count(int reset);      /* kernels launched so far   */
+SRE_API int sre_cuda_device_available(void);        /* 1 if a CUDA device works  */
+SRE_API const char *sre_cuda_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SREGEX_B200_SREGEX_CUDA_H */

@@ -1,0 +1,995 @@
+/*
+ * sre_cuda_api.cu -- the C ABI of libsregex_cuda: the reference's executor
+ * entry points (include/sregex/sregex.h) and the batch extension
+ * (include/sregex_cuda.h), implemented on the CUDA kernels of ../kernels.
+ *
+ * No CPU fallback lives here: every *_exec entry point uploads its input (when
+ * given a host buffer), launches kernels and downloads the verdict.  Without a
+ * usable CUDA device the create/exec calls fail (NULL / SRE_ERROR) and say so
+ * on stderr.
+ */
+#include <sregex_cuda.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../host/sre_internal.h"
+#include "../kernels/sre_kernels.cuh"
+#include "../lower/sre_lower.h"
+
+namespace {
+
+std::atomic<long>   g_launches(0);
+int                 g_variant = 0;
+thread_local char   g_err[256] = "";
+
+const uint32_t MAX_DFA_STATES = 4096;
+const uint32_t MAX_NFA_STATES = 4096;
+const size_t   PIKE_SCRATCH_BUDGET = (size_t) 6 << 30;
+
+int fail(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "libsregex_cuda: %s\n", g_err);
+    return SRE_ERROR;
+}
+
+#define CUDA_TRY(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t e_ = (expr);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            return fail("%s failed: %s", #expr, cudaGetErrorString(e_));                 \
+        }                                                                                \
+    } while (0)
+
+void count_launches(int n) { g_launches += n; }
+
+bool device_ok()
+{
+    static int state = -1;
+    if (state < 0) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        state = (e == cudaSuccess && n > 0) ? 1 : 0;
+        if (!state) {
+            cudaGetLastError();
+        }
+    }
+    return state == 1;
+}
+
+/* host-side builder of one device blob holding every table of a program */
+struct blob_t {
+    std::vector<uint8_t> bytes;
+    size_t add(const void *p, size_t n)
+    {
+        size_t ofs = (bytes.size() + 255) & ~(size_t) 255;
+        bytes.resize(ofs + ((n + 15) & ~(size_t) 15), 0);
+        if (n) {
+            memcpy(&bytes[ofs], p, n);
+        }
+        return ofs;
+    }
+};
+
+}  // namespace
+
+struct sre_cuda_program_s {
+    sre_program_t      *prog = nullptr;
+    sre_lowered_t       low;
+    uint8_t            *d_blob = nullptr;
+    bool                has_dfa = false, has_nfa = false;
+    sre_dev_dfa_t       dfa;
+    sre_dev_nfa_t       nfa;
+    sre_dev_pike_t      pike;
+    uint32_t            nfa_shift = 0;
+    /* lazily grown workspaces */
+    uint8_t            *pike_scratch = nullptr;
+    size_t              pike_nctx = 0;
+    uint8_t            *stream_ws = nullptr;
+    size_t              stream_ws_bytes = 0;
+    sre_stream_ws_t     ws;
+    uint32_t           *d_exit = nullptr;       /* exit state + match offset */
+    uint8_t            *io_buf = nullptr;       /* host-variant staging      */
+    size_t              io_bytes = 0;
+    /* stream_reduce -> stream_resolve hand-over */
+    const uint8_t      *red_buf = nullptr;
+    size_t              red_len = 0;
+    int                 red_top = 0;
+};
+
+namespace {
+
+void program_destroy(void *data)
+{
+    sre_cuda_program_t *cp = static_cast<sre_cuda_program_t *>(data);
+    if (cp->prog) {
+        cp->prog->lowered = nullptr;
+    }
+    cudaFree(cp->d_blob);
+    cudaFree(cp->pike_scratch);
+    cudaFree(cp->stream_ws);
+    cudaFree(cp->d_exit);
+    cudaFree(cp->io_buf);
+    delete cp;
+}
+
+int upload(sre_cuda_program_t *cp)
+{
+    const sre_program_t *prog = cp->prog;
+    const sre_nfa_t &n = cp->low.nfa;
+    blob_t b;
+    size_t o_t256 = 0, o_tcls = 0, o_dcls = 0, o_fin = 0;
+
+    cp->has_dfa = cp->low.has_dfa;
+    if (cp->has_dfa) {
+        const sre_dfa_t &d = cp->low.dfa;
+        if (!d.t256.empty()) {
+            o_t256 = b.add(d.t256.data(), d.t256.size());
+        }
+        o_tcls = b.add(d.trans.data(), d.trans.size() * 2);
+        o_dcls = b.add(d.clsmap, 256);
+        o_fin = b.add(d.fin.data(), d.fin.size());
+    }
+
+    /* NFA tables, every bitset row padded to WP = 32 * words-per-lane words */
+    cp->has_nfa = n.nstates <= MAX_NFA_STATES;
+    size_t o_ncls = 0, o_kind = 0, o_mv = 0, o_mt = 0, o_eof = 0, o_init = 0, o_shift = 0, o_follow = 0,
+           o_rowidx = 0;
+    uint32_t WP = 32, nrows = 0;
+    if (cp->has_nfa) {
+        const uint32_t wpl = (n.nwords + 31) / 32;
+        WP = 32 * (wpl <= 1 ? 1 : wpl <= 2 ? 2 : 4);
+        const uint32_t W = n.nwords;
+        auto pad_rows = [&](const std::vector<uint32_t> &src, size_t rows) {
+            std::vector<uint32_t> out(rows * WP, 0);
+            for (size_t r = 0; r < rows; r++) {
+                memcpy(&out[r * WP], &src[r * W], W * 4);
+            }
+            return out;
+        };
+        std::vector<uint32_t> mv = pad_rows(n.mv, n.nclasses), mt = pad_rows(n.mt, n.nclasses),
+                              eofm = pad_rows(n.mt_eof, 1), init = pad_rows(n.init, 1),
+                              shift = pad_rows(n.shift_mask, 1);
+        std::vector<int32_t> rowidx((size_t) WP * 32, -1);
+        for (uint32_t s = 0; s < n.nstates; s++) {
+            const bool is_shift = (n.shift_mask[s >> 5] >> (s & 31)) & 1;
+            const bool is_match = prog->insts[n.state_pc[s]].opcode == SRE_OPCODE_MATCH;
+            cp->nfa_shift += is_shift;
+            if (!is_shift && !is_match) {
+                rowidx[s] = (int32_t) nrows++;
+            }
+        }
+        std::vector<uint32_t> follow((size_t) n.nkinds * (nrows ? nrows : 1) * WP, 0);
+        for (uint32_t k = 0; k < n.nkinds; k++) {
+            for (uint32_t s = 0; s < n.nstates; s++) {
+                if (rowidx[s] >= 0) {
+                    memcpy(&follow[((size_t) k * nrows + rowidx[s]) * WP], n.follow_row(k, s), W * 4);
+                }
+            }
+        }
+        o_ncls = b.add(n.clsmap, 256);
+        o_kind = b.add(n.cls_kind.data(), n.cls_kind.size());
+        o_mv = b.add(mv.data(), mv.size() * 4);
+        o_mt = b.add(mt.data(), mt.size() * 4);
+        o_eof = b.add(eofm.data(), eofm.size() * 4);
+        o_init = b.add(init.data(), init.size() * 4);
+        o_shift = b.add(shift.data(), shift.size() * 4);
+        o_follow = b.add(follow.data(), follow.size() * 4);
+        o_rowidx = b.add(rowidx.data(), rowidx.size() * 4);
+    }
+
+    /* Pike: the bytecode itself */
+    std::vector<uint32_t> slot_ofs(prog->nregexes + 1, 0);
+    for (sre_uint_t i = 0; i < prog->nregexes; i++) {
+        slot_ofs[i + 1] = slot_ofs[i] + 2 * (uint32_t) (prog->multi_ncaps[i] + 1);
+    }
+    const size_t o_insts = b.add(prog->insts, (size_t) prog->len * sizeof(sre_instruction_t));
+    const size_t o_ranges = b.add(prog->ranges, (size_t) prog->nranges * 2);
+    const size_t o_leading = b.add(prog->leading, (size_t) prog->nleading * 4);
+    const size_t o_slots = b.add(slot_ofs.data(), slot_ofs.size() * 4);
+
+    if (cudaMalloc(&cp->d_blob, b.bytes.size() + 256) != cudaSuccess
+        || cudaMemcpy(cp->d_blob, b.bytes.data(), b.bytes.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+    {
+        return fail("uploading program tables failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    uint8_t *base = cp->d_blob;
+
+    if (cp->has_dfa) {
+        const sre_dfa_t &d = cp->low.dfa;
+        cp->dfa.nstates = d.nstates;
+        cp->dfa.nclasses = d.nclasses;
+        cp->dfa.start = d.start;
+        cp->dfa.acc = d.acc;
+        cp->dfa.t256 = d.t256.empty() ? nullptr : base + o_t256;
+        cp->dfa.tcls = reinterpret_cast<const uint16_t *>(base + o_tcls);
+        cp->dfa.clsmap = base + o_dcls;
+        cp->dfa.fin = base + o_fin;
+    }
+    if (cp->has_nfa) {
+        cp->nfa.nstates = n.nstates;
+        cp->nfa.nwords = WP;
+        cp->nfa.nclasses = n.nclasses;
+        cp->nfa.nkinds = n.nkinds;
+        cp->nfa.clsmap = base + o_ncls;
+        cp->nfa.cls_kind = base + o_kind;
+        cp->nfa.mv = reinterpret_cast<const uint32_t *>(base + o_mv);
+        cp->nfa.mt = reinterpret_cast<const uint32_t *>(base + o_mt);
+        cp->nfa.mt_eof = reinterpret_cast<const uint32_t *>(base + o_eof);
+        cp->nfa.init = reinterpret_cast<const uint32_t *>(base + o_init);
+        cp->nfa.shift_mask = reinterpret_cast<const uint32_t *>(base + o_shift);
+        cp->nfa.follow = reinterpret_cast<const uint32_t *>(base + o_follow);
+        cp->nfa.rowidx = reinterpret_cast<const int32_t *>(base + o_rowidx);
+        cp->nfa.nrows = nrows ? nrows : 1;
+    }
+
+    static_assert(sizeof(sre_instruction_t) == sizeof(sre_dev_inst_t), "instruction layout");
+    sre_dev_pike_t &pk = cp->pike;
+    pk.len = prog->len;
+    pk.nslots = slot_ofs[prog->nregexes];
+    pk.nregexes = (uint32_t) prog->nregexes;
+    pk.nleading = prog->nleading;
+    pk.leading_byte = prog->leading_byte;
+    pk.insts = reinterpret_cast<const sre_dev_inst_t *>(base + o_insts);
+    pk.ranges = base + o_ranges;
+    pk.leading = reinterpret_cast<const int32_t *>(base + o_leading);
+    pk.slot_ofs = reinterpret_cast<const uint32_t *>(base + o_slots);
+    pk.max_threads = 2 * prog->len + 16;
+    pk.stack_cap = 2 * prog->len + 8;
+    pk.ctx_stride = (sre_pike_ctx_bytes(pk.len, pk.nslots, pk.max_threads, pk.stack_cap) + 255)
+                    & ~(uint64_t) 255;
+    return SRE_OK;
+}
+
+cudaStream_t as_stream(void *s) { return static_cast<cudaStream_t>(s); }
+
+/* pick the Thompson tier for a line batch */
+int thompson_dispatch(sre_cuda_program_t *cp, const uint8_t *dev_buf, const int64_t *dev_offsets,
+    size_t nlines, size_t pitch, size_t linelen, int32_t *dev_rc, int engine, cudaStream_t st)
+{
+    int launches = 0;
+    cudaError_t err;
+    const bool aligned = dev_offsets == nullptr && (reinterpret_cast<uintptr_t>(dev_buf) & 15) == 0
+                         && (pitch & 15) == 0 && linelen <= pitch && linelen < (1ull << 31);
+
+    if (engine == SRE_CUDA_ENGINE_AUTO) {
+        engine = cp->has_dfa ? (aligned ? SRE_CUDA_ENGINE_DFA_TILED : SRE_CUDA_ENGINE_DFA_GENERIC)
+                             : SRE_CUDA_ENGINE_NFA;
+    }
+    switch (engine) {
+    case SRE_CUDA_ENGINE_DFA_TILED:
+        if (!cp->has_dfa || !aligned) {
+            return fail("DFA_TILED engine needs a DFA and 16-byte aligned fixed-pitch lines");
+        }
+        err = sre_launch_dfa_lines(cp->dfa, dev_buf, nlines, pitch, linelen, dev_rc, g_variant, st,
+                                   &launches);
+        if (err == cudaErrorInvalidConfiguration) {
+            /* table too large for shared memory next to the staging rings */
+            err = sre_launch_dfa_ragged(cp->dfa, dev_buf, dev_offsets, nlines, pitch, linelen, dev_rc,
+                                        st, &launches);
+        }
+        break;
+    case SRE_CUDA_ENGINE_DFA_GENERIC:
+        if (!cp->has_dfa) {
+            return fail("no DFA for this program (subset construction exceeded %u states)",
+                        MAX_DFA_STATES);
+        }
+        err = sre_launch_dfa_ragged(cp->dfa, dev_buf, dev_offsets, nlines, pitch, linelen, dev_rc, st,
+                                    &launches);
+        break;
+    case SRE_CUDA_ENGINE_NFA:
+        if (!cp->has_nfa) {
+            return fail("program has more than %u lowered states", MAX_NFA_STATES);
+        }
+        err = sre_launch_nfa_lines(cp->nfa, dev_buf, dev_offsets, nlines, pitch, linelen, nullptr, 1, 1,
+                                   dev_rc, st, &launches);
+        break;
+    default:
+        return fail("unknown engine %d", engine);
+    }
+    count_launches(launches);
+    if (err != cudaSuccess) {
+        return fail("Thompson kernel launch failed: %s", cudaGetErrorString(err));
+    }
+    return SRE_OK;
+}
+
+int ensure_pike_scratch(sre_cuda_program_t *cp, size_t nlines)
+{
+    size_t want = nlines < 148 * 1024 ? nlines : 148 * 1024;
+    const size_t by_budget = PIKE_SCRATCH_BUDGET / cp->pike.ctx_stride;
+    if (want > by_budget) {
+        want = by_budget ? by_budget : 1;
+    }
+    if (want == 0) {
+        want = 1;
+    }
+    if (cp->pike_nctx >= want) {
+        return SRE_OK;
+    }
+    cudaFree(cp->pike_scratch);
+    cp->pike_scratch = nullptr;
+    cp->pike_nctx = 0;
+    CUDA_TRY(cudaMalloc(&cp->pike_scratch, want * cp->pike.ctx_stride));
+    cp->pike_nctx = want;
+    return SRE_OK;
+}
+
+/* size the levels of the stream scan and carve the workspace */
+int ensure_stream_ws(sre_cuda_program_t *cp, size_t len)
+{
+    const size_t piece = sre_stream_piece_bytes(), fan = sre_stream_fan();
+    const uint32_t fs = sre_stream_fn_stride(cp->dfa.nstates);
+    sre_stream_ws_t &ws = cp->ws;
+    size_t cnt = len / piece + ((len % piece) || len == 0 ? 1 : 0), total = 0;
+    int l = 0;
+    for (;; l++) {
+        ws.count[l] = cnt;
+        total += ((cnt * fs + 255) & ~(size_t) 255) + ((cnt + 255) & ~(size_t) 255);
+        if (cnt <= fan || l == 3) {
+            break;
+        }
+        cnt = (cnt + fan - 1) / fan;
+    }
+    if (ws.count[l] > fan) {
+        return fail("stream too long for the 4-level scan");
+    }
+    for (int k = l + 1; k < 4; k++) {
+        ws.count[k] = 0;
+    }
+    total += 256;
+    if (cp->stream_ws_bytes < total) {
+        cudaFree(cp->stream_ws);
+        cp->stream_ws = nullptr;
+        cp->stream_ws_bytes = 0;
+        CUDA_TRY(cudaMalloc(&cp->stream_ws, total));
+        cp->stream_ws_bytes = total;
+    }
+    uint8_t *p = cp->stream_ws;
+    for (int k = 0; k <= l; k++) {
+        ws.fn[k] = p;
+        p += (ws.count[k] * fs + 255) & ~(size_t) 255;
+        ws.entry[k] = p;
+        p += (ws.count[k] + 255) & ~(size_t) 255;
+    }
+    ws.first_acc = reinterpret_cast<unsigned long long *>(p);
+    if (cp->d_exit == nullptr) {
+        CUDA_TRY(cudaMalloc(&cp->d_exit, 64));
+    }
+    return SRE_OK;
+}
+
+bool stream_capable(const sre_cuda_program_t *cp)
+{
+    return cp->has_dfa && cp->dfa.t256 != nullptr && cp->dfa.nstates <= 32;
+}
+
+}  // namespace
+
+/* ======================================================================== *
+ * batch extension (include/sregex_cuda.h)
+ * ======================================================================== */
+
+extern "C" {
+
+SRE_API int sre_cuda_device_available(void) { return device_ok() ? 1 : 0; }
+SRE_API const char *sre_cuda_last_error(void) { return g_err; }
+SRE_API void sre_cuda_set_variant(int variant) { g_variant = variant; }
+
+SRE_API long sre_cuda_launch_count(int reset)
+{
+    return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+SRE_API sre_cuda_program_t *
+sre_cuda_program_create(sre_program_t *prog)
+{
+    if (prog == NULL || prog->magic != SRE_PROGRAM_MAGIC) {
+        fail("not a program compiled by this library");
+        return NULL;
+    }
+    if (prog->lowered) {
+        return static_cast<sre_cuda_program_t *>(prog->lowered);
+    }
+    if (!device_ok()) {
+        fail("no usable CUDA device (libsregex_cuda has no CPU fallback)");
+        return NULL;
+    }
+    sre_cuda_program_t *cp = new (std::nothrow) sre_cuda_program_t();
+    if (cp == NULL) {
+        return NULL;
+    }
+    cp->prog = prog;
+    if (sre_lower_program(prog, MAX_DFA_STATES, &cp->low) != SRE_OK || upload(cp) != SRE_OK) {
+        cp->prog = nullptr;
+        program_destroy(cp);
+        return NULL;
+    }
+    if (sre_pool_add_cleanup(prog->pool, program_destroy, cp) != SRE_OK) {
+        cp->prog = nullptr;
+        program_destroy(cp);
+        return NULL;
+    }
+    prog->lowered = cp;
+    return cp;
+}
+
+SRE_API int
+sre_cuda_program_info(sre_cuda_program_t *cp, sre_cuda_info_t *info)
+{
+    if (cp == NULL || info == NULL) {
+        return SRE_ERROR;
+    }
+    memset(info, 0, sizeof(*info));
+    info->prog_len = cp->prog->len;
+    info->nfa_states = cp->low.nfa.nstates;
+    info->nfa_classes = cp->low.nfa.nclasses;
+    info->nfa_kinds = cp->low.nfa.nkinds;
+    info->nfa_shift_states = cp->nfa_shift;
+    info->dfa_states = cp->has_dfa ? cp->low.dfa.nstates : 0;
+    info->dfa_classes = cp->has_dfa ? cp->low.dfa.nclasses : 0;
+    info->dfa_byte_table = cp->has_dfa && cp->dfa.t256 != nullptr;
+    info->nregexes = (uint32_t) cp->prog->nregexes;
+    info->pike_slots = cp->pike.nslots;
+    info->pike_ctx_bytes = cp->pike.ctx_stride;
+    return SRE_OK;
+}
+
+SRE_API int
+sre_cuda_thompson_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, size_t nlines,
+    size_t pitch, size_t linelen, int32_t *dev_rc, int engine, void *stream)
+{
+    if (cp == NULL) {
+        return fail("NULL program");
+    }
+    if (nlines == 0) {
+        return SRE_OK;
+    }
+    return thompson_dispatch(cp, dev_buf, nullptr, nlines, pitch, linelen, dev_rc, engine,
+                             as_stream(stream));
+}
+
+SRE_API int
+sre_cuda_thompson_exec_ragged(sre_cuda_program_t *cp, const uint8_t *dev_buf,
+    const int64_t *dev_offsets, size_t nlines, int32_t *dev_rc, int engine, void *stream)
+{
+    if (cp == NULL || dev_offsets == NULL) {
+        return fail("NULL program or offsets");
+    }
+    if (nlines == 0) {
+        return SRE_OK;
+    }
+    if (engine == SRE_CUDA_ENGINE_DFA_TILED) {
+        engine = SRE_CUDA_ENGINE_DFA_GENERIC;
+    }
+    return thompson_dispatch(cp, dev_buf, dev_offsets, nlines, 0, 0, dev_rc, engine, as_stream(stream));
+}
+
+SRE_API int
+sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const int64_t *dev_offsets,
+    size_t nlines, size_t pitch, size_t linelen, const int32_t *dev_select, int32_t *dev_rc,
+    int64_t *dev_ovec, size_t ovec_slots, void *stream)
+{
+    if (cp == NULL) {
+        return fail("NULL program");
+    }
+    if (nlines == 0) {
+        return SRE_OK;
+    }
+    if (ensure_pike_scratch(cp, nlines) != SRE_OK) {
+        return SRE_ERROR;
+    }
+    int launches = 0;
+    cudaError_t err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen,
+                                            dev_select, dev_rc, dev_ovec, (uint32_t) ovec_slots,
+                                            cp->pike_scratch, cp->pike_nctx < nlines ? cp->pike_nctx : nlines,
+                                            as_stream(stream), &launches);
+    count_launches(launches);
+    if (err != cudaSuccess) {
+        return fail("Pike kernel launch failed: %s", cudaGetErrorString(err));
+    }
+    return SRE_OK;
+}
+
+SRE_API int
+sre_cuda_thompson_stream_reduce(sre_cuda_program_t *cp, const uint8_t *dev_buf, size_t len,
+    uint8_t *host_fn, void *stream)
+{
+    if (cp == NULL || !stream_capable(cp)) {
+        return fail("stream scan needs a DFA with at most 32 states");
+    }
+    if (reinterpret_cast<uintptr_t>(dev_buf) & 15) {
+        return fail("stream buffer must be 16-byte aligned");
+    }
+    if (ensure_stream_ws(cp, len) != SRE_OK) {
+        return SRE_ERROR;
+    }
+    /* reduce on the device, then compose the (<= FAN) top-level functions on
+     * the host into one */
+    int launches = 0;
+    cudaStream_t st = as_stream(stream);
+    cudaError_t err = sre_launch_dfa_stream_reduce(cp->dfa, dev_buf, len, cp->ws, st, &launches);
+    count_launches(launches);
+    if (err != cudaSuccess) {
+        return fail("stream kernels failed: %s", cudaGetErrorString(err));
+    }
+    int top = 0;
+    while (top < 3 && cp->ws.count[top] > sre_stream_fan()) {
+        top++;
+    }
+    const uint32_t fs = sre_stream_fn_stride(cp->dfa.nstates), D = cp->dfa.nstates;
+    std::vector<uint8_t> fns(cp->ws.count[top] * fs);
+    CUDA_TRY(cudaMemcpyAsync(fns.data(), cp->ws.fn[top], fns.size(), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (uint32_t d = 0; d < D; d++) {
+        uint32_t s = d;
+        for (size_t j = 0; j < cp->ws.count[top]; j++) {
+            s = fns[j * fs + s];
+        }
+        host_fn[d] = (uint8_t) s;
+    }
+    cp->red_buf = dev_buf;
+    cp->red_len = len;
+    cp->red_top = top;
+    return SRE_OK;
+}
+
+/* after stream_reduce on the same buffer: redo the walk from the true entry */
+SRE_API int
+sre_cuda_thompson_stream_resolve(sre_cuda_program_t *cp, uint32_t entry_state, uint32_t *exit_state,
+    int64_t *first_match_offset, void *stream)
+{
+    if (cp == NULL || cp->red_buf == nullptr) {
+        return fail("stream_resolve without stream_reduce");
+    }
+    cudaStream_t st = as_stream(stream);
+    int launches = 0;
+    /* the function levels are still in the workspace; only the walks depend
+     * on the entry state */
+    cudaError_t err = sre_launch_dfa_stream_walk(cp->dfa, entry_state, cp->ws, cp->d_exit, st, &launches);
+    if (err == cudaSuccess) {
+        err = sre_launch_dfa_stream_locate(cp->dfa, cp->red_buf, cp->red_len, cp->ws,
+                                           reinterpret_cast<long long *>(cp->d_exit + 2), st, &launches);
+    }
+    count_launches(launches);
+    if (err != cudaSuccess) {
+        return fail("stream kernels failed: %s", cudaGetErrorString(err));
+    }
+    struct { uint32_t exit, pad; long long off; } h;
+    CUDA_TRY(cudaMemcpyAsync(&h, cp->d_exit, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *exit_state = h.exit;
+    if (first_match_offset) {
+        *first_match_offset = entry_state == cp->dfa.acc ? 0 : h.off;
+    }
+    return SRE_OK;
+}
+
+SRE_API int
+sre_cuda_thompson_exec_stream(sre_cuda_program_t *cp, const uint8_t *dev_buf, size_t len,
+    size_t chunk_bytes, unsigned eof, uint32_t *state_io, int64_t *match_chunk, void *stream)
+{
+    if (cp == NULL || state_io == NULL) {
+        return fail("NULL program or state");
+    }
+    if (!stream_capable(cp)) {
+        return fail("stream scan needs a DFA with at most 32 states (this program: %u)",
+                    cp->has_dfa ? cp->dfa.nstates : 0);
+    }
+    if (reinterpret_cast<uintptr_t>(dev_buf) & 15) {
+        return fail("stream buffer must be 16-byte aligned");
+    }
+    cudaStream_t st = as_stream(stream);
+    const uint32_t entry = *state_io == SRE_CUDA_STATE_INIT ? cp->dfa.start : *state_io;
+    if (entry >= cp->dfa.nstates) {
+        return fail("bad stream state");
+    }
+    if (ensure_stream_ws(cp, len) != SRE_OK) {
+        return SRE_ERROR;
+    }
+    int launches = 0;
+    cudaError_t err = sre_launch_dfa_stream_reduce(cp->dfa, dev_buf, len, cp->ws, st, &launches);
+    if (err == cudaSuccess) {
+        err = sre_launch_dfa_stream_walk(cp->dfa, entry, cp->ws, cp->d_exit, st, &launches);
+    }
+    if (err == cudaSuccess) {
+        err = sre_launch_dfa_stream_locate(cp->dfa, dev_buf, len, cp->ws,
+                                           reinterpret_cast<long long *>(cp->d_exit + 2), st, &launches);
+    }
+    count_launches(launches);
+    if (err != cudaSuccess) {
+        return fail("stream kernels failed: %s", cudaGetErrorString(err));
+    }
+    struct { uint32_t exit, pad; long long off; } h;
+    CUDA_TRY(cudaMemcpyAsync(&h, cp->d_exit, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *state_io = h.exit;
+
+    const size_t nchunks = chunk_bytes ? (len + chunk_bytes - 1) / chunk_bytes : 1;
+    if (h.exit == cp->dfa.acc) {
+        if (match_chunk) {
+            *match_chunk = (entry == cp->dfa.acc || h.off < 0 || !chunk_bytes)
+                               ? 0 : (int64_t) ((size_t) h.off / chunk_bytes);
+        }
+        return SRE_OK;
+    }
+    if (eof) {
+        if (cp->low.dfa.fin[h.exit]) {
+            if (match_chunk) {
+                *match_chunk = nchunks ? (int64_t) nchunks - 1 : 0;
+            }
+            return SRE_OK;
+        }
+        return SRE_DECLINED;
+    }
+    return SRE_AGAIN;
+}
+
+/* ---- host-buffer conveniences --------------------------------------------- */
+
+static int ensure_io(sre_cuda_program_t *cp, size_t bytes)
+{
+    if (cp->io_bytes >= bytes) {
+        return SRE_OK;
+    }
+    cudaFree(cp->io_buf);
+    cp->io_buf = nullptr;
+    cp->io_bytes = 0;
+    CUDA_TRY(cudaMalloc(&cp->io_buf, bytes));
+    cp->io_bytes = bytes;
+    return SRE_OK;
+}
+
+SRE_API int
+sre_cuda_thompson_exec_lines_host(sre_cuda_program_t *cp, const uint8_t *host_buf, size_t nlines,
+    size_t pitch, size_t linelen, int32_t *host_rc, int engine)
+{
+    if (cp == NULL) {
+        return fail("NULL program");
+    }
+    if (nlines == 0) {
+        return SRE_OK;
+    }
+    const size_t in_bytes = (nlines - 1) * pitch + linelen, in_pad = (in_bytes + 255) & ~(size_t) 255;
+    if (ensure_io(cp, in_pad + nlines * 4 + 256) != SRE_OK) {
+        return SRE_ERROR;
+    }
+    int32_t *d_rc = reinterpret_cast<int32_t *>(cp->io_buf + in_pad);
+    CUDA_TRY(cudaMemcpyAsync(cp->io_buf, host_buf, in_bytes, cudaMemcpyHostToDevice, 0));
+    if (thompson_dispatch(cp, cp->io_buf, nullptr, nlines, pitch, linelen, d_rc, engine, 0) != SRE_OK) {
+        return SRE_ERROR;
+    }
+    CUDA_TRY(cudaMemcpyAsync(host_rc, d_rc, nlines * 4, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return SRE_OK;
+}
+
+SRE_API int
+sre_cuda_pike_exec_lines_host(sre_cuda_program_t *cp, const uint8_t *host_buf, size_t nlines,
+    size_t pitch, size_t linelen, int gate_with_thompson, int32_t *host_rc, int64_t *host_ovec,
+    size_t ovec_slots)
+{
+    if (cp == NULL) {
+        return fail("NULL program");
+    }
+    if (nlines == 0) {
+        return SRE_OK;
+    }
+    const size_t in_bytes = (nlines - 1) * pitch + linelen, in_pad = (in_bytes + 255) & ~(size_t) 255;
+    const size_t rc_pad = (nlines * 4 + 255) & ~(size_t) 255;
+    if (ensure_io(cp, in_pad + 2 * rc_pad + nlines * ovec_slots * 8 + 256) != SRE_OK) {
+        return SRE_ERROR;
+    }
+    int32_t *d_sel = reinterpret_cast<int32_t *>(cp->io_buf + in_pad);
+    int32_t *d_rc = reinterpret_cast<int32_t *>(cp->io_buf + in_pad + rc_pad);
+    int64_t *d_ov = reinterpret_cast<int64_t *>(cp->io_buf + in_pad + 2 * rc_pad);
+    CUDA_TRY(cudaMemcpyAsync(cp->io_buf, host_buf, in_bytes, cudaMemcpyHostToDevice, 0));
+    if (gate_with_thompson
+        && thompson_dispatch(cp, cp->io_buf, nullptr, nlines, pitch, linelen, d_sel,
+                             SRE_CUDA_ENGINE_AUTO, 0) != SRE_OK)
+    {
+        return SRE_ERROR;
+    }
+    if (sre_cuda_pike_exec_lines(cp, cp->io_buf, nullptr, nlines, pitch, linelen,
+                                 gate_with_thompson ? d_sel : nullptr, d_rc, d_ov, ovec_slots, 0) != SRE_OK)
+    {
+        return SRE_ERROR;
+    }
+    CUDA_TRY(cudaMemcpyAsync(host_rc, d_rc, nlines * 4, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaMemcpyAsync(host_ovec, d_ov, nlines * ovec_slots * 8, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return SRE_OK;
+}
+
+}  /* extern "C" */
+
+/* ======================================================================== *
+ * the reference's executor API (include/sregex/sregex.h)
+ * ======================================================================== */
+
+struct sre_vm_thompson_ctx_s {
+    sre_cuda_program_t  *cp;
+    uint8_t             *d_mem;         /* state (WP words) | rc | input       */
+    size_t               d_cap;         /* input capacity                      */
+    uint32_t             state_words;
+    bool                 started;
+};
+
+struct sre_vm_pike_ctx_s {
+    sre_cuda_program_t  *cp;
+    sre_int_t           *ovector;
+    size_t               ovec_slots;
+    uint8_t             *d_ctx;         /* persistent Pike context             */
+    int64_t             *d_out;
+    uint8_t             *d_in;
+    size_t               d_in_cap;
+    std::vector<int64_t> *h_out;
+    sre_int_t            pending[2];
+};
+
+struct sre_vm_thompson_code_s {
+    sre_cuda_program_t  *cp;
+};
+
+namespace {
+
+void thompson_ctx_cleanup(void *data)
+{
+    sre_vm_thompson_ctx_t *ctx = static_cast<sre_vm_thompson_ctx_t *>(data);
+    cudaFree(ctx->d_mem);
+    ctx->d_mem = nullptr;
+}
+
+void pike_ctx_cleanup(void *data)
+{
+    sre_vm_pike_ctx_t *ctx = static_cast<sre_vm_pike_ctx_t *>(data);
+    cudaFree(ctx->d_ctx);
+    cudaFree(ctx->d_out);
+    cudaFree(ctx->d_in);
+    delete ctx->h_out;
+    ctx->d_ctx = nullptr;
+    ctx->d_out = nullptr;
+    ctx->d_in = nullptr;
+    ctx->h_out = nullptr;
+}
+
+const size_t THOMPSON_HDR = 4096 * 4 + 256;     /* state words + rc */
+
+int thompson_reserve(sre_vm_thompson_ctx_t *ctx, size_t len)
+{
+    if (ctx->d_mem && ctx->d_cap >= len) {
+        return SRE_OK;
+    }
+    uint8_t *fresh = nullptr;
+    const size_t cap = len < 4096 ? 4096 : (len + 255) & ~(size_t) 255;
+    CUDA_TRY(cudaMalloc(&fresh, THOMPSON_HDR + cap));
+    if (ctx->d_mem) {
+        cudaMemcpy(fresh, ctx->d_mem, THOMPSON_HDR, cudaMemcpyDeviceToDevice);
+        cudaFree(ctx->d_mem);
+    }
+    ctx->d_mem = fresh;
+    ctx->d_cap = cap;
+    return SRE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+/* reference: sre_vm_thompson_create_ctx, sre_vm_thompson.c:25-60 */
+SRE_API sre_vm_thompson_ctx_t *
+sre_vm_thompson_create_ctx(sre_pool_t *pool, sre_program_t *prog)
+{
+    sre_cuda_program_t *cp = sre_cuda_program_create(prog);
+    if (cp == NULL) {
+        return NULL;
+    }
+    if (!cp->has_dfa && !cp->has_nfa) {
+        fail("program too large for the GPU Thompson tiers");
+        return NULL;
+    }
+    sre_vm_thompson_ctx_t *ctx = static_cast<sre_vm_thompson_ctx_t *>(sre_pcalloc(pool, sizeof(*ctx)));
+    if (ctx == NULL) {
+        return NULL;
+    }
+    ctx->cp = cp;
+    ctx->started = false;
+    if (thompson_reserve(ctx, 4096) != SRE_OK
+        || sre_pool_add_cleanup(pool, thompson_ctx_cleanup, ctx) != SRE_OK)
+    {
+        cudaFree(ctx->d_mem);
+        return NULL;
+    }
+    return ctx;
+}
+
+/*
+ * reference: sre_vm_thompson_exec, sre_vm_thompson.c:63-270.  Same contract:
+ * SRE_OK as soon as a step of this call sees a live MATCH thread, SRE_AGAIN
+ * when !eof, SRE_DECLINED at eof; state is carried on the device between calls.
+ */
+SRE_API sre_int_t
+sre_vm_thompson_exec(sre_vm_thompson_ctx_t *ctx, sre_char *input, size_t size, unsigned eof)
+{
+    if (ctx == NULL || ctx->cp == NULL) {
+        return SRE_ERROR;
+    }
+    sre_cuda_program_t *cp = ctx->cp;
+    if (thompson_reserve(ctx, size) != SRE_OK) {
+        return SRE_ERROR;
+    }
+    uint32_t *d_state = reinterpret_cast<uint32_t *>(ctx->d_mem);
+    int32_t *d_rc = reinterpret_cast<int32_t *>(ctx->d_mem + 4096 * 4);
+    uint8_t *d_in = ctx->d_mem + THOMPSON_HDR;
+    if (size) {
+        CUDA_TRY(cudaMemcpyAsync(d_in, input, size, cudaMemcpyHostToDevice, 0));
+    }
+
+    /* long buffers over a small DFA: the chunk-parallel scan */
+    if (stream_capable(cp) && size >= (1u << 16)) {
+        uint32_t st = SRE_CUDA_STATE_INIT;
+        if (ctx->started) {
+            CUDA_TRY(cudaMemcpy(&st, d_state, 4, cudaMemcpyDeviceToHost));
+        }
+        const int rc = sre_cuda_thompson_exec_stream(cp, d_in, size, size, eof, &st, NULL, 0);
+        if (rc == SRE_ERROR) {
+            return SRE_ERROR;
+        }
+        CUDA_TRY(cudaMemcpy(d_state, &st, 4, cudaMemcpyHostToDevice));
+        ctx->started = true;
+        return rc;
+    }
+
+    int launches = 0;
+    cudaError_t err;
+    if (cp->has_dfa) {
+        err = sre_launch_dfa_carry(cp->dfa, d_in, nullptr, 1, 0, size, d_state, !ctx->started, eof != 0,
+                                   d_rc, 0, &launches);
+    } else {
+        err = sre_launch_nfa_lines(cp->nfa, d_in, nullptr, 1, 0, size, d_state, !ctx->started, eof != 0,
+                                   d_rc, 0, &launches);
+    }
+    count_launches(launches);
+    if (err != cudaSuccess) {
+        return fail("Thompson kernel launch failed: %s", cudaGetErrorString(err));
+    }
+    ctx->started = true;
+    int32_t rc = SRE_ERROR;
+    CUDA_TRY(cudaMemcpy(&rc, d_rc, 4, cudaMemcpyDeviceToHost));
+    return rc;
+}
+
+/* reference: sre_vm_thompson_jit_compile, sre_vm_thompson_jit.c:39-155.  Here:
+ * lowering + determinisation + upload (done once, cached in the program). */
+SRE_API sre_int_t
+sre_vm_thompson_jit_compile(sre_pool_t *pool, sre_program_t *prog, sre_vm_thompson_code_t **pcode)
+{
+    *pcode = NULL;
+    if (!device_ok()) {
+        return SRE_DECLINED;    /* like the reference on a non-x86-64 target */
+    }
+    sre_cuda_program_t *cp = sre_cuda_program_create(prog);
+    if (cp == NULL) {
+        return SRE_ERROR;
+    }
+    sre_vm_thompson_code_t *code = static_cast<sre_vm_thompson_code_t *>(sre_pcalloc(pool, sizeof(*code)));
+    if (code == NULL) {
+        return SRE_ERROR;
+    }
+    code->cp = cp;
+    *pcode = code;
+    return SRE_OK;
+}
+
+SRE_API sre_vm_thompson_ctx_t *
+sre_vm_thompson_jit_create_ctx(sre_pool_t *pool, sre_program_t *prog)
+{
+    return sre_vm_thompson_create_ctx(pool, prog);
+}
+
+SRE_API sre_vm_thompson_exec_pt
+sre_vm_thompson_jit_get_handler(sre_vm_thompson_code_t *code)
+{
+    (void) code;
+    return sre_vm_thompson_exec;
+}
+
+SRE_API sre_int_t
+sre_vm_thompson_jit_free(sre_vm_thompson_code_t *code)
+{
+    (void) code;        /* tables belong to the program's pool */
+    return SRE_OK;
+}
+
+/* reference: sre_vm_pike_create_ctx, sre_vm_pike.c:94-145 */
+SRE_API sre_vm_pike_ctx_t *
+sre_vm_pike_create_ctx(sre_pool_t *pool, sre_program_t *prog, sre_int_t *ovector, size_t ovecsize)
+{
+    sre_cuda_program_t *cp = sre_cuda_program_create(prog);
+    if (cp == NULL) {
+        return NULL;
+    }
+    sre_vm_pike_ctx_t *ctx = static_cast<sre_vm_pike_ctx_t *>(sre_pcalloc(pool, sizeof(*ctx)));
+    if (ctx == NULL) {
+        return NULL;
+    }
+    ctx->cp = cp;
+    ctx->ovector = ovector;
+    ctx->ovec_slots = ovecsize / sizeof(sre_int_t);
+    ctx->h_out = new (std::nothrow) std::vector<int64_t>(4 + ctx->ovec_slots + 2, -1);
+    ctx->d_in_cap = 4096;
+    int launches = 0;
+    if (ctx->h_out == NULL
+        || cudaMalloc(&ctx->d_ctx, cp->pike.ctx_stride) != cudaSuccess
+        || cudaMalloc(&ctx->d_out, (4 + ctx->ovec_slots + 2) * 8) != cudaSuccess
+        || cudaMalloc(&ctx->d_in, ctx->d_in_cap) != cudaSuccess
+        || sre_launch_pike_ctx_init(cp->pike, ctx->d_ctx, 0, &launches) != cudaSuccess
+        || sre_pool_add_cleanup(pool, pike_ctx_cleanup, ctx) != SRE_OK)
+    {
+        fail("creating the Pike context failed: %s", cudaGetErrorString(cudaGetLastError()));
+        pike_ctx_cleanup(ctx);
+        return NULL;
+    }
+    count_launches(launches);
+    return ctx;
+}
+
+/* reference: sre_vm_pike_exec, sre_vm_pike.c:148-689 */
+SRE_API sre_int_t
+sre_vm_pike_exec(sre_vm_pike_ctx_t *ctx, sre_char *input, size_t size, unsigned eof,
+    sre_int_t **pending_matched)
+{
+    if (ctx == NULL || ctx->cp == NULL || ctx->d_ctx == NULL) {
+        return SRE_ERROR;
+    }
+    if (size > ctx->d_in_cap) {
+        cudaFree(ctx->d_in);
+        ctx->d_in = nullptr;
+        ctx->d_in_cap = (size + 4095) & ~(size_t) 4095;
+        CUDA_TRY(cudaMalloc(&ctx->d_in, ctx->d_in_cap));
+    }
+    if (size) {
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_in, input, size, cudaMemcpyHostToDevice, 0));
+    }
+    int launches = 0;
+    cudaError_t err = sre_launch_pike_stream(ctx->cp->pike, ctx->d_ctx, ctx->d_in, size, eof != 0,
+                                             pending_matched != NULL, ctx->d_out,
+                                             (uint32_t) ctx->ovec_slots, 0, &launches);
+    count_launches(launches);
+    if (err != cudaSuccess) {
+        return fail("Pike kernel launch failed: %s", cudaGetErrorString(err));
+    }
+    std::vector<int64_t> &out = *ctx->h_out;
+    CUDA_TRY(cudaMemcpy(out.data(), ctx->d_out, (4 + ctx->ovec_slots) * 8, cudaMemcpyDeviceToHost));
+
+    const sre_int_t rc = (sre_int_t) out[0];
+    if (rc >= 0) {
+        for (size_t i = 0; i < ctx->ovec_slots; i++) {
+            ctx->ovector[i] = (sre_int_t) out[4 + i];
+        }
+    } else if (rc == SRE_AGAIN) {
+        /* temp captures: only $& is reported (sre_vm_pike.c:692-735) */
+        if (ctx->ovec_slots > 0) ctx->ovector[0] = (sre_int_t) out[4];
+        if (ctx->ovec_slots > 1) ctx->ovector[1] = (sre_int_t) out[5];
+        if (pending_matched) {
+            if (out[1]) {
+                ctx->pending[0] = (sre_int_t) out[2];
+                ctx->pending[1] = (sre_int_t) out[3];
+                *pending_matched = ctx->pending;
+            } else {
+                *pending_matched = NULL;
+            }
+        }
+    }
+    return rc;
+}
+
+}  /* extern "C" */

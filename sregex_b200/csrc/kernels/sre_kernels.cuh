@@ -1,0 +1,125 @@
+/*
+ * sre_kernels.cuh -- device-side table layouts and kernel launch prototypes
+ * of libsregex_cuda (sm_100a).  See DESIGN.md section 4 for each kernel's
+ * bound and algorithmic bytes.
+ */
+#ifndef SRE_KERNELS_CUH
+#define SRE_KERNELS_CUH
+
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+/* status codes as seen by kernels (== include/sregex/sregex.h) */
+#define SRE_K_OK        0
+#define SRE_K_ERROR    (-1)
+#define SRE_K_AGAIN    (-2)
+#define SRE_K_DECLINED (-5)
+
+/* ---- DFA tier ------------------------------------------------------------ */
+struct sre_dev_dfa_t {
+    uint32_t         nstates, nclasses, start, acc;
+    const uint8_t   *t256;      /* [nstates][256] next state (u8), or NULL    */
+    const uint16_t  *tcls;      /* [nstates][nclasses] next state * nclasses  */
+    const uint8_t   *clsmap;    /* [256]                                      */
+    const uint8_t   *fin;       /* [nstates]                                  */
+};
+
+/* ---- NFA tier ------------------------------------------------------------ */
+struct sre_dev_nfa_t {
+    uint32_t         nstates, nwords, nclasses, nkinds;
+    const uint8_t   *clsmap;    /* [256]                                      */
+    const uint8_t   *cls_kind;  /* [nclasses]                                 */
+    const uint32_t  *mv;        /* [nclasses][nwords]                         */
+    const uint32_t  *mt;        /* [nclasses][nwords]                         */
+    const uint32_t  *mt_eof;    /* [nwords]                                   */
+    const uint32_t  *init;      /* [nwords]                                   */
+    const uint32_t  *shift_mask;/* [nwords]                                   */
+    const uint32_t  *follow;    /* [nkinds][nrows][nwords], complex rows only */
+    const int32_t   *rowidx;    /* [nstates] -> row or -1                     */
+    uint32_t         nrows;
+};
+
+/* ---- Pike tier (runs the bytecode itself) -------------------------------- */
+struct sre_dev_inst_t {         /* == host sre_instruction_t, 16 bytes        */
+    uint8_t   opcode, ch;
+    uint16_t  nranges;
+    int32_t   x, y, v;
+};
+
+struct sre_dev_pike_t {
+    uint32_t                 len;           /* instructions                   */
+    uint32_t                 nslots;        /* capture slots, all regexes     */
+    uint32_t                 nregexes;
+    uint32_t                 nleading;
+    int32_t                  leading_byte;
+    const sre_dev_inst_t    *insts;
+    const uint8_t           *ranges;        /* (from,to) pairs                */
+    const int32_t           *leading;       /* pcs of leading instructions    */
+    const uint32_t          *slot_ofs;      /* [nregexes+1] first slot        */
+    uint32_t                 max_threads;   /* thread pool entries per ctx    */
+    uint32_t                 stack_cap;     /* DFS stack entries per ctx      */
+    uint64_t                 ctx_stride;    /* bytes of scratch per ctx       */
+};
+
+/* launchers (sre_kernels.cu); all asynchronous on `stream` ------------------ */
+
+/* line i = buf[i*pitch, i*pitch+linelen); needs buf%16==0 && pitch%16==0     */
+cudaError_t sre_launch_dfa_lines(const sre_dev_dfa_t &dfa, const uint8_t *buf,
+    size_t nlines, size_t pitch, size_t linelen, int32_t *rc, int variant,
+    cudaStream_t stream, int *launches);
+
+/* ragged / unaligned lines: line i = buf[off[i], off[i+1]) or fixed pitch    */
+cudaError_t sre_launch_dfa_ragged(const sre_dev_dfa_t &dfa, const uint8_t *buf,
+    const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen,
+    int32_t *rc, cudaStream_t stream, int *launches);
+
+/*
+ * Bit-parallel NFA, one warp per line.  state_io (nlines*nwords u32, may be
+ * NULL) carries the thread set across calls when from_init == 0 / for
+ * SRE_AGAIN; rc is SRE_OK / SRE_DECLINED (eof) / SRE_AGAIN (!eof).
+ */
+cudaError_t sre_launch_nfa_lines(const sre_dev_nfa_t &nfa, const uint8_t *buf,
+    const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen,
+    uint32_t *state_io, int from_init, int eof, int32_t *rc,
+    cudaStream_t stream, int *launches);
+
+/* serial DFA with state carry (one thread per line; the classic exec path)   */
+cudaError_t sre_launch_dfa_carry(const sre_dev_dfa_t &dfa, const uint8_t *buf,
+    const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen,
+    uint32_t *state_io, int from_init, int eof, int32_t *rc,
+    cudaStream_t stream, int *launches);
+
+/* Pike VM over lines; select may be NULL (all) or an rc array (run where ==0) */
+size_t sre_pike_concurrency(size_t nlines);
+cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
+    const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen,
+    const int32_t *select, int32_t *rc, int64_t *ovec, uint32_t ovec_slots,
+    uint8_t *scratch, size_t nctx, cudaStream_t stream, int *launches);
+
+/* Pike VM streaming step on one persistent context (classic API)             */
+cudaError_t sre_launch_pike_stream(const sre_dev_pike_t &pk, uint8_t *ctx,
+    const uint8_t *buf, size_t len, int eof, int want_pending, int64_t *out,
+    uint32_t ovec_slots, cudaStream_t stream, int *launches);
+cudaError_t sre_launch_pike_ctx_init(const sre_dev_pike_t &pk, uint8_t *ctx,
+    cudaStream_t stream, int *launches);
+
+/* chunk-parallel DFA stream scan (nstates <= 64) ---------------------------- */
+struct sre_stream_ws_t {        /* workspace owned by the caller              */
+    uint8_t  *fn[4];            /* transfer functions per level               */
+    size_t    count[4];
+    uint8_t  *entry[4];         /* entry state per element per level          */
+    unsigned long long *first_acc;  /* first piece whose exit is ACC          */
+};
+size_t sre_stream_piece_bytes(void);
+cudaError_t sre_launch_dfa_stream_reduce(const sre_dev_dfa_t &dfa, const uint8_t *buf,
+    size_t len, const sre_stream_ws_t &ws, cudaStream_t stream, int *launches);
+cudaError_t sre_launch_dfa_stream_walk(const sre_dev_dfa_t &dfa, uint32_t entry_state,
+    const sre_stream_ws_t &ws, uint32_t *exit_state, cudaStream_t stream, int *launches);
+cudaError_t sre_launch_dfa_stream_locate(const sre_dev_dfa_t &dfa, const uint8_t *buf,
+    size_t len, const sre_stream_ws_t &ws, long long *dev_match_offset,
+    cudaStream_t stream, int *launches);
+uint32_t sre_stream_fan(void);
+uint32_t sre_stream_fn_stride(uint32_t nstates);
+size_t sre_pike_ctx_bytes(uint32_t len, uint32_t nslots, uint32_t nthreads, uint32_t stack_cap);
+
+#endif

@@ -1,0 +1,734 @@
+/*
+ * sre_pike.cu -- Pike VM (leftmost-first match, sub-match captures, matched
+ * regex id) for sm_100a: one CUDA thread runs one context.
+ *
+ * What it replaces: sre_vm_pike_exec and helpers (reference sre_vm_pike.c:
+ * exec :148-689, add_thread :756-942, prepare_matched_captures :945-989,
+ * prepare_temp_captures :692-735, find_first_byte :992-1061) and the
+ * copy-on-write capture vectors of sre_capture.c.
+ *
+ * The Perl-priority result of the reference is a property of the exact order
+ * in which it walks its thread lists (DFS pre-order of the closure, the
+ * revisited-SPLIT rule :770-786, "cut lower priority on match" :535-553,
+ * look-ahead closures prepended with the current list's tag :506-525), so the
+ * kernel keeps that sequential algorithm per context and is parallel across
+ * contexts (= lines).  Differences in mechanism only:
+ *   - the program is the read-only flat bytecode; dedup tags live in the
+ *     context (tag counters simply keep growing across lines, so no clearing);
+ *   - add_thread's recursion is an explicit DFS stack with an undo log for the
+ *     SAVE slots, which gives each branch of a SPLIT the captures the reference
+ *     gives it through copy-on-write;
+ *   - every list thread owns a private copy of its capture slots.
+ * All context state lives in one block of global memory, so the same routine
+ * serves the batch entry points (context re-initialised per line) and the
+ * streaming sre_vm_pike_exec (context persists between calls).
+ */
+#include "sre_kernels.cuh"
+
+namespace {
+
+enum {
+    OP_CHAR = 1, OP_MATCH = 2, OP_JMP = 3, OP_SPLIT = 4, OP_ANY = 5, OP_SAVE = 6,
+    OP_IN = 7, OP_NOTIN = 8, OP_ASSERT = 9
+};
+enum { AS_SMALL_Z = 0x01, AS_DOLLAR = 0x02, AS_BIG_B = 0x04, AS_SMALL_B = 0x08,
+       AS_BIG_A = 0x10, AS_CARET = 0x20 };
+
+constexpr int RC_DONE = -4;
+
+struct pike_hdr_t {
+    uint32_t  tag, prog_tag;
+    int64_t   processed_bytes;
+    int32_t   head[2], tail[2], count[2];   /* two thread lists              */
+    int32_t   cur;                          /* which one is clist            */
+    int32_t   free_head, pool_used;
+    int32_t   has_matched, matched_id;
+    int32_t   initial_count;
+    int64_t   last_matched_pos;
+    int64_t   pending[2];
+    uint8_t   first_buf, seen_start_state, eof, empty_capture, seen_newline, seen_word,
+              error, pad;
+};
+
+struct stack_ent_t {
+    int32_t  kind;      /* -1: visit pc; >= 0: restore slot `kind`           */
+    int32_t  pc;
+    int64_t  val;
+};
+
+__host__ __device__ inline size_t a16(size_t v) { return (v + 15) & ~(size_t) 15; }
+
+/* carve the context block */
+struct pike_ctx_t {
+    pike_hdr_t   *h;
+    uint32_t     *tags;
+    int32_t      *initial;
+    int64_t      *matched;
+    int64_t      *cap;          /* working capture of add_thread             */
+    int32_t      *t_pc, *t_next;
+    uint8_t      *t_sw;
+    int64_t      *t_cap;
+    stack_ent_t  *stk;
+};
+
+__host__ __device__ inline size_t pike_ctx_bytes(uint32_t len, uint32_t nslots, uint32_t nthreads,
+                                                 uint32_t stack_cap)
+{
+    size_t n = a16(sizeof(pike_hdr_t));
+    n += a16((size_t) (len + 1) * 4);       /* tags      */
+    n += a16((size_t) (len + 1) * 4);       /* initial   */
+    n += a16((size_t) nslots * 8) * 2;      /* matched, cap */
+    n += a16((size_t) nthreads * 4) * 2;    /* t_pc, t_next */
+    n += a16(nthreads);                     /* t_sw      */
+    n += a16((size_t) nthreads * nslots * 8);
+    n += a16((size_t) stack_cap * sizeof(stack_ent_t));
+    return n;
+}
+
+__device__ inline pike_ctx_t pike_carve(const sre_dev_pike_t &pk, uint8_t *base)
+{
+    pike_ctx_t c;
+    uint8_t *p = base;
+    c.h = reinterpret_cast<pike_hdr_t *>(p);        p += a16(sizeof(pike_hdr_t));
+    c.tags = reinterpret_cast<uint32_t *>(p);       p += a16((size_t) (pk.len + 1) * 4);
+    c.initial = reinterpret_cast<int32_t *>(p);     p += a16((size_t) (pk.len + 1) * 4);
+    c.matched = reinterpret_cast<int64_t *>(p);     p += a16((size_t) pk.nslots * 8);
+    c.cap = reinterpret_cast<int64_t *>(p);         p += a16((size_t) pk.nslots * 8);
+    c.t_pc = reinterpret_cast<int32_t *>(p);        p += a16((size_t) pk.max_threads * 4);
+    c.t_next = reinterpret_cast<int32_t *>(p);      p += a16((size_t) pk.max_threads * 4);
+    c.t_sw = p;                                     p += a16(pk.max_threads);
+    c.t_cap = reinterpret_cast<int64_t *>(p);       p += a16((size_t) pk.max_threads * pk.nslots * 8);
+    c.stk = reinterpret_cast<stack_ent_t *>(p);
+    return c;
+}
+
+__device__ inline bool isword(uint32_t c)
+{
+    return (c - '0' < 10u) || ((c | 0x20) - 'a' < 26u) || c == '_';
+}
+
+__device__ inline bool in_ranges(const sre_dev_pike_t &pk, const sre_dev_inst_t &in, uint32_t b)
+{
+    const uint8_t *r = pk.ranges + 2 * (size_t) in.v;
+    for (uint32_t j = 0; j < in.nranges; j++) {
+        if (b >= r[2 * j] && b <= r[2 * j + 1]) {
+            return true;
+        }
+    }
+    return false;
+}
+
+__device__ inline bool consumes(const sre_dev_pike_t &pk, const sre_dev_inst_t &in, uint32_t b)
+{
+    switch (in.opcode) {
+    case OP_CHAR:  return in.ch == b;
+    case OP_ANY:   return true;
+    case OP_IN:    return in_ranges(pk, in, b);
+    case OP_NOTIN: return !in_ranges(pk, in, b);
+    default:       return false;
+    }
+}
+
+/* fresh context for a new stream / line; tags are NOT cleared (see header) */
+__device__ inline void pike_reset(pike_ctx_t &c, bool first_time)
+{
+    pike_hdr_t *h = c.h;
+    if (first_time) {
+        h->tag = 0;
+        h->prog_tag = 0;
+    }
+    h->processed_bytes = 0;
+    h->head[0] = h->head[1] = -1;
+    h->tail[0] = h->tail[1] = -1;
+    h->count[0] = h->count[1] = 0;
+    h->cur = 0;
+    h->free_head = -1;
+    h->pool_used = 0;
+    h->has_matched = 0;
+    h->matched_id = 0;
+    h->initial_count = 0;
+    h->last_matched_pos = -1;
+    h->first_buf = 1;
+    h->seen_start_state = 0;
+    h->eof = 0;
+    h->empty_capture = 0;
+    h->seen_newline = 0;
+    h->seen_word = 0;
+    h->error = 0;
+}
+
+__device__ inline void list_clear(pike_ctx_t &c, int l)
+{
+    pike_hdr_t *h = c.h;
+    if (h->head[l] >= 0) {
+        c.t_next[h->tail[l]] = h->free_head;
+        h->free_head = h->head[l];
+    }
+    h->head[l] = h->tail[l] = -1;
+    h->count[l] = 0;
+}
+
+/* a temporary list used by assertion_hold */
+struct tmp_list_t { int32_t head, tail, count; };
+
+/*
+ * add_thread (sre_vm_pike.c:756-942).  Appends to list `l` (0/1) or, when
+ * l < 0, to *tmp.  c.cap holds the capture of the calling thread and is
+ * restored to that value on return.  Returns SRE_K_OK, RC_DONE or SRE_K_ERROR.
+ */
+__device__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, tmp_list_t *tmp,
+    int32_t pc0, int64_t pos, const uint8_t *buffer, bool want_done)
+{
+    pike_hdr_t *h = c.h;
+    const uint32_t tag = h->tag;
+    int sp = 0;
+    c.stk[sp].kind = -1;
+    c.stk[sp].pc = pc0;
+    sp++;
+
+    while (sp > 0) {
+        sp--;
+        if (c.stk[sp].kind >= 0) {
+            c.cap[c.stk[sp].kind] = c.stk[sp].val;
+            continue;
+        }
+        int32_t pc = c.stk[sp].pc;
+
+        for (;;) {
+            const sre_dev_inst_t in = pk.insts[pc];
+            uint32_t seen_word = 0;
+            bool add = false;
+
+            if (c.tags[pc] == tag) {
+                /* the revisited-SPLIT rule, :770-786 */
+                if (in.opcode == OP_SPLIT && c.tags[in.y] != tag) {
+                    if (pc == 0) {
+                        h->seen_start_state = 1;
+                    }
+                    pc = in.y;
+                    continue;
+                }
+                break;
+            }
+            c.tags[pc] = tag;
+
+            switch (in.opcode) {
+            case OP_JMP:
+                pc = in.x;
+                continue;
+
+            case OP_SPLIT:
+                if (pc == 0) {
+                    h->seen_start_state = 1;
+                }
+                if (sp >= (int) pk.stack_cap) {
+                    return SRE_K_ERROR;
+                }
+                c.stk[sp].kind = -1;
+                c.stk[sp].pc = in.y;
+                sp++;
+                pc = in.x;
+                continue;
+
+            case OP_SAVE:
+                if (sp >= (int) pk.stack_cap) {
+                    return SRE_K_ERROR;
+                }
+                c.stk[sp].kind = in.v;
+                c.stk[sp].val = c.cap[in.v];
+                sp++;
+                c.cap[in.v] = h->processed_bytes + pos;
+                pc++;
+                continue;
+
+            case OP_ASSERT:
+                switch (in.v) {
+                case AS_BIG_A:
+                    if (pos || h->processed_bytes) {
+                        break;
+                    }
+                    pc++;
+                    continue;
+                case AS_CARET:
+                    if (pos == 0) {
+                        if (h->processed_bytes && !h->seen_newline) {
+                            break;
+                        }
+                    } else if (buffer[pos - 1] != '\n') {
+                        break;
+                    }
+                    pc++;
+                    continue;
+                case AS_SMALL_B:
+                case AS_BIG_B:
+                    seen_word = pos == 0 ? 0 : isword(buffer[pos - 1]);
+                    add = true;
+                    break;
+                default:            /* look-ahead: postponed */
+                    add = true;
+                    break;
+                }
+                break;
+
+            case OP_MATCH:
+                h->last_matched_pos = c.cap[1];
+                if (want_done) {
+                    for (uint32_t i = 0; i < pk.nslots; i++) {
+                        c.matched[i] = c.cap[i];
+                    }
+                    h->matched_id = in.v;
+                    /* unwind the undo log so c.cap is the caller's again */
+                    while (sp > 0) {
+                        sp--;
+                        if (c.stk[sp].kind >= 0) {
+                            c.cap[c.stk[sp].kind] = c.stk[sp].val;
+                        }
+                    }
+                    return RC_DONE;
+                }
+                add = true;
+                break;
+
+            default:
+                add = true;
+                break;
+            }
+
+            if (add) {
+                int32_t t;
+                if (h->free_head >= 0) {
+                    t = h->free_head;
+                    h->free_head = c.t_next[t];
+                } else if (h->pool_used < (int32_t) pk.max_threads) {
+                    t = h->pool_used++;
+                } else {
+                    return SRE_K_ERROR;
+                }
+                c.t_pc[t] = pc;
+                c.t_sw[t] = (uint8_t) seen_word;
+                c.t_next[t] = -1;
+                int64_t *dst = c.t_cap + (size_t) t * pk.nslots;
+                for (uint32_t i = 0; i < pk.nslots; i++) {
+                    dst[i] = c.cap[i];
+                }
+                if (l >= 0) {
+                    if (h->head[l] < 0) {
+                        h->head[l] = t;
+                    } else {
+                        c.t_next[h->tail[l]] = t;
+                    }
+                    h->tail[l] = t;
+                    h->count[l]++;
+                } else {
+                    if (tmp->head < 0) {
+                        tmp->head = t;
+                    } else {
+                        c.t_next[tmp->tail] = t;
+                    }
+                    tmp->tail = t;
+                    tmp->count++;
+                }
+            }
+            break;
+        }
+    }
+    return SRE_K_OK;
+}
+
+__device__ inline int64_t find_first_byte(const sre_dev_pike_t &pk, const uint8_t *buf, int64_t pos,
+    int64_t last)
+{
+    if (pk.leading_byte != -1) {
+        const uint32_t lb = (uint32_t) pk.leading_byte;
+        while (pos < last && buf[pos] != lb) {
+            pos++;
+        }
+        return pos;
+    }
+    for (; pos != last; pos++) {
+        const uint32_t b = buf[pos];
+        for (uint32_t i = 0; i < pk.nleading; i++) {
+            if (consumes(pk, pk.insts[pk.leading[i]], b)) {
+                return pos;
+            }
+        }
+    }
+    return pos;
+}
+
+/* prepare_matched_captures, :945-989.  complete: whole slice + -1 fill */
+__device__ inline int prepare_matched(const sre_dev_pike_t &pk, pike_ctx_t &c, int64_t *ovector,
+    uint32_t ovec_slots, bool complete)
+{
+    const int32_t id = c.h->matched_id;
+    if (id < 0 || (uint32_t) id >= pk.nregexes) {
+        return SRE_K_ERROR;
+    }
+    const uint32_t ofs = pk.slot_ofs[id];
+    const uint32_t n = complete ? pk.slot_ofs[id + 1] - ofs : 2;
+    for (uint32_t i = 0; i < n && i < ovec_slots; i++) {
+        ovector[i] = c.matched[ofs + i];
+    }
+    if (complete) {
+        for (uint32_t i = n; i < ovec_slots; i++) {
+            ovector[i] = -1;
+        }
+    }
+    return SRE_K_OK;
+}
+
+/*
+ * One sre_vm_pike_exec call (:148-689).  ovector: caller's vector
+ * (ovec_slots entries).  *pending_set: 1 when h->pending holds a pending match.
+ */
+__device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t *input, int64_t size,
+    bool eof, int64_t *ovector, uint32_t ovec_slots, int *pending_set)
+{
+    pike_hdr_t *h = c.h;
+    int64_t sp, last = size;
+    int rc;
+
+    *pending_set = 0;
+    if (h->eof) {
+        return SRE_K_ERROR;
+    }
+    h->last_matched_pos = -1;
+
+    if (h->empty_capture) {                         /* :179-193 */
+        h->empty_capture = 0;
+        if (size == 0) {
+            if (eof) {
+                h->eof = 1;
+                return SRE_K_DECLINED;
+            }
+            return SRE_K_AGAIN;
+        }
+        sp = 1;
+    } else {
+        sp = 0;
+    }
+
+    int cl = h->cur, nl = cl ^ 1;
+
+    if (h->first_buf) {                             /* :202-229 */
+        h->first_buf = 0;
+        for (uint32_t i = 0; i < pk.nslots; i++) {
+            c.cap[i] = -1;
+        }
+        h->tag = h->prog_tag + 1;
+        rc = pike_add_thread(pk, c, cl, nullptr, 0, sp, input, false);
+        if (rc != SRE_K_OK) {
+            h->prog_tag = h->tag;
+            return SRE_K_ERROR;
+        }
+        h->initial_count = h->count[cl];
+        int32_t i = 0;
+        for (int32_t t = h->head[cl]; t >= 0 && c.t_next[t] >= 0; t = c.t_next[t]) {
+            c.initial[i++] = c.t_pc[t];
+        }
+    } else {
+        h->tag = h->prog_tag;
+    }
+
+    for (; sp < last || (eof && sp == last); sp++) {
+        if (h->head[cl] < 0) {
+            break;
+        }
+
+        /* first-byte prefilter, :256-309 */
+        if (pk.nleading && h->seen_start_state) {
+            h->seen_start_state = 0;
+            bool skip = !(sp == last || h->count[cl] != h->initial_count);
+            if (skip) {
+                int32_t i = 0;
+                for (int32_t t = h->head[cl]; t >= 0 && c.t_next[t] >= 0; t = c.t_next[t], i++) {
+                    if (c.t_pc[t] != c.initial[i]) {
+                        skip = false;
+                        break;
+                    }
+                }
+            }
+            if (skip) {
+                const int64_t p = find_first_byte(pk, input, sp, last);
+                if (p > sp) {
+                    sp = p;
+                    list_clear(c, cl);
+                    for (uint32_t i = 0; i < pk.nslots; i++) {
+                        c.cap[i] = -1;
+                    }
+                    h->tag++;
+                    rc = pike_add_thread(pk, c, cl, nullptr, 0, sp, input, false);
+                    if (rc != SRE_K_OK) {
+                        h->prog_tag = h->tag;
+                        return SRE_K_ERROR;
+                    }
+                    if (sp == last) {
+                        break;
+                    }
+                }
+            }
+        }
+
+        h->tag++;
+        const bool at_end = (sp == last);
+        const uint32_t byte = at_end ? 0 : input[sp];
+        const bool cur_word = !at_end && isword(byte);
+
+        while (h->head[cl] >= 0) {                  /* :314-567 */
+            const int32_t t = h->head[cl];
+            h->head[cl] = c.t_next[t];
+            if (h->head[cl] < 0) {
+                h->tail[cl] = -1;
+            }
+            h->count[cl]--;
+
+            const int32_t pc = c.t_pc[t];
+            const sre_dev_inst_t in = pk.insts[pc];
+            const int64_t *tcap = c.t_cap + (size_t) t * pk.nslots;
+            bool got_match = false;
+
+            if (in.opcode == OP_ASSERT) {           /* :449-528 */
+                const bool seen_word = c.t_sw[t] || (sp == 0 && h->seen_word);
+                bool hold = false;
+                switch (in.v) {
+                case AS_SMALL_Z: hold = at_end; break;
+                case AS_DOLLAR:  hold = at_end || byte == '\n'; break;
+                case AS_BIG_B:   hold = (seen_word == cur_word); break;
+                case AS_SMALL_B: hold = (seen_word != cur_word); break;
+                default: break;
+                }
+                if (hold) {
+                    for (uint32_t i = 0; i < pk.nslots; i++) {
+                        c.cap[i] = tcap[i];
+                    }
+                    tmp_list_t tl = { -1, -1, 0 };
+                    h->tag--;
+                    rc = pike_add_thread(pk, c, -1, &tl, pc + 1, sp, input, false);
+                    if (rc != SRE_K_OK) {
+                        h->prog_tag = h->tag + 1;
+                        return SRE_K_ERROR;
+                    }
+                    if (tl.head >= 0) {             /* prepend, :519-523 */
+                        c.t_next[tl.tail] = h->head[cl];
+                        if (h->head[cl] < 0) {
+                            h->tail[cl] = tl.tail;
+                        }
+                        h->head[cl] = tl.head;
+                        h->count[cl] += tl.count;
+                    }
+                    h->tag++;
+                }
+            } else if (in.opcode == OP_MATCH) {     /* :530-553 */
+                h->last_matched_pos = tcap[1];
+                for (uint32_t i = 0; i < pk.nslots; i++) {
+                    c.matched[i] = tcap[i];
+                }
+                h->matched_id = in.v;
+                got_match = true;
+            } else if (!at_end && consumes(pk, in, byte)) {
+                for (uint32_t i = 0; i < pk.nslots; i++) {
+                    c.cap[i] = tcap[i];
+                }
+                rc = pike_add_thread(pk, c, nl, nullptr, pc + 1, sp + 1, input, true);
+                if (rc == RC_DONE) {
+                    got_match = true;
+                } else if (rc != SRE_K_OK) {
+                    h->prog_tag = h->tag;
+                    return SRE_K_ERROR;
+                }
+            }
+
+            /* free the thread */
+            c.t_next[t] = h->free_head;
+            h->free_head = t;
+
+            if (got_match) {
+                h->has_matched = 1;
+                list_clear(c, cl);
+                break;
+            }
+        }
+
+        /* step_done: swap lists */
+        cl ^= 1;
+        nl ^= 1;
+        list_clear(c, nl);
+        if (at_end) {
+            break;
+        }
+    }
+
+    if (h->last_matched_pos >= 0) {                 /* :586-601 */
+        const int64_t p = h->last_matched_pos - h->processed_bytes;
+        if (p > 0) {
+            h->seen_newline = (input[p - 1] == '\n');
+            h->seen_word = isword(input[p - 1]);
+        }
+        h->last_matched_pos = -1;
+    }
+
+    h->prog_tag = h->tag;
+    h->cur = cl;
+
+    if (h->has_matched) {
+        if (eof || h->head[cl] < 0) {               /* :607-636 */
+            if (prepare_matched(pk, c, ovector, ovec_slots, true) != SRE_K_OK) {
+                return SRE_K_ERROR;
+            }
+            if (h->head[cl] >= 0) {
+                list_clear(c, cl);
+                h->eof = 1;
+            }
+            h->processed_bytes = ovector[1];
+            h->empty_capture = (ovector[0] == ovector[1]);
+            h->has_matched = 0;
+            h->first_buf = 1;
+            return h->matched_id;
+        }
+        /* :640-658 */
+        *pending_set = 1;
+        if (prepare_matched(pk, c, h->pending, 2, false) != SRE_K_OK) {
+            return SRE_K_ERROR;
+        }
+    } else if (eof) {
+        h->eof = 1;
+        return SRE_K_DECLINED;
+    }
+
+    h->processed_bytes += sp;
+
+    /* prepare_temp_captures, :692-735 (note: end slot read without the
+     * per-regex offset, :721) */
+    ovector[0] = -1;
+    if (ovec_slots > 1) {
+        ovector[1] = -1;
+    }
+    for (int32_t t = h->head[cl]; t >= 0; t = c.t_next[t]) {
+        const int64_t *tcap = c.t_cap + (size_t) t * pk.nslots;
+        for (uint32_t i = 0; i < pk.nregexes; i++) {
+            const int64_t b0 = tcap[pk.slot_ofs[i]];
+            if (b0 != -1 && (ovector[0] == -1 || b0 < ovector[0])) {
+                ovector[0] = b0;
+            }
+            const int64_t b1 = tcap[1];
+            if (ovec_slots > 1 && b1 != -1 && (ovector[1] == -1 || b1 > ovector[1])) {
+                ovector[1] = b1;
+            }
+        }
+    }
+    return SRE_K_AGAIN;
+}
+
+/* ---- kernels --------------------------------------------------------------- */
+
+__global__ void __launch_bounds__(128)
+k_pike_lines(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
+             size_t nlines, size_t pitch, size_t linelen, const int32_t *__restrict__ select,
+             int32_t *__restrict__ rc, int64_t *__restrict__ ovec, uint32_t ovec_slots,
+             uint8_t *scratch, size_t nctx)
+{
+    const size_t tid = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= nctx) {
+        return;
+    }
+    pike_ctx_t c = pike_carve(pk, scratch + tid * pk.ctx_stride);
+    bool first = true;
+
+    for (size_t line = tid; line < nlines; line += nctx) {
+        int64_t *ov = ovec + line * ovec_slots;
+        if (select && select[line] != SRE_K_OK) {
+            rc[line] = select[line];
+            for (uint32_t i = 0; i < ovec_slots; i++) {
+                ov[i] = -1;
+            }
+            continue;
+        }
+        const size_t start = offsets ? (size_t) offsets[line] : line * pitch;
+        const size_t end = offsets ? (size_t) offsets[line + 1] : start + linelen;
+        pike_reset(c, first);
+        first = false;
+        if (c.h->tag > 0xf0000000u) {       /* tag space nearly used up */
+            for (uint32_t i = 0; i <= pk.len; i++) {
+                c.tags[i] = 0;
+            }
+            c.h->tag = c.h->prog_tag = 0;
+        }
+        int pending;
+        const int r = pike_exec(pk, c, buf + start, (int64_t) (end - start), true, ov, ovec_slots,
+                                &pending);
+        rc[line] = r;
+        if (r < 0) {
+            for (uint32_t i = 0; i < ovec_slots; i++) {
+                ov[i] = -1;
+            }
+        }
+    }
+}
+
+__global__ void k_pike_ctx_init(sre_dev_pike_t pk, uint8_t *ctx)
+{
+    pike_ctx_t c = pike_carve(pk, ctx);
+    for (uint32_t i = 0; i <= pk.len; i++) {
+        c.tags[i] = 0;
+    }
+    pike_reset(c, true);
+}
+
+/* out[0] = rc, out[1] = pending flag, out[2..3] = pending, out[4..] = ovector */
+__global__ void k_pike_stream(sre_dev_pike_t pk, uint8_t *ctx, const uint8_t *buf, size_t len, int eof,
+                              int64_t *out, uint32_t ovec_slots)
+{
+    pike_ctx_t c = pike_carve(pk, ctx);
+    int pending = 0;
+    const int r = pike_exec(pk, c, buf, (int64_t) len, eof != 0, out + 4, ovec_slots, &pending);
+    out[0] = r;
+    out[1] = pending;
+    out[2] = c.h->pending[0];
+    out[3] = c.h->pending[1];
+}
+
+}  // namespace
+
+size_t sre_pike_ctx_bytes(uint32_t len, uint32_t nslots, uint32_t nthreads, uint32_t stack_cap)
+{
+    return pike_ctx_bytes(len, nslots, nthreads, stack_cap);
+}
+
+cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
+    const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen, const int32_t *select,
+    int32_t *rc, int64_t *ovec, uint32_t ovec_slots, uint8_t *scratch, size_t nctx,
+    cudaStream_t stream, int *launches)
+{
+    if (nlines == 0 || nctx == 0) {
+        return cudaSuccess;
+    }
+    if (launches) {
+        ++*launches;
+    }
+    const unsigned grid = (unsigned) ((nctx + 127) / 128);
+    k_pike_lines<<<grid, 128, 0, stream>>>(pk, buf, offsets, nlines, pitch, linelen, select, rc, ovec,
+                                          ovec_slots, scratch, nctx);
+    return cudaGetLastError();
+}
+
+cudaError_t sre_launch_pike_ctx_init(const sre_dev_pike_t &pk, uint8_t *ctx, cudaStream_t stream,
+    int *launches)
+{
+    if (launches) {
+        ++*launches;
+    }
+    k_pike_ctx_init<<<1, 1, 0, stream>>>(pk, ctx);
+    return cudaGetLastError();
+}
+
+cudaError_t sre_launch_pike_stream(const sre_dev_pike_t &pk, uint8_t *ctx, const uint8_t *buf,
+    size_t len, int eof, int want_pending, int64_t *out, uint32_t ovec_slots, cudaStream_t stream,
+    int *launches)
+{
+    (void) want_pending;
+    if (launches) {
+        ++*launches;
+    }
+    k_pike_stream<<<1, 1, 0, stream>>>(pk, ctx, buf, len, eof, out, ovec_slots);
+    return cudaGetLastError();
+}

@@ -1,0 +1,160 @@
+"""Batch / device-pointer entry points of libsregex_cuda (include/sregex_cuda.h)
+for torch tensors.  torch is used for device memory and streams only; the
+matching is done by the library's own CUDA kernels."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import capi
+
+ENGINE_AUTO, ENGINE_DFA_TILED, ENGINE_DFA_GENERIC, ENGINE_NFA = 0, 1, 2, 3
+STATE_INIT = 0xFFFFFFFF
+
+
+class Info(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in (
+        "prog_len", "nfa_states", "nfa_classes", "nfa_kinds", "nfa_shift_states", "dfa_states",
+        "dfa_classes", "dfa_byte_table", "nregexes", "pike_slots")] + [("pike_ctx_bytes", C.c_uint64)]
+
+
+_lib = None
+
+
+def lib():
+    """The product library.  Loading never needs a GPU; compute calls do."""
+    global _lib
+    if _lib is None:
+        sl = capi.load("cuda")
+        L = sl.L
+        vp, sz, i32p, i64p = C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p
+        sig = {
+            "sre_cuda_program_create": (vp, [vp]),
+            "sre_cuda_program_info": (C.c_int, [vp, C.POINTER(Info)]),
+            "sre_cuda_thompson_exec_lines": (C.c_int, [vp, vp, sz, sz, sz, i32p, C.c_int, vp]),
+            "sre_cuda_thompson_exec_ragged": (C.c_int, [vp, vp, i64p, sz, i32p, C.c_int, vp]),
+            "sre_cuda_pike_exec_lines": (C.c_int, [vp, vp, i64p, sz, sz, sz, i32p, i32p, i64p, sz, vp]),
+            "sre_cuda_thompson_exec_stream": (C.c_int, [vp, vp, sz, sz, C.c_uint, C.POINTER(C.c_uint32),
+                                                        C.POINTER(C.c_int64), vp]),
+            "sre_cuda_thompson_stream_reduce": (C.c_int, [vp, vp, sz, C.c_char_p, vp]),
+            "sre_cuda_thompson_stream_resolve": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_uint32),
+                                                           C.POINTER(C.c_int64), vp]),
+            "sre_cuda_thompson_exec_lines_host": (C.c_int, [vp, vp, sz, sz, sz, i32p, C.c_int]),
+            "sre_cuda_pike_exec_lines_host": (C.c_int, [vp, vp, sz, sz, sz, C.c_int, i32p, i64p, sz]),
+            "sre_cuda_set_variant": (None, [C.c_int]),
+            "sre_cuda_launch_count": (C.c_long, [C.c_int]),
+            "sre_cuda_device_available": (C.c_int, []),
+            "sre_cuda_last_error": (C.c_char_p, []),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        sl.ext_symbols = list(sig)
+        _lib = sl
+    return _lib
+
+
+class SreCudaError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc != capi.SRE_OK:
+        raise SreCudaError(lib().L.sre_cuda_last_error().decode() or f"rc={rc}")
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class CudaProgram:
+    """A compiled regex (set) lowered to GPU tables."""
+
+    def __init__(self, regexes, flags=None, multi=None):
+        self.lib = lib()
+        if not self.lib.L.sre_cuda_device_available():
+            raise SreCudaError("no usable CUDA device (libsregex_cuda has no CPU fallback)")
+        self.program = self.lib.compile(regexes, flags, multi)
+        self.cp = self.lib.L.sre_cuda_program_create(self.program.prog)
+        if not self.cp:
+            raise SreCudaError(self.lib.L.sre_cuda_last_error().decode())
+        self.info = Info()
+        _check(self.lib.L.sre_cuda_program_info(self.cp, C.byref(self.info)))
+
+    @property
+    def nslots(self):
+        return self.program.nslots
+
+    def thompson_lines(self, buf: torch.Tensor, nlines: int, pitch: int, linelen: int,
+                       engine: int = ENGINE_AUTO, out: torch.Tensor | None = None) -> torch.Tensor:
+        assert buf.is_cuda and buf.dtype == torch.uint8
+        rc = out if out is not None else torch.empty(nlines, dtype=torch.int32, device=buf.device)
+        _check(self.lib.L.sre_cuda_thompson_exec_lines(self.cp, buf.data_ptr(), nlines, pitch, linelen,
+                                                       rc.data_ptr(), engine, _stream_ptr()))
+        return rc
+
+    def thompson_ragged(self, buf: torch.Tensor, offsets: torch.Tensor, engine: int = ENGINE_AUTO):
+        assert buf.is_cuda and offsets.is_cuda and offsets.dtype == torch.int64
+        n = offsets.numel() - 1
+        rc = torch.empty(n, dtype=torch.int32, device=buf.device)
+        _check(self.lib.L.sre_cuda_thompson_exec_ragged(self.cp, buf.data_ptr(), offsets.data_ptr(), n,
+                                                        rc.data_ptr(), engine, _stream_ptr()))
+        return rc
+
+    def pike_lines(self, buf: torch.Tensor, nlines: int, pitch: int, linelen: int,
+                   offsets: torch.Tensor | None = None, select: torch.Tensor | None = None,
+                   out_rc: torch.Tensor | None = None, out_ovec: torch.Tensor | None = None):
+        n = self.nslots
+        rc = out_rc if out_rc is not None else torch.empty(nlines, dtype=torch.int32, device=buf.device)
+        ov = out_ovec if out_ovec is not None else torch.empty((nlines, n), dtype=torch.int64,
+                                                               device=buf.device)
+        _check(self.lib.L.sre_cuda_pike_exec_lines(
+            self.cp, buf.data_ptr(), offsets.data_ptr() if offsets is not None else None, nlines, pitch,
+            linelen, select.data_ptr() if select is not None else None, rc.data_ptr(), ov.data_ptr(), n,
+            _stream_ptr()))
+        return rc, ov
+
+    def thompson_stream(self, buf: torch.Tensor, length: int, chunk_bytes: int, eof: bool,
+                        state: int = STATE_INIT):
+        """-> (rc, new_state, match_chunk)"""
+        st, mc = C.c_uint32(state), C.c_int64(-1)
+        rc = self.lib.L.sre_cuda_thompson_exec_stream(self.cp, buf.data_ptr(), length, chunk_bytes,
+                                                      int(eof), C.byref(st), C.byref(mc), _stream_ptr())
+        if rc == capi.SRE_ERROR:
+            raise SreCudaError(self.lib.L.sre_cuda_last_error().decode())
+        return rc, st.value, mc.value
+
+    def stream_reduce(self, buf: torch.Tensor, length: int) -> bytes:
+        fn = C.create_string_buffer(max(self.info.dfa_states, 1))
+        _check(self.lib.L.sre_cuda_thompson_stream_reduce(self.cp, buf.data_ptr(), length, fn,
+                                                          _stream_ptr()))
+        return fn.raw[: self.info.dfa_states]
+
+    def stream_resolve(self, entry_state: int):
+        ex, off = C.c_uint32(0), C.c_int64(-1)
+        _check(self.lib.L.sre_cuda_thompson_stream_resolve(self.cp, entry_state, C.byref(ex),
+                                                           C.byref(off), _stream_ptr()))
+        return ex.value, off.value
+
+    # host-buffer (end-to-end) forms: H2D + kernels + D2H inside the call
+    def thompson_lines_host(self, host_buf: torch.Tensor, nlines, pitch, linelen, host_rc: torch.Tensor,
+                            engine: int = ENGINE_AUTO):
+        assert not host_buf.is_cuda and not host_rc.is_cuda
+        _check(self.lib.L.sre_cuda_thompson_exec_lines_host(self.cp, host_buf.data_ptr(), nlines, pitch,
+                                                            linelen, host_rc.data_ptr(), engine))
+        return host_rc
+
+    def pike_lines_host(self, host_buf, nlines, pitch, linelen, host_rc, host_ovec, gate=True):
+        _check(self.lib.L.sre_cuda_pike_exec_lines_host(self.cp, host_buf.data_ptr(), nlines, pitch,
+                                                        linelen, int(gate), host_rc.data_ptr(),
+                                                        host_ovec.data_ptr(), self.nslots))
+        return host_rc, host_ovec
+
+
+def launch_count(reset=False) -> int:
+    return lib().L.sre_cuda_launch_count(int(reset))
+
+
+def set_variant(v: int):
+    lib().L.sre_cuda_set_variant(v)

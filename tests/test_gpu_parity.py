@@ -1,0 +1,237 @@
+"""GPU parity tests proper: libsregex_cuda (through its C ABI) against the
+reference's golden vectors and against the CPU oracle on seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import runnable
+from sregex_b200 import baseline, capi, corpus
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cu():
+    from sregex_b200 import cuda
+    assert cuda.lib().L.sre_cuda_device_available() == 1, "GPU tests need a CUDA device"
+    return cuda
+
+
+# ---- the reference's own API, driven like src/sre_cli.c ----------------------
+
+def test_classic_thompson_golden(golden, cuda):
+    for b in runnable(golden):
+        p = cuda.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        assert cuda.thompson(p, b["subject_b"]) == b["thompson"], (b["file"], b["name"])
+        p.close()
+
+
+def test_classic_thompson_jit_api_golden(golden, cuda):
+    for b in runnable(golden)[::7]:
+        p = cuda.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        assert cuda.thompson(p, b["subject_b"], jit=True) == b["thompson"], (b["file"], b["name"])
+        p.close()
+
+
+def test_classic_thompson_streaming_golden(golden, cuda):
+    """1-byte chunks with SRE_AGAIN carry: whole rc sequence."""
+    for b in runnable(golden)[::3]:
+        p = cuda.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        got = cuda.thompson(p, b["subject_b"], capi.split_chunks(b["subject_b"]))
+        assert got == b["thompson_split"], (b["file"], b["name"])
+        p.close()
+
+
+def test_classic_pike_golden(golden, cuda):
+    for b in runnable(golden):
+        p = cuda.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        rc, ov = cuda.pike(p, b["subject_b"])
+        assert (rc, ov) == (b["pike"]["rc"], b["pike"]["ov"]), (b["file"], b["name"])
+        p.close()
+
+
+def test_classic_pike_streaming_golden(golden, cuda):
+    """1-byte chunks: final rc/ovector and the temp-capture / pending trace."""
+    for b in runnable(golden)[::3]:
+        p = cuda.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        trace, rc, ov = cuda.pike(p, b["subject_b"], capi.split_chunks(b["subject_b"]))
+        want = b["pike_split"]
+        assert (rc, ov) == (want["rc"], want["ov"]), (b["file"], b["name"])
+        assert [list(t) for t in trace] == want["trace"], (b["file"], b["name"])
+        p.close()
+
+
+# ---- batch entry points --------------------------------------------------------
+
+def _golden_batch(golden, cu, engine):
+    """every golden block as a 1-line batch through a given Thompson tier"""
+    bad = []
+    for b in runnable(golden):
+        prog = cu.CudaProgram(b["regexes_b"], b["flags"], multi=b["multi"])
+        if engine in (cu.ENGINE_DFA_TILED, cu.ENGINE_DFA_GENERIC) and prog.info.dfa_states == 0:
+            continue
+        s = b["subject_b"]
+        pitch = max(16, (len(s) + 15) // 16 * 16)
+        buf = torch.zeros(pitch, dtype=torch.uint8)
+        buf[: len(s)] = torch.frombuffer(bytearray(s), dtype=torch.uint8) if s else buf[:0]
+        rc = prog.thompson_lines(buf.cuda(), 1, pitch, len(s), engine=engine)
+        if int(rc[0]) != b["thompson"]:
+            bad.append((b["file"], b["name"]))
+        prog.program.close()
+    assert not bad, bad[:10]
+
+
+def test_batch_golden_dfa_tiled(golden, cu):
+    _golden_batch(golden, cu, cu.ENGINE_DFA_TILED)
+
+
+def test_batch_golden_dfa_generic(golden, cu):
+    _golden_batch(golden, cu, cu.ENGINE_DFA_GENERIC)
+
+
+def test_batch_golden_nfa(golden, cu):
+    _golden_batch(golden, cu, cu.ENGINE_NFA)
+
+
+@pytest.mark.parametrize("nlines,linelen,pitch", [(4096, 1024, 1024), (1000, 1000, 1008), (33, 17, 32),
+                                                  (5, 0, 16), (257, 63, 64), (64, 129, 144)])
+def test_thompson_tiers_vs_oracle(cu, nlines, linelen, pitch):
+    lines = corpus.log_lines(nlines, 1024)[:, 1024 - pitch:] if pitch <= 1024 else None
+    lines = lines.contiguous()
+    host = lines.numpy()
+    _, want, _ = baseline.run_lines("oracle", corpus.C2_REGEX, None, host, nlines, pitch, linelen,
+                                    baseline.ENGINE_THOMPSON)
+    prog = cu.CudaProgram(corpus.C2_REGEX)
+    dev = lines.cuda()
+    for engine in (cu.ENGINE_DFA_TILED, cu.ENGINE_DFA_GENERIC, cu.ENGINE_NFA):
+        for variant in ((0, 1, 2, 3) if engine == cu.ENGINE_DFA_TILED else (0,)):
+            cu.set_variant(variant)
+            got = prog.thompson_lines(dev, nlines, pitch, linelen, engine=engine).cpu().numpy()
+            assert (got == want).all(), (engine, variant, int((got != want).sum()))
+    cu.set_variant(0)
+    if linelen == 1024:
+        assert 0 < (want == 0).sum() < nlines
+
+
+def test_thompson_ragged_vs_oracle(cu):
+    rng = np.random.default_rng(0x5EED)
+    lines = corpus.log_lines(512, 1024).numpy()
+    lens = rng.integers(0, 1024, size=512)
+    lens[:4] = [0, 1, 15, 16]
+    chunks = [lines[i, 1024 - lens[i]:] for i in range(512)]
+    flat = np.concatenate(chunks + [np.zeros(16, np.uint8)])
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    prog = cu.CudaProgram(corpus.C2_REGEX)
+    want = []
+    o = capi.load("oracle")
+    po = o.compile(corpus.C2_REGEX)
+    for c in chunks:
+        want.append(o.thompson(po, c.tobytes()))
+    for engine in (cu.ENGINE_AUTO, cu.ENGINE_NFA):
+        got = prog.thompson_ragged(torch.from_numpy(flat).cuda(), torch.from_numpy(offsets).cuda(),
+                                   engine=engine).cpu().numpy()
+        assert got.tolist() == want, engine
+
+
+def test_pike_lines_vs_oracle(cu):
+    n = 2048
+    lines = corpus.log_lines(n, 1024)
+    host = lines.numpy()
+    prog = cu.CudaProgram(corpus.C3_REGEX)
+    _, want_rc, want_ov = baseline.run_lines("oracle", corpus.C3_REGEX, None, host, n, 1024, 1024,
+                                             baseline.ENGINE_PIKE, ovec_slots=prog.nslots)
+    rc, ov = prog.pike_lines(lines.cuda(), n, 1024, 1024)
+    assert (rc.cpu().numpy() == want_rc).all()
+    assert (ov.cpu().numpy() == want_ov).all()
+    assert (want_rc == 0).all()             # every line holds a request line
+    # gated by a Thompson pass: same answer
+    sel = prog.thompson_lines(lines.cuda(), n, 1024, 1024)
+    rc2, ov2 = prog.pike_lines(lines.cuda(), n, 1024, 1024, select=sel)
+    assert torch.equal(rc, rc2) and torch.equal(ov, ov2)
+
+
+MULTI = [rb"HTTP/1\.[01]\" 5\d\d ", rb"(GET|HEAD) /x/(\d+)", rb"POST /x/0", rb"^1[0-4]\d\.", rb"08:47:0(\d)",
+         rb"zzz+q", rb"\bPUT\b", rb"[a-f]{6}\d"]
+
+
+def test_multi_regex_id_vs_oracle(cu):
+    n = 1024
+    lines = corpus.log_lines(n, 1024)
+    prog = cu.CudaProgram(MULTI)
+    _, want_rc, want_ov = baseline.run_lines("oracle", MULTI, None, lines.numpy(), n, 1024, 1024,
+                                             baseline.ENGINE_PIKE, ovec_slots=prog.nslots)
+    _, want_bool, _ = baseline.run_lines("oracle", MULTI, None, lines.numpy(), n, 1024, 1024,
+                                         baseline.ENGINE_THOMPSON)
+    dev = lines.cuda()
+    sel = prog.thompson_lines(dev, n, 1024, 1024)
+    assert (sel.cpu().numpy() == want_bool).all()
+    rc, ov = prog.pike_lines(dev, n, 1024, 1024, select=sel)
+    assert (rc.cpu().numpy() == want_rc).all()
+    assert (ov.cpu().numpy() == want_ov).all()
+    assert len(set(want_rc.tolist())) > 3   # several different patterns win
+
+
+def test_stream_scan_vs_oracle(cu):
+    """bench/gen-data.pl buffer (scaled down) fed in chunks: same rc sequence as
+    the oracle's sre_vm_thompson_exec with SRE_AGAIN carry."""
+    buf = corpus.gen_data_buffer(40000)          # 200,008 bytes, match at the tail
+    data = bytes(buf.numpy())
+    prog = cu.CudaProgram(corpus.BENCH_REGEX)
+    o = capi.load("oracle")
+    po = o.compile(corpus.BENCH_REGEX)
+    dev = buf.cuda()
+    for chunk in (65536, 4096, 1000):
+        pieces = [(data[i:i + chunk], i + chunk >= len(data)) for i in range(0, len(data), chunk)]
+        want = o.thompson(po, data, pieces)
+        rc, state, mchunk = prog.thompson_stream(dev, len(data), chunk, True)
+        assert rc == want[-1] == capi.SRE_OK
+        assert mchunk == len(want) - 1, (chunk, mchunk, len(want))
+        # carried across two calls
+        cut = (len(data) // 2) // 16 * 16
+        rc1, st1, _ = prog.thompson_stream(dev, cut, chunk, False)
+        assert rc1 == capi.SRE_AGAIN
+        rc2, _, _ = prog.thompson_stream(dev[cut:], len(data) - cut, chunk, True, state=st1)
+        assert rc2 == capi.SRE_OK
+    # no-match variant
+    nomatch = corpus.gen_data_buffer(40000)[:-8].contiguous()
+    rc, _, _ = prog.thompson_stream(nomatch.cuda(), nomatch.numel(), 65536, True)
+    assert rc == capi.SRE_DECLINED == o.thompson(po, bytes(nomatch.numpy()))
+    # multi-GPU building blocks: reduce to a function, then resolve
+    fn = prog.stream_reduce(dev, len(data))
+    ex, off = prog.stream_resolve(0)
+    assert fn[0] == ex == 1 and off == len(data) - 1
+
+
+def test_classic_exec_large_buffer(cuda):
+    """sre_vm_thompson_exec on a 5 MB buffer (the reference's bench config):
+    takes the chunk-parallel path inside the drop-in entry point."""
+    data = bytes(corpus.gen_data_buffer(1048576).numpy())
+    p = cuda.compile(corpus.BENCH_REGEX)
+    assert cuda.thompson(p, data) == capi.SRE_OK
+    assert cuda.thompson(p, data[:-8]) == capi.SRE_DECLINED
+    half = len(data) // 2
+    assert cuda.thompson(p, data, [(data[:half], False), (data[half:], True)]) == [capi.SRE_AGAIN, capi.SRE_OK]
+    rc, ov = cuda.pike(p, data[-4096:])
+    assert (rc, ov) == (0, [4088, 4096])
+
+
+def test_full_size_properties(cu):
+    """BASELINE config 2 at full size (1M x 1 KB): the verdict of every line
+    must equal what the generator planted (5xx status <=> match), and every
+    tier must agree."""
+    n = 1 << 20
+    dev = corpus.log_lines(n, 1024, device="cuda")
+    prog = cu.CudaProgram(corpus.C2_REGEX)
+    rc = prog.thompson_lines(dev, n, 1024, 1024)
+    # status field: 3 digits before the final space of the request
+    is5 = torch.zeros(n, dtype=torch.bool, device="cuda")
+    # find '" ' + '5' pattern directly with tensor ops (independent of the library)
+    q = (dev[:, :-3] == ord('"')) & (dev[:, 1:-2] == ord(' ')) & (dev[:, 2:-1] == ord('5'))
+    is5 = q.any(dim=1)
+    assert torch.equal(rc == 0, is5)
+    assert 0.08 < float(is5.float().mean()) < 0.12
+    rc2 = prog.thompson_lines(dev, n, 1024, 1024, engine=cu.ENGINE_DFA_GENERIC)
+    assert torch.equal(rc, rc2)
+    sub = 1 << 16
+    rc3 = prog.thompson_lines(dev, sub, 1024, 1024, engine=cu.ENGINE_NFA)
+    assert torch.equal(rc[:sub], rc3)
