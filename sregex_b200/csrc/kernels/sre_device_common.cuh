@@ -8,6 +8,7 @@
 #ifndef SRE_DEVICE_COMMON_CUH
 #define SRE_DEVICE_COMMON_CUH
 
+#include <cuda.h>
 #include "sre_kernels.cuh"
 
 namespace sre_dev {
@@ -88,11 +89,13 @@ __device__ __forceinline__ void load_table(uint8_t *dst, const uint8_t *src, siz
  *   [0, tab)            transition table
  *   [.., +fin)          fin[nstates]
  *   [.., +256)          byte-class map (class-compressed variant only)
+ *   [bar_ofs, ...)      per-warp mbarriers of the TMA pipeline
  *   [stage_ofs, ...)    per-warp staging rings (k_dfa_lines only), 1 KB aligned
  */
 struct dfa_smem_plan_t {
-    size_t tab_bytes, fin_ofs, cls_ofs, stage_ofs;
+    size_t tab_bytes, fin_ofs, cls_ofs, bar_ofs, stage_ofs;
 };
+constexpr int MAX_WARPS = 32, MAX_STAGES = 8;
 
 __host__ __device__ inline dfa_smem_plan_t dfa_smem_plan(uint32_t nstates, uint32_t nclasses, bool cls)
 {
@@ -100,7 +103,8 @@ __host__ __device__ inline dfa_smem_plan_t dfa_smem_plan(uint32_t nstates, uint3
     p.tab_bytes = align_up(cls ? (size_t) nstates * nclasses * 2 : (size_t) nstates * 256, 16);
     p.fin_ofs = p.tab_bytes;
     p.cls_ofs = p.fin_ofs + align_up(nstates, 16);
-    p.stage_ofs = align_up(p.cls_ofs + (cls ? 256 : 0), 1024);
+    p.bar_ofs = align_up(p.cls_ofs + (cls ? 256 : 0), 16);
+    p.stage_ofs = align_up(p.bar_ofs + MAX_WARPS * MAX_STAGES * 8, 1024);
     return p;
 }
 
@@ -224,7 +228,271 @@ __device__ __forceinline__ void tile_pipeline(Consumer &cons, const uint8_t *__r
     cp_async_wait<0>();
 }
 
+
+/* ---- TMA (cp.async.bulk.tensor) + mbarrier helpers ------------------------- */
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t) __cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+/* one 2-D box {c0 .. c0+box0, c1 .. c1+box1} -> dst, completes on bar */
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int32_t c0, int32_t c1,
+                                            uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+        :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+/*
+ * TMA flavour of the per-warp tile pipeline: the tensor map describes the
+ * corpus as a 2-D byte tensor {pitch, nrows}; one elected lane asks the TMA
+ * unit for a {TW bytes x 32 rows} box per tile, written with the hardware's
+ * 32/64/128-byte swizzle (the same XOR pattern as swizzle<TW>() above, because
+ * the stage buffers are aligned to the swizzle atom), and signals a per-stage
+ * mbarrier.  Rows past nrows and bytes past the pitch are zero-filled by the
+ * hardware.  All STAGES buffers can be in flight; a stage is re-armed as soon
+ * as every lane has consumed it (__syncwarp).
+ */
+template <int TW, int STAGES, class Consumer>
+__device__ __forceinline__ void tile_pipeline_tma(Consumer &cons, const CUtensorMap *tmap, size_t nrows,
+    uint32_t rowlen, uint8_t *my_stage, uint64_t *my_bars, size_t gw, size_t warps_total)
+{
+    constexpr int CPR = TW / 16;
+    constexpr int STAGE_BYTES = 32 * TW;
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t ngroups = (nrows + 31) / 32;
+    if (gw >= ngroups) {
+        return;
+    }
+    const uint32_t my_groups = (uint32_t) ((ngroups - gw + warps_total - 1) / warps_total);
+    const uint32_t ntiles = (rowlen + TW - 1) / TW;
+
+    if (ntiles == 0) {
+        for (uint32_t gi = 0; gi < my_groups; gi++) {
+            cons.begin();
+            cons.end(gw + (size_t) gi * warps_total);
+        }
+        return;
+    }
+
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < STAGES; i++) {
+            mbar_init(&my_bars[i], 1);
+        }
+        fence_mbar_init();
+    }
+    __syncwarp();
+
+    const uint32_t total = my_groups * ntiles;
+
+    /* lane 0 only */
+    auto issue = [&](uint32_t k, uint32_t gi, uint32_t t) {
+        const size_t group = gw + (size_t) gi * warps_total;
+        uint64_t *bar = &my_bars[k % STAGES];
+        mbar_arrive_expect_tx(bar, STAGE_BYTES);
+        tma_load_2d(my_stage + (k % STAGES) * STAGE_BYTES, tmap, (int32_t) (t * TW),
+                    (int32_t) (group * 32), bar);
+    };
+
+    /* producer cursor (tile index, group index, tile-in-row) */
+    uint32_t pk = 0, pgi = 0, pt = 0;
+    auto produce = [&]() {
+        if (pk < total) {
+            if (lane == 0) {
+                issue(pk, pgi, pt);
+            }
+            pk++;
+            if (++pt == ntiles) {
+                pt = 0;
+                pgi++;
+            }
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < STAGES; i++) {
+        produce();
+    }
+
+    uint32_t t = 0;
+    size_t group = gw;
+    const uint32_t swz = swizzle<TW>(lane);
+    cons.begin();
+
+    for (uint32_t k = 0; k < total; k++) {
+        mbar_wait(&my_bars[k % STAGES], (k / STAGES) & 1);
+
+        const uint8_t *row = my_stage + (k % STAGES) * STAGE_BYTES + lane * TW;
+        const uint32_t left = rowlen - t * TW;
+        if (left >= (uint32_t) TW) {
+#pragma unroll
+            for (int c = 0; c < CPR; c++) {
+                cons.chunk(*reinterpret_cast<const uint4 *>(row + ((c ^ swz) << 4)));
+            }
+        } else {
+            for (uint32_t i = 0; i < left; i++) {
+                cons.byte(row[(((i >> 4) ^ swz) << 4) | (i & 15)]);
+            }
+        }
+        __syncwarp();       /* every lane is done with this stage */
+        produce();          /* ... so it can be re-armed */
+
+        if (++t == ntiles) {
+            cons.end(group);
+            t = 0;
+            group += warps_total;
+            cons.begin();
+        }
+    }
+}
+
+/*
+ * Early-release flavour: a lane copies its row of the landed tile into
+ * registers in two 64-byte halves; as soon as the second half is in registers
+ * (i.e. half-way through the tile's processing time) the stage buffer is handed
+ * back to the TMA unit.  The staging memory per line is therefore only
+ * STAGES x 128 bytes with STAGES = 1 or 2, which lets 40-48 warps per SM be
+ * resident: the per-byte dependent chain (PRMT -> LDS.U8, ~35 cycles) needs
+ * that many independent lines in flight to keep the shared-memory pipe busy.
+ * TW is fixed at 128 (the row width the TMA unit moves efficiently).
+ */
+template <int STAGES, class Consumer>
+__device__ __forceinline__ void tile_pipeline_tma_early(Consumer &cons, const CUtensorMap *tmap, size_t nrows,
+    uint32_t rowlen, uint8_t *my_stage, uint64_t *my_bars, size_t gw, size_t warps_total)
+{
+    constexpr int TW = 128;
+    constexpr int STAGE_BYTES = 32 * TW;
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t ngroups = (nrows + 31) / 32;
+    if (gw >= ngroups) {
+        return;
+    }
+    const uint32_t my_groups = (uint32_t) ((ngroups - gw + warps_total - 1) / warps_total);
+    const uint32_t ntiles = (rowlen + TW - 1) / TW;
+
+    if (ntiles == 0) {
+        for (uint32_t gi = 0; gi < my_groups; gi++) {
+            cons.begin();
+            cons.end(gw + (size_t) gi * warps_total);
+        }
+        return;
+    }
+
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < STAGES; i++) {
+            mbar_init(&my_bars[i], 1);
+        }
+        fence_mbar_init();
+    }
+    __syncwarp();
+
+    const uint32_t total = my_groups * ntiles;
+    uint32_t pk = 0, pgi = 0, pt = 0;
+    auto produce = [&]() {
+        if (pk < total) {
+            if (lane == 0) {
+                uint64_t *bar = &my_bars[pk % STAGES];
+                mbar_arrive_expect_tx(bar, STAGE_BYTES);
+                tma_load_2d(my_stage + (pk % STAGES) * STAGE_BYTES, tmap, (int32_t) (pt * TW),
+                            (int32_t) ((gw + (size_t) pgi * warps_total) * 32), bar);
+            }
+            pk++;
+            if (++pt == ntiles) {
+                pt = 0;
+                pgi++;
+            }
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < STAGES; i++) {
+        produce();
+    }
+
+    uint32_t t = 0;
+    size_t group = gw;
+    const uint32_t swz = lane & 7;
+    cons.begin();
+
+    for (uint32_t k = 0; k < total; k++) {
+        mbar_wait(&my_bars[k % STAGES], (k / STAGES) & 1);
+        const uint8_t *row = my_stage + (k % STAGES) * STAGE_BYTES + lane * TW;
+        const uint32_t left = rowlen - t * TW;
+
+        uint4 a[4], b[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            a[c] = *reinterpret_cast<const uint4 *>(row + ((c ^ swz) << 4));
+        }
+        if (left >= (uint32_t) TW) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                cons.chunk(a[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                b[c] = *reinterpret_cast<const uint4 *>(row + (((c + 4) ^ swz) << 4));
+            }
+            __syncwarp();
+            produce();
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                cons.chunk(b[c]);
+            }
+        } else {
+            /* ragged last tile of a row: byte loop straight from the stage */
+            for (uint32_t i = 0; i < left; i++) {
+                cons.byte(row[(((i >> 4) ^ swz) << 4) | (i & 15)]);
+            }
+            __syncwarp();
+            produce();
+        }
+
+        if (++t == ntiles) {
+            cons.end(group);
+            t = 0;
+            group += warps_total;
+            cons.begin();
+        }
+    }
+}
+
 int num_sms();
+/* host: 2-D byte tensor {pitch, nrows}, box {tw, 32}, swizzle by tw */
+cudaError_t make_row_tensor_map(CUtensorMap *map, const uint8_t *buf, size_t nrows, size_t pitch, int tw);
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
 }  // namespace sre_dev

@@ -633,6 +633,11 @@ k_pike_lines(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
     }
     pike_ctx_t c = pike_carve(pk, scratch + tid * pk.ctx_stride);
     bool first = true;
+    /* the scratch is reused across launches: stale tags must not alias the
+     * restarted tag counter */
+    for (uint32_t i = 0; i <= pk.len; i++) {
+        c.tags[i] = 0;
+    }
 
     for (size_t line = tid; line < nlines; line += nctx) {
         int64_t *ov = ovec + line * ovec_slots;

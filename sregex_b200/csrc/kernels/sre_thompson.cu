@@ -94,6 +94,82 @@ k_dfa_lines(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t nlines, s
                               (size_t) gridDim.x * warps_per_block);
 }
 
+/* same consumer, input staged by the TMA unit instead of cp.async */
+template <int TW, int STAGES, bool CLS>
+__global__ void __launch_bounds__(1024, 1)
+k_dfa_lines_tma(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t nlines,
+                uint32_t linelen, int32_t *__restrict__ rc)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, CLS);
+    uint8_t *s_tab = smem;
+    uint8_t *s_fin = smem + plan.fin_ofs;
+    uint8_t *s_cls = smem + plan.cls_ofs;
+
+    load_table(s_tab, CLS ? reinterpret_cast<const uint8_t *>(dfa.tcls) : dfa.t256, plan.tab_bytes);
+    load_table(s_fin, dfa.fin, align_up(dfa.nstates, 16));
+    if (CLS) {
+        load_table(s_cls, dfa.clsmap, 256);
+    }
+    __syncthreads();
+
+    const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    line_consumer_t<CLS> cons;
+    cons.st256.tab = s_tab;
+    cons.stcls.tab = reinterpret_cast<const uint16_t *>(s_tab);
+    cons.stcls.cls = s_cls;
+    cons.stcls.ncls = dfa.nclasses;
+    cons.fin = s_fin;
+    cons.start = dfa.start;
+    cons.acc = dfa.acc;
+    cons.nlines = nlines;
+    cons.rc = rc;
+
+    tile_pipeline_tma<TW, STAGES>(cons, &tmap, nlines, linelen,
+                                  smem + plan.stage_ofs + (size_t) warp * STAGES * 32 * TW,
+                                  reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES,
+                                  (size_t) blockIdx.x * warps_per_block + warp,
+                                  (size_t) gridDim.x * warps_per_block);
+}
+
+/* TMA staging with early stage release (see tile_pipeline_tma_early) */
+template <int STAGES, bool CLS, int THREADS, int BLOCKS>
+__global__ void __launch_bounds__(THREADS, BLOCKS)
+k_dfa_lines_tma_early(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t nlines,
+                      uint32_t linelen, int32_t *__restrict__ rc)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, CLS);
+    uint8_t *s_tab = smem;
+    uint8_t *s_fin = smem + plan.fin_ofs;
+    uint8_t *s_cls = smem + plan.cls_ofs;
+
+    load_table(s_tab, CLS ? reinterpret_cast<const uint8_t *>(dfa.tcls) : dfa.t256, plan.tab_bytes);
+    load_table(s_fin, dfa.fin, align_up(dfa.nstates, 16));
+    if (CLS) {
+        load_table(s_cls, dfa.clsmap, 256);
+    }
+    __syncthreads();
+
+    const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    line_consumer_t<CLS> cons;
+    cons.st256.tab = s_tab;
+    cons.stcls.tab = reinterpret_cast<const uint16_t *>(s_tab);
+    cons.stcls.cls = s_cls;
+    cons.stcls.ncls = dfa.nclasses;
+    cons.fin = s_fin;
+    cons.start = dfa.start;
+    cons.acc = dfa.acc;
+    cons.nlines = nlines;
+    cons.rc = rc;
+
+    tile_pipeline_tma_early<STAGES>(cons, &tmap, nlines, linelen,
+                                    smem + plan.stage_ofs + (size_t) warp * STAGES * 32 * 128,
+                                    reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES,
+                                    (size_t) blockIdx.x * warps_per_block + warp,
+                                    (size_t) gridDim.x * warps_per_block);
+}
+
 /* ---- k_dfa_generic --------------------------------------------------------- */
 
 template <bool CLS, bool SMEM_TAB>
@@ -291,6 +367,40 @@ k_nfa_lines(sre_dev_nfa_t nfa, const uint8_t *__restrict__ buf, const int64_t *_
 namespace sre_dev {
 static int g_num_sms = 0;
 
+cudaError_t make_row_tensor_map(CUtensorMap *map, const uint8_t *buf, size_t nrows, size_t pitch, int tw)
+{
+    typedef CUresult (*encode_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+    static encode_fn_t encode = nullptr;
+    if (encode == nullptr) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+            return e != cudaSuccess ? e : cudaErrorNotSupported;
+        }
+        encode = reinterpret_cast<encode_fn_t>(fn);
+    }
+    if (pitch % 16 || (reinterpret_cast<uintptr_t>(buf) & 15) || nrows == 0 || nrows >= (1ull << 31)
+        || pitch >= (1ull << 31))
+    {
+        return cudaErrorInvalidValue;
+    }
+    const cuuint64_t gdim[2] = { (cuuint64_t) pitch, (cuuint64_t) nrows };
+    const cuuint64_t gstride[1] = { (cuuint64_t) pitch };
+    const cuuint32_t box[2] = { (cuuint32_t) tw, 32 };
+    const cuuint32_t estride[2] = { 1, 1 };
+    const CUtensorMapSwizzle swz = tw >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : tw == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                 : tw == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(buf), gdim, gstride,
+                              box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 int num_sms()
 {
     if (g_num_sms == 0) {
@@ -307,29 +417,113 @@ int num_sms()
 
 namespace {
 
+/* how many warps per block / blocks per SM fit next to the tables */
+bool pick_shape(size_t fixed, size_t per_warp, int *warps, int *blocks_per_sm)
+{
+    *warps = 16;
+    *blocks_per_sm = 2;
+    while (*blocks_per_sm * (fixed + *warps * per_warp + 1024) > SMEM_LIMIT) {
+        if (*blocks_per_sm == 2) {
+            *blocks_per_sm = 1;
+            *warps = 32;
+        } else if (*warps > 4) {
+            *warps -= 4;
+        } else {
+            return false;
+        }
+    }
+    return true;
+}
+
+template <int TW, int STAGES, bool CLS>
+cudaError_t launch_dfa_lines_tma_t(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines,
+    size_t pitch, size_t linelen, int32_t *rc, cudaStream_t stream)
+{
+    static_assert(STAGES <= MAX_STAGES, "stages");
+    const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, CLS);
+    const size_t per_warp = (size_t) STAGES * 32 * TW;
+    int warps, blocks_per_sm;
+    if (!pick_shape(plan.stage_ofs, per_warp, &warps, &blocks_per_sm)) {
+        return cudaErrorInvalidConfiguration;
+    }
+    CUtensorMap tmap;
+    cudaError_t err = make_row_tensor_map(&tmap, buf, nlines, pitch, TW);
+    if (err != cudaSuccess) {
+        return err;
+    }
+    const size_t smem = plan.stage_ofs + warps * per_warp;
+    auto kern = k_dfa_lines_tma<TW, STAGES, CLS>;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (err != cudaSuccess) {
+            return err;
+        }
+        smem_set = smem;
+    }
+    const size_t ngroups = (nlines + 31) / 32;
+    size_t grid = (size_t) num_sms() * blocks_per_sm;
+    const size_t need = (ngroups + warps - 1) / warps;
+    if (grid > need) {
+        grid = need;
+    }
+    kern<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen, rc);
+    return cudaGetLastError();
+}
+
+template <int STAGES, bool CLS, int THREADS, int BLOCKS>
+cudaError_t launch_dfa_lines_early_t(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines,
+    size_t pitch, size_t linelen, int32_t *rc, cudaStream_t stream)
+{
+    const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, CLS);
+    const int warps = THREADS / 32;
+    const size_t smem = plan.stage_ofs + (size_t) warps * STAGES * 32 * 128;
+    if (BLOCKS * (smem + 1024) > SMEM_LIMIT) {
+        return cudaErrorInvalidConfiguration;
+    }
+    CUtensorMap tmap;
+    cudaError_t err = make_row_tensor_map(&tmap, buf, nlines, pitch, 128);
+    if (err != cudaSuccess) {
+        return err;
+    }
+    auto kern = k_dfa_lines_tma_early<STAGES, CLS, THREADS, BLOCKS>;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (err != cudaSuccess) {
+            return err;
+        }
+        smem_set = smem;
+    }
+    const size_t ngroups = (nlines + 31) / 32;
+    size_t grid = (size_t) num_sms() * BLOCKS;
+    const size_t need = (ngroups + warps - 1) / warps;
+    if (grid > need) {
+        grid = need;
+    }
+    kern<<<(unsigned) grid, THREADS, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen, rc);
+    return cudaGetLastError();
+}
+
 template <int TW, int STAGES, bool CLS>
 cudaError_t launch_dfa_lines_t(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines,
     size_t pitch, size_t linelen, int32_t *rc, cudaStream_t stream)
 {
     const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, CLS);
     const size_t per_warp = (size_t) STAGES * 32 * TW;
-    /* prefer 2 blocks of 16 warps per SM; fall back to what fits */
-    int warps = 16, blocks_per_sm = 2;
-    while (blocks_per_sm * (plan.stage_ofs + warps * per_warp + 1024) > SMEM_LIMIT) {
-        if (blocks_per_sm == 2) {
-            blocks_per_sm = 1;
-            warps = 32;
-        } else if (warps > 4) {
-            warps -= 4;
-        } else {
-            return cudaErrorInvalidConfiguration;
-        }
+    int warps, blocks_per_sm;
+    if (!pick_shape(plan.stage_ofs, per_warp, &warps, &blocks_per_sm)) {
+        return cudaErrorInvalidConfiguration;
     }
     const size_t smem = plan.stage_ofs + warps * per_warp;
     auto kern = k_dfa_lines<TW, STAGES, CLS>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (err != cudaSuccess) {
-        return err;
+    static size_t smem_set = 0;         /* per template instance */
+    if (smem > smem_set) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (err != cudaSuccess) {
+            return err;
+        }
+        smem_set = smem;
     }
     const size_t ngroups = (nlines + 31) / 32;
     size_t grid = (size_t) num_sms() * blocks_per_sm;
@@ -358,20 +552,37 @@ cudaError_t sre_launch_dfa_lines(const sre_dev_dfa_t &dfa, const uint8_t *buf, s
     if (launches) {
         ++*launches;
     }
+#define SRE_LINES(FN, TW, ST)                                                                 \
+    (cls ? FN<TW, ST, true>(dfa, buf, nlines, pitch, linelen, rc, stream)                      \
+         : FN<TW, ST, false>(dfa, buf, nlines, pitch, linelen, rc, stream))
     switch (variant) {
-    case 1:
-        return cls ? launch_dfa_lines_t<128, 2, true>(dfa, buf, nlines, pitch, linelen, rc, stream)
-                   : launch_dfa_lines_t<128, 2, false>(dfa, buf, nlines, pitch, linelen, rc, stream);
-    case 2:
-        return cls ? launch_dfa_lines_t<32, 4, true>(dfa, buf, nlines, pitch, linelen, rc, stream)
-                   : launch_dfa_lines_t<32, 4, false>(dfa, buf, nlines, pitch, linelen, rc, stream);
-    case 3:
-        return cls ? launch_dfa_lines_t<64, 4, true>(dfa, buf, nlines, pitch, linelen, rc, stream)
-                   : launch_dfa_lines_t<64, 4, false>(dfa, buf, nlines, pitch, linelen, rc, stream);
-    default:
-        return cls ? launch_dfa_lines_t<64, 3, true>(dfa, buf, nlines, pitch, linelen, rc, stream)
-                   : launch_dfa_lines_t<64, 3, false>(dfa, buf, nlines, pitch, linelen, rc, stream);
+    /* TMA-staged, whole-tile stage occupancy */
+    case 6:  return SRE_LINES(launch_dfa_lines_tma_t, 64, 4);
+    case 1:  return SRE_LINES(launch_dfa_lines_tma_t, 128, 2);
+    case 2:  return SRE_LINES(launch_dfa_lines_tma_t, 32, 4);
+    case 3:  return SRE_LINES(launch_dfa_lines_tma_t, 64, 3);
+    case 4:  return SRE_LINES(launch_dfa_lines_tma_t, 128, 3);
+    case 5:  return SRE_LINES(launch_dfa_lines_tma_t, 32, 6);
+    /* TMA-staged, early stage release: <stages, threads/block, blocks/SM> */
+#define SRE_EARLY(ST, TH, BL)                                                                  \
+    (cls ? launch_dfa_lines_early_t<ST, true, TH, BL>(dfa, buf, nlines, pitch, linelen, rc, stream) \
+         : launch_dfa_lines_early_t<ST, false, TH, BL>(dfa, buf, nlines, pitch, linelen, rc, stream))
+    case 0:                                     /* default: best measured on B200 */
+    case 23: return SRE_EARLY(1, 1024, 1);      /* 32 warps/SM */
+    case 20: return SRE_EARLY(1, 640, 2);       /* 40 warps/SM */
+    case 21: return SRE_EARLY(1, 768, 2);       /* 48 warps/SM */
+    case 22: return SRE_EARLY(2, 768, 1);       /* 24 warps/SM */
+    case 24: return SRE_EARLY(1, 512, 3);       /* 48 warps/SM */
+    case 25: return SRE_EARLY(2, 832, 1);       /* 26 warps/SM */
+#undef SRE_EARLY
+    /* cp.async-staged */
+    case 10: return SRE_LINES(launch_dfa_lines_t, 64, 3);
+    case 11: return SRE_LINES(launch_dfa_lines_t, 128, 2);
+    case 12: return SRE_LINES(launch_dfa_lines_t, 32, 4);
+    case 13: return SRE_LINES(launch_dfa_lines_t, 64, 4);
+    default: return cudaErrorInvalidValue;
     }
+#undef SRE_LINES
 }
 
 static cudaError_t launch_dfa_generic(const sre_dev_dfa_t &dfa, const uint8_t *buf,

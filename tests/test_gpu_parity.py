@@ -104,7 +104,7 @@ def test_thompson_tiers_vs_oracle(cu, nlines, linelen, pitch):
     prog = cu.CudaProgram(corpus.C2_REGEX)
     dev = lines.cuda()
     for engine in (cu.ENGINE_DFA_TILED, cu.ENGINE_DFA_GENERIC, cu.ENGINE_NFA):
-        for variant in ((0, 1, 2, 3) if engine == cu.ENGINE_DFA_TILED else (0,)):
+        for variant in ((0, 1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 20, 21, 22, 24, 25) if engine == cu.ENGINE_DFA_TILED else (0,)):
             cu.set_variant(variant)
             got = prog.thompson_lines(dev, nlines, pitch, linelen, engine=engine).cpu().numpy()
             assert (got == want).all(), (engine, variant, int((got != want).sum()))
@@ -197,9 +197,15 @@ def test_stream_scan_vs_oracle(cu):
     rc, _, _ = prog.thompson_stream(nomatch.cuda(), nomatch.numel(), 65536, True)
     assert rc == capi.SRE_DECLINED == o.thompson(po, bytes(nomatch.numpy()))
     # multi-GPU building blocks: reduce to a function, then resolve
+    # (the match ends on the last byte, so it is the EOF step that sees it:
+    #  the exit state is not ACC and there is no in-stream match offset)
     fn = prog.stream_reduce(dev, len(data))
     ex, off = prog.stream_resolve(0)
-    assert fn[0] == ex == 1 and off == len(data) - 1
+    assert fn[0] == ex != 1 and off == -1
+    longer = torch.cat([buf, torch.tensor(list(b"xyz"), dtype=torch.uint8)]).cuda()
+    fn = prog.stream_reduce(longer, longer.numel())
+    ex, off = prog.stream_resolve(0)
+    assert fn[0] == ex == 1 and off == len(data)      # the step on 'x' sees the MATCH thread
 
 
 def test_classic_exec_large_buffer(cuda):
