@@ -69,9 +69,13 @@ SRE_API int sre_cuda_thompson_exec_ragged(sre_cuda_program_t *cp,
  * per line.  dev_rc[i] = matched regex id (>= 0), SRE_DECLINED or SRE_ERROR;
  * dev_ovec[i*ovec_slots ..] = what the reference leaves in the caller's ovector
  * (matched regex's groups, -1 fill; all -1 when there is no match).
- * dev_offsets may be NULL (fixed pitch).  dev_select may be NULL; otherwise only
- * lines with dev_select[i] == SRE_OK are run (others: rc = dev_select[i]), which
- * lets a Thompson pass gate the capture pass.
+ * dev_offsets may be NULL (fixed pitch).  dev_select: when given, only lines with
+ * dev_select[i] == SRE_OK are run (others: rc = dev_select[i]), which lets a
+ * Thompson pass gate the capture pass.  When dev_select is NULL and the lines
+ * are aligned fixed-pitch, the library runs that gate itself with the
+ * determinised program, which also yields per line the offset after which no
+ * earlier-started thread is alive; the Pike search of a line starts there (an
+ * exact form of the reference's first-byte prefilter, sre_vm_pike.c:256-309).
  */
 SRE_API int sre_cuda_pike_exec_lines(sre_cuda_program_t *cp,
     const uint8_t *dev_buf, const int64_t *dev_offsets, size_t nlines,
@@ -104,6 +108,10 @@ SRE_API int sre_cuda_thompson_stream_reduce(sre_cuda_program_t *cp,
 SRE_API int sre_cuda_thompson_stream_resolve(sre_cuda_program_t *cp,
     uint32_t entry_state, uint32_t *exit_state, int64_t *first_match_offset,
     void *stream);
+
+/* 1 if the EOF step of the lowered DFA sees a match in `state` (the rc an
+ * sre_vm_thompson_exec(ctx, NULL, 0, eof=1) call would add: SRE_OK vs DECLINED) */
+SRE_API int sre_cuda_dfa_fin(sre_cuda_program_t *cp, uint32_t state);
 
 /* Host-buffer conveniences (the end-to-end path: H2D + kernels + D2H inside) */
 SRE_API int sre_cuda_thompson_exec_lines_host(sre_cuda_program_t *cp,

@@ -112,3 +112,39 @@ long lc_dfa_exec(lc_t *lc, const uint8_t *buf, size_t len, unsigned eof, int use
 }
 
 }
+
+/* transfer function of a buffer over the DFA: out[d] = state reached from d
+ * (test stand-in for the GPU stream reduce in the world_size-2 gloo tests) */
+extern "C" int lc_dfa_fn(lc_t *lc, const uint8_t *buf, size_t len, uint8_t *out)
+{
+    const sre_dfa_t &d = lc->low.dfa;
+    if (!lc->low.has_dfa || d.nstates > 256) return SRE_ERROR;
+    for (uint32_t e = 0; e < d.nstates; e++) {
+        uint32_t s = e;
+        for (size_t i = 0; i < len; i++) {
+            s = d.trans[(size_t) s * d.nclasses + d.clsmap[buf[i]]];
+        }
+        out[e] = (uint8_t) s;
+    }
+    return SRE_OK;
+}
+
+extern "C" int lc_dfa_fin(lc_t *lc, unsigned state)
+{
+    return lc->low.has_dfa && state < lc->low.dfa.nstates ? lc->low.dfa.fin[state] : 0;
+}
+
+/* Pike start hint over the restart table (see sre_lower.h h256); -1 if the
+ * program has no such table */
+extern "C" long lc_hint(lc_t *lc, const uint8_t *buf, size_t len)
+{
+    const sre_dfa_t &d = lc->low.dfa;
+    if (!lc->low.has_dfa || d.h256.empty()) return -1;
+    uint32_t s = 0;
+    long p0 = 0;
+    for (size_t i = 0; i < len; i++) {
+        s = d.h256[(size_t) s * 256 + buf[i]];
+        if (s & 0x80) p0 = (long) i + 1;
+    }
+    return p0;
+}

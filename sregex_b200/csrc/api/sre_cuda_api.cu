@@ -97,6 +97,8 @@ struct sre_cuda_program_s {
     size_t              stream_ws_bytes = 0;
     sre_stream_ws_t     ws;
     uint32_t           *d_exit = nullptr;       /* exit state + match offset */
+    uint8_t            *line_ws = nullptr;      /* gate verdict + start hint */
+    size_t              line_ws_bytes = 0;
     uint8_t            *io_buf = nullptr;       /* host-variant staging      */
     size_t              io_bytes = 0;
     /* stream_reduce -> stream_resolve hand-over */
@@ -118,6 +120,7 @@ void program_destroy(void *data)
     cudaFree(cp->stream_ws);
     cudaFree(cp->d_exit);
     cudaFree(cp->io_buf);
+    cudaFree(cp->line_ws);
     delete cp;
 }
 
@@ -126,13 +129,16 @@ int upload(sre_cuda_program_t *cp)
     const sre_program_t *prog = cp->prog;
     const sre_nfa_t &n = cp->low.nfa;
     blob_t b;
-    size_t o_t256 = 0, o_tcls = 0, o_dcls = 0, o_fin = 0;
+    size_t o_t256 = 0, o_tcls = 0, o_dcls = 0, o_fin = 0, o_h256 = 0;
 
     cp->has_dfa = cp->low.has_dfa;
     if (cp->has_dfa) {
         const sre_dfa_t &d = cp->low.dfa;
         if (!d.t256.empty()) {
             o_t256 = b.add(d.t256.data(), d.t256.size());
+        }
+        if (!d.h256.empty()) {
+            o_h256 = b.add(d.h256.data(), d.h256.size());
         }
         o_tcls = b.add(d.trans.data(), d.trans.size() * 2);
         o_dcls = b.add(d.clsmap, 256);
@@ -213,6 +219,7 @@ int upload(sre_cuda_program_t *cp)
         cp->dfa.tcls = reinterpret_cast<const uint16_t *>(base + o_tcls);
         cp->dfa.clsmap = base + o_dcls;
         cp->dfa.fin = base + o_fin;
+        cp->dfa.h256 = d.h256.empty() ? nullptr : base + o_h256;
     }
     if (cp->has_nfa) {
         cp->nfa.nstates = n.nstates;
@@ -488,10 +495,42 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         return SRE_ERROR;
     }
     int launches = 0;
+    cudaStream_t st = as_stream(stream);
+    const int32_t *start = nullptr;
+
+    /*
+     * No caller-supplied gate: run the determinised program first.  It yields
+     * the Thompson verdict (lines that cannot match are skipped) and, per
+     * line, the offset after which no earlier-started thread is alive, where
+     * the Pike search may begin.
+     */
+    const bool aligned = dev_offsets == nullptr && (reinterpret_cast<uintptr_t>(dev_buf) & 15) == 0
+                         && (pitch & 15) == 0 && linelen <= pitch && linelen < (1ull << 31);
+    if (dev_select == nullptr && cp->has_dfa && cp->dfa.h256 != nullptr && aligned) {
+        const size_t need = ((nlines * 4 + 255) & ~(size_t) 255) * 2;
+        if (cp->line_ws_bytes < need) {
+            cudaFree(cp->line_ws);
+            cp->line_ws = nullptr;
+            cp->line_ws_bytes = 0;
+            CUDA_TRY(cudaMalloc(&cp->line_ws, need));
+            cp->line_ws_bytes = need;
+        }
+        int32_t *gate = reinterpret_cast<int32_t *>(cp->line_ws);
+        int32_t *hint = reinterpret_cast<int32_t *>(cp->line_ws + need / 2);
+        cudaError_t e = sre_launch_dfa_lines_hint(cp->dfa, dev_buf, nlines, pitch, linelen, gate, hint, st,
+                                                  &launches);
+        if (e != cudaSuccess) {
+            count_launches(launches);
+            return fail("hint kernel launch failed: %s", cudaGetErrorString(e));
+        }
+        dev_select = gate;
+        start = hint;
+    }
+
     cudaError_t err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen,
-                                            dev_select, dev_rc, dev_ovec, (uint32_t) ovec_slots,
+                                            dev_select, start, dev_rc, dev_ovec, (uint32_t) ovec_slots,
                                             cp->pike_scratch, cp->pike_nctx < nlines ? cp->pike_nctx : nlines,
-                                            as_stream(stream), &launches);
+                                            st, &launches);
     count_launches(launches);
     if (err != cudaSuccess) {
         return fail("Pike kernel launch failed: %s", cudaGetErrorString(err));
@@ -631,6 +670,15 @@ sre_cuda_thompson_exec_stream(sre_cuda_program_t *cp, const uint8_t *dev_buf, si
         return SRE_DECLINED;
     }
     return SRE_AGAIN;
+}
+
+SRE_API int
+sre_cuda_dfa_fin(sre_cuda_program_t *cp, uint32_t state)
+{
+    if (cp == NULL || !cp->has_dfa || state >= cp->low.dfa.nstates) {
+        return 0;
+    }
+    return cp->low.dfa.fin[state];
 }
 
 /* ---- host-buffer conveniences --------------------------------------------- */

@@ -22,6 +22,7 @@ struct sre_dev_dfa_t {
     const uint16_t  *tcls;      /* [nstates][nclasses] next state * nclasses  */
     const uint8_t   *clsmap;    /* [256]                                      */
     const uint8_t   *fin;       /* [nstates]                                  */
+    const uint8_t   *h256;      /* [256][256] next | restart flag, or NULL    */
 };
 
 /* ---- NFA tier ------------------------------------------------------------ */
@@ -89,12 +90,19 @@ cudaError_t sre_launch_dfa_carry(const sre_dev_dfa_t &dfa, const uint8_t *buf,
     uint32_t *state_io, int from_init, int eof, int32_t *rc,
     cudaStream_t stream, int *launches);
 
-/* Pike VM over lines; select may be NULL (all) or an rc array (run where ==0) */
+/* Thompson verdict + Pike start hint per line (needs dfa.h256, aligned lines):
+ * hint[i] = offset after which no earlier-started thread is alive             */
+cudaError_t sre_launch_dfa_lines_hint(const sre_dev_dfa_t &dfa, const uint8_t *buf,
+    size_t nlines, size_t pitch, size_t linelen, int32_t *rc, int32_t *hint,
+    cudaStream_t stream, int *launches);
+
+/* Pike VM over lines; select may be NULL (all) or an rc array (run where ==0);
+ * start may be NULL or per-line offsets at which the search may begin          */
 size_t sre_pike_concurrency(size_t nlines);
 cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
     const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen,
-    const int32_t *select, int32_t *rc, int64_t *ovec, uint32_t ovec_slots,
-    uint8_t *scratch, size_t nctx, cudaStream_t stream, int *launches);
+    const int32_t *select, const int32_t *start, int32_t *rc, int64_t *ovec,
+    uint32_t ovec_slots, uint8_t *scratch, size_t nctx, cudaStream_t stream, int *launches);
 
 /* Pike VM streaming step on one persistent context (classic API)             */
 cudaError_t sre_launch_pike_stream(const sre_dev_pike_t &pk, uint8_t *ctx,

@@ -382,7 +382,7 @@ __device__ inline int prepare_matched(const sre_dev_pike_t &pk, pike_ctx_t &c, i
  * (ovec_slots entries).  *pending_set: 1 when h->pending holds a pending match.
  */
 __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t *input, int64_t size,
-    bool eof, int64_t *ovector, uint32_t ovec_slots, int *pending_set)
+    bool eof, int64_t *ovector, uint32_t ovec_slots, int *pending_set, int64_t start_pos = 0)
 {
     pike_hdr_t *h = c.h;
     int64_t sp, last = size;
@@ -405,7 +405,9 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
         }
         sp = 1;
     } else {
-        sp = 0;
+        /* batch callers may pass an offset before which no match can start
+         * (see k_dfa_lines_hint); the classic API always starts at 0 */
+        sp = start_pos;
     }
 
     int cl = h->cur, nl = cl ^ 1;
@@ -624,7 +626,7 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
 __global__ void __launch_bounds__(128)
 k_pike_lines(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
              size_t nlines, size_t pitch, size_t linelen, const int32_t *__restrict__ select,
-             int32_t *__restrict__ rc, int64_t *__restrict__ ovec, uint32_t ovec_slots,
+             const int32_t *__restrict__ start_hint, int32_t *__restrict__ rc, int64_t *__restrict__ ovec, uint32_t ovec_slots,
              uint8_t *scratch, size_t nctx)
 {
     const size_t tid = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -660,7 +662,7 @@ k_pike_lines(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
         }
         int pending;
         const int r = pike_exec(pk, c, buf + start, (int64_t) (end - start), true, ov, ovec_slots,
-                                &pending);
+                                &pending, start_hint ? start_hint[line] : 0);
         rc[line] = r;
         if (r < 0) {
             for (uint32_t i = 0; i < ovec_slots; i++) {
@@ -701,7 +703,7 @@ size_t sre_pike_ctx_bytes(uint32_t len, uint32_t nslots, uint32_t nthreads, uint
 
 cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
     const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen, const int32_t *select,
-    int32_t *rc, int64_t *ovec, uint32_t ovec_slots, uint8_t *scratch, size_t nctx,
+    const int32_t *start, int32_t *rc, int64_t *ovec, uint32_t ovec_slots, uint8_t *scratch, size_t nctx,
     cudaStream_t stream, int *launches)
 {
     if (nlines == 0 || nctx == 0) {
@@ -711,7 +713,7 @@ cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
         ++*launches;
     }
     const unsigned grid = (unsigned) ((nctx + 127) / 128);
-    k_pike_lines<<<grid, 128, 0, stream>>>(pk, buf, offsets, nlines, pitch, linelen, select, rc, ovec,
+    k_pike_lines<<<grid, 128, 0, stream>>>(pk, buf, offsets, nlines, pitch, linelen, select, start, rc, ovec,
                                           ovec_slots, scratch, nctx);
     return cudaGetLastError();
 }

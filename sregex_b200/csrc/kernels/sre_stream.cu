@@ -7,8 +7,8 @@
  * program is one DFA state, so a piece of the stream is a function
  * f: state -> state, and function composition is associative:
  *
- *   k_stream_pieces   one CUDA thread per PIECE-byte piece (same shared-memory
- *                     tile pipeline as k_dfa_lines, rows = pieces): runs the
+ *   k_stream_pieces   one CUDA thread per PIECE-byte piece (same TMA tile
+ *                     pipeline as k_dfa_lines, rows = pieces): runs the
  *                     piece from EVERY entry state at once ("speculatively")
  *                     and writes the piece's transfer function (nstates bytes).
  *                     As soon as all live entry states have converged to one
@@ -51,6 +51,7 @@ struct piece_consumer_t {
     size_t          npieces;
     uint32_t        st[DV];
     uint32_t        s;          /* the single state once converged            */
+    uint32_t        accmask;    /* entry states already absorbed by ACC       */
     bool            conv;
 
     __device__ __forceinline__ void begin()
@@ -61,22 +62,32 @@ struct piece_consumer_t {
         }
         conv = false;
         s = 0;
+        accmask = 0;
     }
 
     __device__ __forceinline__ void check()
     {
-        /* all entry states except ACC (absorbing) agree? */
-        uint32_t ref = acc == 0 ? st[1] : st[0];
+        /* converged = every entry state has either been absorbed by ACC (e.g.
+         * entry states that already hold a MATCH thread) or reached one common
+         * state */
+        uint32_t ref = acc, mask = 0;
         bool all = true;
 #pragma unroll
         for (int d = 0; d < DV; d++) {
-            if (d < (int) nstates && d != (int) acc && st[d] != ref) {
-                all = false;
+            if (d < (int) nstates) {
+                if (st[d] == acc) {
+                    mask |= 1u << d;
+                } else if (ref == acc) {
+                    ref = st[d];
+                } else if (st[d] != ref) {
+                    all = false;
+                }
             }
         }
         if (all) {
             conv = true;
             s = ref;
+            accmask = mask;
         }
     }
 
@@ -124,16 +135,16 @@ struct piece_consumer_t {
 #pragma unroll
         for (int d = 0; d < DV; d++) {
             if (d < (int) fs) {
-                const uint32_t v = conv ? (d == (int) acc ? acc : s) : st[d];
+                const uint32_t v = conv ? (((accmask >> d) & 1) ? acc : s) : st[d];
                 out[d] = (uint8_t) (d < (int) nstates ? v : 0);
             }
         }
     }
 };
 
-template <int DV, int TW, int STAGES>
-__global__ void __launch_bounds__(512, 1)
-k_stream_pieces(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t npieces, uint8_t *fn)
+template <int DV, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+k_stream_pieces(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t npieces, uint8_t *fn)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, false);
@@ -149,10 +160,12 @@ k_stream_pieces(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t npiec
     cons.fs = fn_stride(dfa.nstates);
     cons.npieces = npieces;
 
-    tile_pipeline<TW, STAGES>(cons, buf, npieces, PIECE, PIECE,
-                              smem + plan.stage_ofs + (size_t) warp * STAGES * 32 * TW,
-                              (size_t) blockIdx.x * warps_per_block + warp,
-                              (size_t) gridDim.x * warps_per_block);
+    /* rows = pieces: the stream is a {PIECE, npieces} byte tensor */
+    tile_pipeline_tma_early<1>(cons, &tmap, npieces, PIECE,
+                               smem + plan.stage_ofs + (size_t) warp * 32 * 128,
+                               reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES,
+                               (size_t) blockIdx.x * warps_per_block + warp,
+                               (size_t) gridDim.x * warps_per_block);
 }
 
 /* transfer function of the ragged tail (< PIECE bytes), one thread per state */
@@ -169,7 +182,27 @@ __global__ void k_stream_tail(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf
     out[d] = (uint8_t) (d < dfa.nstates ? s : 0);
 }
 
-/* out[i] = in[i*FAN + last] o ... o in[i*FAN] */
+/* a function record held in registers: byte k of a 16/32-byte record */
+struct fn_rec_t {
+    uint4 lo, hi;
+    __device__ __forceinline__ void load(const uint8_t *p, uint32_t fs)
+    {
+        lo = *reinterpret_cast<const uint4 *>(p);
+        if (fs > 16) {
+            hi = *reinterpret_cast<const uint4 *>(p + 16);
+        }
+    }
+    __device__ __forceinline__ uint32_t at(uint32_t k) const
+    {
+        const uint4 &q = (k & 16) ? hi : lo;
+        const uint32_t w = (k & 8) ? ((k & 4) ? q.w : q.z) : ((k & 4) ? q.y : q.x);
+        return (w >> ((k & 3) * 8)) & 0xff;
+    }
+};
+
+/* out[i] = in[i*FAN + last] o ... o in[i*FAN].  The record loads do not depend
+ * on the running composition, so they pipeline; only register selects do. */
+template <int DV>
 __global__ void __launch_bounds__(128)
 k_stream_compose(const uint8_t *__restrict__ in, size_t n_in, uint8_t *__restrict__ out, size_t n_out,
                  uint32_t nstates, uint32_t fs)
@@ -178,27 +211,28 @@ k_stream_compose(const uint8_t *__restrict__ in, size_t n_in, uint8_t *__restric
     if (i >= n_out) {
         return;
     }
-    uint8_t cur[32];
+    uint32_t cur[DV];
 #pragma unroll
-    for (int d = 0; d < 32; d++) {
-        cur[d] = (uint8_t) d;
+    for (int d = 0; d < DV; d++) {
+        cur[d] = d;
     }
     const size_t first = i * FAN, last = first + FAN < n_in ? first + FAN : n_in;
+#pragma unroll 4
     for (size_t j = first; j < last; j++) {
-        const uint8_t *f = in + j * fs;
+        fn_rec_t f;
+        f.load(in + j * fs, fs);
 #pragma unroll
-        for (int d = 0; d < 32; d++) {
-            if (d < (int) nstates) {
-                cur[d] = f[cur[d]];
-            }
+        for (int d = 0; d < DV; d++) {
+            cur[d] = f.at(cur[d]);
         }
     }
     uint8_t *o = out + i * fs;
 #pragma unroll
-    for (int d = 0; d < 32; d++) {
-        if (d < (int) fs) {
-            o[d] = d < (int) nstates ? cur[d] : 0;
-        }
+    for (int d = 0; d < DV; d++) {
+        o[d] = d < (int) nstates ? (uint8_t) cur[d] : 0;
+    }
+    for (uint32_t d = DV; d < fs; d++) {
+        o[d] = 0;
     }
 }
 
@@ -226,11 +260,14 @@ k_stream_entries(const uint8_t *__restrict__ fn, size_t n, uint32_t fs, const ui
     }
     uint32_t s = parent_entry[i];
     const size_t first = i * FAN, last = first + FAN < n ? first + FAN : n;
+#pragma unroll 4
     for (size_t j = first; j < last; j++) {
+        fn_rec_t f;
+        f.load(fn + j * fs, fs);
         if (entry) {
             entry[j] = (uint8_t) s;
         }
-        const uint32_t nx = fn[j * fs + s];
+        const uint32_t nx = f.at(s);
         if (level0 && nx == acc && s != acc) {
             atomicMin(first_acc, (unsigned long long) j);
         }
@@ -260,27 +297,34 @@ __global__ void k_stream_locate(sre_dev_dfa_t dfa, const uint8_t *__restrict__ b
     *match_offset = -1;     /* cannot happen */
 }
 
-template <int DV>
+template <int DV, int THREADS>
 cudaError_t launch_pieces(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t npieces, uint8_t *fn,
     cudaStream_t stream)
 {
-    constexpr int TW = 64, STAGES = 3;
     const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, false);
-    const int warps = 16;
-    const size_t smem = plan.stage_ofs + (size_t) warps * STAGES * 32 * TW;
-    auto kern = k_stream_pieces<DV, TW, STAGES>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    const int warps = THREADS / 32;
+    const size_t smem = plan.stage_ofs + (size_t) warps * 32 * 128;
+    CUtensorMap tmap;
+    cudaError_t err = make_row_tensor_map(&tmap, buf, npieces, PIECE, 128);
     if (err != cudaSuccess) {
         return err;
     }
-    const int bps = 2 * smem + 2048 <= SMEM_LIMIT ? 2 : 1;
+    auto kern = k_stream_pieces<DV, THREADS>;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (err != cudaSuccess) {
+            return err;
+        }
+        smem_set = smem;
+    }
     const size_t ngroups = (npieces + 31) / 32;
-    size_t grid = (size_t) num_sms() * bps;
+    size_t grid = (size_t) num_sms();
     const size_t need = (ngroups + warps - 1) / warps;
     if (grid > need) {
         grid = need;
     }
-    kern<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, buf, npieces, fn);
+    kern<<<(unsigned) grid, THREADS, smem, stream>>>(dfa, tmap, npieces, fn);
     return cudaGetLastError();
 }
 
@@ -305,11 +349,11 @@ cudaError_t sre_launch_dfa_stream_reduce(const sre_dev_dfa_t &dfa, const uint8_t
     if (nfull) {
         if (launches) ++*launches;
         if (dfa.nstates <= 8) {
-            err = launch_pieces<8>(dfa, buf, nfull, ws.fn[0], stream);
+            err = launch_pieces<8, 1024>(dfa, buf, nfull, ws.fn[0], stream);
         } else if (dfa.nstates <= 16) {
-            err = launch_pieces<16>(dfa, buf, nfull, ws.fn[0], stream);
+            err = launch_pieces<16, 768>(dfa, buf, nfull, ws.fn[0], stream);
         } else {
-            err = launch_pieces<32>(dfa, buf, nfull, ws.fn[0], stream);
+            err = launch_pieces<32, 512>(dfa, buf, nfull, ws.fn[0], stream);
         }
         if (err != cudaSuccess) return err;
     }
@@ -321,8 +365,13 @@ cudaError_t sre_launch_dfa_stream_reduce(const sre_dev_dfa_t &dfa, const uint8_t
     for (int l = 0; l < 3 && ws.count[l] > FAN; l++) {
         const size_t n_out = ws.count[l + 1];
         if (launches) ++*launches;
-        k_stream_compose<<<(unsigned) ((n_out + 127) / 128), 128, 0, stream>>>(
-            ws.fn[l], ws.count[l], ws.fn[l + 1], n_out, dfa.nstates, fs);
+        if (dfa.nstates <= 16) {
+            k_stream_compose<16><<<(unsigned) ((n_out + 127) / 128), 128, 0, stream>>>(
+                ws.fn[l], ws.count[l], ws.fn[l + 1], n_out, dfa.nstates, fs);
+        } else {
+            k_stream_compose<32><<<(unsigned) ((n_out + 127) / 128), 128, 0, stream>>>(
+                ws.fn[l], ws.count[l], ws.fn[l + 1], n_out, dfa.nstates, fs);
+        }
         if ((err = cudaGetLastError()) != cudaSuccess) return err;
     }
     return cudaSuccess;

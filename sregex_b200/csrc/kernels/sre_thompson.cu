@@ -170,6 +170,81 @@ k_dfa_lines_tma_early(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tma
                                     (size_t) gridDim.x * warps_per_block);
 }
 
+/* ---- k_dfa_lines_hint ------------------------------------------------------ */
+
+/*
+ * Same automaton through the [256][256] "restart" table: bit 7 of an entry says
+ * that only the ".*?" thread consumed the byte, i.e. every partial match died
+ * on it.  hint = offset just after the last such byte seen before the first
+ * match: a leftmost-first (Pike) search may start there instead of at 0, which
+ * is the reference's first-byte prefilter idea (sre_vm_pike.c:256-309) made
+ * exact by the automaton instead of a thread-list comparison.
+ */
+struct hint_consumer_t {
+    const uint8_t  *tab;        /* h256 in shared memory */
+    const uint8_t  *fin;
+    uint32_t        acc, s, pos, p0;
+    size_t          nlines;
+    int32_t        *rc, *hint;
+
+    __device__ __forceinline__ void begin() { s = 0; pos = 0; p0 = 0; }
+    __device__ __forceinline__ void step(uint32_t addr)
+    {
+        s = tab[addr];
+        pos++;
+        if (s & 0x80) {
+            p0 = pos;
+        }
+    }
+    __device__ __forceinline__ void chunk(const uint4 &v)
+    {
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            step(__byte_perm(w[i], s, 0x5540));
+            step(__byte_perm(w[i], s, 0x5541));
+            step(__byte_perm(w[i], s, 0x5542));
+            step(__byte_perm(w[i], s, 0x5543));
+        }
+    }
+    __device__ __forceinline__ void byte(uint32_t b) { step((s << 8) | b); }
+    __device__ __forceinline__ void end(size_t group)
+    {
+        const size_t line = group * 32 + (threadIdx.x & 31);
+        if (line < nlines) {
+            const uint32_t st = s & 0x7f;
+            rc[line] = (st == acc || fin[st]) ? SRE_K_OK : SRE_K_DECLINED;
+            hint[line] = (int32_t) p0;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(1024, 1)
+k_dfa_lines_hint(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t nlines,
+                 uint32_t linelen, int32_t *__restrict__ rc, int32_t *__restrict__ hint)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    /* plan as for a 256-state byte table */
+    const dfa_smem_plan_t plan = dfa_smem_plan(256, 0, false);
+    load_table(smem, dfa.h256, 65536);
+    load_table(smem + plan.fin_ofs, dfa.fin, align_up(dfa.nstates, 16));
+    __syncthreads();
+
+    const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    hint_consumer_t cons;
+    cons.tab = smem;
+    cons.fin = smem + plan.fin_ofs;
+    cons.acc = dfa.acc;
+    cons.nlines = nlines;
+    cons.rc = rc;
+    cons.hint = hint;
+    tile_pipeline_tma_early<1>(cons, &tmap, nlines, linelen,
+                               smem + plan.stage_ofs + (size_t) warp * 32 * 128,
+                               reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES,
+                               (size_t) blockIdx.x * warps_per_block + warp,
+                               (size_t) gridDim.x * warps_per_block);
+}
+
 /* ---- k_dfa_generic --------------------------------------------------------- */
 
 template <bool CLS, bool SMEM_TAB>
@@ -583,6 +658,45 @@ cudaError_t sre_launch_dfa_lines(const sre_dev_dfa_t &dfa, const uint8_t *buf, s
     default: return cudaErrorInvalidValue;
     }
 #undef SRE_LINES
+}
+
+cudaError_t sre_launch_dfa_lines_hint(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines,
+    size_t pitch, size_t linelen, int32_t *rc, int32_t *hint, cudaStream_t stream, int *launches)
+{
+    if (nlines == 0) {
+        return cudaSuccess;
+    }
+    if (dfa.h256 == nullptr) {
+        return cudaErrorInvalidValue;
+    }
+    const dfa_smem_plan_t plan = dfa_smem_plan(256, 0, false);
+    const int warps = 32;
+    const size_t smem = plan.stage_ofs + (size_t) warps * 32 * 128;
+    CUtensorMap tmap;
+    cudaError_t err = make_row_tensor_map(&tmap, buf, nlines, pitch, 128);
+    if (err != cudaSuccess) {
+        return err;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        err = cudaFuncSetAttribute(k_dfa_lines_hint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (err != cudaSuccess) {
+            return err;
+        }
+        attr_set = true;
+    }
+    const size_t ngroups = (nlines + 31) / 32;
+    size_t grid = (size_t) num_sms();
+    const size_t need = (ngroups + warps - 1) / warps;
+    if (grid > need) {
+        grid = need;
+    }
+    if (launches) {
+        ++*launches;
+    }
+    k_dfa_lines_hint<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen, rc,
+                                                                  hint);
+    return cudaGetLastError();
 }
 
 static cudaError_t launch_dfa_generic(const sre_dev_dfa_t &dfa, const uint8_t *buf,

@@ -310,12 +310,21 @@ bool build_dfa(const sre_nfa_t &nfa, uint32_t max_states, sre_dfa_t &dfa)
     std::unordered_map<std::vector<uint32_t>, uint32_t, set_hash_t> ids;
     std::vector<std::vector<uint32_t> > sets;
     std::vector<uint16_t> trans;        /* [state][C] over NFA classes */
+    std::vector<uint8_t> restart;       /* [state][C]: only the `any` thread moved */
     const uint32_t ACC = 1;
+    /* the state of the ".*?" prefix: pc 1, no pending look-ahead */
+    int32_t any_state = -1;
+    for (uint32_t s = 0; s < n; s++) {
+        if (nfa.state_pc[s] == 1 && nfa.state_allow[s] == 0x0f) {
+            any_state = (int32_t) s;
+        }
+    }
 
     sets.push_back(nfa.init);           /* 0 = start */
     ids[nfa.init] = 0;
     sets.push_back(std::vector<uint32_t>());    /* 1 = ACC (no set) */
     trans.assign(2 * C, (uint16_t) ACC);
+    restart.assign(2 * C, 0);
 
     std::vector<uint32_t> next(W);
     for (uint32_t cur = 0; cur < sets.size(); cur++) {
@@ -337,8 +346,14 @@ bool build_dfa(const sre_nfa_t &nfa, uint32_t max_states, sre_dfa_t &dfa)
                 continue;
             }
             std::fill(next.begin(), next.end(), 0u);
+            bool only_any = any_state >= 0;
             for (uint32_t w = 0; w < W; w++) {
                 uint32_t m = S[w] & mv[w];
+                const uint32_t any_bit = (any_state >= 0 && (uint32_t) any_state / 32 == w)
+                                             ? 1u << (any_state & 31) : 0;
+                if (m != any_bit) {
+                    only_any = false;
+                }
                 while (m) {
                     uint32_t s = w * 32 + __builtin_ctz(m);
                     m &= m - 1;
@@ -361,10 +376,12 @@ bool build_dfa(const sre_nfa_t &nfa, uint32_t max_states, sre_dfa_t &dfa)
                 ids[next] = id;
                 sets.push_back(next);
                 trans.resize(trans.size() + C, 0);
+                restart.resize(restart.size() + C, 0);
             } else {
                 id = it->second;
             }
             trans[(size_t) cur * C + c] = (uint16_t) id;
+            restart[(size_t) cur * C + c] = only_any ? 1 : 0;
         }
     }
 
@@ -382,6 +399,19 @@ bool build_dfa(const sre_nfa_t &nfa, uint32_t max_states, sre_dfa_t &dfa)
             if (sets[d][w] & nfa.mt_eof[w]) {
                 dfa.fin[d] = 1;
                 break;
+            }
+        }
+    }
+
+    if (D <= 128) {
+        dfa.h256.assign((size_t) 256 * 256, 0);
+        for (uint32_t d = 0; d < D; d++) {
+            for (unsigned b = 0; b < 256; b++) {
+                const uint32_t c = nfa.clsmap[b];
+                const uint8_t e = (uint8_t) (trans[(size_t) d * C + c]
+                                             | (restart[(size_t) d * C + c] ? 0x80 : 0));
+                dfa.h256[(size_t) d * 256 + b] = e;
+                dfa.h256[(size_t) (d + 128) * 256 + b] = e;
             }
         }
     }

@@ -73,6 +73,14 @@ struct sre_dfa_t {
     std::vector<uint8_t>    fin;                /* [nstates]                    */
     /* byte-indexed u8 table for the fast kernel, only when nstates <= 256    */
     std::vector<uint8_t>    t256;               /* [nstates][256]               */
+    /*
+     * "restart" table for the Pike start hint, only when nstates <= 128:
+     * [256 rows][256]; row r and row r+128 are identical; entry = next state |
+     * 0x80 when the only thread that consumed the byte is the ".*?" `any`
+     * thread (every partial match died on it), so that a leftmost-first search
+     * may be restarted right after this byte (Pike hint).
+     */
+    std::vector<uint8_t>    h256;
 };
 
 struct sre_lowered_t {

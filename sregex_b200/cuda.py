@@ -40,6 +40,7 @@ def lib():
             "sre_cuda_thompson_stream_reduce": (C.c_int, [vp, vp, sz, C.c_char_p, vp]),
             "sre_cuda_thompson_stream_resolve": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_uint32),
                                                            C.POINTER(C.c_int64), vp]),
+            "sre_cuda_dfa_fin": (C.c_int, [vp, C.c_uint32]),
             "sre_cuda_thompson_exec_lines_host": (C.c_int, [vp, vp, sz, sz, sz, i32p, C.c_int]),
             "sre_cuda_pike_exec_lines_host": (C.c_int, [vp, vp, sz, sz, sz, C.c_int, i32p, i64p, sz]),
             "sre_cuda_set_variant": (None, [C.c_int]),

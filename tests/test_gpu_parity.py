@@ -93,6 +93,26 @@ def test_batch_golden_nfa(golden, cu):
     _golden_batch(golden, cu, cu.ENGINE_NFA)
 
 
+def test_batch_golden_pike_with_start_hint(golden, cu):
+    """every golden block as a 1-line batch through sre_cuda_pike_exec_lines with
+    its internal gate + start-hint pass: rc and the whole ovector"""
+    bad = []
+    for b in runnable(golden):
+        prog = cu.CudaProgram(b["regexes_b"], b["flags"], multi=b["multi"])
+        s = b["subject_b"]
+        pitch = max(16, (len(s) + 15) // 16 * 16)
+        buf = torch.zeros(pitch, dtype=torch.uint8)
+        if s:
+            buf[: len(s)] = torch.frombuffer(bytearray(s), dtype=torch.uint8)
+        rc, ov = prog.pike_lines(buf.cuda(), 1, pitch, len(s))
+        want_rc, want_ov = b["pike"]["rc"], b["pike"]["ov"]
+        got_ov = ov[0].tolist() if want_rc >= 0 else None
+        if int(rc[0]) != want_rc or got_ov != want_ov:
+            bad.append((b["file"], b["name"], int(rc[0]), got_ov, want_rc, want_ov))
+        prog.program.close()
+    assert not bad, bad[:5]
+
+
 @pytest.mark.parametrize("nlines,linelen,pitch", [(4096, 1024, 1024), (1000, 1000, 1008), (33, 17, 32),
                                                   (5, 0, 16), (257, 63, 64), (64, 129, 144)])
 def test_thompson_tiers_vs_oracle(cu, nlines, linelen, pitch):

@@ -1,0 +1,87 @@
+"""CPU tier: the product's lowering pass (sregex_b200/csrc/lower), executed by
+the test-only host executor oracle/lower_check.cpp, against the reference's
+golden vectors -- before and independently of any kernel."""
+import ctypes as C
+import os
+
+import pytest
+
+from conftest import runnable
+from sregex_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lc():
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "liblowercheck.so"))
+    lib.lc_create.restype = C.c_void_p
+    lib.lc_create.argtypes = [C.c_void_p, C.c_uint]
+    lib.lc_destroy.argtypes = [C.c_void_p]
+    lib.lc_reset.argtypes = [C.c_void_p]
+    lib.lc_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint)]
+    lib.lc_nfa_exec.restype = C.c_long
+    lib.lc_nfa_exec.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_uint]
+    lib.lc_dfa_exec.restype = C.c_long
+    lib.lc_dfa_exec.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_uint, C.c_int]
+    lib.lc_hint.restype = C.c_long
+    lib.lc_hint.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    return lib
+
+
+def _stream(fn, chunks):
+    out = []
+    for chunk, eof in chunks:
+        rc = fn(chunk, len(chunk), int(eof))
+        out.append(rc)
+        if rc != capi.SRE_AGAIN:
+            break
+    return out
+
+
+def test_lowered_tables_against_golden(golden, oracle, lc):
+    """NFA tables, DFA (class table and byte table): single buffer verdicts and
+    the rc sequence under 1-byte chunks (exact SRE_OK timing)."""
+    ndfa = 0
+    for b in runnable(golden):
+        p = oracle.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        h = lc.lc_create(p.prog, 4096)
+        assert h
+        s = b["subject_b"]
+        info = (C.c_uint * 6)()
+        lc.lc_info(h, info)
+        tag = (b["file"], b["name"])
+        assert lc.lc_nfa_exec(h, s, len(s), 1) == b["thompson"], tag
+        lc.lc_reset(h)
+        assert _stream(lambda c, n, e: lc.lc_nfa_exec(h, c, n, e), capi.split_chunks(s)) == b["thompson_split"], tag
+        if info[3]:
+            ndfa += 1
+            for t256 in (0, 1):
+                lc.lc_reset(h)
+                assert lc.lc_dfa_exec(h, s, len(s), 1, t256) == b["thompson"], tag
+            lc.lc_reset(h)
+            assert _stream(lambda c, n, e: lc.lc_dfa_exec(h, c, n, e, 1), capi.split_chunks(s)) == b["thompson_split"], tag
+        lc.lc_destroy(h)
+        p.close()
+    assert ndfa >= 1900
+
+
+def test_pike_start_hint_never_passes_the_match_start(golden, oracle, lc):
+    """The restart hint (offset after the last byte that only the `.*?` thread
+    consumed, frozen once the automaton is in its absorbing ACC state, whose row
+    carries no flags) must be <= the start of the leftmost-first match the
+    reference's Pike VM reports, for every matching block of the corpus."""
+    checked = 0
+    for b in runnable(golden):
+        if b["pike"]["rc"] < 0:
+            continue
+        p = oracle.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        h = lc.lc_create(p.prog, 4096)
+        s = b["subject_b"]
+        hint = lc.lc_hint(h, s, len(s))
+        if hint >= 0:
+            assert hint <= b["pike"]["ov"][0], (b["file"], b["name"], hint, b["pike"]["ov"])
+            checked += 1
+        lc.lc_destroy(h)
+        p.close()
+    assert checked > 1000
