@@ -99,3 +99,19 @@ def log_lines(n: int, pitch: int = 1024, device="cpu", seed: int = 0x5EED, first
     pad = cols[None, :] >= end[:, None]
     lines[pad] = ord(".")
     return lines
+
+
+def multi_pattern_set(n: int = 64):
+    """BASELINE config 4: a set of n patterns for sre_regex_parse_multi --
+    4 families x 16 keywords: literal keywords followed by
+    digits, request lines, status codes, and keyword pairs with a gap."""
+    words = ["alpha", "bravo", "charlie", "delta", "echo", "foxtrot", "golf", "hotel", "india", "juliet",
+             "kilo", "lima", "mike", "november", "oscar", "papa"]
+    methods = ["GET", "POST", "PUT", "HEAD"]
+    pats = []
+    for i, w in enumerate(words):
+        pats.append(rb"%s\d+" % w.encode())                                   # keyword + digits
+        pats.append(rb"%s /x/%d\d* HTTP/1\.[01]" % (methods[i % 4].encode(), i % 10))   # request lines
+        pats.append(rb'" 5%02d ' % (i * 6))                                    # specific 5xx status
+        pats.append(rb"%s[a-z]{0,3}%s" % (w[:3].encode(), words[(i + 5) % 16][:2].encode()))  # pair with a gap
+    return pats[:n]

@@ -201,6 +201,24 @@ int upload(sre_cuda_program_t *cp)
     const size_t o_ranges = b.add(prog->ranges, (size_t) prog->nranges * 2);
     const size_t o_leading = b.add(prog->leading, (size_t) prog->nleading * 4);
     const size_t o_slots = b.add(slot_ofs.data(), slot_ofs.size() * 4);
+    /* the regex whose code region holds a pc: regions end at their MATCH */
+    std::vector<uint16_t> pc_regex(prog->len + 1, 0);
+    uint32_t max_slots = 2;
+    {
+        uint32_t r = 0;
+        for (uint32_t pc = 0; pc < prog->len; pc++) {
+            pc_regex[pc] = (uint16_t) (r < prog->nregexes ? r : prog->nregexes - 1);
+            if (prog->insts[pc].opcode == SRE_OPCODE_MATCH) {
+                r++;
+            }
+        }
+        for (sre_uint_t i = 0; i < prog->nregexes; i++) {
+            if (slot_ofs[i + 1] - slot_ofs[i] > max_slots) {
+                max_slots = slot_ofs[i + 1] - slot_ofs[i];
+            }
+        }
+    }
+    const size_t o_pcre = b.add(pc_regex.data(), pc_regex.size() * 2);
 
     if (cudaMalloc(&cp->d_blob, b.bytes.size() + 256) != cudaSuccess
         || cudaMemcpy(cp->d_blob, b.bytes.data(), b.bytes.size(), cudaMemcpyHostToDevice) != cudaSuccess)
@@ -249,9 +267,11 @@ int upload(sre_cuda_program_t *cp)
     pk.ranges = base + o_ranges;
     pk.leading = reinterpret_cast<const int32_t *>(base + o_leading);
     pk.slot_ofs = reinterpret_cast<const uint32_t *>(base + o_slots);
+    pk.pc_regex = reinterpret_cast<const uint16_t *>(base + o_pcre);
+    pk.max_slots = max_slots;
     pk.max_threads = 2 * prog->len + 16;
     pk.stack_cap = 2 * prog->len + 8;
-    pk.ctx_stride = (sre_pike_ctx_bytes(pk.len, pk.nslots, pk.max_threads, pk.stack_cap) + 255)
+    pk.ctx_stride = (sre_pike_ctx_bytes(pk.len, pk.nslots, pk.max_slots, pk.max_threads, pk.stack_cap) + 255)
                     & ~(uint64_t) 255;
     return SRE_OK;
 }

@@ -57,6 +57,8 @@ struct sre_dev_pike_t {
     const uint8_t           *ranges;        /* (from,to) pairs                */
     const int32_t           *leading;       /* pcs of leading instructions    */
     const uint32_t          *slot_ofs;      /* [nregexes+1] first slot        */
+    const uint16_t          *pc_regex;      /* [len] regex that owns the pc   */
+    uint32_t                 max_slots;     /* slots of the largest regex     */
     uint32_t                 max_threads;   /* thread pool entries per ctx    */
     uint32_t                 stack_cap;     /* DFS stack entries per ctx      */
     uint64_t                 ctx_stride;    /* bytes of scratch per ctx       */
@@ -128,6 +130,7 @@ cudaError_t sre_launch_dfa_stream_locate(const sre_dev_dfa_t &dfa, const uint8_t
     cudaStream_t stream, int *launches);
 uint32_t sre_stream_fan(void);
 uint32_t sre_stream_fn_stride(uint32_t nstates);
-size_t sre_pike_ctx_bytes(uint32_t len, uint32_t nslots, uint32_t nthreads, uint32_t stack_cap);
+size_t sre_pike_ctx_bytes(uint32_t len, uint32_t nslots, uint32_t max_slots, uint32_t nthreads,
+    uint32_t stack_cap);
 
 #endif

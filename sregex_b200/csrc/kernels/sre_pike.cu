@@ -18,7 +18,10 @@
  *   - add_thread's recursion is an explicit DFS stack with an undo log for the
  *     SAVE slots, which gives each branch of a SPLIT the captures the reference
  *     gives it through copy-on-write;
- *   - every list thread owns a private copy of its capture slots.
+ *   - every list thread owns a private copy of the capture slots of the regex
+ *     its pc belongs to (a thread inside regex i of a multi-regex set can only
+ *     have written regex i's slots; all others are -1 by construction), so a
+ *     thread costs max_slots instead of nslots values.
  * All context state lives in one block of global memory, so the same routine
  * serves the batch entry points (context re-initialised per line) and the
  * streaming sre_vm_pike_exec (context persists between calls).
@@ -71,8 +74,8 @@ struct pike_ctx_t {
     stack_ent_t  *stk;
 };
 
-__host__ __device__ inline size_t pike_ctx_bytes(uint32_t len, uint32_t nslots, uint32_t nthreads,
-                                                 uint32_t stack_cap)
+__host__ __device__ inline size_t pike_ctx_bytes(uint32_t len, uint32_t nslots, uint32_t max_slots,
+                                                 uint32_t nthreads, uint32_t stack_cap)
 {
     size_t n = a16(sizeof(pike_hdr_t));
     n += a16((size_t) (len + 1) * 4);       /* tags      */
@@ -80,7 +83,7 @@ __host__ __device__ inline size_t pike_ctx_bytes(uint32_t len, uint32_t nslots, 
     n += a16((size_t) nslots * 8) * 2;      /* matched, cap */
     n += a16((size_t) nthreads * 4) * 2;    /* t_pc, t_next */
     n += a16(nthreads);                     /* t_sw      */
-    n += a16((size_t) nthreads * nslots * 8);
+    n += a16((size_t) nthreads * max_slots * 8);
     n += a16((size_t) stack_cap * sizeof(stack_ent_t));
     return n;
 }
@@ -97,7 +100,7 @@ __device__ inline pike_ctx_t pike_carve(const sre_dev_pike_t &pk, uint8_t *base)
     c.t_pc = reinterpret_cast<int32_t *>(p);        p += a16((size_t) pk.max_threads * 4);
     c.t_next = reinterpret_cast<int32_t *>(p);      p += a16((size_t) pk.max_threads * 4);
     c.t_sw = p;                                     p += a16(pk.max_threads);
-    c.t_cap = reinterpret_cast<int64_t *>(p);       p += a16((size_t) pk.max_threads * pk.nslots * 8);
+    c.t_cap = reinterpret_cast<int64_t *>(p);       p += a16((size_t) pk.max_threads * pk.max_slots * 8);
     c.stk = reinterpret_cast<stack_ent_t *>(p);
     return c;
 }
@@ -166,6 +169,37 @@ __device__ inline void list_clear(pike_ctx_t &c, int l)
     }
     h->head[l] = h->tail[l] = -1;
     h->count[l] = 0;
+}
+
+/* working capture <- thread t's slots (everything else is -1 already) */
+__device__ inline void cap_load(const sre_dev_pike_t &pk, pike_ctx_t &c, int32_t t, uint32_t *base_out,
+                                uint32_t *cnt_out)
+{
+    const uint32_t r = pk.pc_regex[c.t_pc[t]], base = pk.slot_ofs[r];
+    const uint32_t cnt = pk.slot_ofs[r + 1] - base;
+    const int64_t *src = c.t_cap + (size_t) t * pk.max_slots;
+    for (uint32_t i = 0; i < cnt; i++) {
+        c.cap[base + i] = src[i];
+    }
+    *base_out = base;
+    *cnt_out = cnt;
+}
+
+__device__ inline void cap_clear(pike_ctx_t &c, uint32_t base, uint32_t cnt)
+{
+    for (uint32_t i = 0; i < cnt; i++) {
+        c.cap[base + i] = -1;
+    }
+}
+
+/* slot g of thread t's full capture vector */
+__device__ inline int64_t thread_slot(const sre_dev_pike_t &pk, const pike_ctx_t &c, int32_t t, uint32_t g)
+{
+    const uint32_t r = pk.pc_regex[c.t_pc[t]], base = pk.slot_ofs[r];
+    if (g < base || g >= pk.slot_ofs[r + 1]) {
+        return -1;
+    }
+    return c.t_cap[(size_t) t * pk.max_slots + (g - base)];
 }
 
 /* a temporary list used by assertion_hold */
@@ -307,9 +341,14 @@ __device__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, t
                 c.t_pc[t] = pc;
                 c.t_sw[t] = (uint8_t) seen_word;
                 c.t_next[t] = -1;
-                int64_t *dst = c.t_cap + (size_t) t * pk.nslots;
-                for (uint32_t i = 0; i < pk.nslots; i++) {
-                    dst[i] = c.cap[i];
+                {
+                    /* only the owning regex's slots can be set (see header) */
+                    const uint32_t r = pk.pc_regex[pc], base = pk.slot_ofs[r];
+                    const uint32_t cnt = pk.slot_ofs[r + 1] - base;
+                    int64_t *dst = c.t_cap + (size_t) t * pk.max_slots;
+                    for (uint32_t i = 0; i < cnt; i++) {
+                        dst[i] = c.cap[base + i];
+                    }
                 }
                 if (l >= 0) {
                     if (h->head[l] < 0) {
@@ -486,8 +525,8 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
 
             const int32_t pc = c.t_pc[t];
             const sre_dev_inst_t in = pk.insts[pc];
-            const int64_t *tcap = c.t_cap + (size_t) t * pk.nslots;
             bool got_match = false;
+            uint32_t cbase = 0, ccnt = 0;
 
             if (in.opcode == OP_ASSERT) {           /* :449-528 */
                 const bool seen_word = c.t_sw[t] || (sp == 0 && h->seen_word);
@@ -500,9 +539,7 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
                 default: break;
                 }
                 if (hold) {
-                    for (uint32_t i = 0; i < pk.nslots; i++) {
-                        c.cap[i] = tcap[i];
-                    }
+                    cap_load(pk, c, t, &cbase, &ccnt);
                     tmp_list_t tl = { -1, -1, 0 };
                     h->tag--;
                     rc = pike_add_thread(pk, c, -1, &tl, pc + 1, sp, input, false);
@@ -519,19 +556,21 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
                         h->count[cl] += tl.count;
                     }
                     h->tag++;
+                    cap_clear(c, cbase, ccnt);
                 }
             } else if (in.opcode == OP_MATCH) {     /* :530-553 */
-                h->last_matched_pos = tcap[1];
+                cap_load(pk, c, t, &cbase, &ccnt);
+                h->last_matched_pos = c.cap[1];
                 for (uint32_t i = 0; i < pk.nslots; i++) {
-                    c.matched[i] = tcap[i];
+                    c.matched[i] = c.cap[i];
                 }
                 h->matched_id = in.v;
                 got_match = true;
+                cap_clear(c, cbase, ccnt);
             } else if (!at_end && consumes(pk, in, byte)) {
-                for (uint32_t i = 0; i < pk.nslots; i++) {
-                    c.cap[i] = tcap[i];
-                }
+                cap_load(pk, c, t, &cbase, &ccnt);
                 rc = pike_add_thread(pk, c, nl, nullptr, pc + 1, sp + 1, input, true);
+                cap_clear(c, cbase, ccnt);
                 if (rc == RC_DONE) {
                     got_match = true;
                 } else if (rc != SRE_K_OK) {
@@ -606,13 +645,12 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
         ovector[1] = -1;
     }
     for (int32_t t = h->head[cl]; t >= 0; t = c.t_next[t]) {
-        const int64_t *tcap = c.t_cap + (size_t) t * pk.nslots;
         for (uint32_t i = 0; i < pk.nregexes; i++) {
-            const int64_t b0 = tcap[pk.slot_ofs[i]];
+            const int64_t b0 = thread_slot(pk, c, t, pk.slot_ofs[i]);
             if (b0 != -1 && (ovector[0] == -1 || b0 < ovector[0])) {
                 ovector[0] = b0;
             }
-            const int64_t b1 = tcap[1];
+            const int64_t b1 = thread_slot(pk, c, t, 1);
             if (ovec_slots > 1 && b1 != -1 && (ovector[1] == -1 || b1 > ovector[1])) {
                 ovector[1] = b1;
             }
@@ -696,9 +734,10 @@ __global__ void k_pike_stream(sre_dev_pike_t pk, uint8_t *ctx, const uint8_t *bu
 
 }  // namespace
 
-size_t sre_pike_ctx_bytes(uint32_t len, uint32_t nslots, uint32_t nthreads, uint32_t stack_cap)
+size_t sre_pike_ctx_bytes(uint32_t len, uint32_t nslots, uint32_t max_slots, uint32_t nthreads,
+    uint32_t stack_cap)
 {
-    return pike_ctx_bytes(len, nslots, nthreads, stack_cap);
+    return pike_ctx_bytes(len, nslots, max_slots, nthreads, stack_cap);
 }
 
 cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,

@@ -191,6 +191,29 @@ def test_multi_regex_id_vs_oracle(cu):
     assert len(set(want_rc.tolist())) > 3   # several different patterns win
 
 
+def test_multi_regex_64_patterns_vs_oracle(cu):
+    """BASELINE config 4 at test size: a 64-pattern sre_regex_parse_multi set;
+    Thompson verdict, matched regex id and ovector against the oracle."""
+    pats = corpus.multi_pattern_set(64)
+    n = 384
+    lines = corpus.log_lines(n, 1024)
+    prog = cu.CudaProgram(pats)
+    assert prog.info.nregexes == 64 and prog.info.nfa_states > 500
+    which = "ref" if baseline.available("ref") else "oracle"
+    _, want_rc, want_ov = baseline.run_lines(which, pats, None, lines.numpy(), n, 1024, 1024,
+                                             baseline.ENGINE_PIKE, nthreads=8, ovec_slots=prog.nslots)
+    dev = lines.cuda()
+    for engine in (cu.ENGINE_AUTO, cu.ENGINE_NFA):
+        sel = prog.thompson_lines(dev, n, 1024, 1024, engine=engine)
+        assert ((sel.cpu().numpy() == 0) == (want_rc >= 0)).all(), engine
+    rc, ov = prog.pike_lines(dev, n, 1024, 1024, select=sel)
+    assert (rc.cpu().numpy() == want_rc).all()
+    assert (ov.cpu().numpy() == want_ov).all()
+    rc2, ov2 = prog.pike_lines(dev, n, 1024, 1024)          # internal gate
+    assert torch.equal(rc, rc2) and torch.equal(ov, ov2)
+    assert len(set(want_rc.tolist())) > 8
+
+
 def test_stream_scan_vs_oracle(cu):
     """bench/gen-data.pl buffer (scaled down) fed in chunks: same rc sequence as
     the oracle's sre_vm_thompson_exec with SRE_AGAIN carry."""
