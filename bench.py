@@ -149,6 +149,8 @@ def main():
     ap.add_argument("--variant", type=int, default=int(os.environ.get("SRE_VARIANT", "0")))
     ap.add_argument("--lines", type=int, default=NLINES)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--l2promo", type=int, default=-1, help="TMA L2 promotion 0..3 (-1: library default)")
+    ap.add_argument("--engine", default="auto", choices=["auto", "tiled", "skip", "generic", "nfa"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -177,11 +179,20 @@ def main():
         dev[i:i + m] = corpus.log_lines(m, PITCH, device="cuda", first_line=rank * n + i)
     prog = cuda.CudaProgram(corpus.C2_REGEX)
     cuda.set_variant(args.variant)
+    if args.l2promo >= 0:
+        cuda.lib().L.sre_cuda_set_l2_promotion(args.l2promo)
     rc = torch.empty(n, dtype=torch.int32, device="cuda")
     info = prog.info
 
+    engine = {"auto": cuda.ENGINE_AUTO, "tiled": cuda.ENGINE_DFA_TILED, "skip": cuda.ENGINE_DFA_SKIP,
+              "generic": cuda.ENGINE_DFA_GENERIC, "nfa": cuda.ENGINE_NFA}[args.engine]
+    engine_name = args.engine
+    if engine_name == "auto":
+        engine_name = ("nfa" if not info.dfa_states else
+                       "dfa_skip" if 1 <= info.dfa_leave_bytes <= 2 else "dfa_tiled")
+
     def step():
-        prog.thompson_lines(dev, n, PITCH, PITCH, engine=cuda.ENGINE_AUTO, out=rc)
+        prog.thompson_lines(dev, n, PITCH, PITCH, engine=engine, out=rc)
 
     def barrier():
         if world > 1:
@@ -235,7 +246,7 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("k_dfa_lines_bytes_per_launch")
+            traffic = json.load(open(tp)).get("bytes_per_launch")
         except Exception:
             traffic = None
 
@@ -246,13 +257,15 @@ def main():
         "config": {
             "workload": "C2: Thompson boolean, regex " + REGEX_NAME + ", 1,048,576 x 1 KB log lines per GPU",
             "lines_per_gpu": n, "line_bytes": PITCH, "sharding": f"lines x {world} ranks, no data-path collective",
-            "engine": "dfa_tiled" if info.dfa_states else "nfa", "dfa_states": info.dfa_states,
+            "engine": engine_name, "dfa_states": info.dfa_states,
             "nfa_states": info.nfa_states, "variant": args.variant,
             "l2_policy": "input (1 GiB per GPU) larger than L2 (126 MB); no flush needed",
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "k_dfa_lines", "kernel_ms": kern_ms, "algorithmic_bytes": algo_bytes},
+                     "kernel": {"dfa_skip": "k_dfa_lines_skipw", "dfa_tiled": "k_dfa_lines_tma_early"}.get(
+                         engine_name, engine_name),
+                     "kernel_ms": kern_ms, "algorithmic_bytes": algo_bytes},
         "gpu_launches": launches,
         "clocks": sampler.result(),
         "hits": int(hits.item()),

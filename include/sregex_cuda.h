@@ -28,7 +28,9 @@ enum {
     SRE_CUDA_ENGINE_AUTO        = 0,    /* best tier available                       */
     SRE_CUDA_ENGINE_DFA_TILED   = 1,    /* smem-staged thread-per-line DFA           */
     SRE_CUDA_ENGINE_DFA_GENERIC = 2,    /* thread-per-line DFA, any alignment        */
-    SRE_CUDA_ENGINE_NFA         = 3     /* warp-per-line bit-parallel NFA            */
+    SRE_CUDA_ENGINE_NFA         = 3,    /* warp-per-line bit-parallel NFA            */
+    SRE_CUDA_ENGINE_DFA_SKIP    = 4     /* DFA_TILED + first-byte skip (start state
+                                           left by <= 4 byte values)                 */
 };
 
 typedef struct {
@@ -40,6 +42,7 @@ typedef struct {
     uint32_t  dfa_states;       /* 0: subset construction gave up                   */
     uint32_t  dfa_classes;
     uint32_t  dfa_byte_table;   /* 1: [state][byte] u8 table (<= 256 states)        */
+    uint32_t  dfa_leave_bytes;  /* byte values leaving the start state (1..4), else 0 */
     uint32_t  nregexes;
     uint32_t  pike_slots;       /* capture slots of the whole set                   */
     uint64_t  pike_ctx_bytes;   /* device scratch per concurrent Pike context       */
@@ -124,6 +127,7 @@ SRE_API int sre_cuda_pike_exec_lines_host(sre_cuda_program_t *cp,
 
 /* Tuning / introspection */
 SRE_API void sre_cuda_set_variant(int variant);     /* tile shape of DFA_TILED   */
+SRE_API void sre_cuda_set_l2_promotion(int mode);   /* TMA L2 promotion: 0..3    */
 SRE_API long sre_cuda_launch_count(int reset);      /* kernels launched so far   */
 SRE_API int sre_cuda_device_available(void);        /* 1 if a CUDA device works  */
 SRE_API const char *sre_cuda_last_error(void);

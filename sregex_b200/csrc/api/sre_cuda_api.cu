@@ -21,6 +21,12 @@
 #include "../kernels/sre_kernels.cuh"
 #include "../lower/sre_lower.h"
 
+/* measurement aid: pure TMA streaming of a line corpus (no automaton) */
+cudaError_t sre_launch_tma_ceiling(const uint8_t *buf, size_t nlines, size_t pitch, size_t linelen,
+    int32_t *rc, int variant, cudaStream_t stream);
+
+void sre_dev_set_l2_promotion(int mode);
+
 namespace {
 
 std::atomic<long>   g_launches(0);
@@ -90,6 +96,9 @@ struct sre_cuda_program_s {
     sre_dev_nfa_t       nfa;
     sre_dev_pike_t      pike;
     uint32_t            nfa_shift = 0;
+    /* byte values that leave the DFA start state (skip-scan tier), <= 4 kept */
+    int                 nleave = 0;             /* -1: more than 4               */
+    uint32_t            leave_pats[4] = { 0, 0, 0, 0 };
     /* lazily grown workspaces */
     uint8_t            *pike_scratch = nullptr;
     size_t              pike_nctx = 0;
@@ -238,6 +247,23 @@ int upload(sre_cuda_program_t *cp)
         cp->dfa.clsmap = base + o_dcls;
         cp->dfa.fin = base + o_fin;
         cp->dfa.h256 = d.h256.empty() ? nullptr : base + o_h256;
+        cp->nleave = 0;
+        if (!d.t256.empty()) {
+            for (unsigned bv = 0; bv < 256 && cp->nleave >= 0; bv++) {
+                if (d.t256[(size_t) d.start * 256 + bv] != d.start) {
+                    if (cp->nleave == 4) {
+                        cp->nleave = -1;
+                    } else {
+                        cp->leave_pats[cp->nleave++] = bv * 0x01010101u;
+                    }
+                }
+            }
+            for (int i = cp->nleave > 0 ? cp->nleave : 0; i < 4 && cp->nleave > 0; i++) {
+                cp->leave_pats[i] = cp->leave_pats[0];
+            }
+        } else {
+            cp->nleave = -1;
+        }
     }
     if (cp->has_nfa) {
         cp->nfa.nstates = n.nstates;
@@ -288,16 +314,26 @@ int thompson_dispatch(sre_cuda_program_t *cp, const uint8_t *dev_buf, const int6
                          && (pitch & 15) == 0 && linelen <= pitch && linelen < (1ull << 31);
 
     if (engine == SRE_CUDA_ENGINE_AUTO) {
-        engine = cp->has_dfa ? (aligned ? SRE_CUDA_ENGINE_DFA_TILED : SRE_CUDA_ENGINE_DFA_GENERIC)
-                             : SRE_CUDA_ENGINE_NFA;
+        engine = !cp->has_dfa ? SRE_CUDA_ENGINE_NFA
+               : !aligned ? SRE_CUDA_ENGINE_DFA_GENERIC
+               : (cp->nleave >= 1 && cp->nleave <= 2 && linelen >= 128) ? SRE_CUDA_ENGINE_DFA_SKIP
+               : SRE_CUDA_ENGINE_DFA_TILED;
     }
     switch (engine) {
+    case SRE_CUDA_ENGINE_DFA_SKIP:
+        if (!cp->has_dfa || !aligned || cp->nleave < 1) {
+            return fail("DFA_SKIP engine needs a byte-table DFA whose start state is left by 1..4 byte "
+                        "values, and 16-byte aligned fixed-pitch lines");
+        }
+        err = sre_launch_dfa_lines_skip(cp->dfa, dev_buf, nlines, pitch, linelen, dev_rc, cp->leave_pats,
+                                        cp->nleave, g_variant, st, &launches);
+        break;
     case SRE_CUDA_ENGINE_DFA_TILED:
         if (!cp->has_dfa || !aligned) {
             return fail("DFA_TILED engine needs a DFA and 16-byte aligned fixed-pitch lines");
         }
-        err = sre_launch_dfa_lines(cp->dfa, dev_buf, nlines, pitch, linelen, dev_rc, g_variant, st,
-                                   &launches);
+        err = sre_launch_dfa_lines(cp->dfa, dev_buf, nlines, pitch, linelen, dev_rc,
+                                   g_variant >= 30 ? 0 : g_variant, st, &launches);
         if (err == cudaErrorInvalidConfiguration) {
             /* table too large for shared memory next to the staging rings */
             err = sre_launch_dfa_ragged(cp->dfa, dev_buf, dev_offsets, nlines, pitch, linelen, dev_rc,
@@ -410,6 +446,7 @@ extern "C" {
 SRE_API int sre_cuda_device_available(void) { return device_ok() ? 1 : 0; }
 SRE_API const char *sre_cuda_last_error(void) { return g_err; }
 SRE_API void sre_cuda_set_variant(int variant) { g_variant = variant; }
+SRE_API void sre_cuda_set_l2_promotion(int mode) { sre_dev_set_l2_promotion(mode); }
 
 SRE_API long sre_cuda_launch_count(int reset)
 {
@@ -464,6 +501,7 @@ sre_cuda_program_info(sre_cuda_program_t *cp, sre_cuda_info_t *info)
     info->dfa_states = cp->has_dfa ? cp->low.dfa.nstates : 0;
     info->dfa_classes = cp->has_dfa ? cp->low.dfa.nclasses : 0;
     info->dfa_byte_table = cp->has_dfa && cp->dfa.t256 != nullptr;
+    info->dfa_leave_bytes = cp->has_dfa && cp->nleave > 0 ? (uint32_t) cp->nleave : 0;
     info->nregexes = (uint32_t) cp->prog->nregexes;
     info->pike_slots = cp->pike.nslots;
     info->pike_ctx_bytes = cp->pike.ctx_stride;
@@ -690,6 +728,16 @@ sre_cuda_thompson_exec_stream(sre_cuda_program_t *cp, const uint8_t *dev_buf, si
         return SRE_DECLINED;
     }
     return SRE_AGAIN;
+}
+
+SRE_API int
+sre_cuda_tma_ceiling(const uint8_t *dev_buf, size_t nlines, size_t pitch, size_t linelen, int32_t *dev_rc,
+    int variant, void *stream)
+{
+    cudaError_t err = sre_launch_tma_ceiling(dev_buf, nlines, pitch, linelen, dev_rc, variant,
+                                             as_stream(stream));
+    count_launches(1);
+    return err == cudaSuccess ? SRE_OK : fail("ceiling kernel: %s", cudaGetErrorString(err));
 }
 
 SRE_API int

@@ -92,6 +92,12 @@ cudaError_t sre_launch_dfa_carry(const sre_dev_dfa_t &dfa, const uint8_t *buf,
     uint32_t *state_io, int from_init, int eof, int32_t *rc,
     cudaStream_t stream, int *launches);
 
+/* skip-scan flavour: start state left by <= 4 byte values (pats: each value
+ * replicated into the 4 bytes of a word)                                       */
+cudaError_t sre_launch_dfa_lines_skip(const sre_dev_dfa_t &dfa, const uint8_t *buf,
+    size_t nlines, size_t pitch, size_t linelen, int32_t *rc, const uint32_t *pats,
+    int npat, int variant, cudaStream_t stream, int *launches);
+
 /* Thompson verdict + Pike start hint per line (needs dfa.h256, aligned lines):
  * hint[i] = offset after which no earlier-started thread is alive             */
 cudaError_t sre_launch_dfa_lines_hint(const sre_dev_dfa_t &dfa, const uint8_t *buf,

@@ -170,6 +170,280 @@ k_dfa_lines_tma_early(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tma
                                     (size_t) gridDim.x * warps_per_block);
 }
 
+/* ---- k_dfa_lines_skipw ------------------------------------------------------ */
+
+/*
+ * Word-skip flavour of the early-release kernel, for automata whose start
+ * state is left by <= 4 byte values: per 4-byte word every lane tests (3 ALU
+ * ops per byte value) whether the word holds a leave byte; if NO lane of the
+ * warp is inside a partial match and NO lane's word holds a leave byte, the
+ * four table look-ups of that word are skipped for the whole warp (a
+ * warp-uniform branch, no divergence).  T[start][b] == start for every skipped
+ * byte and ACC is absorbing, so the result is identical to k_dfa_lines.  On log
+ * text this removes more than half of the LDS.U8 look-ups that bound
+ * k_dfa_lines_tma_early (shared-memory pipe 90 % busy, profiles/).
+ */
+template <int NPAT>
+struct skipw_consumer_t {
+    step256_t       st256;
+    const uint8_t  *fin;
+    uint32_t        start, acc, s;
+    uint32_t        pat[4];
+    size_t          nlines;
+    int32_t        *rc;
+
+    __device__ __forceinline__ void begin() { s = start; }
+    __device__ __forceinline__ void word(uint32_t w)
+    {
+        uint32_t h = 0;
+#pragma unroll
+        for (int p = 0; p < NPAT; p++) {
+            const uint32_t x = w ^ pat[p];
+            h |= (x - 0x01010101u) & ~x & 0x80808080u;     /* some byte of x is zero */
+        }
+        const bool need = (s != acc) && ((s != start) || h != 0);
+        if (__any_sync(0xffffffffu, need)) {
+            s = st256.word(s, w);
+        }
+    }
+    __device__ __forceinline__ void chunk(const uint4 &v)
+    {
+        word(v.x);
+        word(v.y);
+        word(v.z);
+        word(v.w);
+    }
+    __device__ __forceinline__ void byte(uint32_t b) { s = st256.byte(s, b); }
+    __device__ __forceinline__ void end(size_t group)
+    {
+        const size_t line = group * 32 + (threadIdx.x & 31);
+        if (line < nlines) {
+            rc[line] = (s == acc || fin[s]) ? SRE_K_OK : SRE_K_DECLINED;
+        }
+    }
+};
+
+template <int STAGES, int NPAT, int THREADS, int BLOCKS>
+__global__ void __launch_bounds__(THREADS, BLOCKS)
+k_dfa_lines_skipw(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t nlines,
+                  uint32_t linelen, uint4 pats, int32_t *__restrict__ rc)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, false);
+    load_table(smem, dfa.t256, plan.tab_bytes);
+    load_table(smem + plan.fin_ofs, dfa.fin, align_up(dfa.nstates, 16));
+    __syncthreads();
+
+    const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    skipw_consumer_t<NPAT> cons;
+    cons.st256.tab = smem;
+    cons.fin = smem + plan.fin_ofs;
+    cons.start = dfa.start;
+    cons.acc = dfa.acc;
+    cons.pat[0] = pats.x;
+    cons.pat[1] = pats.y;
+    cons.pat[2] = pats.z;
+    cons.pat[3] = pats.w;
+    cons.nlines = nlines;
+    cons.rc = rc;
+    tile_pipeline_tma_early<STAGES>(cons, &tmap, nlines, linelen,
+                                    smem + plan.stage_ofs + (size_t) warp * STAGES * 32 * 128,
+                                    reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES,
+                                    (size_t) blockIdx.x * warps_per_block + warp,
+                                    (size_t) gridDim.x * warps_per_block);
+}
+
+/* ---- k_tma_ceiling (measurement aid) ----------------------------------------- */
+
+/* The same TMA tile pipeline with a consumer that only XORs the bytes: the
+ * memory-side ceiling of this access pattern (boxes of 32 rows x 128 B, one row
+ * per line), to tell how much of the gap to the HBM peak is the automaton's. */
+struct null_consumer_t {
+    uint32_t  x;
+    int32_t  *rc;
+    size_t    nlines;
+    __device__ __forceinline__ void begin() { x = 0; }
+    __device__ __forceinline__ void chunk(const uint4 &v) { x ^= v.x ^ v.y ^ v.z ^ v.w; }
+    __device__ __forceinline__ void byte(uint32_t b) { x ^= b; }
+    __device__ __forceinline__ void end(size_t group)
+    {
+        const size_t line = group * 32 + (threadIdx.x & 31);
+        if (line < nlines) {
+            rc[line] = (int32_t) x;
+        }
+    }
+};
+
+template <int STAGES, int THREADS, bool EARLY>
+__global__ void __launch_bounds__(THREADS, 1)
+k_tma_ceiling(const __grid_constant__ CUtensorMap tmap, size_t nlines, uint32_t linelen, int32_t *rc)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    null_consumer_t cons;
+    cons.rc = rc;
+    cons.nlines = nlines;
+    uint8_t *stage = smem + 2048 + (size_t) warp * STAGES * 32 * 128;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem) + warp * MAX_STAGES;
+    if (EARLY) {
+        tile_pipeline_tma_early<STAGES>(cons, &tmap, nlines, linelen, stage, bars,
+                                        (size_t) blockIdx.x * warps_per_block + warp,
+                                        (size_t) gridDim.x * warps_per_block);
+    } else {
+        tile_pipeline_tma<128, STAGES>(cons, &tmap, nlines, linelen, stage, bars,
+                                       (size_t) blockIdx.x * warps_per_block + warp,
+                                       (size_t) gridDim.x * warps_per_block);
+    }
+}
+
+/* ---- k_dfa_lines_skip ------------------------------------------------------ */
+
+/*
+ * Skip-scan flavour for automata whose start state is left by at most 4
+ * distinct byte values (a literal-prefixed regex: /HTTP.../ leaves on 'H'
+ * only).  While a line is in the start state, bytes outside that set cannot
+ * change anything, so the lane does not look them up: phase 1 marks which of
+ * the 32 words of its 128-byte row contain a leave byte (3 ALU ops per word and
+ * byte value, no shared-memory traffic beyond the LDS.128 of the row); phase 2
+ * walks the table only from marked words until the automaton is back in the
+ * start state.  This is the reference's first-byte prefilter
+ * (sre_vm_pike_find_first_byte, sre_vm_pike.c:992-1061) applied to the
+ * Thompson path; results are identical to k_dfa_lines because T[start][b] ==
+ * start for every skipped byte.  It removes most of the per-byte LDS.U8
+ * look-ups that bound k_dfa_lines (see profiles/), leaving HBM as the limit.
+ */
+template <int STAGES, int NPAT, int THREADS, int BLOCKS>
+__global__ void __launch_bounds__(THREADS, BLOCKS)
+k_dfa_lines_skip(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t nlines,
+                 uint32_t linelen, uint4 pats, int32_t *__restrict__ rc)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int TW = 128, STAGE_BYTES = 32 * TW;
+    const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, false);
+    const uint8_t *tab = smem, *fin = smem + plan.fin_ofs;
+    load_table(smem, dfa.t256, plan.tab_bytes);
+    load_table(smem + plan.fin_ofs, dfa.fin, align_up(dfa.nstates, 16));
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    const size_t gw = (size_t) blockIdx.x * warps_per_block + warp;
+    const size_t warps_total = (size_t) gridDim.x * warps_per_block;
+    uint8_t *my_stage = smem + plan.stage_ofs + (size_t) warp * STAGES * STAGE_BYTES;
+    uint64_t *my_bars = reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES;
+
+    const size_t ngroups = (nlines + 31) / 32;
+    if (gw >= ngroups) {
+        return;
+    }
+    const uint32_t my_groups = (uint32_t) ((ngroups - gw + warps_total - 1) / warps_total);
+    const uint32_t ntiles = (linelen + TW - 1) / TW;
+    const uint32_t start = dfa.start, acc = dfa.acc;
+
+    auto finish = [&](size_t group, uint32_t s) {
+        const size_t line = group * 32 + lane;
+        if (line < nlines) {
+            rc[line] = (s == acc || fin[s]) ? SRE_K_OK : SRE_K_DECLINED;
+        }
+    };
+    if (ntiles == 0) {
+        for (uint32_t gi = 0; gi < my_groups; gi++) {
+            finish(gw + (size_t) gi * warps_total, start);
+        }
+        return;
+    }
+
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < STAGES; i++) {
+            mbar_init(&my_bars[i], 1);
+        }
+        fence_mbar_init();
+    }
+    __syncwarp();
+
+    const uint32_t total = my_groups * ntiles;
+    uint32_t pk = 0, pgi = 0, pt = 0;
+    auto produce = [&]() {
+        if (pk < total) {
+            if (lane == 0) {
+                uint64_t *bar = &my_bars[pk % STAGES];
+                mbar_arrive_expect_tx(bar, STAGE_BYTES);
+                tma_load_2d(my_stage + (pk % STAGES) * STAGE_BYTES, &tmap, (int32_t) (pt * TW),
+                            (int32_t) ((gw + (size_t) pgi * warps_total) * 32), bar);
+            }
+            pk++;
+            if (++pt == ntiles) {
+                pt = 0;
+                pgi++;
+            }
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < STAGES; i++) {
+        produce();
+    }
+
+    const uint32_t pat[4] = { pats.x, pats.y, pats.z, pats.w };
+    const uint32_t swz = lane & 7;
+    uint32_t s = start, t = 0;
+    size_t group = gw;
+
+    for (uint32_t k = 0; k < total; k++) {
+        mbar_wait(&my_bars[k % STAGES], (k / STAGES) & 1);
+        const uint8_t *row = my_stage + (k % STAGES) * STAGE_BYTES + lane * TW;
+        const uint32_t left = linelen - t * TW;
+        const uint32_t limit = left < (uint32_t) TW ? left : (uint32_t) TW;
+
+        /* phase 1: which words of my row hold a byte that leaves the start state */
+        uint32_t wm = 0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(row + ((c ^ swz) << 4));
+            const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint32_t h = 0;
+#pragma unroll
+                for (int p = 0; p < NPAT; p++) {
+                    const uint32_t x = w[i] ^ pat[p];
+                    h |= (x - 0x01010101u) & ~x & 0x80808080u;     /* some byte of x is zero */
+                }
+                wm |= (h ? 1u : 0u) << (c * 4 + i);
+            }
+        }
+
+        /* phase 2: walk only from marked words, until back in the start state */
+        uint32_t pos = 0;
+        while (pos < limit && s != acc) {
+            if (s == start) {
+                const uint32_t rem = wm & (0xffffffffu << (pos >> 2));
+                if (rem == 0) {
+                    break;
+                }
+                const uint32_t np = (uint32_t) (__ffs((int) rem) - 1) << 2;
+                if (np > pos) {
+                    pos = np;
+                    if (pos >= limit) {
+                        break;
+                    }
+                }
+            }
+            const uint32_t b = row[(((pos >> 4) ^ swz) << 4) | (pos & 15)];
+            s = tab[(s << 8) | b];
+            pos++;
+        }
+        __syncwarp();
+        produce();
+
+        if (++t == ntiles) {
+            finish(group, s);
+            t = 0;
+            s = start;
+            group += warps_total;
+        }
+    }
+}
+
 /* ---- k_dfa_lines_hint ------------------------------------------------------ */
 
 /*
@@ -441,6 +715,9 @@ k_nfa_lines(sre_dev_nfa_t nfa, const uint8_t *__restrict__ buf, const int64_t *_
 
 namespace sre_dev {
 static int g_num_sms = 0;
+int g_l2_promotion = 3;     /* 0 none, 1 64 B, 2 128 B, 3 256 B (sre_cuda_set_l2_promotion);
+                               256 B measured best on B200: the neighbouring 128 B of a row
+                               are the next tile of the same line */
 
 cudaError_t make_row_tensor_map(CUtensorMap *map, const uint8_t *buf, size_t nrows, size_t pitch, int tw)
 {
@@ -472,7 +749,7 @@ cudaError_t make_row_tensor_map(CUtensorMap *map, const uint8_t *buf, size_t nro
                                  : tw == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
     const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(buf), gdim, gstride,
                               box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              (CUtensorMapL2promotion) g_l2_promotion, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
@@ -658,6 +935,112 @@ cudaError_t sre_launch_dfa_lines(const sre_dev_dfa_t &dfa, const uint8_t *buf, s
     default: return cudaErrorInvalidValue;
     }
 #undef SRE_LINES
+}
+
+template <bool WORDSKIP, int STAGES, int NPAT, int THREADS, int BLOCKS>
+static cudaError_t launch_dfa_lines_skip_t(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines,
+    size_t pitch, size_t linelen, int32_t *rc, const uint32_t *pats, cudaStream_t stream)
+{
+    const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, false);
+    const int warps = THREADS / 32;
+    const size_t smem = plan.stage_ofs + (size_t) warps * STAGES * 32 * 128;
+    if (BLOCKS * (smem + 1024) > SMEM_LIMIT) {
+        return cudaErrorInvalidConfiguration;
+    }
+    CUtensorMap tmap;
+    cudaError_t err = make_row_tensor_map(&tmap, buf, nlines, pitch, 128);
+    if (err != cudaSuccess) {
+        return err;
+    }
+    auto kern = WORDSKIP ? k_dfa_lines_skipw<STAGES, NPAT, THREADS, BLOCKS>
+                         : k_dfa_lines_skip<STAGES, NPAT, THREADS, BLOCKS>;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (err != cudaSuccess) {
+            return err;
+        }
+        smem_set = smem;
+    }
+    const size_t ngroups = (nlines + 31) / 32;
+    size_t grid = (size_t) num_sms() * BLOCKS;
+    const size_t need = (ngroups + warps - 1) / warps;
+    if (grid > need) {
+        grid = need;
+    }
+    kern<<<(unsigned) grid, THREADS, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen,
+                                                   make_uint4(pats[0], pats[1], pats[2], pats[3]), rc);
+    return cudaGetLastError();
+}
+
+/* npat leave bytes (1..4), replicated into all four byte lanes of pats[] */
+cudaError_t sre_launch_dfa_lines_skip(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines,
+    size_t pitch, size_t linelen, int32_t *rc, const uint32_t *pats, int npat, int variant,
+    cudaStream_t stream, int *launches)
+{
+    if (nlines == 0) {
+        return cudaSuccess;
+    }
+    if (dfa.t256 == nullptr || npat < 1 || npat > 4) {
+        return cudaErrorInvalidValue;
+    }
+    if (launches) {
+        ++*launches;
+    }
+#define SRE_SKIP(WS, ST, TH, BL)                                                                      \
+    (npat == 1 ? launch_dfa_lines_skip_t<WS, ST, 1, TH, BL>(dfa, buf, nlines, pitch, linelen, rc, pats, stream) \
+     : npat == 2 ? launch_dfa_lines_skip_t<WS, ST, 2, TH, BL>(dfa, buf, nlines, pitch, linelen, rc, pats, stream) \
+                 : launch_dfa_lines_skip_t<WS, ST, 4, TH, BL>(dfa, buf, nlines, pitch, linelen, rc, pats, stream))
+    switch (variant) {
+    /* divergent walk (k_dfa_lines_skip) */
+    case 30: return SRE_SKIP(false, 1, 1024, 1);
+    case 31: return SRE_SKIP(false, 2, 768, 1);
+    case 32: return SRE_SKIP(false, 1, 768, 2);
+    case 33: return SRE_SKIP(false, 2, 512, 1);
+    /* warp-uniform word skip (k_dfa_lines_skipw) */
+    case 41: return SRE_SKIP(true, 1, 768, 1);
+    case 42: return SRE_SKIP(true, 1, 640, 2);
+    case 43: return SRE_SKIP(true, 2, 768, 1);
+    case 44: return SRE_SKIP(true, 1, 512, 1);
+    default: return SRE_SKIP(true, 1, 1024, 1);
+    }
+#undef SRE_SKIP
+}
+
+template <int STAGES, int THREADS, bool EARLY>
+static cudaError_t launch_ceiling_t(const uint8_t *buf, size_t nlines, size_t pitch, size_t linelen,
+    int32_t *rc, cudaStream_t stream)
+{
+    const size_t smem = 2048 + (size_t) (THREADS / 32) * STAGES * 32 * 128;
+    CUtensorMap tmap;
+    cudaError_t err = make_row_tensor_map(&tmap, buf, nlines, pitch, 128);
+    if (err != cudaSuccess) {
+        return err;
+    }
+    auto kern = k_tma_ceiling<STAGES, THREADS, EARLY>;
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (err != cudaSuccess) {
+        return err;
+    }
+    kern<<<(unsigned) num_sms(), THREADS, smem, stream>>>(tmap, nlines, (uint32_t) linelen, rc);
+    return cudaGetLastError();
+}
+
+void sre_dev_set_l2_promotion(int mode)
+{
+    sre_dev::g_l2_promotion = mode < 0 ? 0 : mode > 3 ? 3 : mode;
+}
+
+cudaError_t sre_launch_tma_ceiling(const uint8_t *buf, size_t nlines, size_t pitch, size_t linelen,
+    int32_t *rc, int variant, cudaStream_t stream)
+{
+    switch (variant) {
+    case 1:  return launch_ceiling_t<2, 768, false>(buf, nlines, pitch, linelen, rc, stream);
+    case 2:  return launch_ceiling_t<1, 1024, true>(buf, nlines, pitch, linelen, rc, stream);
+    case 3:  return launch_ceiling_t<1, 512, true>(buf, nlines, pitch, linelen, rc, stream);
+    case 4:  return launch_ceiling_t<3, 512, false>(buf, nlines, pitch, linelen, rc, stream);
+    default: return launch_ceiling_t<2, 768, true>(buf, nlines, pitch, linelen, rc, stream);
+    }
 }
 
 cudaError_t sre_launch_dfa_lines_hint(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines,

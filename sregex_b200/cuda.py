@@ -9,14 +9,14 @@ import torch
 
 from . import capi
 
-ENGINE_AUTO, ENGINE_DFA_TILED, ENGINE_DFA_GENERIC, ENGINE_NFA = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_DFA_TILED, ENGINE_DFA_GENERIC, ENGINE_NFA, ENGINE_DFA_SKIP = 0, 1, 2, 3, 4
 STATE_INIT = 0xFFFFFFFF
 
 
 class Info(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in (
         "prog_len", "nfa_states", "nfa_classes", "nfa_kinds", "nfa_shift_states", "dfa_states",
-        "dfa_classes", "dfa_byte_table", "nregexes", "pike_slots")] + [("pike_ctx_bytes", C.c_uint64)]
+        "dfa_classes", "dfa_byte_table", "dfa_leave_bytes", "nregexes", "pike_slots")] + [("pike_ctx_bytes", C.c_uint64)]
 
 
 _lib = None
@@ -44,6 +44,7 @@ def lib():
             "sre_cuda_thompson_exec_lines_host": (C.c_int, [vp, vp, sz, sz, sz, i32p, C.c_int]),
             "sre_cuda_pike_exec_lines_host": (C.c_int, [vp, vp, sz, sz, sz, C.c_int, i32p, i64p, sz]),
             "sre_cuda_set_variant": (None, [C.c_int]),
+            "sre_cuda_set_l2_promotion": (None, [C.c_int]),
             "sre_cuda_launch_count": (C.c_long, [C.c_int]),
             "sre_cuda_device_available": (C.c_int, []),
             "sre_cuda_last_error": (C.c_char_p, []),

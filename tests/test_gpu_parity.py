@@ -70,6 +70,8 @@ def _golden_batch(golden, cu, engine):
         prog = cu.CudaProgram(b["regexes_b"], b["flags"], multi=b["multi"])
         if engine in (cu.ENGINE_DFA_TILED, cu.ENGINE_DFA_GENERIC) and prog.info.dfa_states == 0:
             continue
+        if engine == cu.ENGINE_DFA_SKIP and prog.info.dfa_leave_bytes == 0:
+            continue
         s = b["subject_b"]
         pitch = max(16, (len(s) + 15) // 16 * 16)
         buf = torch.zeros(pitch, dtype=torch.uint8)
@@ -91,6 +93,11 @@ def test_batch_golden_dfa_generic(golden, cu):
 
 def test_batch_golden_nfa(golden, cu):
     _golden_batch(golden, cu, cu.ENGINE_NFA)
+
+
+def test_batch_golden_dfa_skip(golden, cu):
+    """skip-scan tier on every block whose start state is left by <= 4 byte values"""
+    _golden_batch(golden, cu, cu.ENGINE_DFA_SKIP)
 
 
 def test_batch_golden_pike_with_start_hint(golden, cu):
@@ -123,8 +130,10 @@ def test_thompson_tiers_vs_oracle(cu, nlines, linelen, pitch):
                                     baseline.ENGINE_THOMPSON)
     prog = cu.CudaProgram(corpus.C2_REGEX)
     dev = lines.cuda()
-    for engine in (cu.ENGINE_DFA_TILED, cu.ENGINE_DFA_GENERIC, cu.ENGINE_NFA):
-        for variant in ((0, 1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 20, 21, 22, 24, 25) if engine == cu.ENGINE_DFA_TILED else (0,)):
+    for engine in (cu.ENGINE_DFA_TILED, cu.ENGINE_DFA_GENERIC, cu.ENGINE_NFA, cu.ENGINE_DFA_SKIP, cu.ENGINE_AUTO):
+        variants = {cu.ENGINE_DFA_TILED: (0, 1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 20, 21, 22, 24, 25),
+                    cu.ENGINE_DFA_SKIP: (0, 30, 31, 32, 33, 41, 42, 43, 44)}.get(engine, (0,))
+        for variant in variants:
             cu.set_variant(variant)
             got = prog.thompson_lines(dev, nlines, pitch, linelen, engine=engine).cpu().numpy()
             assert (got == want).all(), (engine, variant, int((got != want).sum()))
