@@ -389,7 +389,7 @@ __device__ __forceinline__ void tile_pipeline_tma(Consumer &cons, const CUtensor
  * that many independent lines in flight to keep the shared-memory pipe busy.
  * TW is fixed at 128 (the row width the TMA unit moves efficiently).
  */
-template <int STAGES, class Consumer>
+template <int STAGES, class Consumer, bool FULLCOPY = false>
 __device__ __forceinline__ void tile_pipeline_tma_early(Consumer &cons, const CUtensorMap *tmap, size_t nrows,
     uint32_t rowlen, uint8_t *my_stage, uint64_t *my_bars, size_t gw, size_t warps_total)
 {
@@ -458,16 +458,31 @@ __device__ __forceinline__ void tile_pipeline_tma_early(Consumer &cons, const CU
             a[c] = *reinterpret_cast<const uint4 *>(row + ((c ^ swz) << 4));
         }
         if (left >= (uint32_t) TW) {
+            if (FULLCOPY) {
+                /* whole row to registers first: the stage is re-armed before
+                 * any byte is processed (registers are the second buffer) */
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                cons.chunk(a[c]);
-            }
+                for (int c = 0; c < 4; c++) {
+                    b[c] = *reinterpret_cast<const uint4 *>(row + (((c + 4) ^ swz) << 4));
+                }
+                __syncwarp();
+                produce();
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                b[c] = *reinterpret_cast<const uint4 *>(row + (((c + 4) ^ swz) << 4));
+                for (int c = 0; c < 4; c++) {
+                    cons.chunk(a[c]);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    cons.chunk(a[c]);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    b[c] = *reinterpret_cast<const uint4 *>(row + (((c + 4) ^ swz) << 4));
+                }
+                __syncwarp();
+                produce();
             }
-            __syncwarp();
-            produce();
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 cons.chunk(b[c]);

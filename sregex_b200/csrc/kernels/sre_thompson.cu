@@ -223,7 +223,7 @@ struct skipw_consumer_t {
     }
 };
 
-template <int STAGES, int NPAT, int THREADS, int BLOCKS>
+template <int STAGES, int NPAT, int THREADS, int BLOCKS, bool FULLCOPY>
 __global__ void __launch_bounds__(THREADS, BLOCKS)
 k_dfa_lines_skipw(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t nlines,
                   uint32_t linelen, uint4 pats, int32_t *__restrict__ rc)
@@ -246,11 +246,10 @@ k_dfa_lines_skipw(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, s
     cons.pat[3] = pats.w;
     cons.nlines = nlines;
     cons.rc = rc;
-    tile_pipeline_tma_early<STAGES>(cons, &tmap, nlines, linelen,
-                                    smem + plan.stage_ofs + (size_t) warp * STAGES * 32 * 128,
-                                    reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES,
-                                    (size_t) blockIdx.x * warps_per_block + warp,
-                                    (size_t) gridDim.x * warps_per_block);
+    tile_pipeline_tma_early<STAGES, skipw_consumer_t<NPAT>, FULLCOPY>(
+        cons, &tmap, nlines, linelen, smem + plan.stage_ofs + (size_t) warp * STAGES * 32 * 128,
+        reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES,
+        (size_t) blockIdx.x * warps_per_block + warp, (size_t) gridDim.x * warps_per_block);
 }
 
 /* ---- k_tma_ceiling (measurement aid) ----------------------------------------- */
@@ -937,7 +936,7 @@ cudaError_t sre_launch_dfa_lines(const sre_dev_dfa_t &dfa, const uint8_t *buf, s
 #undef SRE_LINES
 }
 
-template <bool WORDSKIP, int STAGES, int NPAT, int THREADS, int BLOCKS>
+template <int WORDSKIP, int STAGES, int NPAT, int THREADS, int BLOCKS>
 static cudaError_t launch_dfa_lines_skip_t(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines,
     size_t pitch, size_t linelen, int32_t *rc, const uint32_t *pats, cudaStream_t stream)
 {
@@ -952,8 +951,9 @@ static cudaError_t launch_dfa_lines_skip_t(const sre_dev_dfa_t &dfa, const uint8
     if (err != cudaSuccess) {
         return err;
     }
-    auto kern = WORDSKIP ? k_dfa_lines_skipw<STAGES, NPAT, THREADS, BLOCKS>
-                         : k_dfa_lines_skip<STAGES, NPAT, THREADS, BLOCKS>;
+    auto kern = WORDSKIP == 2 ? k_dfa_lines_skipw<STAGES, NPAT, THREADS, BLOCKS, true>
+              : WORDSKIP == 1 ? k_dfa_lines_skipw<STAGES, NPAT, THREADS, BLOCKS, false>
+                              : k_dfa_lines_skip<STAGES, NPAT, THREADS, BLOCKS>;
     static size_t smem_set = 0;
     if (smem > smem_set) {
         err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
@@ -993,16 +993,21 @@ cudaError_t sre_launch_dfa_lines_skip(const sre_dev_dfa_t &dfa, const uint8_t *b
                  : launch_dfa_lines_skip_t<WS, ST, 4, TH, BL>(dfa, buf, nlines, pitch, linelen, rc, pats, stream))
     switch (variant) {
     /* divergent walk (k_dfa_lines_skip) */
-    case 30: return SRE_SKIP(false, 1, 1024, 1);
-    case 31: return SRE_SKIP(false, 2, 768, 1);
-    case 32: return SRE_SKIP(false, 1, 768, 2);
-    case 33: return SRE_SKIP(false, 2, 512, 1);
-    /* warp-uniform word skip (k_dfa_lines_skipw) */
-    case 41: return SRE_SKIP(true, 1, 768, 1);
-    case 42: return SRE_SKIP(true, 1, 640, 2);
-    case 43: return SRE_SKIP(true, 2, 768, 1);
-    case 44: return SRE_SKIP(true, 1, 512, 1);
-    default: return SRE_SKIP(true, 1, 1024, 1);
+    case 30: return SRE_SKIP(0, 1, 1024, 1);
+    case 31: return SRE_SKIP(0, 2, 768, 1);
+    case 32: return SRE_SKIP(0, 1, 768, 2);
+    case 33: return SRE_SKIP(0, 2, 512, 1);
+    /* warp-uniform word skip (k_dfa_lines_skipw), half-row register copies */
+    case 41: return SRE_SKIP(1, 1, 768, 1);
+    case 42: return SRE_SKIP(1, 1, 640, 2);
+    case 43: return SRE_SKIP(1, 2, 768, 1);
+    case 44: return SRE_SKIP(1, 1, 512, 1);
+    /* ... whole-row register copy: the stage is re-armed before processing */
+    case 50: return SRE_SKIP(2, 1, 768, 1);
+    case 51: return SRE_SKIP(2, 1, 896, 1);
+    case 52: return SRE_SKIP(2, 1, 1024, 1);
+    case 53: return SRE_SKIP(2, 1, 640, 1);
+    default: return SRE_SKIP(1, 1, 1024, 1);
     }
 #undef SRE_SKIP
 }
