@@ -148,3 +148,18 @@ extern "C" long lc_hint(lc_t *lc, const uint8_t *buf, size_t len)
     }
     return p0;
 }
+
+/* the same hint from the class-compressed restart table (any DFA size) */
+extern "C" long lc_hint_cls(lc_t *lc, const uint8_t *buf, size_t len)
+{
+    const sre_dfa_t &d = lc->low.dfa;
+    if (!lc->low.has_dfa || d.hcls.empty()) return -1;
+    uint32_t s = d.start;
+    long p0 = 0;
+    for (size_t i = 0; i < len && s != d.acc; i++) {
+        const uint16_t e = d.hcls[(size_t) s * d.hncls + d.hclsmap[buf[i]]];
+        s = e & 0x7fff;
+        if (e & 0x8000) p0 = (long) i + 1;
+    }
+    return p0;
+}

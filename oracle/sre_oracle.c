@@ -307,6 +307,17 @@ struct sre_vm_pike_ctx_s {
                      seen_newline, seen_word;
 };
 
+/* test statistic: longest Pike thread list seen (sizing of the GPU kernels) */
+static uint32_t oracle_max_list;
+SRE_API uint32_t oracle_pike_max_list(int reset)
+{
+    uint32_t v = oracle_max_list;
+    if (reset) {
+        oracle_max_list = 0;
+    }
+    return v;
+}
+
 static void
 op_list_reset(op_list_t *l)
 {
@@ -467,6 +478,9 @@ op_add_thread(sre_vm_pike_ctx_t *ctx, op_list_t *l, int32_t pc, sre_int_t *cap,
     *l->tailp = t;
     l->tailp = &t->next;
     l->count++;
+    if (l->count > oracle_max_list) {
+        oracle_max_list = l->count;
+    }
     return SRE_OK;
 }
 

@@ -13,6 +13,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -31,6 +32,7 @@ namespace {
 
 std::atomic<long>   g_launches(0);
 int                 g_variant = 0;
+int                 g_pike_general_only = 0;    /* tests: force k_pike_lines */
 thread_local char   g_err[256] = "";
 
 const uint32_t MAX_DFA_STATES = 4096;
@@ -138,7 +140,7 @@ int upload(sre_cuda_program_t *cp)
     const sre_program_t *prog = cp->prog;
     const sre_nfa_t &n = cp->low.nfa;
     blob_t b;
-    size_t o_t256 = 0, o_tcls = 0, o_dcls = 0, o_fin = 0, o_h256 = 0;
+    size_t o_t256 = 0, o_tcls = 0, o_dcls = 0, o_fin = 0, o_h256 = 0, o_hcls = 0, o_hmap = 0;
 
     cp->has_dfa = cp->low.has_dfa;
     if (cp->has_dfa) {
@@ -148,6 +150,10 @@ int upload(sre_cuda_program_t *cp)
         }
         if (!d.h256.empty()) {
             o_h256 = b.add(d.h256.data(), d.h256.size());
+        }
+        if (!d.hcls.empty()) {
+            o_hcls = b.add(d.hcls.data(), d.hcls.size() * 2);
+            o_hmap = b.add(d.hclsmap, 256);
         }
         o_tcls = b.add(d.trans.data(), d.trans.size() * 2);
         o_dcls = b.add(d.clsmap, 256);
@@ -247,6 +253,9 @@ int upload(sre_cuda_program_t *cp)
         cp->dfa.clsmap = base + o_dcls;
         cp->dfa.fin = base + o_fin;
         cp->dfa.h256 = d.h256.empty() ? nullptr : base + o_h256;
+        cp->dfa.hcls = d.hcls.empty() ? nullptr : reinterpret_cast<const uint16_t *>(base + o_hcls);
+        cp->dfa.hclsmap = d.hcls.empty() ? nullptr : base + o_hmap;
+        cp->dfa.hncls = d.hncls;
         cp->nleave = 0;
         if (!d.t256.empty()) {
             for (unsigned bv = 0; bv < 256 && cp->nleave >= 0; bv++) {
@@ -367,7 +376,13 @@ int thompson_dispatch(sre_cuda_program_t *cp, const uint8_t *dev_buf, const int6
 
 int ensure_pike_scratch(sre_cuda_program_t *cp, size_t nlines)
 {
-    size_t want = nlines < 148 * 1024 ? nlines : 148 * 1024;
+    static long cap = -1;       /* SRE_PIKE_NCTX: concurrency override (tuning) */
+    if (cap < 0) {
+        const char *e = getenv("SRE_PIKE_NCTX");
+        cap = e ? atol(e) : 0;
+    }
+    const size_t max_ctx = cap > 0 ? (size_t) cap : (size_t) 148 * 1024;
+    size_t want = nlines < max_ctx ? nlines : max_ctx;
     const size_t by_budget = PIKE_SCRATCH_BUDGET / cp->pike.ctx_stride;
     if (want > by_budget) {
         want = by_budget ? by_budget : 1;
@@ -446,6 +461,7 @@ extern "C" {
 SRE_API int sre_cuda_device_available(void) { return device_ok() ? 1 : 0; }
 SRE_API const char *sre_cuda_last_error(void) { return g_err; }
 SRE_API void sre_cuda_set_variant(int variant) { g_variant = variant; }
+SRE_API void sre_cuda_set_pike_general_only(int on) { g_pike_general_only = on; }
 SRE_API void sre_cuda_set_l2_promotion(int mode) { sre_dev_set_l2_promotion(mode); }
 
 SRE_API long sre_cuda_launch_count(int reset)
@@ -564,7 +580,8 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
      */
     const bool aligned = dev_offsets == nullptr && (reinterpret_cast<uintptr_t>(dev_buf) & 15) == 0
                          && (pitch & 15) == 0 && linelen <= pitch && linelen < (1ull << 31);
-    if (dev_select == nullptr && cp->has_dfa && cp->dfa.h256 != nullptr && aligned) {
+    const bool tiled_hint = cp->has_dfa && cp->dfa.h256 != nullptr && aligned;
+    if (dev_select == nullptr && (tiled_hint || (cp->has_dfa && cp->dfa.hcls != nullptr))) {
         const size_t need = ((nlines * 4 + 255) & ~(size_t) 255) * 2;
         if (cp->line_ws_bytes < need) {
             cudaFree(cp->line_ws);
@@ -575,8 +592,10 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         }
         int32_t *gate = reinterpret_cast<int32_t *>(cp->line_ws);
         int32_t *hint = reinterpret_cast<int32_t *>(cp->line_ws + need / 2);
-        cudaError_t e = sre_launch_dfa_lines_hint(cp->dfa, dev_buf, nlines, pitch, linelen, gate, hint, st,
-                                                  &launches);
+        cudaError_t e = tiled_hint
+            ? sre_launch_dfa_lines_hint(cp->dfa, dev_buf, nlines, pitch, linelen, gate, hint, st, &launches)
+            : sre_launch_dfa_generic_hint(cp->dfa, dev_buf, dev_offsets, nlines, pitch, linelen, gate, hint, st,
+                                          &launches);
         if (e != cudaSuccess) {
             count_launches(launches);
             return fail("hint kernel launch failed: %s", cudaGetErrorString(e));
@@ -585,10 +604,22 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         start = hint;
     }
 
-    cudaError_t err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen,
-                                            dev_select, start, dev_rc, dev_ovec, (uint32_t) ovec_slots,
-                                            cp->pike_scratch, cp->pike_nctx < nlines ? cp->pike_nctx : nlines,
-                                            st, &launches);
+    cudaError_t err;
+    const size_t nctx = cp->pike_nctx < nlines ? cp->pike_nctx : nlines;
+    if (sre_pike_small_applicable(cp->pike) && linelen < (1ull << 31) && !g_pike_general_only) {
+        /* shared-memory kernel first; the general kernel re-runs what it gave up on */
+        err = sre_launch_pike_small(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, dev_select, start,
+                                    dev_rc, dev_ovec, (uint32_t) ovec_slots, st, &launches);
+        if (err == cudaSuccess) {
+            err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, dev_select,
+                                        start, dev_rc, dev_ovec, (uint32_t) ovec_slots, cp->pike_scratch,
+                                        nctx < 16384 ? nctx : 16384, 1, st, &launches);
+        }
+    } else {
+        err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, dev_select, start,
+                                    dev_rc, dev_ovec, (uint32_t) ovec_slots, cp->pike_scratch, nctx, 0, st,
+                                    &launches);
+    }
     count_launches(launches);
     if (err != cudaSuccess) {
         return fail("Pike kernel launch failed: %s", cudaGetErrorString(err));

@@ -14,6 +14,7 @@
 #define SRE_K_ERROR    (-1)
 #define SRE_K_AGAIN    (-2)
 #define SRE_K_DECLINED (-5)
+#define SRE_K_RETRY    (-100)  /* internal: line must be re-run by the general kernel */
 
 /* ---- DFA tier ------------------------------------------------------------ */
 struct sre_dev_dfa_t {
@@ -23,6 +24,9 @@ struct sre_dev_dfa_t {
     const uint8_t   *clsmap;    /* [256]                                      */
     const uint8_t   *fin;       /* [nstates]                                  */
     const uint8_t   *h256;      /* [256][256] next | restart flag, or NULL    */
+    const uint16_t  *hcls;      /* [nstates][hncls] next | 0x8000 restart, or NULL */
+    const uint8_t   *hclsmap;   /* [256]                                      */
+    uint32_t         hncls;
 };
 
 /* ---- NFA tier ------------------------------------------------------------ */
@@ -104,13 +108,27 @@ cudaError_t sre_launch_dfa_lines_hint(const sre_dev_dfa_t &dfa, const uint8_t *b
     size_t nlines, size_t pitch, size_t linelen, int32_t *rc, int32_t *hint,
     cudaStream_t stream, int *launches);
 
+/* same for any DFA size / alignment / ragged offsets (thread per line, dfa.hcls) */
+cudaError_t sre_launch_dfa_generic_hint(const sre_dev_dfa_t &dfa, const uint8_t *buf,
+    const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen, int32_t *rc,
+    int32_t *hint, cudaStream_t stream, int *launches);
+
 /* Pike VM over lines; select may be NULL (all) or an rc array (run where ==0);
  * start may be NULL or per-line offsets at which the search may begin          */
 size_t sre_pike_concurrency(size_t nlines);
 cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
     const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen,
     const int32_t *select, const int32_t *start, int32_t *rc, int64_t *ovec,
-    uint32_t ovec_slots, uint8_t *scratch, size_t nctx, cudaStream_t stream, int *launches);
+    uint32_t ovec_slots, uint8_t *scratch, size_t nctx, int retry_only, cudaStream_t stream,
+    int *launches);
+
+/* shared-memory Pike for small single-regex programs; lines that exceed its
+ * capacities get rc = SRE_K_RETRY (re-run them with retry_only = 1 above)      */
+bool sre_pike_small_applicable(const sre_dev_pike_t &pk);
+cudaError_t sre_launch_pike_small(const sre_dev_pike_t &pk, const uint8_t *buf,
+    const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen,
+    const int32_t *select, const int32_t *start, int32_t *rc, int64_t *ovec,
+    uint32_t ovec_slots, cudaStream_t stream, int *launches);
 
 /* Pike VM streaming step on one persistent context (classic API)             */
 cudaError_t sre_launch_pike_stream(const sre_dev_pike_t &pk, uint8_t *ctx,

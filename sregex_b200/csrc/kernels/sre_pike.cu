@@ -664,8 +664,8 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
 __global__ void __launch_bounds__(128)
 k_pike_lines(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
              size_t nlines, size_t pitch, size_t linelen, const int32_t *__restrict__ select,
-             const int32_t *__restrict__ start_hint, int32_t *__restrict__ rc, int64_t *__restrict__ ovec, uint32_t ovec_slots,
-             uint8_t *scratch, size_t nctx)
+             const int32_t *__restrict__ start_hint, int32_t *__restrict__ rc, int64_t *__restrict__ ovec,
+             uint32_t ovec_slots, uint8_t *scratch, size_t nctx, int retry_only)
 {
     const size_t tid = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= nctx) {
@@ -681,7 +681,12 @@ k_pike_lines(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
 
     for (size_t line = tid; line < nlines; line += nctx) {
         int64_t *ov = ovec + line * ovec_slots;
-        if (select && select[line] != SRE_K_OK) {
+        if (retry_only) {
+            /* second pass after k_pike_small: only the lines it gave up on */
+            if (rc[line] != SRE_K_RETRY) {
+                continue;
+            }
+        } else if (select && select[line] != SRE_K_OK) {
             rc[line] = select[line];
             for (uint32_t i = 0; i < ovec_slots; i++) {
                 ov[i] = -1;
@@ -743,7 +748,7 @@ size_t sre_pike_ctx_bytes(uint32_t len, uint32_t nslots, uint32_t max_slots, uin
 cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
     const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen, const int32_t *select,
     const int32_t *start, int32_t *rc, int64_t *ovec, uint32_t ovec_slots, uint8_t *scratch, size_t nctx,
-    cudaStream_t stream, int *launches)
+    int retry_only, cudaStream_t stream, int *launches)
 {
     if (nlines == 0 || nctx == 0) {
         return cudaSuccess;
@@ -753,7 +758,7 @@ cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
     }
     const unsigned grid = (unsigned) ((nctx + 127) / 128);
     k_pike_lines<<<grid, 128, 0, stream>>>(pk, buf, offsets, nlines, pitch, linelen, select, start, rc, ovec,
-                                          ovec_slots, scratch, nctx);
+                                          ovec_slots, scratch, nctx, retry_only);
     return cudaGetLastError();
 }
 

@@ -584,6 +584,65 @@ k_dfa_generic(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, const int64_t 
     }
 }
 
+/* ---- k_dfa_generic_hint ---------------------------------------------------- */
+
+/* verdict + Pike start hint (see k_dfa_lines_hint) from the class-compressed
+ * restart table, for DFAs of any size and lines of any alignment */
+template <bool SMEM_TAB>
+__global__ void __launch_bounds__(256)
+k_dfa_generic_hint(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
+                   size_t nlines, size_t pitch, size_t linelen, int32_t *__restrict__ rc,
+                   int32_t *__restrict__ hint)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint8_t s_cls[256];
+    const uint16_t *tab = dfa.hcls;
+    const uint32_t C = dfa.hncls;
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        s_cls[i] = dfa.hclsmap[i];
+    }
+    if (SMEM_TAB) {
+        load_table(smem, reinterpret_cast<const uint8_t *>(dfa.hcls), align_up((size_t) dfa.nstates * C * 2, 16));
+        tab = reinterpret_cast<const uint16_t *>(smem);
+    }
+    __syncthreads();
+
+    for (size_t line = (size_t) blockIdx.x * blockDim.x + threadIdx.x; line < nlines;
+         line += (size_t) gridDim.x * blockDim.x)
+    {
+        size_t p = offsets ? (size_t) offsets[line] : line * pitch;
+        const size_t begin = p, end = offsets ? (size_t) offsets[line + 1] : p + linelen;
+        uint32_t s = dfa.start, p0 = 0;
+        auto step = [&](uint32_t b) {
+            const uint32_t e = SMEM_TAB ? tab[s * C + s_cls[b]] : __ldg(tab + s * C + s_cls[b]);
+            s = e & 0x7fff;
+            p++;
+            if (e & 0x8000) {
+                p0 = (uint32_t) (p - begin);
+            }
+        };
+        while (p < end && ((reinterpret_cast<uintptr_t>(buf) + p) & 15) && s != dfa.acc) {
+            step(buf[p]);
+        }
+        while (p + 16 <= end && s != dfa.acc) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(buf + p));
+            const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    step((w[i] >> (8 * k)) & 0xff);
+                }
+            }
+        }
+        while (p < end && s != dfa.acc) {
+            step(buf[p]);
+        }
+        rc[line] = (s == dfa.acc || dfa.fin[s]) ? SRE_K_OK : SRE_K_DECLINED;
+        hint[line] = (int32_t) p0;
+    }
+}
+
 /* ---- k_nfa_lines ----------------------------------------------------------- */
 
 /*
@@ -1046,6 +1105,44 @@ cudaError_t sre_launch_tma_ceiling(const uint8_t *buf, size_t nlines, size_t pit
     case 4:  return launch_ceiling_t<3, 512, false>(buf, nlines, pitch, linelen, rc, stream);
     default: return launch_ceiling_t<2, 768, true>(buf, nlines, pitch, linelen, rc, stream);
     }
+}
+
+cudaError_t sre_launch_dfa_generic_hint(const sre_dev_dfa_t &dfa, const uint8_t *buf, const int64_t *offsets,
+    size_t nlines, size_t pitch, size_t linelen, int32_t *rc, int32_t *hint, cudaStream_t stream, int *launches)
+{
+    if (nlines == 0) {
+        return cudaSuccess;
+    }
+    if (dfa.hcls == nullptr) {
+        return cudaErrorInvalidValue;
+    }
+    const size_t tab = align_up((size_t) dfa.nstates * dfa.hncls * 2, 16);
+    const bool fits = tab <= 160 * 1024;
+    size_t grid = (nlines + 255) / 256;
+    const size_t cap = (size_t) num_sms() * (fits ? 1 : 8);
+    if (grid > cap) {
+        grid = cap;
+    }
+    if (launches) {
+        ++*launches;
+    }
+    if (fits) {
+        static size_t smem_set = 0;
+        if (tab > smem_set) {
+            cudaError_t e = cudaFuncSetAttribute(k_dfa_generic_hint<true>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tab);
+            if (e != cudaSuccess) {
+                return e;
+            }
+            smem_set = tab;
+        }
+        k_dfa_generic_hint<true><<<(unsigned) grid, 256, tab, stream>>>(dfa, buf, offsets, nlines, pitch,
+                                                                        linelen, rc, hint);
+    } else {
+        k_dfa_generic_hint<false><<<(unsigned) grid, 256, 0, stream>>>(dfa, buf, offsets, nlines, pitch,
+                                                                       linelen, rc, hint);
+    }
+    return cudaGetLastError();
 }
 
 cudaError_t sre_launch_dfa_lines_hint(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines,

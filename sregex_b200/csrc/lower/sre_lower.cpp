@@ -416,6 +416,20 @@ bool build_dfa(const sre_nfa_t &nfa, uint32_t max_states, sre_dfa_t &dfa)
         }
     }
 
+    if (D <= 32767) {
+        dfa.hncls = C;
+        for (unsigned b = 0; b < 256; b++) {
+            dfa.hclsmap[b] = nfa.clsmap[b];
+        }
+        dfa.hcls.assign((size_t) D * C, 0);
+        for (uint32_t d = 0; d < D; d++) {
+            for (uint32_t c = 0; c < C; c++) {
+                dfa.hcls[(size_t) d * C + c] =
+                    (uint16_t) (trans[(size_t) d * C + c] | (restart[(size_t) d * C + c] ? 0x8000 : 0));
+            }
+        }
+    }
+
     /* merge NFA byte classes whose DFA columns coincide */
     std::map<std::vector<uint16_t>, uint32_t> cols;
     std::vector<uint32_t> remap(C);

@@ -81,6 +81,11 @@ struct sre_dfa_t {
      * may be restarted right after this byte (Pike hint).
      */
     std::vector<uint8_t>    h256;
+    /* the same information for any DFA size: [nstates][hncls] u16 over the NFA
+     * byte classes (hclsmap), entry = next state | 0x8000 restart flag         */
+    uint32_t                hncls = 0;
+    uint8_t                 hclsmap[256];
+    std::vector<uint16_t>   hcls;
 };
 
 struct sre_lowered_t {

@@ -100,11 +100,22 @@ def test_batch_golden_dfa_skip(golden, cu):
     _golden_batch(golden, cu, cu.ENGINE_DFA_SKIP)
 
 
-def test_batch_golden_pike_with_start_hint(golden, cu):
+@pytest.mark.parametrize("general_only", [0, 1])
+def test_batch_golden_pike_with_start_hint(golden, cu, general_only):
     """every golden block as a 1-line batch through sre_cuda_pike_exec_lines with
-    its internal gate + start-hint pass: rc and the whole ovector"""
+    its internal gate + start-hint pass: rc and the whole ovector.  Once through
+    the shared-memory tier (k_pike_small, with k_pike_lines re-running what it
+    gives up on) and once through the general kernel alone."""
+    cu.lib().L.sre_cuda_set_pike_general_only(general_only)
+    try:
+        _golden_pike_batch(golden, cu, step=1 if general_only == 0 else 2)
+    finally:
+        cu.lib().L.sre_cuda_set_pike_general_only(0)
+
+
+def _golden_pike_batch(golden, cu, step):
     bad = []
-    for b in runnable(golden):
+    for b in runnable(golden)[::step]:
         prog = cu.CudaProgram(b["regexes_b"], b["flags"], multi=b["multi"])
         s = b["subject_b"]
         pitch = max(16, (len(s) + 15) // 16 * 16)
@@ -177,6 +188,26 @@ def test_pike_lines_vs_oracle(cu):
     sel = prog.thompson_lines(lines.cuda(), n, 1024, 1024)
     rc2, ov2 = prog.pike_lines(lines.cuda(), n, 1024, 1024, select=sel)
     assert torch.equal(rc, rc2) and torch.equal(ov, ov2)
+
+
+def test_pike_ragged_lines_vs_oracle(cu):
+    """ragged offsets: gate + start hint come from the class-table kernel"""
+    rng = np.random.default_rng(7)
+    lines = corpus.log_lines(300, 1024).numpy()
+    lens = rng.integers(0, 1024, size=300)
+    lens[:3] = [0, 1, 1023]
+    chunks = [lines[i, 1024 - lens[i]:] for i in range(300)]
+    flat = np.concatenate(chunks + [np.zeros(16, np.uint8)])
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    prog = cu.CudaProgram(corpus.C3_REGEX)
+    o = capi.load("oracle")
+    po = o.compile(corpus.C3_REGEX)
+    rc, ov = prog.pike_lines(torch.from_numpy(flat).cuda(), 300, 0, 0, offsets=torch.from_numpy(offsets).cuda())
+    rc, ov = rc.cpu().tolist(), ov.cpu().tolist()
+    for i, c in enumerate(chunks):
+        wrc, wov = o.pike(po, c.tobytes())
+        assert rc[i] == wrc and (wov is None or ov[i] == wov), i
+    assert sum(1 for r in rc if r == 0) > 50
 
 
 MULTI = [rb"HTTP/1\.[01]\" 5\d\d ", rb"(GET|HEAD) /x/(\d+)", rb"POST /x/0", rb"^1[0-4]\d\.", rb"08:47:0(\d)",

@@ -26,6 +26,8 @@ def lc():
     lib.lc_dfa_exec.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_uint, C.c_int]
     lib.lc_hint.restype = C.c_long
     lib.lc_hint.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    lib.lc_hint_cls.restype = C.c_long
+    lib.lc_hint_cls.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     return lib
 
 
@@ -82,6 +84,10 @@ def test_pike_start_hint_never_passes_the_match_start(golden, oracle, lc):
         if hint >= 0:
             assert hint <= b["pike"]["ov"][0], (b["file"], b["name"], hint, b["pike"]["ov"])
             checked += 1
+        hint2 = lc.lc_hint_cls(h, s, len(s))
+        if hint2 >= 0:
+            assert hint2 <= b["pike"]["ov"][0], (b["file"], b["name"], hint2, b["pike"]["ov"])
+            assert hint < 0 or hint2 == hint
         lc.lc_destroy(h)
         p.close()
     assert checked > 1000
