@@ -581,7 +581,7 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
     const bool aligned = dev_offsets == nullptr && (reinterpret_cast<uintptr_t>(dev_buf) & 15) == 0
                          && (pitch & 15) == 0 && linelen <= pitch && linelen < (1ull << 31);
     const bool tiled_hint = cp->has_dfa && cp->dfa.h256 != nullptr && aligned;
-    if (dev_select == nullptr && (tiled_hint || (cp->has_dfa && cp->dfa.hcls != nullptr))) {
+    if (tiled_hint || (cp->has_dfa && cp->dfa.hcls != nullptr)) {
         const size_t need = ((nlines * 4 + 255) & ~(size_t) 255) * 2;
         if (cp->line_ws_bytes < need) {
             cudaFree(cp->line_ws);
@@ -600,7 +600,11 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
             count_launches(launches);
             return fail("hint kernel launch failed: %s", cudaGetErrorString(e));
         }
-        dev_select = gate;
+        /* a caller-supplied gate is honoured as given; the start hints are
+         * valid for every line either way */
+        if (dev_select == nullptr) {
+            dev_select = gate;
+        }
         start = hint;
     }
 

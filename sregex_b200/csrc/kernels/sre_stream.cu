@@ -8,24 +8,25 @@
  * f: state -> state, and function composition is associative:
  *
  *   k_stream_pieces   one CUDA thread per PIECE-byte piece (same TMA tile
- *                     pipeline as k_dfa_lines, rows = pieces): runs the
- *                     piece from EVERY entry state at once ("speculatively")
- *                     and writes the piece's transfer function (nstates bytes).
- *                     As soon as all live entry states have converged to one
- *                     state the thread drops to the single-state inner loop, so
- *                     for automata that forget their history quickly the cost
- *                     is ~1 table look-up per byte, as in k_dfa_lines.
- *   k_stream_compose  thread i composes G consecutive functions of one level
- *                     into one function of the next level (reduction tree).
- *   k_stream_top      one thread walks the (<= G) functions of the top level
- *                     from the true entry state: exact entry state of every
- *                     top-level element, and the exit state of the stream.
- *   k_stream_entries  pushes exact entry states down one level; at level 0 it
- *                     records the first piece in which the automaton enters
- *                     ACC (= in which the reference's loop would return SRE_OK).
- *   k_stream_locate   re-runs that one piece to get the exact byte offset.
+ *                     pipeline as k_dfa_lines, rows = pieces): runs the first
+ *                     16-byte chunks of the piece from EVERY entry state
+ *                     ("speculatively") until all of them have either been
+ *                     absorbed by ACC or met in one state, then the single-state
+ *                     inner loop of k_dfa_lines; writes the piece's transfer
+ *                     function (nstates bytes, padded to 16/32).
+ *   k_stream_tail     the ragged end (< PIECE bytes): one warp, 128-byte
+ *                     sub-chunks per lane, shuffle-tree composition.
+ *   k_stream_compose  one warp composes FAN = 256 consecutive functions (8 per
+ *                     lane serially, then a 5-round shuffle tree) into one
+ *                     function of the next level; loads are coalesced.
+ *   k_stream_entries  walks one level down from exact entry states: one warp
+ *                     per parent propagates the entry state across its lanes
+ *                     and writes the exact entry state of all 256 children; at
+ *                     level 0 it records the first piece whose step enters ACC
+ *                     (= in which the reference's loop would return SRE_OK).
+ *   k_stream_locate   one warp re-runs that piece to get the exact byte offset.
  *
- * Everything is exact: no piece result depends on a guess.
+ * Everything is exact: no result depends on a guess.
  */
 #include "sre_device_common.cuh"
 
@@ -33,53 +34,137 @@ using namespace sre_dev;
 
 namespace {
 
-constexpr uint32_t PIECE = 1024;    /* bytes per level-0 piece                */
-constexpr uint32_t FAN = 256;       /* functions composed per thread          */
+constexpr uint32_t PIECE = 4096;    /* bytes per level-0 piece                */
+constexpr uint32_t FAN = 256;       /* functions composed per warp            */
+constexpr uint32_t PER_LANE = FAN / 32;
 
-/* function records are FS = 16/32 bytes apart (nstates rounded up) */
+/* function records are 16 or 32 bytes (nstates rounded up) */
 __host__ __device__ inline uint32_t fn_stride(uint32_t nstates)
 {
     return nstates <= 16 ? 16 : 32;
 }
 
-/* D-way consumer: st[d] = state reached from entry state d */
-template <int DV>
+/* ---- a state -> state function packed into NW = DV/4 words --------------------- */
+
+template <int NW>
+struct fn_t {
+    uint32_t w[NW];
+
+    __device__ __forceinline__ void identity()
+    {
+#pragma unroll
+        for (int i = 0; i < NW; i++) {
+            w[i] = 0x03020100u + 0x04040404u * i;
+        }
+    }
+    /* byte k, k dynamic */
+    __device__ __forceinline__ uint32_t at(uint32_t k) const
+    {
+        uint32_t v = w[0];
+#pragma unroll
+        for (int i = 1; i < NW; i++) {
+            v = (k >> 2) == (uint32_t) i ? w[i] : v;
+        }
+        return (v >> ((k & 3) * 8)) & 0xff;
+    }
+    /* byte d, d a compile-time constant after unrolling */
+    __device__ __forceinline__ uint32_t get(int d) const { return (w[d >> 2] >> ((d & 3) * 8)) & 0xff; }
+    __device__ __forceinline__ void set(int d, uint32_t v)
+    {
+        w[d >> 2] = (w[d >> 2] & ~(0xffu << ((d & 3) * 8))) | (v << ((d & 3) * 8));
+    }
+    /* this = g o this  (apply this first, then g) */
+    __device__ __forceinline__ void then(const fn_t &g)
+    {
+        fn_t r;
+#pragma unroll
+        for (int i = 0; i < NW; i++) {
+            r.w[i] = 0;
+        }
+#pragma unroll
+        for (int d = 0; d < NW * 4; d++) {
+            r.w[d >> 2] |= g.at(get(d)) << ((d & 3) * 8);
+        }
+        *this = r;
+    }
+    __device__ __forceinline__ void load(const uint8_t *p)
+    {
+        const uint4 a = *reinterpret_cast<const uint4 *>(p);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+        if (NW > 4) {
+            const uint4 b = *reinterpret_cast<const uint4 *>(p + 16);
+            w[4 % NW] = b.x; w[5 % NW] = b.y; w[6 % NW] = b.z; w[7 % NW] = b.w;
+        }
+    }
+    __device__ __forceinline__ void store(uint8_t *p) const
+    {
+        *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (NW > 4) {
+            *reinterpret_cast<uint4 *>(p + 16) = make_uint4(w[4 % NW], w[5 % NW], w[6 % NW], w[7 % NW]);
+        }
+    }
+    __device__ __forceinline__ fn_t shfl_down(uint32_t delta) const
+    {
+        fn_t r;
+#pragma unroll
+        for (int i = 0; i < NW; i++) {
+            r.w[i] = __shfl_down_sync(0xffffffffu, w[i], delta);
+        }
+        return r;
+    }
+};
+
+/* compose the functions held by the 32 lanes in lane order; lane 0 gets the result */
+template <int NW>
+__device__ __forceinline__ void warp_compose(fn_t<NW> &f)
+{
+    const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+    for (uint32_t s = 1; s < 32; s <<= 1) {
+        const fn_t<NW> g = f.shfl_down(s);
+        if ((lane & (2 * s - 1)) == 0) {
+            f.then(g);
+        }
+    }
+}
+
+/* ---- level 0: pieces ------------------------------------------------------------ */
+
+/* NW*4-way consumer: byte d of `st` = state reached from entry state d */
+template <int NW>
 struct piece_consumer_t {
     const uint8_t  *tab;        /* [nstates][256] in shared memory            */
     uint8_t        *fn;         /* level-0 function records                   */
-    uint32_t        nstates, acc, fs;
+    uint32_t        nstates, acc;
     size_t          npieces;
-    uint32_t        st[DV];
-    uint32_t        s;          /* the single state once converged            */
+    fn_t<NW>        st;
+    uint32_t        s;          /* the single live state once converged       */
     uint32_t        accmask;    /* entry states already absorbed by ACC       */
     bool            conv;
 
     __device__ __forceinline__ void begin()
     {
-#pragma unroll
-        for (int d = 0; d < DV; d++) {
-            st[d] = d < (int) nstates ? d : 0;
-        }
+        st.identity();
         conv = false;
         s = 0;
         accmask = 0;
     }
 
+    /* converged = every entry state was absorbed by ACC (e.g. entry states that
+     * already hold a MATCH thread) or has reached one common state */
     __device__ __forceinline__ void check()
     {
-        /* converged = every entry state has either been absorbed by ACC (e.g.
-         * entry states that already hold a MATCH thread) or reached one common
-         * state */
         uint32_t ref = acc, mask = 0;
         bool all = true;
 #pragma unroll
-        for (int d = 0; d < DV; d++) {
+        for (int d = 0; d < NW * 4; d++) {
             if (d < (int) nstates) {
-                if (st[d] == acc) {
+                const uint32_t v = st.get(d);
+                if (v == acc) {
                     mask |= 1u << d;
                 } else if (ref == acc) {
-                    ref = st[d];
-                } else if (st[d] != ref) {
+                    ref = v;
+                } else if (v != ref) {
                     all = false;
                 }
             }
@@ -93,21 +178,17 @@ struct piece_consumer_t {
 
     __device__ __forceinline__ void chunk(const uint4 &v)
     {
+        step256_t st256 = { tab };
         if (conv) {
-            step256_t st256 = { tab };
             s = st256.word(st256.word(st256.word(st256.word(s, v.x), v.y), v.z), v.w);
             return;
         }
-        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t b = (w[i] >> (8 * k)) & 0xff;
-#pragma unroll
-                for (int d = 0; d < DV; d++) {
-                    st[d] = tab[(st[d] << 8) | b];
-                }
+        for (int d = 0; d < NW * 4; d++) {
+            if (d < (int) nstates) {
+                uint32_t x = st.get(d);
+                x = st256.word(st256.word(st256.word(st256.word(x, v.x), v.y), v.z), v.w);
+                st.set(d, x);
             }
         }
         check();
@@ -120,8 +201,10 @@ struct piece_consumer_t {
             return;
         }
 #pragma unroll
-        for (int d = 0; d < DV; d++) {
-            st[d] = tab[(st[d] << 8) | b];
+        for (int d = 0; d < NW * 4; d++) {
+            if (d < (int) nstates) {
+                st.set(d, tab[(st.get(d) << 8) | b]);
+            }
         }
     }
 
@@ -131,19 +214,25 @@ struct piece_consumer_t {
         if (piece >= npieces) {
             return;
         }
-        uint8_t *out = fn + piece * fs;
+        if (conv) {
 #pragma unroll
-        for (int d = 0; d < DV; d++) {
-            if (d < (int) fs) {
-                const uint32_t v = conv ? (((accmask >> d) & 1) ? acc : s) : st[d];
-                out[d] = (uint8_t) (d < (int) nstates ? v : 0);
+            for (int d = 0; d < NW * 4; d++) {
+                st.set(d, d < (int) nstates ? (((accmask >> d) & 1) ? acc : s) : 0);
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < NW * 4; d++) {
+                if (d >= (int) nstates) {
+                    st.set(d, 0);
+                }
             }
         }
+        st.store(fn + piece * (NW * 4));
     }
 };
 
-template <int DV, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int NW>
+__global__ void __launch_bounds__(1024, 1)
 k_stream_pieces(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t npieces, uint8_t *fn)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -152,12 +241,11 @@ k_stream_pieces(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, siz
     __syncthreads();
 
     const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
-    piece_consumer_t<DV> cons;
+    piece_consumer_t<NW> cons;
     cons.tab = smem;
     cons.fn = fn;
     cons.nstates = dfa.nstates;
     cons.acc = dfa.acc;
-    cons.fs = fn_stride(dfa.nstates);
     cons.npieces = npieces;
 
     /* rows = pieces: the stream is a {PIECE, npieces} byte tensor */
@@ -168,148 +256,197 @@ k_stream_pieces(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, siz
                                (size_t) gridDim.x * warps_per_block);
 }
 
-/* transfer function of the ragged tail (< PIECE bytes), one thread per state */
-__global__ void k_stream_tail(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, uint8_t *out)
+/* function of bytes [begin, end) computed from every entry state (global table) */
+template <int NW>
+__device__ __forceinline__ void span_function(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t begin,
+                                              size_t end, fn_t<NW> &f)
 {
-    const uint32_t d = threadIdx.x;
-    if (d >= fn_stride(dfa.nstates)) {
-        return;
-    }
-    uint32_t s = d < dfa.nstates ? d : 0;
-    for (size_t i = 0; i < len; i++) {
-        s = dfa.t256[(s << 8) | buf[i]];
-    }
-    out[d] = (uint8_t) (d < dfa.nstates ? s : 0);
-}
-
-/* a function record held in registers: byte k of a 16/32-byte record */
-struct fn_rec_t {
-    uint4 lo, hi;
-    __device__ __forceinline__ void load(const uint8_t *p, uint32_t fs)
-    {
-        lo = *reinterpret_cast<const uint4 *>(p);
-        if (fs > 16) {
-            hi = *reinterpret_cast<const uint4 *>(p + 16);
+    f.identity();
+    for (size_t i = begin; i < end; i++) {
+        const uint32_t b = buf[i];
+#pragma unroll
+        for (int d = 0; d < NW * 4; d++) {
+            if (d < (int) dfa.nstates) {
+                f.set(d, __ldg(dfa.t256 + ((f.get(d) << 8) | b)));
+            }
         }
     }
-    __device__ __forceinline__ uint32_t at(uint32_t k) const
-    {
-        const uint4 &q = (k & 16) ? hi : lo;
-        const uint32_t w = (k & 8) ? ((k & 4) ? q.w : q.z) : ((k & 4) ? q.y : q.x);
-        return (w >> ((k & 3) * 8)) & 0xff;
-    }
-};
-
-/* out[i] = in[i*FAN + last] o ... o in[i*FAN].  The record loads do not depend
- * on the running composition, so they pipeline; only register selects do. */
-template <int DV>
-__global__ void __launch_bounds__(128)
-k_stream_compose(const uint8_t *__restrict__ in, size_t n_in, uint8_t *__restrict__ out, size_t n_out,
-                 uint32_t nstates, uint32_t fs)
-{
-    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_out) {
-        return;
-    }
-    uint32_t cur[DV];
 #pragma unroll
-    for (int d = 0; d < DV; d++) {
-        cur[d] = d;
-    }
-    const size_t first = i * FAN, last = first + FAN < n_in ? first + FAN : n_in;
-#pragma unroll 4
-    for (size_t j = first; j < last; j++) {
-        fn_rec_t f;
-        f.load(in + j * fs, fs);
-#pragma unroll
-        for (int d = 0; d < DV; d++) {
-            cur[d] = f.at(cur[d]);
+    for (int d = 0; d < NW * 4; d++) {
+        if (d >= (int) dfa.nstates) {
+            f.set(d, 0);
         }
     }
-    uint8_t *o = out + i * fs;
+}
+
+/* the ragged tail (< PIECE bytes): one warp, 128-byte sub-chunks per lane */
+template <int NW>
+__global__ void __launch_bounds__(32)
+k_stream_tail(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, uint8_t *out)
+{
+    const uint32_t lane = threadIdx.x;
+    const size_t sub = (len + 31) / 32;
+    const size_t b = lane * sub < len ? lane * sub : len, e = b + sub < len ? b + sub : len;
+    fn_t<NW> f;
+    span_function<NW>(dfa, buf, b, e, f);
+    warp_compose<NW>(f);
+    if (lane == 0) {
+        f.store(out);
+    }
+}
+
+/* ---- upper levels ------------------------------------------------------------------ */
+
+/* lane's local composition of its PER_LANE consecutive records */
+template <int NW>
+__device__ __forceinline__ void lane_compose(const uint8_t *in, size_t first, size_t n_in, fn_t<NW> &f)
+{
+    f.identity();
 #pragma unroll
-    for (int d = 0; d < DV; d++) {
-        o[d] = d < (int) nstates ? (uint8_t) cur[d] : 0;
-    }
-    for (uint32_t d = DV; d < fs; d++) {
-        o[d] = 0;
+    for (uint32_t k = 0; k < PER_LANE; k++) {
+        if (first + k < n_in) {
+            fn_t<NW> g;
+            g.load(in + (first + k) * (NW * 4));
+            f.then(g);
+        }
     }
 }
 
-/* serial walk of the top level: entry state of each element, stream exit */
-__global__ void k_stream_top(const uint8_t *__restrict__ fn, size_t n, uint32_t fs, uint32_t entry_state,
-                             uint8_t *entry, uint32_t *exit_state, unsigned long long *first_acc)
+/* out[w] = in[w*FAN + FAN-1] o ... o in[w*FAN], one warp per output */
+template <int NW>
+__global__ void __launch_bounds__(256)
+k_stream_compose(const uint8_t *__restrict__ in, size_t n_in, uint8_t *__restrict__ out, size_t n_out)
 {
-    uint32_t s = entry_state;
-    for (size_t j = 0; j < n; j++) {
-        entry[j] = (uint8_t) s;
-        s = fn[j * fs + s];
-    }
-    *exit_state = s;
-    *first_acc = ~0ull;
-}
-
-/* entries of level L from entries of level L+1; level 0 records first ACC */
-__global__ void __launch_bounds__(128)
-k_stream_entries(const uint8_t *__restrict__ fn, size_t n, uint32_t fs, const uint8_t *__restrict__ parent_entry,
-                 size_t n_parent, uint8_t *entry, uint32_t acc, int level0, unsigned long long *first_acc)
-{
-    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_parent) {
+    const size_t w = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (w >= n_out) {
         return;
     }
-    uint32_t s = parent_entry[i];
-    const size_t first = i * FAN, last = first + FAN < n ? first + FAN : n;
+    fn_t<NW> f;
+    lane_compose<NW>(in, w * FAN + lane * PER_LANE, n_in, f);
+    warp_compose<NW>(f);
+    if (lane == 0) {
+        f.store(out + w * (NW * 4));
+    }
+}
+
+/*
+ * One warp per parent p: from the exact entry state of p (parent_entry[p], or
+ * root_state when parent_entry is NULL) compute the exact entry state of each
+ * of its <= FAN children at this level.  exit_state (may be NULL) receives the
+ * state after the last child of parent 0.  At level 0, first_acc is lowered to
+ * the first child whose step enters ACC.
+ */
+template <int NW>
+__global__ void __launch_bounds__(256)
+k_stream_entries(const uint8_t *__restrict__ fn, size_t n, const uint8_t *__restrict__ parent_entry,
+                 uint32_t root_state, size_t n_parent, uint8_t *entry, uint32_t acc, int level0,
+                 unsigned long long *first_acc, uint32_t *exit_state)
+{
+    const size_t p = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (p >= n_parent) {
+        return;
+    }
+    const size_t first = p * FAN + lane * PER_LANE;
+    fn_t<NW> total;
+    lane_compose<NW>(fn, first, n, total);
+
+    /* state entering each lane's run: serial over lanes, 32 cheap steps */
+    uint32_t s = parent_entry ? parent_entry[p] : root_state, mine = 0;
 #pragma unroll 4
-    for (size_t j = first; j < last; j++) {
-        fn_rec_t f;
-        f.load(fn + j * fs, fs);
-        if (entry) {
+    for (uint32_t l = 0; l < 32; l++) {
+        if (lane == l) {
+            mine = s;
+        }
+        s = __shfl_sync(0xffffffffu, total.at(s), l);
+    }
+    if (exit_state && p == 0 && lane == 0) {
+        *exit_state = s;
+    }
+
+    s = mine;
+#pragma unroll
+    for (uint32_t k = 0; k < PER_LANE; k++) {
+        const size_t j = first + k;
+        if (j < n) {
+            fn_t<NW> g;
+            g.load(fn + j * (NW * 4));
             entry[j] = (uint8_t) s;
+            const uint32_t nx = g.at(s);
+            if (level0 && nx == acc && s != acc) {
+                atomicMin(first_acc, (unsigned long long) j);
+            }
+            s = nx;
         }
-        const uint32_t nx = f.at(s);
-        if (level0 && nx == acc && s != acc) {
-            atomicMin(first_acc, (unsigned long long) j);
-        }
-        s = nx;
     }
 }
 
-/* exact offset (relative to buf) of the byte whose step enters ACC */
-__global__ void k_stream_locate(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len,
-                                const uint8_t *__restrict__ entry0, uint32_t entry_state_if_single,
-                                const unsigned long long *first_acc, long long *match_offset)
+__global__ void k_stream_reset(unsigned long long *first_acc) { *first_acc = ~0ull; }
+
+/* exact offset of the byte whose step enters ACC inside piece *first_acc */
+template <int NW>
+__global__ void __launch_bounds__(32)
+k_stream_locate(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len,
+                const uint8_t *__restrict__ entry0, const unsigned long long *first_acc,
+                long long *match_offset)
 {
+    const uint32_t lane = threadIdx.x;
     const unsigned long long piece = *first_acc;
     if (piece == ~0ull) {
-        *match_offset = -1;
+        if (lane == 0) {
+            *match_offset = -1;
+        }
         return;
     }
-    uint32_t s = entry0 ? entry0[piece] : entry_state_if_single;
     const size_t start = (size_t) piece * PIECE, end = start + PIECE < len ? start + PIECE : len;
-    for (size_t i = start; i < end; i++) {
-        s = dfa.t256[(s << 8) | buf[i]];
-        if (s == dfa.acc) {
-            *match_offset = (long long) i;
-            return;
+    const size_t sub = (end - start + 31) / 32;
+    const size_t b = start + lane * sub < end ? start + lane * sub : end, e = b + sub < end ? b + sub : end;
+    fn_t<NW> f;
+    span_function<NW>(dfa, buf, b, e, f);
+
+    uint32_t s = entry0[piece], mine = 0;
+    for (uint32_t l = 0; l < 32; l++) {
+        if (lane == l) {
+            mine = s;
         }
+        s = __shfl_sync(0xffffffffu, f.at(s), l);
     }
-    *match_offset = -1;     /* cannot happen */
+    /* the first lane whose sub-chunk takes a non-ACC state into ACC */
+    const bool hit = mine != dfa.acc && f.at(mine) == dfa.acc;
+    const uint32_t who = __ffs(__ballot_sync(0xffffffffu, hit));
+    if (who == 0) {
+        if (lane == 0) {
+            *match_offset = -1;     /* cannot happen */
+        }
+        return;
+    }
+    if (lane == who - 1) {
+        s = mine;
+        for (size_t i = b; i < e; i++) {
+            s = __ldg(dfa.t256 + ((s << 8) | buf[i]));
+            if (s == dfa.acc) {
+                *match_offset = (long long) i;
+                return;
+            }
+        }
+        *match_offset = -1;
+    }
 }
 
-template <int DV, int THREADS>
+template <int NW>
 cudaError_t launch_pieces(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t npieces, uint8_t *fn,
     cudaStream_t stream)
 {
     const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, false);
-    const int warps = THREADS / 32;
+    const int warps = 32;
     const size_t smem = plan.stage_ofs + (size_t) warps * 32 * 128;
     CUtensorMap tmap;
     cudaError_t err = make_row_tensor_map(&tmap, buf, npieces, PIECE, 128);
     if (err != cudaSuccess) {
         return err;
     }
-    auto kern = k_stream_pieces<DV, THREADS>;
+    auto kern = k_stream_pieces<NW>;
     static size_t smem_set = 0;
     if (smem > smem_set) {
         err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
@@ -324,8 +461,62 @@ cudaError_t launch_pieces(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t n
     if (grid > need) {
         grid = need;
     }
-    kern<<<(unsigned) grid, THREADS, smem, stream>>>(dfa, tmap, npieces, fn);
+    kern<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, npieces, fn);
     return cudaGetLastError();
+}
+
+int top_level(const sre_stream_ws_t &ws)
+{
+    int top = 0;
+    while (top < 3 && ws.count[top] > FAN) {
+        top++;
+    }
+    return top;
+}
+
+template <int NW>
+cudaError_t reduce_t(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t len, const sre_stream_ws_t &ws,
+    cudaStream_t stream, int *launches)
+{
+    cudaError_t err;
+    const uint32_t fs = NW * 4;
+    const size_t nfull = len / PIECE, tail = len % PIECE;
+    if (nfull) {
+        if (launches) ++*launches;
+        if ((err = launch_pieces<NW>(dfa, buf, nfull, ws.fn[0], stream)) != cudaSuccess) return err;
+    }
+    if (tail || len == 0) {
+        if (launches) ++*launches;
+        k_stream_tail<NW><<<1, 32, 0, stream>>>(dfa, buf + nfull * PIECE, tail, ws.fn[0] + nfull * fs);
+        if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    }
+    for (int l = 0; l < 3 && ws.count[l] > FAN; l++) {
+        const size_t n_out = ws.count[l + 1];
+        if (launches) ++*launches;
+        k_stream_compose<NW><<<(unsigned) ((n_out * 32 + 255) / 256), 256, 0, stream>>>(
+            ws.fn[l], ws.count[l], ws.fn[l + 1], n_out);
+        if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    }
+    return cudaSuccess;
+}
+
+template <int NW>
+cudaError_t walk_t(const sre_dev_dfa_t &dfa, uint32_t entry_state, const sre_stream_ws_t &ws,
+    uint32_t *exit_state, cudaStream_t stream, int *launches)
+{
+    cudaError_t err;
+    const int top = top_level(ws);
+    if (launches) ++*launches;
+    k_stream_reset<<<1, 1, 0, stream>>>(ws.first_acc);
+    for (int l = top; l >= 0; l--) {
+        const size_t n_parent = l == top ? 1 : ws.count[l + 1];
+        if (launches) ++*launches;
+        k_stream_entries<NW><<<(unsigned) ((n_parent * 32 + 255) / 256), 256, 0, stream>>>(
+            ws.fn[l], ws.count[l], l == top ? nullptr : ws.entry[l + 1], entry_state, n_parent, ws.entry[l],
+            dfa.acc, l == 0, ws.first_acc, l == top ? exit_state : nullptr);
+        if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace
@@ -342,39 +533,8 @@ uint32_t sre_stream_fn_stride(uint32_t nstates) { return fn_stride(nstates); }
 cudaError_t sre_launch_dfa_stream_reduce(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t len,
     const sre_stream_ws_t &ws, cudaStream_t stream, int *launches)
 {
-    cudaError_t err;
-    const uint32_t fs = fn_stride(dfa.nstates);
-    const size_t nfull = len / PIECE, tail = len % PIECE;
-
-    if (nfull) {
-        if (launches) ++*launches;
-        if (dfa.nstates <= 8) {
-            err = launch_pieces<8, 1024>(dfa, buf, nfull, ws.fn[0], stream);
-        } else if (dfa.nstates <= 16) {
-            err = launch_pieces<16, 768>(dfa, buf, nfull, ws.fn[0], stream);
-        } else {
-            err = launch_pieces<32, 512>(dfa, buf, nfull, ws.fn[0], stream);
-        }
-        if (err != cudaSuccess) return err;
-    }
-    if (tail || len == 0) {
-        if (launches) ++*launches;
-        k_stream_tail<<<1, 32, 0, stream>>>(dfa, buf + nfull * PIECE, tail, ws.fn[0] + nfull * fs);
-        if ((err = cudaGetLastError()) != cudaSuccess) return err;
-    }
-    for (int l = 0; l < 3 && ws.count[l] > FAN; l++) {
-        const size_t n_out = ws.count[l + 1];
-        if (launches) ++*launches;
-        if (dfa.nstates <= 16) {
-            k_stream_compose<16><<<(unsigned) ((n_out + 127) / 128), 128, 0, stream>>>(
-                ws.fn[l], ws.count[l], ws.fn[l + 1], n_out, dfa.nstates, fs);
-        } else {
-            k_stream_compose<32><<<(unsigned) ((n_out + 127) / 128), 128, 0, stream>>>(
-                ws.fn[l], ws.count[l], ws.fn[l + 1], n_out, dfa.nstates, fs);
-        }
-        if ((err = cudaGetLastError()) != cudaSuccess) return err;
-    }
-    return cudaSuccess;
+    return dfa.nstates <= 16 ? reduce_t<4>(dfa, buf, len, ws, stream, launches)
+                             : reduce_t<8>(dfa, buf, len, ws, stream, launches);
 }
 
 /*
@@ -385,39 +545,18 @@ cudaError_t sre_launch_dfa_stream_reduce(const sre_dev_dfa_t &dfa, const uint8_t
 cudaError_t sre_launch_dfa_stream_walk(const sre_dev_dfa_t &dfa, uint32_t entry_state,
     const sre_stream_ws_t &ws, uint32_t *exit_state, cudaStream_t stream, int *launches)
 {
-    cudaError_t err;
-    const uint32_t fs = fn_stride(dfa.nstates);
-    int top = 0;
-    while (top < 3 && ws.count[top] > FAN) {
-        top++;
-    }
-    if (launches) ++*launches;
-    k_stream_top<<<1, 1, 0, stream>>>(ws.fn[top], ws.count[top], fs, entry_state, ws.entry[top],
-                                      exit_state, ws.first_acc);
-    if ((err = cudaGetLastError()) != cudaSuccess) return err;
-
-    if (top == 0) {
-        /* single level (count[0] <= FAN): one thread looks for the first ACC */
-        if (launches) ++*launches;
-        k_stream_entries<<<1, 1, 0, stream>>>(ws.fn[0], ws.count[0], fs, ws.entry[0], 1, nullptr, dfa.acc,
-                                              1, ws.first_acc);
-        if ((err = cudaGetLastError()) != cudaSuccess) return err;
-    }
-    for (int l = top - 1; l >= 0; l--) {
-        const size_t n_parent = ws.count[l + 1];
-        if (launches) ++*launches;
-        k_stream_entries<<<(unsigned) ((n_parent + 127) / 128), 128, 0, stream>>>(
-            ws.fn[l], ws.count[l], fs, ws.entry[l + 1], n_parent, ws.entry[l], dfa.acc, l == 0,
-            ws.first_acc);
-        if ((err = cudaGetLastError()) != cudaSuccess) return err;
-    }
-    return cudaSuccess;
+    return dfa.nstates <= 16 ? walk_t<4>(dfa, entry_state, ws, exit_state, stream, launches)
+                             : walk_t<8>(dfa, entry_state, ws, exit_state, stream, launches);
 }
 
 cudaError_t sre_launch_dfa_stream_locate(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t len,
     const sre_stream_ws_t &ws, long long *dev_match_offset, cudaStream_t stream, int *launches)
 {
     if (launches) ++*launches;
-    k_stream_locate<<<1, 1, 0, stream>>>(dfa, buf, len, ws.entry[0], 0, ws.first_acc, dev_match_offset);
+    if (dfa.nstates <= 16) {
+        k_stream_locate<4><<<1, 32, 0, stream>>>(dfa, buf, len, ws.entry[0], ws.first_acc, dev_match_offset);
+    } else {
+        k_stream_locate<8><<<1, 32, 0, stream>>>(dfa, buf, len, ws.entry[0], ws.first_acc, dev_match_offset);
+    }
     return cudaGetLastError();
 }

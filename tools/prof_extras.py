@@ -42,3 +42,10 @@ timed("thompson lines C2 nfa", lambda: p2.thompson_lines(dev, m, 1024, 1024, eng
 timed("pike lines C3", lambda: p3.pike_lines(dev, m, 1024, 1024), m * 1024, reps=1)
 sel = p2.thompson_lines(dev, m, 1024, 1024)
 timed("pike lines C2 gated (10% hits)", lambda: p2.pike_lines(dev, m, 1024, 1024, select=sel), m * 1024, reps=1)
+pm = cuda.CudaProgram(corpus.multi_pattern_set(64))
+print("multi64: nfa", pm.info.nfa_states, "dfa", pm.info.dfa_states, "classes", pm.info.dfa_classes)
+timed("multi64 thompson gate (auto)", lambda: pm.thompson_lines(dev, n, 1024, 1024), flat.numel())
+timed("multi64 thompson nfa", lambda: pm.thompson_lines(dev, m, 1024, 1024, engine=cuda.ENGINE_NFA), m * 1024, reps=1)
+timed("multi64 pike (gate+hint inside)", lambda: pm.pike_lines(dev, m, 1024, 1024), m * 1024, reps=1)
+rcm, _ = pm.pike_lines(dev, m, 1024, 1024)
+print("multi64 matched fraction", float((rcm >= 0).float().mean()))
