@@ -309,32 +309,47 @@ def main():
             }
             assert cb["hits"] == int((host_rc[:ns] == 0).sum()), "CPU baseline disagrees with GPU verdicts"
 
-        # ---- extras: Pike + captures (C3) and the stream scan (C5 style) ----------
+        # ---- extras: the other BASELINE configs at bench size (not the headline) ----
         if not args.no_extras and world == 1:
             extra = {}
-            try:
-                p3 = cuda.CudaProgram(corpus.C3_REGEX)
-                m = min(n, 1 << 18)
-                prc = torch.empty(m, dtype=torch.int32, device="cuda")
-                pov = torch.empty((m, p3.nslots), dtype=torch.int64, device="cuda")
-                p3.pike_lines(dev, m, PITCH, PITCH, out_rc=prc, out_ovec=pov)
+
+            def timed_gbs(fn, nbytes, reps=2):
+                fn()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                p3.pike_lines(dev, m, PITCH, PITCH, out_rc=prc, out_ovec=pov)
+                for _ in range(reps):
+                    fn()
                 b.record()
                 torch.cuda.synchronize()
-                extra["pike_c3_gbs"] = m * PITCH / (a.elapsed_time(b) * 1e-3) / 1e9
-                extra["pike_c3_lines"] = m
+                return nbytes * reps / (a.elapsed_time(b) * 1e-3) / 1e9
+
+            try:
+                # C3: Pike with 4 capture groups over every line (gate + start hint + Pike kernels)
+                p3 = cuda.CudaProgram(corpus.C3_REGEX)
+                prc = torch.empty(n, dtype=torch.int32, device="cuda")
+                pov = torch.empty((n, p3.nslots), dtype=torch.int64, device="cuda")
+                extra["c3_pike_4groups_gbs"] = timed_gbs(
+                    lambda: p3.pike_lines(dev, n, PITCH, PITCH, out_rc=prc, out_ovec=pov), n * PITCH)
+                extra["c3_lines"] = n
+                extra["c3_matched_lines"] = int((prc == 0).sum())
+                # C4: 64-pattern set: which pattern matched (Thompson gate, then Pike on the hits)
+                pm = cuda.CudaProgram(corpus.multi_pattern_set(64))
+                m = min(n, 1 << 17)
+                extra["c4_multi64_gate_gbs"] = timed_gbs(lambda: pm.thompson_lines(dev, n, PITCH, PITCH), n * PITCH)
+                mrc = torch.empty(m, dtype=torch.int32, device="cuda")
+                mov = torch.empty((m, pm.nslots), dtype=torch.int64, device="cuda")
+                extra["c4_multi64_id_gbs"] = timed_gbs(
+                    lambda: pm.pike_lines(dev, m, PITCH, PITCH, out_rc=mrc, out_ovec=mov), m * PITCH, reps=1)
+                extra["c4_lines"] = m
+                extra["c4_matched_fraction"] = float((mrc >= 0).float().mean())
+                extra["c4_dfa_states"] = pm.info.dfa_states
+                # C5: one stream, chunk-parallel transfer-function scan (the whole resident corpus
+                # as a single stream, 64 KB reference chunks)
                 p1 = cuda.CudaProgram(corpus.BENCH_REGEX)
                 flat = dev.view(-1)
-                p1.thompson_stream(flat, flat.numel(), 65536, True)
-                a.record()
-                for _ in range(3):
-                    p1.thompson_stream(flat, flat.numel(), 65536, True)
-                b.record()
-                torch.cuda.synchronize()
-                extra["stream_scan_gbs"] = 3 * flat.numel() / (a.elapsed_time(b) * 1e-3) / 1e9
-                extra["stream_bytes"] = flat.numel()
+                extra["c5_stream_scan_gbs"] = timed_gbs(
+                    lambda: p1.thompson_stream(flat, flat.numel(), 65536, True), flat.numel(), reps=3)
+                extra["c5_stream_bytes"] = flat.numel()
             except Exception as e:      # extras never break the headline line
                 extra["error"] = repr(e)
             out["extra"] = extra
