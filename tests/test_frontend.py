@@ -37,3 +37,58 @@ def test_flags_newline_and_counted(oracle, ref):
              (rb"(?:a|)(|b)\b\B\A\z^$", 0), (rb"[]a][^]a][a\-z][-a][a-]", 0)]
     for rx, fl in cases:
         assert oracle.compile(rx, fl).dump() == ref.compile(rx, fl).dump(), rx
+
+
+def test_random_regex_fuzz_against_live_reference(oracle, ref):
+    """Seeded random regex strings over the metacharacter alphabet: same program
+    dump, same capture count, or the same syntax-error offset as the reference
+    (needs oracle/_ref, i.e. runs in the build container)."""
+    import random
+    rng = random.Random(0x5EED)
+    atoms = ["a", "b", "c", "Z", "0", "9", " ", "\n", ".", "^", "$", "|", "(", ")", "(?:", "[", "]", "[^", "-",
+             "*", "+", "?", "{2}", "{1,3}", "{0,}", "{,2}", "{3,1}", "{", "}", ":", "\\d", "\\D", "\\w", "\\W", "\\s",
+             "\\S", "\\b", "\\B", "\\A", "\\z", "\\Z", "\\h", "\\H", "\\v", "\\V", "\\N", "\\C", "\\n", "\\t", "\\e",
+             "\\x41", "\\x{4a}", "\\x{123}", "\\o{101}", "\\o{777}", "\\101", "\\0", "\\1", "\\8", "\\cA", "\\c",
+             "\\", "\\\\", "\\.", "\\[", "\\-", "\\#", "\\p", "é", "{500}", "{499}", "a{2}{3}", "x**"]
+    same = errs = 0
+    for i in range(4000):
+        rx = "".join(rng.choice(atoms) for _ in range(rng.randrange(1, 9))).encode("latin-1")
+        if b"\0" in rx:
+            continue
+        flags = rng.choice([0, 0, capi.SRE_REGEX_CASELESS, capi.SRE_REGEX_NEWLINE, 3])
+        try:
+            pr = ref.compile(rx, flags)
+            want = ("ok", pr.ncaps, pr.dump())
+            pr.close()
+        except capi.SreSyntaxError as e:
+            want = ("err", e.offset)
+            errs += 1
+        try:
+            po = oracle.compile(rx, flags)
+            got = ("ok", po.ncaps, po.dump())
+            po.close()
+        except capi.SreSyntaxError as e:
+            got = ("err", e.offset)
+        assert got == want, (rx, flags, got[:2], want[:2])
+        same += 1
+    assert same > 3500 and 500 < errs < 3500
+
+
+def test_random_multi_regex_fuzz_against_live_reference(oracle, ref):
+    import random
+    rng = random.Random(7)
+    pool = [rb"a(b)c", rb"x|y(z)", rb"\d+", rb"(", rb"[a-", rb"(?:q)*?", rb"^w$", rb"(a)(b)(c)", rb"", rb"a{2,1}"]
+    for _ in range(300):
+        pats = [rng.choice(pool) for _ in range(rng.randrange(1, 5))]
+        flags = [rng.choice([0, 1]) for _ in pats]
+        try:
+            pr = ref.compile(pats, flags, multi=True)
+            want = ("ok", pr.ncaps, pr.dump())
+        except capi.SreSyntaxError as e:
+            want = ("err", e.offset, e.regex_id)
+        try:
+            po = oracle.compile(pats, flags, multi=True)
+            got = ("ok", po.ncaps, po.dump())
+        except capi.SreSyntaxError as e:
+            got = ("err", e.offset, e.regex_id)
+        assert got == want, (pats, flags)

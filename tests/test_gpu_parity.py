@@ -324,3 +324,58 @@ def test_full_size_properties(cu):
     sub = 1 << 16
     rc3 = prog.thompson_lines(dev, sub, 1024, 1024, engine=cu.ENGINE_NFA)
     assert torch.equal(rc[:sub], rc3)
+
+
+def test_random_regex_fuzz_gpu_vs_oracle(cu):
+    """Seeded random regexes (assertions, nested repetition, classes) x batches of
+    random short lines: every Thompson tier and the Pike path (rc + ovector)
+    against the CPU oracle."""
+    import random
+    rng = random.Random(99)
+    atoms = ["a", "b", "ab", " ", "\\n", "_", ".", "^", "$", "\\b", "\\B", "\\A", "\\z", "|", "(", ")", "(?:", "*",
+             "+", "?", "*?", "+?", "??", "{2}", "{0,2}", "{1,}", "[ab]", "[^a]", "\\w", "\\W", "\\s", "\\d", "1"]
+    alphabet = list(b"ab \n_1.")
+    o = capi.load("oracle")
+    done = 0
+    nlines, pitch = 96, 32
+    while done < 150:
+        rx = "".join(rng.choice(atoms) for _ in range(rng.randrange(1, 8))).encode()
+        try:
+            po = o.compile(rx, 0)
+        except capi.SreSyntaxError:
+            continue
+        done += 1
+        linelen = rng.choice([0, 1, 7, 16, 17, 31, 32])
+        host = np.array([rng.choice(alphabet) for _ in range(nlines * pitch)], dtype=np.uint8).reshape(nlines, pitch)
+        prog = cu.CudaProgram(rx)
+        _, want_t, _ = baseline.run_lines("oracle", rx, None, host, nlines, pitch, linelen, baseline.ENGINE_THOMPSON)
+        _, want_rc, want_ov = baseline.run_lines("oracle", rx, None, host, nlines, pitch, linelen,
+                                                 baseline.ENGINE_PIKE, ovec_slots=prog.nslots)
+        dev = torch.from_numpy(host).cuda()
+        engines = [cu.ENGINE_AUTO, cu.ENGINE_NFA]
+        if prog.info.dfa_states:
+            engines += [cu.ENGINE_DFA_TILED, cu.ENGINE_DFA_GENERIC]
+        if prog.info.dfa_leave_bytes:
+            engines.append(cu.ENGINE_DFA_SKIP)
+        for e in engines:
+            got = prog.thompson_lines(dev, nlines, pitch, linelen, engine=e).cpu().numpy()
+            assert (got == want_t).all(), (rx, linelen, e)
+        rc, ov = prog.pike_lines(dev, nlines, pitch, linelen)
+        assert (rc.cpu().numpy() == want_rc).all(), (rx, linelen)
+        assert (ov.cpu().numpy() == want_ov).all(), (rx, linelen)
+        prog.program.close()
+        po.close()
+
+
+def test_unaligned_and_padded_lines(cu):
+    """base pointer off by one (generic tier), pitch > linelen with junk between lines"""
+    n = 200
+    lines = corpus.log_lines(n, 1024)
+    prog = cu.CudaProgram(corpus.C2_REGEX)
+    _, want, _ = baseline.run_lines("oracle", corpus.C2_REGEX, None, lines.numpy(), n, 1024, 1000,
+                                    baseline.ENGINE_THOMPSON)
+    shifted = torch.cat([torch.zeros(1, dtype=torch.uint8), lines.view(-1)]).cuda()
+    got = prog.thompson_lines(shifted[1:], n, 1024, 1000)
+    assert (got.cpu().numpy() == want).all()
+    got = prog.thompson_lines(lines.cuda(), n, 1024, 1000)
+    assert (got.cpu().numpy() == want).all()

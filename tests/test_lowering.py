@@ -91,3 +91,48 @@ def test_pike_start_hint_never_passes_the_match_start(golden, oracle, lc):
         lc.lc_destroy(h)
         p.close()
     assert checked > 1000
+
+
+def test_random_regex_fuzz_lowering_vs_live_reference(oracle, ref, lc):
+    """Random regexes (heavy on assertions and nested repetition) x random
+    subjects: the lowered NFA / DFA verdicts and the oracle's Pike results
+    against the reference itself, single buffer and split at a random point."""
+    import random
+    rng = random.Random(2026)
+    atoms = ["a", "b", "ab", " ", "\\n", "_", ".", "^", "$", "\\b", "\\B", "\\A", "\\z", "|", "(", ")", "(?:", "*",
+             "+", "?", "*?", "+?", "??", "{2}", "{0,2}", "{1,}", "[ab]", "[^a]", "\\w", "\\W", "\\s", "\\d", "1"]
+    alphabet = b"ab \n_1."
+    tried = 0
+    for _ in range(1500):
+        rx = "".join(rng.choice(atoms) for _ in range(rng.randrange(1, 8))).encode()
+        try:
+            pr = ref.compile(rx, 0)
+        except capi.SreSyntaxError:
+            continue
+        po = oracle.compile(rx, 0)
+        h = lc.lc_create(po.prog, 4096)
+        info = (C.c_uint * 6)()
+        lc.lc_info(h, info)
+        tried += 1
+        for _ in range(6):
+            s = bytes(rng.choice(alphabet) for _ in range(rng.randrange(0, 12)))
+            want = ref.thompson(pr, s)
+            lc.lc_reset(h)
+            assert lc.lc_nfa_exec(h, s, len(s), 1) == want, (rx, s)
+            if info[3]:
+                lc.lc_reset(h)
+                assert lc.lc_dfa_exec(h, s, len(s), 1, 1) == want, (rx, s)
+            prc, pov = ref.pike(pr, s)
+            assert oracle.pike(po, s) == (prc, pov), (rx, s)
+            assert oracle.thompson(po, s) == want, (rx, s)
+            if prc >= 0:
+                hint = lc.lc_hint_cls(h, s, len(s))
+                assert hint <= pov[0], (rx, s, hint, pov)
+            cut = rng.randrange(0, len(s) + 1)
+            chunks = [(s[:cut], False), (s[cut:], True)]
+            lc.lc_reset(h)
+            assert _stream(lambda c, n, e: lc.lc_nfa_exec(h, c, n, e), chunks)[-1] == want, (rx, s, cut)
+        lc.lc_destroy(h)
+        po.close()
+        pr.close()
+    assert tried > 600
