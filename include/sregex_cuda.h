@@ -129,6 +129,7 @@ SRE_API int sre_cuda_pike_exec_lines_host(sre_cuda_program_t *cp,
 SRE_API void sre_cuda_set_variant(int variant);     /* tile shape of DFA_TILED   */
 SRE_API void sre_cuda_set_l2_promotion(int mode);   /* TMA L2 promotion: 0..3    */
 SRE_API void sre_cuda_set_pike_general_only(int on);/* 1: skip the smem Pike tier */
+SRE_API void sre_cuda_set_stream_piece(int bytes);  /* stream scan piece: 1024..8192 */
 SRE_API long sre_cuda_launch_count(int reset);      /* kernels launched so far   */
 SRE_API int sre_cuda_device_available(void);        /* 1 if a CUDA device works  */
 SRE_API const char *sre_cuda_last_error(void);

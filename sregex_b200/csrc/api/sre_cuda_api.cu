@@ -462,6 +462,7 @@ SRE_API int sre_cuda_device_available(void) { return device_ok() ? 1 : 0; }
 SRE_API const char *sre_cuda_last_error(void) { return g_err; }
 SRE_API void sre_cuda_set_variant(int variant) { g_variant = variant; }
 SRE_API void sre_cuda_set_pike_general_only(int on) { g_pike_general_only = on; }
+SRE_API void sre_cuda_set_stream_piece(int bytes) { sre_stream_set_piece_bytes((uint32_t) bytes); }
 SRE_API void sre_cuda_set_l2_promotion(int mode) { sre_dev_set_l2_promotion(mode); }
 
 SRE_API long sre_cuda_launch_count(int reset)

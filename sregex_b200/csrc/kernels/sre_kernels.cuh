@@ -145,6 +145,7 @@ struct sre_stream_ws_t {        /* workspace owned by the caller              */
     unsigned long long *first_acc;  /* first piece whose exit is ACC          */
 };
 size_t sre_stream_piece_bytes(void);
+void sre_stream_set_piece_bytes(uint32_t bytes);   /* 1024, 2048, 4096 (default) or 8192 */
 cudaError_t sre_launch_dfa_stream_reduce(const sre_dev_dfa_t &dfa, const uint8_t *buf,
     size_t len, const sre_stream_ws_t &ws, cudaStream_t stream, int *launches);
 cudaError_t sre_launch_dfa_stream_walk(const sre_dev_dfa_t &dfa, uint32_t entry_state,

@@ -34,7 +34,7 @@ using namespace sre_dev;
 
 namespace {
 
-constexpr uint32_t PIECE = 4096;    /* bytes per level-0 piece                */
+uint32_t g_piece = 4096;            /* bytes per level-0 piece (1024..8192, power of two) */
 constexpr uint32_t FAN = 256;       /* functions composed per warp            */
 constexpr uint32_t PER_LANE = FAN / 32;
 
@@ -233,7 +233,8 @@ struct piece_consumer_t {
 
 template <int NW>
 __global__ void __launch_bounds__(1024, 1)
-k_stream_pieces(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t npieces, uint8_t *fn)
+k_stream_pieces(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t npieces, uint8_t *fn,
+                uint32_t PIECE)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, false);
@@ -389,7 +390,7 @@ template <int NW>
 __global__ void __launch_bounds__(32)
 k_stream_locate(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len,
                 const uint8_t *__restrict__ entry0, const unsigned long long *first_acc,
-                long long *match_offset)
+                long long *match_offset, uint32_t PIECE)
 {
     const uint32_t lane = threadIdx.x;
     const unsigned long long piece = *first_acc;
@@ -441,6 +442,7 @@ cudaError_t launch_pieces(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t n
     const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, false);
     const int warps = 32;
     const size_t smem = plan.stage_ofs + (size_t) warps * 32 * 128;
+    const uint32_t PIECE = g_piece;
     CUtensorMap tmap;
     cudaError_t err = make_row_tensor_map(&tmap, buf, npieces, PIECE, 128);
     if (err != cudaSuccess) {
@@ -461,7 +463,7 @@ cudaError_t launch_pieces(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t n
     if (grid > need) {
         grid = need;
     }
-    kern<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, npieces, fn);
+    kern<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, npieces, fn, PIECE);
     return cudaGetLastError();
 }
 
@@ -479,7 +481,7 @@ cudaError_t reduce_t(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t len, c
     cudaStream_t stream, int *launches)
 {
     cudaError_t err;
-    const uint32_t fs = NW * 4;
+    const uint32_t fs = NW * 4, PIECE = g_piece;
     const size_t nfull = len / PIECE, tail = len % PIECE;
     if (nfull) {
         if (launches) ++*launches;
@@ -521,7 +523,13 @@ cudaError_t walk_t(const sre_dev_dfa_t &dfa, uint32_t entry_state, const sre_str
 
 }  // namespace
 
-size_t sre_stream_piece_bytes(void) { return PIECE; }
+size_t sre_stream_piece_bytes(void) { return g_piece; }
+void sre_stream_set_piece_bytes(uint32_t b)
+{
+    if (b == 1024 || b == 2048 || b == 4096 || b == 8192) {
+        g_piece = b;
+    }
+}
 uint32_t sre_stream_fan(void) { return FAN; }
 uint32_t sre_stream_fn_stride(uint32_t nstates) { return fn_stride(nstates); }
 
@@ -554,9 +562,11 @@ cudaError_t sre_launch_dfa_stream_locate(const sre_dev_dfa_t &dfa, const uint8_t
 {
     if (launches) ++*launches;
     if (dfa.nstates <= 16) {
-        k_stream_locate<4><<<1, 32, 0, stream>>>(dfa, buf, len, ws.entry[0], ws.first_acc, dev_match_offset);
+        k_stream_locate<4><<<1, 32, 0, stream>>>(dfa, buf, len, ws.entry[0], ws.first_acc, dev_match_offset,
+                                                 g_piece);
     } else {
-        k_stream_locate<8><<<1, 32, 0, stream>>>(dfa, buf, len, ws.entry[0], ws.first_acc, dev_match_offset);
+        k_stream_locate<8><<<1, 32, 0, stream>>>(dfa, buf, len, ws.entry[0], ws.first_acc, dev_match_offset,
+                                                 g_piece);
     }
     return cudaGetLastError();
 }
