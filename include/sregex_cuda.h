@@ -86,6 +86,19 @@ SRE_API int sre_cuda_pike_exec_lines(sre_cuda_program_t *cp,
     int64_t *dev_ovec, size_t ovec_slots, void *stream);
 
 /*
+ * Global scan: all non-overlapping matches of every line, i.e. the batch form of
+ * calling sre_vm_pike_exec again after each match on the rest of the data (the
+ * post-match continuation of sre_vm_pike.c:624-635 incl. the one-byte skip after
+ * an empty match, :179-193 -- what ngx_replace_filter does).  Per line at most
+ * max_matches matches: dev_count[i], dev_spans[i][k] = ($0 start, $0 end),
+ * dev_ids[i][k] = regex id.
+ */
+SRE_API int sre_cuda_pike_exec_lines_all(sre_cuda_program_t *cp,
+    const uint8_t *dev_buf, const int64_t *dev_offsets, size_t nlines,
+    size_t pitch, size_t linelen, size_t max_matches, int32_t *dev_count,
+    int64_t *dev_spans, int32_t *dev_ids, void *stream);
+
+/*
  * Chunk-parallel form of a sequence of sre_vm_thompson_exec(ctx, chunk_k,
  * chunk_bytes, eof) calls over one long stream resident on the device.
  * *state_io carries the automaton state across calls (set it to

@@ -218,6 +218,30 @@ class SreLib:
             L.sre_destroy_pool(pool)
 
 
+def pike_all(lib: "SreLib", p: Program, data: bytes, limit: int = 64):
+    """All non-overlapping matches through the classic API: after a match the
+    same ctx is given the rest of the data from ovector[1] on (post-match
+    continuation, sre_vm_pike.c:624-635).  -> list of (rc, start, end)"""
+    L = lib.L
+    pool = L.sre_create_pool(1024)
+    n = p.nslots
+    ov = (C.c_ssize_t * n)(*([-99] * n))
+    out = []
+    try:
+        ctx = L.sre_vm_pike_create_ctx(pool, p.prog, ov, n * C.sizeof(C.c_ssize_t))
+        at = 0
+        buf = C.create_string_buffer(data, len(data) + 1)
+        while len(out) < limit:
+            rc = L.sre_vm_pike_exec(ctx, C.cast(C.addressof(buf) + at, C.c_void_p), len(data) - at, 1, None)
+            if rc < 0:
+                break
+            out.append((rc, ov[0], ov[1]))
+            at = ov[1]
+    finally:
+        L.sre_destroy_pool(pool)
+    return out
+
+
 def split_chunks(data: bytes):
     """The reference CLI's "splitted" feeding pattern (src/sre_cli.c:369-385):
     an empty non-eof chunk before every 1-byte chunk, then an empty eof chunk."""

@@ -633,6 +633,32 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
 }
 
 SRE_API int
+sre_cuda_pike_exec_lines_all(sre_cuda_program_t *cp, const uint8_t *dev_buf, const int64_t *dev_offsets,
+    size_t nlines, size_t pitch, size_t linelen, size_t max_matches, int32_t *dev_count, int64_t *dev_spans,
+    int32_t *dev_ids, void *stream)
+{
+    if (cp == NULL || max_matches == 0) {
+        return fail("NULL program or max_matches == 0");
+    }
+    if (nlines == 0) {
+        return SRE_OK;
+    }
+    if (ensure_pike_scratch(cp, nlines) != SRE_OK) {
+        return SRE_ERROR;
+    }
+    int launches = 0;
+    cudaError_t err = sre_launch_pike_lines_all(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen,
+                                                (uint32_t) max_matches, dev_count, dev_spans, dev_ids,
+                                                cp->pike_scratch, cp->pike_nctx < nlines ? cp->pike_nctx : nlines,
+                                                as_stream(stream), &launches);
+    count_launches(launches);
+    if (err != cudaSuccess) {
+        return fail("Pike kernel launch failed: %s", cudaGetErrorString(err));
+    }
+    return SRE_OK;
+}
+
+SRE_API int
 sre_cuda_thompson_stream_reduce(sre_cuda_program_t *cp, const uint8_t *dev_buf, size_t len,
     uint8_t *host_fn, void *stream)
 {

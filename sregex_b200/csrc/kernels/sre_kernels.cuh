@@ -130,6 +130,12 @@ cudaError_t sre_launch_pike_small(const sre_dev_pike_t &pk, const uint8_t *buf,
     const int32_t *select, const int32_t *start, int32_t *rc, int64_t *ovec,
     uint32_t ovec_slots, cudaStream_t stream, int *launches);
 
+/* all non-overlapping matches per line (post-match continuation, global scan)  */
+cudaError_t sre_launch_pike_lines_all(const sre_dev_pike_t &pk, const uint8_t *buf,
+    const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen, uint32_t max_matches,
+    int32_t *count, int64_t *spans, int32_t *ids, uint8_t *scratch, size_t nctx,
+    cudaStream_t stream, int *launches);
+
 /* Pike VM streaming step on one persistent context (classic API)             */
 cudaError_t sre_launch_pike_stream(const sre_dev_pike_t &pk, uint8_t *ctx,
     const uint8_t *buf, size_t len, int eof, int want_pending, int64_t *out,

@@ -715,6 +715,55 @@ k_pike_lines(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
     }
 }
 
+/*
+ * All non-overlapping matches of every line: the reference's post-match
+ * continuation (sre_vm_pike.c:624-635: after a match the ctx restarts at
+ * ovector[1], and skips one byte after an empty match, :179-193), i.e. what
+ * ngx_replace_filter does for global substitution, as one batch call.
+ * spans[line][k] = ($0 start, $0 end) absolute in the line, ids[line][k] =
+ * regex id, count[line] = matches found (capped at max_matches).
+ */
+__global__ void __launch_bounds__(128)
+k_pike_lines_all(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
+                 size_t nlines, size_t pitch, size_t linelen, uint32_t max_matches,
+                 int32_t *__restrict__ count, int64_t *__restrict__ spans, int32_t *__restrict__ ids,
+                 uint8_t *scratch, size_t nctx)
+{
+    const size_t tid = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= nctx) {
+        return;
+    }
+    pike_ctx_t c = pike_carve(pk, scratch + tid * pk.ctx_stride);
+    for (uint32_t i = 0; i <= pk.len; i++) {
+        c.tags[i] = 0;
+    }
+    bool first = true;
+    for (size_t line = tid; line < nlines; line += nctx) {
+        const size_t start = offsets ? (size_t) offsets[line] : line * pitch;
+        const int64_t len = (int64_t) (offsets ? (size_t) offsets[line + 1] - start : linelen);
+        pike_reset(c, first);
+        first = false;
+        uint32_t m = 0;
+        int64_t at = 0, ov[2];
+        while (m < max_matches) {
+            int pending;
+            const int r = pike_exec(pk, c, buf + start + at, len - at, true, ov, 2, &pending);
+            if (r < 0) {
+                break;
+            }
+            spans[(line * max_matches + m) * 2] = ov[0];
+            spans[(line * max_matches + m) * 2 + 1] = ov[1];
+            ids[line * max_matches + m] = r;
+            m++;
+            at = ov[1];
+            if (c.h->eof) {
+                break;
+            }
+        }
+        count[line] = (int32_t) m;
+    }
+}
+
 __global__ void k_pike_ctx_init(sre_dev_pike_t pk, uint8_t *ctx)
 {
     pike_ctx_t c = pike_carve(pk, ctx);
@@ -759,6 +808,22 @@ cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
     const unsigned grid = (unsigned) ((nctx + 127) / 128);
     k_pike_lines<<<grid, 128, 0, stream>>>(pk, buf, offsets, nlines, pitch, linelen, select, start, rc, ovec,
                                           ovec_slots, scratch, nctx, retry_only);
+    return cudaGetLastError();
+}
+
+cudaError_t sre_launch_pike_lines_all(const sre_dev_pike_t &pk, const uint8_t *buf, const int64_t *offsets,
+    size_t nlines, size_t pitch, size_t linelen, uint32_t max_matches, int32_t *count, int64_t *spans,
+    int32_t *ids, uint8_t *scratch, size_t nctx, cudaStream_t stream, int *launches)
+{
+    if (nlines == 0 || nctx == 0) {
+        return cudaSuccess;
+    }
+    if (launches) {
+        ++*launches;
+    }
+    const unsigned grid = (unsigned) ((nctx + 127) / 128);
+    k_pike_lines_all<<<grid, 128, 0, stream>>>(pk, buf, offsets, nlines, pitch, linelen, max_matches, count,
+                                              spans, ids, scratch, nctx);
     return cudaGetLastError();
 }
 

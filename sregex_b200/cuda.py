@@ -35,6 +35,7 @@ def lib():
             "sre_cuda_thompson_exec_lines": (C.c_int, [vp, vp, sz, sz, sz, i32p, C.c_int, vp]),
             "sre_cuda_thompson_exec_ragged": (C.c_int, [vp, vp, i64p, sz, i32p, C.c_int, vp]),
             "sre_cuda_pike_exec_lines": (C.c_int, [vp, vp, i64p, sz, sz, sz, i32p, i32p, i64p, sz, vp]),
+            "sre_cuda_pike_exec_lines_all": (C.c_int, [vp, vp, i64p, sz, sz, sz, sz, i32p, i64p, i32p, vp]),
             "sre_cuda_thompson_exec_stream": (C.c_int, [vp, vp, sz, sz, C.c_uint, C.POINTER(C.c_uint32),
                                                         C.POINTER(C.c_int64), vp]),
             "sre_cuda_thompson_stream_reduce": (C.c_int, [vp, vp, sz, C.c_char_p, vp]),
@@ -118,6 +119,17 @@ class CudaProgram:
             linelen, select.data_ptr() if select is not None else None, rc.data_ptr(), ov.data_ptr(), n,
             _stream_ptr()))
         return rc, ov
+
+    def pike_lines_all(self, buf: torch.Tensor, nlines: int, pitch: int, linelen: int, max_matches: int,
+                       offsets: torch.Tensor | None = None):
+        """-> (count int32[n], spans int64[n, max_matches, 2], ids int32[n, max_matches])"""
+        count = torch.zeros(nlines, dtype=torch.int32, device=buf.device)
+        spans = torch.full((nlines, max_matches, 2), -1, dtype=torch.int64, device=buf.device)
+        ids = torch.full((nlines, max_matches), -1, dtype=torch.int32, device=buf.device)
+        _check(self.lib.L.sre_cuda_pike_exec_lines_all(
+            self.cp, buf.data_ptr(), offsets.data_ptr() if offsets is not None else None, nlines, pitch,
+            linelen, max_matches, count.data_ptr(), spans.data_ptr(), ids.data_ptr(), _stream_ptr()))
+        return count, spans, ids
 
     def thompson_stream(self, buf: torch.Tensor, length: int, chunk_bytes: int, eof: bool,
                         state: int = STATE_INIT):

@@ -379,3 +379,29 @@ def test_unaligned_and_padded_lines(cu):
     assert (got.cpu().numpy() == want).all()
     got = prog.thompson_lines(lines.cuda(), n, 1024, 1000)
     assert (got.cpu().numpy() == want).all()
+
+
+def test_global_scan_classic_and_batch(golden, cuda, cu):
+    """all non-overlapping matches: the classic ctx continuation on the GPU and the
+    batch entry point sre_cuda_pike_exec_lines_all, against the oracle"""
+    o = capi.load("oracle")
+    for b in runnable(golden)[::40]:
+        po = o.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        pc = cuda.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        s = b["subject_b"] * 3
+        assert capi.pike_all(cuda, pc, s) == capi.pike_all(o, po, s), (b["file"], b["name"])
+        po.close()
+        pc.close()
+    # batch: a few lines of log text, several matches per line
+    rx = rb"(\d+)\.|HTTP"
+    n, K = 64, 12
+    lines = corpus.log_lines(n, 1024)
+    prog = cu.CudaProgram(rx)
+    count, spans, ids = prog.pike_lines_all(lines.cuda(), n, 1024, 1024, K)
+    po = o.compile(rx)
+    for i in range(n):
+        want = capi.pike_all(o, po, bytes(lines[i].numpy()), limit=K)
+        assert int(count[i]) == len(want), i
+        got = [(int(ids[i, k]), int(spans[i, k, 0]), int(spans[i, k, 1])) for k in range(len(want))]
+        assert got == want, i
+    assert int(count.max()) >= 5

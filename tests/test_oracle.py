@@ -73,3 +73,18 @@ def test_oracle_against_live_reference_fuzz(golden, oracle, ref):
             assert oracle.pike(po, s, chunks) == ref.pike(pr, s, chunks), (b["name"], s, chunks)
         po.close()
         pr.close()
+
+
+def test_post_match_continuation_against_live_reference(golden, oracle, ref):
+    """global scan through the classic API: after each match the ctx is given the
+    rest of the data (sre_vm_pike.c:624-635, empty-match skip :179-193)"""
+    n = 0
+    for b in runnable(golden)[::2]:
+        po = oracle.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        pr = ref.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        s = b["subject_b"] * 2
+        assert capi.pike_all(oracle, po, s) == capi.pike_all(ref, pr, s), (b["file"], b["name"])
+        n += 1
+        po.close()
+        pr.close()
+    assert n > 900
