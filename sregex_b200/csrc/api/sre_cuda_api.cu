@@ -163,7 +163,7 @@ int upload(sre_cuda_program_t *cp)
     /* NFA tables, every bitset row padded to WP = 32 * words-per-lane words */
     cp->has_nfa = n.nstates <= MAX_NFA_STATES;
     size_t o_ncls = 0, o_kind = 0, o_mv = 0, o_mt = 0, o_eof = 0, o_init = 0, o_shift = 0, o_follow = 0,
-           o_rowidx = 0;
+           o_rowidx = 0, o_any = 0, o_cmask = 0, o_mmask = 0;
     uint32_t WP = 32, nrows = 0;
     if (cp->has_nfa) {
         const uint32_t wpl = (n.nwords + 31) / 32;
@@ -180,14 +180,33 @@ int upload(sre_cuda_program_t *cp)
                               eofm = pad_rows(n.mt_eof, 1), init = pad_rows(n.init, 1),
                               shift = pad_rows(n.shift_mask, 1);
         std::vector<int32_t> rowidx((size_t) WP * 32, -1);
+        std::vector<uint32_t> cmask(WP, 0), mmask(WP, 0), anyrow((size_t) n.nkinds * WP, 0);
+        int32_t any_state = -1;
+        for (uint32_t s = 0; s < n.nstates; s++) {
+            if (n.state_pc[s] == 1 && n.state_allow[s] == 0x0f) {
+                any_state = (int32_t) s;     /* the ".*?" prefix: always alive, consumes every byte */
+            }
+        }
         for (uint32_t s = 0; s < n.nstates; s++) {
             const bool is_shift = (n.shift_mask[s >> 5] >> (s & 31)) & 1;
             const bool is_match = prog->insts[n.state_pc[s]].opcode == SRE_OPCODE_MATCH;
             cp->nfa_shift += is_shift;
-            if (!is_shift && !is_match) {
+            if (is_match) {
+                mmask[s >> 5] |= 1u << (s & 31);
+            }
+            if (!is_shift && !is_match && (int32_t) s != any_state) {
                 rowidx[s] = (int32_t) nrows++;
+                cmask[s >> 5] |= 1u << (s & 31);
             }
         }
+        if (any_state < 0) {
+            return fail("program without the .*? prefix state");
+        }
+        for (uint32_t k = 0; k < n.nkinds; k++) {
+            memcpy(&anyrow[(size_t) k * WP], n.follow_row(k, (uint32_t) any_state), W * 4);
+        }
+        /* the any state must not also take the shift path */
+        shift[any_state >> 5] &= ~(1u << (any_state & 31));
         std::vector<uint32_t> follow((size_t) n.nkinds * (nrows ? nrows : 1) * WP, 0);
         for (uint32_t k = 0; k < n.nkinds; k++) {
             for (uint32_t s = 0; s < n.nstates; s++) {
@@ -205,6 +224,9 @@ int upload(sre_cuda_program_t *cp)
         o_shift = b.add(shift.data(), shift.size() * 4);
         o_follow = b.add(follow.data(), follow.size() * 4);
         o_rowidx = b.add(rowidx.data(), rowidx.size() * 4);
+        o_any = b.add(anyrow.data(), anyrow.size() * 4);
+        o_cmask = b.add(cmask.data(), cmask.size() * 4);
+        o_mmask = b.add(mmask.data(), mmask.size() * 4);
     }
 
     /* Pike: the bytecode itself */
@@ -289,6 +311,10 @@ int upload(sre_cuda_program_t *cp)
         cp->nfa.follow = reinterpret_cast<const uint32_t *>(base + o_follow);
         cp->nfa.rowidx = reinterpret_cast<const int32_t *>(base + o_rowidx);
         cp->nfa.nrows = nrows ? nrows : 1;
+        cp->nfa.any_follow = reinterpret_cast<const uint32_t *>(base + o_any);
+        cp->nfa.complex_mask = reinterpret_cast<const uint32_t *>(base + o_cmask);
+        cp->nfa.match_mask = reinterpret_cast<const uint32_t *>(base + o_mmask);
+        cp->nfa.match_lookahead = n.has_match_lookahead ? 1 : 0;
     }
 
     static_assert(sizeof(sre_instruction_t) == sizeof(sre_dev_inst_t), "instruction layout");

@@ -42,6 +42,10 @@ struct sre_dev_nfa_t {
     const uint32_t  *follow;    /* [nkinds][nrows][nwords], complex rows only */
     const int32_t   *rowidx;    /* [nstates] -> row or -1                     */
     uint32_t         nrows;
+    const uint32_t  *any_follow;   /* [nkinds][nwords] follow row of the ".*?" any state */
+    const uint32_t  *complex_mask; /* [nwords] movers that need a follow-row OR          */
+    const uint32_t  *match_mask;   /* [nwords] MATCH states                              */
+    uint32_t         match_lookahead;  /* some MATCH state has a pending look-ahead     */
 };
 
 /* ---- Pike tier (runs the bytecode itself) -------------------------------- */

@@ -647,14 +647,24 @@ k_dfa_generic_hint(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, const int
 
 /*
  * One warp per line.  The thread set has WPL*1024 bits; lane l holds words
- * j*32 + l (j < WPL).  All bitset tables are padded to 32*WPL words per row.
+ * j*32 + l (j < WPL).  All bitset tables are padded to WP = 32*WPL words per row.
+ * Per byte: class look-up, S & mv[class] = movers, then
+ *   - the ".*?" `any` state always moves: its follow row (the fresh-start
+ *     closure) is OR-ed in from registers / shared memory, no look-up;
+ *   - states whose only successor is s+1 move by a one-bit shift across lanes;
+ *   - the remaining ("complex") movers OR their follow rows, found by ballot.
+ * Match detection: when no MATCH state carries a pending look-ahead assertion
+ * the kernel only accumulates the states seen and tests them against the MATCH
+ * mask every 16 bytes; otherwise it tests S & mt[class] at every step.
+ * The input is read with warp-uniform 16-byte loads (one transaction per warp).
  */
-template <int WPL>
+template <int WPL, bool SMEM_TAB>
 __global__ void __launch_bounds__(256)
 k_nfa_lines(sre_dev_nfa_t nfa, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
             size_t nlines, size_t pitch, size_t linelen, uint32_t *state_io, int from_init, int eof,
             int32_t *__restrict__ rc)
 {
+    extern __shared__ __align__(1024) uint32_t nfa_smem[];
     __shared__ uint8_t s_cls[256];
     __shared__ uint8_t s_kind[256];
     constexpr uint32_t WP = 32 * WPL;
@@ -663,89 +673,134 @@ k_nfa_lines(sre_dev_nfa_t nfa, const uint8_t *__restrict__ buf, const int64_t *_
         s_cls[i] = nfa.clsmap[i];
         s_kind[i] = i < nfa.nclasses ? nfa.cls_kind[i] : 0;
     }
+    const uint32_t *mvtab = nfa.mv, *mttab = nfa.mt;
+    if (SMEM_TAB) {
+        const uint32_t n = nfa.nclasses * WP;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            nfa_smem[i] = nfa.mv[i];
+            if (nfa.match_lookahead) {
+                nfa_smem[n + i] = nfa.mt[i];
+            }
+        }
+        mvtab = nfa_smem;
+        mttab = nfa_smem + n;
+    }
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31;
     const size_t warps_total = ((size_t) gridDim.x * blockDim.x) >> 5;
     const size_t gw = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const bool la = nfa.match_lookahead != 0;
 
-    uint32_t shiftm[WPL], mteof[WPL];
+    uint32_t shiftm[WPL], mteof[WPL], complexm[WPL], matchm[WPL];
 #pragma unroll
     for (int j = 0; j < WPL; j++) {
         shiftm[j] = nfa.shift_mask[j * 32 + lane];
         mteof[j] = nfa.mt_eof[j * 32 + lane];
+        complexm[j] = nfa.complex_mask[j * 32 + lane];
+        matchm[j] = nfa.match_mask[j * 32 + lane];
     }
 
     for (size_t line = gw; line < nlines; line += warps_total) {
         size_t p = offsets ? (size_t) offsets[line] : line * pitch;
         const size_t end = offsets ? (size_t) offsets[line + 1] : p + linelen;
 
-        uint32_t S[WPL];
+        uint32_t S[WPL], seen[WPL];
 #pragma unroll
         for (int j = 0; j < WPL; j++) {
             S[j] = (from_init || state_io == nullptr) ? nfa.init[j * 32 + lane]
                                                       : state_io[line * WP + j * 32 + lane];
+            seen[j] = 0;
         }
         uint32_t hit = 0;
 
-        while (p < end && !__any_sync(FULL, hit)) {
-            const uint32_t n = (uint32_t) (end - p < 32 ? end - p : 32);
-            const uint32_t mine = lane < n ? buf[p + lane] : 0;
-
-            for (uint32_t i = 0; i < n; i++) {
-                const uint32_t b = __shfl_sync(FULL, mine, i);
-                const uint32_t c = s_cls[b], kind = s_kind[c];
-                const uint32_t *mvrow = nfa.mv + (size_t) c * WP, *mtrow = nfa.mt + (size_t) c * WP;
-                uint32_t m[WPL], nxt[WPL];
+        auto step = [&](uint32_t b) {
+            const uint32_t c = s_cls[b];
+            const uint32_t *mvrow = mvtab + (size_t) c * WP;
+            uint32_t m[WPL], nxt[WPL];
+            const uint32_t *anyrow = nfa.any_follow + (nfa.nkinds == 1 ? 0 : s_kind[c]) * WP;
 #pragma unroll
-                for (int j = 0; j < WPL; j++) {
-                    hit |= S[j] & __ldg(mtrow + j * 32 + lane);
-                    m[j] = S[j] & __ldg(mvrow + j * 32 + lane);
+            for (int j = 0; j < WPL; j++) {
+                if (la) {
+                    hit |= S[j] & (SMEM_TAB ? mttab[(size_t) c * WP + j * 32 + lane]
+                                            : __ldg(mttab + (size_t) c * WP + j * 32 + lane));
+                } else {
+                    seen[j] |= S[j];
                 }
-                /* states whose only successor is s+1: shift left by one bit */
-                uint32_t carry = 0;
+                m[j] = S[j] & (SMEM_TAB ? mvrow[j * 32 + lane] : __ldg(mvrow + j * 32 + lane));
+                /* the `any` state is in every set and consumes every byte */
+                nxt[j] = __ldg(anyrow + j * 32 + lane);
+            }
+            uint32_t carry = 0;
 #pragma unroll
-                for (int j = 0; j < WPL; j++) {
-                    const uint32_t sh = m[j] & shiftm[j];
-                    uint32_t up = __shfl_up_sync(FULL, sh >> 31, 1);
-                    if (lane == 0) {
-                        up = carry;
-                    }
-                    carry = __shfl_sync(FULL, sh >> 31, 31);
-                    nxt[j] = (sh << 1) | up;
+            for (int j = 0; j < WPL; j++) {
+                const uint32_t sh = m[j] & shiftm[j];
+                uint32_t up = __shfl_up_sync(FULL, sh >> 31, 1);
+                if (lane == 0) {
+                    up = carry;
                 }
-                /* the rest: OR their follow rows */
+                carry = __shfl_sync(FULL, sh >> 31, 31);
+                nxt[j] |= (sh << 1) | up;
+            }
 #pragma unroll
-                for (int j = 0; j < WPL; j++) {
-                    const uint32_t cm = m[j] & ~shiftm[j];
-                    uint32_t bal = __ballot_sync(FULL, cm != 0);
-                    while (bal) {
-                        const uint32_t src = __ffs(bal) - 1;
-                        bal &= bal - 1;
-                        uint32_t w = __shfl_sync(FULL, cm, src);
-                        while (w) {
-                            const uint32_t bit = __ffs(w) - 1;
-                            w &= w - 1;
-                            const uint32_t state = ((uint32_t) j * 32 + src) * 32 + bit;
-                            const int32_t r = __ldg(nfa.rowidx + state);
-                            const uint32_t *row = nfa.follow + ((size_t) kind * nfa.nrows + r) * WP;
+            for (int j = 0; j < WPL; j++) {
+                const uint32_t cm = m[j] & complexm[j];
+                uint32_t bal = __ballot_sync(FULL, cm != 0);
+                while (bal) {
+                    const uint32_t src = __ffs(bal) - 1;
+                    bal &= bal - 1;
+                    uint32_t w = __shfl_sync(FULL, cm, src);
+                    while (w) {
+                        const uint32_t bit = __ffs(w) - 1;
+                        w &= w - 1;
+                        const uint32_t state = ((uint32_t) j * 32 + src) * 32 + bit;
+                        const int32_t r = __ldg(nfa.rowidx + state);
+                        const uint32_t kind = nfa.nkinds == 1 ? 0 : s_kind[c];
+                        const uint32_t *row = nfa.follow + ((size_t) kind * nfa.nrows + r) * WP;
 #pragma unroll
-                            for (int jj = 0; jj < WPL; jj++) {
-                                nxt[jj] |= __ldg(row + jj * 32 + lane);
-                            }
+                        for (int jj = 0; jj < WPL; jj++) {
+                            nxt[jj] |= __ldg(row + jj * 32 + lane);
                         }
                     }
                 }
+            }
 #pragma unroll
-                for (int j = 0; j < WPL; j++) {
-                    S[j] = nxt[j];
+            for (int j = 0; j < WPL; j++) {
+                S[j] = nxt[j];
+            }
+        };
+        auto matched_so_far = [&]() {
+            uint32_t h = hit;
+#pragma unroll
+            for (int j = 0; j < WPL; j++) {
+                h |= seen[j] & matchm[j];
+            }
+            return __any_sync(FULL, h) != 0;
+        };
+
+        bool done = false;
+        while (p < end && ((reinterpret_cast<uintptr_t>(buf) + p) & 15)) {
+            step(buf[p++]);                 /* warp-uniform address */
+        }
+        while (!done && p + 16 <= end) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(buf + p));
+            const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    step((w[i] >> (8 * k)) & 0xff);
                 }
             }
-            p += n;
+            p += 16;
+            done = matched_so_far();
+        }
+        while (!done && p < end) {
+            step(buf[p++]);
         }
 
         int32_t r;
-        if (__any_sync(FULL, hit)) {
+        if (matched_so_far()) {
             r = SRE_K_OK;
         } else if (eof) {
             uint32_t h = 0;
@@ -1254,17 +1309,28 @@ cudaError_t sre_launch_nfa_lines(const sre_dev_nfa_t &nfa, const uint8_t *buf,
     if (launches) {
         ++*launches;
     }
+    /* mv (and mt when needed) tables in shared memory when they fit */
+    const size_t tab = (size_t) nfa.nclasses * nfa.nwords * 4 * (nfa.match_lookahead ? 2 : 1);
+    const bool fits = tab <= 24 * 1024;
+#define SRE_NFA(W)                                                                                   \
+    do {                                                                                             \
+        if (fits) {                                                                                  \
+            k_nfa_lines<W, true><<<(unsigned) grid, 256, tab, stream>>>(nfa, buf, offsets, nlines, pitch, \
+                                                                        linelen, state_io, from_init, eof, rc); \
+        } else {                                                                                     \
+            k_nfa_lines<W, false><<<(unsigned) grid, 256, 0, stream>>>(nfa, buf, offsets, nlines, pitch,  \
+                                                                       linelen, state_io, from_init, eof, rc); \
+        }                                                                                            \
+    } while (0)
     if (wpl <= 1) {
-        k_nfa_lines<1><<<(unsigned) grid, 256, 0, stream>>>(nfa, buf, offsets, nlines, pitch, linelen,
-                                                           state_io, from_init, eof, rc);
+        SRE_NFA(1);
     } else if (wpl <= 2) {
-        k_nfa_lines<2><<<(unsigned) grid, 256, 0, stream>>>(nfa, buf, offsets, nlines, pitch, linelen,
-                                                           state_io, from_init, eof, rc);
+        SRE_NFA(2);
     } else if (wpl <= 4) {
-        k_nfa_lines<4><<<(unsigned) grid, 256, 0, stream>>>(nfa, buf, offsets, nlines, pitch, linelen,
-                                                           state_io, from_init, eof, rc);
+        SRE_NFA(4);
     } else {
         return cudaErrorInvalidValue;
     }
+#undef SRE_NFA
     return cudaGetLastError();
 }
