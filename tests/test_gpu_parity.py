@@ -143,7 +143,7 @@ def test_thompson_tiers_vs_oracle(cu, nlines, linelen, pitch):
     dev = lines.cuda()
     for engine in (cu.ENGINE_DFA_TILED, cu.ENGINE_DFA_GENERIC, cu.ENGINE_NFA, cu.ENGINE_DFA_SKIP, cu.ENGINE_AUTO):
         variants = {cu.ENGINE_DFA_TILED: (0, 1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 20, 21, 22, 24, 25),
-                    cu.ENGINE_DFA_SKIP: (0, 30, 31, 32, 33, 41, 42, 43, 44, 50, 51, 52, 53)}.get(engine, (0,))
+                    cu.ENGINE_DFA_SKIP: (0, 30, 31, 32, 33, 40, 41, 42, 43, 44, 50, 51, 52, 53, 61, 62)}.get(engine, (0,))
         for variant in variants:
             cu.set_variant(variant)
             got = prog.thompson_lines(dev, nlines, pitch, linelen, engine=engine).cpu().numpy()
