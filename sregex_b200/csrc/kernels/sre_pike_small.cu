@@ -76,21 +76,27 @@ __device__ __forceinline__ sre_dev_inst_t load_inst(const sre_dev_pike_t &pk, in
     return in;
 }
 
-/* K: threads per list, M: capture slots, H: hold-stack records, DS: DFS stack */
-template <int K, int M, int H, int DS>
+/*
+ * K: threads per list, M: capture slots, H: hold-stack records, DS: DFS stack.
+ * C16: capture values are 16-bit line offsets, two per word (lines shorter than
+ * 32 KB): half the shared memory per context, twice the resident warps.
+ */
+template <int K, int M, int H, int DS, bool C16>
 struct small_ctx_t {
+    /* words per capture vector */
+    static constexpr int MW = C16 ? (M + 1) / 2 : M;
     /* shared-memory sections, in words per lane */
     static constexpr int CAP = 0;
-    static constexpr int MAT = CAP + M;
-    static constexpr int L0PC = MAT + M;
+    static constexpr int MAT = CAP + MW;
+    static constexpr int L0PC = MAT + MW;
     static constexpr int L0CAP = L0PC + K;
-    static constexpr int L1PC = L0CAP + K * M;
+    static constexpr int L1PC = L0CAP + K * MW;
     static constexpr int L1CAP = L1PC + K;
-    static constexpr int HSPC = L1CAP + K * M;
+    static constexpr int HSPC = L1CAP + K * MW;
     static constexpr int HSCAP = HSPC + H;
-    static constexpr int DSA = HSCAP + H * M;
+    static constexpr int DSA = HSCAP + H * MW;
     static constexpr int DSB = DSA + DS;
-    static constexpr int WORDS = DSB + DS;
+    static constexpr int WORDS = DSB + (C16 ? 0 : DS);
 
     int32_t    *sm;         /* base + threadIdx.x; stride BLOCK */
     uint64_t    m_cur, m_prev;
@@ -99,6 +105,27 @@ struct small_ctx_t {
     bool        overflow;
 
     __device__ __forceinline__ int32_t &w(int e) { return sm[e * BLOCK]; }
+
+    /* capture slot `slot` of the vector starting at word section `sec` */
+    __device__ __forceinline__ int32_t cap_get(int sec, uint32_t slot)
+    {
+        if (!C16) {
+            return w(sec + slot);
+        }
+        const int32_t word = w(sec + (slot >> 1));
+        return (slot & 1) ? (word >> 16) : (int32_t) (int16_t) (word & 0xffff);
+    }
+    __device__ __forceinline__ void cap_set(int sec, uint32_t slot, int32_t v)
+    {
+        if (!C16) {
+            w(sec + slot) = v;
+            return;
+        }
+        int32_t &word = w(sec + (slot >> 1));
+        word = (slot & 1) ? ((word & 0xffff) | (v << 16)) : ((word & ~0xffff) | (v & 0xffff));
+    }
+    /* number of words holding nslots captures */
+    __device__ __forceinline__ uint32_t cap_words() const { return C16 ? (nslots + 1) >> 1 : nslots; }
 
     /* tag test / set against ctx->tag (hold == false) or ctx->tag - 1 */
     __device__ __forceinline__ bool tagged(int32_t pc, bool hold) const
@@ -117,6 +144,34 @@ struct small_ctx_t {
         }
     }
 
+    /* DFS stack entry: visit pc (slot < 0) or restore capture slot to a value */
+    __device__ __forceinline__ void ds_push(int &sp, int32_t a, int32_t slot)
+    {
+        if (C16) {
+            w(DSA + sp) = slot < 0 ? a : (int32_t) (0x80000000u | ((uint32_t) slot << 16) | ((uint32_t) a & 0xffff));
+        } else {
+            w(DSA + sp) = a;
+            w(DSB + sp) = slot;
+        }
+        sp++;
+    }
+    __device__ __forceinline__ void ds_pop(int sp, int32_t &a, int32_t &slot)
+    {
+        if (C16) {
+            const int32_t e = w(DSA + sp);
+            if (e < 0) {
+                slot = (e >> 16) & 0x7fff;
+                a = (int32_t) (int16_t) (e & 0xffff);
+            } else {
+                slot = -1;
+                a = e;
+            }
+        } else {
+            a = w(DSA + sp);
+            slot = w(DSB + sp);
+        }
+    }
+
     /*
      * add_thread (sre_vm_pike.c:756-942).  Appends thread records to the array
      * at (pc_sec, cap_sec) with capacity `cap_n`, counting in *n.  The working
@@ -127,14 +182,14 @@ struct small_ctx_t {
                               int32_t pc0, int32_t pos, const uint8_t *buffer, bool want_done, bool hold)
     {
         int sp = 0;
-        w(DSA) = pc0;
-        w(DSB) = -1;
-        sp = 1;
+        ds_push(sp, pc0, -1);
+        const uint32_t ncw = cap_words();
         while (sp > 0) {
             sp--;
-            const int32_t a = w(DSA + sp), b = w(DSB + sp);
+            int32_t a, b;
+            ds_pop(sp, a, b);
             if (b >= 0) {               /* restore slot b to value a */
-                w(CAP + b) = a;
+                cap_set(CAP, b, a);
                 continue;
             }
             int32_t pc = a;
@@ -160,19 +215,15 @@ struct small_ctx_t {
                     if (sp >= DS) {
                         return -1;
                     }
-                    w(DSA + sp) = in.y;
-                    w(DSB + sp) = -1;
-                    sp++;
+                    ds_push(sp, in.y, -1);
                     pc = in.x;
                     continue;
                 case OP_SAVE:
                     if (sp >= DS) {
                         return -1;
                     }
-                    w(DSA + sp) = w(CAP + in.v);
-                    w(DSB + sp) = in.v;
-                    sp++;
-                    w(CAP + in.v) = pos;
+                    ds_push(sp, cap_get(CAP, in.v), in.v);
+                    cap_set(CAP, in.v, pos);
                     pc++;
                     continue;
                 case OP_ASSERT:
@@ -201,7 +252,7 @@ struct small_ctx_t {
                     break;
                 case OP_MATCH:
                     if (want_done) {
-                        for (uint32_t i = 0; i < nslots; i++) {
+                        for (uint32_t i = 0; i < ncw; i++) {
                             w(MAT + i) = w(CAP + i);
                         }
                         matched_id = in.v;
@@ -220,8 +271,8 @@ struct small_ctx_t {
                     }
                     const int t = *n;
                     w(pc_sec + t) = pc | (int32_t) (seen_word << 16);
-                    for (uint32_t i = 0; i < nslots; i++) {
-                        w(cap_sec + t * M + i) = w(CAP + i);
+                    for (uint32_t i = 0; i < ncw; i++) {
+                        w(cap_sec + t * MW + i) = w(CAP + i);
                     }
                     *n = t + 1;
                 }
@@ -232,7 +283,7 @@ struct small_ctx_t {
     }
 };
 
-template <int K, int M, int H, int DS>
+template <int K, int M, int H, int DS, bool C16>
 __global__ void __launch_bounds__(BLOCK)
 k_pike_small(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
              size_t nlines, size_t pitch, size_t linelen, const int32_t *__restrict__ select,
@@ -240,7 +291,8 @@ k_pike_small(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
              uint32_t ovec_slots)
 {
     extern __shared__ int32_t smem_words[];
-    typedef small_ctx_t<K, M, H, DS> ctx_t;
+    typedef small_ctx_t<K, M, H, DS, C16> ctx_t;
+    constexpr int MW = ctx_t::MW;
     ctx_t c;
     c.sm = smem_words + threadIdx.x;
     c.nslots = pk.nslots;
@@ -267,7 +319,8 @@ k_pike_small(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
         bool matched = false;
         int cur = 0, ncl = 0, nnl = 0, hs = 0;
 
-        for (uint32_t i = 0; i < c.nslots; i++) {
+        const uint32_t ncw = c.cap_words();
+        for (uint32_t i = 0; i < ncw; i++) {
             c.w(ctx_t::CAP + i) = -1;
         }
         /* first_buf: the initial closure at the start offset, :202-216 */
@@ -294,10 +347,10 @@ k_pike_small(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
                 if (hs > 0) {
                     hs--;
                     tp = ctx_t::HSPC + hs;
-                    tc = ctx_t::HSCAP + hs * M;
+                    tc = ctx_t::HSCAP + hs * MW;
                 } else if (i < ncl) {
                     tp = cl_pc + i;
-                    tc = cl_cap + i * M;
+                    tc = cl_cap + i * MW;
                     i++;
                 } else {
                     break;
@@ -318,7 +371,7 @@ k_pike_small(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
                     default: break;
                     }
                     if (hold) {
-                        for (uint32_t k = 0; k < c.nslots; k++) {
+                        for (uint32_t k = 0; k < ncw; k++) {
                             c.w(ctx_t::CAP + k) = c.w(tc + k);
                         }
                         /* closure with tag - 1, prepended to clist: append it
@@ -334,22 +387,22 @@ k_pike_small(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
                             int32_t tmp = c.w(ctx_t::HSPC + lo);
                             c.w(ctx_t::HSPC + lo) = c.w(ctx_t::HSPC + hi);
                             c.w(ctx_t::HSPC + hi) = tmp;
-                            for (uint32_t k = 0; k < c.nslots; k++) {
-                                tmp = c.w(ctx_t::HSCAP + lo * M + k);
-                                c.w(ctx_t::HSCAP + lo * M + k) = c.w(ctx_t::HSCAP + hi * M + k);
-                                c.w(ctx_t::HSCAP + hi * M + k) = tmp;
+                            for (uint32_t k = 0; k < ncw; k++) {
+                                tmp = c.w(ctx_t::HSCAP + lo * MW + k);
+                                c.w(ctx_t::HSCAP + lo * MW + k) = c.w(ctx_t::HSCAP + hi * MW + k);
+                                c.w(ctx_t::HSCAP + hi * MW + k) = tmp;
                             }
                         }
                         hs = top;
                     }
                 } else if (in.opcode == OP_MATCH) {         /* :530-553 */
-                    for (uint32_t k = 0; k < c.nslots; k++) {
+                    for (uint32_t k = 0; k < ncw; k++) {
                         c.w(ctx_t::MAT + k) = c.w(tc + k);
                     }
                     c.matched_id = in.v;
                     got_match = true;
                 } else if (!at_end && consumes(pk, in, byte)) {
-                    for (uint32_t k = 0; k < c.nslots; k++) {
+                    for (uint32_t k = 0; k < ncw; k++) {
                         c.w(ctx_t::CAP + k) = c.w(tc + k);
                     }
                     const int r = c.add_thread(pk, nl_pc, nl_cap, K, &nnl, pc + 1, sp + 1, input, true, false);
@@ -383,7 +436,7 @@ k_pike_small(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
         if (matched) {
             rc[line] = c.matched_id;
             for (uint32_t i = 0; i < ovec_slots; i++) {
-                ov[i] = i < c.nslots ? (int64_t) c.w(ctx_t::MAT + i) : -1;
+                ov[i] = i < c.nslots ? (int64_t) c.cap_get(ctx_t::MAT, i) : -1;
             }
         } else {
             rc[line] = SRE_K_DECLINED;
@@ -416,19 +469,26 @@ cudaError_t sre_launch_pike_small(const sre_dev_pike_t &pk, const uint8_t *buf, 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     size_t grid = (nlines + BLOCK - 1) / BLOCK;
 
-#define SRE_SMALL(KK, MM, HH, DD)                                                                   \
+#define SRE_SMALL_C(KK, MM, HH, DD, CC)                                                             \
     do {                                                                                            \
-        auto kern = k_pike_small<KK, MM, HH, DD>;                                                   \
-        const size_t smem = (size_t) small_ctx_t<KK, MM, HH, DD>::WORDS * BLOCK * 4;                \
+        auto kern = k_pike_small<KK, MM, HH, DD, CC>;                                               \
+        const size_t smem = (size_t) small_ctx_t<KK, MM, HH, DD, CC>::WORDS * BLOCK * 4;            \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
         if (e != cudaSuccess) return e;                                                             \
-        const size_t per_sm = (227 * 1024) / (smem + 1024);                                         \
+        size_t per_sm = (227 * 1024) / (smem + 1024);                                               \
+        if (per_sm > 32) per_sm = 32;                                                               \
         const size_t cap = (size_t) sms * (per_sm ? per_sm : 1);                                    \
         if (grid > cap) grid = cap;                                                                 \
         kern<<<(unsigned) grid, BLOCK, smem, stream>>>(pk, buf, offsets, nlines, pitch, linelen, select, \
                                                         start, rc, ovec, ovec_slots);               \
     } while (0)
+#define SRE_SMALL(KK, MM, HH, DD)                                                                   \
+    do {                                                                                            \
+        if (c16) SRE_SMALL_C(KK, MM, HH, DD, true); else SRE_SMALL_C(KK, MM, HH, DD, false);        \
+    } while (0)
 
+    /* 16-bit capture offsets when every line is shorter than 32 KB */
+    const bool c16 = offsets == nullptr && linelen < 32767;
     /* K = 8 threads per list covers 96 % of the reference's t/ corpus (longer
      * lists fall back to k_pike_lines); M = capture slots */
     if (pk.nslots <= 4) {
@@ -442,6 +502,7 @@ cudaError_t sre_launch_pike_small(const sre_dev_pike_t &pk, const uint8_t *buf, 
     } else {
         SRE_SMALL(8, 16, 4, 12);
     }
+#undef SRE_SMALL_C
 #undef SRE_SMALL
     return cudaGetLastError();
 }
