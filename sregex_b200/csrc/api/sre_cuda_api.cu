@@ -422,7 +422,8 @@ int ensure_pike_scratch(sre_cuda_program_t *cp, size_t nlines)
     cudaFree(cp->pike_scratch);
     cp->pike_scratch = nullptr;
     cp->pike_nctx = 0;
-    CUDA_TRY(cudaMalloc(&cp->pike_scratch, want * cp->pike.ctx_stride));
+    /* contexts are interleaved in groups of 32 (sre_pike.cu: batch_base) */
+    CUDA_TRY(cudaMalloc(&cp->pike_scratch, ((want + 31) / 32 * 32) * cp->pike.ctx_stride));
     cp->pike_nctx = want;
     return SRE_OK;
 }

@@ -13,8 +13,10 @@
  * look-ahead closures prepended with the current list's tag :506-525), so the
  * kernel keeps that sequential algorithm per context and is parallel across
  * contexts (= lines).  Differences in mechanism only:
- *   - the program is the read-only flat bytecode; dedup tags live in the
- *     context (tag counters simply keep growing across lines, so no clearing);
+ *   - the program is the read-only flat bytecode; the dedup marks are two bit
+ *     sets per context selected by the parity of the tag counter (only the
+ *     current and the previous epoch are ever consulted), in shared memory in
+ *     the batch kernels;
  *   - add_thread's recursion is an explicit DFS stack with an undo log for the
  *     SAVE slots, which gives each branch of a SPLIT the captures the reference
  *     gives it through copy-on-write;
@@ -26,6 +28,7 @@
  * serves the batch entry points (context re-initialised per line) and the
  * streaming sre_vm_pike_exec (context persists between calls).
  */
+#include <cstdlib>
 #include "sre_kernels.cuh"
 
 namespace {
@@ -53,56 +56,171 @@ struct pike_hdr_t {
               error, pad;
 };
 
-struct stack_ent_t {
-    int32_t  kind;      /* -1: visit pc; >= 0: restore slot `kind`           */
-    int32_t  pc;
-    int64_t  val;
-};
-
-__host__ __device__ inline size_t a16(size_t v) { return (v + 15) & ~(size_t) 15; }
-
-/* carve the context block */
+/*
+ * Context memory.  Every array element is one or two 32-bit words; word e of a
+ * context lives at base[e * stride].  Batch kernels interleave the contexts of
+ * a warp (stride 32, lane l starts at word l), so that lanes touching the same
+ * element -- the common case, they run the same program on similar lines --
+ * share 128-byte lines in L1/L2; the streaming ctx of the classic API is a
+ * single context with stride 1.  The scalar header lives in registers / local
+ * memory (`hdr`) and is only stored in the block between streaming calls.
+ */
 struct pike_ctx_t {
-    pike_hdr_t   *h;
-    uint32_t     *tags;
-    int32_t      *initial;
-    int64_t      *matched;
-    int64_t      *cap;          /* working capture of add_thread             */
-    int32_t      *t_pc, *t_next;
-    uint8_t      *t_sw;
-    int64_t      *t_cap;
-    stack_ent_t  *stk;
+    pike_hdr_t    hdr;
+    pike_hdr_t   *h;            /* = &hdr */
+    uint32_t     *base;
+    uint32_t      stride;
+    uint32_t      o_initial, o_matched, o_cap, o_thr, o_stk, o_hdr;
+    uint32_t      max_slots, rec;       /* rec = words of one thread record */
+    /* dedup marks: two bit sets (epoch parity) of tagw words each; word i of
+     * set p is tagp[(p * tagw + i) * tstride] -- shared memory in the batch
+     * kernels when it fits, else part of the context block */
+    uint32_t     *tagp;
+    uint32_t      tagw, tstride;
+
+    __device__ __forceinline__ uint32_t &W(uint32_t e) const { return base[(size_t) e * stride]; }
+    __device__ __forceinline__ int64_t get64(uint32_t e) const
+    {
+        return (int64_t) (((uint64_t) W(e + 1) << 32) | W(e));
+    }
+    __device__ __forceinline__ void set64(uint32_t e, int64_t v) const
+    {
+        W(e) = (uint32_t) v;
+        W(e + 1) = (uint32_t) ((uint64_t) v >> 32);
+    }
+    __device__ __forceinline__ uint32_t &tagword(uint32_t tag, uint32_t i) const
+    {
+        return tagp[(size_t) ((tag & 1) * tagw + i) * tstride];
+    }
+    __device__ __forceinline__ bool tag_test(uint32_t pc, uint32_t tag) const
+    {
+        return (tagword(tag, pc >> 5) >> (pc & 31)) & 1;
+    }
+    __device__ __forceinline__ void tag_set(uint32_t pc, uint32_t tag) const
+    {
+        tagword(tag, pc >> 5) |= 1u << (pc & 31);
+    }
+    /* open epoch `tag`: forget the marks of epoch tag - 2 */
+    __device__ __forceinline__ void tag_open(uint32_t tag) const
+    {
+        for (uint32_t i = 0; i < tagw; i++) {
+            tagword(tag, i) = 0;
+        }
+    }
+    __device__ __forceinline__ int32_t &initial(uint32_t i) const
+    {
+        return reinterpret_cast<int32_t &>(W(o_initial + i));
+    }
+    /* thread record t: {pc, next, seen_word, cap[max_slots]} */
+    __device__ __forceinline__ int32_t &t_pc(uint32_t t) const
+    {
+        return reinterpret_cast<int32_t &>(W(o_thr + t * rec));
+    }
+    __device__ __forceinline__ int32_t &t_next(uint32_t t) const
+    {
+        return reinterpret_cast<int32_t &>(W(o_thr + t * rec + 1));
+    }
+    __device__ __forceinline__ uint32_t &t_sw(uint32_t t) const { return W(o_thr + t * rec + 2); }
+    __device__ __forceinline__ int64_t cap(uint32_t i) const { return get64(o_cap + 2 * i); }
+    __device__ __forceinline__ void set_cap(uint32_t i, int64_t v) const { set64(o_cap + 2 * i, v); }
+    __device__ __forceinline__ int64_t matched(uint32_t i) const { return get64(o_matched + 2 * i); }
+    __device__ __forceinline__ void set_matched(uint32_t i, int64_t v) const { set64(o_matched + 2 * i, v); }
+    __device__ __forceinline__ int64_t t_cap(uint32_t t, uint32_t i) const
+    {
+        return get64(o_thr + t * rec + 3 + 2 * i);
+    }
+    __device__ __forceinline__ void set_t_cap(uint32_t t, uint32_t i, int64_t v) const
+    {
+        set64(o_thr + t * rec + 3 + 2 * i, v);
+    }
+    /* DFS stack entry: {kind, pc, val} */
+    __device__ __forceinline__ int32_t stk_kind(uint32_t i) const { return (int32_t) W(o_stk + 4 * i); }
+    __device__ __forceinline__ int32_t stk_pc(uint32_t i) const { return (int32_t) W(o_stk + 4 * i + 1); }
+    __device__ __forceinline__ int64_t stk_val(uint32_t i) const { return get64(o_stk + 4 * i + 2); }
+    __device__ __forceinline__ void stk_set(uint32_t i, int32_t kind, int32_t pc, int64_t val) const
+    {
+        W(o_stk + 4 * i) = (uint32_t) kind;
+        W(o_stk + 4 * i + 1) = (uint32_t) pc;
+        set64(o_stk + 4 * i + 2, val);
+    }
 };
 
-__host__ __device__ inline size_t pike_ctx_bytes(uint32_t len, uint32_t nslots, uint32_t max_slots,
-                                                 uint32_t nthreads, uint32_t stack_cap)
+/* words of one context block; the same walk gives the section offsets */
+struct pike_layout_t {
+    uint32_t o_tags, o_initial, o_matched, o_cap, o_thr, o_stk, o_hdr, tagw, rec;
+    size_t   words;
+};
+
+__host__ __device__ inline pike_layout_t pike_layout(uint32_t len, uint32_t nslots, uint32_t max_slots,
+                                                     uint32_t nthreads, uint32_t stack_cap)
 {
-    size_t n = a16(sizeof(pike_hdr_t));
-    n += a16((size_t) (len + 1) * 4);       /* tags      */
-    n += a16((size_t) (len + 1) * 4);       /* initial   */
-    n += a16((size_t) nslots * 8) * 2;      /* matched, cap */
-    n += a16((size_t) nthreads * 4) * 2;    /* t_pc, t_next */
-    n += a16(nthreads);                     /* t_sw      */
-    n += a16((size_t) nthreads * max_slots * 8);
-    n += a16((size_t) stack_cap * sizeof(stack_ent_t));
-    return n;
+    pike_layout_t L;
+    size_t o = 0;
+    L.tagw = (len + 1 + 31) / 32;
+    L.rec = 3 + 2 * max_slots;
+    L.o_tags = (uint32_t) o;     o += 2 * (size_t) L.tagw;
+    L.o_initial = (uint32_t) o;  o += len + 1;
+    L.o_matched = (uint32_t) o;  o += 2 * (size_t) nslots;
+    L.o_cap = (uint32_t) o;      o += 2 * (size_t) nslots;
+    L.o_thr = (uint32_t) o;      o += (size_t) nthreads * L.rec;
+    L.o_stk = (uint32_t) o;      o += 4 * (size_t) stack_cap;
+    L.o_hdr = (uint32_t) o;      o += (sizeof(pike_hdr_t) + 3) / 4;    /* streaming ctx only */
+    L.words = o;
+    return L;
 }
 
-__device__ inline pike_ctx_t pike_carve(const sre_dev_pike_t &pk, uint8_t *base)
+/* attach a context view to its memory: base = first word of this lane.
+ * smem_tags: marks of this context in shared memory (word stride smem_stride) */
+__device__ inline void pike_attach(pike_ctx_t &c, const sre_dev_pike_t &pk, uint32_t *base, uint32_t stride,
+                                   uint32_t *smem_tags = nullptr, uint32_t smem_stride = 0)
 {
-    pike_ctx_t c;
-    uint8_t *p = base;
-    c.h = reinterpret_cast<pike_hdr_t *>(p);        p += a16(sizeof(pike_hdr_t));
-    c.tags = reinterpret_cast<uint32_t *>(p);       p += a16((size_t) (pk.len + 1) * 4);
-    c.initial = reinterpret_cast<int32_t *>(p);     p += a16((size_t) (pk.len + 1) * 4);
-    c.matched = reinterpret_cast<int64_t *>(p);     p += a16((size_t) pk.nslots * 8);
-    c.cap = reinterpret_cast<int64_t *>(p);         p += a16((size_t) pk.nslots * 8);
-    c.t_pc = reinterpret_cast<int32_t *>(p);        p += a16((size_t) pk.max_threads * 4);
-    c.t_next = reinterpret_cast<int32_t *>(p);      p += a16((size_t) pk.max_threads * 4);
-    c.t_sw = p;                                     p += a16(pk.max_threads);
-    c.t_cap = reinterpret_cast<int64_t *>(p);       p += a16((size_t) pk.max_threads * pk.max_slots * 8);
-    c.stk = reinterpret_cast<stack_ent_t *>(p);
-    return c;
+    const pike_layout_t L = pike_layout(pk.len, pk.nslots, pk.max_slots, pk.max_threads, pk.stack_cap);
+    c.h = &c.hdr;
+    c.base = base;
+    c.stride = stride;
+    c.max_slots = pk.max_slots;
+    c.rec = L.rec;
+    c.o_initial = L.o_initial;
+    c.o_matched = L.o_matched;
+    c.o_cap = L.o_cap;
+    c.o_thr = L.o_thr;
+    c.o_stk = L.o_stk;
+    c.o_hdr = L.o_hdr;
+    c.tagw = L.tagw;
+    if (smem_tags) {
+        c.tagp = smem_tags;
+        c.tstride = smem_stride;
+    } else {
+        c.tagp = base + (size_t) L.o_tags * stride;
+        c.tstride = stride;
+    }
+}
+
+/* batch layout: contexts 32g .. 32g+31 share one interleaved block */
+__device__ inline uint32_t *batch_base(const sre_dev_pike_t &pk, uint8_t *scratch, size_t tid, uint32_t stride)
+{
+    if (stride == 1) {
+        return reinterpret_cast<uint32_t *>(scratch + tid * pk.ctx_stride);
+    }
+    return reinterpret_cast<uint32_t *>(scratch + (tid >> 5) * (32 * pk.ctx_stride)) + (tid & 31);
+}
+
+__device__ inline void pike_hdr_store(const sre_dev_pike_t &pk, pike_ctx_t &c)
+{
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(&c.hdr);
+    const uint32_t o = c.o_hdr;
+    for (uint32_t i = 0; i < (sizeof(pike_hdr_t) + 3) / 4; i++) {
+        c.W(o + i) = src[i];
+    }
+}
+
+__device__ inline void pike_hdr_load(const sre_dev_pike_t &pk, pike_ctx_t &c)
+{
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&c.hdr);
+    const uint32_t o = c.o_hdr;
+    for (uint32_t i = 0; i < (sizeof(pike_hdr_t) + 3) / 4; i++) {
+        dst[i] = c.W(o + i);
+    }
 }
 
 __device__ inline bool isword(uint32_t c)
@@ -132,7 +250,7 @@ __device__ inline bool consumes(const sre_dev_pike_t &pk, const sre_dev_inst_t &
     }
 }
 
-/* fresh context for a new stream / line; tags are NOT cleared (see header) */
+/* fresh context for a new stream / line */
 __device__ inline void pike_reset(pike_ctx_t &c, bool first_time)
 {
     pike_hdr_t *h = c.h;
@@ -164,7 +282,7 @@ __device__ inline void list_clear(pike_ctx_t &c, int l)
 {
     pike_hdr_t *h = c.h;
     if (h->head[l] >= 0) {
-        c.t_next[h->tail[l]] = h->free_head;
+        c.t_next(h->tail[l]) = h->free_head;
         h->free_head = h->head[l];
     }
     h->head[l] = h->tail[l] = -1;
@@ -175,11 +293,10 @@ __device__ inline void list_clear(pike_ctx_t &c, int l)
 __device__ inline void cap_load(const sre_dev_pike_t &pk, pike_ctx_t &c, int32_t t, uint32_t *base_out,
                                 uint32_t *cnt_out)
 {
-    const uint32_t r = pk.pc_regex[c.t_pc[t]], base = pk.slot_ofs[r];
+    const uint32_t r = pk.pc_regex[c.t_pc(t)], base = pk.slot_ofs[r];
     const uint32_t cnt = pk.slot_ofs[r + 1] - base;
-    const int64_t *src = c.t_cap + (size_t) t * pk.max_slots;
     for (uint32_t i = 0; i < cnt; i++) {
-        c.cap[base + i] = src[i];
+        c.set_cap(base + i, c.t_cap(t, i));
     }
     *base_out = base;
     *cnt_out = cnt;
@@ -188,18 +305,18 @@ __device__ inline void cap_load(const sre_dev_pike_t &pk, pike_ctx_t &c, int32_t
 __device__ inline void cap_clear(pike_ctx_t &c, uint32_t base, uint32_t cnt)
 {
     for (uint32_t i = 0; i < cnt; i++) {
-        c.cap[base + i] = -1;
+        c.set_cap(base + i, -1);
     }
 }
 
 /* slot g of thread t's full capture vector */
 __device__ inline int64_t thread_slot(const sre_dev_pike_t &pk, const pike_ctx_t &c, int32_t t, uint32_t g)
 {
-    const uint32_t r = pk.pc_regex[c.t_pc[t]], base = pk.slot_ofs[r];
+    const uint32_t r = pk.pc_regex[c.t_pc(t)], base = pk.slot_ofs[r];
     if (g < base || g >= pk.slot_ofs[r + 1]) {
         return -1;
     }
-    return c.t_cap[(size_t) t * pk.max_slots + (g - base)];
+    return c.t_cap(t, g - base);
 }
 
 /* a temporary list used by assertion_hold */
@@ -216,26 +333,25 @@ __device__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, t
     pike_hdr_t *h = c.h;
     const uint32_t tag = h->tag;
     int sp = 0;
-    c.stk[sp].kind = -1;
-    c.stk[sp].pc = pc0;
+    c.stk_set(sp, -1, pc0, 0);
     sp++;
 
     while (sp > 0) {
         sp--;
-        if (c.stk[sp].kind >= 0) {
-            c.cap[c.stk[sp].kind] = c.stk[sp].val;
+        if (c.stk_kind(sp) >= 0) {
+            c.set_cap(c.stk_kind(sp), c.stk_val(sp));
             continue;
         }
-        int32_t pc = c.stk[sp].pc;
+        int32_t pc = c.stk_pc(sp);
 
         for (;;) {
             const sre_dev_inst_t in = pk.insts[pc];
             uint32_t seen_word = 0;
             bool add = false;
 
-            if (c.tags[pc] == tag) {
+            if (c.tag_test(pc, tag)) {
                 /* the revisited-SPLIT rule, :770-786 */
-                if (in.opcode == OP_SPLIT && c.tags[in.y] != tag) {
+                if (in.opcode == OP_SPLIT && !c.tag_test(in.y, tag)) {
                     if (pc == 0) {
                         h->seen_start_state = 1;
                     }
@@ -244,7 +360,7 @@ __device__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, t
                 }
                 break;
             }
-            c.tags[pc] = tag;
+            c.tag_set(pc, tag);
 
             switch (in.opcode) {
             case OP_JMP:
@@ -258,8 +374,7 @@ __device__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, t
                 if (sp >= (int) pk.stack_cap) {
                     return SRE_K_ERROR;
                 }
-                c.stk[sp].kind = -1;
-                c.stk[sp].pc = in.y;
+                c.stk_set(sp, -1, in.y, 0);
                 sp++;
                 pc = in.x;
                 continue;
@@ -268,10 +383,9 @@ __device__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, t
                 if (sp >= (int) pk.stack_cap) {
                     return SRE_K_ERROR;
                 }
-                c.stk[sp].kind = in.v;
-                c.stk[sp].val = c.cap[in.v];
+                c.stk_set(sp, in.v, 0, c.cap(in.v));
                 sp++;
-                c.cap[in.v] = h->processed_bytes + pos;
+                c.set_cap(in.v, h->processed_bytes + pos);
                 pc++;
                 continue;
 
@@ -305,17 +419,17 @@ __device__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, t
                 break;
 
             case OP_MATCH:
-                h->last_matched_pos = c.cap[1];
+                h->last_matched_pos = c.cap(1);
                 if (want_done) {
                     for (uint32_t i = 0; i < pk.nslots; i++) {
-                        c.matched[i] = c.cap[i];
+                        c.set_matched(i, c.cap(i));
                     }
                     h->matched_id = in.v;
                     /* unwind the undo log so c.cap is the caller's again */
                     while (sp > 0) {
                         sp--;
-                        if (c.stk[sp].kind >= 0) {
-                            c.cap[c.stk[sp].kind] = c.stk[sp].val;
+                        if (c.stk_kind(sp) >= 0) {
+                            c.set_cap(c.stk_kind(sp), c.stk_val(sp));
                         }
                     }
                     return RC_DONE;
@@ -332,29 +446,28 @@ __device__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, t
                 int32_t t;
                 if (h->free_head >= 0) {
                     t = h->free_head;
-                    h->free_head = c.t_next[t];
+                    h->free_head = c.t_next(t);
                 } else if (h->pool_used < (int32_t) pk.max_threads) {
                     t = h->pool_used++;
                 } else {
                     return SRE_K_ERROR;
                 }
-                c.t_pc[t] = pc;
-                c.t_sw[t] = (uint8_t) seen_word;
-                c.t_next[t] = -1;
+                c.t_pc(t) = pc;
+                c.t_sw(t) = seen_word;
+                c.t_next(t) = -1;
                 {
                     /* only the owning regex's slots can be set (see header) */
                     const uint32_t r = pk.pc_regex[pc], base = pk.slot_ofs[r];
                     const uint32_t cnt = pk.slot_ofs[r + 1] - base;
-                    int64_t *dst = c.t_cap + (size_t) t * pk.max_slots;
                     for (uint32_t i = 0; i < cnt; i++) {
-                        dst[i] = c.cap[base + i];
+                        c.set_t_cap(t, i, c.cap(base + i));
                     }
                 }
                 if (l >= 0) {
                     if (h->head[l] < 0) {
                         h->head[l] = t;
                     } else {
-                        c.t_next[h->tail[l]] = t;
+                        c.t_next(h->tail[l]) = t;
                     }
                     h->tail[l] = t;
                     h->count[l]++;
@@ -362,7 +475,7 @@ __device__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, t
                     if (tmp->head < 0) {
                         tmp->head = t;
                     } else {
-                        c.t_next[tmp->tail] = t;
+                        c.t_next(tmp->tail) = t;
                     }
                     tmp->tail = t;
                     tmp->count++;
@@ -406,7 +519,7 @@ __device__ inline int prepare_matched(const sre_dev_pike_t &pk, pike_ctx_t &c, i
     const uint32_t ofs = pk.slot_ofs[id];
     const uint32_t n = complete ? pk.slot_ofs[id + 1] - ofs : 2;
     for (uint32_t i = 0; i < n && i < ovec_slots; i++) {
-        ovector[i] = c.matched[ofs + i];
+        ovector[i] = c.matched(ofs + i);
     }
     if (complete) {
         for (uint32_t i = n; i < ovec_slots; i++) {
@@ -454,9 +567,10 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
     if (h->first_buf) {                             /* :202-229 */
         h->first_buf = 0;
         for (uint32_t i = 0; i < pk.nslots; i++) {
-            c.cap[i] = -1;
+            c.set_cap(i, -1);
         }
         h->tag = h->prog_tag + 1;
+        c.tag_open(h->tag);
         rc = pike_add_thread(pk, c, cl, nullptr, 0, sp, input, false);
         if (rc != SRE_K_OK) {
             h->prog_tag = h->tag;
@@ -464,8 +578,8 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
         }
         h->initial_count = h->count[cl];
         int32_t i = 0;
-        for (int32_t t = h->head[cl]; t >= 0 && c.t_next[t] >= 0; t = c.t_next[t]) {
-            c.initial[i++] = c.t_pc[t];
+        for (int32_t t = h->head[cl]; t >= 0 && c.t_next(t) >= 0; t = c.t_next(t)) {
+            c.initial(i++) = c.t_pc(t);
         }
     } else {
         h->tag = h->prog_tag;
@@ -482,8 +596,8 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
             bool skip = !(sp == last || h->count[cl] != h->initial_count);
             if (skip) {
                 int32_t i = 0;
-                for (int32_t t = h->head[cl]; t >= 0 && c.t_next[t] >= 0; t = c.t_next[t], i++) {
-                    if (c.t_pc[t] != c.initial[i]) {
+                for (int32_t t = h->head[cl]; t >= 0 && c.t_next(t) >= 0; t = c.t_next(t), i++) {
+                    if (c.t_pc(t) != c.initial(i)) {
                         skip = false;
                         break;
                     }
@@ -495,9 +609,10 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
                     sp = p;
                     list_clear(c, cl);
                     for (uint32_t i = 0; i < pk.nslots; i++) {
-                        c.cap[i] = -1;
+                        c.set_cap(i, -1);
                     }
                     h->tag++;
+                    c.tag_open(h->tag);
                     rc = pike_add_thread(pk, c, cl, nullptr, 0, sp, input, false);
                     if (rc != SRE_K_OK) {
                         h->prog_tag = h->tag;
@@ -511,25 +626,26 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
         }
 
         h->tag++;
+        c.tag_open(h->tag);
         const bool at_end = (sp == last);
         const uint32_t byte = at_end ? 0 : input[sp];
         const bool cur_word = !at_end && isword(byte);
 
         while (h->head[cl] >= 0) {                  /* :314-567 */
             const int32_t t = h->head[cl];
-            h->head[cl] = c.t_next[t];
+            h->head[cl] = c.t_next(t);
             if (h->head[cl] < 0) {
                 h->tail[cl] = -1;
             }
             h->count[cl]--;
 
-            const int32_t pc = c.t_pc[t];
+            const int32_t pc = c.t_pc(t);
             const sre_dev_inst_t in = pk.insts[pc];
             bool got_match = false;
             uint32_t cbase = 0, ccnt = 0;
 
             if (in.opcode == OP_ASSERT) {           /* :449-528 */
-                const bool seen_word = c.t_sw[t] || (sp == 0 && h->seen_word);
+                const bool seen_word = c.t_sw(t) != 0 || (sp == 0 && h->seen_word);
                 bool hold = false;
                 switch (in.v) {
                 case AS_SMALL_Z: hold = at_end; break;
@@ -548,7 +664,7 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
                         return SRE_K_ERROR;
                     }
                     if (tl.head >= 0) {             /* prepend, :519-523 */
-                        c.t_next[tl.tail] = h->head[cl];
+                        c.t_next(tl.tail) = h->head[cl];
                         if (h->head[cl] < 0) {
                             h->tail[cl] = tl.tail;
                         }
@@ -560,9 +676,9 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
                 }
             } else if (in.opcode == OP_MATCH) {     /* :530-553 */
                 cap_load(pk, c, t, &cbase, &ccnt);
-                h->last_matched_pos = c.cap[1];
+                h->last_matched_pos = c.cap(1);
                 for (uint32_t i = 0; i < pk.nslots; i++) {
-                    c.matched[i] = c.cap[i];
+                    c.set_matched(i, c.cap(i));
                 }
                 h->matched_id = in.v;
                 got_match = true;
@@ -580,7 +696,7 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
             }
 
             /* free the thread */
-            c.t_next[t] = h->free_head;
+            c.t_next(t) = h->free_head;
             h->free_head = t;
 
             if (got_match) {
@@ -644,7 +760,7 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
     if (ovec_slots > 1) {
         ovector[1] = -1;
     }
-    for (int32_t t = h->head[cl]; t >= 0; t = c.t_next[t]) {
+    for (int32_t t = h->head[cl]; t >= 0; t = c.t_next(t)) {
         for (uint32_t i = 0; i < pk.nregexes; i++) {
             const int64_t b0 = thread_slot(pk, c, t, pk.slot_ofs[i]);
             if (b0 != -1 && (ovector[0] == -1 || b0 < ovector[0])) {
@@ -665,19 +781,18 @@ __global__ void __launch_bounds__(128)
 k_pike_lines(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
              size_t nlines, size_t pitch, size_t linelen, const int32_t *__restrict__ select,
              const int32_t *__restrict__ start_hint, int32_t *__restrict__ rc, int64_t *__restrict__ ovec,
-             uint32_t ovec_slots, uint8_t *scratch, size_t nctx, int retry_only)
+             uint32_t ovec_slots, uint8_t *scratch, size_t nctx, int retry_only, uint32_t stride,
+             int smem_tags)
 {
     const size_t tid = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= nctx) {
         return;
     }
-    pike_ctx_t c = pike_carve(pk, scratch + tid * pk.ctx_stride);
+    extern __shared__ uint32_t smem_marks[];
+    pike_ctx_t c;
+    pike_attach(c, pk, batch_base(pk, scratch, tid, stride), stride,
+                smem_tags ? smem_marks + threadIdx.x : nullptr, blockDim.x);
     bool first = true;
-    /* the scratch is reused across launches: stale tags must not alias the
-     * restarted tag counter */
-    for (uint32_t i = 0; i <= pk.len; i++) {
-        c.tags[i] = 0;
-    }
 
     for (size_t line = tid; line < nlines; line += nctx) {
         int64_t *ov = ovec + line * ovec_slots;
@@ -697,12 +812,6 @@ k_pike_lines(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
         const size_t end = offsets ? (size_t) offsets[line + 1] : start + linelen;
         pike_reset(c, first);
         first = false;
-        if (c.h->tag > 0xf0000000u) {       /* tag space nearly used up */
-            for (uint32_t i = 0; i <= pk.len; i++) {
-                c.tags[i] = 0;
-            }
-            c.h->tag = c.h->prog_tag = 0;
-        }
         int pending;
         const int r = pike_exec(pk, c, buf + start, (int64_t) (end - start), true, ov, ovec_slots,
                                 &pending, start_hint ? start_hint[line] : 0);
@@ -727,16 +836,16 @@ __global__ void __launch_bounds__(128)
 k_pike_lines_all(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
                  size_t nlines, size_t pitch, size_t linelen, uint32_t max_matches,
                  int32_t *__restrict__ count, int64_t *__restrict__ spans, int32_t *__restrict__ ids,
-                 uint8_t *scratch, size_t nctx)
+                 uint8_t *scratch, size_t nctx, uint32_t stride, int smem_tags)
 {
     const size_t tid = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= nctx) {
         return;
     }
-    pike_ctx_t c = pike_carve(pk, scratch + tid * pk.ctx_stride);
-    for (uint32_t i = 0; i <= pk.len; i++) {
-        c.tags[i] = 0;
-    }
+    extern __shared__ uint32_t smem_marks[];
+    pike_ctx_t c;
+    pike_attach(c, pk, batch_base(pk, scratch, tid, stride), stride,
+                smem_tags ? smem_marks + threadIdx.x : nullptr, blockDim.x);
     bool first = true;
     for (size_t line = tid; line < nlines; line += nctx) {
         const size_t start = offsets ? (size_t) offsets[line] : line * pitch;
@@ -766,20 +875,24 @@ k_pike_lines_all(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64
 
 __global__ void k_pike_ctx_init(sre_dev_pike_t pk, uint8_t *ctx)
 {
-    pike_ctx_t c = pike_carve(pk, ctx);
-    for (uint32_t i = 0; i <= pk.len; i++) {
-        c.tags[i] = 0;
-    }
+    pike_ctx_t c;
+    pike_attach(c, pk, reinterpret_cast<uint32_t *>(ctx), 1);
+    c.tag_open(0);
+    c.tag_open(1);
     pike_reset(c, true);
+    pike_hdr_store(pk, c);
 }
 
 /* out[0] = rc, out[1] = pending flag, out[2..3] = pending, out[4..] = ovector */
 __global__ void k_pike_stream(sre_dev_pike_t pk, uint8_t *ctx, const uint8_t *buf, size_t len, int eof,
                               int64_t *out, uint32_t ovec_slots)
 {
-    pike_ctx_t c = pike_carve(pk, ctx);
+    pike_ctx_t c;
+    pike_attach(c, pk, reinterpret_cast<uint32_t *>(ctx), 1);
+    pike_hdr_load(pk, c);
     int pending = 0;
     const int r = pike_exec(pk, c, buf, (int64_t) len, eof != 0, out + 4, ovec_slots, &pending);
+    pike_hdr_store(pk, c);
     out[0] = r;
     out[1] = pending;
     out[2] = c.h->pending[0];
@@ -788,10 +901,36 @@ __global__ void k_pike_stream(sre_dev_pike_t pk, uint8_t *ctx, const uint8_t *bu
 
 }  // namespace
 
+/* per-context (1, default) or warp-interleaved (32) scratch; SRE_PIKE_INTERLEAVE=1
+ * selects the latter (measured slower on divergent multi-pattern sets) */
+static uint32_t batch_stride()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SRE_PIKE_INTERLEAVE");
+        v = (e && atoi(e) > 0) ? 32 : 1;
+    }
+    return (uint32_t) v;
+}
+
+/* shared memory for the dedup marks of a 128-thread block; 0 = keep them in
+ * the context block (programs beyond ~3000 instructions) */
+static size_t mark_bytes(const sre_dev_pike_t &pk)
+{
+    static bool opted = false;
+    if (!opted) {
+        opted = true;
+        cudaFuncSetAttribute(k_pike_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(k_pike_lines_all, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    }
+    const size_t b = (size_t) 2 * ((pk.len + 1 + 31) / 32) * 128 * sizeof(uint32_t);
+    return b <= 96 * 1024 ? b : 0;
+}
+
 size_t sre_pike_ctx_bytes(uint32_t len, uint32_t nslots, uint32_t max_slots, uint32_t nthreads,
     uint32_t stack_cap)
 {
-    return pike_ctx_bytes(len, nslots, max_slots, nthreads, stack_cap);
+    return pike_layout(len, nslots, max_slots, nthreads, stack_cap).words * 4;
 }
 
 cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
@@ -806,8 +945,10 @@ cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
         ++*launches;
     }
     const unsigned grid = (unsigned) ((nctx + 127) / 128);
-    k_pike_lines<<<grid, 128, 0, stream>>>(pk, buf, offsets, nlines, pitch, linelen, select, start, rc, ovec,
-                                          ovec_slots, scratch, nctx, retry_only);
+    const size_t marks = mark_bytes(pk);
+    k_pike_lines<<<grid, 128, marks, stream>>>(pk, buf, offsets, nlines, pitch, linelen, select, start, rc,
+                                              ovec, ovec_slots, scratch, nctx, retry_only, batch_stride(),
+                                              marks != 0);
     return cudaGetLastError();
 }
 
@@ -822,8 +963,10 @@ cudaError_t sre_launch_pike_lines_all(const sre_dev_pike_t &pk, const uint8_t *b
         ++*launches;
     }
     const unsigned grid = (unsigned) ((nctx + 127) / 128);
-    k_pike_lines_all<<<grid, 128, 0, stream>>>(pk, buf, offsets, nlines, pitch, linelen, max_matches, count,
-                                              spans, ids, scratch, nctx);
+    const size_t marks = mark_bytes(pk);
+    k_pike_lines_all<<<grid, 128, marks, stream>>>(pk, buf, offsets, nlines, pitch, linelen, max_matches,
+                                                  count, spans, ids, scratch, nctx, batch_stride(),
+                                                  marks != 0);
     return cudaGetLastError();
 }
 
