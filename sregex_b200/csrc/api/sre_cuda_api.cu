@@ -330,6 +330,29 @@ int upload(sre_cuda_program_t *cp)
     pk.slot_ofs = reinterpret_cast<const uint32_t *>(base + o_slots);
     pk.pc_regex = reinterpret_cast<const uint16_t *>(base + o_pcre);
     pk.max_slots = max_slots;
+    /* byte set of the leading instructions (sre_regex_compiler.c:123-241), for
+     * the kernel's start-state shortcut */
+    memset(pk.leadset, 0, sizeof(pk.leadset));
+    for (uint32_t i = 0; i < prog->nleading; i++) {
+        const sre_instruction_t &in = prog->insts[prog->leading[i]];
+        for (uint32_t b = 0; b < 256; b++) {
+            bool hit = false;
+            if (in.opcode == SRE_OPCODE_CHAR) {
+                hit = (in.ch == b);
+            } else {
+                for (uint32_t j = 0; j < in.nranges; j++) {
+                    const sre_vm_range_t &r = prog->ranges[in.v + j];
+                    hit |= (b >= r.from && b <= r.to);
+                }
+                if (in.opcode == SRE_OPCODE_NOTIN) {
+                    hit = !hit;
+                }
+            }
+            if (hit) {
+                pk.leadset[b >> 5] |= 1u << (b & 31);
+            }
+        }
+    }
     pk.max_threads = 2 * prog->len + 16;
     pk.stack_cap = 2 * prog->len + 8;
     pk.ctx_stride = (sre_pike_ctx_bytes(pk.len, pk.nslots, pk.max_slots, pk.max_threads, pk.stack_cap) + 255)

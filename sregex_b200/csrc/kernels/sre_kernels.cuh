@@ -70,6 +70,7 @@ struct sre_dev_pike_t {
     uint32_t                 max_threads;   /* thread pool entries per ctx    */
     uint32_t                 stack_cap;     /* DFS stack entries per ctx      */
     uint64_t                 ctx_stride;    /* bytes of scratch per ctx       */
+    uint32_t                 leadset[8];    /* bytes some leading inst takes  */
 };
 
 /* launchers (sre_kernels.cu); all asynchronous on `stream` ------------------ */

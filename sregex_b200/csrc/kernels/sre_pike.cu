@@ -49,11 +49,9 @@ struct pike_hdr_t {
     int32_t   cur;                          /* which one is clist            */
     int32_t   free_head, pool_used;
     int32_t   has_matched, matched_id;
-    int32_t   initial_count;
     int64_t   last_matched_pos;
     int64_t   pending[2];
-    uint8_t   first_buf, seen_start_state, eof, empty_capture, seen_newline, seen_word,
-              error, pad;
+    uint8_t   first_buf, eof, empty_capture, seen_newline, seen_word, error, pad[2];
 };
 
 /*
@@ -70,8 +68,17 @@ struct pike_ctx_t {
     pike_hdr_t   *h;            /* = &hdr */
     uint32_t     *base;
     uint32_t      stride;
-    uint32_t      o_initial, o_matched, o_cap, o_thr, o_stk, o_hdr;
+    uint32_t      o_matched, o_thr, o_stk, o_hdr;
     uint32_t      max_slots, rec;       /* rec = words of one thread record */
+    /* working capture: only the slots [cap_base, cap_base + max_slots) of one
+     * regex can be set at any time (see header), so that window is all that
+     * is stored: 64-bit slot j at capp[(2j, 2j+1) * cstride] */
+    uint32_t     *capp;
+    uint32_t      cstride, cap_base;
+    /* first SK entries of the DFS stack (shared memory in the kernels); deeper
+     * entries spill to the context block */
+    uint32_t     *stkp;
+    uint32_t      sstride, sk;
     /* dedup marks: two bit sets (epoch parity) of tagw words each; word i of
      * set p is tagp[(p * tagw + i) * tstride] -- shared memory in the batch
      * kernels when it fits, else part of the context block */
@@ -107,10 +114,6 @@ struct pike_ctx_t {
             tagword(tag, i) = 0;
         }
     }
-    __device__ __forceinline__ int32_t &initial(uint32_t i) const
-    {
-        return reinterpret_cast<int32_t &>(W(o_initial + i));
-    }
     /* thread record t: {pc, next, seen_word, cap[max_slots]} */
     __device__ __forceinline__ int32_t &t_pc(uint32_t t) const
     {
@@ -121,8 +124,30 @@ struct pike_ctx_t {
         return reinterpret_cast<int32_t &>(W(o_thr + t * rec + 1));
     }
     __device__ __forceinline__ uint32_t &t_sw(uint32_t t) const { return W(o_thr + t * rec + 2); }
-    __device__ __forceinline__ int64_t cap(uint32_t i) const { return get64(o_cap + 2 * i); }
-    __device__ __forceinline__ void set_cap(uint32_t i, int64_t v) const { set64(o_cap + 2 * i, v); }
+    /* absolute slot i of the working capture */
+    __device__ __forceinline__ int64_t cap(uint32_t i) const
+    {
+        const uint32_t j = i - cap_base;
+        if (j >= max_slots) {
+            return -1;
+        }
+        return (int64_t) (((uint64_t) capp[(size_t) (2 * j + 1) * cstride] << 32) | capp[(size_t) 2 * j * cstride]);
+    }
+    /* i must lie in the current window */
+    __device__ __forceinline__ void set_cap(uint32_t i, int64_t v) const
+    {
+        const uint32_t j = i - cap_base;
+        if (j < max_slots) {
+            capp[(size_t) 2 * j * cstride] = (uint32_t) v;
+            capp[(size_t) (2 * j + 1) * cstride] = (uint32_t) ((uint64_t) v >> 32);
+        }
+    }
+    __device__ __forceinline__ void cap_reset() const
+    {
+        for (uint32_t j = 0; j < 2 * max_slots; j++) {
+            capp[(size_t) j * cstride] = 0xffffffffu;
+        }
+    }
     __device__ __forceinline__ int64_t matched(uint32_t i) const { return get64(o_matched + 2 * i); }
     __device__ __forceinline__ void set_matched(uint32_t i, int64_t v) const { set64(o_matched + 2 * i, v); }
     __device__ __forceinline__ int64_t t_cap(uint32_t t, uint32_t i) const
@@ -134,20 +159,31 @@ struct pike_ctx_t {
         set64(o_thr + t * rec + 3 + 2 * i, v);
     }
     /* DFS stack entry: {kind, pc, val} */
-    __device__ __forceinline__ int32_t stk_kind(uint32_t i) const { return (int32_t) W(o_stk + 4 * i); }
-    __device__ __forceinline__ int32_t stk_pc(uint32_t i) const { return (int32_t) W(o_stk + 4 * i + 1); }
-    __device__ __forceinline__ int64_t stk_val(uint32_t i) const { return get64(o_stk + 4 * i + 2); }
+    __device__ __forceinline__ uint32_t &stkw(uint32_t i, uint32_t k) const
+    {
+        if (i < sk) {
+            return stkp[(size_t) (4 * i + k) * sstride];
+        }
+        return W(o_stk + 4 * i + k);
+    }
+    __device__ __forceinline__ int32_t stk_kind(uint32_t i) const { return (int32_t) stkw(i, 0); }
+    __device__ __forceinline__ int32_t stk_pc(uint32_t i) const { return (int32_t) stkw(i, 1); }
+    __device__ __forceinline__ int64_t stk_val(uint32_t i) const
+    {
+        return (int64_t) (((uint64_t) stkw(i, 3) << 32) | stkw(i, 2));
+    }
     __device__ __forceinline__ void stk_set(uint32_t i, int32_t kind, int32_t pc, int64_t val) const
     {
-        W(o_stk + 4 * i) = (uint32_t) kind;
-        W(o_stk + 4 * i + 1) = (uint32_t) pc;
-        set64(o_stk + 4 * i + 2, val);
+        stkw(i, 0) = (uint32_t) kind;
+        stkw(i, 1) = (uint32_t) pc;
+        stkw(i, 2) = (uint32_t) val;
+        stkw(i, 3) = (uint32_t) ((uint64_t) val >> 32);
     }
 };
 
 /* words of one context block; the same walk gives the section offsets */
 struct pike_layout_t {
-    uint32_t o_tags, o_initial, o_matched, o_cap, o_thr, o_stk, o_hdr, tagw, rec;
+    uint32_t o_tags, o_matched, o_cap, o_thr, o_stk, o_hdr, tagw, rec;
     size_t   words;
 };
 
@@ -159,9 +195,8 @@ __host__ __device__ inline pike_layout_t pike_layout(uint32_t len, uint32_t nslo
     L.tagw = (len + 1 + 31) / 32;
     L.rec = 3 + 2 * max_slots;
     L.o_tags = (uint32_t) o;     o += 2 * (size_t) L.tagw;
-    L.o_initial = (uint32_t) o;  o += len + 1;
     L.o_matched = (uint32_t) o;  o += 2 * (size_t) nslots;
-    L.o_cap = (uint32_t) o;      o += 2 * (size_t) nslots;
+    L.o_cap = (uint32_t) o;      o += 2 * (size_t) max_slots;
     L.o_thr = (uint32_t) o;      o += (size_t) nthreads * L.rec;
     L.o_stk = (uint32_t) o;      o += 4 * (size_t) stack_cap;
     L.o_hdr = (uint32_t) o;      o += (sizeof(pike_hdr_t) + 3) / 4;    /* streaming ctx only */
@@ -169,10 +204,30 @@ __host__ __device__ inline pike_layout_t pike_layout(uint32_t len, uint32_t nslo
     return L;
 }
 
-/* attach a context view to its memory: base = first word of this lane.
- * smem_tags: marks of this context in shared memory (word stride smem_stride) */
+/* shared memory of a block of B contexts: [marks | stack | capture window],
+ * each part optional (bit 0 / 1 / 2 of `parts`) */
+enum { SM_MARKS = 1, SM_STACK = 2, SM_CAP = 4, SM_STACK_ENTRIES = 8 };
+
+__host__ __device__ inline size_t pike_smem_words(const sre_dev_pike_t &pk, int parts, uint32_t B)
+{
+    size_t w = 0;
+    if (parts & SM_MARKS) {
+        w += (size_t) 2 * ((pk.len + 1 + 31) / 32) * B;
+    }
+    if (parts & SM_STACK) {
+        w += (size_t) 4 * SM_STACK_ENTRIES * B;
+    }
+    if (parts & SM_CAP) {
+        w += (size_t) 2 * pk.max_slots * B;
+    }
+    return w;
+}
+
+/* attach a context view to its memory: base = first word of this lane of the
+ * context block; smem = the block's shared memory, this context being lane
+ * `lane` of B */
 __device__ inline void pike_attach(pike_ctx_t &c, const sre_dev_pike_t &pk, uint32_t *base, uint32_t stride,
-                                   uint32_t *smem_tags = nullptr, uint32_t smem_stride = 0)
+                                   uint32_t *smem, int parts, uint32_t lane, uint32_t B)
 {
     const pike_layout_t L = pike_layout(pk.len, pk.nslots, pk.max_slots, pk.max_threads, pk.stack_cap);
     c.h = &c.hdr;
@@ -180,19 +235,36 @@ __device__ inline void pike_attach(pike_ctx_t &c, const sre_dev_pike_t &pk, uint
     c.stride = stride;
     c.max_slots = pk.max_slots;
     c.rec = L.rec;
-    c.o_initial = L.o_initial;
     c.o_matched = L.o_matched;
-    c.o_cap = L.o_cap;
     c.o_thr = L.o_thr;
     c.o_stk = L.o_stk;
     c.o_hdr = L.o_hdr;
     c.tagw = L.tagw;
-    if (smem_tags) {
-        c.tagp = smem_tags;
-        c.tstride = smem_stride;
+    c.cap_base = 0;
+    if (parts & SM_MARKS) {
+        c.tagp = smem + lane;
+        c.tstride = B;
+        smem += (size_t) 2 * L.tagw * B;
     } else {
         c.tagp = base + (size_t) L.o_tags * stride;
         c.tstride = stride;
+    }
+    if (parts & SM_STACK) {
+        c.stkp = smem + lane;
+        c.sstride = B;
+        c.sk = SM_STACK_ENTRIES;
+        smem += (size_t) 4 * SM_STACK_ENTRIES * B;
+    } else {
+        c.stkp = nullptr;
+        c.sstride = 0;
+        c.sk = 0;
+    }
+    if (parts & SM_CAP) {
+        c.capp = smem + lane;
+        c.cstride = B;
+    } else {
+        c.capp = base + (size_t) L.o_cap * stride;
+        c.cstride = stride;
     }
 }
 
@@ -267,10 +339,8 @@ __device__ inline void pike_reset(pike_ctx_t &c, bool first_time)
     h->pool_used = 0;
     h->has_matched = 0;
     h->matched_id = 0;
-    h->initial_count = 0;
     h->last_matched_pos = -1;
     h->first_buf = 1;
-    h->seen_start_state = 0;
     h->eof = 0;
     h->empty_capture = 0;
     h->seen_newline = 0;
@@ -295,6 +365,7 @@ __device__ inline void cap_load(const sre_dev_pike_t &pk, pike_ctx_t &c, int32_t
 {
     const uint32_t r = pk.pc_regex[c.t_pc(t)], base = pk.slot_ofs[r];
     const uint32_t cnt = pk.slot_ofs[r + 1] - base;
+    c.cap_base = base;
     for (uint32_t i = 0; i < cnt; i++) {
         c.set_cap(base + i, c.t_cap(t, i));
     }
@@ -304,6 +375,8 @@ __device__ inline void cap_load(const sre_dev_pike_t &pk, pike_ctx_t &c, int32_t
 
 __device__ inline void cap_clear(pike_ctx_t &c, uint32_t base, uint32_t cnt)
 {
+    /* add_thread may have moved the (then all -1) window to another regex */
+    c.cap_base = base;
     for (uint32_t i = 0; i < cnt; i++) {
         c.set_cap(base + i, -1);
     }
@@ -326,9 +399,21 @@ struct tmp_list_t { int32_t head, tail, count; };
  * add_thread (sre_vm_pike.c:756-942).  Appends to list `l` (0/1) or, when
  * l < 0, to *tmp.  c.cap holds the capture of the calling thread and is
  * restored to that value on return.  Returns SRE_K_OK, RC_DONE or SRE_K_ERROR.
+ *
+ * nb = the byte the new threads will be stepped on (0..255), NB_END when they
+ * will only see the end of input, NB_UNKNOWN when it is not in this buffer.
+ * A thread parked on a consuming instruction that cannot take nb would be
+ * dropped by the next step without any effect, so it is not appended at all;
+ * for the same reason the whole closure of the regexes is skipped at the
+ * start state when nb is outside the leading-byte set (nleading != 0 means
+ * every path from pc 0 must first consume a leading byte).  Lists at the end
+ * of a non-final buffer are complete (NB_UNKNOWN), so AGAIN, the temporary
+ * captures and pending matches are those of the reference.
  */
+enum { NB_END = -2, NB_UNKNOWN = -1 };
+
 __device__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, tmp_list_t *tmp,
-    int32_t pc0, int64_t pos, const uint8_t *buffer, bool want_done)
+    int32_t pc0, int64_t pos, const uint8_t *buffer, bool want_done, int nb)
 {
     pike_hdr_t *h = c.h;
     const uint32_t tag = h->tag;
@@ -352,9 +437,6 @@ __device__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, t
             if (c.tag_test(pc, tag)) {
                 /* the revisited-SPLIT rule, :770-786 */
                 if (in.opcode == OP_SPLIT && !c.tag_test(in.y, tag)) {
-                    if (pc == 0) {
-                        h->seen_start_state = 1;
-                    }
                     pc = in.y;
                     continue;
                 }
@@ -368,8 +450,11 @@ __device__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, t
                 continue;
 
             case OP_SPLIT:
-                if (pc == 0) {
-                    h->seen_start_state = 1;
+                if (pc == 0 && pk.nleading && nb != NB_UNKNOWN
+                    && (nb == NB_END || !((pk.leadset[nb >> 5] >> (nb & 31)) & 1)))
+                {
+                    pc = in.y;          /* only the ".*?" thread can go on */
+                    continue;
                 }
                 if (sp >= (int) pk.stack_cap) {
                     return SRE_K_ERROR;
@@ -383,6 +468,7 @@ __device__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, t
                 if (sp >= (int) pk.stack_cap) {
                     return SRE_K_ERROR;
                 }
+                c.cap_base = pk.slot_ofs[pk.pc_regex[pc]];
                 c.stk_set(sp, in.v, 0, c.cap(in.v));
                 sp++;
                 c.set_cap(in.v, h->processed_bytes + pos);
@@ -437,8 +523,8 @@ __device__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, t
                 add = true;
                 break;
 
-            default:
-                add = true;
+            default:                    /* CHAR / ANY / IN / NOTIN */
+                add = !(nb == NB_END || (nb >= 0 && !consumes(pk, in, (uint32_t) nb)));
                 break;
             }
 
@@ -566,20 +652,15 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
 
     if (h->first_buf) {                             /* :202-229 */
         h->first_buf = 0;
-        for (uint32_t i = 0; i < pk.nslots; i++) {
-            c.set_cap(i, -1);
-        }
+        c.cap_base = 0;
+        c.cap_reset();
         h->tag = h->prog_tag + 1;
         c.tag_open(h->tag);
-        rc = pike_add_thread(pk, c, cl, nullptr, 0, sp, input, false);
+        rc = pike_add_thread(pk, c, cl, nullptr, 0, sp, input, false,
+                             sp < last ? (int) input[sp] : (eof ? NB_END : NB_UNKNOWN));
         if (rc != SRE_K_OK) {
             h->prog_tag = h->tag;
             return SRE_K_ERROR;
-        }
-        h->initial_count = h->count[cl];
-        int32_t i = 0;
-        for (int32_t t = h->head[cl]; t >= 0 && c.t_next(t) >= 0; t = c.t_next(t)) {
-            c.initial(i++) = c.t_pc(t);
         }
     } else {
         h->tag = h->prog_tag;
@@ -590,38 +671,17 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
             break;
         }
 
-        /* first-byte prefilter, :256-309 */
-        if (pk.nleading && h->seen_start_state) {
-            h->seen_start_state = 0;
-            bool skip = !(sp == last || h->count[cl] != h->initial_count);
-            if (skip) {
-                int32_t i = 0;
-                for (int32_t t = h->head[cl]; t >= 0 && c.t_next(t) >= 0; t = c.t_next(t), i++) {
-                    if (c.t_pc(t) != c.initial(i)) {
-                        skip = false;
-                        break;
-                    }
-                }
-            }
-            if (skip) {
-                const int64_t p = find_first_byte(pk, input, sp, last);
-                if (p > sp) {
-                    sp = p;
-                    list_clear(c, cl);
-                    for (uint32_t i = 0; i < pk.nslots; i++) {
-                        c.set_cap(i, -1);
-                    }
-                    h->tag++;
-                    c.tag_open(h->tag);
-                    rc = pike_add_thread(pk, c, cl, nullptr, 0, sp, input, false);
-                    if (rc != SRE_K_OK) {
-                        h->prog_tag = h->tag;
-                        return SRE_K_ERROR;
-                    }
-                    if (sp == last) {
-                        break;
-                    }
-                }
+        /*
+         * First-byte prefilter (:256-309, find_first_byte :992-1061; result-
+         * neutral in the reference too).  Here the list holds nothing but the
+         * ".*?" thread exactly when no regex thread is in flight, and then the
+         * scan can move to just before the next byte a leading instruction
+         * takes: stepping the ".*?" thread there rebuilds the start closure.
+         */
+        if (pk.nleading && h->count[cl] == 1 && sp + 1 < last && c.t_pc(h->head[cl]) == 1) {
+            const int64_t p = find_first_byte(pk, input, sp + 1, last);
+            if (p - 1 > sp) {
+                sp = p - 1;
             }
         }
 
@@ -630,6 +690,8 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
         const bool at_end = (sp == last);
         const uint32_t byte = at_end ? 0 : input[sp];
         const bool cur_word = !at_end && isword(byte);
+        const int nb_cur = at_end ? NB_END : (int) byte;
+        const int nb_next = sp + 1 < last ? (int) input[sp + 1] : (eof ? NB_END : NB_UNKNOWN);
 
         while (h->head[cl] >= 0) {                  /* :314-567 */
             const int32_t t = h->head[cl];
@@ -658,7 +720,7 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
                     cap_load(pk, c, t, &cbase, &ccnt);
                     tmp_list_t tl = { -1, -1, 0 };
                     h->tag--;
-                    rc = pike_add_thread(pk, c, -1, &tl, pc + 1, sp, input, false);
+                    rc = pike_add_thread(pk, c, -1, &tl, pc + 1, sp, input, false, nb_cur);
                     if (rc != SRE_K_OK) {
                         h->prog_tag = h->tag + 1;
                         return SRE_K_ERROR;
@@ -685,7 +747,7 @@ __device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t 
                 cap_clear(c, cbase, ccnt);
             } else if (!at_end && consumes(pk, in, byte)) {
                 cap_load(pk, c, t, &cbase, &ccnt);
-                rc = pike_add_thread(pk, c, nl, nullptr, pc + 1, sp + 1, input, true);
+                rc = pike_add_thread(pk, c, nl, nullptr, pc + 1, sp + 1, input, true, nb_next);
                 cap_clear(c, cbase, ccnt);
                 if (rc == RC_DONE) {
                     got_match = true;
@@ -782,16 +844,15 @@ k_pike_lines(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
              size_t nlines, size_t pitch, size_t linelen, const int32_t *__restrict__ select,
              const int32_t *__restrict__ start_hint, int32_t *__restrict__ rc, int64_t *__restrict__ ovec,
              uint32_t ovec_slots, uint8_t *scratch, size_t nctx, int retry_only, uint32_t stride,
-             int smem_tags)
+             int parts)
 {
     const size_t tid = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= nctx) {
         return;
     }
-    extern __shared__ uint32_t smem_marks[];
+    extern __shared__ uint32_t smem_ctx[];
     pike_ctx_t c;
-    pike_attach(c, pk, batch_base(pk, scratch, tid, stride), stride,
-                smem_tags ? smem_marks + threadIdx.x : nullptr, blockDim.x);
+    pike_attach(c, pk, batch_base(pk, scratch, tid, stride), stride, smem_ctx, parts, threadIdx.x, blockDim.x);
     bool first = true;
 
     for (size_t line = tid; line < nlines; line += nctx) {
@@ -836,16 +897,15 @@ __global__ void __launch_bounds__(128)
 k_pike_lines_all(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
                  size_t nlines, size_t pitch, size_t linelen, uint32_t max_matches,
                  int32_t *__restrict__ count, int64_t *__restrict__ spans, int32_t *__restrict__ ids,
-                 uint8_t *scratch, size_t nctx, uint32_t stride, int smem_tags)
+                 uint8_t *scratch, size_t nctx, uint32_t stride, int parts)
 {
     const size_t tid = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= nctx) {
         return;
     }
-    extern __shared__ uint32_t smem_marks[];
+    extern __shared__ uint32_t smem_ctx[];
     pike_ctx_t c;
-    pike_attach(c, pk, batch_base(pk, scratch, tid, stride), stride,
-                smem_tags ? smem_marks + threadIdx.x : nullptr, blockDim.x);
+    pike_attach(c, pk, batch_base(pk, scratch, tid, stride), stride, smem_ctx, parts, threadIdx.x, blockDim.x);
     bool first = true;
     for (size_t line = tid; line < nlines; line += nctx) {
         const size_t start = offsets ? (size_t) offsets[line] : line * pitch;
@@ -876,7 +936,7 @@ k_pike_lines_all(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64
 __global__ void k_pike_ctx_init(sre_dev_pike_t pk, uint8_t *ctx)
 {
     pike_ctx_t c;
-    pike_attach(c, pk, reinterpret_cast<uint32_t *>(ctx), 1);
+    pike_attach(c, pk, reinterpret_cast<uint32_t *>(ctx), 1, nullptr, 0, 0, 1);
     c.tag_open(0);
     c.tag_open(1);
     pike_reset(c, true);
@@ -885,11 +945,13 @@ __global__ void k_pike_ctx_init(sre_dev_pike_t pk, uint8_t *ctx)
 
 /* out[0] = rc, out[1] = pending flag, out[2..3] = pending, out[4..] = ovector */
 __global__ void k_pike_stream(sre_dev_pike_t pk, uint8_t *ctx, const uint8_t *buf, size_t len, int eof,
-                              int64_t *out, uint32_t ovec_slots)
+                              int64_t *out, uint32_t ovec_slots, int parts)
 {
+    extern __shared__ uint32_t smem_ctx[];
     pike_ctx_t c;
-    pike_attach(c, pk, reinterpret_cast<uint32_t *>(ctx), 1);
+    pike_attach(c, pk, reinterpret_cast<uint32_t *>(ctx), 1, smem_ctx, parts, 0, 1);
     pike_hdr_load(pk, c);
+    c.cap_reset();      /* between calls the working capture is all -1 */
     int pending = 0;
     const int r = pike_exec(pk, c, buf, (int64_t) len, eof != 0, out + 4, ovec_slots, &pending);
     pike_hdr_store(pk, c);
@@ -913,9 +975,9 @@ static uint32_t batch_stride()
     return (uint32_t) v;
 }
 
-/* shared memory for the dedup marks of a 128-thread block; 0 = keep them in
- * the context block (programs beyond ~3000 instructions) */
-static size_t mark_bytes(const sre_dev_pike_t &pk)
+/* which parts of a context go to shared memory for blocks of B contexts;
+ * *bytes = dynamic shared memory to ask for */
+static int smem_parts(const sre_dev_pike_t &pk, uint32_t B, bool marks_allowed, size_t *bytes)
 {
     static bool opted = false;
     if (!opted) {
@@ -923,8 +985,16 @@ static size_t mark_bytes(const sre_dev_pike_t &pk)
         cudaFuncSetAttribute(k_pike_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         cudaFuncSetAttribute(k_pike_lines_all, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     }
-    const size_t b = (size_t) 2 * ((pk.len + 1 + 31) / 32) * 128 * sizeof(uint32_t);
-    return b <= 96 * 1024 ? b : 0;
+    const size_t budget = B == 1 ? 40 * 1024 : 96 * 1024;
+    int parts = SM_STACK;
+    if (pike_smem_words(pk, parts | SM_CAP, B) * 4 <= budget / 2) {
+        parts |= SM_CAP;
+    }
+    if (marks_allowed && pike_smem_words(pk, parts | SM_MARKS, B) * 4 <= budget) {
+        parts |= SM_MARKS;
+    }
+    *bytes = pike_smem_words(pk, parts, B) * 4;
+    return parts;
 }
 
 size_t sre_pike_ctx_bytes(uint32_t len, uint32_t nslots, uint32_t max_slots, uint32_t nthreads,
@@ -945,10 +1015,11 @@ cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
         ++*launches;
     }
     const unsigned grid = (unsigned) ((nctx + 127) / 128);
-    const size_t marks = mark_bytes(pk);
-    k_pike_lines<<<grid, 128, marks, stream>>>(pk, buf, offsets, nlines, pitch, linelen, select, start, rc,
-                                              ovec, ovec_slots, scratch, nctx, retry_only, batch_stride(),
-                                              marks != 0);
+    size_t smem;
+    const int parts = smem_parts(pk, 128, true, &smem);
+    k_pike_lines<<<grid, 128, smem, stream>>>(pk, buf, offsets, nlines, pitch, linelen, select, start, rc,
+                                             ovec, ovec_slots, scratch, nctx, retry_only, batch_stride(),
+                                             parts);
     return cudaGetLastError();
 }
 
@@ -963,10 +1034,10 @@ cudaError_t sre_launch_pike_lines_all(const sre_dev_pike_t &pk, const uint8_t *b
         ++*launches;
     }
     const unsigned grid = (unsigned) ((nctx + 127) / 128);
-    const size_t marks = mark_bytes(pk);
-    k_pike_lines_all<<<grid, 128, marks, stream>>>(pk, buf, offsets, nlines, pitch, linelen, max_matches,
-                                                  count, spans, ids, scratch, nctx, batch_stride(),
-                                                  marks != 0);
+    size_t smem;
+    const int parts = smem_parts(pk, 128, true, &smem);
+    k_pike_lines_all<<<grid, 128, smem, stream>>>(pk, buf, offsets, nlines, pitch, linelen, max_matches,
+                                                 count, spans, ids, scratch, nctx, batch_stride(), parts);
     return cudaGetLastError();
 }
 
@@ -988,6 +1059,9 @@ cudaError_t sre_launch_pike_stream(const sre_dev_pike_t &pk, uint8_t *ctx, const
     if (launches) {
         ++*launches;
     }
-    k_pike_stream<<<1, 1, 0, stream>>>(pk, ctx, buf, len, eof, out, ovec_slots);
+    /* the marks persist between calls, so they stay in the ctx block */
+    size_t smem;
+    const int parts = smem_parts(pk, 1, false, &smem);
+    k_pike_stream<<<1, 1, smem, stream>>>(pk, ctx, buf, len, eof, out, ovec_slots, parts);
     return cudaGetLastError();
 }
