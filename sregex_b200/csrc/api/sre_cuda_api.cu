@@ -135,6 +135,123 @@ void program_destroy(void *data)
     delete cp;
 }
 
+/*
+ * The threads add_thread(pc 0) parks on consuming instructions, in the order
+ * the reference's closure walk (sre_vm_pike.c:756-942: x before y, the
+ * revisited-SPLIT rule :770-786) reaches them, each with the slots SAVEd on
+ * its path; then bucketed by the byte they can take.  The Pike kernel appends
+ * bucket[next byte] instead of walking the closure at every position.  Only
+ * for programs whose start closure is context free: nleading != 0 (no MATCH,
+ * no ANY) and no assertion on the way.
+ */
+static bool build_start_closure(const sre_program_t *prog, const std::vector<uint16_t> &pc_regex,
+    const std::vector<uint32_t> &slot_ofs, std::vector<uint32_t> &ofs, std::vector<sre_dev_start_t> &ents)
+{
+    if (!prog->nleading || prog->len < 3 || prog->insts[0].opcode != SRE_OPCODE_SPLIT
+        || prog->insts[0].y != 1 || prog->insts[1].opcode != SRE_OPCODE_ANY)
+    {
+        return false;
+    }
+    struct item_t { int32_t kind, pc; };            /* kind -1: visit pc; else undo one SAVE */
+    std::vector<item_t> stack;
+    std::vector<int32_t> saved;                     /* slots SAVEd on the current path */
+    std::vector<uint8_t> seen(prog->len, 0);
+    std::vector<sre_dev_start_t> finals;
+    seen[0] = 1;
+    stack.push_back({ -1, prog->insts[0].x });
+    while (!stack.empty()) {
+        const item_t it = stack.back();
+        stack.pop_back();
+        if (it.kind >= 0) {
+            saved.pop_back();
+            continue;
+        }
+        int32_t pc = it.pc;
+        for (;;) {
+            if (pc < 0 || (uint32_t) pc >= prog->len) {
+                return false;
+            }
+            const sre_instruction_t &in = prog->insts[pc];
+            if (seen[pc]) {
+                if (in.opcode == SRE_OPCODE_SPLIT && !seen[in.y]) {
+                    pc = in.y;
+                    continue;
+                }
+                break;
+            }
+            seen[pc] = 1;
+            if (in.opcode == SRE_OPCODE_JMP) {
+                pc = in.x;
+                continue;
+            }
+            if (in.opcode == SRE_OPCODE_SPLIT) {
+                stack.push_back({ -1, in.y });
+                pc = in.x;
+                continue;
+            }
+            if (in.opcode == SRE_OPCODE_SAVE) {
+                stack.push_back({ 0, 0 });
+                saved.push_back(in.v);
+                pc++;
+                continue;
+            }
+            if (in.opcode == SRE_OPCODE_ASSERT || in.opcode == SRE_OPCODE_MATCH
+                || in.opcode == SRE_OPCODE_ANY)
+            {
+                return false;
+            }
+            sre_dev_start_t e;
+            memset(&e, 0, sizeof(e));
+            e.pc = pc;
+            const uint32_t base = slot_ofs[pc_regex[pc]], end = slot_ofs[pc_regex[pc] + 1];
+            for (int32_t v : saved) {
+                if ((uint32_t) v < base || (uint32_t) v >= end || (uint32_t) v - base > 255) {
+                    return false;
+                }
+                const uint8_t rel = (uint8_t) ((uint32_t) v - base);
+                bool dup = false;
+                for (uint32_t k = 0; k < e.nsl; k++) {
+                    dup |= (e.sl[k] == rel);
+                }
+                if (dup) {
+                    continue;
+                }
+                if (e.nsl == sizeof(e.sl)) {
+                    return false;
+                }
+                e.sl[e.nsl++] = rel;
+            }
+            finals.push_back(e);
+            break;
+        }
+    }
+    ofs.assign(257, 0);
+    ents.clear();
+    for (uint32_t b = 0; b < 256; b++) {
+        ofs[b] = (uint32_t) ents.size();
+        for (const sre_dev_start_t &e : finals) {
+            const sre_instruction_t &in = prog->insts[e.pc];
+            bool hit = false;
+            if (in.opcode == SRE_OPCODE_CHAR) {
+                hit = (in.ch == b);
+            } else {
+                for (uint32_t j = 0; j < in.nranges; j++) {
+                    const sre_vm_range_t &r = prog->ranges[in.v + j];
+                    hit |= (b >= r.from && b <= r.to);
+                }
+                if (in.opcode == SRE_OPCODE_NOTIN) {
+                    hit = !hit;
+                }
+            }
+            if (hit) {
+                ents.push_back(e);
+            }
+        }
+    }
+    ofs[256] = (uint32_t) ents.size();
+    return true;
+}
+
 int upload(sre_cuda_program_t *cp)
 {
     const sre_program_t *prog = cp->prog;
@@ -256,6 +373,15 @@ int upload(sre_cuda_program_t *cp)
         }
     }
     const size_t o_pcre = b.add(pc_regex.data(), pc_regex.size() * 2);
+    std::vector<uint32_t> start_ofs;
+    std::vector<sre_dev_start_t> start_ent;
+    const bool has_start = build_start_closure(prog, pc_regex, slot_ofs, start_ofs, start_ent);
+    size_t o_sofs = 0, o_sent = 0;
+    if (has_start) {
+        o_sofs = b.add(start_ofs.data(), start_ofs.size() * 4);
+        start_ent.push_back(sre_dev_start_t());       /* never an empty table */
+        o_sent = b.add(start_ent.data(), start_ent.size() * sizeof(sre_dev_start_t));
+    }
 
     if (cudaMalloc(&cp->d_blob, b.bytes.size() + 256) != cudaSuccess
         || cudaMemcpy(cp->d_blob, b.bytes.data(), b.bytes.size(), cudaMemcpyHostToDevice) != cudaSuccess)
@@ -329,6 +455,8 @@ int upload(sre_cuda_program_t *cp)
     pk.leading = reinterpret_cast<const int32_t *>(base + o_leading);
     pk.slot_ofs = reinterpret_cast<const uint32_t *>(base + o_slots);
     pk.pc_regex = reinterpret_cast<const uint16_t *>(base + o_pcre);
+    pk.start_ofs = has_start ? reinterpret_cast<const uint32_t *>(base + o_sofs) : nullptr;
+    pk.start_ent = has_start ? reinterpret_cast<const sre_dev_start_t *>(base + o_sent) : nullptr;
     pk.max_slots = max_slots;
     /* byte set of the leading instructions (sre_regex_compiler.c:123-241), for
      * the kernel's start-state shortcut */

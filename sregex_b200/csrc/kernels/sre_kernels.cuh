@@ -55,6 +55,14 @@ struct sre_dev_inst_t {         /* == host sre_instruction_t, 16 bytes        */
     int32_t   x, y, v;
 };
 
+/* one thread of the start closure (threads that closure(pc 0) parks on a
+ * consuming instruction), with the capture slots the path to it SAVEs */
+struct sre_dev_start_t {
+    int32_t   pc;
+    uint8_t   nsl;          /* slots set to the current position ...          */
+    uint8_t   sl[7];        /* ... relative to the owning regex's first slot  */
+};
+
 struct sre_dev_pike_t {
     uint32_t                 len;           /* instructions                   */
     uint32_t                 nslots;        /* capture slots, all regexes     */
@@ -71,6 +79,10 @@ struct sre_dev_pike_t {
     uint32_t                 stack_cap;     /* DFS stack entries per ctx      */
     uint64_t                 ctx_stride;    /* bytes of scratch per ctx       */
     uint32_t                 leadset[8];    /* bytes some leading inst takes  */
+    /* start closure by next byte: entries [start_ofs[b], start_ofs[b+1]) in
+     * priority order; NULL when closure(pc 0) meets an assertion             */
+    const uint32_t          *start_ofs;
+    const sre_dev_start_t   *start_ent;
 };
 
 /* launchers (sre_kernels.cu); all asynchronous on `stream` ------------------ */

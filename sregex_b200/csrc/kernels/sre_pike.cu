@@ -52,7 +52,9 @@ struct pike_hdr_t {
     int64_t   last_matched_pos;
     int64_t   pending[2];
     uint8_t   first_buf, eof, empty_capture, seen_newline, seen_word, error, pad[2];
+    uint32_t  pad2[2];                      /* 26 words: 2-way bank conflicts at most as a shared array */
 };
+static_assert(sizeof(pike_hdr_t) == 104, "pike_hdr_t layout");
 
 /*
  * Context memory.  Every array element is one or two 32-bit words; word e of a
@@ -60,12 +62,11 @@ struct pike_hdr_t {
  * a warp (stride 32, lane l starts at word l), so that lanes touching the same
  * element -- the common case, they run the same program on similar lines --
  * share 128-byte lines in L1/L2; the streaming ctx of the classic API is a
- * single context with stride 1.  The scalar header lives in registers / local
- * memory (`hdr`) and is only stored in the block between streaming calls.
+ * single context with stride 1.  The scalar header lives in shared memory and
+ * is only stored in the block between streaming calls.
  */
 struct pike_ctx_t {
-    pike_hdr_t    hdr;
-    pike_hdr_t   *h;            /* = &hdr */
+    pike_hdr_t   *h;            /* scalar state, in shared memory */
     uint32_t     *base;
     uint32_t      stride;
     uint32_t      o_matched, o_thr, o_stk, o_hdr;
@@ -220,17 +221,19 @@ __host__ __device__ inline size_t pike_smem_words(const sre_dev_pike_t &pk, int 
     if (parts & SM_CAP) {
         w += (size_t) 2 * pk.max_slots * B;
     }
+    w = (w + 1) & ~(size_t) 1;
+    w += sizeof(pike_hdr_t) / 4 * B;        /* always */
     return w;
 }
 
 /* attach a context view to its memory: base = first word of this lane of the
  * context block; smem = the block's shared memory, this context being lane
  * `lane` of B */
-__device__ inline void pike_attach(pike_ctx_t &c, const sre_dev_pike_t &pk, uint32_t *base, uint32_t stride,
+__device__ __forceinline__ void pike_attach(pike_ctx_t &c, const sre_dev_pike_t &pk, uint32_t *base, uint32_t stride,
                                    uint32_t *smem, int parts, uint32_t lane, uint32_t B)
 {
     const pike_layout_t L = pike_layout(pk.len, pk.nslots, pk.max_slots, pk.max_threads, pk.stack_cap);
-    c.h = &c.hdr;
+    uint32_t *const smem0 = smem;
     c.base = base;
     c.stride = stride;
     c.max_slots = pk.max_slots;
@@ -262,14 +265,19 @@ __device__ inline void pike_attach(pike_ctx_t &c, const sre_dev_pike_t &pk, uint
     if (parts & SM_CAP) {
         c.capp = smem + lane;
         c.cstride = B;
+        smem += (size_t) 2 * pk.max_slots * B;
     } else {
         c.capp = base + (size_t) L.o_cap * stride;
         c.cstride = stride;
     }
+    /* the scalar state is indexed dynamically (head[l] ...): as a local
+     * variable it would live in local memory, so it is always shared */
+    smem += (smem - smem0) & 1;
+    c.h = reinterpret_cast<pike_hdr_t *>(smem) + lane;
 }
 
 /* batch layout: contexts 32g .. 32g+31 share one interleaved block */
-__device__ inline uint32_t *batch_base(const sre_dev_pike_t &pk, uint8_t *scratch, size_t tid, uint32_t stride)
+__device__ __forceinline__ uint32_t *batch_base(const sre_dev_pike_t &pk, uint8_t *scratch, size_t tid, uint32_t stride)
 {
     if (stride == 1) {
         return reinterpret_cast<uint32_t *>(scratch + tid * pk.ctx_stride);
@@ -277,30 +285,30 @@ __device__ inline uint32_t *batch_base(const sre_dev_pike_t &pk, uint8_t *scratc
     return reinterpret_cast<uint32_t *>(scratch + (tid >> 5) * (32 * pk.ctx_stride)) + (tid & 31);
 }
 
-__device__ inline void pike_hdr_store(const sre_dev_pike_t &pk, pike_ctx_t &c)
+__device__ __forceinline__ void pike_hdr_store(const sre_dev_pike_t &pk, pike_ctx_t &c)
 {
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(&c.hdr);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(c.h);
     const uint32_t o = c.o_hdr;
     for (uint32_t i = 0; i < (sizeof(pike_hdr_t) + 3) / 4; i++) {
         c.W(o + i) = src[i];
     }
 }
 
-__device__ inline void pike_hdr_load(const sre_dev_pike_t &pk, pike_ctx_t &c)
+__device__ __forceinline__ void pike_hdr_load(const sre_dev_pike_t &pk, pike_ctx_t &c)
 {
-    uint32_t *dst = reinterpret_cast<uint32_t *>(&c.hdr);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(c.h);
     const uint32_t o = c.o_hdr;
     for (uint32_t i = 0; i < (sizeof(pike_hdr_t) + 3) / 4; i++) {
         dst[i] = c.W(o + i);
     }
 }
 
-__device__ inline bool isword(uint32_t c)
+__device__ __forceinline__ bool isword(uint32_t c)
 {
     return (c - '0' < 10u) || ((c | 0x20) - 'a' < 26u) || c == '_';
 }
 
-__device__ inline bool in_ranges(const sre_dev_pike_t &pk, const sre_dev_inst_t &in, uint32_t b)
+__device__ __forceinline__ bool in_ranges(const sre_dev_pike_t &pk, const sre_dev_inst_t &in, uint32_t b)
 {
     const uint8_t *r = pk.ranges + 2 * (size_t) in.v;
     for (uint32_t j = 0; j < in.nranges; j++) {
@@ -311,7 +319,7 @@ __device__ inline bool in_ranges(const sre_dev_pike_t &pk, const sre_dev_inst_t 
     return false;
 }
 
-__device__ inline bool consumes(const sre_dev_pike_t &pk, const sre_dev_inst_t &in, uint32_t b)
+__device__ __forceinline__ bool consumes(const sre_dev_pike_t &pk, const sre_dev_inst_t &in, uint32_t b)
 {
     switch (in.opcode) {
     case OP_CHAR:  return in.ch == b;
@@ -323,7 +331,7 @@ __device__ inline bool consumes(const sre_dev_pike_t &pk, const sre_dev_inst_t &
 }
 
 /* fresh context for a new stream / line */
-__device__ inline void pike_reset(pike_ctx_t &c, bool first_time)
+__device__ __forceinline__ void pike_reset(pike_ctx_t &c, bool first_time)
 {
     pike_hdr_t *h = c.h;
     if (first_time) {
@@ -348,7 +356,7 @@ __device__ inline void pike_reset(pike_ctx_t &c, bool first_time)
     h->error = 0;
 }
 
-__device__ inline void list_clear(pike_ctx_t &c, int l)
+__device__ __forceinline__ void list_clear(pike_ctx_t &c, int l)
 {
     pike_hdr_t *h = c.h;
     if (h->head[l] >= 0) {
@@ -360,7 +368,7 @@ __device__ inline void list_clear(pike_ctx_t &c, int l)
 }
 
 /* working capture <- thread t's slots (everything else is -1 already) */
-__device__ inline void cap_load(const sre_dev_pike_t &pk, pike_ctx_t &c, int32_t t, uint32_t *base_out,
+__device__ __forceinline__ void cap_load(const sre_dev_pike_t &pk, pike_ctx_t &c, int32_t t, uint32_t *base_out,
                                 uint32_t *cnt_out)
 {
     const uint32_t r = pk.pc_regex[c.t_pc(t)], base = pk.slot_ofs[r];
@@ -373,7 +381,7 @@ __device__ inline void cap_load(const sre_dev_pike_t &pk, pike_ctx_t &c, int32_t
     *cnt_out = cnt;
 }
 
-__device__ inline void cap_clear(pike_ctx_t &c, uint32_t base, uint32_t cnt)
+__device__ __forceinline__ void cap_clear(pike_ctx_t &c, uint32_t base, uint32_t cnt)
 {
     /* add_thread may have moved the (then all -1) window to another regex */
     c.cap_base = base;
@@ -383,7 +391,7 @@ __device__ inline void cap_clear(pike_ctx_t &c, uint32_t base, uint32_t cnt)
 }
 
 /* slot g of thread t's full capture vector */
-__device__ inline int64_t thread_slot(const sre_dev_pike_t &pk, const pike_ctx_t &c, int32_t t, uint32_t g)
+__device__ __forceinline__ int64_t thread_slot(const sre_dev_pike_t &pk, const pike_ctx_t &c, int32_t t, uint32_t g)
 {
     const uint32_t r = pk.pc_regex[c.t_pc(t)], base = pk.slot_ofs[r];
     if (g < base || g >= pk.slot_ofs[r + 1]) {
@@ -394,6 +402,44 @@ __device__ inline int64_t thread_slot(const sre_dev_pike_t &pk, const pike_ctx_t
 
 /* a temporary list used by assertion_hold */
 struct tmp_list_t { int32_t head, tail, count; };
+
+/* take a thread record, park it on pc and append it to list l (or *tmp);
+ * the caller fills its capture.  -1: pool exhausted */
+__device__ __forceinline__ int32_t thread_append(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, tmp_list_t *tmp,
+    int32_t pc, uint32_t seen_word)
+{
+    pike_hdr_t *h = c.h;
+    int32_t t;
+    if (h->free_head >= 0) {
+        t = h->free_head;
+        h->free_head = c.t_next(t);
+    } else if (h->pool_used < (int32_t) pk.max_threads) {
+        t = h->pool_used++;
+    } else {
+        return -1;
+    }
+    c.t_pc(t) = pc;
+    c.t_sw(t) = seen_word;
+    c.t_next(t) = -1;
+    if (l >= 0) {
+        if (h->head[l] < 0) {
+            h->head[l] = t;
+        } else {
+            c.t_next(h->tail[l]) = t;
+        }
+        h->tail[l] = t;
+        h->count[l]++;
+    } else {
+        if (tmp->head < 0) {
+            tmp->head = t;
+        } else {
+            c.t_next(tmp->tail) = t;
+        }
+        tmp->tail = t;
+        tmp->count++;
+    }
+    return t;
+}
 
 /*
  * add_thread (sre_vm_pike.c:756-942).  Appends to list `l` (0/1) or, when
@@ -412,7 +458,7 @@ struct tmp_list_t { int32_t head, tail, count; };
  */
 enum { NB_END = -2, NB_UNKNOWN = -1 };
 
-__device__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, tmp_list_t *tmp,
+__device__ __forceinline__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, tmp_list_t *tmp,
     int32_t pc0, int64_t pos, const uint8_t *buffer, bool want_done, int nb)
 {
     pike_hdr_t *h = c.h;
@@ -450,11 +496,38 @@ __device__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, t
                 continue;
 
             case OP_SPLIT:
-                if (pc == 0 && pk.nleading && nb != NB_UNKNOWN
-                    && (nb == NB_END || !((pk.leadset[nb >> 5] >> (nb & 31)) & 1)))
-                {
-                    pc = in.y;          /* only the ".*?" thread can go on */
-                    continue;
+                if (pc == 0 && pk.nleading && nb != NB_UNKNOWN) {
+                    if (nb == NB_END || !((pk.leadset[nb >> 5] >> (nb & 31)) & 1)) {
+                        pc = in.y;      /* only the ".*?" thread can go on */
+                        continue;
+                    }
+                    if (pk.start_ofs) {
+                        /* the precomputed start closure for this byte; the
+                         * working capture is all -1 here (pc 0 is only reached
+                         * from the start and from the ".*?" thread) */
+                        const uint32_t e1 = pk.start_ofs[nb + 1];
+                        for (uint32_t e = pk.start_ofs[nb]; e < e1; e++) {
+                            const sre_dev_start_t se = pk.start_ent[e];
+                            if (c.tag_test(se.pc, tag)) {
+                                continue;
+                            }
+                            c.tag_set(se.pc, tag);
+                            const int32_t t = thread_append(pk, c, l, tmp, se.pc, 0);
+                            if (t < 0) {
+                                return SRE_K_ERROR;
+                            }
+                            const uint32_t r = pk.pc_regex[se.pc];
+                            const uint32_t cnt = pk.slot_ofs[r + 1] - pk.slot_ofs[r];
+                            for (uint32_t i = 0; i < cnt; i++) {
+                                c.set_t_cap(t, i, -1);
+                            }
+                            for (uint32_t k = 0; k < se.nsl; k++) {
+                                c.set_t_cap(t, se.sl[k], h->processed_bytes + pos);
+                            }
+                        }
+                        pc = in.y;
+                        continue;
+                    }
                 }
                 if (sp >= (int) pk.stack_cap) {
                     return SRE_K_ERROR;
@@ -529,42 +602,15 @@ __device__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, t
             }
 
             if (add) {
-                int32_t t;
-                if (h->free_head >= 0) {
-                    t = h->free_head;
-                    h->free_head = c.t_next(t);
-                } else if (h->pool_used < (int32_t) pk.max_threads) {
-                    t = h->pool_used++;
-                } else {
+                const int32_t t = thread_append(pk, c, l, tmp, pc, seen_word);
+                if (t < 0) {
                     return SRE_K_ERROR;
                 }
-                c.t_pc(t) = pc;
-                c.t_sw(t) = seen_word;
-                c.t_next(t) = -1;
-                {
-                    /* only the owning regex's slots can be set (see header) */
-                    const uint32_t r = pk.pc_regex[pc], base = pk.slot_ofs[r];
-                    const uint32_t cnt = pk.slot_ofs[r + 1] - base;
-                    for (uint32_t i = 0; i < cnt; i++) {
-                        c.set_t_cap(t, i, c.cap(base + i));
-                    }
-                }
-                if (l >= 0) {
-                    if (h->head[l] < 0) {
-                        h->head[l] = t;
-                    } else {
-                        c.t_next(h->tail[l]) = t;
-                    }
-                    h->tail[l] = t;
-                    h->count[l]++;
-                } else {
-                    if (tmp->head < 0) {
-                        tmp->head = t;
-                    } else {
-                        c.t_next(tmp->tail) = t;
-                    }
-                    tmp->tail = t;
-                    tmp->count++;
+                /* only the owning regex's slots can be set (see header) */
+                const uint32_t r = pk.pc_regex[pc], base = pk.slot_ofs[r];
+                const uint32_t cnt = pk.slot_ofs[r + 1] - base;
+                for (uint32_t i = 0; i < cnt; i++) {
+                    c.set_t_cap(t, i, c.cap(base + i));
                 }
             }
             break;
@@ -573,7 +619,7 @@ __device__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, t
     return SRE_K_OK;
 }
 
-__device__ inline int64_t find_first_byte(const sre_dev_pike_t &pk, const uint8_t *buf, int64_t pos,
+__device__ __forceinline__ int64_t find_first_byte(const sre_dev_pike_t &pk, const uint8_t *buf, int64_t pos,
     int64_t last)
 {
     if (pk.leading_byte != -1) {
@@ -595,7 +641,7 @@ __device__ inline int64_t find_first_byte(const sre_dev_pike_t &pk, const uint8_
 }
 
 /* prepare_matched_captures, :945-989.  complete: whole slice + -1 fill */
-__device__ inline int prepare_matched(const sre_dev_pike_t &pk, pike_ctx_t &c, int64_t *ovector,
+__device__ __forceinline__ int prepare_matched(const sre_dev_pike_t &pk, pike_ctx_t &c, int64_t *ovector,
     uint32_t ovec_slots, bool complete)
 {
     const int32_t id = c.h->matched_id;
@@ -619,7 +665,7 @@ __device__ inline int prepare_matched(const sre_dev_pike_t &pk, pike_ctx_t &c, i
  * One sre_vm_pike_exec call (:148-689).  ovector: caller's vector
  * (ovec_slots entries).  *pending_set: 1 when h->pending holds a pending match.
  */
-__device__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t *input, int64_t size,
+__device__ __forceinline__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t *input, int64_t size,
     bool eof, int64_t *ovector, uint32_t ovec_slots, int *pending_set, int64_t start_pos = 0)
 {
     pike_hdr_t *h = c.h;
@@ -935,8 +981,9 @@ k_pike_lines_all(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64
 
 __global__ void k_pike_ctx_init(sre_dev_pike_t pk, uint8_t *ctx)
 {
+    extern __shared__ uint32_t smem_ctx[];
     pike_ctx_t c;
-    pike_attach(c, pk, reinterpret_cast<uint32_t *>(ctx), 1, nullptr, 0, 0, 1);
+    pike_attach(c, pk, reinterpret_cast<uint32_t *>(ctx), 1, smem_ctx, 0, 0, 1);
     c.tag_open(0);
     c.tag_open(1);
     pike_reset(c, true);
@@ -1047,7 +1094,7 @@ cudaError_t sre_launch_pike_ctx_init(const sre_dev_pike_t &pk, uint8_t *ctx, cud
     if (launches) {
         ++*launches;
     }
-    k_pike_ctx_init<<<1, 1, 0, stream>>>(pk, ctx);
+    k_pike_ctx_init<<<1, 1, pike_smem_words(pk, 0, 1) * 4, stream>>>(pk, ctx);
     return cudaGetLastError();
 }
 
