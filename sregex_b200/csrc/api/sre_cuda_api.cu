@@ -757,20 +757,21 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
      * line, the offset after which no earlier-started thread is alive, where
      * the Pike search may begin.
      */
+    /* per-line workspace: gate | start hint | packed line list | its count */
+    const size_t half = (nlines * 4 + 255) & ~(size_t) 255;
+    if (cp->line_ws_bytes < 3 * half + 256) {
+        cudaFree(cp->line_ws);
+        cp->line_ws = nullptr;
+        cp->line_ws_bytes = 0;
+        CUDA_TRY(cudaMalloc(&cp->line_ws, 3 * half + 256));
+        cp->line_ws_bytes = 3 * half + 256;
+    }
     const bool aligned = dev_offsets == nullptr && (reinterpret_cast<uintptr_t>(dev_buf) & 15) == 0
                          && (pitch & 15) == 0 && linelen <= pitch && linelen < (1ull << 31);
     const bool tiled_hint = cp->has_dfa && cp->dfa.h256 != nullptr && aligned;
     if (tiled_hint || (cp->has_dfa && cp->dfa.hcls != nullptr)) {
-        const size_t need = ((nlines * 4 + 255) & ~(size_t) 255) * 2;
-        if (cp->line_ws_bytes < need) {
-            cudaFree(cp->line_ws);
-            cp->line_ws = nullptr;
-            cp->line_ws_bytes = 0;
-            CUDA_TRY(cudaMalloc(&cp->line_ws, need));
-            cp->line_ws_bytes = need;
-        }
         int32_t *gate = reinterpret_cast<int32_t *>(cp->line_ws);
-        int32_t *hint = reinterpret_cast<int32_t *>(cp->line_ws + need / 2);
+        int32_t *hint = reinterpret_cast<int32_t *>(cp->line_ws + half);
         cudaError_t e = tiled_hint
             ? sre_launch_dfa_lines_hint(cp->dfa, dev_buf, nlines, pitch, linelen, gate, hint, st, &launches)
             : sre_launch_dfa_generic_hint(cp->dfa, dev_buf, dev_offsets, nlines, pitch, linelen, gate, hint, st,
@@ -788,18 +789,39 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
     }
 
     cudaError_t err;
+    /* pack the selected lines; the rows of the others are final right away
+     * (rc from the gate, ovector all -1 = all 0xff bytes) */
+    sre_line_list_t lines = { nullptr, nullptr };
+    if (dev_select != nullptr) {
+        if (nlines > 0xffffffffull) {
+            return fail("too many lines for one call");
+        }
+        uint32_t *list = reinterpret_cast<uint32_t *>(cp->line_ws + 2 * half);
+        uint32_t *count = reinterpret_cast<uint32_t *>(cp->line_ws + 3 * half);
+        CUDA_TRY(cudaMemsetAsync(count, 0, 4, st));
+        if (dev_ovec != nullptr && ovec_slots != 0) {
+            CUDA_TRY(cudaMemsetAsync(dev_ovec, 0xff, nlines * ovec_slots * sizeof(int64_t), st));
+        }
+        err = sre_launch_pike_compact(dev_select, nlines, dev_rc, list, count, st, &launches);
+        if (err != cudaSuccess) {
+            count_launches(launches);
+            return fail("compaction kernel launch failed: %s", cudaGetErrorString(err));
+        }
+        lines.list = list;
+        lines.count = count;
+    }
     const size_t nctx = cp->pike_nctx < nlines ? cp->pike_nctx : nlines;
     if (sre_pike_small_applicable(cp->pike) && linelen < (1ull << 31) && !g_pike_general_only) {
         /* shared-memory kernel first; the general kernel re-runs what it gave up on */
-        err = sre_launch_pike_small(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, dev_select, start,
+        err = sre_launch_pike_small(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
                                     dev_rc, dev_ovec, (uint32_t) ovec_slots, st, &launches);
         if (err == cudaSuccess) {
-            err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, dev_select,
+            err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines,
                                         start, dev_rc, dev_ovec, (uint32_t) ovec_slots, cp->pike_scratch,
                                         nctx < 16384 ? nctx : 16384, 1, st, &launches);
         }
     } else {
-        err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, dev_select, start,
+        err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
                                     dev_rc, dev_ovec, (uint32_t) ovec_slots, cp->pike_scratch, nctx, 0, st,
                                     &launches);
     }

@@ -130,12 +130,24 @@ cudaError_t sre_launch_dfa_generic_hint(const sre_dev_dfa_t &dfa, const uint8_t 
     const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen, int32_t *rc,
     int32_t *hint, cudaStream_t stream, int *launches);
 
-/* Pike VM over lines; select may be NULL (all) or an rc array (run where ==0);
+/* the lines a Pike pass works on: list[0 .. *count) (device memory), or every
+ * line 0 .. nlines-1 when list == NULL */
+struct sre_line_list_t {
+    const uint32_t *list;
+    const uint32_t *count;
+};
+
+/* list <- lines with select[line] == SRE_K_OK, in no particular order; the
+ * other lines get rc[line] = select[line].  *count must be 0 beforehand.       */
+cudaError_t sre_launch_pike_compact(const int32_t *select, size_t nlines, int32_t *rc,
+    uint32_t *list, uint32_t *count, cudaStream_t stream, int *launches);
+
+/* Pike VM over the listed lines (rows of rc / ovec not listed are not touched);
  * start may be NULL or per-line offsets at which the search may begin          */
 size_t sre_pike_concurrency(size_t nlines);
 cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
     const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen,
-    const int32_t *select, const int32_t *start, int32_t *rc, int64_t *ovec,
+    sre_line_list_t lines, const int32_t *start, int32_t *rc, int64_t *ovec,
     uint32_t ovec_slots, uint8_t *scratch, size_t nctx, int retry_only, cudaStream_t stream,
     int *launches);
 
@@ -144,7 +156,7 @@ cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
 bool sre_pike_small_applicable(const sre_dev_pike_t &pk);
 cudaError_t sre_launch_pike_small(const sre_dev_pike_t &pk, const uint8_t *buf,
     const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen,
-    const int32_t *select, const int32_t *start, int32_t *rc, int64_t *ovec,
+    sre_line_list_t lines, const int32_t *start, int32_t *rc, int64_t *ovec,
     uint32_t ovec_slots, cudaStream_t stream, int *launches);
 
 /* all non-overlapping matches per line (post-match continuation, global scan)  */

@@ -885,9 +885,36 @@ __device__ __forceinline__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c
 
 /* ---- kernels --------------------------------------------------------------- */
 
+/* the lines the gate let through, packed, so that every lane of the Pike
+ * kernels has work (warp-aggregated append; the order is irrelevant) */
+__global__ void __launch_bounds__(256)
+k_pike_compact(const int32_t *__restrict__ select, size_t nlines, int32_t *__restrict__ rc,
+               uint32_t *__restrict__ list, uint32_t *__restrict__ count)
+{
+    const size_t nthreads = (size_t) gridDim.x * blockDim.x;
+    const size_t rounds = (nlines + nthreads - 1) / nthreads;
+    const uint32_t lane = threadIdx.x & 31;
+    for (size_t r = 0; r < rounds; r++) {
+        const size_t line = r * nthreads + (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+        const int32_t sel = line < nlines ? select[line] : SRE_K_DECLINED;
+        const bool take = line < nlines && sel == SRE_K_OK;
+        const uint32_t m = __ballot_sync(0xffffffffu, take);
+        uint32_t base = 0;
+        if (lane == 0 && m) {
+            base = atomicAdd(count, (uint32_t) __popc(m));
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (take) {
+            list[base + __popc(m & ((1u << lane) - 1))] = (uint32_t) line;
+        } else if (line < nlines) {
+            rc[line] = sel;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128)
 k_pike_lines(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
-             size_t nlines, size_t pitch, size_t linelen, const int32_t *__restrict__ select,
+             size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines,
              const int32_t *__restrict__ start_hint, int32_t *__restrict__ rc, int64_t *__restrict__ ovec,
              uint32_t ovec_slots, uint8_t *scratch, size_t nctx, int retry_only, uint32_t stride,
              int parts)
@@ -901,18 +928,12 @@ k_pike_lines(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
     pike_attach(c, pk, batch_base(pk, scratch, tid, stride), stride, smem_ctx, parts, threadIdx.x, blockDim.x);
     bool first = true;
 
-    for (size_t line = tid; line < nlines; line += nctx) {
+    const size_t nwork = lines.list ? (size_t) *lines.count : nlines;
+    for (size_t k = tid; k < nwork; k += nctx) {
+        const size_t line = lines.list ? (size_t) lines.list[k] : k;
         int64_t *ov = ovec + line * ovec_slots;
-        if (retry_only) {
-            /* second pass after k_pike_small: only the lines it gave up on */
-            if (rc[line] != SRE_K_RETRY) {
-                continue;
-            }
-        } else if (select && select[line] != SRE_K_OK) {
-            rc[line] = select[line];
-            for (uint32_t i = 0; i < ovec_slots; i++) {
-                ov[i] = -1;
-            }
+        /* second pass after k_pike_small: only the lines it gave up on */
+        if (retry_only && rc[line] != SRE_K_RETRY) {
             continue;
         }
         const size_t start = offsets ? (size_t) offsets[line] : line * pitch;
@@ -1050,8 +1071,25 @@ size_t sre_pike_ctx_bytes(uint32_t len, uint32_t nslots, uint32_t max_slots, uin
     return pike_layout(len, nslots, max_slots, nthreads, stack_cap).words * 4;
 }
 
+cudaError_t sre_launch_pike_compact(const int32_t *select, size_t nlines, int32_t *rc, uint32_t *list,
+    uint32_t *count, cudaStream_t stream, int *launches)
+{
+    if (nlines == 0) {
+        return cudaSuccess;
+    }
+    if (launches) {
+        ++*launches;
+    }
+    size_t grid = (nlines + 255) / 256;
+    if (grid > 148 * 8) {
+        grid = 148 * 8;
+    }
+    k_pike_compact<<<(unsigned) grid, 256, 0, stream>>>(select, nlines, rc, list, count);
+    return cudaGetLastError();
+}
+
 cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
-    const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen, const int32_t *select,
+    const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines,
     const int32_t *start, int32_t *rc, int64_t *ovec, uint32_t ovec_slots, uint8_t *scratch, size_t nctx,
     int retry_only, cudaStream_t stream, int *launches)
 {
@@ -1064,7 +1102,7 @@ cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
     const unsigned grid = (unsigned) ((nctx + 127) / 128);
     size_t smem;
     const int parts = smem_parts(pk, 128, true, &smem);
-    k_pike_lines<<<grid, 128, smem, stream>>>(pk, buf, offsets, nlines, pitch, linelen, select, start, rc,
+    k_pike_lines<<<grid, 128, smem, stream>>>(pk, buf, offsets, nlines, pitch, linelen, lines, start, rc,
                                              ovec, ovec_slots, scratch, nctx, retry_only, batch_stride(),
                                              parts);
     return cudaGetLastError();

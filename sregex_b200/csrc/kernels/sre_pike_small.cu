@@ -286,7 +286,7 @@ struct small_ctx_t {
 template <int K, int M, int H, int DS, bool C16>
 __global__ void __launch_bounds__(BLOCK)
 k_pike_small(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
-             size_t nlines, size_t pitch, size_t linelen, const int32_t *__restrict__ select,
+             size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines,
              const int32_t *__restrict__ start_hint, int32_t *__restrict__ rc, int64_t *__restrict__ ovec,
              uint32_t ovec_slots)
 {
@@ -298,15 +298,10 @@ k_pike_small(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
     c.nslots = pk.nslots;
 
     const size_t nthreads = (size_t) gridDim.x * blockDim.x;
-    for (size_t line = (size_t) blockIdx.x * blockDim.x + threadIdx.x; line < nlines; line += nthreads) {
+    const size_t nwork = lines.list ? (size_t) *lines.count : nlines;
+    for (size_t k = (size_t) blockIdx.x * blockDim.x + threadIdx.x; k < nwork; k += nthreads) {
+        const size_t line = lines.list ? (size_t) lines.list[k] : k;
         int64_t *ov = ovec + line * ovec_slots;
-        if (select && select[line] != SRE_K_OK) {
-            rc[line] = select[line];
-            for (uint32_t i = 0; i < ovec_slots; i++) {
-                ov[i] = -1;
-            }
-            continue;
-        }
         const size_t start = offsets ? (size_t) offsets[line] : line * pitch;
         const size_t end = offsets ? (size_t) offsets[line + 1] : start + linelen;
         const uint8_t *input = buf + start;
@@ -455,7 +450,7 @@ bool sre_pike_small_applicable(const sre_dev_pike_t &pk)
 }
 
 cudaError_t sre_launch_pike_small(const sre_dev_pike_t &pk, const uint8_t *buf, const int64_t *offsets,
-    size_t nlines, size_t pitch, size_t linelen, const int32_t *select, const int32_t *start, int32_t *rc,
+    size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines, const int32_t *start, int32_t *rc,
     int64_t *ovec, uint32_t ovec_slots, cudaStream_t stream, int *launches)
 {
     if (nlines == 0) {
@@ -479,7 +474,7 @@ cudaError_t sre_launch_pike_small(const sre_dev_pike_t &pk, const uint8_t *buf, 
         if (per_sm > 32) per_sm = 32;                                                               \
         const size_t cap = (size_t) sms * (per_sm ? per_sm : 1);                                    \
         if (grid > cap) grid = cap;                                                                 \
-        kern<<<(unsigned) grid, BLOCK, smem, stream>>>(pk, buf, offsets, nlines, pitch, linelen, select, \
+        kern<<<(unsigned) grid, BLOCK, smem, stream>>>(pk, buf, offsets, nlines, pitch, linelen, lines,  \
                                                         start, rc, ovec, ovec_slots);               \
     } while (0)
 #define SRE_SMALL(KK, MM, HH, DD)                                                                   \
