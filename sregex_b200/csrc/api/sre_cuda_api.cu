@@ -252,6 +252,166 @@ static bool build_start_closure(const sre_program_t *prog, const std::vector<uin
     return true;
 }
 
+/*
+ * Closure tables for k_pike_table: for every instruction P a thread can be
+ * parked on (and P == len for the start), what add_thread(P + 1) appends when
+ * run on its own -- the walk of sre_vm_pike.c:756-942 (x before y, revisited-
+ * SPLIT rule :770-786, SAVE undone on the way back) with `\A` and `^` decided
+ * by the look-behind context: 0 = at offset 0, 1 = after a newline, 2 =
+ * elsewhere.  Entry = parked pc | (slots SAVEd on the path) << 16.
+ */
+struct closure_table_t {
+    std::vector<uint32_t> ent;
+    std::vector<uint16_t> ofs;
+    std::vector<uint32_t> accept;
+    std::vector<uint8_t>  kind;
+    bool                  ctx_dep = false;
+};
+
+static void closure_walk(const sre_program_t *prog, int32_t pc0, int ctx, std::vector<uint32_t> &out)
+{
+    struct item_t { int32_t kind, pc; uint32_t mask; };
+    std::vector<item_t> stack;
+    std::vector<uint8_t> seen(prog->len, 0);
+    uint32_t mask = 0;
+    stack.push_back({ -1, pc0, 0 });
+    while (!stack.empty()) {
+        const item_t it = stack.back();
+        stack.pop_back();
+        if (it.kind >= 0) {
+            mask = it.mask;
+            continue;
+        }
+        int32_t pc = it.pc;
+        for (;;) {
+            if (pc < 0 || (uint32_t) pc >= prog->len) {
+                break;
+            }
+            const sre_instruction_t &in = prog->insts[pc];
+            if (seen[pc]) {
+                if (in.opcode == SRE_OPCODE_SPLIT && !seen[in.y]) {
+                    pc = in.y;
+                    continue;
+                }
+                break;
+            }
+            seen[pc] = 1;
+            if (in.opcode == SRE_OPCODE_JMP) {
+                pc = in.x;
+                continue;
+            }
+            if (in.opcode == SRE_OPCODE_SPLIT) {
+                stack.push_back({ -1, in.y, 0 });
+                pc = in.x;
+                continue;
+            }
+            if (in.opcode == SRE_OPCODE_SAVE) {
+                stack.push_back({ 0, 0, mask });
+                mask |= 1u << in.v;
+                pc++;
+                continue;
+            }
+            if (in.opcode == SRE_OPCODE_ASSERT && in.v == SRE_REGEX_ASSERT_BIG_A) {
+                if (ctx != 0) {
+                    break;
+                }
+                pc++;
+                continue;
+            }
+            if (in.opcode == SRE_OPCODE_ASSERT && in.v == SRE_REGEX_ASSERT_CARET) {
+                if (ctx == 2) {
+                    break;
+                }
+                pc++;
+                continue;
+            }
+            out.push_back((uint32_t) pc | (mask << 16));    /* parked */
+            break;
+        }
+    }
+}
+
+static bool build_closure_table(const sre_program_t *prog, closure_table_t &T)
+{
+    const uint32_t len = prog->len;
+    if (prog->nregexes != 1 || len > 64 || 2 * (prog->multi_ncaps[0] + 1) > 16) {
+        return false;
+    }
+    T.kind.assign(len, 0);
+    T.accept.assign((size_t) len * 8, 0);
+    for (uint32_t pc = 0; pc < len; pc++) {
+        const sre_instruction_t &in = prog->insts[pc];
+        switch (in.opcode) {
+        case SRE_OPCODE_MATCH:
+            T.kind[pc] = 1;
+            break;
+        case SRE_OPCODE_ASSERT:
+            switch (in.v) {
+            case SRE_REGEX_ASSERT_SMALL_Z: T.kind[pc] = 2; break;
+            case SRE_REGEX_ASSERT_DOLLAR:  T.kind[pc] = 3; break;
+            case SRE_REGEX_ASSERT_BIG_B:   T.kind[pc] = 4; break;
+            case SRE_REGEX_ASSERT_SMALL_B: T.kind[pc] = 5; break;
+            default: T.ctx_dep = true; break;
+            }
+            break;
+        case SRE_OPCODE_CHAR:
+        case SRE_OPCODE_ANY:
+        case SRE_OPCODE_IN:
+        case SRE_OPCODE_NOTIN:
+            for (uint32_t b = 0; b < 256; b++) {
+                bool hit;
+                if (in.opcode == SRE_OPCODE_CHAR) {
+                    hit = (in.ch == b);
+                } else if (in.opcode == SRE_OPCODE_ANY) {
+                    hit = true;
+                } else {
+                    hit = false;
+                    for (uint32_t j = 0; j < in.nranges; j++) {
+                        const sre_vm_range_t &r = prog->ranges[in.v + j];
+                        hit |= (b >= r.from && b <= r.to);
+                    }
+                    if (in.opcode == SRE_OPCODE_NOTIN) {
+                        hit = !hit;
+                    }
+                }
+                if (hit) {
+                    T.accept[(size_t) pc * 8 + (b >> 5)] |= 1u << (b & 31);
+                }
+            }
+            break;
+        default:
+            break;
+        }
+    }
+    T.ofs.assign((size_t) 3 * (len + 2), 0);
+    const int nctx = T.ctx_dep ? 3 : 1;
+    for (int ctx = 0; ctx < nctx; ctx++) {
+        for (uint32_t P = 0; P <= len; P++) {
+            T.ofs[(size_t) ctx * (len + 2) + P] = (uint16_t) T.ent.size();
+            if (P == len) {
+                closure_walk(prog, 0, ctx, T.ent);
+                continue;
+            }
+            const uint8_t op = prog->insts[P].opcode;
+            const bool parks = op == SRE_OPCODE_CHAR || op == SRE_OPCODE_ANY || op == SRE_OPCODE_IN
+                               || op == SRE_OPCODE_NOTIN || (op == SRE_OPCODE_ASSERT && T.kind[P] >= 2);
+            if (parks) {
+                closure_walk(prog, (int32_t) P + 1, ctx, T.ent);
+            }
+            if (T.ent.size() > 4096) {
+                return false;
+            }
+        }
+        T.ofs[(size_t) ctx * (len + 2) + len + 1] = (uint16_t) T.ent.size();
+    }
+    for (int ctx = nctx; ctx < 3; ctx++) {
+        for (uint32_t P = 0; P <= len + 1; P++) {
+            T.ofs[(size_t) ctx * (len + 2) + P] = T.ofs[P];
+        }
+    }
+    return !T.ent.empty();
+}
+
 int upload(sre_cuda_program_t *cp)
 {
     const sre_program_t *prog = cp->prog;
@@ -373,6 +533,15 @@ int upload(sre_cuda_program_t *cp)
         }
     }
     const size_t o_pcre = b.add(pc_regex.data(), pc_regex.size() * 2);
+    closure_table_t clo;
+    const bool has_clo = build_closure_table(prog, clo);
+    size_t o_cent = 0, o_cofs = 0, o_cacc = 0, o_ckind = 0;
+    if (has_clo) {
+        o_cent = b.add(clo.ent.data(), clo.ent.size() * 4);
+        o_cofs = b.add(clo.ofs.data(), clo.ofs.size() * 2);
+        o_cacc = b.add(clo.accept.data(), clo.accept.size() * 4);
+        o_ckind = b.add(clo.kind.data(), clo.kind.size());
+    }
     std::vector<uint32_t> start_ofs;
     std::vector<sre_dev_start_t> start_ent;
     const bool has_start = build_start_closure(prog, pc_regex, slot_ofs, start_ofs, start_ent);
@@ -455,6 +624,12 @@ int upload(sre_cuda_program_t *cp)
     pk.leading = reinterpret_cast<const int32_t *>(base + o_leading);
     pk.slot_ofs = reinterpret_cast<const uint32_t *>(base + o_slots);
     pk.pc_regex = reinterpret_cast<const uint16_t *>(base + o_pcre);
+    pk.clo_ent = has_clo ? reinterpret_cast<const uint32_t *>(base + o_cent) : nullptr;
+    pk.clo_ofs = has_clo ? reinterpret_cast<const uint16_t *>(base + o_cofs) : nullptr;
+    pk.clo_accept = has_clo ? reinterpret_cast<const uint32_t *>(base + o_cacc) : nullptr;
+    pk.clo_kind = has_clo ? base + o_ckind : nullptr;
+    pk.clo_nent = has_clo ? (uint32_t) clo.ent.size() : 0;
+    pk.clo_ctx_dep = clo.ctx_dep ? 1 : 0;
     pk.start_ofs = has_start ? reinterpret_cast<const uint32_t *>(base + o_sofs) : nullptr;
     pk.start_ent = has_start ? reinterpret_cast<const sre_dev_start_t *>(base + o_sent) : nullptr;
     pk.max_slots = max_slots;
@@ -811,7 +986,16 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         lines.count = count;
     }
     const size_t nctx = cp->pike_nctx < nlines ? cp->pike_nctx : nlines;
-    if (sre_pike_small_applicable(cp->pike) && linelen < (1ull << 31) && !g_pike_general_only) {
+    if (sre_pike_table_applicable(cp->pike) && linelen < (1ull << 31) && g_pike_general_only == 0) {
+        /* closure-table kernel first; the general kernel re-runs what it gave up on */
+        err = sre_launch_pike_table(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
+                                    dev_rc, dev_ovec, (uint32_t) ovec_slots, st, &launches);
+        if (err == cudaSuccess) {
+            err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines,
+                                        start, dev_rc, dev_ovec, (uint32_t) ovec_slots, cp->pike_scratch,
+                                        nctx < 16384 ? nctx : 16384, 1, st, &launches);
+        }
+    } else if (sre_pike_small_applicable(cp->pike) && linelen < (1ull << 31) && g_pike_general_only != 1) {
         /* shared-memory kernel first; the general kernel re-runs what it gave up on */
         err = sre_launch_pike_small(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
                                     dev_rc, dev_ovec, (uint32_t) ovec_slots, st, &launches);

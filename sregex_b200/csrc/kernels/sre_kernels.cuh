@@ -83,6 +83,17 @@ struct sre_dev_pike_t {
      * priority order; NULL when closure(pc 0) meets an assertion             */
     const uint32_t          *start_ofs;
     const sre_dev_start_t   *start_ent;
+    /* closure tables of k_pike_table (small single-regex programs; clo_nent
+     * == 0: none).  Closure (ctx, P) = clo_ent[clo_ofs[ctx * (len + 2) + P] ..
+     * clo_ofs[ctx * (len + 2) + P + 1]): what add_thread(P + 1) appends (P ==
+     * len: add_thread(0)) at offset 0 (ctx 0), after a newline (1), elsewhere
+     * (2); entry = pc | slots SAVEd on the path << 16                        */
+    const uint32_t          *clo_ent;
+    const uint16_t          *clo_ofs;
+    const uint32_t          *clo_accept;    /* [len][8] bytes an instruction takes */
+    const uint8_t           *clo_kind;      /* [len] what a parked instruction is  */
+    uint32_t                 clo_nent;
+    uint32_t                 clo_ctx_dep;   /* program has \A or ^             */
 };
 
 /* launchers (sre_kernels.cu); all asynchronous on `stream` ------------------ */
@@ -155,6 +166,14 @@ cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
  * capacities get rc = SRE_K_RETRY (re-run them with retry_only = 1 above)      */
 bool sre_pike_small_applicable(const sre_dev_pike_t &pk);
 cudaError_t sre_launch_pike_small(const sre_dev_pike_t &pk, const uint8_t *buf,
+    const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen,
+    sre_line_list_t lines, const int32_t *start, int32_t *rc, int64_t *ovec,
+    uint32_t ovec_slots, cudaStream_t stream, int *launches);
+
+/* closure-table Pike for small single-regex programs (sre_pike_table.cu);
+ * same contract as sre_launch_pike_small                                       */
+bool sre_pike_table_applicable(const sre_dev_pike_t &pk);
+cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf,
     const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen,
     sre_line_list_t lines, const int32_t *start, int32_t *rc, int64_t *ovec,
     uint32_t ovec_slots, cudaStream_t stream, int *launches);

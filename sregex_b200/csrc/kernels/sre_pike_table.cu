@@ -1,0 +1,398 @@
+/*
+ * sre_pike_table.cu -- the Pike VM for small single-regex programs, driven by
+ * precomputed closure tables (the batch Pike+captures kernel of choice).
+ *
+ * Same results as sre_vm_pike_exec (reference sre_vm_pike.c:148-689) for a
+ * fresh context and one buffer with eof = 1, like sre_pike_small.cu, but
+ * add_thread (:756-942) is not walked at run time.  For every instruction P a
+ * thread can be parked on, the host lists what add_thread(P + 1) appends when
+ * run on its own (sre_cuda_api.cu: build_closure_table -- same walk order,
+ * same revisited-SPLIT rule :770-786): the parked instructions in priority
+ * order, each with the set of capture slots SAVEd on the way, once per
+ * look-behind context (at offset 0 / after a newline / elsewhere, which is all
+ * `\A` and `^` can see).  At run time a closure is "for each entry: skip it if
+ * its instruction is already marked in this step, else mark it and append a
+ * thread whose captures are the parent's with the SAVEd slots set to the
+ * position".  That is the list the walk would have produced: a walk stops at
+ * an instruction marked earlier in the step, and everything below such an
+ * instruction was appended (and marked) by the walk that marked it.  The idea
+ * is the reference JIT's (sre_vm_thompson_x64.dasc:323-394 precomputes the
+ * closure of every consuming instruction), extended with captures.
+ *
+ * On top of that, as in sre_pike.cu: a thread parked on a consuming instruction
+ * that cannot take the next byte is not appended (the next step would drop it
+ * without effect), dedup marks are two 64-bit masks (this step / the previous
+ * one, the only two epochs the reference compares against), and the first-byte
+ * prefilter is left to the start hint of k_dfa_lines_hint.
+ *
+ * A line that needs more than K threads per list or H pending look-ahead
+ * closures is reported SRE_K_RETRY and re-run by k_pike_lines.
+ */
+#include "sre_kernels.cuh"
+
+namespace {
+
+constexpr int TB = 128;     /* threads (= contexts) per block */
+constexpr int K = 8;        /* threads per list               */
+constexpr int H = 4;        /* pending look-ahead closures    */
+enum { NB_END = -2 };
+
+__device__ __forceinline__ bool isword(uint32_t c)
+{
+    return (c - '0' < 10u) || ((c | 0x20) - 'a' < 26u) || c == '_';
+}
+
+/* one lane's context: words at sm[e * TB] */
+template <bool C16>
+struct lane_t {
+    int32_t    *sm;
+    int         ncw;                /* words per capture vector */
+    uint64_t    m_cur, m_prev;
+    /* sections (word offsets), set from ncw */
+    int         MAT, TMP, L0PC, L0CAP, L1PC, L1CAP, HSPC, HSCAP;
+
+    __device__ __forceinline__ static int words(int ncw) { return 2 * ncw + 2 * K * (1 + ncw) + H * (1 + ncw); }
+    __device__ __forceinline__ void layout(int n)
+    {
+        ncw = n;
+        MAT = 0;
+        TMP = MAT + n;
+        L0PC = TMP + n;
+        L0CAP = L0PC + K;
+        L1PC = L0CAP + K * n;
+        L1CAP = L1PC + K;
+        HSPC = L1CAP + K * n;
+        HSCAP = HSPC + H;
+    }
+    __device__ __forceinline__ int32_t &w(int e) { return sm[e * TB]; }
+
+    __device__ __forceinline__ bool tagged(uint32_t pc, bool hold) const
+    {
+        return ((hold ? m_prev : m_cur) >> pc) & 1;
+    }
+    __device__ __forceinline__ void tag(uint32_t pc, bool hold)
+    {
+        const uint64_t bit = 1ull << pc;
+        if (hold) {
+            m_prev |= bit;
+            m_cur &= ~bit;
+        } else {
+            m_cur |= bit;
+            m_prev &= ~bit;
+        }
+    }
+    /* dst vector <- src vector (src < 0: all -1) with the slots of `mask` set to pos */
+    __device__ __forceinline__ void derive(int dst, int src, uint32_t mask, int32_t pos)
+    {
+        if (C16) {
+            const uint32_t p16 = (uint32_t) pos & 0xffff;
+            for (int j = 0; j < ncw; j++) {
+                uint32_t v = src < 0 ? 0xffffffffu : (uint32_t) w(src + j);
+                const uint32_t m = (mask >> (2 * j)) & 3;
+                if (m & 1) {
+                    v = (v & 0xffff0000u) | p16;
+                }
+                if (m & 2) {
+                    v = (v & 0xffffu) | (p16 << 16);
+                }
+                w(dst + j) = (int32_t) v;
+            }
+        } else {
+            for (int j = 0; j < ncw; j++) {
+                const int32_t v = src < 0 ? -1 : w(src + j);
+                w(dst + j) = ((mask >> j) & 1) ? pos : v;
+            }
+        }
+    }
+    __device__ __forceinline__ int32_t cap_get(int sec, uint32_t slot)
+    {
+        if (!C16) {
+            return w(sec + slot);
+        }
+        const int32_t word = w(sec + (slot >> 1));
+        return (slot & 1) ? (word >> 16) : (int32_t) (int16_t) (word & 0xffff);
+    }
+};
+
+/* what a parked instruction is (block table s_kind) */
+enum { KD_CONS = 0, KD_MATCH = 1, KD_SMALL_Z = 2, KD_DOLLAR = 3, KD_BIG_B = 4, KD_SMALL_B = 5 };
+
+template <bool C16>
+__global__ void __launch_bounds__(TB)
+k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
+             size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines,
+             const int32_t *__restrict__ start_hint, int32_t *__restrict__ rc, int64_t *__restrict__ ovec,
+             uint32_t ovec_slots)
+{
+    extern __shared__ int32_t smem_words[];
+    /* block tables: entries | closure offsets | accept sets | kinds, then the lanes */
+    const uint32_t len = pk.len, nofs = 3 * (len + 2);
+    uint32_t *s_ent = reinterpret_cast<uint32_t *>(smem_words);
+    uint32_t *s_accept = s_ent + pk.clo_nent;
+    uint16_t *s_ofs = reinterpret_cast<uint16_t *>(s_accept + len * 8);
+    uint8_t *s_kind = reinterpret_cast<uint8_t *>(s_ofs + nofs);
+    const uint32_t table_words = pk.clo_nent + len * 8 + (nofs * 2 + len + 3) / 4;
+    for (uint32_t i = threadIdx.x; i < pk.clo_nent; i += TB) {
+        s_ent[i] = pk.clo_ent[i];
+    }
+    for (uint32_t i = threadIdx.x; i < len * 8; i += TB) {
+        s_accept[i] = pk.clo_accept[i];
+    }
+    for (uint32_t i = threadIdx.x; i < nofs; i += TB) {
+        s_ofs[i] = pk.clo_ofs[i];
+    }
+    for (uint32_t i = threadIdx.x; i < len; i += TB) {
+        s_kind[i] = pk.clo_kind[i];
+    }
+    __syncthreads();
+
+    lane_t<C16> c;
+    c.sm = smem_words + table_words + threadIdx.x;
+    c.layout(C16 ? (int) (pk.nslots + 1) >> 1 : (int) pk.nslots);
+    const int ncw = c.ncw;
+    const bool ctx_dep = pk.clo_ctx_dep != 0;
+
+    const size_t nthreads = (size_t) gridDim.x * blockDim.x;
+    const size_t nwork = lines.list ? (size_t) *lines.count : nlines;
+    for (size_t k = (size_t) blockIdx.x * blockDim.x + threadIdx.x; k < nwork; k += nthreads) {
+        const size_t line = lines.list ? (size_t) lines.list[k] : k;
+        int64_t *ov = ovec + line * ovec_slots;
+        const size_t start = offsets ? (size_t) offsets[line] : line * pitch;
+        const size_t end = offsets ? (size_t) offsets[line + 1] : start + linelen;
+        const uint8_t *input = buf + start;
+        const int32_t size = (int32_t) (end - start);
+        int32_t sp = start_hint ? start_hint[line] : 0;
+
+        c.m_cur = c.m_prev = 0;
+        bool overflow = false, matched = false;
+        int32_t matched_id = 0;
+        int cur = 0, ncl = 0, nnl = 0, hs = 0;
+
+        /*
+         * closure P appended to the array (pcsec, capsec) of capacity capn at
+         * count n: 0 ok, 1 MATCH reached (want_done), -1 out of room
+         */
+        auto append_closure = [&](uint32_t P, int32_t pos, int parent, int pcsec, int capsec, int capn, int &n,
+                                  bool hold, bool want_done) -> int {
+            uint32_t v = 0;
+            uint32_t prev = 0;
+            if (pos > 0) {
+                prev = input[pos - 1];
+                v = ctx_dep ? (prev == '\n' ? 1u : 2u) : 0u;
+            }
+            const int nb = pos < size ? (int) input[pos] : NB_END;
+            const uint32_t e1 = s_ofs[v * (len + 2) + P + 1];
+            for (uint32_t e = s_ofs[v * (len + 2) + P]; e < e1; e++) {
+                const uint32_t ent = s_ent[e];
+                const uint32_t fpc = ent & 0xff, mask = ent >> 16;
+                const uint32_t kind = s_kind[fpc];
+                if (kind == KD_CONS
+                    && (nb == NB_END || !((s_accept[fpc * 8 + ((uint32_t) nb >> 5)] >> (nb & 31)) & 1)))
+                {
+                    continue;               /* would be dropped by the next step */
+                }
+                if (c.tagged(fpc, hold)) {
+                    continue;
+                }
+                c.tag(fpc, hold);
+                if (kind == KD_MATCH && want_done) {
+                    c.derive(c.MAT, parent, mask, pos);
+                    matched_id = (int32_t) pk.insts[fpc].v;
+                    return 1;
+                }
+                if (n >= capn) {
+                    return -1;
+                }
+                const uint32_t sw = (kind >= KD_BIG_B && pos > 0 && isword(prev)) ? 1u : 0u;
+                c.w(pcsec + n) = (int32_t) (fpc | (sw << 16));
+                c.derive(capsec + n * ncw, parent, mask, pos);
+                n++;
+            }
+            return 0;
+        };
+
+        /* first_buf: the initial closure at the start offset, :202-216 */
+        if (append_closure(len, sp, -1, c.L0PC, c.L0CAP, K, ncl, false, false) < 0) {
+            overflow = true;
+        }
+
+        for (; !overflow && sp <= size; sp++) {
+            if (ncl == 0) {
+                break;
+            }
+            c.m_prev = c.m_cur;         /* ctx->tag++ */
+            c.m_cur = 0;
+            const bool at_end = (sp == size);
+            const uint32_t byte = at_end ? 0 : input[sp];
+            const bool cur_word = !at_end && isword(byte);
+            const int cl_pc = cur ? c.L1PC : c.L0PC, cl_cap = cur ? c.L1CAP : c.L0CAP;
+            const int nl_pc = cur ? c.L0PC : c.L1PC, nl_cap = cur ? c.L0CAP : c.L1CAP;
+            int i = 0;
+
+            for (;;) {
+                /* next thread in priority order: pending look-ahead closures first */
+                int tp, tc;
+                if (hs > 0) {
+                    hs--;
+                    tp = c.HSPC + hs;
+                    /* its closure may be appended over this very record */
+                    for (int j = 0; j < ncw; j++) {
+                        c.w(c.TMP + j) = c.w(c.HSCAP + hs * ncw + j);
+                    }
+                    tc = c.TMP;
+                } else if (i < ncl) {
+                    tp = cl_pc + i;
+                    tc = cl_cap + i * ncw;
+                    i++;
+                } else {
+                    break;
+                }
+                const int32_t rec = c.w(tp);
+                const uint32_t pc = rec & 0xffff;
+                const bool t_sw = (rec >> 16) & 1;
+                const uint32_t kind = s_kind[pc];
+                bool got_match = false;
+
+                if (kind >= KD_SMALL_Z) {                   /* :449-528 */
+                    bool hold;
+                    switch (kind) {
+                    case KD_SMALL_Z: hold = at_end; break;
+                    case KD_DOLLAR:  hold = at_end || byte == '\n'; break;
+                    case KD_BIG_B:   hold = (t_sw == cur_word); break;
+                    default:         hold = (t_sw != cur_word); break;
+                    }
+                    if (hold) {
+                        /* closure with tag - 1, prepended to clist: append it
+                         * above the LIFO top, then reverse that segment */
+                        int top = hs;
+                        if (append_closure(pc, sp, tc, c.HSPC, c.HSCAP, H, top, true, false) < 0) {
+                            overflow = true;
+                            break;
+                        }
+                        for (int lo = hs, hi = top - 1; lo < hi; lo++, hi--) {
+                            int32_t tmp = c.w(c.HSPC + lo);
+                            c.w(c.HSPC + lo) = c.w(c.HSPC + hi);
+                            c.w(c.HSPC + hi) = tmp;
+                            for (int j = 0; j < ncw; j++) {
+                                tmp = c.w(c.HSCAP + lo * ncw + j);
+                                c.w(c.HSCAP + lo * ncw + j) = c.w(c.HSCAP + hi * ncw + j);
+                                c.w(c.HSCAP + hi * ncw + j) = tmp;
+                            }
+                        }
+                        hs = top;
+                    }
+                } else if (kind == KD_MATCH) {              /* :530-553 */
+                    for (int j = 0; j < ncw; j++) {
+                        c.w(c.MAT + j) = c.w(tc + j);
+                    }
+                    matched_id = (int32_t) pk.insts[pc].v;
+                    got_match = true;
+                } else if (!at_end && ((s_accept[pc * 8 + (byte >> 5)] >> (byte & 31)) & 1)) {
+                    const int r = append_closure(pc, sp + 1, tc, nl_pc, nl_cap, K, nnl, false, true);
+                    if (r < 0) {
+                        overflow = true;
+                        break;
+                    }
+                    got_match = (r == 1);
+                }
+
+                if (got_match) {        /* cut every lower-priority thread */
+                    matched = true;
+                    hs = 0;
+                    break;
+                }
+            }
+
+            cur ^= 1;                   /* step_done: swap lists */
+            ncl = nnl;
+            nnl = 0;
+            hs = 0;
+            if (at_end) {
+                break;
+            }
+        }
+
+        if (overflow) {
+            rc[line] = SRE_K_RETRY;
+            continue;
+        }
+        if (matched) {
+            rc[line] = matched_id;
+            for (uint32_t i = 0; i < ovec_slots; i++) {
+                ov[i] = i < pk.nslots ? (int64_t) c.cap_get(c.MAT, i) : -1;
+            }
+        } else {
+            rc[line] = SRE_K_DECLINED;
+            for (uint32_t i = 0; i < ovec_slots; i++) {
+                ov[i] = -1;
+            }
+        }
+    }
+}
+
+size_t table_smem_bytes(const sre_dev_pike_t &pk, bool c16)
+{
+    const uint32_t len = pk.len, nofs = 3 * (len + 2);
+    const size_t table_words = pk.clo_nent + len * 8 + (nofs * 2 + len + 3) / 4;
+    const int ncw = c16 ? (int) (pk.nslots + 1) >> 1 : (int) pk.nslots;
+    const size_t lane_words = 2 * ncw + 2 * K * (1 + ncw) + H * (1 + ncw);
+    return (table_words + lane_words * TB) * 4;
+}
+
+}  // namespace
+
+bool sre_pike_table_applicable(const sre_dev_pike_t &pk)
+{
+    return pk.clo_nent != 0 && pk.nregexes == 1 && pk.len <= 64 && pk.nslots <= 16
+           && table_smem_bytes(pk, false) <= 200 * 1024;
+}
+
+cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, const int64_t *offsets,
+    size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines, const int32_t *start, int32_t *rc,
+    int64_t *ovec, uint32_t ovec_slots, cudaStream_t stream, int *launches)
+{
+    if (nlines == 0) {
+        return cudaSuccess;
+    }
+    if (launches) {
+        ++*launches;
+    }
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+            sms = 148;
+        }
+    }
+    /* 16-bit capture offsets when every line is shorter than 32 KB */
+    const bool c16 = offsets == nullptr && linelen < 32767;
+    const size_t smem = table_smem_bytes(pk, c16);
+    size_t per_sm = (227 * 1024) / (smem + 1024);
+    if (per_sm > 16) {
+        per_sm = 16;
+    }
+    size_t grid = (nlines + TB - 1) / TB;
+    const size_t cap = (size_t) sms * (per_sm ? per_sm : 1);
+    if (grid > cap) {
+        grid = cap;
+    }
+    static bool opted[2] = { false, false };
+    if (!opted[c16]) {
+        cudaError_t e = c16
+            ? cudaFuncSetAttribute(k_pike_table<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+            : cudaFuncSetAttribute(k_pike_table<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) {
+            return e;
+        }
+        opted[c16] = true;
+    }
+    if (c16) {
+        k_pike_table<true><<<(unsigned) grid, TB, smem, stream>>>(pk, buf, offsets, nlines, pitch, linelen, lines,
+                                                                 start, rc, ovec, ovec_slots);
+    } else {
+        k_pike_table<false><<<(unsigned) grid, TB, smem, stream>>>(pk, buf, offsets, nlines, pitch, linelen, lines,
+                                                                  start, rc, ovec, ovec_slots);
+    }
+    return cudaGetLastError();
+}

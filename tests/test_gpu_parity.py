@@ -100,15 +100,16 @@ def test_batch_golden_dfa_skip(golden, cu):
     _golden_batch(golden, cu, cu.ENGINE_DFA_SKIP)
 
 
-@pytest.mark.parametrize("general_only", [0, 1])
+@pytest.mark.parametrize("general_only", [0, 1, 2])
 def test_batch_golden_pike_with_start_hint(golden, cu, general_only):
     """every golden block as a 1-line batch through sre_cuda_pike_exec_lines with
     its internal gate + start-hint pass: rc and the whole ovector.  Once through
-    the shared-memory tier (k_pike_small, with k_pike_lines re-running what it
-    gives up on) and once through the general kernel alone."""
+    the closure-table tier (k_pike_table, with k_pike_lines re-running what it
+    gives up on), once through the general kernel alone (1) and once through the
+    walking shared-memory tier (k_pike_small, 2)."""
     cu.lib().L.sre_cuda_set_pike_general_only(general_only)
     try:
-        _golden_pike_batch(golden, cu, step=1 if general_only == 0 else 2)
+        _golden_pike_batch(golden, cu, step=1 if general_only != 1 else 2)
     finally:
         cu.lib().L.sre_cuda_set_pike_general_only(0)
 
