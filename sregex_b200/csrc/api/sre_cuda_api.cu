@@ -253,22 +253,25 @@ static bool build_start_closure(const sre_program_t *prog, const std::vector<uin
 }
 
 /*
- * Closure tables for k_pike_table: for every instruction P a thread can be
- * parked on (and P == len for the start), what add_thread(P + 1) appends when
+ * Closure tables for k_pike_table: for every instruction a thread can be
+ * parked on (numbered 0 .. npark-1 in pc order; P == npark is the start), what
+ * add_thread(pc + 1) appends when
  * run on its own -- the walk of sre_vm_pike.c:756-942 (x before y, revisited-
  * SPLIT rule :770-786, SAVE undone on the way back) with `\A` and `^` decided
  * by the look-behind context: 0 = at offset 0, 1 = after a newline, 2 =
- * elsewhere.  Entry = parked pc | (slots SAVEd on the path) << 16.
+ * elsewhere.  Entry = parked number | (slots SAVEd on the path) << 16.
  */
 struct closure_table_t {
     std::vector<uint32_t> ent;
     std::vector<uint16_t> ofs;
     std::vector<uint32_t> accept;
     std::vector<uint8_t>  kind;
+    uint32_t              npark = 0;
     bool                  ctx_dep = false;
 };
 
-static void closure_walk(const sre_program_t *prog, int32_t pc0, int ctx, std::vector<uint32_t> &out)
+static void closure_walk(const sre_program_t *prog, const std::vector<int32_t> &park, int32_t pc0, int ctx,
+    std::vector<uint32_t> &out)
 {
     struct item_t { int32_t kind, pc; uint32_t mask; };
     std::vector<item_t> stack;
@@ -325,7 +328,7 @@ static void closure_walk(const sre_program_t *prog, int32_t pc0, int ctx, std::v
                 pc++;
                 continue;
             }
-            out.push_back((uint32_t) pc | (mask << 16));    /* parked */
+            out.push_back((uint32_t) park[pc] | (mask << 16));      /* parked */
             break;
         }
     }
@@ -334,79 +337,93 @@ static void closure_walk(const sre_program_t *prog, int32_t pc0, int ctx, std::v
 static bool build_closure_table(const sre_program_t *prog, closure_table_t &T)
 {
     const uint32_t len = prog->len;
-    if (prog->nregexes != 1 || len > 64 || 2 * (prog->multi_ncaps[0] + 1) > 16) {
+    if (prog->nregexes != 1 || 2 * (prog->multi_ncaps[0] + 1) > 16) {
         return false;
     }
-    T.kind.assign(len, 0);
-    T.accept.assign((size_t) len * 8, 0);
+    /* number the instructions that can hold a thread */
+    std::vector<int32_t> park(len, -1), park_pc;
     for (uint32_t pc = 0; pc < len; pc++) {
         const sre_instruction_t &in = prog->insts[pc];
+        uint8_t kind = 0xff;
         switch (in.opcode) {
-        case SRE_OPCODE_MATCH:
-            T.kind[pc] = 1;
-            break;
-        case SRE_OPCODE_ASSERT:
-            switch (in.v) {
-            case SRE_REGEX_ASSERT_SMALL_Z: T.kind[pc] = 2; break;
-            case SRE_REGEX_ASSERT_DOLLAR:  T.kind[pc] = 3; break;
-            case SRE_REGEX_ASSERT_BIG_B:   T.kind[pc] = 4; break;
-            case SRE_REGEX_ASSERT_SMALL_B: T.kind[pc] = 5; break;
-            default: T.ctx_dep = true; break;
-            }
-            break;
         case SRE_OPCODE_CHAR:
         case SRE_OPCODE_ANY:
         case SRE_OPCODE_IN:
         case SRE_OPCODE_NOTIN:
-            for (uint32_t b = 0; b < 256; b++) {
-                bool hit;
-                if (in.opcode == SRE_OPCODE_CHAR) {
-                    hit = (in.ch == b);
-                } else if (in.opcode == SRE_OPCODE_ANY) {
-                    hit = true;
-                } else {
-                    hit = false;
-                    for (uint32_t j = 0; j < in.nranges; j++) {
-                        const sre_vm_range_t &r = prog->ranges[in.v + j];
-                        hit |= (b >= r.from && b <= r.to);
-                    }
-                    if (in.opcode == SRE_OPCODE_NOTIN) {
-                        hit = !hit;
-                    }
-                }
-                if (hit) {
-                    T.accept[(size_t) pc * 8 + (b >> 5)] |= 1u << (b & 31);
-                }
+            kind = 0;
+            break;
+        case SRE_OPCODE_MATCH:
+            kind = 1;
+            break;
+        case SRE_OPCODE_ASSERT:
+            switch (in.v) {
+            case SRE_REGEX_ASSERT_SMALL_Z: kind = 2; break;
+            case SRE_REGEX_ASSERT_DOLLAR:  kind = 3; break;
+            case SRE_REGEX_ASSERT_BIG_B:   kind = 4; break;
+            case SRE_REGEX_ASSERT_SMALL_B: kind = 5; break;
+            default: T.ctx_dep = true; break;
             }
             break;
         default:
             break;
         }
+        if (kind != 0xff) {
+            park[pc] = (int32_t) park_pc.size();
+            park_pc.push_back((int32_t) pc);
+            T.kind.push_back(kind);
+        }
     }
-    T.ofs.assign((size_t) 3 * (len + 2), 0);
+    const uint32_t np = (uint32_t) park_pc.size();
+    if (np == 0 || np > 64) {
+        return false;
+    }
+    T.npark = np;
+    T.accept.assign((size_t) np * 8, 0);
+    for (uint32_t P = 0; P < np; P++) {
+        const sre_instruction_t &in = prog->insts[park_pc[P]];
+        if (T.kind[P] != 0) {
+            continue;
+        }
+        for (uint32_t b = 0; b < 256; b++) {
+            bool hit;
+            if (in.opcode == SRE_OPCODE_CHAR) {
+                hit = (in.ch == b);
+            } else if (in.opcode == SRE_OPCODE_ANY) {
+                hit = true;
+            } else {
+                hit = false;
+                for (uint32_t j = 0; j < in.nranges; j++) {
+                    const sre_vm_range_t &r = prog->ranges[in.v + j];
+                    hit |= (b >= r.from && b <= r.to);
+                }
+                if (in.opcode == SRE_OPCODE_NOTIN) {
+                    hit = !hit;
+                }
+            }
+            if (hit) {
+                T.accept[(size_t) P * 8 + (b >> 5)] |= 1u << (b & 31);
+            }
+        }
+    }
+    T.ofs.assign((size_t) 3 * (np + 2), 0);
     const int nctx = T.ctx_dep ? 3 : 1;
     for (int ctx = 0; ctx < nctx; ctx++) {
-        for (uint32_t P = 0; P <= len; P++) {
-            T.ofs[(size_t) ctx * (len + 2) + P] = (uint16_t) T.ent.size();
-            if (P == len) {
-                closure_walk(prog, 0, ctx, T.ent);
-                continue;
+        for (uint32_t P = 0; P <= np; P++) {
+            T.ofs[(size_t) ctx * (np + 2) + P] = (uint16_t) T.ent.size();
+            if (P == np) {
+                closure_walk(prog, park, 0, ctx, T.ent);
+            } else if (T.kind[P] != 1) {            /* nothing follows a MATCH */
+                closure_walk(prog, park, park_pc[P] + 1, ctx, T.ent);
             }
-            const uint8_t op = prog->insts[P].opcode;
-            const bool parks = op == SRE_OPCODE_CHAR || op == SRE_OPCODE_ANY || op == SRE_OPCODE_IN
-                               || op == SRE_OPCODE_NOTIN || (op == SRE_OPCODE_ASSERT && T.kind[P] >= 2);
-            if (parks) {
-                closure_walk(prog, (int32_t) P + 1, ctx, T.ent);
-            }
-            if (T.ent.size() > 4096) {
+            if (T.ent.size() > 8192) {
                 return false;
             }
         }
-        T.ofs[(size_t) ctx * (len + 2) + len + 1] = (uint16_t) T.ent.size();
+        T.ofs[(size_t) ctx * (np + 2) + np + 1] = (uint16_t) T.ent.size();
     }
     for (int ctx = nctx; ctx < 3; ctx++) {
-        for (uint32_t P = 0; P <= len + 1; P++) {
-            T.ofs[(size_t) ctx * (len + 2) + P] = T.ofs[P];
+        for (uint32_t P = 0; P <= np + 1; P++) {
+            T.ofs[(size_t) ctx * (np + 2) + P] = T.ofs[P];
         }
     }
     return !T.ent.empty();
@@ -629,6 +646,7 @@ int upload(sre_cuda_program_t *cp)
     pk.clo_accept = has_clo ? reinterpret_cast<const uint32_t *>(base + o_cacc) : nullptr;
     pk.clo_kind = has_clo ? base + o_ckind : nullptr;
     pk.clo_nent = has_clo ? (uint32_t) clo.ent.size() : 0;
+    pk.clo_npark = has_clo ? clo.npark : 0;
     pk.clo_ctx_dep = clo.ctx_dep ? 1 : 0;
     pk.start_ofs = has_start ? reinterpret_cast<const uint32_t *>(base + o_sofs) : nullptr;
     pk.start_ent = has_start ? reinterpret_cast<const sre_dev_start_t *>(base + o_sent) : nullptr;
@@ -988,8 +1006,21 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
     const size_t nctx = cp->pike_nctx < nlines ? cp->pike_nctx : nlines;
     if (sre_pike_table_applicable(cp->pike) && linelen < (1ull << 31) && g_pike_general_only == 0) {
         /* closure-table kernel first; the general kernel re-runs what it gave up on */
+        static int k1 = -1, h1 = 2;
+        if (k1 < 0) {           /* SRE_PIKE_TABLE_K="K,H": first-pass capacities (tuning) */
+            const char *e = getenv("SRE_PIKE_TABLE_K");
+            k1 = 5;
+            if (e) {
+                sscanf(e, "%d,%d", &k1, &h1);
+            }
+        }
+        /* small lists first (more resident warps), then the lines that needed more */
         err = sre_launch_pike_table(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
-                                    dev_rc, dev_ovec, (uint32_t) ovec_slots, st, &launches);
+                                    dev_rc, dev_ovec, (uint32_t) ovec_slots, k1, h1, 0, st, &launches);
+        if (err == cudaSuccess && (k1 < 8 || h1 < 4)) {
+            err = sre_launch_pike_table(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
+                                        dev_rc, dev_ovec, (uint32_t) ovec_slots, 8, 4, 1, st, &launches);
+        }
         if (err == cudaSuccess) {
             err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines,
                                         start, dev_rc, dev_ovec, (uint32_t) ovec_slots, cp->pike_scratch,

@@ -84,15 +84,18 @@ struct sre_dev_pike_t {
     const uint32_t          *start_ofs;
     const sre_dev_start_t   *start_ent;
     /* closure tables of k_pike_table (small single-regex programs; clo_nent
-     * == 0: none).  Closure (ctx, P) = clo_ent[clo_ofs[ctx * (len + 2) + P] ..
-     * clo_ofs[ctx * (len + 2) + P + 1]): what add_thread(P + 1) appends (P ==
-     * len: add_thread(0)) at offset 0 (ctx 0), after a newline (1), elsewhere
-     * (2); entry = pc | slots SAVEd on the path << 16                        */
+     * == 0: none), over the clo_npark instructions a thread can be parked on,
+     * numbered in pc order.  Closure (ctx, P) = clo_ent[clo_ofs[ctx * (npark +
+     * 2) + P] .. clo_ofs[ctx * (npark + 2) + P + 1]): what add_thread(pc(P) +
+     * 1) appends (P == npark: add_thread(0)) at offset 0 (ctx 0), after a
+     * newline (1), elsewhere (2); entry = parked number | slots SAVEd on the
+     * path << 16                                                             */
     const uint32_t          *clo_ent;
     const uint16_t          *clo_ofs;
-    const uint32_t          *clo_accept;    /* [len][8] bytes an instruction takes */
-    const uint8_t           *clo_kind;      /* [len] what a parked instruction is  */
+    const uint32_t          *clo_accept;    /* [npark][8] bytes it takes           */
+    const uint8_t           *clo_kind;      /* [npark] what it is                  */
     uint32_t                 clo_nent;
+    uint32_t                 clo_npark;
     uint32_t                 clo_ctx_dep;   /* program has \A or ^             */
 };
 
@@ -171,12 +174,13 @@ cudaError_t sre_launch_pike_small(const sre_dev_pike_t &pk, const uint8_t *buf,
     uint32_t ovec_slots, cudaStream_t stream, int *launches);
 
 /* closure-table Pike for small single-regex programs (sre_pike_table.cu);
- * same contract as sre_launch_pike_small                                       */
+ * same contract as sre_launch_pike_small.  K threads per list, H pending
+ * look-ahead closures per context; retry_only: only lines with rc RETRY        */
 bool sre_pike_table_applicable(const sre_dev_pike_t &pk);
 cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf,
     const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen,
     sre_line_list_t lines, const int32_t *start, int32_t *rc, int64_t *ovec,
-    uint32_t ovec_slots, cudaStream_t stream, int *launches);
+    uint32_t ovec_slots, int K, int H, int retry_only, cudaStream_t stream, int *launches);
 
 /* all non-overlapping matches per line (post-match continuation, global scan)  */
 cudaError_t sre_launch_pike_lines_all(const sre_dev_pike_t &pk, const uint8_t *buf,

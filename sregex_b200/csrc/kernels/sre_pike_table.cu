@@ -4,8 +4,10 @@
  *
  * Same results as sre_vm_pike_exec (reference sre_vm_pike.c:148-689) for a
  * fresh context and one buffer with eof = 1, like sre_pike_small.cu, but
- * add_thread (:756-942) is not walked at run time.  For every instruction P a
- * thread can be parked on, the host lists what add_thread(P + 1) appends when
+ * add_thread (:756-942) is not walked at run time.  Instructions a thread can
+ * be parked on (consuming ones, look-ahead assertions, MATCH) are numbered
+ * 0 .. npark-1 (<= 64; SPLIT / JMP / SAVE and `\A` `^` never hold a thread), and
+ * everything below speaks of those numbers.  For every such instruction P, the host lists what add_thread(P + 1) appends when
  * run on its own (sre_cuda_api.cu: build_closure_table -- same walk order,
  * same revisited-SPLIT rule :770-786): the parked instructions in priority
  * order, each with the set of capture slots SAVEd on the way, once per
@@ -33,8 +35,6 @@
 namespace {
 
 constexpr int TB = 128;     /* threads (= contexts) per block */
-constexpr int K = 8;        /* threads per list               */
-constexpr int H = 4;        /* pending look-ahead closures    */
 enum { NB_END = -2 };
 
 __device__ __forceinline__ bool isword(uint32_t c)
@@ -47,14 +47,16 @@ template <bool C16>
 struct lane_t {
     int32_t    *sm;
     int         ncw;                /* words per capture vector */
+    int         K, H;               /* threads per list, pending look-ahead closures */
     uint64_t    m_cur, m_prev;
     /* sections (word offsets), set from ncw */
     int         MAT, TMP, L0PC, L0CAP, L1PC, L1CAP, HSPC, HSCAP;
 
-    __device__ __forceinline__ static int words(int ncw) { return 2 * ncw + 2 * K * (1 + ncw) + H * (1 + ncw); }
-    __device__ __forceinline__ void layout(int n)
+    __device__ __forceinline__ void layout(int n, int k, int h)
     {
         ncw = n;
+        K = k;
+        H = h;
         MAT = 0;
         TMP = MAT + n;
         L0PC = TMP + n;
@@ -122,11 +124,11 @@ __global__ void __launch_bounds__(TB)
 k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
              size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines,
              const int32_t *__restrict__ start_hint, int32_t *__restrict__ rc, int64_t *__restrict__ ovec,
-             uint32_t ovec_slots)
+             uint32_t ovec_slots, int K, int H, int retry_only)
 {
     extern __shared__ int32_t smem_words[];
     /* block tables: entries | closure offsets | accept sets | kinds, then the lanes */
-    const uint32_t len = pk.len, nofs = 3 * (len + 2);
+    const uint32_t len = pk.clo_npark, nofs = 3 * (len + 2);
     uint32_t *s_ent = reinterpret_cast<uint32_t *>(smem_words);
     uint32_t *s_accept = s_ent + pk.clo_nent;
     uint16_t *s_ofs = reinterpret_cast<uint16_t *>(s_accept + len * 8);
@@ -148,78 +150,109 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
 
     lane_t<C16> c;
     c.sm = smem_words + table_words + threadIdx.x;
-    c.layout(C16 ? (int) (pk.nslots + 1) >> 1 : (int) pk.nslots);
+    c.layout(C16 ? (int) (pk.nslots + 1) >> 1 : (int) pk.nslots, K, H);
     const int ncw = c.ncw;
     const bool ctx_dep = pk.clo_ctx_dep != 0;
 
     const size_t nthreads = (size_t) gridDim.x * blockDim.x;
     const size_t nwork = lines.list ? (size_t) *lines.count : nlines;
-    for (size_t k = (size_t) blockIdx.x * blockDim.x + threadIdx.x; k < nwork; k += nthreads) {
-        const size_t line = lines.list ? (size_t) lines.list[k] : k;
-        int64_t *ov = ovec + line * ovec_slots;
-        const size_t start = offsets ? (size_t) offsets[line] : line * pitch;
-        const size_t end = offsets ? (size_t) offsets[line + 1] : start + linelen;
-        const uint8_t *input = buf + start;
-        const int32_t size = (int32_t) (end - start);
-        int32_t sp = start_hint ? start_hint[line] : 0;
+    size_t k = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
 
-        c.m_cur = c.m_prev = 0;
-        bool overflow = false, matched = false;
-        int32_t matched_id = 0;
-        int cur = 0, ncl = 0, nnl = 0, hs = 0;
+    /* the line this lane is on */
+    size_t line = 0;
+    const uint8_t *input = buf;
+    int32_t size = 0, sp = 0, matched_id = 0;
+    bool active = false, overflow = false, matched = false;
+    int cur = 0, ncl = 0, nnl = 0, hs = 0;
 
-        /*
-         * closure P appended to the array (pcsec, capsec) of capacity capn at
-         * count n: 0 ok, 1 MATCH reached (want_done), -1 out of room
-         */
-        auto append_closure = [&](uint32_t P, int32_t pos, int parent, int pcsec, int capsec, int capn, int &n,
-                                  bool hold, bool want_done) -> int {
-            uint32_t v = 0;
-            uint32_t prev = 0;
-            if (pos > 0) {
-                prev = input[pos - 1];
-                v = ctx_dep ? (prev == '\n' ? 1u : 2u) : 0u;
+    /*
+     * closure P appended to the array (pcsec, capsec) of capacity capn at
+     * count n: 0 ok, 1 MATCH reached (want_done), -1 out of room
+     */
+    auto append_closure = [&](uint32_t P, int32_t pos, int parent, int pcsec, int capsec, int capn, int &n,
+                              bool hold, bool want_done) -> int {
+        uint32_t v = 0;
+        uint32_t prev = 0;
+        if (pos > 0) {
+            prev = input[pos - 1];
+            v = ctx_dep ? (prev == '\n' ? 1u : 2u) : 0u;
+        }
+        const int nb = pos < size ? (int) input[pos] : NB_END;
+        const uint32_t e1 = s_ofs[v * (len + 2) + P + 1];
+        for (uint32_t e = s_ofs[v * (len + 2) + P]; e < e1; e++) {
+            const uint32_t ent = s_ent[e];
+            const uint32_t fpc = ent & 0xff, mask = ent >> 16;
+            const uint32_t kind = s_kind[fpc];
+            if (kind == KD_CONS
+                && (nb == NB_END || !((s_accept[fpc * 8 + ((uint32_t) nb >> 5)] >> (nb & 31)) & 1)))
+            {
+                continue;               /* would be dropped by the next step */
             }
-            const int nb = pos < size ? (int) input[pos] : NB_END;
-            const uint32_t e1 = s_ofs[v * (len + 2) + P + 1];
-            for (uint32_t e = s_ofs[v * (len + 2) + P]; e < e1; e++) {
-                const uint32_t ent = s_ent[e];
-                const uint32_t fpc = ent & 0xff, mask = ent >> 16;
-                const uint32_t kind = s_kind[fpc];
-                if (kind == KD_CONS
-                    && (nb == NB_END || !((s_accept[fpc * 8 + ((uint32_t) nb >> 5)] >> (nb & 31)) & 1)))
-                {
-                    continue;               /* would be dropped by the next step */
-                }
-                if (c.tagged(fpc, hold)) {
-                    continue;
-                }
-                c.tag(fpc, hold);
-                if (kind == KD_MATCH && want_done) {
-                    c.derive(c.MAT, parent, mask, pos);
-                    matched_id = (int32_t) pk.insts[fpc].v;
-                    return 1;
-                }
-                if (n >= capn) {
-                    return -1;
-                }
-                const uint32_t sw = (kind >= KD_BIG_B && pos > 0 && isword(prev)) ? 1u : 0u;
-                c.w(pcsec + n) = (int32_t) (fpc | (sw << 16));
-                c.derive(capsec + n * ncw, parent, mask, pos);
-                n++;
+            if (c.tagged(fpc, hold)) {
+                continue;
             }
-            return 0;
-        };
+            c.tag(fpc, hold);
+            if (kind == KD_MATCH && want_done) {
+                c.derive(c.MAT, parent, mask, pos);
+                matched_id = 0;       /* one regex */
+                return 1;
+            }
+            if (n >= capn) {
+                return -1;
+            }
+            const uint32_t sw = (kind >= KD_BIG_B && pos > 0 && isword(prev)) ? 1u : 0u;
+            c.w(pcsec + n) = (int32_t) (fpc | (sw << 16));
+            c.derive(capsec + n * ncw, parent, mask, pos);
+            n++;
+        }
+        return 0;
+    };
 
-        /* first_buf: the initial closure at the start offset, :202-216 */
-        if (append_closure(len, sp, -1, c.L0PC, c.L0CAP, K, ncl, false, false) < 0) {
-            overflow = true;
+    /*
+     * One loop over (line, byte) pairs: a lane that finishes its line takes
+     * the next one at once instead of waiting for the longest line of the
+     * warp, so every turn is one byte step for every lane that has work left.
+     */
+    bool finished = false;
+    for (;;) {
+        /* the vote is also the point where the lanes of the warp line up
+         * again: without it they drift apart and run one after the other */
+        if (__all_sync(0xffffffffu, finished)) {
+            break;
+        }
+        if (finished) {
+            continue;
+        }
+        if (!active) {
+            if (k >= nwork) {
+                finished = true;
+                continue;
+            }
+            line = lines.list ? (size_t) lines.list[k] : k;
+            k += nthreads;
+            /* a later pass with larger lists: only what the previous one gave up on */
+            if (retry_only && rc[line] != SRE_K_RETRY) {
+                continue;
+            }
+            const size_t start = offsets ? (size_t) offsets[line] : line * pitch;
+            const size_t end = offsets ? (size_t) offsets[line + 1] : start + linelen;
+            input = buf + start;
+            size = (int32_t) (end - start);
+            sp = start_hint ? start_hint[line] : 0;
+            c.m_cur = c.m_prev = 0;
+            overflow = false;
+            matched = false;
+            matched_id = 0;
+            cur = 0; ncl = 0; nnl = 0; hs = 0;
+            active = true;
+            /* first_buf: the initial closure at the start offset, :202-216 */
+            if (append_closure(len, sp, -1, c.L0PC, c.L0CAP, c.K, ncl, false, false) < 0) {
+                overflow = true;
+            }
         }
 
-        for (; !overflow && sp <= size; sp++) {
-            if (ncl == 0) {
-                break;
-            }
+        bool done = overflow || sp > size || ncl == 0;
+        if (!done) {
             c.m_prev = c.m_cur;         /* ctx->tag++ */
             c.m_cur = 0;
             const bool at_end = (sp == size);
@@ -265,7 +298,7 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
                         /* closure with tag - 1, prepended to clist: append it
                          * above the LIFO top, then reverse that segment */
                         int top = hs;
-                        if (append_closure(pc, sp, tc, c.HSPC, c.HSCAP, H, top, true, false) < 0) {
+                        if (append_closure(pc, sp, tc, c.HSPC, c.HSCAP, c.H, top, true, false) < 0) {
                             overflow = true;
                             break;
                         }
@@ -285,10 +318,10 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
                     for (int j = 0; j < ncw; j++) {
                         c.w(c.MAT + j) = c.w(tc + j);
                     }
-                    matched_id = (int32_t) pk.insts[pc].v;
+                    matched_id = 0;
                     got_match = true;
                 } else if (!at_end && ((s_accept[pc * 8 + (byte >> 5)] >> (byte & 31)) & 1)) {
-                    const int r = append_closure(pc, sp + 1, tc, nl_pc, nl_cap, K, nnl, false, true);
+                    const int r = append_closure(pc, sp + 1, tc, nl_pc, nl_cap, c.K, nnl, false, true);
                     if (r < 0) {
                         overflow = true;
                         break;
@@ -307,32 +340,33 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
             ncl = nnl;
             nnl = 0;
             hs = 0;
-            if (at_end) {
-                break;
-            }
+            sp++;
+            done = overflow || at_end || ncl == 0;
         }
 
-        if (overflow) {
-            rc[line] = SRE_K_RETRY;
-            continue;
-        }
-        if (matched) {
-            rc[line] = matched_id;
-            for (uint32_t i = 0; i < ovec_slots; i++) {
-                ov[i] = i < pk.nslots ? (int64_t) c.cap_get(c.MAT, i) : -1;
+        if (done) {
+            int64_t *ov = ovec + line * ovec_slots;
+            if (overflow) {
+                rc[line] = SRE_K_RETRY;
+            } else if (matched) {
+                rc[line] = matched_id;
+                for (uint32_t i = 0; i < ovec_slots; i++) {
+                    ov[i] = i < pk.nslots ? (int64_t) c.cap_get(c.MAT, i) : -1;
+                }
+            } else {
+                rc[line] = SRE_K_DECLINED;
+                for (uint32_t i = 0; i < ovec_slots; i++) {
+                    ov[i] = -1;
+                }
             }
-        } else {
-            rc[line] = SRE_K_DECLINED;
-            for (uint32_t i = 0; i < ovec_slots; i++) {
-                ov[i] = -1;
-            }
+            active = false;
         }
     }
 }
 
-size_t table_smem_bytes(const sre_dev_pike_t &pk, bool c16)
+size_t table_smem_bytes(const sre_dev_pike_t &pk, bool c16, int K, int H)
 {
-    const uint32_t len = pk.len, nofs = 3 * (len + 2);
+    const uint32_t len = pk.clo_npark, nofs = 3 * (len + 2);
     const size_t table_words = pk.clo_nent + len * 8 + (nofs * 2 + len + 3) / 4;
     const int ncw = c16 ? (int) (pk.nslots + 1) >> 1 : (int) pk.nslots;
     const size_t lane_words = 2 * ncw + 2 * K * (1 + ncw) + H * (1 + ncw);
@@ -343,13 +377,13 @@ size_t table_smem_bytes(const sre_dev_pike_t &pk, bool c16)
 
 bool sre_pike_table_applicable(const sre_dev_pike_t &pk)
 {
-    return pk.clo_nent != 0 && pk.nregexes == 1 && pk.len <= 64 && pk.nslots <= 16
-           && table_smem_bytes(pk, false) <= 200 * 1024;
+    return pk.clo_nent != 0 && pk.nregexes == 1 && pk.clo_npark <= 64 && pk.nslots <= 16
+           && table_smem_bytes(pk, false, 8, 4) <= 200 * 1024;
 }
 
 cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, const int64_t *offsets,
     size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines, const int32_t *start, int32_t *rc,
-    int64_t *ovec, uint32_t ovec_slots, cudaStream_t stream, int *launches)
+    int64_t *ovec, uint32_t ovec_slots, int K, int H, int retry_only, cudaStream_t stream, int *launches)
 {
     if (nlines == 0) {
         return cudaSuccess;
@@ -367,7 +401,7 @@ cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, 
     }
     /* 16-bit capture offsets when every line is shorter than 32 KB */
     const bool c16 = offsets == nullptr && linelen < 32767;
-    const size_t smem = table_smem_bytes(pk, c16);
+    const size_t smem = table_smem_bytes(pk, c16, K, H);
     size_t per_sm = (227 * 1024) / (smem + 1024);
     if (per_sm > 16) {
         per_sm = 16;
@@ -389,10 +423,10 @@ cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, 
     }
     if (c16) {
         k_pike_table<true><<<(unsigned) grid, TB, smem, stream>>>(pk, buf, offsets, nlines, pitch, linelen, lines,
-                                                                 start, rc, ovec, ovec_slots);
+                                                                 start, rc, ovec, ovec_slots, K, H, retry_only);
     } else {
         k_pike_table<false><<<(unsigned) grid, TB, smem, stream>>>(pk, buf, offsets, nlines, pitch, linelen, lines,
-                                                                  start, rc, ovec, ovec_slots);
+                                                                  start, rc, ovec, ovec_slots, K, H, retry_only);
     }
     return cudaGetLastError();
 }
