@@ -163,3 +163,152 @@ extern "C" long lc_hint_cls(lc_t *lc, const uint8_t *buf, size_t len)
     }
     return p0;
 }
+
+/*
+ * CPU model of k_pike_table (sregex_b200/csrc/kernels/sre_pike_table.cu): the
+ * Pike VM driven by the closure tables of sre_closure.h, for one buffer with
+ * eof = 1 on a fresh context, started at offset `start`.  Thread lists are
+ * unbounded here (the kernel reports lines beyond its capacities as RETRY).
+ * Returns the rc of sre_vm_pike_exec, or -1000 when the program has no table;
+ * ovec receives 2 * (ncaps + 1) values.
+ */
+#include "../sregex_b200/csrc/lower/sre_closure.h"
+
+namespace {
+
+struct tp_thread_t {
+    uint32_t             park;
+    bool                 seen_word;
+    std::vector<int64_t> cap;
+};
+
+inline bool tp_isword(uint32_t c)
+{
+    return (c - '0' < 10u) || ((c | 0x20) - 'a' < 26u) || c == '_';
+}
+
+}  // namespace
+
+extern "C" long lc_table_pike(sre_program_t *prog, const uint8_t *input, long size, long start, int64_t *ovec)
+{
+    sre_closure_table_t T;
+    if (!sre_build_closure_table(prog, T)) {
+        return -1000;
+    }
+    const uint32_t np = T.npark;
+    const size_t nslots = 2 * (prog->multi_ncaps[0] + 1);
+    uint64_t m_cur = 0, m_prev = 0;
+    std::vector<tp_thread_t> clist, nlist, hold;     /* hold: LIFO, back = top */
+    std::vector<int64_t> matched_cap;
+    bool matched = false;
+
+    /* 0 ok, 1 MATCH reached (want_done) */
+    auto append_closure = [&](uint32_t P, long pos, const std::vector<int64_t> &parent,
+                              std::vector<tp_thread_t> &out, bool use_prev, bool want_done) -> int {
+        uint32_t v = 0, prev = 0;
+        if (pos > 0) {
+            prev = input[pos - 1];
+            v = T.ctx_dep ? (prev == '\n' ? 1u : 2u) : 0u;
+        }
+        const int nb = pos < size ? (int) input[pos] : -2;
+        const uint32_t e1 = T.ofs[v * (np + 2) + P + 1];
+        for (uint32_t e = T.ofs[v * (np + 2) + P]; e < e1; e++) {
+            const uint32_t fp = T.ent[e] & 0xff, mask = T.ent[e] >> 16;
+            const uint32_t kind = T.kind[fp];
+            if (kind == 0 && (nb == -2 || !((T.accept[fp * 8 + ((uint32_t) nb >> 5)] >> (nb & 31)) & 1))) {
+                continue;
+            }
+            uint64_t &marks = use_prev ? m_prev : m_cur, &other = use_prev ? m_cur : m_prev;
+            if ((marks >> fp) & 1) {
+                continue;
+            }
+            marks |= 1ull << fp;
+            other &= ~(1ull << fp);
+            std::vector<int64_t> cap = parent;
+            for (size_t s = 0; s < nslots; s++) {
+                if ((mask >> s) & 1) {
+                    cap[s] = pos;
+                }
+            }
+            if (kind == 1 && want_done) {
+                matched_cap = cap;
+                return 1;
+            }
+            tp_thread_t t;
+            t.park = fp;
+            t.seen_word = kind >= 4 && pos > 0 && tp_isword(prev);
+            t.cap = cap;
+            out.push_back(t);
+        }
+        return 0;
+    };
+
+    const std::vector<int64_t> none(nslots, -1);
+    long sp = start;
+    append_closure(np, sp, none, clist, false, false);
+    for (; sp <= size; sp++) {
+        if (clist.empty()) {
+            break;
+        }
+        m_prev = m_cur;
+        m_cur = 0;
+        const bool at_end = (sp == size);
+        const uint32_t byte = at_end ? 0 : input[sp];
+        const bool cur_word = !at_end && tp_isword(byte);
+        size_t i = 0;
+        hold.clear();
+        for (;;) {
+            tp_thread_t t;
+            if (!hold.empty()) {
+                t = hold.back();
+                hold.pop_back();
+            } else if (i < clist.size()) {
+                t = clist[i++];
+            } else {
+                break;
+            }
+            const uint32_t kind = T.kind[t.park];
+            bool got_match = false;
+            if (kind >= 2) {
+                bool holds;
+                switch (kind) {
+                case 2:  holds = at_end; break;
+                case 3:  holds = at_end || byte == '\n'; break;
+                case 4:  holds = (t.seen_word == cur_word); break;
+                default: holds = (t.seen_word != cur_word); break;
+                }
+                if (holds) {
+                    std::vector<tp_thread_t> add;
+                    append_closure(t.park, sp, t.cap, add, true, false);
+                    for (size_t k = add.size(); k-- > 0;) {     /* prepended: first one on top */
+                        hold.push_back(add[k]);
+                    }
+                }
+            } else if (kind == 1) {
+                matched_cap = t.cap;
+                got_match = true;
+            } else if (!at_end && ((T.accept[t.park * 8 + (byte >> 5)] >> (byte & 31)) & 1)) {
+                got_match = append_closure(t.park, sp + 1, t.cap, nlist, false, true) == 1;
+            }
+            if (got_match) {
+                matched = true;
+                break;
+            }
+        }
+        clist.swap(nlist);
+        nlist.clear();
+        if (at_end) {
+            break;
+        }
+    }
+    if (!matched) {
+        for (size_t s = 0; s < nslots; s++) {
+            ovec[s] = -1;
+        }
+        return SRE_DECLINED;
+    }
+    for (size_t s = 0; s < nslots; s++) {
+        ovec[s] = matched_cap[s];
+    }
+    return 0;
+}

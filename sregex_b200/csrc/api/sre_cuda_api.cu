@@ -21,6 +21,7 @@
 #include "../host/sre_internal.h"
 #include "../kernels/sre_kernels.cuh"
 #include "../lower/sre_lower.h"
+#include "../lower/sre_closure.h"
 
 /* measurement aid: pure TMA streaming of a line corpus (no automaton) */
 cudaError_t sre_launch_tma_ceiling(const uint8_t *buf, size_t nlines, size_t pitch, size_t linelen,
@@ -133,300 +134,6 @@ void program_destroy(void *data)
     cudaFree(cp->io_buf);
     cudaFree(cp->line_ws);
     delete cp;
-}
-
-/*
- * The threads add_thread(pc 0) parks on consuming instructions, in the order
- * the reference's closure walk (sre_vm_pike.c:756-942: x before y, the
- * revisited-SPLIT rule :770-786) reaches them, each with the slots SAVEd on
- * its path; then bucketed by the byte they can take.  The Pike kernel appends
- * bucket[next byte] instead of walking the closure at every position.  Only
- * for programs whose start closure is context free: nleading != 0 (no MATCH,
- * no ANY) and no assertion on the way.
- */
-static bool build_start_closure(const sre_program_t *prog, const std::vector<uint16_t> &pc_regex,
-    const std::vector<uint32_t> &slot_ofs, std::vector<uint32_t> &ofs, std::vector<sre_dev_start_t> &ents)
-{
-    if (!prog->nleading || prog->len < 3 || prog->insts[0].opcode != SRE_OPCODE_SPLIT
-        || prog->insts[0].y != 1 || prog->insts[1].opcode != SRE_OPCODE_ANY)
-    {
-        return false;
-    }
-    struct item_t { int32_t kind, pc; };            /* kind -1: visit pc; else undo one SAVE */
-    std::vector<item_t> stack;
-    std::vector<int32_t> saved;                     /* slots SAVEd on the current path */
-    std::vector<uint8_t> seen(prog->len, 0);
-    std::vector<sre_dev_start_t> finals;
-    seen[0] = 1;
-    stack.push_back({ -1, prog->insts[0].x });
-    while (!stack.empty()) {
-        const item_t it = stack.back();
-        stack.pop_back();
-        if (it.kind >= 0) {
-            saved.pop_back();
-            continue;
-        }
-        int32_t pc = it.pc;
-        for (;;) {
-            if (pc < 0 || (uint32_t) pc >= prog->len) {
-                return false;
-            }
-            const sre_instruction_t &in = prog->insts[pc];
-            if (seen[pc]) {
-                if (in.opcode == SRE_OPCODE_SPLIT && !seen[in.y]) {
-                    pc = in.y;
-                    continue;
-                }
-                break;
-            }
-            seen[pc] = 1;
-            if (in.opcode == SRE_OPCODE_JMP) {
-                pc = in.x;
-                continue;
-            }
-            if (in.opcode == SRE_OPCODE_SPLIT) {
-                stack.push_back({ -1, in.y });
-                pc = in.x;
-                continue;
-            }
-            if (in.opcode == SRE_OPCODE_SAVE) {
-                stack.push_back({ 0, 0 });
-                saved.push_back(in.v);
-                pc++;
-                continue;
-            }
-            if (in.opcode == SRE_OPCODE_ASSERT || in.opcode == SRE_OPCODE_MATCH
-                || in.opcode == SRE_OPCODE_ANY)
-            {
-                return false;
-            }
-            sre_dev_start_t e;
-            memset(&e, 0, sizeof(e));
-            e.pc = pc;
-            const uint32_t base = slot_ofs[pc_regex[pc]], end = slot_ofs[pc_regex[pc] + 1];
-            for (int32_t v : saved) {
-                if ((uint32_t) v < base || (uint32_t) v >= end || (uint32_t) v - base > 255) {
-                    return false;
-                }
-                const uint8_t rel = (uint8_t) ((uint32_t) v - base);
-                bool dup = false;
-                for (uint32_t k = 0; k < e.nsl; k++) {
-                    dup |= (e.sl[k] == rel);
-                }
-                if (dup) {
-                    continue;
-                }
-                if (e.nsl == sizeof(e.sl)) {
-                    return false;
-                }
-                e.sl[e.nsl++] = rel;
-            }
-            finals.push_back(e);
-            break;
-        }
-    }
-    ofs.assign(257, 0);
-    ents.clear();
-    for (uint32_t b = 0; b < 256; b++) {
-        ofs[b] = (uint32_t) ents.size();
-        for (const sre_dev_start_t &e : finals) {
-            const sre_instruction_t &in = prog->insts[e.pc];
-            bool hit = false;
-            if (in.opcode == SRE_OPCODE_CHAR) {
-                hit = (in.ch == b);
-            } else {
-                for (uint32_t j = 0; j < in.nranges; j++) {
-                    const sre_vm_range_t &r = prog->ranges[in.v + j];
-                    hit |= (b >= r.from && b <= r.to);
-                }
-                if (in.opcode == SRE_OPCODE_NOTIN) {
-                    hit = !hit;
-                }
-            }
-            if (hit) {
-                ents.push_back(e);
-            }
-        }
-    }
-    ofs[256] = (uint32_t) ents.size();
-    return true;
-}
-
-/*
- * Closure tables for k_pike_table: for every instruction a thread can be
- * parked on (numbered 0 .. npark-1 in pc order; P == npark is the start), what
- * add_thread(pc + 1) appends when
- * run on its own -- the walk of sre_vm_pike.c:756-942 (x before y, revisited-
- * SPLIT rule :770-786, SAVE undone on the way back) with `\A` and `^` decided
- * by the look-behind context: 0 = at offset 0, 1 = after a newline, 2 =
- * elsewhere.  Entry = parked number | (slots SAVEd on the path) << 16.
- */
-struct closure_table_t {
-    std::vector<uint32_t> ent;
-    std::vector<uint16_t> ofs;
-    std::vector<uint32_t> accept;
-    std::vector<uint8_t>  kind;
-    uint32_t              npark = 0;
-    bool                  ctx_dep = false;
-};
-
-static void closure_walk(const sre_program_t *prog, const std::vector<int32_t> &park, int32_t pc0, int ctx,
-    std::vector<uint32_t> &out)
-{
-    struct item_t { int32_t kind, pc; uint32_t mask; };
-    std::vector<item_t> stack;
-    std::vector<uint8_t> seen(prog->len, 0);
-    uint32_t mask = 0;
-    stack.push_back({ -1, pc0, 0 });
-    while (!stack.empty()) {
-        const item_t it = stack.back();
-        stack.pop_back();
-        if (it.kind >= 0) {
-            mask = it.mask;
-            continue;
-        }
-        int32_t pc = it.pc;
-        for (;;) {
-            if (pc < 0 || (uint32_t) pc >= prog->len) {
-                break;
-            }
-            const sre_instruction_t &in = prog->insts[pc];
-            if (seen[pc]) {
-                if (in.opcode == SRE_OPCODE_SPLIT && !seen[in.y]) {
-                    pc = in.y;
-                    continue;
-                }
-                break;
-            }
-            seen[pc] = 1;
-            if (in.opcode == SRE_OPCODE_JMP) {
-                pc = in.x;
-                continue;
-            }
-            if (in.opcode == SRE_OPCODE_SPLIT) {
-                stack.push_back({ -1, in.y, 0 });
-                pc = in.x;
-                continue;
-            }
-            if (in.opcode == SRE_OPCODE_SAVE) {
-                stack.push_back({ 0, 0, mask });
-                mask |= 1u << in.v;
-                pc++;
-                continue;
-            }
-            if (in.opcode == SRE_OPCODE_ASSERT && in.v == SRE_REGEX_ASSERT_BIG_A) {
-                if (ctx != 0) {
-                    break;
-                }
-                pc++;
-                continue;
-            }
-            if (in.opcode == SRE_OPCODE_ASSERT && in.v == SRE_REGEX_ASSERT_CARET) {
-                if (ctx == 2) {
-                    break;
-                }
-                pc++;
-                continue;
-            }
-            out.push_back((uint32_t) park[pc] | (mask << 16));      /* parked */
-            break;
-        }
-    }
-}
-
-static bool build_closure_table(const sre_program_t *prog, closure_table_t &T)
-{
-    const uint32_t len = prog->len;
-    if (prog->nregexes != 1 || 2 * (prog->multi_ncaps[0] + 1) > 16) {
-        return false;
-    }
-    /* number the instructions that can hold a thread */
-    std::vector<int32_t> park(len, -1), park_pc;
-    for (uint32_t pc = 0; pc < len; pc++) {
-        const sre_instruction_t &in = prog->insts[pc];
-        uint8_t kind = 0xff;
-        switch (in.opcode) {
-        case SRE_OPCODE_CHAR:
-        case SRE_OPCODE_ANY:
-        case SRE_OPCODE_IN:
-        case SRE_OPCODE_NOTIN:
-            kind = 0;
-            break;
-        case SRE_OPCODE_MATCH:
-            kind = 1;
-            break;
-        case SRE_OPCODE_ASSERT:
-            switch (in.v) {
-            case SRE_REGEX_ASSERT_SMALL_Z: kind = 2; break;
-            case SRE_REGEX_ASSERT_DOLLAR:  kind = 3; break;
-            case SRE_REGEX_ASSERT_BIG_B:   kind = 4; break;
-            case SRE_REGEX_ASSERT_SMALL_B: kind = 5; break;
-            default: T.ctx_dep = true; break;
-            }
-            break;
-        default:
-            break;
-        }
-        if (kind != 0xff) {
-            park[pc] = (int32_t) park_pc.size();
-            park_pc.push_back((int32_t) pc);
-            T.kind.push_back(kind);
-        }
-    }
-    const uint32_t np = (uint32_t) park_pc.size();
-    if (np == 0 || np > 64) {
-        return false;
-    }
-    T.npark = np;
-    T.accept.assign((size_t) np * 8, 0);
-    for (uint32_t P = 0; P < np; P++) {
-        const sre_instruction_t &in = prog->insts[park_pc[P]];
-        if (T.kind[P] != 0) {
-            continue;
-        }
-        for (uint32_t b = 0; b < 256; b++) {
-            bool hit;
-            if (in.opcode == SRE_OPCODE_CHAR) {
-                hit = (in.ch == b);
-            } else if (in.opcode == SRE_OPCODE_ANY) {
-                hit = true;
-            } else {
-                hit = false;
-                for (uint32_t j = 0; j < in.nranges; j++) {
-                    const sre_vm_range_t &r = prog->ranges[in.v + j];
-                    hit |= (b >= r.from && b <= r.to);
-                }
-                if (in.opcode == SRE_OPCODE_NOTIN) {
-                    hit = !hit;
-                }
-            }
-            if (hit) {
-                T.accept[(size_t) P * 8 + (b >> 5)] |= 1u << (b & 31);
-            }
-        }
-    }
-    T.ofs.assign((size_t) 3 * (np + 2), 0);
-    const int nctx = T.ctx_dep ? 3 : 1;
-    for (int ctx = 0; ctx < nctx; ctx++) {
-        for (uint32_t P = 0; P <= np; P++) {
-            T.ofs[(size_t) ctx * (np + 2) + P] = (uint16_t) T.ent.size();
-            if (P == np) {
-                closure_walk(prog, park, 0, ctx, T.ent);
-            } else if (T.kind[P] != 1) {            /* nothing follows a MATCH */
-                closure_walk(prog, park, park_pc[P] + 1, ctx, T.ent);
-            }
-            if (T.ent.size() > 8192) {
-                return false;
-            }
-        }
-        T.ofs[(size_t) ctx * (np + 2) + np + 1] = (uint16_t) T.ent.size();
-    }
-    for (int ctx = nctx; ctx < 3; ctx++) {
-        for (uint32_t P = 0; P <= np + 1; P++) {
-            T.ofs[(size_t) ctx * (np + 2) + P] = T.ofs[P];
-        }
-    }
-    return !T.ent.empty();
 }
 
 int upload(sre_cuda_program_t *cp)
@@ -550,8 +257,8 @@ int upload(sre_cuda_program_t *cp)
         }
     }
     const size_t o_pcre = b.add(pc_regex.data(), pc_regex.size() * 2);
-    closure_table_t clo;
-    const bool has_clo = build_closure_table(prog, clo);
+    sre_closure_table_t clo;
+    const bool has_clo = sre_build_closure_table(prog, clo);
     size_t o_cent = 0, o_cofs = 0, o_cacc = 0, o_ckind = 0;
     if (has_clo) {
         o_cent = b.add(clo.ent.data(), clo.ent.size() * 4);
@@ -560,13 +267,14 @@ int upload(sre_cuda_program_t *cp)
         o_ckind = b.add(clo.kind.data(), clo.kind.size());
     }
     std::vector<uint32_t> start_ofs;
-    std::vector<sre_dev_start_t> start_ent;
-    const bool has_start = build_start_closure(prog, pc_regex, slot_ofs, start_ofs, start_ent);
+    static_assert(sizeof(sre_start_ent_t) == sizeof(sre_dev_start_t), "start entry layout");
+    std::vector<sre_start_ent_t> start_ent;
+    const bool has_start = sre_build_start_closure(prog, pc_regex, slot_ofs, start_ofs, start_ent);
     size_t o_sofs = 0, o_sent = 0;
     if (has_start) {
         o_sofs = b.add(start_ofs.data(), start_ofs.size() * 4);
-        start_ent.push_back(sre_dev_start_t());       /* never an empty table */
-        o_sent = b.add(start_ent.data(), start_ent.size() * sizeof(sre_dev_start_t));
+        start_ent.push_back(sre_start_ent_t());       /* never an empty table */
+        o_sent = b.add(start_ent.data(), start_ent.size() * sizeof(sre_start_ent_t));
     }
 
     if (cudaMalloc(&cp->d_blob, b.bytes.size() + 256) != cudaSuccess

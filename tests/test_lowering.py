@@ -28,7 +28,18 @@ def lc():
     lib.lc_hint.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     lib.lc_hint_cls.restype = C.c_long
     lib.lc_hint_cls.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    lib.lc_table_pike.restype = C.c_long
+    lib.lc_table_pike.argtypes = [C.c_void_p, C.c_char_p, C.c_long, C.c_long, C.POINTER(C.c_int64)]
     return lib
+
+
+def _table_pike(lc, prog, s, start=0):
+    """the closure-table Pike (CPU model of k_pike_table) -> (rc, ovector) or None"""
+    ov = (C.c_int64 * prog.nslots)()
+    rc = lc.lc_table_pike(prog.prog, s, len(s), start, ov)
+    if rc == -1000:
+        return None
+    return rc, (list(ov) if rc >= 0 else None)
 
 
 def _stream(fn, chunks):
@@ -136,3 +147,58 @@ def test_random_regex_fuzz_lowering_vs_live_reference(oracle, ref, lc):
         po.close()
         pr.close()
     assert tried > 600
+
+
+def test_closure_table_pike_golden(golden, oracle, lc):
+    """the closure tables of sre_closure.cpp, run by the CPU model of
+    k_pike_table, reproduce the reference's Pike rc + ovector on every
+    single-regex golden block -- from offset 0 and from the DFA start hint"""
+    checked = hinted = 0
+    for b in runnable(golden):
+        if b["multi"]:
+            continue
+        p = oracle.compile(b["regexes_b"], b["flags"], multi=False)
+        s = b["subject_b"]
+        got = _table_pike(lc, p, s)
+        if got is not None:
+            assert got == (b["pike"]["rc"], b["pike"]["ov"]), (b["file"], b["name"])
+            checked += 1
+            h = lc.lc_create(p.prog, 4096)
+            hint = lc.lc_hint_cls(h, s, len(s)) if h else -1
+            if hint > 0:
+                assert _table_pike(lc, p, s, hint) == (b["pike"]["rc"], b["pike"]["ov"]), (b["file"], b["name"])
+                hinted += 1
+            if h:
+                lc.lc_destroy(h)
+        p.close()
+    assert checked > 1500 and hinted > 100, (checked, hinted)
+
+
+def test_closure_table_pike_fuzz_vs_live_reference(ref, oracle, lc):
+    """random regexes rich in assertions, nested repetition and captures x
+    random subjects: the closure-table Pike against the reference itself"""
+    import random
+    rng = random.Random(777)
+    atoms = ["a", "b", "ab", " ", "\\n", "_", ".", "^", "$", "\\b", "\\B", "\\A", "\\z", "|", "(", ")", "(?:",
+             "*", "+", "?", "*?", "+?", "??", "{2}", "{0,2}", "{1,}", "[ab]", "[^a]", "\\w", "\\W", "\\s", "\\d",
+             "1", "(a|b)", "(a*)", "(\\w+)"]
+    alphabet = b"ab \n_1."
+    tried = 0
+    for _ in range(2500):
+        rx = "".join(rng.choice(atoms) for _ in range(rng.randrange(1, 9))).encode()
+        try:
+            pr = ref.compile(rx, 0)
+        except capi.SreSyntaxError:
+            continue
+        po = oracle.compile(rx, 0)
+        if _table_pike(lc, po, b"") is None:
+            po.close()
+            pr.close()
+            continue
+        tried += 1
+        for _ in range(8):
+            s = bytes(rng.choice(alphabet) for _ in range(rng.randrange(0, 14)))
+            assert _table_pike(lc, po, s) == ref.pike(pr, s), (rx, s)
+        po.close()
+        pr.close()
+    assert tried > 1000
