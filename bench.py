@@ -334,12 +334,12 @@ def main():
                 extra["c3_matched_lines"] = int((prc == 0).sum())
                 # C4: 64-pattern set: which pattern matched (Thompson gate, then Pike on the hits)
                 pm = cuda.CudaProgram(corpus.multi_pattern_set(64))
-                m = min(n, 1 << 17)
+                m = n
                 extra["c4_multi64_gate_gbs"] = timed_gbs(lambda: pm.thompson_lines(dev, n, PITCH, PITCH), n * PITCH)
                 mrc = torch.empty(m, dtype=torch.int32, device="cuda")
                 mov = torch.empty((m, pm.nslots), dtype=torch.int64, device="cuda")
                 extra["c4_multi64_id_gbs"] = timed_gbs(
-                    lambda: pm.pike_lines(dev, m, PITCH, PITCH, out_rc=mrc, out_ovec=mov), m * PITCH, reps=1)
+                    lambda: pm.pike_lines(dev, m, PITCH, PITCH, out_rc=mrc, out_ovec=mov), m * PITCH)
                 extra["c4_lines"] = m
                 extra["c4_matched_fraction"] = float((mrc >= 0).float().mean())
                 extra["c4_dfa_states"] = pm.info.dfa_states
