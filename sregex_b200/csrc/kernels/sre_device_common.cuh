@@ -56,6 +56,38 @@ struct step256_t {
     }
 };
 
+/*
+ * The same table with rows padded to 260 bytes (65 words): row s starts s
+ * banks further on, so lanes that sit in different states and read bytes of the
+ * same 4-byte group -- the rule on text over a small alphabet -- no longer
+ * collide on one bank.  Costs one IMAD per byte on top of the byte extract.
+ */
+constexpr uint32_t ROW260 = 260;
+struct step260_t {
+    const uint8_t *tab;
+    __device__ __forceinline__ uint32_t word(uint32_t s, uint32_t w) const
+    {
+        s = tab[s * ROW260 + __byte_perm(w, 0, 0x4440)];
+        s = tab[s * ROW260 + __byte_perm(w, 0, 0x4441)];
+        s = tab[s * ROW260 + __byte_perm(w, 0, 0x4442)];
+        s = tab[s * ROW260 + __byte_perm(w, 0, 0x4443)];
+        return s;
+    }
+    __device__ __forceinline__ uint32_t byte(uint32_t s, uint32_t b) const
+    {
+        return tab[s * ROW260 + b];
+    }
+};
+
+/* [nstates][256] in global memory -> rows of ROW260 bytes in shared memory */
+__device__ __forceinline__ void load_table260(uint8_t *dst, const uint8_t *src, uint32_t nstates)
+{
+    for (uint32_t i = threadIdx.x; i < nstates * 64; i += blockDim.x) {
+        reinterpret_cast<uint32_t *>(dst)[(i >> 6) * (ROW260 / 4) + (i & 63)] =
+            reinterpret_cast<const uint32_t *>(src)[i];
+    }
+}
+
 /* byte-class compressed u16 table: extract, LDS.U8 class, IMAD, LDS.U16 */
 struct stepcls_t {
     const uint16_t *tab;

@@ -133,7 +133,7 @@ __device__ __forceinline__ void warp_compose(fn_t<NW> &f)
 /* NW*4-way consumer: byte d of `st` = state reached from entry state d */
 template <int NW>
 struct piece_consumer_t {
-    const uint8_t  *tab;        /* [nstates][256] in shared memory            */
+    const uint8_t  *tab;        /* [nstates] rows of ROW260 bytes in shared memory */
     uint8_t        *fn;         /* level-0 function records                   */
     uint32_t        nstates, acc;
     size_t          npieces;
@@ -178,7 +178,7 @@ struct piece_consumer_t {
 
     __device__ __forceinline__ void chunk(const uint4 &v)
     {
-        step256_t st256 = { tab };
+        step260_t st256 = { tab };
         if (conv) {
             s = st256.word(st256.word(st256.word(st256.word(s, v.x), v.y), v.z), v.w);
             return;
@@ -197,13 +197,13 @@ struct piece_consumer_t {
     __device__ __forceinline__ void byte(uint32_t b)
     {
         if (conv) {
-            s = tab[(s << 8) | b];
+            s = tab[s * ROW260 + b];
             return;
         }
 #pragma unroll
         for (int d = 0; d < NW * 4; d++) {
             if (d < (int) nstates) {
-                st.set(d, tab[(st.get(d) << 8) | b]);
+                st.set(d, tab[st.get(d) * ROW260 + b]);
             }
         }
     }
@@ -237,8 +237,9 @@ k_stream_pieces(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, siz
                 uint32_t PIECE)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, false);
-    load_table(smem, dfa.t256, plan.tab_bytes);
+    /* one extra row of room for the padding of the rows */
+    const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates + 1, dfa.nclasses, false);
+    load_table260(smem, dfa.t256, dfa.nstates);
     __syncthreads();
 
     const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
@@ -439,7 +440,7 @@ template <int NW>
 cudaError_t launch_pieces(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t npieces, uint8_t *fn,
     cudaStream_t stream)
 {
-    const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, false);
+    const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates + 1, dfa.nclasses, false);   /* as the kernel */
     const int warps = 32;
     const size_t smem = plan.stage_ofs + (size_t) warps * 32 * 128;
     const uint32_t PIECE = g_piece;
