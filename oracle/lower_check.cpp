@@ -192,14 +192,16 @@ inline bool tp_isword(uint32_t c)
 extern "C" long lc_table_pike(sre_program_t *prog, const uint8_t *input, long size, long start, int64_t *ovec)
 {
     sre_closure_table_t T;
-    if (!sre_build_closure_table(prog, T)) {
+    if (!sre_build_closure_table(prog, 4096, T)) {
         return -1000;
     }
     const uint32_t np = T.npark;
-    const size_t nslots = 2 * (prog->multi_ncaps[0] + 1);
-    uint64_t m_cur = 0, m_prev = 0;
+    const size_t nslots = T.max_slots;          /* a thread carries the slots of its own regex */
+    /* dedup marks: "marked in this step" / "marked in the previous step" */
+    std::vector<uint8_t> m_cur(np, 0), m_prev(np, 0);
     std::vector<tp_thread_t> clist, nlist, hold;     /* hold: LIFO, back = top */
     std::vector<int64_t> matched_cap;
+    long matched_id = 0;
     bool matched = false;
 
     /* 0 ok, 1 MATCH reached (want_done) */
@@ -211,19 +213,29 @@ extern "C" long lc_table_pike(sre_program_t *prog, const uint8_t *input, long si
             v = T.ctx_dep ? (prev == '\n' ? 1u : 2u) : 0u;
         }
         const int nb = pos < size ? (int) input[pos] : -2;
-        const uint32_t e1 = T.ofs[v * (np + 2) + P + 1];
-        for (uint32_t e = T.ofs[v * (np + 2) + P]; e < e1; e++) {
-            const uint32_t fp = T.ent[e] & 0xff, mask = T.ent[e] >> 16;
+        const uint32_t *list = T.ent.data();
+        uint32_t e0 = T.ofs[v * (np + 2) + P], e1 = T.ofs[v * (np + 2) + P + 1];
+        bool filtered = false;
+        if ((P == np || (int32_t) P == T.p_any) && !T.bent.empty() && nb >= 0) {
+            list = T.bent.data();           /* the start closure by next byte */
+            e0 = T.bofs[v * 257 + nb];
+            e1 = T.bofs[v * 257 + nb + 1];
+            filtered = true;
+        }
+        for (uint32_t e = e0; e < e1; e++) {
+            const uint32_t fp = list[e] & 0xffff, mask = list[e] >> 16;
             const uint32_t kind = T.kind[fp];
-            if (kind == 0 && (nb == -2 || !((T.accept[fp * 8 + ((uint32_t) nb >> 5)] >> (nb & 31)) & 1))) {
+            if (!filtered && kind == 0
+                && (nb == -2 || !((T.accept[T.acc_idx[fp] * 8 + ((uint32_t) nb >> 5)] >> (nb & 31)) & 1)))
+            {
                 continue;
             }
-            uint64_t &marks = use_prev ? m_prev : m_cur, &other = use_prev ? m_cur : m_prev;
-            if ((marks >> fp) & 1) {
+            std::vector<uint8_t> &marks = use_prev ? m_prev : m_cur, &other = use_prev ? m_cur : m_prev;
+            if (marks[fp]) {
                 continue;
             }
-            marks |= 1ull << fp;
-            other &= ~(1ull << fp);
+            marks[fp] = 1;
+            other[fp] = 0;
             std::vector<int64_t> cap = parent;
             for (size_t s = 0; s < nslots; s++) {
                 if ((mask >> s) & 1) {
@@ -232,6 +244,7 @@ extern "C" long lc_table_pike(sre_program_t *prog, const uint8_t *input, long si
             }
             if (kind == 1 && want_done) {
                 matched_cap = cap;
+                matched_id = T.regex[fp];
                 return 1;
             }
             tp_thread_t t;
@@ -251,7 +264,7 @@ extern "C" long lc_table_pike(sre_program_t *prog, const uint8_t *input, long si
             break;
         }
         m_prev = m_cur;
-        m_cur = 0;
+        std::fill(m_cur.begin(), m_cur.end(), 0);
         const bool at_end = (sp == size);
         const uint32_t byte = at_end ? 0 : input[sp];
         const bool cur_word = !at_end && tp_isword(byte);
@@ -286,8 +299,9 @@ extern "C" long lc_table_pike(sre_program_t *prog, const uint8_t *input, long si
                 }
             } else if (kind == 1) {
                 matched_cap = t.cap;
+                matched_id = T.regex[t.park];
                 got_match = true;
-            } else if (!at_end && ((T.accept[t.park * 8 + (byte >> 5)] >> (byte & 31)) & 1)) {
+            } else if (!at_end && ((T.accept[T.acc_idx[t.park] * 8 + (byte >> 5)] >> (byte & 31)) & 1)) {
                 got_match = append_closure(t.park, sp + 1, t.cap, nlist, false, true) == 1;
             }
             if (got_match) {
@@ -307,8 +321,10 @@ extern "C" long lc_table_pike(sre_program_t *prog, const uint8_t *input, long si
         }
         return SRE_DECLINED;
     }
+    /* prepare_matched_captures :945-989: the matched regex's slots, then -1 */
+    const size_t cnt = 2 * (size_t) (prog->multi_ncaps[matched_id] + 1);
     for (size_t s = 0; s < nslots; s++) {
-        ovec[s] = matched_cap[s];
+        ovec[s] = s < cnt ? matched_cap[s] : -1;
     }
-    return 0;
+    return matched_id;
 }

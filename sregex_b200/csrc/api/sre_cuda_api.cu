@@ -258,13 +258,17 @@ int upload(sre_cuda_program_t *cp)
     }
     const size_t o_pcre = b.add(pc_regex.data(), pc_regex.size() * 2);
     sre_closure_table_t clo;
-    const bool has_clo = sre_build_closure_table(prog, clo);
-    size_t o_cent = 0, o_cofs = 0, o_cacc = 0, o_ckind = 0;
+    const bool has_clo = sre_build_closure_table(prog, 4096, clo);
+    size_t o_cent = 0, o_cofs = 0, o_cacc = 0, o_ckind = 0, o_caidx = 0, o_creg = 0, o_cbent = 0, o_cbofs = 0;
     if (has_clo) {
         o_cent = b.add(clo.ent.data(), clo.ent.size() * 4);
         o_cofs = b.add(clo.ofs.data(), clo.ofs.size() * 2);
         o_cacc = b.add(clo.accept.data(), clo.accept.size() * 4);
         o_ckind = b.add(clo.kind.data(), clo.kind.size());
+        o_caidx = b.add(clo.acc_idx.data(), clo.acc_idx.size() * 2);
+        o_creg = b.add(clo.regex.data(), clo.regex.size() * 2);
+        o_cbent = b.add(clo.bent.data(), clo.bent.size() * 4);
+        o_cbofs = b.add(clo.bofs.data(), clo.bofs.size() * 2);
     }
     std::vector<uint32_t> start_ofs;
     static_assert(sizeof(sre_start_ent_t) == sizeof(sre_dev_start_t), "start entry layout");
@@ -355,6 +359,13 @@ int upload(sre_cuda_program_t *cp)
     pk.clo_kind = has_clo ? base + o_ckind : nullptr;
     pk.clo_nent = has_clo ? (uint32_t) clo.ent.size() : 0;
     pk.clo_npark = has_clo ? clo.npark : 0;
+    pk.clo_accidx = has_clo ? reinterpret_cast<const uint16_t *>(base + o_caidx) : nullptr;
+    pk.clo_regex = has_clo ? reinterpret_cast<const uint16_t *>(base + o_creg) : nullptr;
+    pk.clo_bent = has_clo ? reinterpret_cast<const uint32_t *>(base + o_cbent) : nullptr;
+    pk.clo_bofs = has_clo ? reinterpret_cast<const uint16_t *>(base + o_cbofs) : nullptr;
+    pk.clo_nbent = has_clo ? (uint32_t) clo.bent.size() : 0;
+    pk.clo_nsets = has_clo ? clo.nsets : 0;
+    pk.clo_p_any = has_clo && clo.p_any >= 0 ? (uint32_t) clo.p_any : 0xffffffffu;
     pk.clo_ctx_dep = clo.ctx_dep ? 1 : 0;
     pk.start_ofs = has_start ? reinterpret_cast<const uint32_t *>(base + o_sofs) : nullptr;
     pk.start_ent = has_start ? reinterpret_cast<const sre_dev_start_t *>(base + o_sent) : nullptr;
@@ -714,20 +725,28 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
     const size_t nctx = cp->pike_nctx < nlines ? cp->pike_nctx : nlines;
     if (sre_pike_table_applicable(cp->pike) && linelen < (1ull << 31) && g_pike_general_only == 0) {
         /* closure-table kernel first; the general kernel re-runs what it gave up on */
-        static int k1 = -1, h1 = 2;
-        if (k1 < 0) {           /* SRE_PIKE_TABLE_K="K,H": first-pass capacities (tuning) */
+        static int ek1 = -1, eh1 = 2, ek2 = 0, eh2 = 0;
+        if (ek1 < 0) {          /* SRE_PIKE_TABLE_K="K1,H1[,K2,H2]": list capacities of the two passes (tuning) */
             const char *e = getenv("SRE_PIKE_TABLE_K");
-            k1 = 5;
+            ek1 = 0;
             if (e) {
-                sscanf(e, "%d,%d", &k1, &h1);
+                sscanf(e, "%d,%d,%d,%d", &ek1, &eh1, &ek2, &eh2);
             }
         }
-        /* small lists first (more resident warps), then the lines that needed more */
+        /* small lists first (more resident warps), then the lines that needed more.
+         * A set of regexes can have as many live threads as members share a prefix. */
+        const bool big = cp->pike.nregexes > 1 || cp->pike.clo_npark > 64;
+        const int k1 = ek1 > 0 ? ek1 : (big ? 12 : 5), h1 = ek1 > 0 ? eh1 : 2;
+        int k2 = ek2 > 0 ? ek2 : (big ? 32 : 8);
+        const int h2 = ek2 > 0 ? eh2 : 4;
+        if ((uint32_t) k2 > cp->pike.clo_npark) {
+            k2 = (int) cp->pike.clo_npark;
+        }
         err = sre_launch_pike_table(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
                                     dev_rc, dev_ovec, (uint32_t) ovec_slots, k1, h1, 0, st, &launches);
-        if (err == cudaSuccess && (k1 < 8 || h1 < 4)) {
+        if (err == cudaSuccess && (k1 < k2 || h1 < h2)) {
             err = sre_launch_pike_table(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
-                                        dev_rc, dev_ovec, (uint32_t) ovec_slots, 8, 4, 1, st, &launches);
+                                        dev_rc, dev_ovec, (uint32_t) ovec_slots, k2, h2, 1, st, &launches);
         }
         if (err == cudaSuccess) {
             err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines,

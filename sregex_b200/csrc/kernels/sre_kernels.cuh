@@ -83,19 +83,18 @@ struct sre_dev_pike_t {
      * priority order; NULL when closure(pc 0) meets an assertion             */
     const uint32_t          *start_ofs;
     const sre_dev_start_t   *start_ent;
-    /* closure tables of k_pike_table (small single-regex programs; clo_nent
-     * == 0: none), over the clo_npark instructions a thread can be parked on,
-     * numbered in pc order.  Closure (ctx, P) = clo_ent[clo_ofs[ctx * (npark +
-     * 2) + P] .. clo_ofs[ctx * (npark + 2) + P + 1]): what add_thread(pc(P) +
-     * 1) appends (P == npark: add_thread(0)) at offset 0 (ctx 0), after a
-     * newline (1), elsewhere (2); entry = parked number | slots SAVEd on the
-     * path << 16                                                             */
-    const uint32_t          *clo_ent;
-    const uint16_t          *clo_ofs;
-    const uint32_t          *clo_accept;    /* [npark][8] bytes it takes           */
+    /* closure tables of k_pike_table (lower/sre_closure.h; clo_nent == 0:
+     * none), over the clo_npark instructions a thread can be parked on       */
+    const uint32_t          *clo_ent;       /* parked number | slots SAVEd << 16  */
+    const uint16_t          *clo_ofs;       /* [3][npark + 2]                      */
+    const uint32_t          *clo_accept;    /* [nsets][8] distinct byte sets       */
+    const uint16_t          *clo_accidx;    /* [npark] byte set it takes           */
+    const uint16_t          *clo_regex;     /* [npark] owning regex                */
     const uint8_t           *clo_kind;      /* [npark] what it is                  */
-    uint32_t                 clo_nent;
-    uint32_t                 clo_npark;
+    const uint32_t          *clo_bent;      /* start closure bucketed by next byte */
+    const uint16_t          *clo_bofs;      /* [3][257]                            */
+    uint32_t                 clo_nent, clo_nbent, clo_nsets, clo_npark;
+    uint32_t                 clo_p_any;     /* parked number of the ".*?" ANY      */
     uint32_t                 clo_ctx_dep;   /* program has \A or ^             */
 };
 

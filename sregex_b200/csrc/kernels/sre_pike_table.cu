@@ -1,6 +1,7 @@
 /*
- * sre_pike_table.cu -- the Pike VM for small single-regex programs, driven by
- * precomputed closure tables (the batch Pike+captures kernel of choice).
+ * sre_pike_table.cu -- the Pike VM driven by precomputed closure tables (the
+ * batch Pike+captures kernel of choice: single regexes and regex sets whose
+ * tables fit in shared memory).
  *
  * Same results as sre_vm_pike_exec (reference sre_vm_pike.c:148-689) for a
  * fresh context and one buffer with eof = 1, like sre_pike_small.cu, but
@@ -42,21 +43,28 @@ __device__ __forceinline__ bool isword(uint32_t c)
     return (c - '0' < 10u) || ((c | 0x20) - 'a' < 26u) || c == '_';
 }
 
-/* one lane's context: words at sm[e * TB] */
-template <bool C16>
+/*
+ * one lane's context: words at sm[e * TB].  BIG: more than 64 parked
+ * instructions -- the dedup marks are two bit sets in shared memory (MK, 2 x mw
+ * words, the current one chosen by `par`) instead of two 64-bit registers.
+ */
+template <bool C16, bool BIG>
 struct lane_t {
     int32_t    *sm;
     int         ncw;                /* words per capture vector */
     int         K, H;               /* threads per list, pending look-ahead closures */
     uint64_t    m_cur, m_prev;
+    int         mw, par;            /* BIG: words per mark set, parity of the current set */
     /* sections (word offsets), set from ncw */
-    int         MAT, TMP, L0PC, L0CAP, L1PC, L1CAP, HSPC, HSCAP;
+    int         MAT, TMP, L0PC, L0CAP, L1PC, L1CAP, HSPC, HSCAP, MK;
 
-    __device__ __forceinline__ void layout(int n, int k, int h)
+    __device__ __forceinline__ void layout(int n, int k, int h, int npark)
     {
         ncw = n;
         K = k;
         H = h;
+        mw = BIG ? (npark + 31) >> 5 : 0;
+        par = 0;
         MAT = 0;
         TMP = MAT + n;
         L0PC = TMP + n;
@@ -65,15 +73,51 @@ struct lane_t {
         L1CAP = L1PC + K;
         HSPC = L1CAP + K * n;
         HSCAP = HSPC + H;
+        MK = HSCAP + H * n;
     }
     __device__ __forceinline__ int32_t &w(int e) { return sm[e * TB]; }
 
-    __device__ __forceinline__ bool tagged(uint32_t pc, bool hold) const
+    /* all marks off (new line) */
+    __device__ __forceinline__ void marks_reset()
     {
+        if (BIG) {
+            for (int j = 0; j < 2 * mw; j++) {
+                w(MK + j) = 0;
+            }
+            par = 0;
+        } else {
+            m_cur = m_prev = 0;
+        }
+    }
+    /* ctx->tag++: the current set becomes the previous one, the new current one is empty */
+    __device__ __forceinline__ void marks_advance()
+    {
+        if (BIG) {
+            par ^= 1;
+            for (int j = 0; j < mw; j++) {
+                w(MK + par * mw + j) = 0;
+            }
+        } else {
+            m_prev = m_cur;
+            m_cur = 0;
+        }
+    }
+    /* marked with ctx->tag (hold == false) or with ctx->tag - 1 */
+    __device__ __forceinline__ bool tagged(uint32_t pc, bool hold)
+    {
+        if (BIG) {
+            return ((uint32_t) w(MK + (par ^ (int) hold) * mw + (int) (pc >> 5)) >> (pc & 31)) & 1;
+        }
         return ((hold ? m_prev : m_cur) >> pc) & 1;
     }
     __device__ __forceinline__ void tag(uint32_t pc, bool hold)
     {
+        if (BIG) {
+            const int32_t bit = (int32_t) (1u << (pc & 31));
+            w(MK + (par ^ (int) hold) * mw + (int) (pc >> 5)) |= bit;
+            w(MK + (par ^ (int) hold ^ 1) * mw + (int) (pc >> 5)) &= ~bit;
+            return;
+        }
         const uint64_t bit = 1ull << pc;
         if (hold) {
             m_prev |= bit;
@@ -119,7 +163,21 @@ struct lane_t {
 /* what a parked instruction is (block table s_kind) */
 enum { KD_CONS = 0, KD_MATCH = 1, KD_SMALL_Z = 2, KD_DOLLAR = 3, KD_BIG_B = 4, KD_SMALL_B = 5 };
 
-template <bool C16>
+/* block tables in shared memory, in this order (words, then halves, then bytes) */
+struct tables_t {
+    uint32_t  *ent, *bent, *accept;
+    uint16_t  *ofs, *bofs, *accidx, *regex;
+    uint8_t   *kind;
+};
+
+__host__ __device__ inline size_t table_words(const sre_dev_pike_t &pk)
+{
+    const size_t np = pk.clo_npark;
+    const size_t halves = 3 * (np + 2) + (pk.clo_nbent ? 3 * 257 : 0) + 2 * np;
+    return pk.clo_nent + pk.clo_nbent + (size_t) pk.clo_nsets * 8 + (halves * 2 + np + 3) / 4;
+}
+
+template <bool C16, bool BIG>
 __global__ void __launch_bounds__(TB)
 k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
              size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines,
@@ -127,30 +185,46 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
              uint32_t ovec_slots, int K, int H, int retry_only)
 {
     extern __shared__ int32_t smem_words[];
-    /* block tables: entries | closure offsets | accept sets | kinds, then the lanes */
-    const uint32_t len = pk.clo_npark, nofs = 3 * (len + 2);
-    uint32_t *s_ent = reinterpret_cast<uint32_t *>(smem_words);
-    uint32_t *s_accept = s_ent + pk.clo_nent;
-    uint16_t *s_ofs = reinterpret_cast<uint16_t *>(s_accept + len * 8);
-    uint8_t *s_kind = reinterpret_cast<uint8_t *>(s_ofs + nofs);
-    const uint32_t table_words = pk.clo_nent + len * 8 + (nofs * 2 + len + 3) / 4;
+    const uint32_t len = pk.clo_npark, nofs = 3 * (len + 2), nbofs = pk.clo_nbent ? 3 * 257 : 0;
+    tables_t t;
+    t.ent = reinterpret_cast<uint32_t *>(smem_words);
+    t.bent = t.ent + pk.clo_nent;
+    t.accept = t.bent + pk.clo_nbent;
+    t.ofs = reinterpret_cast<uint16_t *>(t.accept + pk.clo_nsets * 8);
+    t.bofs = t.ofs + nofs;
+    t.accidx = t.bofs + nbofs;
+    t.regex = t.accidx + len;
+    t.kind = reinterpret_cast<uint8_t *>(t.regex + len);
     for (uint32_t i = threadIdx.x; i < pk.clo_nent; i += TB) {
-        s_ent[i] = pk.clo_ent[i];
+        t.ent[i] = pk.clo_ent[i];
     }
-    for (uint32_t i = threadIdx.x; i < len * 8; i += TB) {
-        s_accept[i] = pk.clo_accept[i];
+    for (uint32_t i = threadIdx.x; i < pk.clo_nbent; i += TB) {
+        t.bent[i] = pk.clo_bent[i];
+    }
+    for (uint32_t i = threadIdx.x; i < pk.clo_nsets * 8; i += TB) {
+        t.accept[i] = pk.clo_accept[i];
     }
     for (uint32_t i = threadIdx.x; i < nofs; i += TB) {
-        s_ofs[i] = pk.clo_ofs[i];
+        t.ofs[i] = pk.clo_ofs[i];
+    }
+    for (uint32_t i = threadIdx.x; i < nbofs; i += TB) {
+        t.bofs[i] = pk.clo_bofs[i];
     }
     for (uint32_t i = threadIdx.x; i < len; i += TB) {
-        s_kind[i] = pk.clo_kind[i];
+        t.accidx[i] = pk.clo_accidx[i];
+        t.regex[i] = pk.clo_regex[i];
+        t.kind[i] = pk.clo_kind[i];
     }
     __syncthreads();
+    const uint32_t *s_ent = t.ent, *s_bent = t.bent, *s_accept = t.accept;
+    const uint16_t *s_ofs = t.ofs, *s_bofs = t.bofs, *s_accidx = t.accidx, *s_regex = t.regex;
+    const uint8_t *s_kind = t.kind;
+    const uint32_t p_any = pk.clo_p_any;
 
-    lane_t<C16> c;
-    c.sm = smem_words + table_words + threadIdx.x;
-    c.layout(C16 ? (int) (pk.nslots + 1) >> 1 : (int) pk.nslots, K, H);
+    lane_t<C16, BIG> c;
+    c.sm = smem_words + table_words(pk) + threadIdx.x;
+    /* a thread carries the slots of its own regex only */
+    c.layout(C16 ? (int) (pk.max_slots + 1) >> 1 : (int) pk.max_slots, K, H, (int) len);
     const int ncw = c.ncw;
     const bool ctx_dep = pk.clo_ctx_dep != 0;
 
@@ -178,13 +252,23 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
             v = ctx_dep ? (prev == '\n' ? 1u : 2u) : 0u;
         }
         const int nb = pos < size ? (int) input[pos] : NB_END;
-        const uint32_t e1 = s_ofs[v * (len + 2) + P + 1];
-        for (uint32_t e = s_ofs[v * (len + 2) + P]; e < e1; e++) {
-            const uint32_t ent = s_ent[e];
-            const uint32_t fpc = ent & 0xff, mask = ent >> 16;
+        const uint32_t *list = s_ent;
+        uint32_t e = s_ofs[v * (len + 2) + P], e1 = s_ofs[v * (len + 2) + P + 1];
+        bool filtered = false;
+        if ((P == len || P == p_any) && pk.clo_nbent && nb >= 0) {
+            /* the start closure, already restricted to this next byte */
+            list = s_bent;
+            e = s_bofs[v * 257 + (uint32_t) nb];
+            e1 = s_bofs[v * 257 + (uint32_t) nb + 1];
+            filtered = true;
+        }
+        for (; e < e1; e++) {
+            const uint32_t ent = list[e];
+            const uint32_t fpc = ent & 0xffff, mask = ent >> 16;
             const uint32_t kind = s_kind[fpc];
-            if (kind == KD_CONS
-                && (nb == NB_END || !((s_accept[fpc * 8 + ((uint32_t) nb >> 5)] >> (nb & 31)) & 1)))
+            if (!filtered && kind == KD_CONS
+                && (nb == NB_END
+                    || !((s_accept[(uint32_t) s_accidx[fpc] * 8 + ((uint32_t) nb >> 5)] >> (nb & 31)) & 1)))
             {
                 continue;               /* would be dropped by the next step */
             }
@@ -194,7 +278,7 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
             c.tag(fpc, hold);
             if (kind == KD_MATCH && want_done) {
                 c.derive(c.MAT, parent, mask, pos);
-                matched_id = 0;       /* one regex */
+                matched_id = (int32_t) s_regex[fpc];
                 return 1;
             }
             if (n >= capn) {
@@ -239,7 +323,7 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
             input = buf + start;
             size = (int32_t) (end - start);
             sp = start_hint ? start_hint[line] : 0;
-            c.m_cur = c.m_prev = 0;
+            c.marks_reset();
             overflow = false;
             matched = false;
             matched_id = 0;
@@ -253,8 +337,7 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
 
         bool done = overflow || sp > size || ncl == 0;
         if (!done) {
-            c.m_prev = c.m_cur;         /* ctx->tag++ */
-            c.m_cur = 0;
+            c.marks_advance();          /* ctx->tag++ */
             const bool at_end = (sp == size);
             const uint32_t byte = at_end ? 0 : input[sp];
             const bool cur_word = !at_end && isword(byte);
@@ -318,9 +401,9 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
                     for (int j = 0; j < ncw; j++) {
                         c.w(c.MAT + j) = c.w(tc + j);
                     }
-                    matched_id = 0;
+                    matched_id = (int32_t) s_regex[pc];
                     got_match = true;
-                } else if (!at_end && ((s_accept[pc * 8 + (byte >> 5)] >> (byte & 31)) & 1)) {
+                } else if (!at_end && ((s_accept[(uint32_t) s_accidx[pc] * 8 + (byte >> 5)] >> (byte & 31)) & 1)) {
                     const int r = append_closure(pc, sp + 1, tc, nl_pc, nl_cap, c.K, nnl, false, true);
                     if (r < 0) {
                         overflow = true;
@@ -349,9 +432,11 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
             if (overflow) {
                 rc[line] = SRE_K_RETRY;
             } else if (matched) {
+                /* prepare_matched_captures :945-989: the matched regex's slots, the rest -1 */
+                const uint32_t cnt = pk.slot_ofs[matched_id + 1] - pk.slot_ofs[matched_id];
                 rc[line] = matched_id;
                 for (uint32_t i = 0; i < ovec_slots; i++) {
-                    ov[i] = i < pk.nslots ? (int64_t) c.cap_get(c.MAT, i) : -1;
+                    ov[i] = i < cnt ? (int64_t) c.cap_get(c.MAT, i) : -1;
                 }
             } else {
                 rc[line] = SRE_K_DECLINED;
@@ -366,19 +451,18 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
 
 size_t table_smem_bytes(const sre_dev_pike_t &pk, bool c16, int K, int H)
 {
-    const uint32_t len = pk.clo_npark, nofs = 3 * (len + 2);
-    const size_t table_words = pk.clo_nent + len * 8 + (nofs * 2 + len + 3) / 4;
-    const int ncw = c16 ? (int) (pk.nslots + 1) >> 1 : (int) pk.nslots;
-    const size_t lane_words = 2 * ncw + 2 * K * (1 + ncw) + H * (1 + ncw);
-    return (table_words + lane_words * TB) * 4;
+    const bool big = pk.clo_npark > 64;
+    const int ncw = c16 ? (int) (pk.max_slots + 1) >> 1 : (int) pk.max_slots;
+    const size_t lane_words = 2 * ncw + 2 * K * (1 + ncw) + H * (1 + ncw)
+                              + (big ? 2 * ((pk.clo_npark + 31) >> 5) : 0);
+    return (table_words(pk) + lane_words * TB) * 4;
 }
 
 }  // namespace
 
 bool sre_pike_table_applicable(const sre_dev_pike_t &pk)
 {
-    return pk.clo_nent != 0 && pk.nregexes == 1 && pk.clo_npark <= 64 && pk.nslots <= 16
-           && table_smem_bytes(pk, false, 8, 4) <= 200 * 1024;
+    return pk.clo_nent != 0 && pk.max_slots <= 16 && table_smem_bytes(pk, false, 32, 4) <= 200 * 1024;
 }
 
 cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, const int64_t *offsets,
@@ -401,6 +485,7 @@ cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, 
     }
     /* 16-bit capture offsets when every line is shorter than 32 KB */
     const bool c16 = offsets == nullptr && linelen < 32767;
+    const bool big = pk.clo_npark > 64;
     const size_t smem = table_smem_bytes(pk, c16, K, H);
     size_t per_sm = (227 * 1024) / (smem + 1024);
     if (per_sm > 16) {
@@ -411,22 +496,20 @@ cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, 
     if (grid > cap) {
         grid = cap;
     }
-    static bool opted[2] = { false, false };
-    if (!opted[c16]) {
-        cudaError_t e = c16
-            ? cudaFuncSetAttribute(k_pike_table<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
-            : cudaFuncSetAttribute(k_pike_table<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    void (*kern)(sre_dev_pike_t, const uint8_t *, const int64_t *, size_t, size_t, size_t, sre_line_list_t,
+                 const int32_t *, int32_t *, int64_t *, uint32_t, int, int, int) =
+        c16 ? (big ? k_pike_table<true, true> : k_pike_table<true, false>)
+            : (big ? k_pike_table<false, true> : k_pike_table<false, false>);
+    static bool opted[4] = { false, false, false, false };
+    const int which = (c16 ? 2 : 0) + (big ? 1 : 0);
+    if (!opted[which]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) {
             return e;
         }
-        opted[c16] = true;
+        opted[which] = true;
     }
-    if (c16) {
-        k_pike_table<true><<<(unsigned) grid, TB, smem, stream>>>(pk, buf, offsets, nlines, pitch, linelen, lines,
-                                                                 start, rc, ovec, ovec_slots, K, H, retry_only);
-    } else {
-        k_pike_table<false><<<(unsigned) grid, TB, smem, stream>>>(pk, buf, offsets, nlines, pitch, linelen, lines,
-                                                                  start, rc, ovec, ovec_slots, K, H, retry_only);
-    }
+    kern<<<(unsigned) grid, TB, smem, stream>>>(pk, buf, offsets, nlines, pitch, linelen, lines, start, rc, ovec,
+                                               ovec_slots, K, H, retry_only);
     return cudaGetLastError();
 }

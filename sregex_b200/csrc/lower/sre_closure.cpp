@@ -123,18 +123,24 @@ bool sre_build_start_closure(const sre_program_t *prog, const std::vector<uint16
 }
 
 /*
- * Closure tables for k_pike_table: for every instruction a thread can be
- * parked on (numbered 0 .. npark-1 in pc order; P == npark is the start), what
- * add_thread(pc + 1) appends when
- * run on its own -- the walk of sre_vm_pike.c:756-942 (x before y, revisited-
- * SPLIT rule :770-786, SAVE undone on the way back) with `\A` and `^` decided
- * by the look-behind context: 0 = at offset 0, 1 = after a newline, 2 =
- * elsewhere.  Entry = parked number | (slots SAVEd on the path) << 16.
+ * Closure tables (see sre_closure.h): the walk of sre_vm_pike.c:756-942 (x
+ * before y, revisited-SPLIT rule :770-786, SAVE undone on the way back) run on
+ * its own from every instruction a thread can be parked on.
  */
 
-static void closure_walk(const sre_program_t *prog, const std::vector<int32_t> &park, int32_t pc0, int ctx,
-    std::vector<uint32_t> &out)
+namespace {
+
+struct walk_env_t {
+    const sre_program_t          *prog;
+    const std::vector<int32_t>   *park;
+    const std::vector<uint16_t>  *pc_regex;
+    const std::vector<uint32_t>  *slot_ofs;
+};
+
+/* false: a SAVE outside the 16-slot window of its regex */
+bool closure_walk(const walk_env_t &env, int32_t pc0, int ctx, std::vector<uint32_t> &out)
 {
+    const sre_program_t *prog = env.prog;
     struct item_t { int32_t kind, pc; uint32_t mask; };
     std::vector<item_t> stack;
     std::vector<uint8_t> seen(prog->len, 0);
@@ -171,8 +177,12 @@ static void closure_walk(const sre_program_t *prog, const std::vector<int32_t> &
                 continue;
             }
             if (in.opcode == SRE_OPCODE_SAVE) {
+                const uint32_t rel = (uint32_t) in.v - (*env.slot_ofs)[(*env.pc_regex)[pc]];
+                if (rel >= 16) {
+                    return false;
+                }
                 stack.push_back({ 0, 0, mask });
-                mask |= 1u << in.v;
+                mask |= 1u << rel;
                 pc++;
                 continue;
             }
@@ -190,17 +200,42 @@ static void closure_walk(const sre_program_t *prog, const std::vector<int32_t> &
                 pc++;
                 continue;
             }
-            out.push_back((uint32_t) park[pc] | (mask << 16));      /* parked */
+            out.push_back((uint32_t) (*env.park)[pc] | (mask << 16));       /* parked */
             break;
         }
     }
+    return true;
 }
 
-bool sre_build_closure_table(const sre_program_t *prog, sre_closure_table_t &T)
+}  // namespace
+
+bool sre_build_closure_table(const sre_program_t *prog, uint32_t max_park, sre_closure_table_t &T)
 {
     const uint32_t len = prog->len;
-    if (prog->nregexes != 1 || 2 * (prog->multi_ncaps[0] + 1) > 16) {
+    if (prog->nregexes == 0 || prog->nregexes > 65535) {
         return false;
+    }
+    /* the regex that owns a pc (code regions end at their MATCH) and its slots */
+    std::vector<uint32_t> slot_ofs(prog->nregexes + 1, 0);
+    for (sre_uint_t i = 0; i < prog->nregexes; i++) {
+        const uint32_t cnt = 2 * (uint32_t) (prog->multi_ncaps[i] + 1);
+        if (cnt > 16) {
+            return false;
+        }
+        if (cnt > T.max_slots) {
+            T.max_slots = cnt;
+        }
+        slot_ofs[i + 1] = slot_ofs[i] + cnt;
+    }
+    std::vector<uint16_t> pc_regex(len + 1, 0);
+    {
+        uint32_t r = 0;
+        for (uint32_t pc = 0; pc < len; pc++) {
+            pc_regex[pc] = (uint16_t) (r < prog->nregexes ? r : prog->nregexes - 1);
+            if (prog->insts[pc].opcode == SRE_OPCODE_MATCH) {
+                r++;
+            }
+        }
     }
     /* number the instructions that can hold a thread */
     std::vector<int32_t> park(len, -1);
@@ -235,19 +270,27 @@ bool sre_build_closure_table(const sre_program_t *prog, sre_closure_table_t &T)
             park[pc] = (int32_t) park_pc.size();
             park_pc.push_back((int32_t) pc);
             T.kind.push_back(kind);
+            T.regex.push_back(in.opcode == SRE_OPCODE_MATCH ? (uint16_t) in.v : pc_regex[pc]);
         }
     }
     const uint32_t np = (uint32_t) park_pc.size();
-    if (np == 0 || np > 64) {
+    if (np == 0 || np > max_park || np > 60000) {
         return false;
     }
     T.npark = np;
-    T.accept.assign((size_t) np * 8, 0);
+    if (len >= 3 && prog->insts[0].opcode == SRE_OPCODE_SPLIT && prog->insts[0].y == 1
+        && prog->insts[1].opcode == SRE_OPCODE_ANY)
+    {
+        T.p_any = park[1];
+    }
+    /* byte sets of the consuming instructions, identical ones shared */
+    T.acc_idx.assign(np, 0);
     for (uint32_t P = 0; P < np; P++) {
         const sre_instruction_t &in = prog->insts[park_pc[P]];
         if (T.kind[P] != 0) {
             continue;
         }
+        uint32_t set[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
         for (uint32_t b = 0; b < 256; b++) {
             bool hit;
             if (in.opcode == SRE_OPCODE_CHAR) {
@@ -265,21 +308,39 @@ bool sre_build_closure_table(const sre_program_t *prog, sre_closure_table_t &T)
                 }
             }
             if (hit) {
-                T.accept[(size_t) P * 8 + (b >> 5)] |= 1u << (b & 31);
+                set[b >> 5] |= 1u << (b & 31);
             }
         }
+        uint32_t k = 0;
+        for (; k < T.nsets; k++) {
+            if (memcmp(&T.accept[(size_t) k * 8], set, sizeof(set)) == 0) {
+                break;
+            }
+        }
+        if (k == T.nsets) {
+            T.accept.insert(T.accept.end(), set, set + 8);
+            T.nsets++;
+        }
+        T.acc_idx[P] = (uint16_t) k;
     }
+    if (T.nsets == 0) {
+        T.accept.assign(8, 0);
+        T.nsets = 1;
+    }
+
+    const walk_env_t env = { prog, &park, &pc_regex, &slot_ofs };
     T.ofs.assign((size_t) 3 * (np + 2), 0);
     const int nctx = T.ctx_dep ? 3 : 1;
     for (int ctx = 0; ctx < nctx; ctx++) {
         for (uint32_t P = 0; P <= np; P++) {
             T.ofs[(size_t) ctx * (np + 2) + P] = (uint16_t) T.ent.size();
+            bool ok = true;
             if (P == np) {
-                closure_walk(prog, park, 0, ctx, T.ent);
+                ok = closure_walk(env, 0, ctx, T.ent);
             } else if (T.kind[P] != 1) {            /* nothing follows a MATCH */
-                closure_walk(prog, park, park_pc[P] + 1, ctx, T.ent);
+                ok = closure_walk(env, park_pc[P] + 1, ctx, T.ent);
             }
-            if (T.ent.size() > 8192) {
+            if (!ok || T.ent.size() > 60000) {
                 return false;
             }
         }
@@ -290,6 +351,39 @@ bool sre_build_closure_table(const sre_program_t *prog, sre_closure_table_t &T)
             T.ofs[(size_t) ctx * (np + 2) + P] = T.ofs[P];
         }
     }
-    return !T.ent.empty();
-}
+    if (T.ent.empty()) {
+        return false;
+    }
 
+    /* the start closure by next byte, when it is long enough to matter */
+    T.bofs.assign((size_t) 3 * 257, 0);
+    const uint32_t s0 = T.ofs[np], s1 = T.ofs[np + 1];
+    if (s1 - s0 > 8) {
+        for (int ctx = 0; ctx < nctx; ctx++) {
+            const uint32_t e0 = T.ofs[(size_t) ctx * (np + 2) + np], e1 = T.ofs[(size_t) ctx * (np + 2) + np + 1];
+            for (uint32_t b = 0; b < 256; b++) {
+                T.bofs[(size_t) ctx * 257 + b] = (uint16_t) T.bent.size();
+                for (uint32_t e = e0; e < e1; e++) {
+                    const uint32_t P = T.ent[e] & 0xffff;
+                    if (T.kind[P] == 0
+                        && !((T.accept[(size_t) T.acc_idx[P] * 8 + (b >> 5)] >> (b & 31)) & 1))
+                    {
+                        continue;
+                    }
+                    T.bent.push_back(T.ent[e]);
+                }
+                if (T.bent.size() > 60000) {
+                    T.bent.clear();
+                    return true;            /* tables are fine, just no buckets */
+                }
+            }
+            T.bofs[(size_t) ctx * 257 + 256] = (uint16_t) T.bent.size();
+        }
+        for (int ctx = nctx; ctx < 3; ctx++) {
+            for (uint32_t b = 0; b <= 256; b++) {
+                T.bofs[(size_t) ctx * 257 + b] = T.bofs[b];
+            }
+        }
+    }
+    return true;
+}

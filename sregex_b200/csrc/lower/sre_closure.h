@@ -32,24 +32,39 @@ bool sre_build_start_closure(const sre_program_t *prog, const std::vector<uint16
     const std::vector<uint32_t> &slot_ofs, std::vector<uint32_t> &ofs, std::vector<sre_start_ent_t> &ents);
 
 /*
- * Closure tables of a small single-regex program.  The instructions a thread
+ * Closure tables of a program (one regex or a set).  The instructions a thread
  * can be parked on (consuming, look-ahead assertion, MATCH) are numbered
  * 0 .. npark-1 in pc order.  Closure (ctx, P) = ent[ofs[ctx * (npark + 2) + P]
  * .. ofs[ctx * (npark + 2) + P + 1]) = what add_thread(pc(P) + 1) appends when
  * run on its own (P == npark: add_thread(0)), with `\A` and `^` decided by the
  * look-behind context ctx: 0 = at offset 0, 1 = after a newline, 2 = elsewhere.
- * Entry = parked number | (slots SAVEd on the path) << 16.
+ * Entry = parked number | (slots SAVEd on the path) << 16, the slots counted
+ * from the first slot of the regex that owns the parked instruction (a thread
+ * only ever carries the slots of its own regex).
+ *
+ * The start closure (P == npark, and P == p_any, the ".*?" thread, whose
+ * closure is the same list) is also given bucketed by the next byte when it is
+ * long: bent[bofs[ctx * 257 + b] .. bofs[ctx * 257 + b + 1]) = its entries that
+ * are not consuming instructions unable to take byte b.
  */
 struct sre_closure_table_t {
     std::vector<uint32_t> ent;
     std::vector<uint16_t> ofs;
-    std::vector<uint32_t> accept;       /* [npark][8]: bytes a consuming instruction takes */
+    std::vector<uint32_t> accept;       /* [nsets][8]: distinct byte sets */
+    std::vector<uint16_t> acc_idx;      /* [npark]: byte set of a consuming instruction */
     std::vector<uint8_t>  kind;         /* [npark]: 0 consuming, 1 MATCH, 2 \z, 3 $, 4 \B, 5 \b */
+    std::vector<uint16_t> regex;        /* [npark]: owning regex */
     std::vector<int32_t>  park_pc;      /* [npark]: its pc */
+    std::vector<uint32_t> bent;         /* bucketed start closure (may be empty) */
+    std::vector<uint16_t> bofs;         /* [3][257] */
     uint32_t              npark = 0;
+    uint32_t              nsets = 0;
+    uint32_t              max_slots = 0;        /* slots of the largest regex (<= 16) */
+    int32_t               p_any = -1;           /* parked number of the ".*?" ANY (pc 1), -1: none */
     bool                  ctx_dep = false;      /* program has \A or ^ */
 };
 
-bool sre_build_closure_table(const sre_program_t *prog, sre_closure_table_t &T);
+/* max_park: give up beyond that many parked instructions */
+bool sre_build_closure_table(const sre_program_t *prog, uint32_t max_park, sre_closure_table_t &T);
 
 #endif

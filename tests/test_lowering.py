@@ -151,13 +151,13 @@ def test_random_regex_fuzz_lowering_vs_live_reference(oracle, ref, lc):
 
 def test_closure_table_pike_golden(golden, oracle, lc):
     """the closure tables of sre_closure.cpp, run by the CPU model of
-    k_pike_table, reproduce the reference's Pike rc + ovector on every
-    single-regex golden block -- from offset 0 and from the DFA start hint"""
-    checked = hinted = 0
+    k_pike_table, reproduce the reference's Pike rc (regex id) + ovector on
+    every golden block, multi-regex sets included -- from offset 0 and from the
+    DFA start hint"""
+    checked = hinted = multi = 0
     for b in runnable(golden):
-        if b["multi"]:
-            continue
-        p = oracle.compile(b["regexes_b"], b["flags"], multi=False)
+        p = oracle.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        multi += bool(b["multi"])
         s = b["subject_b"]
         got = _table_pike(lc, p, s)
         if got is not None:
@@ -171,7 +171,38 @@ def test_closure_table_pike_golden(golden, oracle, lc):
             if h:
                 lc.lc_destroy(h)
         p.close()
-    assert checked > 1500 and hinted > 100, (checked, hinted)
+    assert checked > 1500 and hinted > 100 and multi > 5, (checked, hinted, multi)
+
+
+def test_closure_table_pike_multi_regex_fuzz(ref, oracle, lc):
+    """random regex SETS (2-5 members, assertions and captures) x random
+    subjects: regex id and ovector slice of the closure-table Pike against the
+    reference itself (sre_vm_pike.c:945-989 prepare_matched_captures)"""
+    import random
+    rng = random.Random(4242)
+    atoms = ["a", "b", "ab", " ", "_", ".", "^", "$", "\\b", "\\B", "\\A", "\\z", "|", "(a)", "(b*)", "(?:ab)+",
+             "*", "+", "?", "+?", "{1,2}", "[ab]", "[^a]", "\\w", "\\d", "1", "(\\w+)", "\\n"]
+    alphabet = b"ab \n_1."
+    tried = 0
+    for _ in range(1500):
+        n = rng.randrange(2, 6)
+        rxs = ["".join(rng.choice(atoms) for _ in range(rng.randrange(1, 6))).encode() for _ in range(n)]
+        try:
+            pr = ref.compile(rxs, 0, multi=True)
+        except capi.SreSyntaxError:
+            continue
+        po = oracle.compile(rxs, 0, multi=True)
+        if _table_pike(lc, po, b"") is None:
+            po.close()
+            pr.close()
+            continue
+        tried += 1
+        for _ in range(6):
+            s = bytes(rng.choice(alphabet) for _ in range(rng.randrange(0, 14)))
+            assert _table_pike(lc, po, s) == ref.pike(pr, s), (rxs, s)
+        po.close()
+        pr.close()
+    assert tried > 500
 
 
 def test_closure_table_pike_fuzz_vs_live_reference(ref, oracle, lc):
@@ -202,3 +233,19 @@ def test_closure_table_pike_fuzz_vs_live_reference(ref, oracle, lc):
         po.close()
         pr.close()
     assert tried > 1000
+
+
+def test_closure_table_pike_64_pattern_set(oracle, lc):
+    """the C4 pattern set (64 regexes, bucketed start closure) over log lines:
+    matched id + ovector of the closure-table Pike == the oracle's Pike"""
+    from sregex_b200 import corpus
+    po = oracle.compile(corpus.multi_pattern_set(64), 0, multi=True)
+    lines = corpus.log_lines(300, 1024).numpy()
+    hits = 0
+    for i in range(300):
+        s = bytes(lines[i])
+        want = oracle.pike(po, s)
+        assert _table_pike(lc, po, s) == want, i
+        hits += want[0] >= 0
+    assert hits > 50
+    po.close()
