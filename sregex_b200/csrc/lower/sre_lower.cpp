@@ -385,23 +385,91 @@ bool build_dfa(const sre_nfa_t &nfa, uint32_t max_states, sre_dfa_t &dfa)
         }
     }
 
-    const uint32_t D = (uint32_t) sets.size();
-    dfa.nstates = D;
-    dfa.start = 0;
-    dfa.acc = ACC;
-    dfa.fin.assign(D, 0);
-    dfa.fin[ACC] = 1;
-    for (uint32_t d = 0; d < D; d++) {
+    /* the EOF step (mt_eof) per subset state */
+    const uint32_t D0 = (uint32_t) sets.size();
+    std::vector<uint8_t> fin0(D0, 0);
+    fin0[ACC] = 1;
+    for (uint32_t d = 0; d < D0; d++) {
         if (d == ACC) {
             continue;
         }
         for (uint32_t w = 0; w < W; w++) {
             if (sets[d][w] & nfa.mt_eof[w]) {
-                dfa.fin[d] = 1;
+                fin0[d] = 1;
                 break;
             }
         }
     }
+
+    /*
+     * Minimise (Moore refinement).  Two states are merged when no input tells
+     * them apart by: being ACC (kept on its own: kernels stop / report at the
+     * step that enters it), the EOF verdict, and per byte class the successor
+     * block and the restart flag of the transition (the Pike start hint reads
+     * it).  Block of state 0 stays 0, ACC stays 1.
+     */
+    std::vector<uint32_t> block(D0);
+    uint32_t nblocks = 0;
+    {
+        for (uint32_t d = 0; d < D0; d++) {
+            block[d] = d == ACC ? 1 : (fin0[d] == fin0[0] ? 0 : 2);
+        }
+        nblocks = 3;
+        /* state 0 and ACC are visited first: their blocks keep the numbers 0 and 1 */
+        std::vector<uint32_t> order;
+        order.push_back(0);
+        order.push_back(ACC);
+        for (uint32_t d = 0; d < D0; d++) {
+            if (d != 0 && d != ACC) {
+                order.push_back(d);
+            }
+        }
+        std::vector<uint32_t> sig(C + 1), newblock(D0);
+        for (;;) {
+            std::map<std::vector<uint32_t>, uint32_t> seen;
+            uint32_t nb = 0;
+            for (uint32_t d : order) {
+                sig[0] = block[d];
+                for (uint32_t c = 0; c < C; c++) {
+                    sig[c + 1] = block[trans[(size_t) d * C + c]] * 2 + restart[(size_t) d * C + c];
+                }
+                std::map<std::vector<uint32_t>, uint32_t>::iterator it = seen.find(sig);
+                if (it == seen.end()) {
+                    newblock[d] = nb;
+                    seen[sig] = nb++;
+                } else {
+                    newblock[d] = it->second;
+                }
+            }
+            const bool stable = (nb == nblocks);
+            block = newblock;
+            nblocks = nb;
+            if (stable) {
+                break;
+            }
+        }
+    }
+    if (nblocks < D0) {
+        std::vector<uint16_t> t2((size_t) nblocks * C, 0);
+        std::vector<uint8_t> r2((size_t) nblocks * C, 0), f2(nblocks, 0);
+        for (uint32_t d = 0; d < D0; d++) {
+            const uint32_t bd = block[d];
+            f2[bd] = fin0[d];
+            for (uint32_t c = 0; c < C; c++) {
+                t2[(size_t) bd * C + c] = (uint16_t) block[trans[(size_t) d * C + c]];
+                r2[(size_t) bd * C + c] = restart[(size_t) d * C + c];
+            }
+        }
+        trans.swap(t2);
+        restart.swap(r2);
+        fin0.swap(f2);
+    }
+
+    const uint32_t D = nblocks < D0 ? nblocks : D0;
+    dfa.nstates = D;
+    dfa.start = 0;
+    dfa.acc = ACC;
+    dfa.fin.assign(fin0.begin(), fin0.begin() + D);
 
     if (D <= 128) {
         dfa.h256.assign((size_t) 256 * 256, 0);
