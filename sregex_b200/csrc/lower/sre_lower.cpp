@@ -424,23 +424,42 @@ bool build_dfa(const sre_nfa_t &nfa, uint32_t max_states, sre_dfa_t &dfa)
                 order.push_back(d);
             }
         }
-        std::vector<uint32_t> sig(C + 1), newblock(D0);
+        /* signature of d under the current blocks: (block, per class successor block + flag);
+         * states are bucketed by a hash of it and compared in full within a bucket */
+        auto sig_at = [&](uint32_t d, uint32_t c) -> uint32_t {
+            return c == 0 ? block[d]
+                          : block[trans[(size_t) d * C + c - 1]] * 2 + restart[(size_t) d * C + c - 1];
+        };
+        std::vector<uint32_t> newblock(D0), rep;
+        std::unordered_map<uint64_t, std::vector<uint32_t> > buckets;
         for (;;) {
-            std::map<std::vector<uint32_t>, uint32_t> seen;
-            uint32_t nb = 0;
+            buckets.clear();
+            rep.clear();
             for (uint32_t d : order) {
-                sig[0] = block[d];
-                for (uint32_t c = 0; c < C; c++) {
-                    sig[c + 1] = block[trans[(size_t) d * C + c]] * 2 + restart[(size_t) d * C + c];
+                uint64_t h = 1469598103934665603ull;
+                for (uint32_t c = 0; c <= C; c++) {
+                    h = (h ^ sig_at(d, c)) * 1099511628211ull;
                 }
-                std::map<std::vector<uint32_t>, uint32_t>::iterator it = seen.find(sig);
-                if (it == seen.end()) {
-                    newblock[d] = nb;
-                    seen[sig] = nb++;
-                } else {
-                    newblock[d] = it->second;
+                std::vector<uint32_t> &cands = buckets[h];
+                uint32_t found = 0xffffffffu;
+                for (uint32_t b : cands) {
+                    bool same = true;
+                    for (uint32_t c = 0; c <= C && same; c++) {
+                        same = sig_at(rep[b], c) == sig_at(d, c);
+                    }
+                    if (same) {
+                        found = b;
+                        break;
+                    }
                 }
+                if (found == 0xffffffffu) {
+                    found = (uint32_t) rep.size();
+                    rep.push_back(d);
+                    cands.push_back(found);
+                }
+                newblock[d] = found;
             }
+            const uint32_t nb = (uint32_t) rep.size();
             const bool stable = (nb == nblocks);
             block = newblock;
             nblocks = nb;
