@@ -141,7 +141,12 @@ SRE_API int sre_cuda_pike_exec_lines_host(sre_cuda_program_t *cp,
 /* Tuning / introspection */
 SRE_API void sre_cuda_set_variant(int variant);     /* tile shape of DFA_TILED   */
 SRE_API void sre_cuda_set_l2_promotion(int mode);   /* TMA L2 promotion: 0..3    */
-SRE_API void sre_cuda_set_pike_general_only(int on);/* 1: skip the smem Pike tier */
+/* Pike tier used by sre_cuda_pike_exec_lines (tests): 0 = closure-table kernel,
+ * then the general kernel for what it gives up on (default); 1 = general kernel
+ * only; 2 = walking shared-memory kernel instead of the table kernel           */
+SRE_API void sre_cuda_set_pike_general_only(int mode);
+/* which of those the last sre_cuda_pike_exec_lines call used (0 / 1 / 2), -1: none yet */
+SRE_API int sre_cuda_pike_last_tier(void);
 SRE_API void sre_cuda_set_stream_piece(int bytes);  /* stream scan piece: 1024..8192 */
 SRE_API long sre_cuda_launch_count(int reset);      /* kernels launched so far   */
 SRE_API int sre_cuda_device_available(void);        /* 1 if a CUDA device works  */

@@ -34,6 +34,7 @@ namespace {
 std::atomic<long>   g_launches(0);
 int                 g_variant = 0;
 int                 g_pike_general_only = 0;    /* tests: force k_pike_lines */
+std::atomic<int>    g_pike_last_tier{-1};       /* tier of the last sre_cuda_pike_exec_lines */
 thread_local char   g_err[256] = "";
 
 const uint32_t MAX_DFA_STATES = 4096;
@@ -552,6 +553,7 @@ SRE_API int sre_cuda_device_available(void) { return device_ok() ? 1 : 0; }
 SRE_API const char *sre_cuda_last_error(void) { return g_err; }
 SRE_API void sre_cuda_set_variant(int variant) { g_variant = variant; }
 SRE_API void sre_cuda_set_pike_general_only(int on) { g_pike_general_only = on; }
+SRE_API int sre_cuda_pike_last_tier(void) { return g_pike_last_tier.load(); }
 SRE_API void sre_cuda_set_stream_piece(int bytes) { sre_stream_set_piece_bytes((uint32_t) bytes); }
 SRE_API void sre_cuda_set_l2_promotion(int mode) { sre_dev_set_l2_promotion(mode); }
 
@@ -723,25 +725,29 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         lines.count = count;
     }
     const size_t nctx = cp->pike_nctx < nlines ? cp->pike_nctx : nlines;
-    if (sre_pike_table_applicable(cp->pike) && linelen < (1ull << 31) && g_pike_general_only == 0) {
-        /* closure-table kernel first; the general kernel re-runs what it gave up on */
-        static int ek1 = -1, eh1 = 2, ek2 = 0, eh2 = 0;
-        if (ek1 < 0) {          /* SRE_PIKE_TABLE_K="K1,H1[,K2,H2]": list capacities of the two passes (tuning) */
-            const char *e = getenv("SRE_PIKE_TABLE_K");
-            ek1 = 0;
-            if (e) {
-                sscanf(e, "%d,%d,%d,%d", &ek1, &eh1, &ek2, &eh2);
-            }
+    /* closure-table kernel: list capacities of its two passes.  Small lists
+     * first (more resident warps), then the lines that needed more; a set of
+     * regexes can have as many live threads as members share a prefix. */
+    static int ek1 = -1, eh1 = 2, ek2 = 0, eh2 = 0;
+    if (ek1 < 0) {              /* SRE_PIKE_TABLE_K="K1,H1[,K2,H2]" (tuning) */
+        const char *e = getenv("SRE_PIKE_TABLE_K");
+        ek1 = 0;
+        if (e) {
+            sscanf(e, "%d,%d,%d,%d", &ek1, &eh1, &ek2, &eh2);
         }
-        /* small lists first (more resident warps), then the lines that needed more.
-         * A set of regexes can have as many live threads as members share a prefix. */
-        const bool big = cp->pike.nregexes > 1 || cp->pike.clo_npark > 64;
-        const int k1 = ek1 > 0 ? ek1 : (big ? 12 : 5), h1 = ek1 > 0 ? eh1 : 2;
-        int k2 = ek2 > 0 ? ek2 : (big ? 32 : 8);
-        const int h2 = ek2 > 0 ? eh2 : 4;
-        if ((uint32_t) k2 > cp->pike.clo_npark) {
-            k2 = (int) cp->pike.clo_npark;
-        }
+    }
+    const bool big = cp->pike.nregexes > 1 || cp->pike.clo_npark > 64;
+    const int k1 = ek1 > 0 ? ek1 : (big ? 12 : 5), h1 = ek1 > 0 ? eh1 : 2;
+    int k2 = ek2 > 0 ? ek2 : (big ? 32 : 8);
+    const int h2 = ek2 > 0 ? eh2 : 4;
+    if (cp->pike.clo_npark && (uint32_t) k2 > cp->pike.clo_npark) {
+        k2 = (int) cp->pike.clo_npark;
+    }
+    if (sre_pike_table_applicable(cp->pike, k2 > k1 ? k2 : k1, h2) && linelen < (1ull << 31)
+        && g_pike_general_only == 0)
+    {
+        /* the general kernel re-runs what the table kernel gave up on */
+        g_pike_last_tier = 0;
         err = sre_launch_pike_table(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
                                     dev_rc, dev_ovec, (uint32_t) ovec_slots, k1, h1, 0, st, &launches);
         if (err == cudaSuccess && (k1 < k2 || h1 < h2)) {
@@ -755,6 +761,7 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         }
     } else if (sre_pike_small_applicable(cp->pike) && linelen < (1ull << 31) && g_pike_general_only != 1) {
         /* shared-memory kernel first; the general kernel re-runs what it gave up on */
+        g_pike_last_tier = 2;
         err = sre_launch_pike_small(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
                                     dev_rc, dev_ovec, (uint32_t) ovec_slots, st, &launches);
         if (err == cudaSuccess) {
@@ -763,6 +770,7 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
                                         nctx < 16384 ? nctx : 16384, 1, st, &launches);
         }
     } else {
+        g_pike_last_tier = 1;
         err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
                                     dev_rc, dev_ovec, (uint32_t) ovec_slots, cp->pike_scratch, nctx, 0, st,
                                     &launches);

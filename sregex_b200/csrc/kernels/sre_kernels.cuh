@@ -175,7 +175,7 @@ cudaError_t sre_launch_pike_small(const sre_dev_pike_t &pk, const uint8_t *buf,
 /* closure-table Pike for small single-regex programs (sre_pike_table.cu);
  * same contract as sre_launch_pike_small.  K threads per list, H pending
  * look-ahead closures per context; retry_only: only lines with rc RETRY        */
-bool sre_pike_table_applicable(const sre_dev_pike_t &pk);
+bool sre_pike_table_applicable(const sre_dev_pike_t &pk, int K, int H);   /* with lists of K / H */
 cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf,
     const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen,
     sre_line_list_t lines, const int32_t *start, int32_t *rc, int64_t *ovec,

@@ -130,6 +130,12 @@ struct lane_t {
     /* dst vector <- src vector (src < 0: all -1) with the slots of `mask` set to pos */
     __device__ __forceinline__ void derive(int dst, int src, uint32_t mask, int32_t pos)
     {
+        if (mask == 0 && src >= 0) {        /* the common case: nothing SAVEd on the way */
+            for (int j = 0; j < ncw; j++) {
+                w(dst + j) = w(src + j);
+            }
+            return;
+        }
         if (C16) {
             const uint32_t p16 = (uint32_t) pos & 0xffff;
             for (int j = 0; j < ncw; j++) {
@@ -460,9 +466,9 @@ size_t table_smem_bytes(const sre_dev_pike_t &pk, bool c16, int K, int H)
 
 }  // namespace
 
-bool sre_pike_table_applicable(const sre_dev_pike_t &pk)
+bool sre_pike_table_applicable(const sre_dev_pike_t &pk, int K, int H)
 {
-    return pk.clo_nent != 0 && pk.max_slots <= 16 && table_smem_bytes(pk, false, 32, 4) <= 200 * 1024;
+    return pk.clo_nent != 0 && pk.max_slots <= 16 && table_smem_bytes(pk, false, K, H) <= 200 * 1024;
 }
 
 cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, const int64_t *offsets,

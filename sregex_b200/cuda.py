@@ -47,6 +47,7 @@ def lib():
             "sre_cuda_set_variant": (None, [C.c_int]),
             "sre_cuda_set_l2_promotion": (None, [C.c_int]),
             "sre_cuda_set_pike_general_only": (None, [C.c_int]),
+            "sre_cuda_pike_last_tier": (C.c_int, []),
             "sre_cuda_set_stream_piece": (None, [C.c_int]),
             "sre_cuda_launch_count": (C.c_long, [C.c_int]),
             "sre_cuda_device_available": (C.c_int, []),

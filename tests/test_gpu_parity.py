@@ -253,6 +253,27 @@ def test_multi_regex_64_patterns_vs_oracle(cu):
     rc2, ov2 = prog.pike_lines(dev, n, 1024, 1024)          # internal gate
     assert torch.equal(rc, rc2) and torch.equal(ov, ov2)
     assert len(set(want_rc.tolist())) > 8
+    # the set runs on the closure-table kernel, not on the general fallback
+    assert cu.lib().L.sre_cuda_pike_last_tier() == 0
+    # ... and the general kernel alone gives the same rows
+    cu.lib().L.sre_cuda_set_pike_general_only(1)
+    try:
+        rc3, ov3 = prog.pike_lines(dev, n, 1024, 1024)
+        assert cu.lib().L.sre_cuda_pike_last_tier() == 1
+    finally:
+        cu.lib().L.sre_cuda_set_pike_general_only(0)
+    assert torch.equal(rc, rc3) and torch.equal(ov, ov3)
+
+
+def test_pike_tier_selection(cu):
+    """the configurations the bench reports must run on the fast tier: C3 (4
+    groups, 10 slots, 1 KB lines) on the closure-table kernel"""
+    n = 256
+    dev = corpus.log_lines(n, 1024).cuda()
+    prog = cu.CudaProgram(corpus.C3_REGEX)
+    rc, _ = prog.pike_lines(dev, n, 1024, 1024)
+    assert cu.lib().L.sre_cuda_pike_last_tier() == 0
+    assert int((rc == 0).sum()) == n
 
 
 def test_stream_scan_vs_oracle(cu):
