@@ -332,6 +332,17 @@ def main():
                     lambda: p3.pike_lines(dev, n, PITCH, PITCH, out_rc=prc, out_ovec=pov), n * PITCH)
                 extra["c3_lines"] = n
                 extra["c3_matched_lines"] = int((prc == 0).sum())
+                # ... beside the reference's Pike VM on the host cores, same rows compared
+                cores = host_cores()
+                which = "ref" if baseline.available("ref") else "oracle"
+                ns = min(n, 2048 * cores)
+                secs, crc, cov = baseline.run_lines(which, corpus.C3_REGEX, None, host[:ns].numpy(), ns, PITCH,
+                                                    PITCH, baseline.ENGINE_PIKE, nthreads=cores,
+                                                    ovec_slots=p3.nslots)
+                extra["c3_cpu_pike_gbs"] = ns * PITCH / secs / 1e9
+                extra["c3_cpu_sample_lines"] = ns
+                assert (prc[:ns].cpu().numpy() == crc).all() and (pov[:ns].cpu().numpy() == cov).all(), \
+                    "C3: GPU Pike rows differ from the CPU reference"
                 # C4: 64-pattern set: which pattern matched (Thompson gate, then Pike on the hits)
                 pm = cuda.CudaProgram(corpus.multi_pattern_set(64))
                 m = n
@@ -342,6 +353,14 @@ def main():
                     lambda: pm.pike_lines(dev, m, PITCH, PITCH, out_rc=mrc, out_ovec=mov), m * PITCH)
                 extra["c4_lines"] = m
                 extra["c4_matched_fraction"] = float((mrc >= 0).float().mean())
+                ns4 = min(n, 128 * cores)
+                secs, crc, cov = baseline.run_lines(which, corpus.multi_pattern_set(64), None, host[:ns4].numpy(),
+                                                    ns4, PITCH, PITCH, baseline.ENGINE_PIKE, nthreads=cores,
+                                                    ovec_slots=pm.nslots)
+                extra["c4_cpu_pike_gbs"] = ns4 * PITCH / secs / 1e9
+                extra["c4_cpu_sample_lines"] = ns4
+                assert (mrc[:ns4].cpu().numpy() == crc).all() and (mov[:ns4].cpu().numpy() == cov).all(), \
+                    "C4: GPU matched ids / ovectors differ from the CPU reference"
                 extra["c4_dfa_states"] = pm.info.dfa_states
                 # C5: one stream, chunk-parallel transfer-function scan (the whole resident corpus
                 # as a single stream, 64 KB reference chunks)
