@@ -254,7 +254,9 @@ k_stream_pieces(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, siz
     tile_pipeline_tma_early<1>(cons, &tmap, npieces, PIECE,
                                smem + plan.stage_ofs + (size_t) warp * 32 * 128,
                                reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES,
-                               (size_t) blockIdx.x * warps_per_block + warp,
+                               /* block-major interleave: a partial last round of
+                                * groups is spread over all SMs, not over the first few */
+                               (size_t) warp * gridDim.x + blockIdx.x,
                                (size_t) gridDim.x * warps_per_block);
 }
 
