@@ -243,6 +243,10 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
     const uint8_t *input = buf;
     int32_t size = 0, sp = 0, matched_id = 0;
     bool active = false, overflow = false, matched = false;
+    /* the ".*?" thread is not kept in the lists: it is always the last thread of
+     * a list, always takes the byte and never carries a capture, so one flag
+     * stands for it (off once a match has cut the lower-priority threads) */
+    bool any_alive = false;
     int cur = 0, ncl = 0, nnl = 0, hs = 0;
 
     /*
@@ -271,6 +275,9 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
         for (; e < e1; e++) {
             const uint32_t ent = list[e];
             const uint32_t fpc = ent & 0xffff, mask = ent >> 16;
+            if (fpc == p_any) {
+                continue;               /* the ".*?" thread itself: see any_alive */
+            }
             const uint32_t kind = s_kind[fpc];
             if (!filtered && kind == KD_CONS
                 && (nb == NB_END
@@ -334,6 +341,7 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
             matched = false;
             matched_id = 0;
             cur = 0; ncl = 0; nnl = 0; hs = 0;
+            any_alive = p_any != 0xffffffffu;
             active = true;
             /* first_buf: the initial closure at the start offset, :202-216 */
             if (append_closure(len, sp, -1, c.L0PC, c.L0CAP, c.K, ncl, false, false) < 0) {
@@ -341,7 +349,7 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
             }
         }
 
-        bool done = overflow || sp > size || ncl == 0;
+        bool done = overflow || sp > size || (ncl == 0 && !any_alive);
         if (!done) {
             c.marks_advance();          /* ctx->tag++ */
             const bool at_end = (sp == size);
@@ -420,8 +428,19 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
 
                 if (got_match) {        /* cut every lower-priority thread */
                     matched = true;
+                    any_alive = false;
                     hs = 0;
                     break;
+                }
+            }
+            /* the ".*?" thread, last in priority: takes the byte and restarts the regex */
+            if (any_alive && !at_end && !overflow) {
+                const int r = append_closure(p_any, sp + 1, -1, nl_pc, nl_cap, c.K, nnl, false, true);
+                if (r < 0) {
+                    overflow = true;
+                } else if (r == 1) {
+                    matched = true;
+                    any_alive = false;
                 }
             }
 
@@ -430,7 +449,7 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
             nnl = 0;
             hs = 0;
             sp++;
-            done = overflow || at_end || ncl == 0;
+            done = overflow || at_end || (ncl == 0 && !any_alive);
         }
 
         if (done) {
