@@ -737,7 +737,7 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         }
     }
     const bool big = cp->pike.nregexes > 1 || cp->pike.clo_npark > 64;
-    const int k1 = ek1 > 0 ? ek1 : (big ? 12 : 5), h1 = ek1 > 0 ? eh1 : 2;
+    const int k1 = ek1 > 0 ? ek1 : (big ? 12 : 4), h1 = ek1 > 0 ? eh1 : 2;
     int k2 = ek2 > 0 ? ek2 : (big ? 32 : 8);
     const int h2 = ek2 > 0 ? eh2 : 4;
     if (cp->pike.clo_npark && (uint32_t) k2 > cp->pike.clo_npark) {
