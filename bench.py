@@ -92,7 +92,7 @@ class ClockSampler(threading.Thread):
 
 def cpu_baseline_sample(lines_host, regex, cores, which):
     """reference Thompson JIT + interpreter over a bounded sample, all cores"""
-    from sregex_b200 import baseline
+    from oracle import cpu_baseline as baseline
     n = lines_host.shape[0]
     out = {}
     for name, eng in (("jit", baseline.ENGINE_JIT), ("interp", baseline.ENGINE_THOMPSON)):
@@ -111,7 +111,8 @@ def run_reference_arm(args):
     if rank != 0:
         return
     import numpy as np  # noqa: F401
-    from sregex_b200 import baseline, corpus
+    from oracle import cpu_baseline as baseline
+    from sregex_b200 import corpus
     cores = host_cores()
     which = "ref" if baseline.available("ref") else "oracle"
     engine = baseline.ENGINE_JIT if which == "ref" else baseline.ENGINE_THOMPSON
@@ -160,7 +161,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from sregex_b200 import baseline, corpus, cuda
+    from oracle import cpu_baseline as baseline
+    from sregex_b200 import corpus, cuda
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-from . import capi
+from sregex_b200 import capi
 
 ENGINE_THOMPSON, ENGINE_JIT, ENGINE_PIKE = 0, 1, 2
 

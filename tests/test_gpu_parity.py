@@ -5,7 +5,8 @@ import pytest
 import torch
 
 from conftest import runnable
-from sregex_b200 import baseline, capi, corpus
+from oracle import cpu_baseline as baseline
+from sregex_b200 import capi, corpus
 
 pytestmark = pytest.mark.gpu
 
