@@ -49,11 +49,15 @@ def measured_hbm_peak():
 
 
 class ClockSampler(threading.Thread):
-    """SM clock + throttle reasons during the timed region (NVML, 2 ms period)."""
+    """SM clock + throttle reasons during the timed region (NVML, 4 ms period).
+    Started before the warm-up steps -- the first NVML queries take the driver
+    for milliseconds and would stall kernel launches inside a short timed region
+    -- and told with mark() where the timed region begins."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.samples, self.reasons, self.stop_flag, self.max_mhz = [], set(), False, None
+        self.first = 0
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -82,10 +86,16 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.004)
+
+    def mark(self):
+        """the timed region starts now: earlier samples (but the last one) and
+        earlier throttle reasons do not count"""
+        self.first = max(0, len(self.samples) - 1)
+        self.reasons = set()
 
     def result(self):
-        s = sorted(self.samples)
+        s = sorted(self.samples[self.first:])
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
@@ -201,21 +211,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step()
-    if world > 1:           # NCCL's first collective pays its set-up cost: not part of a step
-        warm = (rc == 0).sum()
+    # the closing match count (and, at N > 1, NCCL's first collective) pay a one-off
+    # set-up cost (lazy kernel loading): not part of a step
+    warm = (rc == 0).sum()
+    if world > 1:
         dist.all_reduce(warm)
     barrier()
 
-    sampler = ClockSampler(local)
-    sampler.start()
+    while sampler.nv is not None and len(sampler.samples) < 3:
+        time.sleep(0.002)       # the sampler's first queries are over before anything is timed
     cuda.launch_count(reset=True)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
            for _ in range(args.steps)]
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     t_start.record()
     for a, b in evs:
         a.record()
