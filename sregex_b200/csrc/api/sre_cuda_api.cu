@@ -367,6 +367,12 @@ int upload(sre_cuda_program_t *cp)
     pk.clo_nbent = has_clo ? (uint32_t) clo.bent.size() : 0;
     pk.clo_nsets = has_clo ? clo.nsets : 0;
     pk.clo_p_any = has_clo && clo.p_any >= 0 ? (uint32_t) clo.p_any : 0xffffffffu;
+    pk.clo_has_hold = 0;
+    for (uint8_t k : clo.kind) {
+        if (k >= 2) {
+            pk.clo_has_hold = 1;
+        }
+    }
     pk.clo_ctx_dep = clo.ctx_dep ? 1 : 0;
     pk.start_ofs = has_start ? reinterpret_cast<const uint32_t *>(base + o_sofs) : nullptr;
     pk.start_ent = has_start ? reinterpret_cast<const sre_dev_start_t *>(base + o_sent) : nullptr;
@@ -737,9 +743,11 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         }
     }
     const bool big = cp->pike.nregexes > 1 || cp->pike.clo_npark > 64;
-    const int k1 = ek1 > 0 ? ek1 : (big ? 12 : 4), h1 = ek1 > 0 ? eh1 : 2;
+    const int k1 = ek1 > 0 ? ek1 : (big ? 12 : 4);
     int k2 = ek2 > 0 ? ek2 : (big ? 32 : 8);
-    const int h2 = ek2 > 0 ? eh2 : 4;
+    /* no look-ahead assertion in the program: no pending closures to hold */
+    const int h1 = cp->pike.clo_has_hold ? (ek1 > 0 ? eh1 : 2) : 0;
+    const int h2 = cp->pike.clo_has_hold ? (ek2 > 0 ? eh2 : 4) : 0;
     if (cp->pike.clo_npark && (uint32_t) k2 > cp->pike.clo_npark) {
         k2 = (int) cp->pike.clo_npark;
     }

@@ -95,6 +95,7 @@ struct sre_dev_pike_t {
     const uint16_t          *clo_bofs;      /* [3][257]                            */
     uint32_t                 clo_nent, clo_nbent, clo_nsets, clo_npark;
     uint32_t                 clo_p_any;     /* parked number of the ".*?" ANY      */
+    uint32_t                 clo_has_hold;  /* some parked instruction is a look-ahead assertion */
     uint32_t                 clo_ctx_dep;   /* program has \A or ^             */
 };
 

@@ -183,7 +183,10 @@ __host__ __device__ inline size_t table_words(const sre_dev_pike_t &pk)
     return pk.clo_nent + pk.clo_nbent + (size_t) pk.clo_nsets * 8 + (halves * 2 + np + 3) / 4;
 }
 
-template <bool C16, bool BIG>
+/* HOLD: the program has look-ahead assertions ($ \z \b \B), whose closures are
+ * prepended to the current list through the LIFO; without them that code is
+ * compiled out of the thread loop */
+template <bool C16, bool BIG, bool HOLD>
 __global__ void __launch_bounds__(TB)
 k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
              size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines,
@@ -362,7 +365,7 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
             for (;;) {
                 /* next thread in priority order: pending look-ahead closures first */
                 int tp, tc;
-                if (hs > 0) {
+                if (HOLD && hs > 0) {
                     hs--;
                     tp = c.HSPC + hs;
                     /* its closure may be appended over this very record */
@@ -383,7 +386,7 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
                 const uint32_t kind = s_kind[pc];
                 bool got_match = false;
 
-                if (kind >= KD_SMALL_Z) {                   /* :449-528 */
+                if (HOLD && kind >= KD_SMALL_Z) {           /* :449-528 */
                     bool hold;
                     switch (kind) {
                     case KD_SMALL_Z: hold = at_end; break;
@@ -521,12 +524,17 @@ cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, 
     if (grid > cap) {
         grid = cap;
     }
-    void (*kern)(sre_dev_pike_t, const uint8_t *, const int64_t *, size_t, size_t, size_t, sre_line_list_t,
-                 const int32_t *, int32_t *, int64_t *, uint32_t, int, int, int) =
-        c16 ? (big ? k_pike_table<true, true> : k_pike_table<true, false>)
-            : (big ? k_pike_table<false, true> : k_pike_table<false, false>);
-    static bool opted[4] = { false, false, false, false };
-    const int which = (c16 ? 2 : 0) + (big ? 1 : 0);
+    typedef void (*kern_t)(sre_dev_pike_t, const uint8_t *, const int64_t *, size_t, size_t, size_t,
+                           sre_line_list_t, const int32_t *, int32_t *, int64_t *, uint32_t, int, int, int);
+    static const kern_t kerns[8] = {
+        k_pike_table<false, false, false>, k_pike_table<false, false, true>,
+        k_pike_table<false, true, false>,  k_pike_table<false, true, true>,
+        k_pike_table<true, false, false>,  k_pike_table<true, false, true>,
+        k_pike_table<true, true, false>,   k_pike_table<true, true, true>,
+    };
+    const int which = (c16 ? 4 : 0) + (big ? 2 : 0) + (pk.clo_has_hold ? 1 : 0);
+    const kern_t kern = kerns[which];
+    static bool opted[8] = { false, false, false, false, false, false, false, false };
     if (!opted[which]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) {
