@@ -48,19 +48,20 @@ __device__ __forceinline__ bool isword(uint32_t c)
  * instructions -- the dedup marks are two bit sets in shared memory (MK, 2 x mw
  * words, the current one chosen by `par`) instead of two 64-bit registers.
  */
-template <bool C16, bool BIG>
+template <bool C16, bool BIG, int NCW>
 struct lane_t {
     int32_t    *sm;
-    int         ncw;                /* words per capture vector */
+    int         ncw_rt;             /* words per capture vector (NCW == 0: only known at run time) */
+    __device__ __forceinline__ int ncw_() const { return NCW ? NCW : ncw_rt; }
     int         K, H;               /* threads per list, pending look-ahead closures */
     uint64_t    m_cur, m_prev;
     int         mw, par;            /* BIG: words per mark set, parity of the current set */
-    /* sections (word offsets), set from ncw */
+    /* sections (word offsets), set from the vector width */
     int         MAT, TMP, L0PC, L0CAP, L1PC, L1CAP, HSPC, HSCAP, MK;
 
     __device__ __forceinline__ void layout(int n, int k, int h, int npark)
     {
-        ncw = n;
+        ncw_rt = n;
         K = k;
         H = h;
         mw = BIG ? (npark + 31) >> 5 : 0;
@@ -131,14 +132,14 @@ struct lane_t {
     __device__ __forceinline__ void derive(int dst, int src, uint32_t mask, int32_t pos)
     {
         if (mask == 0 && src >= 0) {        /* the common case: nothing SAVEd on the way */
-            for (int j = 0; j < ncw; j++) {
+            for (int j = 0; j < ncw_(); j++) {
                 w(dst + j) = w(src + j);
             }
             return;
         }
         if (C16) {
             const uint32_t p16 = (uint32_t) pos & 0xffff;
-            for (int j = 0; j < ncw; j++) {
+            for (int j = 0; j < ncw_(); j++) {
                 uint32_t v = src < 0 ? 0xffffffffu : (uint32_t) w(src + j);
                 const uint32_t m = (mask >> (2 * j)) & 3;
                 if (m & 1) {
@@ -150,7 +151,7 @@ struct lane_t {
                 w(dst + j) = (int32_t) v;
             }
         } else {
-            for (int j = 0; j < ncw; j++) {
+            for (int j = 0; j < ncw_(); j++) {
                 const int32_t v = src < 0 ? -1 : w(src + j);
                 w(dst + j) = ((mask >> j) & 1) ? pos : v;
             }
@@ -186,7 +187,7 @@ __host__ __device__ inline size_t table_words(const sre_dev_pike_t &pk)
 /* HOLD: the program has look-ahead assertions ($ \z \b \B), whose closures are
  * prepended to the current list through the LIFO; without them that code is
  * compiled out of the thread loop */
-template <bool C16, bool BIG, bool HOLD>
+template <bool C16, bool BIG, bool HOLD, int NCW>
 __global__ void __launch_bounds__(TB)
 k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
              size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines,
@@ -230,11 +231,11 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
     const uint8_t *s_kind = t.kind;
     const uint32_t p_any = pk.clo_p_any;
 
-    lane_t<C16, BIG> c;
+    lane_t<C16, BIG, NCW> c;
     c.sm = smem_words + table_words(pk) + threadIdx.x;
     /* a thread carries the slots of its own regex only */
     c.layout(C16 ? (int) (pk.max_slots + 1) >> 1 : (int) pk.max_slots, K, H, (int) len);
-    const int ncw = c.ncw;
+    const int ncw = c.ncw_();
     const bool ctx_dep = pk.clo_ctx_dep != 0;
 
     const size_t nthreads = (size_t) gridDim.x * blockDim.x;
@@ -526,21 +527,27 @@ cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, 
     }
     typedef void (*kern_t)(sre_dev_pike_t, const uint8_t *, const int64_t *, size_t, size_t, size_t,
                            sre_line_list_t, const int32_t *, int32_t *, int64_t *, uint32_t, int, int, int);
-    static const kern_t kerns[8] = {
-        k_pike_table<false, false, false>, k_pike_table<false, false, true>,
-        k_pike_table<false, true, false>,  k_pike_table<false, true, true>,
-        k_pike_table<true, false, false>,  k_pike_table<true, false, true>,
-        k_pike_table<true, true, false>,   k_pike_table<true, true, true>,
+    /* [c16][big][hold][capture words: 0 = run-time, 1, 3, 5 (16-bit) / 2, 6, 10 (32-bit)] */
+#define SRE_TAB_ROW(C, B, H, N1, N2, N3)                                                            \
+    { k_pike_table<C, B, H, 0>, k_pike_table<C, B, H, N1>, k_pike_table<C, B, H, N2>, k_pike_table<C, B, H, N3> }
+    static const kern_t kerns[8][4] = {
+        SRE_TAB_ROW(false, false, false, 2, 6, 10), SRE_TAB_ROW(false, false, true, 2, 6, 10),
+        SRE_TAB_ROW(false, true, false, 2, 6, 10),  SRE_TAB_ROW(false, true, true, 2, 6, 10),
+        SRE_TAB_ROW(true, false, false, 1, 3, 5),   SRE_TAB_ROW(true, false, true, 1, 3, 5),
+        SRE_TAB_ROW(true, true, false, 1, 3, 5),    SRE_TAB_ROW(true, true, true, 1, 3, 5),
     };
+#undef SRE_TAB_ROW
     const int which = (c16 ? 4 : 0) + (big ? 2 : 0) + (pk.clo_has_hold ? 1 : 0);
-    const kern_t kern = kerns[which];
-    static bool opted[8] = { false, false, false, false, false, false, false, false };
-    if (!opted[which]) {
+    /* 0, 2 or 4 capture groups get unrolled capture loops */
+    const int sel = pk.max_slots == 2 ? 1 : pk.max_slots == 6 ? 2 : pk.max_slots == 10 ? 3 : 0;
+    const kern_t kern = kerns[which][sel];
+    static bool opted[8][4];
+    if (!opted[which][sel]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) {
             return e;
         }
-        opted[which] = true;
+        opted[which][sel] = true;
     }
     kern<<<(unsigned) grid, TB, smem, stream>>>(pk, buf, offsets, nlines, pitch, linelen, lines, start, rc, ovec,
                                                ovec_slots, K, H, retry_only);
