@@ -213,17 +213,18 @@ extern "C" long lc_table_pike(sre_program_t *prog, const uint8_t *input, long si
             v = T.ctx_dep ? (prev == '\n' ? 1u : 2u) : 0u;
         }
         const int nb = pos < size ? (int) input[pos] : -2;
-        const uint32_t *list = T.ent.data();
+        const uint32_t *list = T.ent.data(), *lmask = T.emask.data();
         uint32_t e0 = T.ofs[v * (np + 2) + P], e1 = T.ofs[v * (np + 2) + P + 1];
         bool filtered = false;
         if ((P == np || (int32_t) P == T.p_any) && !T.bent.empty() && nb >= 0) {
             list = T.bent.data();           /* the start closure by next byte */
+            lmask = T.bmask.data();
             e0 = T.bofs[v * 257 + nb];
             e1 = T.bofs[v * 257 + nb + 1];
             filtered = true;
         }
         for (uint32_t e = e0; e < e1; e++) {
-            const uint32_t fp = list[e] & 0xffff, mask = list[e] >> 16;
+            const uint32_t fp = list[e], mask = lmask[e];
             const uint32_t kind = T.kind[fp];
             if (!filtered && kind == 0
                 && (nb == -2 || !((T.accept[T.acc_idx[fp] * 8 + ((uint32_t) nb >> 5)] >> (nb & 31)) & 1)))

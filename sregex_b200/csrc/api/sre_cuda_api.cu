@@ -261,8 +261,11 @@ int upload(sre_cuda_program_t *cp)
     sre_closure_table_t clo;
     const bool has_clo = sre_build_closure_table(prog, 4096, clo);
     size_t o_cent = 0, o_cofs = 0, o_cacc = 0, o_ckind = 0, o_caidx = 0, o_creg = 0, o_cbent = 0, o_cbofs = 0;
+    size_t o_cemask = 0, o_cbmask = 0;
     if (has_clo) {
         o_cent = b.add(clo.ent.data(), clo.ent.size() * 4);
+        o_cemask = b.add(clo.emask.data(), clo.emask.size() * 4);
+        o_cbmask = b.add(clo.bmask.data(), clo.bmask.size() * 4);
         o_cofs = b.add(clo.ofs.data(), clo.ofs.size() * 2);
         o_cacc = b.add(clo.accept.data(), clo.accept.size() * 4);
         o_ckind = b.add(clo.kind.data(), clo.kind.size());
@@ -360,6 +363,8 @@ int upload(sre_cuda_program_t *cp)
     pk.clo_kind = has_clo ? base + o_ckind : nullptr;
     pk.clo_nent = has_clo ? (uint32_t) clo.ent.size() : 0;
     pk.clo_npark = has_clo ? clo.npark : 0;
+    pk.clo_emask = has_clo ? reinterpret_cast<const uint32_t *>(base + o_cemask) : nullptr;
+    pk.clo_bmask = has_clo ? reinterpret_cast<const uint32_t *>(base + o_cbmask) : nullptr;
     pk.clo_accidx = has_clo ? reinterpret_cast<const uint16_t *>(base + o_caidx) : nullptr;
     pk.clo_regex = has_clo ? reinterpret_cast<const uint16_t *>(base + o_creg) : nullptr;
     pk.clo_bent = has_clo ? reinterpret_cast<const uint32_t *>(base + o_cbent) : nullptr;
@@ -751,7 +756,7 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
     if (cp->pike.clo_npark && (uint32_t) k2 > cp->pike.clo_npark) {
         k2 = (int) cp->pike.clo_npark;
     }
-    if (sre_pike_table_applicable(cp->pike, k2 > k1 ? k2 : k1, h2) && linelen < (1ull << 31)
+    if (sre_pike_table_applicable(cp->pike, dev_offsets, linelen, k2 > k1 ? k2 : k1, h2) && linelen < (1ull << 31)
         && g_pike_general_only == 0)
     {
         /* the general kernel re-runs what the table kernel gave up on */

@@ -85,13 +85,15 @@ struct sre_dev_pike_t {
     const sre_dev_start_t   *start_ent;
     /* closure tables of k_pike_table (lower/sre_closure.h; clo_nent == 0:
      * none), over the clo_npark instructions a thread can be parked on       */
-    const uint32_t          *clo_ent;       /* parked number | slots SAVEd << 16  */
+    const uint32_t          *clo_ent;       /* parked number                       */
+    const uint32_t          *clo_emask;     /* slots SAVEd on the path to it       */
     const uint16_t          *clo_ofs;       /* [3][npark + 2]                      */
     const uint32_t          *clo_accept;    /* [nsets][8] distinct byte sets       */
     const uint16_t          *clo_accidx;    /* [npark] byte set it takes           */
     const uint16_t          *clo_regex;     /* [npark] owning regex                */
     const uint8_t           *clo_kind;      /* [npark] what it is                  */
     const uint32_t          *clo_bent;      /* start closure bucketed by next byte */
+    const uint32_t          *clo_bmask;
     const uint16_t          *clo_bofs;      /* [3][257]                            */
     uint32_t                 clo_nent, clo_nbent, clo_nsets, clo_npark;
     uint32_t                 clo_p_any;     /* parked number of the ".*?" ANY      */
@@ -176,7 +178,8 @@ cudaError_t sre_launch_pike_small(const sre_dev_pike_t &pk, const uint8_t *buf,
 /* closure-table Pike for small single-regex programs (sre_pike_table.cu);
  * same contract as sre_launch_pike_small.  K threads per list, H pending
  * look-ahead closures per context; retry_only: only lines with rc RETRY        */
-bool sre_pike_table_applicable(const sre_dev_pike_t &pk, int K, int H);   /* with lists of K / H */
+bool sre_pike_table_applicable(const sre_dev_pike_t &pk, const int64_t *offsets, size_t linelen,
+    int K, int H);             /* for these lines, with lists of K / H */
 cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf,
     const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen,
     sre_line_list_t lines, const int32_t *start, int32_t *rc, int64_t *ovec,

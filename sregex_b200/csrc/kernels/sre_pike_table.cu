@@ -172,7 +172,7 @@ enum { KD_CONS = 0, KD_MATCH = 1, KD_SMALL_Z = 2, KD_DOLLAR = 3, KD_BIG_B = 4, K
 
 /* block tables in shared memory, in this order (words, then halves, then bytes) */
 struct tables_t {
-    uint32_t  *ent, *bent, *accept;
+    uint32_t  *ent, *emask, *bent, *bmask, *accept;
     uint16_t  *ofs, *bofs, *accidx, *regex;
     uint8_t   *kind;
 };
@@ -181,7 +181,7 @@ __host__ __device__ inline size_t table_words(const sre_dev_pike_t &pk)
 {
     const size_t np = pk.clo_npark;
     const size_t halves = 3 * (np + 2) + (pk.clo_nbent ? 3 * 257 : 0) + 2 * np;
-    return pk.clo_nent + pk.clo_nbent + (size_t) pk.clo_nsets * 8 + (halves * 2 + np + 3) / 4;
+    return 2 * (size_t) (pk.clo_nent + pk.clo_nbent) + (size_t) pk.clo_nsets * 8 + (halves * 2 + np + 3) / 4;
 }
 
 /* HOLD: the program has look-ahead assertions ($ \z \b \B), whose closures are
@@ -198,8 +198,10 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
     const uint32_t len = pk.clo_npark, nofs = 3 * (len + 2), nbofs = pk.clo_nbent ? 3 * 257 : 0;
     tables_t t;
     t.ent = reinterpret_cast<uint32_t *>(smem_words);
-    t.bent = t.ent + pk.clo_nent;
-    t.accept = t.bent + pk.clo_nbent;
+    t.emask = t.ent + pk.clo_nent;
+    t.bent = t.emask + pk.clo_nent;
+    t.bmask = t.bent + pk.clo_nbent;
+    t.accept = t.bmask + pk.clo_nbent;
     t.ofs = reinterpret_cast<uint16_t *>(t.accept + pk.clo_nsets * 8);
     t.bofs = t.ofs + nofs;
     t.accidx = t.bofs + nbofs;
@@ -207,9 +209,11 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
     t.kind = reinterpret_cast<uint8_t *>(t.regex + len);
     for (uint32_t i = threadIdx.x; i < pk.clo_nent; i += TB) {
         t.ent[i] = pk.clo_ent[i];
+        t.emask[i] = pk.clo_emask[i];
     }
     for (uint32_t i = threadIdx.x; i < pk.clo_nbent; i += TB) {
         t.bent[i] = pk.clo_bent[i];
+        t.bmask[i] = pk.clo_bmask[i];
     }
     for (uint32_t i = threadIdx.x; i < pk.clo_nsets * 8; i += TB) {
         t.accept[i] = pk.clo_accept[i];
@@ -226,7 +230,7 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
         t.kind[i] = pk.clo_kind[i];
     }
     __syncthreads();
-    const uint32_t *s_ent = t.ent, *s_bent = t.bent, *s_accept = t.accept;
+    const uint32_t *s_ent = t.ent, *s_emask = t.emask, *s_bent = t.bent, *s_bmask = t.bmask, *s_accept = t.accept;
     const uint16_t *s_ofs = t.ofs, *s_bofs = t.bofs, *s_accidx = t.accidx, *s_regex = t.regex;
     const uint8_t *s_kind = t.kind;
     const uint32_t p_any = pk.clo_p_any;
@@ -266,19 +270,19 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
             v = ctx_dep ? (prev == '\n' ? 1u : 2u) : 0u;
         }
         const int nb = pos < size ? (int) input[pos] : NB_END;
-        const uint32_t *list = s_ent;
+        const uint32_t *list = s_ent, *lmask = s_emask;
         uint32_t e = s_ofs[v * (len + 2) + P], e1 = s_ofs[v * (len + 2) + P + 1];
         bool filtered = false;
         if ((P == len || P == p_any) && pk.clo_nbent && nb >= 0) {
             /* the start closure, already restricted to this next byte */
             list = s_bent;
+            lmask = s_bmask;
             e = s_bofs[v * 257 + (uint32_t) nb];
             e1 = s_bofs[v * 257 + (uint32_t) nb + 1];
             filtered = true;
         }
         for (; e < e1; e++) {
-            const uint32_t ent = list[e];
-            const uint32_t fpc = ent & 0xffff, mask = ent >> 16;
+            const uint32_t fpc = list[e];
             if (fpc == p_any) {
                 continue;               /* the ".*?" thread itself: see any_alive */
             }
@@ -293,6 +297,7 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
                 continue;
             }
             c.tag(fpc, hold);
+            const uint32_t mask = lmask[e];
             if (kind == KD_MATCH && want_done) {
                 c.derive(c.MAT, parent, mask, pos);
                 matched_id = (int32_t) s_regex[fpc];
@@ -489,9 +494,16 @@ size_t table_smem_bytes(const sre_dev_pike_t &pk, bool c16, int K, int H)
 
 }  // namespace
 
-bool sre_pike_table_applicable(const sre_dev_pike_t &pk, int K, int H)
+/* 16-bit capture offsets when every line is shorter than 32 KB */
+static bool use_c16(const int64_t *offsets, size_t linelen)
 {
-    return pk.clo_nent != 0 && pk.max_slots <= 16 && table_smem_bytes(pk, false, K, H) <= 200 * 1024;
+    return offsets == nullptr && linelen < 32767;
+}
+
+bool sre_pike_table_applicable(const sre_dev_pike_t &pk, const int64_t *offsets, size_t linelen, int K, int H)
+{
+    return pk.clo_nent != 0 && pk.max_slots <= 32
+           && table_smem_bytes(pk, use_c16(offsets, linelen), K, H) <= 200 * 1024;
 }
 
 cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, const int64_t *offsets,
@@ -512,8 +524,7 @@ cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, 
             sms = 148;
         }
     }
-    /* 16-bit capture offsets when every line is shorter than 32 KB */
-    const bool c16 = offsets == nullptr && linelen < 32767;
+    const bool c16 = use_c16(offsets, linelen);
     const bool big = pk.clo_npark > 64;
     const size_t smem = table_smem_bytes(pk, c16, K, H);
     size_t per_sm = (227 * 1024) / (smem + 1024);

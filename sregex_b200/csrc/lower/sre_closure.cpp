@@ -137,8 +137,9 @@ struct walk_env_t {
     const std::vector<uint32_t>  *slot_ofs;
 };
 
-/* false: a SAVE outside the 16-slot window of its regex */
-bool closure_walk(const walk_env_t &env, int32_t pc0, int ctx, std::vector<uint32_t> &out)
+/* false: a SAVE outside the 32-slot window of its regex */
+bool closure_walk(const walk_env_t &env, int32_t pc0, int ctx, std::vector<uint32_t> &out,
+    std::vector<uint32_t> &out_mask)
 {
     const sre_program_t *prog = env.prog;
     struct item_t { int32_t kind, pc; uint32_t mask; };
@@ -178,7 +179,7 @@ bool closure_walk(const walk_env_t &env, int32_t pc0, int ctx, std::vector<uint3
             }
             if (in.opcode == SRE_OPCODE_SAVE) {
                 const uint32_t rel = (uint32_t) in.v - (*env.slot_ofs)[(*env.pc_regex)[pc]];
-                if (rel >= 16) {
+                if (rel >= 32) {
                     return false;
                 }
                 stack.push_back({ 0, 0, mask });
@@ -200,7 +201,8 @@ bool closure_walk(const walk_env_t &env, int32_t pc0, int ctx, std::vector<uint3
                 pc++;
                 continue;
             }
-            out.push_back((uint32_t) (*env.park)[pc] | (mask << 16));       /* parked */
+            out.push_back((uint32_t) (*env.park)[pc]);      /* parked */
+            out_mask.push_back(mask);
             break;
         }
     }
@@ -219,7 +221,7 @@ bool sre_build_closure_table(const sre_program_t *prog, uint32_t max_park, sre_c
     std::vector<uint32_t> slot_ofs(prog->nregexes + 1, 0);
     for (sre_uint_t i = 0; i < prog->nregexes; i++) {
         const uint32_t cnt = 2 * (uint32_t) (prog->multi_ncaps[i] + 1);
-        if (cnt > 16) {
+        if (cnt > 32) {
             return false;
         }
         if (cnt > T.max_slots) {
@@ -336,9 +338,9 @@ bool sre_build_closure_table(const sre_program_t *prog, uint32_t max_park, sre_c
             T.ofs[(size_t) ctx * (np + 2) + P] = (uint16_t) T.ent.size();
             bool ok = true;
             if (P == np) {
-                ok = closure_walk(env, 0, ctx, T.ent);
+                ok = closure_walk(env, 0, ctx, T.ent, T.emask);
             } else if (T.kind[P] != 1) {            /* nothing follows a MATCH */
-                ok = closure_walk(env, park_pc[P] + 1, ctx, T.ent);
+                ok = closure_walk(env, park_pc[P] + 1, ctx, T.ent, T.emask);
             }
             if (!ok || T.ent.size() > 60000) {
                 return false;
@@ -364,16 +366,18 @@ bool sre_build_closure_table(const sre_program_t *prog, uint32_t max_park, sre_c
             for (uint32_t b = 0; b < 256; b++) {
                 T.bofs[(size_t) ctx * 257 + b] = (uint16_t) T.bent.size();
                 for (uint32_t e = e0; e < e1; e++) {
-                    const uint32_t P = T.ent[e] & 0xffff;
+                    const uint32_t P = T.ent[e];
                     if (T.kind[P] == 0
                         && !((T.accept[(size_t) T.acc_idx[P] * 8 + (b >> 5)] >> (b & 31)) & 1))
                     {
                         continue;
                     }
                     T.bent.push_back(T.ent[e]);
+                    T.bmask.push_back(T.emask[e]);
                 }
                 if (T.bent.size() > 60000) {
                     T.bent.clear();
+                    T.bmask.clear();
                     return true;            /* tables are fine, just no buckets */
                 }
             }

@@ -38,9 +38,10 @@ bool sre_build_start_closure(const sre_program_t *prog, const std::vector<uint16
  * .. ofs[ctx * (npark + 2) + P + 1]) = what add_thread(pc(P) + 1) appends when
  * run on its own (P == npark: add_thread(0)), with `\A` and `^` decided by the
  * look-behind context ctx: 0 = at offset 0, 1 = after a newline, 2 = elsewhere.
- * Entry = parked number | (slots SAVEd on the path) << 16, the slots counted
- * from the first slot of the regex that owns the parked instruction (a thread
- * only ever carries the slots of its own regex).
+ * Entry i = parked number ent[i] + the slots SAVEd on the path as a bit set
+ * emask[i], the slots counted from the first slot of the regex that owns the
+ * parked instruction (a thread only ever carries the slots of its own regex;
+ * at most 32 of them, i.e. 15 groups).
  *
  * The start closure (P == npark, and P == p_any, the ".*?" thread, whose
  * closure is the same list) is also given bucketed by the next byte when it is
@@ -48,18 +49,18 @@ bool sre_build_start_closure(const sre_program_t *prog, const std::vector<uint16
  * are not consuming instructions unable to take byte b.
  */
 struct sre_closure_table_t {
-    std::vector<uint32_t> ent;
+    std::vector<uint32_t> ent, emask;
     std::vector<uint16_t> ofs;
     std::vector<uint32_t> accept;       /* [nsets][8]: distinct byte sets */
     std::vector<uint16_t> acc_idx;      /* [npark]: byte set of a consuming instruction */
     std::vector<uint8_t>  kind;         /* [npark]: 0 consuming, 1 MATCH, 2 \z, 3 $, 4 \B, 5 \b */
     std::vector<uint16_t> regex;        /* [npark]: owning regex */
     std::vector<int32_t>  park_pc;      /* [npark]: its pc */
-    std::vector<uint32_t> bent;         /* bucketed start closure (may be empty) */
+    std::vector<uint32_t> bent, bmask;  /* bucketed start closure (may be empty) */
     std::vector<uint16_t> bofs;         /* [3][257] */
     uint32_t              npark = 0;
     uint32_t              nsets = 0;
-    uint32_t              max_slots = 0;        /* slots of the largest regex (<= 16) */
+    uint32_t              max_slots = 0;        /* slots of the largest regex (<= 32) */
     int32_t               p_any = -1;           /* parked number of the ".*?" ANY (pc 1), -1: none */
     bool                  ctx_dep = false;      /* program has \A or ^ */
 };

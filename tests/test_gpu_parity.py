@@ -266,6 +266,21 @@ def test_multi_regex_64_patterns_vs_oracle(cu):
     assert torch.equal(rc, rc3) and torch.equal(ov, ov3)
 
 
+def test_pike_many_groups_on_the_table_tier(cu):
+    """a 14-group log regex (30 capture slots): full ovectors against the oracle,
+    and it runs on the closure-table kernel"""
+    from test_lowering import WIDE_REGEX
+    n = 512
+    lines = corpus.log_lines(n, 1024)
+    prog = cu.CudaProgram(WIDE_REGEX)
+    _, want_rc, want_ov = baseline.run_lines("oracle", WIDE_REGEX, None, lines.numpy(), n, 1024, 1024,
+                                             baseline.ENGINE_PIKE, nthreads=8, ovec_slots=prog.nslots)
+    rc, ov = prog.pike_lines(lines.cuda(), n, 1024, 1024)
+    assert cu.lib().L.sre_cuda_pike_last_tier() == 0
+    assert (rc.cpu().numpy() == want_rc).all() and int((rc == 0).sum()) == n
+    assert (ov.cpu().numpy() == want_ov).all()
+
+
 def test_pike_tier_selection(cu):
     """the configurations the bench reports must run on the fast tier: C3 (4
     groups, 10 slots, 1 KB lines) on the closure-table kernel"""

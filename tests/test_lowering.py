@@ -249,3 +249,23 @@ def test_closure_table_pike_64_pattern_set(oracle, lc):
         hits += want[0] >= 0
     assert hits > 50
     po.close()
+
+
+WIDE_REGEX = rb'(\d+)\.(\d+)\.(\d+)\.(\d+) - - \[(\d+)/(\w+)/(\d+):(\d+):(\d+):(\d+) ([+-]\d+)\] "(\S*) (\w+) (\S+) HTTP'
+
+
+def test_closure_table_pike_many_groups(oracle, lc):
+    """14 capture groups (30 slots, beyond the 16-bit save masks of narrow
+    programs): the closure-table Pike == the oracle's Pike on log lines"""
+    from sregex_b200 import corpus
+    po = oracle.compile(WIDE_REGEX, 0)
+    assert po.ncaps == 14
+    lines = corpus.log_lines(200, 1024).numpy()
+    hits = 0
+    for i in range(200):
+        s = bytes(lines[i])
+        want = oracle.pike(po, s)
+        assert _table_pike(lc, po, s) == want, i
+        hits += want[0] >= 0
+    assert hits == 200
+    po.close()
