@@ -64,18 +64,35 @@ struct step256_t {
  */
 constexpr uint32_t ROW260 = 260;
 struct step260_t {
-    const uint8_t *tab;
+    uint32_t tab_s;             /* shared-window address of the table */
+    __device__ __forceinline__ static uint32_t lds_u8(uint32_t addr)
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+        return v;
+    }
+    __device__ __forceinline__ uint32_t row0(uint32_t b) const
+    {
+        uint32_t a;
+        asm volatile("add.u32 %0, %1, %2;" : "=r"(a) : "r"(tab_s), "r"(b));
+        return a;
+    }
+    /* the byte's address within row 0 is computed off the state -> state chain,
+     * which is then one IMAD and one LDS per byte */
     __device__ __forceinline__ uint32_t word(uint32_t s, uint32_t w) const
     {
-        s = tab[s * ROW260 + __byte_perm(w, 0, 0x4440)];
-        s = tab[s * ROW260 + __byte_perm(w, 0, 0x4441)];
-        s = tab[s * ROW260 + __byte_perm(w, 0, 0x4442)];
-        s = tab[s * ROW260 + __byte_perm(w, 0, 0x4443)];
+        /* (opaque adds: the compiler would otherwise re-associate them into the chain) */
+        const uint32_t a0 = row0(__byte_perm(w, 0, 0x4440)), a1 = row0(__byte_perm(w, 0, 0x4441));
+        const uint32_t a2 = row0(__byte_perm(w, 0, 0x4442)), a3 = row0(__byte_perm(w, 0, 0x4443));
+        s = lds_u8(s * ROW260 + a0);
+        s = lds_u8(s * ROW260 + a1);
+        s = lds_u8(s * ROW260 + a2);
+        s = lds_u8(s * ROW260 + a3);
         return s;
     }
     __device__ __forceinline__ uint32_t byte(uint32_t s, uint32_t b) const
     {
-        return tab[s * ROW260 + b];
+        return lds_u8(s * ROW260 + tab_s + b);
     }
 };
 

@@ -133,7 +133,7 @@ __device__ __forceinline__ void warp_compose(fn_t<NW> &f)
 /* NW*4-way consumer: byte d of `st` = state reached from entry state d */
 template <int NW>
 struct piece_consumer_t {
-    const uint8_t  *tab;        /* [nstates] rows of ROW260 bytes in shared memory */
+    uint32_t        tab_s;      /* [nstates] rows of ROW260 bytes in shared memory (shared-window address) */
     uint8_t        *fn;         /* level-0 function records                   */
     uint32_t        nstates, acc;
     size_t          npieces;
@@ -178,7 +178,7 @@ struct piece_consumer_t {
 
     __device__ __forceinline__ void chunk(const uint4 &v)
     {
-        step260_t st256 = { tab };
+        step260_t st256 = { tab_s };
         if (conv) {
             s = st256.word(st256.word(st256.word(st256.word(s, v.x), v.y), v.z), v.w);
             return;
@@ -196,14 +196,15 @@ struct piece_consumer_t {
 
     __device__ __forceinline__ void byte(uint32_t b)
     {
+        step260_t st256 = { tab_s };
         if (conv) {
-            s = tab[s * ROW260 + b];
+            s = st256.byte(s, b);
             return;
         }
 #pragma unroll
         for (int d = 0; d < NW * 4; d++) {
             if (d < (int) nstates) {
-                st.set(d, tab[st.get(d) * ROW260 + b]);
+                st.set(d, st256.byte(st.get(d), b));
             }
         }
     }
@@ -244,7 +245,7 @@ k_stream_pieces(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, siz
 
     const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
     piece_consumer_t<NW> cons;
-    cons.tab = smem;
+    cons.tab_s = (uint32_t) __cvta_generic_to_shared(smem);
     cons.fn = fn;
     cons.nstates = dfa.nstates;
     cons.acc = dfa.acc;
