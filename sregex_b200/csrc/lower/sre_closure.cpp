@@ -375,10 +375,12 @@ bool sre_build_closure_table(const sre_program_t *prog, uint32_t max_park, sre_c
                     T.bent.push_back(T.ent[e]);
                     T.bmask.push_back(T.emask[e]);
                 }
-                if (T.bent.size() > 60000) {
+                if (T.bent.size() > 4096) {
+                    /* buckets that are not selective would only cost shared
+                     * memory: the tables are fine without them */
                     T.bent.clear();
                     T.bmask.clear();
-                    return true;            /* tables are fine, just no buckets */
+                    return true;
                 }
             }
             T.bofs[(size_t) ctx * 257 + 256] = (uint16_t) T.bent.size();

@@ -281,6 +281,40 @@ def test_pike_many_groups_on_the_table_tier(cu):
     assert (ov.cpu().numpy() == want_ov).all()
 
 
+def test_big_regex_set_with_assertions_vs_oracle(cu):
+    """a set of 40 random regexes rich in look-ahead / look-behind assertions
+    (> 64 parked instructions: bit-set marks in shared memory, pending
+    look-ahead closures, per-context closure tables) over random short lines:
+    matched id + ovector == the oracle's Pike, on the table tier"""
+    import random
+    rng = random.Random(99)
+    atoms = ["a", "b", "ab", " ", "_", "1", ".", "^", "$", "\\b", "\\B", "\\z", "\\A", "(a)", "(b+)", "(?:ab)*", "+", "?",
+             "[ab]", "[^a ]", "\\w", "\\d", "(\\w+)", "|"]
+    oracle = capi.load("oracle")
+    pats = []
+    while len(pats) < 40:
+        rx = "".join(rng.choice(atoms) for _ in range(rng.randrange(2, 7))).encode()
+        try:
+            oracle.compile(rx, 0).close()
+        except capi.SreSyntaxError:
+            continue
+        pats.append(rx)
+    prog = cu.CudaProgram(pats)
+    assert prog.info.nregexes == 40
+    n, linelen, pitch = 4096, 24, 32
+    alphabet = np.frombuffer(b"ab _1.\n", dtype=np.uint8)
+    rs = np.random.RandomState(7)
+    lines = np.zeros((n, pitch), dtype=np.uint8)
+    lines[:, :linelen] = alphabet[rs.randint(0, len(alphabet), size=(n, linelen))]
+    _, want_rc, want_ov = baseline.run_lines("oracle", pats, None, lines, n, pitch, linelen,
+                                             baseline.ENGINE_PIKE, nthreads=8, ovec_slots=prog.nslots)
+    rc, ov = prog.pike_lines(torch.from_numpy(lines).cuda(), n, pitch, linelen)
+    assert cu.lib().L.sre_cuda_pike_last_tier() == 0
+    assert (rc.cpu().numpy() == want_rc).all()
+    assert (ov.cpu().numpy() == want_ov).all()
+    assert len(set(want_rc.tolist())) > 5
+
+
 def test_pike_tier_selection(cu):
     """the configurations the bench reports must run on the fast tier: C3 (4
     groups, 10 slots, 1 KB lines) on the closure-table kernel"""
