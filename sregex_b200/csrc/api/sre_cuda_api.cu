@@ -736,6 +736,8 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         lines.count = count;
     }
     const size_t nctx = cp->pike_nctx < nlines ? cp->pike_nctx : nlines;
+    /* the table kernel's work counter lives next to the packed-list count */
+    unsigned long long *next_work = reinterpret_cast<unsigned long long *>(cp->line_ws + 3 * half + 64);
     /* closure-table kernel: list capacities of its two passes.  Small lists
      * first (more resident warps), then the lines that needed more; a set of
      * regexes can have as many live threads as members share a prefix. */
@@ -762,10 +764,10 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         /* the general kernel re-runs what the table kernel gave up on */
         g_pike_last_tier = 0;
         err = sre_launch_pike_table(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
-                                    dev_rc, dev_ovec, (uint32_t) ovec_slots, k1, h1, 0, st, &launches);
+                                    dev_rc, dev_ovec, (uint32_t) ovec_slots, k1, h1, 0, next_work, st, &launches);
         if (err == cudaSuccess && (k1 < k2 || h1 < h2)) {
             err = sre_launch_pike_table(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
-                                        dev_rc, dev_ovec, (uint32_t) ovec_slots, k2, h2, 1, st, &launches);
+                                        dev_rc, dev_ovec, (uint32_t) ovec_slots, k2, h2, 1, next_work, st, &launches);
         }
         if (err == cudaSuccess) {
             err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines,

@@ -177,13 +177,15 @@ cudaError_t sre_launch_pike_small(const sre_dev_pike_t &pk, const uint8_t *buf,
 
 /* closure-table Pike for small single-regex programs (sre_pike_table.cu);
  * same contract as sre_launch_pike_small.  K threads per list, H pending
- * look-ahead closures per context; retry_only: only lines with rc RETRY        */
+ * look-ahead closures per context; retry_only: only lines with rc RETRY;
+ * next_work: 8 bytes of device memory for the kernel's work counter            */
 bool sre_pike_table_applicable(const sre_dev_pike_t &pk, const int64_t *offsets, size_t linelen,
     int K, int H);             /* for these lines, with lists of K / H */
 cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf,
     const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen,
     sre_line_list_t lines, const int32_t *start, int32_t *rc, int64_t *ovec,
-    uint32_t ovec_slots, int K, int H, int retry_only, cudaStream_t stream, int *launches);
+    uint32_t ovec_slots, int K, int H, int retry_only, unsigned long long *next_work,
+    cudaStream_t stream, int *launches);
 
 /* all non-overlapping matches per line (post-match continuation, global scan)  */
 cudaError_t sre_launch_pike_lines_all(const sre_dev_pike_t &pk, const uint8_t *buf,

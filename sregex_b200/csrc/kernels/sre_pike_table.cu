@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(TB)
 k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
              size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines,
              const int32_t *__restrict__ start_hint, int32_t *__restrict__ rc, int64_t *__restrict__ ovec,
-             uint32_t ovec_slots, int K, int H, int retry_only)
+             uint32_t ovec_slots, int K, int H, int retry_only, unsigned long long *next_work)
 {
     extern __shared__ int32_t smem_words[];
     const uint32_t len = pk.clo_npark, nofs = 3 * (len + 2), nbofs = pk.clo_nbent ? 3 * 257 : 0;
@@ -319,23 +319,44 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
      * the next one at once instead of waiting for the longest line of the
      * warp, so every turn is one byte step for every lane that has work left.
      */
+    /*
+     * Work is handed out line by line from a global counter (the first line of
+     * every lane is its own index): a lane that finishes early takes the next
+     * line of the whole launch, so short and long lines even out whatever the
+     * number of lines per lane.  One atomic per warp and turn, for all lanes
+     * that need a line.
+     */
     bool finished = false;
+    bool first_line = true;
+    const uint32_t lane = threadIdx.x & 31;
     for (;;) {
-        /* the vote is also the point where the lanes of the warp line up
+        /* the votes are also the point where the lanes of the warp line up
          * again: without it they drift apart and run one after the other */
         if (__all_sync(0xffffffffu, finished)) {
             break;
+        }
+        const bool need = !finished && !active && !first_line;
+        const uint32_t needers = __ballot_sync(0xffffffffu, need);
+        if (needers) {
+            unsigned long long base = 0;
+            if (lane == (uint32_t) (__ffs(needers) - 1)) {
+                base = atomicAdd(next_work, (unsigned long long) __popc(needers));
+            }
+            base = __shfl_sync(0xffffffffu, base, __ffs(needers) - 1);
+            if (need) {
+                k = nthreads + (size_t) base + __popc(needers & ((1u << lane) - 1));
+            }
         }
         if (finished) {
             continue;
         }
         if (!active) {
+            first_line = false;
             if (k >= nwork) {
                 finished = true;
                 continue;
             }
             line = lines.list ? (size_t) lines.list[k] : k;
-            k += nthreads;
             /* a later pass with larger lists: only what the previous one gave up on */
             if (retry_only && rc[line] != SRE_K_RETRY) {
                 continue;
@@ -508,13 +529,18 @@ bool sre_pike_table_applicable(const sre_dev_pike_t &pk, const int64_t *offsets,
 
 cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, const int64_t *offsets,
     size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines, const int32_t *start, int32_t *rc,
-    int64_t *ovec, uint32_t ovec_slots, int K, int H, int retry_only, cudaStream_t stream, int *launches)
+    int64_t *ovec, uint32_t ovec_slots, int K, int H, int retry_only, unsigned long long *next_work,
+    cudaStream_t stream, int *launches)
 {
     if (nlines == 0) {
         return cudaSuccess;
     }
     if (launches) {
         ++*launches;
+    }
+    cudaError_t ce = cudaMemsetAsync(next_work, 0, sizeof(*next_work), stream);
+    if (ce != cudaSuccess) {
+        return ce;
     }
     static int sms = 0;
     if (sms == 0) {
@@ -537,7 +563,8 @@ cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, 
         grid = cap;
     }
     typedef void (*kern_t)(sre_dev_pike_t, const uint8_t *, const int64_t *, size_t, size_t, size_t,
-                           sre_line_list_t, const int32_t *, int32_t *, int64_t *, uint32_t, int, int, int);
+                           sre_line_list_t, const int32_t *, int32_t *, int64_t *, uint32_t, int, int, int,
+                           unsigned long long *);
     /* [c16][big][hold][capture words: 0 = run-time, 1, 3, 5 (16-bit) / 2, 6, 10 (32-bit)] */
 #define SRE_TAB_ROW(C, B, H, N1, N2, N3)                                                            \
     { k_pike_table<C, B, H, 0>, k_pike_table<C, B, H, N1>, k_pike_table<C, B, H, N2>, k_pike_table<C, B, H, N3> }
@@ -561,6 +588,6 @@ cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, 
         opted[which][sel] = true;
     }
     kern<<<(unsigned) grid, TB, smem, stream>>>(pk, buf, offsets, nlines, pitch, linelen, lines, start, rc, ovec,
-                                               ovec_slots, K, H, retry_only);
+                                               ovec_slots, K, H, retry_only, next_work);
     return cudaGetLastError();
 }
