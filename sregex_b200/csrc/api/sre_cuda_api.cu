@@ -37,7 +37,7 @@ int                 g_pike_general_only = 0;    /* tests: force k_pike_lines */
 std::atomic<int>    g_pike_last_tier{-1};       /* tier of the last sre_cuda_pike_exec_lines */
 thread_local char   g_err[256] = "";
 
-const uint32_t MAX_DFA_STATES = 4096;
+const uint32_t MAX_DFA_STATES = 16384;    /* beyond: the NFA tier (the table is read from L2 when it exceeds shared memory) */
 const uint32_t MAX_NFA_STATES = 4096;
 const size_t   PIKE_SCRATCH_BUDGET = (size_t) 6 << 30;
 
