@@ -261,15 +261,14 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
      * closure P appended to the array (pcsec, capsec) of capacity capn at
      * count n: 0 ok, 1 MATCH reached (want_done), -1 out of room
      */
-    auto append_closure = [&](uint32_t P, int32_t pos, int parent, int pcsec, int capsec, int capn, int &n,
-                              bool hold, bool want_done) -> int {
+    /* prev / nb: the bytes before and at `pos` (nb: NB_END at the end of the line);
+     * the caller has them at hand for the whole step */
+    auto append_closure = [&](uint32_t P, int32_t pos, uint32_t prev, int nb, int parent, int pcsec, int capsec,
+                              int capn, int &n, bool hold, bool want_done) -> int {
         uint32_t v = 0;
-        uint32_t prev = 0;
         if (pos > 0) {
-            prev = input[pos - 1];
             v = ctx_dep ? (prev == '\n' ? 1u : 2u) : 0u;
         }
-        const int nb = pos < size ? (int) input[pos] : NB_END;
         const uint32_t *list = s_ent, *lmask = s_emask;
         uint32_t e = s_ofs[v * (len + 2) + P], e1 = s_ofs[v * (len + 2) + P + 1];
         bool filtered = false;
@@ -374,7 +373,10 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
             any_alive = p_any != 0xffffffffu;
             active = true;
             /* first_buf: the initial closure at the start offset, :202-216 */
-            if (append_closure(len, sp, -1, c.L0PC, c.L0CAP, c.K, ncl, false, false) < 0) {
+            if (append_closure(len, sp, sp > 0 ? (uint32_t) input[sp - 1] : 0u,
+                               sp < size ? (int) input[sp] : NB_END, -1, c.L0PC, c.L0CAP, c.K, ncl, false, false)
+                < 0)
+            {
                 overflow = true;
             }
         }
@@ -385,6 +387,10 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
             const bool at_end = (sp == size);
             const uint32_t byte = at_end ? 0 : input[sp];
             const bool cur_word = !at_end && isword(byte);
+            /* the byte the threads appended in this step will be stepped on, and (for
+             * the look-ahead closures of this position) the byte before this one */
+            const int nb_next = sp + 1 < size ? (int) input[sp + 1] : NB_END;
+            const uint32_t prev_byte = (HOLD && sp > 0) ? (uint32_t) input[sp - 1] : 0u;
             const int cl_pc = cur ? c.L1PC : c.L0PC, cl_cap = cur ? c.L1CAP : c.L0CAP;
             const int nl_pc = cur ? c.L0PC : c.L1PC, nl_cap = cur ? c.L0CAP : c.L1CAP;
             int i = 0;
@@ -425,7 +431,9 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
                         /* closure with tag - 1, prepended to clist: append it
                          * above the LIFO top, then reverse that segment */
                         int top = hs;
-                        if (append_closure(pc, sp, tc, c.HSPC, c.HSCAP, c.H, top, true, false) < 0) {
+                        if (append_closure(pc, sp, prev_byte, at_end ? NB_END : (int) byte, tc, c.HSPC, c.HSCAP,
+                                           c.H, top, true, false) < 0)
+                        {
                             overflow = true;
                             break;
                         }
@@ -448,7 +456,7 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
                     matched_id = (int32_t) s_regex[pc];
                     got_match = true;
                 } else if (!at_end && ((s_accept[(uint32_t) s_accidx[pc] * 8 + (byte >> 5)] >> (byte & 31)) & 1)) {
-                    const int r = append_closure(pc, sp + 1, tc, nl_pc, nl_cap, c.K, nnl, false, true);
+                    const int r = append_closure(pc, sp + 1, byte, nb_next, tc, nl_pc, nl_cap, c.K, nnl, false, true);
                     if (r < 0) {
                         overflow = true;
                         break;
@@ -465,7 +473,7 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
             }
             /* the ".*?" thread, last in priority: takes the byte and restarts the regex */
             if (any_alive && !at_end && !overflow) {
-                const int r = append_closure(p_any, sp + 1, -1, nl_pc, nl_cap, c.K, nnl, false, true);
+                const int r = append_closure(p_any, sp + 1, byte, nb_next, -1, nl_pc, nl_cap, c.K, nnl, false, true);
                 if (r < 0) {
                     overflow = true;
                 } else if (r == 1) {
