@@ -736,8 +736,8 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         lines.count = count;
     }
     const size_t nctx = cp->pike_nctx < nlines ? cp->pike_nctx : nlines;
-    /* the table kernel's work counter lives next to the packed-list count */
-    unsigned long long *next_work = reinterpret_cast<unsigned long long *>(cp->line_ws + 3 * half + 64);
+    /* the table kernel's bookkeeping lives next to the packed-list count */
+    sre_pike_work_t *work = reinterpret_cast<sre_pike_work_t *>(cp->line_ws + 3 * half + 64);
     /* closure-table kernel: list capacities of its two passes.  Small lists
      * first (more resident warps), then the lines that needed more; a set of
      * regexes can have as many live threads as members share a prefix. */
@@ -764,15 +764,17 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         /* the general kernel re-runs what the table kernel gave up on */
         g_pike_last_tier = 0;
         err = sre_launch_pike_table(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
-                                    dev_rc, dev_ovec, (uint32_t) ovec_slots, k1, h1, 0, next_work, st, &launches);
-        if (err == cudaSuccess && (k1 < k2 || h1 < h2)) {
+                                    dev_rc, dev_ovec, (uint32_t) ovec_slots, k1, h1, 0, work, st, &launches);
+        const bool two = (k1 < k2 || h1 < h2);
+        if (err == cudaSuccess && two) {
             err = sre_launch_pike_table(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
-                                        dev_rc, dev_ovec, (uint32_t) ovec_slots, k2, h2, 1, next_work, st, &launches);
+                                        dev_rc, dev_ovec, (uint32_t) ovec_slots, k2, h2, 1, work, st, &launches);
         }
         if (err == cudaSuccess) {
             err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines,
                                         start, dev_rc, dev_ovec, (uint32_t) ovec_slots, cp->pike_scratch,
-                                        nctx < 16384 ? nctx : 16384, 1, st, &launches);
+                                        nctx < 16384 ? nctx : 16384, 1, st, &launches,
+                                        &work->given_up[two ? 1 : 0]);
         }
     } else if (sre_pike_small_applicable(cp->pike) && linelen < (1ull << 31) && g_pike_general_only != 1) {
         /* shared-memory kernel first; the general kernel re-runs what it gave up on */

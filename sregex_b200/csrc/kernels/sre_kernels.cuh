@@ -165,7 +165,7 @@ cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
     const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen,
     sre_line_list_t lines, const int32_t *start, int32_t *rc, int64_t *ovec,
     uint32_t ovec_slots, uint8_t *scratch, size_t nctx, int retry_only, cudaStream_t stream,
-    int *launches);
+    int *launches, const uint32_t *retry_count = nullptr);      /* retry_count: device, 0 = nothing to re-run */
 
 /* shared-memory Pike for small single-regex programs; lines that exceed its
  * capacities get rc = SRE_K_RETRY (re-run them with retry_only = 1 above)      */
@@ -175,16 +175,24 @@ cudaError_t sre_launch_pike_small(const sre_dev_pike_t &pk, const uint8_t *buf,
     sre_line_list_t lines, const int32_t *start, int32_t *rc, int64_t *ovec,
     uint32_t ovec_slots, cudaStream_t stream, int *launches);
 
+/* device-side bookkeeping of one sre_cuda_pike_exec_lines call: the table
+ * kernel's work counter, and how many lines each table pass gave up on (so
+ * that the passes after it return at once when there is nothing to re-run)    */
+struct sre_pike_work_t {
+    unsigned long long next;
+    uint32_t           given_up[2];
+};
+
 /* closure-table Pike for small single-regex programs (sre_pike_table.cu);
  * same contract as sre_launch_pike_small.  K threads per list, H pending
  * look-ahead closures per context; retry_only: only lines with rc RETRY;
- * next_work: 8 bytes of device memory for the kernel's work counter            */
+ * pass: 0 first pass, 1 the retry pass; work: device memory, see above       */
 bool sre_pike_table_applicable(const sre_dev_pike_t &pk, const int64_t *offsets, size_t linelen,
     int K, int H);             /* for these lines, with lists of K / H */
 cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf,
     const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen,
     sre_line_list_t lines, const int32_t *start, int32_t *rc, int64_t *ovec,
-    uint32_t ovec_slots, int K, int H, int retry_only, unsigned long long *next_work,
+    uint32_t ovec_slots, int K, int H, int pass, sre_pike_work_t *work,
     cudaStream_t stream, int *launches);
 
 /* all non-overlapping matches per line (post-match continuation, global scan)  */

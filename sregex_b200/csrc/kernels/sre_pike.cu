@@ -917,8 +917,11 @@ k_pike_lines(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
              size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines,
              const int32_t *__restrict__ start_hint, int32_t *__restrict__ rc, int64_t *__restrict__ ovec,
              uint32_t ovec_slots, uint8_t *scratch, size_t nctx, int retry_only, uint32_t stride,
-             int parts)
+             int parts, const uint32_t *retry_count)
 {
+    if (retry_only && retry_count && *retry_count == 0) {
+        return;                 /* the faster tiers gave up on no line */
+    }
     const size_t tid = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= nctx) {
         return;
@@ -1091,7 +1094,7 @@ cudaError_t sre_launch_pike_compact(const int32_t *select, size_t nlines, int32_
 cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
     const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines,
     const int32_t *start, int32_t *rc, int64_t *ovec, uint32_t ovec_slots, uint8_t *scratch, size_t nctx,
-    int retry_only, cudaStream_t stream, int *launches)
+    int retry_only, cudaStream_t stream, int *launches, const uint32_t *retry_count)
 {
     if (nlines == 0 || nctx == 0) {
         return cudaSuccess;
@@ -1104,7 +1107,7 @@ cudaError_t sre_launch_pike_lines(const sre_dev_pike_t &pk, const uint8_t *buf,
     const int parts = smem_parts(pk, 128, true, &smem);
     k_pike_lines<<<grid, 128, smem, stream>>>(pk, buf, offsets, nlines, pitch, linelen, lines, start, rc,
                                              ovec, ovec_slots, scratch, nctx, retry_only, batch_stride(),
-                                             parts);
+                                             parts, retry_count);
     return cudaGetLastError();
 }
 

@@ -192,9 +192,15 @@ __global__ void __launch_bounds__(TB)
 k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
              size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines,
              const int32_t *__restrict__ start_hint, int32_t *__restrict__ rc, int64_t *__restrict__ ovec,
-             uint32_t ovec_slots, int K, int H, int retry_only, unsigned long long *next_work)
+             uint32_t ovec_slots, int K, int H, int pass, sre_pike_work_t *work)
 {
     extern __shared__ int32_t smem_words[];
+    /* the retry pass has nothing to do when the first pass gave up on no line */
+    const bool retry_only = pass != 0;
+    if (retry_only && work->given_up[0] == 0) {
+        return;
+    }
+    unsigned long long *next_work = &work->next;
     const uint32_t len = pk.clo_npark, nofs = 3 * (len + 2), nbofs = pk.clo_nbent ? 3 * 257 : 0;
     tables_t t;
     t.ent = reinterpret_cast<uint32_t *>(smem_words);
@@ -494,6 +500,7 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
             int64_t *ov = ovec + line * ovec_slots;
             if (overflow) {
                 rc[line] = SRE_K_RETRY;
+                atomicAdd(&work->given_up[pass], 1u);
             } else if (matched) {
                 /* prepare_matched_captures :945-989: the matched regex's slots, the rest -1 */
                 const uint32_t cnt = pk.slot_ofs[matched_id + 1] - pk.slot_ofs[matched_id];
@@ -537,7 +544,7 @@ bool sre_pike_table_applicable(const sre_dev_pike_t &pk, const int64_t *offsets,
 
 cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, const int64_t *offsets,
     size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines, const int32_t *start, int32_t *rc,
-    int64_t *ovec, uint32_t ovec_slots, int K, int H, int retry_only, unsigned long long *next_work,
+    int64_t *ovec, uint32_t ovec_slots, int K, int H, int pass, sre_pike_work_t *work,
     cudaStream_t stream, int *launches)
 {
     if (nlines == 0) {
@@ -546,7 +553,8 @@ cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, 
     if (launches) {
         ++*launches;
     }
-    cudaError_t ce = cudaMemsetAsync(next_work, 0, sizeof(*next_work), stream);
+    /* first pass: everything; retry pass: the work counter only */
+    cudaError_t ce = cudaMemsetAsync(work, 0, pass == 0 ? sizeof(*work) : sizeof(work->next), stream);
     if (ce != cudaSuccess) {
         return ce;
     }
@@ -572,7 +580,7 @@ cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, 
     }
     typedef void (*kern_t)(sre_dev_pike_t, const uint8_t *, const int64_t *, size_t, size_t, size_t,
                            sre_line_list_t, const int32_t *, int32_t *, int64_t *, uint32_t, int, int, int,
-                           unsigned long long *);
+                           sre_pike_work_t *);
     /* [c16][big][hold][capture words: 0 = run-time, 1, 3, 5 (16-bit) / 2, 6, 10 (32-bit)] */
 #define SRE_TAB_ROW(C, B, H, N1, N2, N3)                                                            \
     { k_pike_table<C, B, H, 0>, k_pike_table<C, B, H, N1>, k_pike_table<C, B, H, N2>, k_pike_table<C, B, H, N3> }
@@ -596,6 +604,6 @@ cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf, 
         opted[which][sel] = true;
     }
     kern<<<(unsigned) grid, TB, smem, stream>>>(pk, buf, offsets, nlines, pitch, linelen, lines, start, rc, ovec,
-                                               ovec_slots, K, H, retry_only, next_work);
+                                               ovec_slots, K, H, pass, work);
     return cudaGetLastError();
 }
