@@ -7,29 +7,41 @@
  * fresh context and one buffer with eof = 1, like sre_pike_small.cu, but
  * add_thread (:756-942) is not walked at run time.  Instructions a thread can
  * be parked on (consuming ones, look-ahead assertions, MATCH) are numbered
- * 0 .. npark-1 (<= 64; SPLIT / JMP / SAVE and `\A` `^` never hold a thread), and
- * everything below speaks of those numbers.  For every such instruction P, the host lists what add_thread(P + 1) appends when
- * run on its own (sre_cuda_api.cu: build_closure_table -- same walk order,
- * same revisited-SPLIT rule :770-786): the parked instructions in priority
- * order, each with the set of capture slots SAVEd on the way, once per
- * look-behind context (at offset 0 / after a newline / elsewhere, which is all
- * `\A` and `^` can see).  At run time a closure is "for each entry: skip it if
- * its instruction is already marked in this step, else mark it and append a
- * thread whose captures are the parent's with the SAVEd slots set to the
- * position".  That is the list the walk would have produced: a walk stops at
- * an instruction marked earlier in the step, and everything below such an
- * instruction was appended (and marked) by the walk that marked it.  The idea
- * is the reference JIT's (sre_vm_thompson_x64.dasc:323-394 precomputes the
- * closure of every consuming instruction), extended with captures.
+ * 0 .. npark-1 (SPLIT / JMP / SAVE and `\A` `^` never hold a thread), and
+ * everything below speaks of those numbers.  For every such instruction P, the
+ * host lists what add_thread(pc(P) + 1) appends when run on its own
+ * (lower/sre_closure.cpp -- same walk order, same revisited-SPLIT rule
+ * :770-786): the parked instructions in priority order, each with the set of
+ * capture slots SAVEd on the way, once per look-behind context (at offset 0 /
+ * after a newline / elsewhere, which is all `\A` and `^` can see).  At run time
+ * a closure is "for each entry: skip it if its instruction is already marked in
+ * this step, else mark it and append a thread whose captures are the parent's
+ * with the SAVEd slots set to the position".  That is the list the walk would
+ * have produced: a walk stops at an instruction marked earlier in the step, and
+ * everything below such an instruction was appended (and marked) by the walk
+ * that marked it.  The idea is the reference JIT's
+ * (sre_vm_thompson_x64.dasc:323-394 precomputes the closure of every consuming
+ * instruction), extended with captures.  oracle/lower_check.cpp holds a CPU
+ * model of this kernel over the same tables (tests/test_lowering.py).
  *
- * On top of that, as in sre_pike.cu: a thread parked on a consuming instruction
- * that cannot take the next byte is not appended (the next step would drop it
- * without effect), dedup marks are two 64-bit masks (this step / the previous
- * one, the only two epochs the reference compares against), and the first-byte
- * prefilter is left to the start hint of k_dfa_lines_hint.
+ * On top of that:
+ *   - a thread parked on a consuming instruction that cannot take the next byte
+ *     is not appended (the next step would drop it without effect);
+ *   - the ".*?" thread is a flag, not a list entry (it is always last, always
+ *     takes the byte and carries no capture); its closure -- the start closure
+ *     -- comes bucketed by the next byte when it is long (regex sets);
+ *   - dedup marks are "this step / the previous step", the only two epochs the
+ *     reference compares against: two 64-bit registers, or two bit sets in
+ *     shared memory for programs with more than 64 parked instructions;
+ *   - a thread carries the capture slots of its own regex only (<= 32), as
+ *     16-bit line offsets when lines are shorter than 32 KB;
+ *   - the first-byte prefilter is left to the start hint of k_dfa_lines_hint;
+ *   - lines are handed out from a global counter, and every turn of the one
+ *     (line, byte) loop starts with a warp vote that lines the lanes up again.
  *
  * A line that needs more than K threads per list or H pending look-ahead
- * closures is reported SRE_K_RETRY and re-run by k_pike_lines.
+ * closures is reported SRE_K_RETRY and re-run with larger lists, then by
+ * k_pike_lines.
  */
 #include "sre_kernels.cuh"
 
