@@ -23,10 +23,18 @@
  *   - every list thread owns a private copy of the capture slots of the regex
  *     its pc belongs to (a thread inside regex i of a multi-regex set can only
  *     have written regex i's slots; all others are -1 by construction), so a
- *     thread costs max_slots instead of nslots values.
- * All context state lives in one block of global memory, so the same routine
- * serves the batch entry points (context re-initialised per line) and the
- * streaming sre_vm_pike_exec (context persists between calls).
+ *     thread costs max_slots instead of nslots values;
+ *   - a thread parked on a consuming instruction that cannot take the next byte
+ *     of the buffer is not appended (see pike_add_thread), and the first-byte
+ *     prefilter (:256-309) becomes "the list holds only the .*? thread".
+ * The thread records live in one block of global memory per context, the hot
+ * rest (scalar state, marks, the top of the DFS stack, the working capture
+ * window) in shared memory; the same routine serves the batch entry points
+ * (context re-initialised per line; since the closure-table kernel of
+ * sre_pike_table.cu took over the batch work this is its fallback: programs
+ * whose tables do not fit, regexes with more than 15 groups, lines it gave up
+ * on) and the streaming sre_vm_pike_exec (context persists between calls,
+ * header and marks stored back into the block).
  */
 #include <cstdlib>
 #include "sre_kernels.cuh"
