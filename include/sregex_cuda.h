@@ -138,6 +138,20 @@ SRE_API int sre_cuda_pike_exec_lines_host(sre_cuda_program_t *cp,
     int gate_with_thompson, int32_t *host_rc, int64_t *host_ovec,
     size_t ovec_slots);
 
+/*
+ * Line index of a '\n'-delimited device buffer, for the ragged entry points
+ * above (new: the reference is handed one buffer per exec call by its caller).
+ * dev_offsets[0] = 0, dev_offsets[i+1] = one past the '\n' that ends line i; a
+ * last line without '\n' ends at len.  So line i = [dev_offsets[i],
+ * dev_offsets[i+1]) includes its terminator (`$` still matches before it,
+ * sre_vm_thompson.c:183-188).  dev_offsets has room for max_lines + 1 values;
+ * *nlines = lines found, which may exceed max_lines (then only the first
+ * max_lines are indexed: call again with a larger array).  Synchronises the
+ * stream.
+ */
+SRE_API int sre_cuda_index_lines(const uint8_t *dev_buf, size_t len,
+    int64_t *dev_offsets, size_t max_lines, size_t *nlines, void *stream);
+
 /* Tuning / introspection */
 SRE_API void sre_cuda_set_variant(int variant);     /* tile shape of DFA_TILED   */
 SRE_API void sre_cuda_set_l2_promotion(int mode);   /* TMA L2 promotion: 0..3    */

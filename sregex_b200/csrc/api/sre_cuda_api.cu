@@ -563,6 +563,36 @@ extern "C" {
 SRE_API int sre_cuda_device_available(void) { return device_ok() ? 1 : 0; }
 SRE_API const char *sre_cuda_last_error(void) { return g_err; }
 SRE_API void sre_cuda_set_variant(int variant) { g_variant = variant; }
+SRE_API int
+sre_cuda_index_lines(const uint8_t *dev_buf, size_t len, int64_t *dev_offsets, size_t max_lines, size_t *nlines,
+    void *stream)
+{
+    if ((dev_buf == NULL && len != 0) || dev_offsets == NULL || nlines == NULL) {
+        return fail("NULL buffer, offsets or nlines");
+    }
+    cudaStream_t st = as_stream(stream);
+    const size_t need = sre_lines_workspace_bytes(len);
+    unsigned long long *ws = nullptr;
+    CUDA_TRY(cudaMalloc(&ws, need));
+    int launches = 0;
+    cudaError_t err = sre_launch_index_lines(dev_buf, len, dev_offsets, max_lines, ws, st, &launches);
+    count_launches(launches);
+    unsigned long long found = 0;
+    if (err == cudaSuccess) {
+        err = cudaMemcpyAsync(&found, ws + need / sizeof(unsigned long long) - 1, sizeof(found),
+                              cudaMemcpyDeviceToHost, st);
+    }
+    if (err == cudaSuccess) {
+        err = cudaStreamSynchronize(st);
+    }
+    cudaFree(ws);
+    if (err != cudaSuccess) {
+        return fail("line index failed: %s", cudaGetErrorString(err));
+    }
+    *nlines = (size_t) found;
+    return SRE_OK;
+}
+
 SRE_API void sre_cuda_set_pike_general_only(int on) { g_pike_general_only = on; }
 SRE_API int sre_cuda_pike_last_tier(void) { return g_pike_last_tier.load(); }
 SRE_API void sre_cuda_set_stream_piece(int bytes) { sre_stream_set_piece_bytes((uint32_t) bytes); }

@@ -201,6 +201,15 @@ cudaError_t sre_launch_pike_lines_all(const sre_dev_pike_t &pk, const uint8_t *b
     int32_t *count, int64_t *spans, int32_t *ids, uint8_t *scratch, size_t nctx,
     cudaStream_t stream, int *launches);
 
+/* line index of a '\n'-delimited buffer (sre_lines.cu): offsets[0] = 0,
+ * offsets[i+1] = one past the newline ending line i (at most max_lines of them);
+ * a last line without newline ends at len; workspace
+ * (sre_lines_workspace_bytes(len) bytes): its last word receives the number of
+ * lines found (which may exceed max_lines)                                      */
+size_t sre_lines_workspace_bytes(size_t len);
+cudaError_t sre_launch_index_lines(const uint8_t *buf, size_t len, int64_t *offsets, size_t max_lines,
+    unsigned long long *workspace, cudaStream_t stream, int *launches);
+
 /* Pike VM streaming step on one persistent context (classic API)             */
 cudaError_t sre_launch_pike_stream(const sre_dev_pike_t &pk, uint8_t *ctx,
     const uint8_t *buf, size_t len, int eof, int want_pending, int64_t *out,

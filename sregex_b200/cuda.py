@@ -48,6 +48,8 @@ def lib():
             "sre_cuda_set_l2_promotion": (None, [C.c_int]),
             "sre_cuda_set_pike_general_only": (None, [C.c_int]),
             "sre_cuda_pike_last_tier": (C.c_int, []),
+            "sre_cuda_index_lines": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                               C.POINTER(C.c_size_t), C.c_void_p]),
             "sre_cuda_set_stream_piece": (None, [C.c_int]),
             "sre_cuda_launch_count": (C.c_long, [C.c_int]),
             "sre_cuda_device_available": (C.c_int, []),
@@ -167,6 +169,21 @@ class CudaProgram:
                                                         linelen, int(gate), host_rc.data_ptr(),
                                                         host_ovec.data_ptr(), self.nslots))
         return host_rc, host_ovec
+
+
+def index_lines(buf: torch.Tensor, length: int | None = None, max_lines: int | None = None) -> torch.Tensor:
+    """Offsets (int64, on the device) of the '\\n'-delimited lines of a device byte
+    buffer: line i = buf[off[i], off[i+1]), terminator included; feed them to
+    thompson_ragged / pike_lines(offsets=...)."""
+    length = buf.numel() if length is None else length
+    cap = max_lines if max_lines is not None else max(1024, length // 64)
+    while True:
+        off = torch.empty(cap + 1, dtype=torch.int64, device=buf.device)
+        n = C.c_size_t(0)
+        _check(lib().L.sre_cuda_index_lines(buf.data_ptr(), length, off.data_ptr(), cap, C.byref(n), _stream_ptr()))
+        if n.value <= cap or max_lines is not None:
+            return off[: min(n.value, cap) + 1]
+        cap = n.value
 
 
 def launch_count(reset=False) -> int:

@@ -315,6 +315,41 @@ def test_big_regex_set_with_assertions_vs_oracle(cu):
     assert len(set(want_rc.tolist())) > 5
 
 
+def test_index_lines_and_ragged_grep(cu):
+    """a '\\n'-delimited buffer -> device line index -> ragged Thompson + Pike:
+    offsets against a host scan, verdicts / ovectors against the oracle per line"""
+    rs = np.random.RandomState(11)
+    oracle = capi.load("oracle")
+    for trailing_newline in (True, False):
+        src = corpus.log_lines(3000, 1024).numpy()
+        lens = rs.randint(0, 300, size=3000)
+        lens[::97] = 0                                  # empty lines
+        parts = [bytes(src[i, 1024 - 60 - lens[i]: 1024 - 60]) + b"\n" for i in range(3000)]
+        data = b"".join(parts)
+        if not trailing_newline:
+            data += b"GET /x/1 HTTP/1.1\" 503 "        # last line without terminator
+        host = np.frombuffer(data, dtype=np.uint8)
+        want_off = np.concatenate([[0], np.flatnonzero(host == 10) + 1]).astype(np.int64)
+        if not trailing_newline:
+            want_off = np.concatenate([want_off, [len(data)]])
+        dev = torch.from_numpy(host.copy()).cuda()
+        off = cu.index_lines(dev)
+        assert np.array_equal(off.cpu().numpy(), want_off)
+        # too small an array: the count is still reported, the prefix is right
+        off_small = cu.index_lines(dev, max_lines=100)
+        assert np.array_equal(off_small.cpu().numpy(), want_off[:101])
+        n = len(want_off) - 1
+        prog = cu.CudaProgram(corpus.C2_REGEX)
+        got = prog.thompson_ragged(dev, off).cpu().numpy()
+        po = oracle.compile(corpus.C2_REGEX, 0)
+        want = np.array([oracle.thompson(po, data[want_off[i]:want_off[i + 1]]) for i in range(n)])
+        assert np.array_equal(got, want)
+        assert (want == 0).sum() > 10
+        po.close()
+    empty = cu.index_lines(torch.empty(0, dtype=torch.uint8, device="cuda"))
+    assert empty.cpu().tolist() == [0]
+
+
 def test_pike_tier_selection(cu):
     """the configurations the bench reports must run on the fast tier: C3 (4
     groups, 10 slots, 1 KB lines) on the closure-table kernel"""
