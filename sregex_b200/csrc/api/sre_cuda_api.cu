@@ -572,8 +572,17 @@ sre_cuda_index_lines(const uint8_t *dev_buf, size_t len, int64_t *dev_offsets, s
     }
     cudaStream_t st = as_stream(stream);
     const size_t need = sre_lines_workspace_bytes(len);
-    unsigned long long *ws = nullptr;
-    CUDA_TRY(cudaMalloc(&ws, need));
+    /* block counts: a grow-only workspace per host thread (cudaMalloc / cudaFree
+     * per call would cost more than the three kernels) */
+    static thread_local unsigned long long *ws = nullptr;
+    static thread_local size_t ws_bytes = 0;
+    if (ws_bytes < need) {
+        cudaFree(ws);
+        ws = nullptr;
+        ws_bytes = 0;
+        CUDA_TRY(cudaMalloc(&ws, need + need / 2));
+        ws_bytes = need + need / 2;
+    }
     int launches = 0;
     cudaError_t err = sre_launch_index_lines(dev_buf, len, dev_offsets, max_lines, ws, st, &launches);
     count_launches(launches);
@@ -585,7 +594,6 @@ sre_cuda_index_lines(const uint8_t *dev_buf, size_t len, int64_t *dev_offsets, s
     if (err == cudaSuccess) {
         err = cudaStreamSynchronize(st);
     }
-    cudaFree(ws);
     if (err != cudaSuccess) {
         return fail("line index failed: %s", cudaGetErrorString(err));
     }

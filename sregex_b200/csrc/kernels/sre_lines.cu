@@ -158,6 +158,27 @@ k_lines_write(const uint8_t *__restrict__ buf, size_t len, const unsigned long l
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         offsets[0] = 0;
     }
+    if (begin + LB_PER_THREAD <= len && ((reinterpret_cast<uintptr_t>(buf) + begin) & 15) == 0) {
+        /* 16-byte loads; the set bits of the equality mask give the positions */
+#pragma unroll
+        for (uint32_t k = 0; k < LB_PER_THREAD; k += 16) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(buf + begin + k));
+            const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++) {
+                uint32_t m = nl_mask(w[j]);
+                while (m) {
+                    const uint32_t byte = (uint32_t) (__ffs((int) m) - 1) >> 3;
+                    m &= m - 1;
+                    if (rank < max_lines) {
+                        offsets[rank + 1] = (int64_t) (begin + k + 4 * j + byte + 1);
+                    }
+                    rank++;
+                }
+            }
+        }
+        return;
+    }
     for (size_t p = begin; p < begin + LB_PER_THREAD && p < len; p++) {
         if (buf[p] == '\n') {
             if (rank < max_lines) {
