@@ -350,6 +350,30 @@ def test_index_lines_and_ragged_grep(cu):
     assert empty.cpu().tolist() == [0]
 
 
+def test_long_lines_32bit_captures(cu):
+    """lines of 40,000 bytes (beyond the 16-bit capture offsets of the table
+    kernel): Thompson verdicts and full Pike ovectors against the oracle"""
+    n, linelen = 48, 40000
+    rs = np.random.RandomState(3)
+    alphabet = np.frombuffer(b"abcdefghij0123456789/_-. ", dtype=np.uint8)
+    lines = alphabet[rs.randint(0, len(alphabet), size=(n, linelen))].copy()
+    needle = np.frombuffer(b' GET /x/42 HTTP/1.1" 503 ', dtype=np.uint8)
+    for i in range(0, n, 2):                                   # every other line matches, far into the line
+        at = 33000 + 97 * i
+        lines[i, at:at + len(needle)] = needle
+    for rx in (corpus.C2_REGEX, corpus.C3_REGEX):
+        prog = cu.CudaProgram(rx)
+        _, want_t, _ = baseline.run_lines("oracle", rx, None, lines, n, linelen, linelen, baseline.ENGINE_THOMPSON)
+        _, want_rc, want_ov = baseline.run_lines("oracle", rx, None, lines, n, linelen, linelen,
+                                                 baseline.ENGINE_PIKE, ovec_slots=prog.nslots)
+        dev = torch.from_numpy(lines).cuda()
+        assert (prog.thompson_lines(dev, n, linelen, linelen).cpu().numpy() == want_t).all()
+        rc, ov = prog.pike_lines(dev, n, linelen, linelen)
+        assert (rc.cpu().numpy() == want_rc).all() and (ov.cpu().numpy() == want_ov).all()
+        assert int((rc == 0).sum()) >= n // 2
+        assert int(ov.max()) > 32767
+
+
 def test_pike_tier_selection(cu):
     """the configurations the bench reports must run on the fast tier: C3 (4
     groups, 10 slots, 1 KB lines) on the closure-table kernel"""
