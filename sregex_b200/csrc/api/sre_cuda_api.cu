@@ -789,12 +789,16 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
     }
     const bool big = cp->pike.nregexes > 1 || cp->pike.clo_npark > 64;
     const int k1 = ek1 > 0 ? ek1 : (big ? 12 : 4);
-    int k2 = ek2 > 0 ? ek2 : (big ? 32 : 8);
+    int k2 = ek2 > 0 ? ek2 : (big ? 32 : 16);
     /* no look-ahead assertion in the program: no pending closures to hold */
     const int h1 = cp->pike.clo_has_hold ? (ek1 > 0 ? eh1 : 2) : 0;
     const int h2 = cp->pike.clo_has_hold ? (ek2 > 0 ? eh2 : 4) : 0;
     if (cp->pike.clo_npark && (uint32_t) k2 > cp->pike.clo_npark) {
         k2 = (int) cp->pike.clo_npark;
+    }
+    /* wide capture vectors: shrink the retry lists until a block fits in shared memory */
+    while (k2 > k1 && !sre_pike_table_applicable(cp->pike, dev_offsets, linelen, k2, h2)) {
+        k2 = k2 - 4 > k1 ? k2 - 4 : k1;
     }
     if (sre_pike_table_applicable(cp->pike, dev_offsets, linelen, k2 > k1 ? k2 : k1, h2) && linelen < (1ull << 31)
         && g_pike_general_only == 0)
