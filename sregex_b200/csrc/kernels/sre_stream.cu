@@ -19,11 +19,11 @@
  *   k_stream_compose  one warp composes FAN = 256 consecutive functions (8 per
  *                     lane serially, then a 5-round shuffle tree) into one
  *                     function of the next level; loads are coalesced.
- *   k_stream_entries  walks one level down from exact entry states: one warp
- *                     per parent propagates the entry state across its lanes
- *                     and writes the exact entry state of all 256 children; at
- *                     level 0 it records the first piece whose step enters ACC
- *                     (= in which the reference's loop would return SRE_OK).
+ *   k_stream_descend  one warp walks back down from the true entry state along
+ *                     the only path that matters: at each level the child of
+ *                     the current parent whose step first enters ACC (= in
+ *                     which the reference's loop would return SRE_OK); also
+ *                     yields the state after the whole stream.
  *   k_stream_locate   one warp re-runs that piece to get the exact byte offset.
  *
  * Everything is exact: no result depends on a guess.
@@ -336,58 +336,75 @@ k_stream_compose(const uint8_t *__restrict__ in, size_t n_in, uint8_t *__restric
 }
 
 /*
- * One warp per parent p: from the exact entry state of p (parent_entry[p], or
- * root_state when parent_entry is NULL) compute the exact entry state of each
- * of its <= FAN children at this level.  exit_state (may be NULL) receives the
- * state after the last child of parent 0.  At level 0, first_acc is lowered to
- * the first child whose step enters ACC.
+ * The walk down needs one path only: at every level, the child of the current
+ * parent whose step takes a non-ACC state into ACC (ACC is absorbing, so that
+ * is the child in which the match is first seen).  One warp: per level it
+ * composes the <= FAN children of the parent (8 per lane), propagates the entry
+ * state across the lanes and picks the first such child.  Outputs: the state
+ * after the whole stream, the first piece whose step enters ACC (or ~0) and the
+ * exact entry state of that piece (entry0[piece], for k_stream_locate).
  */
+struct stream_levels_t {
+    const uint8_t *fn[4];
+    size_t         count[4];
+    int            top;
+};
+
 template <int NW>
-__global__ void __launch_bounds__(256)
-k_stream_entries(const uint8_t *__restrict__ fn, size_t n, const uint8_t *__restrict__ parent_entry,
-                 uint32_t root_state, size_t n_parent, uint8_t *entry, uint32_t acc, int level0,
+__global__ void __launch_bounds__(32)
+k_stream_descend(stream_levels_t lv, uint32_t root_state, uint32_t acc, uint8_t *entry0,
                  unsigned long long *first_acc, uint32_t *exit_state)
 {
-    const size_t p = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
-    if (p >= n_parent) {
-        return;
-    }
-    const size_t first = p * FAN + lane * PER_LANE;
-    fn_t<NW> total;
-    lane_compose<NW>(fn, first, n, total);
-
-    /* state entering each lane's run: serial over lanes, 32 cheap steps */
-    uint32_t s = parent_entry ? parent_entry[p] : root_state, mine = 0;
+    const uint32_t lane = threadIdx.x;
+    size_t parent = 0;
+    uint32_t s_in = root_state;
+    for (int l = lv.top; l >= 0; l--) {
+        const size_t n = lv.count[l], first = parent * FAN + lane * PER_LANE;
+        fn_t<NW> total;
+        lane_compose<NW>(lv.fn[l], first, n, total);
+        uint32_t s = s_in, mine = 0;
 #pragma unroll 4
-    for (uint32_t l = 0; l < 32; l++) {
-        if (lane == l) {
-            mine = s;
-        }
-        s = __shfl_sync(0xffffffffu, total.at(s), l);
-    }
-    if (exit_state && p == 0 && lane == 0) {
-        *exit_state = s;
-    }
-
-    s = mine;
-#pragma unroll
-    for (uint32_t k = 0; k < PER_LANE; k++) {
-        const size_t j = first + k;
-        if (j < n) {
-            fn_t<NW> g;
-            g.load(fn + j * (NW * 4));
-            entry[j] = (uint8_t) s;
-            const uint32_t nx = g.at(s);
-            if (level0 && nx == acc && s != acc) {
-                atomicMin(first_acc, (unsigned long long) j);
+        for (uint32_t k = 0; k < 32; k++) {
+            if (lane == k) {
+                mine = s;
             }
-            s = nx;
+            s = __shfl_sync(0xffffffffu, total.at(s), k);
         }
+        if (l == lv.top && lane == 0 && exit_state) {
+            *exit_state = s;
+        }
+        s = mine;
+        unsigned long long hit = ~0ull;
+        uint32_t hit_entry = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < PER_LANE; k++) {
+            const size_t j = first + k;
+            if (j < n && j < (parent + 1) * FAN) {
+                fn_t<NW> g;
+                g.load(lv.fn[l] + j * (NW * 4));
+                const uint32_t nx = g.at(s);
+                if (nx == acc && s != acc && hit == ~0ull) {
+                    hit = j;
+                    hit_entry = s;
+                }
+                s = nx;
+            }
+        }
+        const uint32_t who = __ffs(__ballot_sync(0xffffffffu, hit != ~0ull));
+        if (who == 0) {
+            if (lane == 0) {
+                *first_acc = ~0ull;
+            }
+            return;
+        }
+        parent = (size_t) __shfl_sync(0xffffffffu, hit, who - 1);
+        s_in = __shfl_sync(0xffffffffu, hit_entry, who - 1);
+    }
+    if (lane == 0) {
+        *first_acc = (unsigned long long) parent;
+        entry0[parent] = (uint8_t) s_in;
     }
 }
-
-__global__ void k_stream_reset(unsigned long long *first_acc) { *first_acc = ~0ull; }
 
 /* exact offset of the byte whose step enters ACC inside piece *first_acc */
 template <int NW>
@@ -510,19 +527,15 @@ template <int NW>
 cudaError_t walk_t(const sre_dev_dfa_t &dfa, uint32_t entry_state, const sre_stream_ws_t &ws,
     uint32_t *exit_state, cudaStream_t stream, int *launches)
 {
-    cudaError_t err;
-    const int top = top_level(ws);
-    if (launches) ++*launches;
-    k_stream_reset<<<1, 1, 0, stream>>>(ws.first_acc);
-    for (int l = top; l >= 0; l--) {
-        const size_t n_parent = l == top ? 1 : ws.count[l + 1];
-        if (launches) ++*launches;
-        k_stream_entries<NW><<<(unsigned) ((n_parent * 32 + 255) / 256), 256, 0, stream>>>(
-            ws.fn[l], ws.count[l], l == top ? nullptr : ws.entry[l + 1], entry_state, n_parent, ws.entry[l],
-            dfa.acc, l == 0, ws.first_acc, l == top ? exit_state : nullptr);
-        if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    stream_levels_t lv;
+    lv.top = top_level(ws);
+    for (int l = 0; l < 4; l++) {
+        lv.fn[l] = ws.fn[l];
+        lv.count[l] = ws.count[l];
     }
-    return cudaSuccess;
+    if (launches) ++*launches;
+    k_stream_descend<NW><<<1, 32, 0, stream>>>(lv, entry_state, dfa.acc, ws.entry[0], ws.first_acc, exit_state);
+    return cudaGetLastError();
 }
 
 }  // namespace
