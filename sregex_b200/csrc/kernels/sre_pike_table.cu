@@ -140,32 +140,21 @@ struct lane_t {
             m_prev &= ~bit;
         }
     }
-    /* dst vector <- src vector (src < 0: all -1) with the slots of `mask` set to pos */
+    /* dst vector <- src vector (src < 0: all -1) with the slots of `mask` set to pos:
+     * a plain copy, then one (half-)word store per SAVEd slot -- the same path
+     * for every lane, whatever its mask */
     __device__ __forceinline__ void derive(int dst, int src, uint32_t mask, int32_t pos)
     {
-        if (mask == 0 && src >= 0) {        /* the common case: nothing SAVEd on the way */
-            for (int j = 0; j < ncw_(); j++) {
-                w(dst + j) = w(src + j);
-            }
-            return;
+        for (int j = 0; j < ncw_(); j++) {
+            w(dst + j) = src < 0 ? -1 : w(src + j);
         }
-        if (C16) {
-            const uint32_t p16 = (uint32_t) pos & 0xffff;
-            for (int j = 0; j < ncw_(); j++) {
-                uint32_t v = src < 0 ? 0xffffffffu : (uint32_t) w(src + j);
-                const uint32_t m = (mask >> (2 * j)) & 3;
-                if (m & 1) {
-                    v = (v & 0xffff0000u) | p16;
-                }
-                if (m & 2) {
-                    v = (v & 0xffffu) | (p16 << 16);
-                }
-                w(dst + j) = (int32_t) v;
-            }
-        } else {
-            for (int j = 0; j < ncw_(); j++) {
-                const int32_t v = src < 0 ? -1 : w(src + j);
-                w(dst + j) = ((mask >> j) & 1) ? pos : v;
+        while (mask) {
+            const uint32_t slot = (uint32_t) __ffs((int) mask) - 1;
+            mask &= mask - 1;
+            if (C16) {
+                reinterpret_cast<int16_t *>(&w(dst + (int) (slot >> 1)))[slot & 1] = (int16_t) pos;
+            } else {
+                w(dst + (int) slot) = pos;
             }
         }
     }
