@@ -263,6 +263,10 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
      * stands for it (off once a match has cut the lower-priority threads) */
     bool any_alive = false;
     int cur = 0, ncl = 0, nnl = 0, hs = 0;
+    /* the byte at sp (NB_END at the end of the line) and the one before it,
+     * carried from step to step: one load per step */
+    int nb_cur = NB_END;
+    uint32_t prev_byte = 0;
 
     /*
      * closure P appended to the array (pcsec, capsec) of capacity capn at
@@ -380,10 +384,9 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
             any_alive = p_any != 0xffffffffu;
             active = true;
             /* first_buf: the initial closure at the start offset, :202-216 */
-            if (append_closure(len, sp, sp > 0 ? (uint32_t) input[sp - 1] : 0u,
-                               sp < size ? (int) input[sp] : NB_END, -1, c.L0PC, c.L0CAP, c.K, ncl, false, false)
-                < 0)
-            {
+            prev_byte = sp > 0 ? (uint32_t) input[sp - 1] : 0u;
+            nb_cur = sp < size ? (int) input[sp] : NB_END;
+            if (append_closure(len, sp, prev_byte, nb_cur, -1, c.L0PC, c.L0CAP, c.K, ncl, false, false) < 0) {
                 overflow = true;
             }
         }
@@ -392,12 +395,10 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
         if (!done) {
             c.marks_advance();          /* ctx->tag++ */
             const bool at_end = (sp == size);
-            const uint32_t byte = at_end ? 0 : input[sp];
+            const uint32_t byte = at_end ? 0 : (uint32_t) nb_cur;
             const bool cur_word = !at_end && isword(byte);
-            /* the byte the threads appended in this step will be stepped on, and (for
-             * the look-ahead closures of this position) the byte before this one */
+            /* the byte the threads appended in this step will be stepped on */
             const int nb_next = sp + 1 < size ? (int) input[sp + 1] : NB_END;
-            const uint32_t prev_byte = (HOLD && sp > 0) ? (uint32_t) input[sp - 1] : 0u;
             const int cl_pc = cur ? c.L1PC : c.L0PC, cl_cap = cur ? c.L1CAP : c.L0CAP;
             const int nl_pc = cur ? c.L0PC : c.L1PC, nl_cap = cur ? c.L0CAP : c.L1CAP;
             int i = 0;
@@ -494,6 +495,8 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
             nnl = 0;
             hs = 0;
             sp++;
+            prev_byte = byte;
+            nb_cur = nb_next;
             done = overflow || at_end || (ncl == 0 && !any_alive);
         }
 
