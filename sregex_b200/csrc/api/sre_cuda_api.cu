@@ -707,9 +707,6 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
     if (nlines == 0) {
         return SRE_OK;
     }
-    if (ensure_pike_scratch(cp, nlines) != SRE_OK) {
-        return SRE_ERROR;
-    }
     int launches = 0;
     cudaStream_t st = as_stream(stream);
     const int32_t *start = nullptr;
@@ -773,7 +770,6 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         lines.list = list;
         lines.count = count;
     }
-    const size_t nctx = cp->pike_nctx < nlines ? cp->pike_nctx : nlines;
     /* the table kernel's bookkeeping lives next to the packed-list count */
     sre_pike_work_t *work = reinterpret_cast<sre_pike_work_t *>(cp->line_ws + 3 * half + 64);
     /* closure-table kernel: list capacities of its two passes.  Small lists
@@ -800,9 +796,19 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
     while (k2 > k1 && !sre_pike_table_applicable(cp->pike, dev_offsets, linelen, k2, h2)) {
         k2 = k2 - 4 > k1 ? k2 - 4 : k1;
     }
-    if (sre_pike_table_applicable(cp->pike, dev_offsets, linelen, k2 > k1 ? k2 : k1, h2) && linelen < (1ull << 31)
-        && g_pike_general_only == 0)
-    {
+    const bool use_table = sre_pike_table_applicable(cp->pike, dev_offsets, linelen, k2 > k1 ? k2 : k1, h2)
+                           && linelen < (1ull << 31) && g_pike_general_only == 0;
+    const bool use_small = !use_table && sre_pike_small_applicable(cp->pike) && linelen < (1ull << 31)
+                           && g_pike_general_only != 1;
+    /* global-memory contexts of k_pike_lines: one per concurrent line when it
+     * does all the work, a few thousand when it only re-runs what a
+     * shared-memory tier gave up on */
+    if (ensure_pike_scratch(cp, (use_table || use_small) ? (nlines < 16384 ? nlines : 16384) : nlines) != SRE_OK) {
+        count_launches(launches);
+        return SRE_ERROR;
+    }
+    const size_t nctx = cp->pike_nctx < nlines ? cp->pike_nctx : nlines;
+    if (use_table) {
         /* the general kernel re-runs what the table kernel gave up on */
         g_pike_last_tier = 0;
         err = sre_launch_pike_table(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
@@ -818,7 +824,7 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
                                         nctx < 16384 ? nctx : 16384, 1, st, &launches,
                                         &work->given_up[two ? 1 : 0]);
         }
-    } else if (sre_pike_small_applicable(cp->pike) && linelen < (1ull << 31) && g_pike_general_only != 1) {
+    } else if (use_small) {
         /* shared-memory kernel first; the general kernel re-runs what it gave up on */
         g_pike_last_tier = 2;
         err = sre_launch_pike_small(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
