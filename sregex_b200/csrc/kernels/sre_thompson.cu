@@ -556,6 +556,17 @@ k_dfa_generic(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, const int64_t 
     const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, CLS);
     const uint8_t *tab = CLS ? reinterpret_cast<const uint8_t *>(dfa.tcls) : dfa.t256;
     const uint8_t *fin = dfa.fin, *cls = dfa.clsmap;
+    /* the byte-class map always sits in shared memory: it is on every byte's
+     * chain, and 256 bytes do not take anything from L1, which a table too
+     * large for shared memory lives on */
+    __shared__ uint8_t s_clsmap[256];
+    if (CLS && !SMEM_TAB) {
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+            s_clsmap[i] = dfa.clsmap[i];
+        }
+        __syncthreads();
+        cls = s_clsmap;
+    }
     if (SMEM_TAB) {
         load_table(smem, tab, plan.tab_bytes);
         load_table(smem + plan.fin_ofs, dfa.fin, align_up(dfa.nstates, 16));
