@@ -733,7 +733,10 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         int32_t *gate = reinterpret_cast<int32_t *>(cp->line_ws);
         int32_t *hint = reinterpret_cast<int32_t *>(cp->line_ws + half);
         cudaError_t e = tiled_hint
-            ? sre_launch_dfa_lines_hint(cp->dfa, dev_buf, nlines, pitch, linelen, gate, hint, st, &launches)
+            ? sre_launch_dfa_lines_hint(cp->dfa, dev_buf, nlines, pitch, linelen, gate, hint,
+                                        (cp->nleave >= 1 && cp->nleave <= 2 && linelen >= 128) ? cp->leave_pats
+                                                                                                : nullptr,
+                                        cp->nleave, st, &launches)
             : sre_launch_dfa_generic_hint(cp->dfa, dev_buf, dev_offsets, nlines, pitch, linelen, gate, hint, st,
                                           &launches);
         if (e != cudaSuccess) {

@@ -136,10 +136,12 @@ cudaError_t sre_launch_dfa_lines_skip(const sre_dev_dfa_t &dfa, const uint8_t *b
     int npat, int variant, cudaStream_t stream, int *launches);
 
 /* Thompson verdict + Pike start hint per line (needs dfa.h256, aligned lines):
- * hint[i] = offset after which no earlier-started thread is alive             */
+ * hint[i] = offset after which no earlier-started thread is alive; pats / npat
+ * (may be NULL / 0): the 1 or 2 byte values that leave the start state, as
+ * for sre_launch_dfa_lines_skip, to skip words no lane needs                  */
 cudaError_t sre_launch_dfa_lines_hint(const sre_dev_dfa_t &dfa, const uint8_t *buf,
     size_t nlines, size_t pitch, size_t linelen, int32_t *rc, int32_t *hint,
-    cudaStream_t stream, int *launches);
+    const uint32_t *pats, int npat, cudaStream_t stream, int *launches);
 
 /* same for any DFA size / alignment / ragged offsets (thread per line, dfa.hcls) */
 cudaError_t sre_launch_dfa_generic_hint(const sre_dev_dfa_t &dfa, const uint8_t *buf,

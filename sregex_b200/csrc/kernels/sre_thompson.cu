@@ -544,6 +544,111 @@ k_dfa_lines_hint(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, si
                                (size_t) gridDim.x * warps_per_block);
 }
 
+/*
+ * The same with the word skip of k_dfa_lines_skipw (NPAT = 1 or 2 "leave"
+ * bytes of the start state): a 4-byte word no lane needs is not looked up.  A
+ * lane that skips a word sits in the start state and the word holds no leave
+ * byte, so each of its bytes is one "only the .*? thread consumed it" and the
+ * hint moves to the end of the word; a lane already in ACC keeps its hint.
+ */
+template <int NPAT>
+struct hint_skip_consumer_t {
+    const uint8_t  *tab;        /* h256 in shared memory */
+    const uint8_t  *fin;
+    uint32_t        acc, start, s, pos, p0;
+    uint32_t        pat[2];
+    size_t          nlines;
+    int32_t        *rc, *hint;
+
+    __device__ __forceinline__ void begin() { s = start; pos = 0; p0 = 0; }
+    __device__ __forceinline__ void step(uint32_t addr)
+    {
+        s = tab[addr];
+        pos++;
+        if (s & 0x80) {
+            p0 = pos;
+        }
+    }
+    __device__ __forceinline__ uint32_t leave(uint32_t w) const
+    {
+        uint32_t h = 0;
+#pragma unroll
+        for (int p = 0; p < NPAT; p++) {
+            const uint32_t x = w ^ pat[p];
+            h |= (x - 0x01010101u) & ~x & 0x80808080u;
+        }
+        return h;
+    }
+    __device__ __forceinline__ void word(uint32_t w, bool look)
+    {
+        if (look) {
+            step(__byte_perm(w, s, 0x5540));
+            step(__byte_perm(w, s, 0x5541));
+            step(__byte_perm(w, s, 0x5542));
+            step(__byte_perm(w, s, 0x5543));
+        } else {
+            pos += 4;
+            if ((s & 0x7f) == start) {
+                p0 = pos;
+            }
+        }
+    }
+    __device__ __forceinline__ void chunk(const uint4 &v)
+    {
+        const uint32_t st = s & 0x7f;
+        uint32_t bits = (leave(v.x) ? 1u : 0u) | (leave(v.y) ? 2u : 0u) | (leave(v.z) ? 4u : 0u)
+                      | (leave(v.w) ? 8u : 0u);
+        bits = st == acc ? 0u : (st != start ? 15u : bits);
+        uint32_t m = __reduce_or_sync(0xffffffffu, bits);
+        m |= m << 1;
+        m |= m << 2;
+        word(v.x, m & 1);
+        word(v.y, m & 2);
+        word(v.z, m & 4);
+        word(v.w, m & 8);
+    }
+    __device__ __forceinline__ void byte(uint32_t b) { step((s << 8) | b); }
+    __device__ __forceinline__ void end(size_t group)
+    {
+        const size_t line = group * 32 + (threadIdx.x & 31);
+        if (line < nlines) {
+            const uint32_t st = s & 0x7f;
+            rc[line] = (st == acc || fin[st]) ? SRE_K_OK : SRE_K_DECLINED;
+            hint[line] = (int32_t) p0;
+        }
+    }
+};
+
+template <int NPAT>
+__global__ void __launch_bounds__(1024, 1)
+k_dfa_lines_hint_skip(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t nlines,
+                      uint32_t linelen, uint32_t pat0, uint32_t pat1, int32_t *__restrict__ rc,
+                      int32_t *__restrict__ hint)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const dfa_smem_plan_t plan = dfa_smem_plan(256, 0, false);
+    load_table(smem, dfa.h256, 65536);
+    load_table(smem + plan.fin_ofs, dfa.fin, align_up(dfa.nstates, 16));
+    __syncthreads();
+
+    const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    hint_skip_consumer_t<NPAT> cons;
+    cons.tab = smem;
+    cons.fin = smem + plan.fin_ofs;
+    cons.acc = dfa.acc;
+    cons.start = dfa.start;
+    cons.pat[0] = pat0;
+    cons.pat[1] = pat1;
+    cons.nlines = nlines;
+    cons.rc = rc;
+    cons.hint = hint;
+    tile_pipeline_tma_early<1>(cons, &tmap, nlines, linelen,
+                               smem + plan.stage_ofs + (size_t) warp * 32 * 128,
+                               reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES,
+                               (size_t) blockIdx.x * warps_per_block + warp,
+                               (size_t) gridDim.x * warps_per_block);
+}
+
 /* ---- k_dfa_generic --------------------------------------------------------- */
 
 template <bool CLS, bool SMEM_TAB>
@@ -1243,7 +1348,8 @@ cudaError_t sre_launch_dfa_generic_hint(const sre_dev_dfa_t &dfa, const uint8_t 
 }
 
 cudaError_t sre_launch_dfa_lines_hint(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines,
-    size_t pitch, size_t linelen, int32_t *rc, int32_t *hint, cudaStream_t stream, int *launches)
+    size_t pitch, size_t linelen, int32_t *rc, int32_t *hint, const uint32_t *pats, int npat,
+    cudaStream_t stream, int *launches)
 {
     if (nlines == 0) {
         return cudaSuccess;
@@ -1262,6 +1368,14 @@ cudaError_t sre_launch_dfa_lines_hint(const sre_dev_dfa_t &dfa, const uint8_t *b
     static bool attr_set = false;
     if (!attr_set) {
         err = cudaFuncSetAttribute(k_dfa_lines_hint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (err == cudaSuccess) {
+            err = cudaFuncSetAttribute(k_dfa_lines_hint_skip<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int) smem);
+        }
+        if (err == cudaSuccess) {
+            err = cudaFuncSetAttribute(k_dfa_lines_hint_skip<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int) smem);
+        }
         if (err != cudaSuccess) {
             return err;
         }
@@ -1276,8 +1390,17 @@ cudaError_t sre_launch_dfa_lines_hint(const sre_dev_dfa_t &dfa, const uint8_t *b
     if (launches) {
         ++*launches;
     }
-    k_dfa_lines_hint<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen, rc,
-                                                                  hint);
+    /* word skip when the start state is left by one or two byte values */
+    if (pats != nullptr && npat == 1) {
+        k_dfa_lines_hint_skip<1><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen,
+                                                                               pats[0], pats[0], rc, hint);
+    } else if (pats != nullptr && npat == 2) {
+        k_dfa_lines_hint_skip<2><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen,
+                                                                               pats[0], pats[1], rc, hint);
+    } else {
+        k_dfa_lines_hint<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen, rc,
+                                                                      hint);
+    }
     return cudaGetLastError();
 }
 

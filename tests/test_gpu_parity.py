@@ -374,6 +374,22 @@ def test_long_lines_32bit_captures(cu):
         assert int(ov.max()) > 32767
 
 
+@pytest.mark.parametrize("rx", [corpus.C2_REGEX, rb'[Hh]TTP/1\.[01]" (5\d\d) ', rb'(GET|PUT) (/x/\d+) '])
+def test_pike_with_word_skipping_hint_pass(cu, rx):
+    """literal-prefixed regexes (start state left by 1 or 2 byte values; the third
+    one by more, so it takes the plain hint kernel): the gate + start hint pass
+    skips words, and rc + ovector still equal the oracle's on 1 KB lines"""
+    n = 4096
+    lines = corpus.log_lines(n, 1024)
+    prog = cu.CudaProgram(rx)
+    _, want_rc, want_ov = baseline.run_lines("oracle", rx, None, lines.numpy(), n, 1024, 1024,
+                                             baseline.ENGINE_PIKE, nthreads=8, ovec_slots=prog.nslots)
+    rc, ov = prog.pike_lines(lines.cuda(), n, 1024, 1024)
+    assert (rc.cpu().numpy() == want_rc).all()
+    assert (ov.cpu().numpy() == want_ov).all()
+    assert 0 < int((rc == 0).sum()) < n
+
+
 def test_pike_tier_selection(cu):
     """the configurations the bench reports must run on the fast tier: C3 (4
     groups, 10 slots, 1 KB lines) on the closure-table kernel"""
