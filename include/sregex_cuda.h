@@ -72,7 +72,9 @@ SRE_API int sre_cuda_thompson_exec_ragged(sre_cuda_program_t *cp,
  * per line.  dev_rc[i] = matched regex id (>= 0), SRE_DECLINED or SRE_ERROR;
  * dev_ovec[i*ovec_slots ..] = what the reference leaves in the caller's ovector
  * (matched regex's groups, -1 fill; all -1 when there is no match).
- * dev_offsets may be NULL (fixed pitch).  dev_select: when given, only lines with
+ * dev_offsets may be NULL (fixed pitch); with dev_offsets, pitch is ignored and
+ * linelen, when non-zero, is an upper bound on the line lengths (below 32 KB it
+ * lets the kernels keep capture offsets in 16 bits).  dev_select: when given, only lines with
  * dev_select[i] == SRE_OK are run (others: rc = dev_select[i]), which lets a
  * Thompson pass gate the capture pass.  When dev_select is NULL and the lines
  * are aligned fixed-pitch, the library runs that gate itself with the

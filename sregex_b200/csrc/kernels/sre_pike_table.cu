@@ -383,10 +383,15 @@ k_pike_table(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
             cur = 0; ncl = 0; nnl = 0; hs = 0;
             any_alive = p_any != 0xffffffffu;
             active = true;
+            if (C16 && size > 32766) {      /* longer than the caller's bound: not with 16-bit offsets */
+                overflow = true;
+            }
             /* first_buf: the initial closure at the start offset, :202-216 */
             prev_byte = sp > 0 ? (uint32_t) input[sp - 1] : 0u;
             nb_cur = sp < size ? (int) input[sp] : NB_END;
-            if (append_closure(len, sp, prev_byte, nb_cur, -1, c.L0PC, c.L0CAP, c.K, ncl, false, false) < 0) {
+            if (!overflow
+                && append_closure(len, sp, prev_byte, nb_cur, -1, c.L0PC, c.L0CAP, c.K, ncl, false, false) < 0)
+            {
                 overflow = true;
             }
         }
@@ -534,10 +539,13 @@ size_t table_smem_bytes(const sre_dev_pike_t &pk, bool c16, int K, int H)
 
 }  // namespace
 
-/* 16-bit capture offsets when every line is shorter than 32 KB */
+/* 16-bit capture offsets when every line is shorter than 32 KB: linelen is the
+ * line length (fixed pitch) or, with offsets, the caller's upper bound on it
+ * (0 = none given).  A longer line met anyway is handed to the next tier. */
 static bool use_c16(const int64_t *offsets, size_t linelen)
 {
-    return offsets == nullptr && linelen < 32767;
+    (void) offsets;
+    return linelen != 0 && linelen < 32767;
 }
 
 bool sre_pike_table_applicable(const sre_dev_pike_t &pk, const int64_t *offsets, size_t linelen, int K, int H)

@@ -114,6 +114,9 @@ class CudaProgram:
                    offsets: torch.Tensor | None = None, select: torch.Tensor | None = None,
                    out_rc: torch.Tensor | None = None, out_ovec: torch.Tensor | None = None):
         n = self.nslots
+        if offsets is not None and linelen == 0 and nlines > 0:
+            # an upper bound on the line lengths lets the kernels pack capture offsets
+            linelen = int((offsets[1:nlines + 1] - offsets[:nlines]).max())
         rc = out_rc if out_rc is not None else torch.empty(nlines, dtype=torch.int32, device=buf.device)
         ov = out_ovec if out_ovec is not None else torch.empty((nlines, n), dtype=torch.int64,
                                                                device=buf.device)

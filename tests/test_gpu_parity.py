@@ -372,6 +372,11 @@ def test_long_lines_32bit_captures(cu):
         assert (rc.cpu().numpy() == want_rc).all() and (ov.cpu().numpy() == want_ov).all()
         assert int((rc == 0).sum()) >= n // 2
         assert int(ov.max()) > 32767
+        # the same lines as a ragged batch with a (wrong) caller's bound of 500 bytes: lines
+        # beyond what 16-bit capture offsets can hold are handed to the next tier, not mangled
+        off = torch.arange(0, (n + 1) * linelen, linelen, dtype=torch.int64, device="cuda")
+        rc2, ov2 = prog.pike_lines(dev.view(-1), n, 0, 500, offsets=off)
+        assert torch.equal(rc, rc2) and torch.equal(ov, ov2)
 
 
 @pytest.mark.parametrize("rx", [corpus.C2_REGEX, rb'[Hh]TTP/1\.[01]" (5\d\d) ', rb'(GET|PUT) (/x/\d+) '])
