@@ -160,7 +160,6 @@ def main():
     ap.add_argument("--variant", type=int, default=int(os.environ.get("SRE_VARIANT", "0")))
     ap.add_argument("--lines", type=int, default=NLINES)
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--l2promo", type=int, default=-1, help="TMA L2 promotion 0..3 (-1: library default)")
     ap.add_argument("--engine", default="auto", choices=["auto", "tiled", "skip", "generic", "nfa"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -190,9 +189,6 @@ def main():
         m = min(blk, n - i)
         dev[i:i + m] = corpus.log_lines(m, PITCH, device="cuda", first_line=rank * n + i)
     prog = cuda.CudaProgram(corpus.C2_REGEX)
-    cuda.set_variant(args.variant)
-    if args.l2promo >= 0:
-        cuda.lib().L.sre_cuda_set_l2_promotion(args.l2promo)
     rc = torch.empty(n, dtype=torch.int32, device="cuda")
     info = prog.info
 
@@ -202,6 +198,8 @@ def main():
     if engine_name == "auto":
         engine_name = ("nfa" if not info.dfa_states else
                        "dfa_skip" if 1 <= info.dfa_leave_bytes <= 2 else "dfa_tiled")
+
+    engine = cuda.engine_variant(engine, args.variant)
 
     def step():
         prog.thompson_lines(dev, n, PITCH, PITCH, engine=engine, out=rc)

@@ -10,6 +10,15 @@
  * device pointers; `stream` is a cudaStream_t passed as void* (NULL = default
  * stream).  Functions returning int give SRE_OK or SRE_ERROR unless noted; there
  * is no CPU fallback -- without a usable CUDA device they return SRE_ERROR.
+ *
+ * Threading: a lowered program is immutable.  Every call takes its device
+ * scratch from the device's stream-ordered memory pool on the caller's stream
+ * and returns it there, so one program may be used from any number of host
+ * threads and CUDA streams at the same time (the reference's JIT run time is
+ * re-entrant in the same way; its interpreter and Pike VM are not, since they
+ * write dedup tags into the program: sre_vm_thompson.c:284, sre_vm_pike.c:792).
+ * The host-buffer (*_host) and classic (sregex.h) entry points work on the
+ * calling thread's per-thread default stream.
  */
 #ifndef SREGEX_B200_SREGEX_CUDA_H
 #define SREGEX_B200_SREGEX_CUDA_H
@@ -29,9 +38,13 @@ enum {
     SRE_CUDA_ENGINE_DFA_TILED   = 1,    /* smem-staged thread-per-line DFA           */
     SRE_CUDA_ENGINE_DFA_GENERIC = 2,    /* thread-per-line DFA, any alignment        */
     SRE_CUDA_ENGINE_NFA         = 3,    /* warp-per-line bit-parallel NFA            */
-    SRE_CUDA_ENGINE_DFA_SKIP    = 4     /* DFA_TILED + first-byte skip (start state
-                                           left by <= 4 byte values)                 */
+    SRE_CUDA_ENGINE_DFA_SKIP    = 4     /* DFA_TILED + word skip; needs a start state
+                                           left by <= 4 byte values (AUTO picks it
+                                           when 1 or 2 byte values leave it)          */
 };
+/* tuning: launch shape of DFA_TILED / DFA_SKIP (0 = default); pass
+ * engine | SRE_CUDA_ENGINE_VARIANT(v) */
+#define SRE_CUDA_ENGINE_VARIANT(v)  (((v) & 0xff) << 8)
 
 typedef struct {
     uint32_t  prog_len;         /* bytecode instructions                            */
@@ -46,6 +59,10 @@ typedef struct {
     uint32_t  nregexes;
     uint32_t  pike_slots;       /* capture slots of the whole set                   */
     uint64_t  pike_ctx_bytes;   /* device scratch per concurrent Pike context       */
+    uint32_t  dfa_start;        /* DFA state a stream begins in                     */
+    uint32_t  dfa_acc;          /* absorbing "a step saw a live MATCH thread" state */
+    uint32_t  image_states;     /* states of the stream scan's image automaton      */
+    uint32_t  reserved;
 } sre_cuda_info_t;
 
 /* Lowering pass (host) + upload.  The batch analogue of
@@ -102,30 +119,51 @@ SRE_API int sre_cuda_pike_exec_lines_all(sre_cuda_program_t *cp,
 
 /*
  * Chunk-parallel form of a sequence of sre_vm_thompson_exec(ctx, chunk_k,
- * chunk_bytes, eof) calls over one long stream resident on the device.
+ * chunk_bytes, eof) calls over one long stream resident on the device
+ * (sre_vm_thompson.c:63-270; the carried thread lists are one DFA state here).
+ * Works for every program that has a DFA (any number of states).
  * *state_io carries the automaton state across calls (set it to
  * SRE_CUDA_STATE_INIT before the first call).  Returns SRE_OK / SRE_AGAIN /
  * SRE_DECLINED like the reference would after the last chunk; on SRE_OK
  * *match_chunk (if not NULL) is the index of the chunk_bytes-sized chunk in
- * which the reference's call sequence first returns SRE_OK.
+ * which the reference's call sequence first returns SRE_OK.  dev_buf must be
+ * 16-byte aligned.
  */
-#define SRE_CUDA_STATE_INIT  0xffffffffu
+#define SRE_CUDA_STATE_INIT     0xffffffffu     /* the state a stream begins in       */
+#define SRE_CUDA_STATE_UNKNOWN  0xfffffffeu     /* entry state not known (yet)        */
 SRE_API int sre_cuda_thompson_exec_stream(sre_cuda_program_t *cp,
     const uint8_t *dev_buf, size_t len, size_t chunk_bytes, unsigned eof,
     uint32_t *state_io, int64_t *match_chunk, void *stream);
 
 /*
- * Pieces of the stream scan, exposed for multi-GPU sharding: each
- * rank reduces its shard to one transfer function (nstates bytes, host), the
- * functions are all-gathered, composed in rank order, and each rank then
- * resolves its own first match with the entry state it was given.
+ * Pieces of the stream scan, exposed for multi-GPU sharding: every
+ * rank owns a contiguous part of the stream.
+ *   1. the ranks exchange halos: the last SRE_CUDA_STREAM_HALO bytes of each part;
+ *   2. _reduce turns a part into one record (SRE_CUDA_STREAM_FN_BYTES bytes,
+ *      host): the states the part can be entered in -- whatever the stream
+ *      held before the halo -- and the state each of them leads to.  dev_halo =
+ *      the preceding part's halo (device), or NULL with entry_state given (the
+ *      first part: SRE_CUDA_STATE_INIT) or SRE_CUDA_STATE_UNKNOWN;
+ *   3. the records are all-gathered; sre_cuda_stream_fn_apply chains them in
+ *      rank order from the stream's start state, which gives every rank its
+ *      true entry state (SRE_CUDA_STATE_UNKNOWN from a record that is still
+ *      unresolved: its rank must _resolve first and publish the new record);
+ *   4. _resolve yields the part's exit state and the offset (within the part)
+ *      of the step that first sees a match, -1 if none, and the part's record
+ *      again, now {entry -> exit}.
+ * The scan handle keeps the part's records on the device between 2 and 4.
  */
-SRE_API int sre_cuda_thompson_stream_reduce(sre_cuda_program_t *cp,
-    const uint8_t *dev_buf, size_t len, uint8_t *host_fn /* [dfa_states] */,
-    void *stream);
-SRE_API int sre_cuda_thompson_stream_resolve(sre_cuda_program_t *cp,
+#define SRE_CUDA_STREAM_FN_BYTES  32
+#define SRE_CUDA_STREAM_HALO      256
+typedef struct sre_cuda_stream_scan_s  sre_cuda_stream_scan_t;
+SRE_API sre_cuda_stream_scan_t *sre_cuda_thompson_stream_reduce(sre_cuda_program_t *cp,
+    const uint8_t *dev_buf, size_t len, const uint8_t *dev_halo, uint32_t entry_state,
+    uint8_t *host_fn /* [SRE_CUDA_STREAM_FN_BYTES], may be NULL */, void *stream);
+SRE_API int sre_cuda_thompson_stream_resolve(sre_cuda_stream_scan_t *scan,
     uint32_t entry_state, uint32_t *exit_state, int64_t *first_match_offset,
-    void *stream);
+    uint8_t *host_fn /* may be NULL */);
+SRE_API void sre_cuda_thompson_stream_free(sre_cuda_stream_scan_t *scan);
+SRE_API uint32_t sre_cuda_stream_fn_apply(const uint8_t *fn, uint32_t state);
 
 /* 1 if the EOF step of the lowered DFA sees a match in `state` (the rc an
  * sre_vm_thompson_exec(ctx, NULL, 0, eof=1) call would add: SRE_OK vs DECLINED) */
@@ -155,18 +193,16 @@ SRE_API int sre_cuda_index_lines(const uint8_t *dev_buf, size_t len,
     int64_t *dev_offsets, size_t max_lines, size_t *nlines, void *stream);
 
 /* Tuning / introspection */
-SRE_API void sre_cuda_set_variant(int variant);     /* tile shape of DFA_TILED   */
-SRE_API void sre_cuda_set_l2_promotion(int mode);   /* TMA L2 promotion: 0..3    */
-/* Pike tier used by sre_cuda_pike_exec_lines (tests): 0 = closure-table kernel,
- * then the general kernel for what it gives up on (default); 1 = general kernel
- * only; 2 = walking shared-memory kernel instead of the table kernel           */
-SRE_API void sre_cuda_set_pike_general_only(int mode);
-/* which of those the last sre_cuda_pike_exec_lines call used (0 / 1 / 2), -1: none yet */
-SRE_API int sre_cuda_pike_last_tier(void);
-SRE_API void sre_cuda_set_stream_piece(int bytes);  /* stream scan piece: 1024..8192 */
+/* Pike tier sre_cuda_pike_exec_lines may use for this program (tests): 0 =
+ * closure-table kernel, then the general kernel for what it gives up on
+ * (default); 1 = general kernel only; 2 = walking shared-memory kernel instead
+ * of the table kernel */
+SRE_API void sre_cuda_program_set_pike_tier(sre_cuda_program_t *cp, int mode);
+/* which of those the last sre_cuda_pike_exec_lines call on the program used, -1: none yet */
+SRE_API int sre_cuda_program_last_pike_tier(sre_cuda_program_t *cp);
 SRE_API long sre_cuda_launch_count(int reset);      /* kernels launched so far   */
 SRE_API int sre_cuda_device_available(void);        /* 1 if a CUDA device works  */
-SRE_API const char *sre_cuda_last_error(void);
+SRE_API const char *sre_cuda_last_error(void);      /* of the calling thread     */
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,8 @@
  *
  * It applies literally the step rule documented in sre_lower.h.
  */
+#include <cstring>
+
 #include "../sregex_b200/csrc/lower/sre_lower.h"
 
 struct lc_t {
@@ -328,4 +330,153 @@ extern "C" long lc_table_pike(sre_program_t *prog, const uint8_t *input, long si
         ovec[s] = s < cnt ? matched_cap[s] : -1;
     }
     return matched_id;
+}
+
+/*
+ * Host model of the candidate-based stream scan of kernels/sre_stream.cu (see
+ * sre_image.h): per piece the image automaton walks the `window` bytes before
+ * the piece and yields the candidate entry states; the piece is run from each;
+ * the pieces are then chained by looking the carried state up among the
+ * candidates.  A piece whose window stays wide is "unresolved" and run from the
+ * carried state itself.  Checks the claim the kernels rest on -- the carried
+ * state is always among the candidates -- on the CPU:
+ * returns 0, or -2 when a carried state was not among a piece's candidates.
+ * out[0] = exit state, out[1] = offset of the step entering ACC (-1: none),
+ * out[2] = unresolved pieces, out[3] = largest candidate count seen.
+ */
+#include "../sregex_b200/csrc/lower/sre_image.h"
+
+extern "C" int lc_stream_model(lc_t *lc, const uint8_t *buf, size_t len, size_t piece, size_t window,
+    unsigned K, unsigned entry, long long *out)
+{
+    const sre_dfa_t &d = lc->low.dfa;
+    if (!lc->low.has_dfa) return SRE_ERROR;
+    sre_image_t U;
+    if (!sre_build_image_automaton(d, K, 60000, 512, U)) return SRE_ERROR;
+    const uint32_t C = d.nclasses;
+    auto step = [&](uint32_t s, uint8_t b) -> uint32_t {
+        return s == d.acc ? s : d.trans[(size_t) s * C + d.clsmap[b]];
+    };
+    uint32_t s = entry;
+    long long first = -1, unresolved = 0, maxc = 0;
+    for (size_t p = 0; p < len || p == 0; p += piece) {
+        const size_t e = p + piece < len ? p + piece : len;
+        std::vector<uint32_t> cand;
+        bool resolved = true;
+        if (p == 0) {
+            cand.push_back(entry);
+        } else {
+            resolved = false;
+            for (size_t w = window; !resolved; w *= 16) {
+                const size_t from = w < p ? p - w : 0;
+                uint32_t u = 0;
+                for (size_t i = from; i < p; i++) {
+                    u = U.trans[(size_t) u * C + d.clsmap[buf[i]]];
+                }
+                if (U.ncand[u] != 0xff) {
+                    resolved = true;
+                    for (uint32_t j = 0; j < U.ncand[u]; j++) cand.push_back(U.cand[(size_t) u * K + j]);
+                }
+                if (from == 0 || w >= piece) break;
+            }
+        }
+        if ((long long) cand.size() > maxc) maxc = (long long) cand.size();
+        uint32_t t = s;
+        if (s == d.acc) {
+            /* absorbed earlier */
+        } else if (!resolved) {
+            unresolved++;
+            for (size_t i = p; i < e; i++) t = step(t, buf[i]);
+        } else {
+            bool found = false;
+            for (uint32_t c0 : cand) {
+                if (c0 == s) found = true;
+            }
+            if (!found) return -2;
+            for (size_t i = p; i < e; i++) t = step(t, buf[i]);
+        }
+        if (t == d.acc && s != d.acc && first < 0) {
+            uint32_t x = s;
+            for (size_t i = p; i < e; i++) {
+                x = step(x, buf[i]);
+                if (x == d.acc) { first = (long long) i; break; }
+            }
+        }
+        s = t;
+        if (len == 0) break;
+    }
+    out[0] = s;
+    out[1] = first;
+    out[2] = unresolved;
+    out[3] = maxc;
+    return 0;
+}
+
+/* image automaton statistics: out[0] = U-states, out[1] = narrow ones */
+extern "C" int lc_image_info(lc_t *lc, unsigned K, unsigned *out)
+{
+    sre_image_t U;
+    if (!lc->low.has_dfa || !sre_build_image_automaton(lc->low.dfa, K, 60000, 512, U)) return SRE_ERROR;
+    out[0] = U.nstates;
+    out[1] = 0;
+    for (uint32_t u = 0; u < U.nstates; u++) out[1] += U.ncand[u] != 0xff;
+    return SRE_OK;
+}
+
+/*
+ * CPU stand-in for sre_cuda_thompson_stream_reduce in the world_size-2 gloo
+ * tests: the record of a whole stream part in the format of kernels/sre_stream.cu
+ * (8 candidate entry states as u16, then the 8 states they lead to; 0xffff =
+ * empty slot; first candidate 0xfffe = unresolved).  Candidates: {entry} when
+ * known (entry != 0xfffffffe), else the image of all states under the halo.
+ */
+extern "C" int lc_stream_part_record(lc_t *lc, const uint8_t *buf, size_t len, const uint8_t *halo, size_t halo_len,
+    unsigned entry, uint8_t *out32)
+{
+    const sre_dfa_t &d = lc->low.dfa;
+    const unsigned K = 8;
+    if (!lc->low.has_dfa) return SRE_ERROR;
+    uint16_t rec[16];
+    for (int i = 0; i < 16; i++) rec[i] = 0xffff;
+    std::vector<uint32_t> cand;
+    if (entry != 0xfffffffeu) {
+        if (entry != d.acc) cand.push_back(entry);
+    } else if (halo == NULL) {
+        rec[0] = 0xfffe;
+        memcpy(out32, rec, 32);
+        return SRE_OK;
+    } else {
+        sre_image_t U;
+        if (!sre_build_image_automaton(d, K, 60000, 512, U)) return SRE_ERROR;
+        uint32_t u = 0;
+        for (size_t i = 0; i < halo_len; i++) u = U.trans[(size_t) u * d.nclasses + d.clsmap[halo[i]]];
+        if (U.ncand[u] == 0xff) {
+            rec[0] = 0xfffe;
+            memcpy(out32, rec, 32);
+            return SRE_OK;
+        }
+        for (uint32_t j = 0; j < U.ncand[u]; j++) cand.push_back(U.cand[(size_t) u * K + j]);
+    }
+    for (size_t j = 0; j < cand.size(); j++) {
+        uint32_t s = cand[j];
+        for (size_t i = 0; i < len && s != d.acc; i++) s = d.trans[(size_t) s * d.nclasses + d.clsmap[buf[i]]];
+        rec[j] = (uint16_t) cand[j];
+        rec[8 + j] = (uint16_t) s;
+    }
+    memcpy(out32, rec, 32);
+    return SRE_OK;
+}
+
+/* exit state and offset of the first step entering ACC (-1) of a part run from `entry` */
+extern "C" long long lc_stream_part_run(lc_t *lc, const uint8_t *buf, size_t len, unsigned entry, unsigned *exit_state)
+{
+    const sre_dfa_t &d = lc->low.dfa;
+    uint32_t s = entry;
+    long long first = -1;
+    for (size_t i = 0; i < len && s != d.acc; i++) {
+        s = d.trans[(size_t) s * d.nclasses + d.clsmap[buf[i]]];
+        if (s == d.acc) first = (long long) i;
+    }
+    *exit_state = s;
+    return first;
 }

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -22,19 +23,11 @@
 #include "../kernels/sre_kernels.cuh"
 #include "../lower/sre_lower.h"
 #include "../lower/sre_closure.h"
-
-/* measurement aid: pure TMA streaming of a line corpus (no automaton) */
-cudaError_t sre_launch_tma_ceiling(const uint8_t *buf, size_t nlines, size_t pitch, size_t linelen,
-    int32_t *rc, int variant, cudaStream_t stream);
-
-void sre_dev_set_l2_promotion(int mode);
+#include "../lower/sre_image.h"
 
 namespace {
 
-std::atomic<long>   g_launches(0);
-int                 g_variant = 0;
-int                 g_pike_general_only = 0;    /* tests: force k_pike_lines */
-std::atomic<int>    g_pike_last_tier{-1};       /* tier of the last sre_cuda_pike_exec_lines */
+std::atomic<long>   g_launches(0);     /* statistics only */
 thread_local char   g_err[256] = "";
 
 const uint32_t MAX_DFA_STATES = 16384;    /* beyond: the NFA tier (the table is read from L2 when it exceeds shared memory) */
@@ -60,6 +53,56 @@ int fail(const char *fmt, ...)
     } while (0)
 
 void count_launches(int n) { g_launches += n; }
+
+/*
+ * Per-call device scratch.  Nothing mutable lives in a program: every entry
+ * point takes what it needs from the device's stream-ordered pool
+ * (cudaMallocAsync) on the caller's stream and gives it back on the same stream
+ * when the call returns, so one program can be used from any number of host
+ * threads and CUDA streams at once.  The pool keeps freed blocks (release
+ * threshold = never), so a steady caller pays for the allocation once.
+ */
+void pool_keep_memory()
+{
+    static std::once_flag once[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) {
+        return;
+    }
+    std::call_once(once[dev], [dev]() {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    });
+}
+
+struct scratch_t {
+    uint8_t      *p = nullptr;
+    cudaStream_t  st = nullptr;
+    scratch_t() {}
+    scratch_t(const scratch_t &) = delete;
+    scratch_t &operator=(const scratch_t &) = delete;
+    ~scratch_t() { release(); }
+    cudaError_t alloc(size_t bytes, cudaStream_t stream)
+    {
+        release();
+        pool_keep_memory();
+        st = stream;
+        void *q = nullptr;
+        cudaError_t e = cudaMallocAsync(&q, bytes ? bytes : 16, stream);
+        p = static_cast<uint8_t *>(q);
+        return e;
+    }
+    void release()
+    {
+        if (p) {
+            cudaFreeAsync(p, st);
+            p = nullptr;
+        }
+    }
+};
 
 bool device_ok()
 {
@@ -91,33 +134,25 @@ struct blob_t {
 
 }  // namespace
 
+/* Immutable after sre_cuda_program_create (apart from the two tuning words at
+ * the end): all run-time state lives in per-call scratch or in contexts. */
 struct sre_cuda_program_s {
     sre_program_t      *prog = nullptr;
     sre_lowered_t       low;
+    sre_image_t         image;                  /* stream scan: image automaton of the DFA */
     uint8_t            *d_blob = nullptr;
-    bool                has_dfa = false, has_nfa = false;
+    bool                has_dfa = false, has_nfa = false, has_image = false;
     sre_dev_dfa_t       dfa;
+    sre_dev_image_t     img;
     sre_dev_nfa_t       nfa;
     sre_dev_pike_t      pike;
     uint32_t            nfa_shift = 0;
     /* byte values that leave the DFA start state (skip-scan tier), <= 4 kept */
     int                 nleave = 0;             /* -1: more than 4               */
     uint32_t            leave_pats[4] = { 0, 0, 0, 0 };
-    /* lazily grown workspaces */
-    uint8_t            *pike_scratch = nullptr;
-    size_t              pike_nctx = 0;
-    uint8_t            *stream_ws = nullptr;
-    size_t              stream_ws_bytes = 0;
-    sre_stream_ws_t     ws;
-    uint32_t           *d_exit = nullptr;       /* exit state + match offset */
-    uint8_t            *line_ws = nullptr;      /* gate verdict + start hint */
-    size_t              line_ws_bytes = 0;
-    uint8_t            *io_buf = nullptr;       /* host-variant staging      */
-    size_t              io_bytes = 0;
-    /* stream_reduce -> stream_resolve hand-over */
-    const uint8_t      *red_buf = nullptr;
-    size_t              red_len = 0;
-    int                 red_top = 0;
+    /* tests: which Pike tier sre_cuda_pike_exec_lines may use / used last */
+    std::atomic<int>    pike_tier_mode{0};
+    std::atomic<int>    pike_last_tier{-1};
 };
 
 namespace {
@@ -129,11 +164,6 @@ void program_destroy(void *data)
         cp->prog->lowered = nullptr;
     }
     cudaFree(cp->d_blob);
-    cudaFree(cp->pike_scratch);
-    cudaFree(cp->stream_ws);
-    cudaFree(cp->d_exit);
-    cudaFree(cp->io_buf);
-    cudaFree(cp->line_ws);
     delete cp;
 }
 
@@ -143,6 +173,7 @@ int upload(sre_cuda_program_t *cp)
     const sre_nfa_t &n = cp->low.nfa;
     blob_t b;
     size_t o_t256 = 0, o_tcls = 0, o_dcls = 0, o_fin = 0, o_h256 = 0, o_hcls = 0, o_hmap = 0;
+    size_t o_itrans = 0, o_icand = 0, o_incand = 0;
 
     cp->has_dfa = cp->low.has_dfa;
     if (cp->has_dfa) {
@@ -160,6 +191,13 @@ int upload(sre_cuda_program_t *cp)
         o_tcls = b.add(d.trans.data(), d.trans.size() * 2);
         o_dcls = b.add(d.clsmap, 256);
         o_fin = b.add(d.fin.data(), d.fin.size());
+        /* image automaton for the stream scan: narrow sets up to 60000, 512 wide ones */
+        cp->has_image = sre_build_image_automaton(d, SRE_STREAM_K, 60000, 512, cp->image);
+        if (cp->has_image) {
+            o_itrans = b.add(cp->image.trans.data(), cp->image.trans.size() * 2);
+            o_icand = b.add(cp->image.cand.data(), cp->image.cand.size() * 2);
+            o_incand = b.add(cp->image.ncand.data(), cp->image.ncand.size());
+        }
     }
 
     /* NFA tables, every bitset row padded to WP = 32 * words-per-lane words */
@@ -306,6 +344,14 @@ int upload(sre_cuda_program_t *cp)
         cp->dfa.hcls = d.hcls.empty() ? nullptr : reinterpret_cast<const uint16_t *>(base + o_hcls);
         cp->dfa.hclsmap = d.hcls.empty() ? nullptr : base + o_hmap;
         cp->dfa.hncls = d.hncls;
+        if (cp->has_image) {
+            cp->img.nstates = cp->image.nstates;
+            cp->img.nclasses = cp->image.nclasses;
+            cp->img.K = cp->image.K;
+            cp->img.trans = reinterpret_cast<const uint16_t *>(base + o_itrans);
+            cp->img.cand = reinterpret_cast<const uint16_t *>(base + o_icand);
+            cp->img.ncand = base + o_incand;
+        }
         cp->nleave = 0;
         if (!d.t256.empty()) {
             for (unsigned bv = 0; bv < 256 && cp->nleave >= 0; bv++) {
@@ -414,7 +460,7 @@ int upload(sre_cuda_program_t *cp)
 
 cudaStream_t as_stream(void *s) { return static_cast<cudaStream_t>(s); }
 
-/* pick the Thompson tier for a line batch */
+/* pick the Thompson tier for a line batch; engine: SRE_CUDA_ENGINE_* | variant << 8 */
 int thompson_dispatch(sre_cuda_program_t *cp, const uint8_t *dev_buf, const int64_t *dev_offsets,
     size_t nlines, size_t pitch, size_t linelen, int32_t *dev_rc, int engine, cudaStream_t st)
 {
@@ -422,6 +468,8 @@ int thompson_dispatch(sre_cuda_program_t *cp, const uint8_t *dev_buf, const int6
     cudaError_t err;
     const bool aligned = dev_offsets == nullptr && (reinterpret_cast<uintptr_t>(dev_buf) & 15) == 0
                          && (pitch & 15) == 0 && linelen <= pitch && linelen < (1ull << 31);
+    const int variant = (engine >> 8) & 0xff;
+    engine &= 0xff;
 
     if (engine == SRE_CUDA_ENGINE_AUTO) {
         engine = !cp->has_dfa ? SRE_CUDA_ENGINE_NFA
@@ -436,14 +484,13 @@ int thompson_dispatch(sre_cuda_program_t *cp, const uint8_t *dev_buf, const int6
                         "values, and 16-byte aligned fixed-pitch lines");
         }
         err = sre_launch_dfa_lines_skip(cp->dfa, dev_buf, nlines, pitch, linelen, dev_rc, cp->leave_pats,
-                                        cp->nleave, g_variant, st, &launches);
+                                        cp->nleave, variant, st, &launches);
         break;
     case SRE_CUDA_ENGINE_DFA_TILED:
         if (!cp->has_dfa || !aligned) {
             return fail("DFA_TILED engine needs a DFA and 16-byte aligned fixed-pitch lines");
         }
-        err = sre_launch_dfa_lines(cp->dfa, dev_buf, nlines, pitch, linelen, dev_rc,
-                                   g_variant >= 30 ? 0 : g_variant, st, &launches);
+        err = sre_launch_dfa_lines(cp->dfa, dev_buf, nlines, pitch, linelen, dev_rc, variant, st, &launches);
         if (err == cudaErrorInvalidConfiguration) {
             /* table too large for shared memory next to the staging rings */
             err = sre_launch_dfa_ragged(cp->dfa, dev_buf, dev_offsets, nlines, pitch, linelen, dev_rc,
@@ -475,7 +522,8 @@ int thompson_dispatch(sre_cuda_program_t *cp, const uint8_t *dev_buf, const int6
     return SRE_OK;
 }
 
-int ensure_pike_scratch(sre_cuda_program_t *cp, size_t nlines)
+/* how many global-memory Pike contexts a call over nlines lines gets */
+size_t pike_contexts(const sre_cuda_program_t *cp, size_t nlines)
 {
     static long cap = -1;       /* SRE_PIKE_NCTX: concurrency override (tuning) */
     if (cap < 0) {
@@ -486,34 +534,46 @@ int ensure_pike_scratch(sre_cuda_program_t *cp, size_t nlines)
     size_t want = nlines < max_ctx ? nlines : max_ctx;
     const size_t by_budget = PIKE_SCRATCH_BUDGET / cp->pike.ctx_stride;
     if (want > by_budget) {
-        want = by_budget ? by_budget : 1;
+        want = by_budget;
     }
-    if (want == 0) {
-        want = 1;
-    }
-    if (cp->pike_nctx >= want) {
-        return SRE_OK;
-    }
-    cudaFree(cp->pike_scratch);
-    cp->pike_scratch = nullptr;
-    cp->pike_nctx = 0;
-    /* contexts are interleaved in groups of 32 (sre_pike.cu: batch_base) */
-    CUDA_TRY(cudaMalloc(&cp->pike_scratch, ((want + 31) / 32 * 32) * cp->pike.ctx_stride));
-    cp->pike_nctx = want;
-    return SRE_OK;
+    return want ? want : 1;
 }
 
+/* contexts are interleaved in groups of 32 (sre_pike.cu: batch_base) */
+size_t pike_scratch_bytes(const sre_cuda_program_t *cp, size_t nctx)
+{
+    return ((nctx + 31) / 32 * 32) * cp->pike.ctx_stride;
+}
+
+}  // namespace
+
+/* one reduced stream part: its records (all levels) stay on the device until
+ * the part has been resolved with its true entry state */
+struct sre_cuda_stream_scan_s {
+    sre_cuda_program_t *cp = nullptr;
+    const uint8_t      *buf = nullptr;
+    size_t              len = 0;
+    cudaStream_t        st = nullptr;
+    scratch_t           mem;
+    sre_stream_ws_t     ws;
+    int                 top = 0;
+    /* device results: [0] fixed piece, [1] exit state | entry of the ACC piece, [2] match offset */
+    unsigned long long *d_res = nullptr;
+};
+
+namespace {
+
 /* size the levels of the stream scan and carve the workspace */
-int ensure_stream_ws(sre_cuda_program_t *cp, size_t len)
+int stream_scan_alloc(sre_cuda_stream_scan_t *sc)
 {
     const size_t piece = sre_stream_piece_bytes(), fan = sre_stream_fan();
-    const uint32_t fs = sre_stream_fn_stride(cp->dfa.nstates);
-    sre_stream_ws_t &ws = cp->ws;
-    size_t cnt = len / piece + ((len % piece) || len == 0 ? 1 : 0), total = 0;
+    const size_t fs = SRE_STREAM_FN_BYTES;
+    sre_stream_ws_t &ws = sc->ws;
+    size_t cnt = sc->len / piece + ((sc->len % piece) || sc->len == 0 ? 1 : 0), total = 0;
     int l = 0;
     for (;; l++) {
         ws.count[l] = cnt;
-        total += ((cnt * fs + 255) & ~(size_t) 255) + ((cnt + 255) & ~(size_t) 255);
+        total += (cnt * fs + 255) & ~(size_t) 255;
         if (cnt <= fan || l == 3) {
             break;
         }
@@ -522,34 +582,118 @@ int ensure_stream_ws(sre_cuda_program_t *cp, size_t len)
     if (ws.count[l] > fan) {
         return fail("stream too long for the 4-level scan");
     }
+    sc->top = l;
     for (int k = l + 1; k < 4; k++) {
         ws.count[k] = 0;
+        ws.fn[k] = nullptr;
     }
     total += 256;
-    if (cp->stream_ws_bytes < total) {
-        cudaFree(cp->stream_ws);
-        cp->stream_ws = nullptr;
-        cp->stream_ws_bytes = 0;
-        CUDA_TRY(cudaMalloc(&cp->stream_ws, total));
-        cp->stream_ws_bytes = total;
-    }
-    uint8_t *p = cp->stream_ws;
+    CUDA_TRY(sc->mem.alloc(total, sc->st));
+    uint8_t *p = sc->mem.p;
     for (int k = 0; k <= l; k++) {
         ws.fn[k] = p;
         p += (ws.count[k] * fs + 255) & ~(size_t) 255;
-        ws.entry[k] = p;
-        p += (ws.count[k] + 255) & ~(size_t) 255;
     }
     ws.first_acc = reinterpret_cast<unsigned long long *>(p);
-    if (cp->d_exit == nullptr) {
-        CUDA_TRY(cudaMalloc(&cp->d_exit, 64));
+    sc->d_res = reinterpret_cast<unsigned long long *>(p + 64);
+    return SRE_OK;
+}
+
+/* the top level's records composed into the part's one record (host) */
+int stream_root_record(sre_cuda_stream_scan_t *sc, uint8_t *host_fn)
+{
+    std::vector<uint8_t> top(sc->ws.count[sc->top] * SRE_STREAM_FN_BYTES);
+    CUDA_TRY(cudaMemcpyAsync(top.data(), sc->ws.fn[sc->top], top.size(), cudaMemcpyDeviceToHost, sc->st));
+    CUDA_TRY(cudaStreamSynchronize(sc->st));
+    sre_stream_fn_identity(host_fn);
+    for (size_t j = 0; j < sc->ws.count[sc->top]; j++) {
+        sre_stream_fn_compose(host_fn, &top[j * SRE_STREAM_FN_BYTES]);
     }
     return SRE_OK;
 }
 
-bool stream_capable(const sre_cuda_program_t *cp)
+int stream_reduce(sre_cuda_program_t *cp, const uint8_t *dev_buf, size_t len, const uint8_t *dev_halo,
+    uint32_t entry, cudaStream_t st, sre_cuda_stream_scan_t **out)
 {
-    return cp->has_dfa && cp->dfa.t256 != nullptr && cp->dfa.nstates <= 32;
+    *out = nullptr;
+    if (!cp->has_dfa || !cp->has_image) {
+        return fail("the stream scan needs the determinised program (this one exceeded %u DFA states)",
+                    MAX_DFA_STATES);
+    }
+    if (reinterpret_cast<uintptr_t>(dev_buf) & 15) {
+        return fail("stream buffer must be 16-byte aligned");
+    }
+    if (entry != SRE_STREAM_UNKNOWN && entry >= cp->dfa.nstates) {
+        return fail("bad stream state");
+    }
+    sre_cuda_stream_scan_t *sc = new (std::nothrow) sre_cuda_stream_scan_t();
+    if (sc == nullptr) {
+        return fail("out of memory");
+    }
+    sc->cp = cp;
+    sc->buf = dev_buf;
+    sc->len = len;
+    sc->st = st;
+    if (stream_scan_alloc(sc) != SRE_OK) {
+        delete sc;
+        return SRE_ERROR;
+    }
+    int launches = 0;
+    cudaError_t err = sre_launch_dfa_stream_reduce(cp->dfa, cp->img, dev_buf, len, dev_halo, entry, sc->ws, st,
+                                                   &launches);
+    count_launches(launches);
+    if (err != cudaSuccess) {
+        delete sc;
+        return fail("stream kernels failed: %s", cudaGetErrorString(err));
+    }
+    *out = sc;
+    return SRE_OK;
+}
+
+/*
+ * With the true entry state: repair the unresolved pieces (normally none), walk
+ * down to the first match.  One device round trip when nothing needs repair.
+ */
+int stream_resolve(sre_cuda_stream_scan_t *sc, uint32_t entry, uint32_t *exit_state, int64_t *match_offset,
+    size_t *repaired)
+{
+    sre_cuda_program_t *cp = sc->cp;
+    struct { unsigned long long fixed; uint32_t out[2]; long long off; } h;
+    size_t rounds = 0;
+    for (int burst = 1;; burst = 16) {
+        int launches = 0;
+        cudaError_t err = cudaSuccess;
+        for (int i = 0; i < burst && err == cudaSuccess; i++) {
+            err = sre_launch_dfa_stream_fix(cp->dfa, sc->buf, sc->len, entry, sc->ws, sc->d_res, sc->st, &launches);
+        }
+        if (err == cudaSuccess) {
+            err = sre_launch_dfa_stream_walk(cp->dfa, cp->img, sc->buf, sc->len, entry, sc->ws,
+                                             reinterpret_cast<uint32_t *>(sc->d_res + 1),
+                                             reinterpret_cast<long long *>(sc->d_res + 2), sc->st, &launches);
+        }
+        count_launches(launches);
+        if (err != cudaSuccess) {
+            return fail("stream kernels failed: %s", cudaGetErrorString(err));
+        }
+        CUDA_TRY(cudaMemcpyAsync(&h, sc->d_res, sizeof(h), cudaMemcpyDeviceToHost, sc->st));
+        CUDA_TRY(cudaStreamSynchronize(sc->st));
+        if (h.fixed == ~0ull) {
+            break;              /* the last repair round found nothing left: the walk is valid */
+        }
+        rounds += burst;
+        if (rounds > sc->ws.count[0] + 16) {
+            return fail("stream scan: repair does not terminate");
+        }
+    }
+    if (h.out[0] == 0xffffffffu) {
+        return fail("stream scan: a piece does not know the state it was entered in");
+    }
+    *exit_state = h.out[0];
+    *match_offset = entry == cp->dfa.acc ? 0 : h.off;
+    if (repaired) {
+        *repaired = rounds;
+    }
+    return SRE_OK;
 }
 
 }  // namespace
@@ -562,7 +706,7 @@ extern "C" {
 
 SRE_API int sre_cuda_device_available(void) { return device_ok() ? 1 : 0; }
 SRE_API const char *sre_cuda_last_error(void) { return g_err; }
-SRE_API void sre_cuda_set_variant(int variant) { g_variant = variant; }
+
 SRE_API int
 sre_cuda_index_lines(const uint8_t *dev_buf, size_t len, int64_t *dev_offsets, size_t max_lines, size_t *nlines,
     void *stream)
@@ -572,23 +716,15 @@ sre_cuda_index_lines(const uint8_t *dev_buf, size_t len, int64_t *dev_offsets, s
     }
     cudaStream_t st = as_stream(stream);
     const size_t need = sre_lines_workspace_bytes(len);
-    /* block counts: a grow-only workspace per host thread (cudaMalloc / cudaFree
-     * per call would cost more than the three kernels) */
-    static thread_local unsigned long long *ws = nullptr;
-    static thread_local size_t ws_bytes = 0;
-    if (ws_bytes < need) {
-        cudaFree(ws);
-        ws = nullptr;
-        ws_bytes = 0;
-        CUDA_TRY(cudaMalloc(&ws, need + need / 2));
-        ws_bytes = need + need / 2;
-    }
+    scratch_t ws;
+    CUDA_TRY(ws.alloc(need, st));
+    unsigned long long *w = reinterpret_cast<unsigned long long *>(ws.p);
     int launches = 0;
-    cudaError_t err = sre_launch_index_lines(dev_buf, len, dev_offsets, max_lines, ws, st, &launches);
+    cudaError_t err = sre_launch_index_lines(dev_buf, len, dev_offsets, max_lines, w, st, &launches);
     count_launches(launches);
     unsigned long long found = 0;
     if (err == cudaSuccess) {
-        err = cudaMemcpyAsync(&found, ws + need / sizeof(unsigned long long) - 1, sizeof(found),
+        err = cudaMemcpyAsync(&found, w + need / sizeof(unsigned long long) - 1, sizeof(found),
                               cudaMemcpyDeviceToHost, st);
     }
     if (err == cudaSuccess) {
@@ -601,10 +737,19 @@ sre_cuda_index_lines(const uint8_t *dev_buf, size_t len, int64_t *dev_offsets, s
     return SRE_OK;
 }
 
-SRE_API void sre_cuda_set_pike_general_only(int on) { g_pike_general_only = on; }
-SRE_API int sre_cuda_pike_last_tier(void) { return g_pike_last_tier.load(); }
-SRE_API void sre_cuda_set_stream_piece(int bytes) { sre_stream_set_piece_bytes((uint32_t) bytes); }
-SRE_API void sre_cuda_set_l2_promotion(int mode) { sre_dev_set_l2_promotion(mode); }
+SRE_API void
+sre_cuda_program_set_pike_tier(sre_cuda_program_t *cp, int mode)
+{
+    if (cp) {
+        cp->pike_tier_mode = mode;
+    }
+}
+
+SRE_API int
+sre_cuda_program_last_pike_tier(sre_cuda_program_t *cp)
+{
+    return cp ? cp->pike_last_tier.load() : -1;
+}
 
 SRE_API long sre_cuda_launch_count(int reset)
 {
@@ -618,6 +763,9 @@ sre_cuda_program_create(sre_program_t *prog)
         fail("not a program compiled by this library");
         return NULL;
     }
+    /* one lowering per program, also when several threads ask at once */
+    static std::mutex create_lock;
+    std::lock_guard<std::mutex> guard(create_lock);
     if (prog->lowered) {
         return static_cast<sre_cuda_program_t *>(prog->lowered);
     }
@@ -663,6 +811,9 @@ sre_cuda_program_info(sre_cuda_program_t *cp, sre_cuda_info_t *info)
     info->nregexes = (uint32_t) cp->prog->nregexes;
     info->pike_slots = cp->pike.nslots;
     info->pike_ctx_bytes = cp->pike.ctx_stride;
+    info->dfa_start = cp->has_dfa ? cp->dfa.start : 0;
+    info->dfa_acc = cp->has_dfa ? cp->dfa.acc : 0;
+    info->image_states = cp->has_image ? cp->image.nstates : 0;
     return SRE_OK;
 }
 
@@ -690,7 +841,7 @@ sre_cuda_thompson_exec_ragged(sre_cuda_program_t *cp, const uint8_t *dev_buf,
     if (nlines == 0) {
         return SRE_OK;
     }
-    if (engine == SRE_CUDA_ENGINE_DFA_TILED) {
+    if ((engine & 0xff) == SRE_CUDA_ENGINE_DFA_TILED) {
         engine = SRE_CUDA_ENGINE_DFA_GENERIC;
     }
     return thompson_dispatch(cp, dev_buf, dev_offsets, nlines, 0, 0, dev_rc, engine, as_stream(stream));
@@ -719,19 +870,14 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
      */
     /* per-line workspace: gate | start hint | packed line list | its count */
     const size_t half = (nlines * 4 + 255) & ~(size_t) 255;
-    if (cp->line_ws_bytes < 3 * half + 256) {
-        cudaFree(cp->line_ws);
-        cp->line_ws = nullptr;
-        cp->line_ws_bytes = 0;
-        CUDA_TRY(cudaMalloc(&cp->line_ws, 3 * half + 256));
-        cp->line_ws_bytes = 3 * half + 256;
-    }
+    scratch_t line_ws;
+    CUDA_TRY(line_ws.alloc(3 * half + 256, st));
     const bool aligned = dev_offsets == nullptr && (reinterpret_cast<uintptr_t>(dev_buf) & 15) == 0
                          && (pitch & 15) == 0 && linelen <= pitch && linelen < (1ull << 31);
     const bool tiled_hint = cp->has_dfa && cp->dfa.h256 != nullptr && aligned;
     if (tiled_hint || (cp->has_dfa && cp->dfa.hcls != nullptr)) {
-        int32_t *gate = reinterpret_cast<int32_t *>(cp->line_ws);
-        int32_t *hint = reinterpret_cast<int32_t *>(cp->line_ws + half);
+        int32_t *gate = reinterpret_cast<int32_t *>(line_ws.p);
+        int32_t *hint = reinterpret_cast<int32_t *>(line_ws.p + half);
         cudaError_t e = tiled_hint
             ? sre_launch_dfa_lines_hint(cp->dfa, dev_buf, nlines, pitch, linelen, gate, hint,
                                         (cp->nleave >= 1 && cp->nleave <= 2 && linelen >= 128) ? cp->leave_pats
@@ -759,8 +905,8 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         if (nlines > 0xffffffffull) {
             return fail("too many lines for one call");
         }
-        uint32_t *list = reinterpret_cast<uint32_t *>(cp->line_ws + 2 * half);
-        uint32_t *count = reinterpret_cast<uint32_t *>(cp->line_ws + 3 * half);
+        uint32_t *list = reinterpret_cast<uint32_t *>(line_ws.p + 2 * half);
+        uint32_t *count = reinterpret_cast<uint32_t *>(line_ws.p + 3 * half);
         CUDA_TRY(cudaMemsetAsync(count, 0, 4, st));
         if (dev_ovec != nullptr && ovec_slots != 0) {
             CUDA_TRY(cudaMemsetAsync(dev_ovec, 0xff, nlines * ovec_slots * sizeof(int64_t), st));
@@ -774,17 +920,18 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         lines.count = count;
     }
     /* the table kernel's bookkeeping lives next to the packed-list count */
-    sre_pike_work_t *work = reinterpret_cast<sre_pike_work_t *>(cp->line_ws + 3 * half + 64);
+    sre_pike_work_t *work = reinterpret_cast<sre_pike_work_t *>(line_ws.p + 3 * half + 64);
     /* closure-table kernel: list capacities of its two passes.  Small lists
      * first (more resident warps), then the lines that needed more; a set of
      * regexes can have as many live threads as members share a prefix. */
     static int ek1 = -1, eh1 = 2, ek2 = 0, eh2 = 0;
     if (ek1 < 0) {              /* SRE_PIKE_TABLE_K="K1,H1[,K2,H2]" (tuning) */
         const char *e = getenv("SRE_PIKE_TABLE_K");
-        ek1 = 0;
+        int k1e = 0;
         if (e) {
-            sscanf(e, "%d,%d,%d,%d", &ek1, &eh1, &ek2, &eh2);
+            sscanf(e, "%d,%d,%d,%d", &k1e, &eh1, &ek2, &eh2);
         }
+        ek1 = k1e;
     }
     const bool big = cp->pike.nregexes > 1 || cp->pike.clo_npark > 64;
     const int k1 = ek1 > 0 ? ek1 : (big ? 12 : 4);
@@ -799,21 +946,20 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
     while (k2 > k1 && !sre_pike_table_applicable(cp->pike, dev_offsets, linelen, k2, h2)) {
         k2 = k2 - 4 > k1 ? k2 - 4 : k1;
     }
+    const int tier_mode = cp->pike_tier_mode.load();
     const bool use_table = sre_pike_table_applicable(cp->pike, dev_offsets, linelen, k2 > k1 ? k2 : k1, h2)
-                           && linelen < (1ull << 31) && g_pike_general_only == 0;
+                           && linelen < (1ull << 31) && tier_mode == 0;
     const bool use_small = !use_table && sre_pike_small_applicable(cp->pike) && linelen < (1ull << 31)
-                           && g_pike_general_only != 1;
+                           && tier_mode != 1;
     /* global-memory contexts of k_pike_lines: one per concurrent line when it
      * does all the work, a few thousand when it only re-runs what a
      * shared-memory tier gave up on */
-    if (ensure_pike_scratch(cp, (use_table || use_small) ? (nlines < 16384 ? nlines : 16384) : nlines) != SRE_OK) {
-        count_launches(launches);
-        return SRE_ERROR;
-    }
-    const size_t nctx = cp->pike_nctx < nlines ? cp->pike_nctx : nlines;
+    const size_t nctx = pike_contexts(cp, (use_table || use_small) ? (nlines < 16384 ? nlines : 16384) : nlines);
+    scratch_t pike_scratch;
+    CUDA_TRY(pike_scratch.alloc(pike_scratch_bytes(cp, nctx), st));
     if (use_table) {
         /* the general kernel re-runs what the table kernel gave up on */
-        g_pike_last_tier = 0;
+        cp->pike_last_tier = 0;
         err = sre_launch_pike_table(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
                                     dev_rc, dev_ovec, (uint32_t) ovec_slots, k1, h1, 0, work, st, &launches);
         const bool two = (k1 < k2 || h1 < h2);
@@ -823,24 +969,23 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         }
         if (err == cudaSuccess) {
             err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines,
-                                        start, dev_rc, dev_ovec, (uint32_t) ovec_slots, cp->pike_scratch,
-                                        nctx < 16384 ? nctx : 16384, 1, st, &launches,
-                                        &work->given_up[two ? 1 : 0]);
+                                        start, dev_rc, dev_ovec, (uint32_t) ovec_slots, pike_scratch.p,
+                                        nctx, 1, st, &launches, &work->given_up[two ? 1 : 0]);
         }
     } else if (use_small) {
         /* shared-memory kernel first; the general kernel re-runs what it gave up on */
-        g_pike_last_tier = 2;
+        cp->pike_last_tier = 2;
         err = sre_launch_pike_small(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
                                     dev_rc, dev_ovec, (uint32_t) ovec_slots, st, &launches);
         if (err == cudaSuccess) {
             err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines,
-                                        start, dev_rc, dev_ovec, (uint32_t) ovec_slots, cp->pike_scratch,
-                                        nctx < 16384 ? nctx : 16384, 1, st, &launches);
+                                        start, dev_rc, dev_ovec, (uint32_t) ovec_slots, pike_scratch.p,
+                                        nctx, 1, st, &launches);
         }
     } else {
-        g_pike_last_tier = 1;
+        cp->pike_last_tier = 1;
         err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
-                                    dev_rc, dev_ovec, (uint32_t) ovec_slots, cp->pike_scratch, nctx, 0, st,
+                                    dev_rc, dev_ovec, (uint32_t) ovec_slots, pike_scratch.p, nctx, 0, st,
                                     &launches);
     }
     count_launches(launches);
@@ -861,14 +1006,14 @@ sre_cuda_pike_exec_lines_all(sre_cuda_program_t *cp, const uint8_t *dev_buf, con
     if (nlines == 0) {
         return SRE_OK;
     }
-    if (ensure_pike_scratch(cp, nlines) != SRE_OK) {
-        return SRE_ERROR;
-    }
+    cudaStream_t st = as_stream(stream);
+    const size_t nctx = pike_contexts(cp, nlines);
+    scratch_t pike_scratch;
+    CUDA_TRY(pike_scratch.alloc(pike_scratch_bytes(cp, nctx), st));
     int launches = 0;
     cudaError_t err = sre_launch_pike_lines_all(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen,
                                                 (uint32_t) max_matches, dev_count, dev_spans, dev_ids,
-                                                cp->pike_scratch, cp->pike_nctx < nlines ? cp->pike_nctx : nlines,
-                                                as_stream(stream), &launches);
+                                                pike_scratch.p, nctx < nlines ? nctx : nlines, st, &launches);
     count_launches(launches);
     if (err != cudaSuccess) {
         return fail("Pike kernel launch failed: %s", cudaGetErrorString(err));
@@ -876,78 +1021,62 @@ sre_cuda_pike_exec_lines_all(sre_cuda_program_t *cp, const uint8_t *dev_buf, con
     return SRE_OK;
 }
 
-SRE_API int
+SRE_API sre_cuda_stream_scan_t *
 sre_cuda_thompson_stream_reduce(sre_cuda_program_t *cp, const uint8_t *dev_buf, size_t len,
-    uint8_t *host_fn, void *stream)
+    const uint8_t *dev_halo, uint32_t entry_state, uint8_t *host_fn, void *stream)
 {
-    if (cp == NULL || !stream_capable(cp)) {
-        return fail("stream scan needs a DFA with at most 32 states");
+    if (cp == NULL) {
+        fail("NULL program");
+        return NULL;
     }
-    if (reinterpret_cast<uintptr_t>(dev_buf) & 15) {
-        return fail("stream buffer must be 16-byte aligned");
+    const uint32_t entry = entry_state == SRE_CUDA_STATE_INIT ? cp->dfa.start
+                         : entry_state == SRE_CUDA_STATE_UNKNOWN ? SRE_STREAM_UNKNOWN : entry_state;
+    sre_cuda_stream_scan_t *sc = nullptr;
+    if (stream_reduce(cp, dev_buf, len, dev_halo, entry, as_stream(stream), &sc) != SRE_OK) {
+        return NULL;
     }
-    if (ensure_stream_ws(cp, len) != SRE_OK) {
+    if (host_fn != NULL && stream_root_record(sc, host_fn) != SRE_OK) {
+        delete sc;
+        return NULL;
+    }
+    return sc;
+}
+
+SRE_API int
+sre_cuda_thompson_stream_resolve(sre_cuda_stream_scan_t *scan, uint32_t entry_state, uint32_t *exit_state,
+    int64_t *first_match_offset, uint8_t *host_fn)
+{
+    if (scan == NULL || exit_state == NULL) {
+        return fail("NULL scan");
+    }
+    const uint32_t entry = entry_state == SRE_CUDA_STATE_INIT ? scan->cp->dfa.start : entry_state;
+    if (entry >= scan->cp->dfa.nstates) {
+        return fail("bad stream state");
+    }
+    int64_t off = -1;
+    if (stream_resolve(scan, entry, exit_state, &off, nullptr) != SRE_OK) {
         return SRE_ERROR;
     }
-    /* reduce on the device, then compose the (<= FAN) top-level functions on
-     * the host into one */
-    int launches = 0;
-    cudaStream_t st = as_stream(stream);
-    cudaError_t err = sre_launch_dfa_stream_reduce(cp->dfa, dev_buf, len, cp->ws, st, &launches);
-    count_launches(launches);
-    if (err != cudaSuccess) {
-        return fail("stream kernels failed: %s", cudaGetErrorString(err));
+    if (first_match_offset) {
+        *first_match_offset = off;
     }
-    int top = 0;
-    while (top < 3 && cp->ws.count[top] > sre_stream_fan()) {
-        top++;
+    if (host_fn != NULL) {
+        return stream_root_record(scan, host_fn);
     }
-    const uint32_t fs = sre_stream_fn_stride(cp->dfa.nstates), D = cp->dfa.nstates;
-    std::vector<uint8_t> fns(cp->ws.count[top] * fs);
-    CUDA_TRY(cudaMemcpyAsync(fns.data(), cp->ws.fn[top], fns.size(), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    for (uint32_t d = 0; d < D; d++) {
-        uint32_t s = d;
-        for (size_t j = 0; j < cp->ws.count[top]; j++) {
-            s = fns[j * fs + s];
-        }
-        host_fn[d] = (uint8_t) s;
-    }
-    cp->red_buf = dev_buf;
-    cp->red_len = len;
-    cp->red_top = top;
     return SRE_OK;
 }
 
-/* after stream_reduce on the same buffer: redo the walk from the true entry */
-SRE_API int
-sre_cuda_thompson_stream_resolve(sre_cuda_program_t *cp, uint32_t entry_state, uint32_t *exit_state,
-    int64_t *first_match_offset, void *stream)
+SRE_API void
+sre_cuda_thompson_stream_free(sre_cuda_stream_scan_t *scan)
 {
-    if (cp == NULL || cp->red_buf == nullptr) {
-        return fail("stream_resolve without stream_reduce");
-    }
-    cudaStream_t st = as_stream(stream);
-    int launches = 0;
-    /* the function levels are still in the workspace; only the walks depend
-     * on the entry state */
-    cudaError_t err = sre_launch_dfa_stream_walk(cp->dfa, entry_state, cp->ws, cp->d_exit, st, &launches);
-    if (err == cudaSuccess) {
-        err = sre_launch_dfa_stream_locate(cp->dfa, cp->red_buf, cp->red_len, cp->ws,
-                                           reinterpret_cast<long long *>(cp->d_exit + 2), st, &launches);
-    }
-    count_launches(launches);
-    if (err != cudaSuccess) {
-        return fail("stream kernels failed: %s", cudaGetErrorString(err));
-    }
-    struct { uint32_t exit, pad; long long off; } h;
-    CUDA_TRY(cudaMemcpyAsync(&h, cp->d_exit, sizeof(h), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    *exit_state = h.exit;
-    if (first_match_offset) {
-        *first_match_offset = entry_state == cp->dfa.acc ? 0 : h.off;
-    }
-    return SRE_OK;
+    delete scan;
+}
+
+SRE_API uint32_t
+sre_cuda_stream_fn_apply(const uint8_t *fn, uint32_t state)
+{
+    const uint32_t r = sre_stream_fn_apply(fn, state);
+    return r == SRE_STREAM_UNKNOWN ? SRE_CUDA_STATE_UNKNOWN : r;
 }
 
 SRE_API int
@@ -957,49 +1086,34 @@ sre_cuda_thompson_exec_stream(sre_cuda_program_t *cp, const uint8_t *dev_buf, si
     if (cp == NULL || state_io == NULL) {
         return fail("NULL program or state");
     }
-    if (!stream_capable(cp)) {
-        return fail("stream scan needs a DFA with at most 32 states (this program: %u)",
-                    cp->has_dfa ? cp->dfa.nstates : 0);
+    if (!cp->has_dfa) {
+        return fail("the stream scan needs the determinised program (this one exceeded %u DFA states)",
+                    MAX_DFA_STATES);
     }
-    if (reinterpret_cast<uintptr_t>(dev_buf) & 15) {
-        return fail("stream buffer must be 16-byte aligned");
-    }
-    cudaStream_t st = as_stream(stream);
     const uint32_t entry = *state_io == SRE_CUDA_STATE_INIT ? cp->dfa.start : *state_io;
-    if (entry >= cp->dfa.nstates) {
-        return fail("bad stream state");
-    }
-    if (ensure_stream_ws(cp, len) != SRE_OK) {
+    sre_cuda_stream_scan_t *sc = nullptr;
+    if (stream_reduce(cp, dev_buf, len, nullptr, entry, as_stream(stream), &sc) != SRE_OK) {
         return SRE_ERROR;
     }
-    int launches = 0;
-    cudaError_t err = sre_launch_dfa_stream_reduce(cp->dfa, dev_buf, len, cp->ws, st, &launches);
-    if (err == cudaSuccess) {
-        err = sre_launch_dfa_stream_walk(cp->dfa, entry, cp->ws, cp->d_exit, st, &launches);
+    uint32_t exit_state = 0;
+    int64_t off = -1;
+    const int r = stream_resolve(sc, entry, &exit_state, &off, nullptr);
+    delete sc;
+    if (r != SRE_OK) {
+        return SRE_ERROR;
     }
-    if (err == cudaSuccess) {
-        err = sre_launch_dfa_stream_locate(cp->dfa, dev_buf, len, cp->ws,
-                                           reinterpret_cast<long long *>(cp->d_exit + 2), st, &launches);
-    }
-    count_launches(launches);
-    if (err != cudaSuccess) {
-        return fail("stream kernels failed: %s", cudaGetErrorString(err));
-    }
-    struct { uint32_t exit, pad; long long off; } h;
-    CUDA_TRY(cudaMemcpyAsync(&h, cp->d_exit, sizeof(h), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    *state_io = h.exit;
+    *state_io = exit_state;
 
     const size_t nchunks = chunk_bytes ? (len + chunk_bytes - 1) / chunk_bytes : 1;
-    if (h.exit == cp->dfa.acc) {
+    if (exit_state == cp->dfa.acc) {
         if (match_chunk) {
-            *match_chunk = (entry == cp->dfa.acc || h.off < 0 || !chunk_bytes)
-                               ? 0 : (int64_t) ((size_t) h.off / chunk_bytes);
+            *match_chunk = (entry == cp->dfa.acc || off < 0 || !chunk_bytes)
+                               ? 0 : (int64_t) ((size_t) off / chunk_bytes);
         }
         return SRE_OK;
     }
     if (eof) {
-        if (cp->low.dfa.fin[h.exit]) {
+        if (cp->low.dfa.fin[exit_state]) {
             if (match_chunk) {
                 *match_chunk = nchunks ? (int64_t) nchunks - 1 : 0;
             }
@@ -1008,16 +1122,6 @@ sre_cuda_thompson_exec_stream(sre_cuda_program_t *cp, const uint8_t *dev_buf, si
         return SRE_DECLINED;
     }
     return SRE_AGAIN;
-}
-
-SRE_API int
-sre_cuda_tma_ceiling(const uint8_t *dev_buf, size_t nlines, size_t pitch, size_t linelen, int32_t *dev_rc,
-    int variant, void *stream)
-{
-    cudaError_t err = sre_launch_tma_ceiling(dev_buf, nlines, pitch, linelen, dev_rc, variant,
-                                             as_stream(stream));
-    count_launches(1);
-    return err == cudaSuccess ? SRE_OK : fail("ceiling kernel: %s", cudaGetErrorString(err));
 }
 
 SRE_API int
@@ -1031,19 +1135,6 @@ sre_cuda_dfa_fin(sre_cuda_program_t *cp, uint32_t state)
 
 /* ---- host-buffer conveniences --------------------------------------------- */
 
-static int ensure_io(sre_cuda_program_t *cp, size_t bytes)
-{
-    if (cp->io_bytes >= bytes) {
-        return SRE_OK;
-    }
-    cudaFree(cp->io_buf);
-    cp->io_buf = nullptr;
-    cp->io_bytes = 0;
-    CUDA_TRY(cudaMalloc(&cp->io_buf, bytes));
-    cp->io_bytes = bytes;
-    return SRE_OK;
-}
-
 SRE_API int
 sre_cuda_thompson_exec_lines_host(sre_cuda_program_t *cp, const uint8_t *host_buf, size_t nlines,
     size_t pitch, size_t linelen, int32_t *host_rc, int engine)
@@ -1054,17 +1145,17 @@ sre_cuda_thompson_exec_lines_host(sre_cuda_program_t *cp, const uint8_t *host_bu
     if (nlines == 0) {
         return SRE_OK;
     }
+    cudaStream_t st = cudaStreamPerThread;
     const size_t in_bytes = (nlines - 1) * pitch + linelen, in_pad = (in_bytes + 255) & ~(size_t) 255;
-    if (ensure_io(cp, in_pad + nlines * 4 + 256) != SRE_OK) {
+    scratch_t io;
+    CUDA_TRY(io.alloc(in_pad + nlines * 4 + 256, st));
+    int32_t *d_rc = reinterpret_cast<int32_t *>(io.p + in_pad);
+    CUDA_TRY(cudaMemcpyAsync(io.p, host_buf, in_bytes, cudaMemcpyHostToDevice, st));
+    if (thompson_dispatch(cp, io.p, nullptr, nlines, pitch, linelen, d_rc, engine, st) != SRE_OK) {
         return SRE_ERROR;
     }
-    int32_t *d_rc = reinterpret_cast<int32_t *>(cp->io_buf + in_pad);
-    CUDA_TRY(cudaMemcpyAsync(cp->io_buf, host_buf, in_bytes, cudaMemcpyHostToDevice, 0));
-    if (thompson_dispatch(cp, cp->io_buf, nullptr, nlines, pitch, linelen, d_rc, engine, 0) != SRE_OK) {
-        return SRE_ERROR;
-    }
-    CUDA_TRY(cudaMemcpyAsync(host_rc, d_rc, nlines * 4, cudaMemcpyDeviceToHost, 0));
-    CUDA_TRY(cudaStreamSynchronize(0));
+    CUDA_TRY(cudaMemcpyAsync(host_rc, d_rc, nlines * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return SRE_OK;
 }
 
@@ -1079,29 +1170,28 @@ sre_cuda_pike_exec_lines_host(sre_cuda_program_t *cp, const uint8_t *host_buf, s
     if (nlines == 0) {
         return SRE_OK;
     }
+    cudaStream_t st = cudaStreamPerThread;
     const size_t in_bytes = (nlines - 1) * pitch + linelen, in_pad = (in_bytes + 255) & ~(size_t) 255;
     const size_t rc_pad = (nlines * 4 + 255) & ~(size_t) 255;
-    if (ensure_io(cp, in_pad + 2 * rc_pad + nlines * ovec_slots * 8 + 256) != SRE_OK) {
-        return SRE_ERROR;
-    }
-    int32_t *d_sel = reinterpret_cast<int32_t *>(cp->io_buf + in_pad);
-    int32_t *d_rc = reinterpret_cast<int32_t *>(cp->io_buf + in_pad + rc_pad);
-    int64_t *d_ov = reinterpret_cast<int64_t *>(cp->io_buf + in_pad + 2 * rc_pad);
-    CUDA_TRY(cudaMemcpyAsync(cp->io_buf, host_buf, in_bytes, cudaMemcpyHostToDevice, 0));
+    scratch_t io;
+    CUDA_TRY(io.alloc(in_pad + 2 * rc_pad + nlines * ovec_slots * 8 + 256, st));
+    int32_t *d_sel = reinterpret_cast<int32_t *>(io.p + in_pad);
+    int32_t *d_rc = reinterpret_cast<int32_t *>(io.p + in_pad + rc_pad);
+    int64_t *d_ov = reinterpret_cast<int64_t *>(io.p + in_pad + 2 * rc_pad);
+    CUDA_TRY(cudaMemcpyAsync(io.p, host_buf, in_bytes, cudaMemcpyHostToDevice, st));
     if (gate_with_thompson
-        && thompson_dispatch(cp, cp->io_buf, nullptr, nlines, pitch, linelen, d_sel,
-                             SRE_CUDA_ENGINE_AUTO, 0) != SRE_OK)
+        && thompson_dispatch(cp, io.p, nullptr, nlines, pitch, linelen, d_sel, SRE_CUDA_ENGINE_AUTO, st) != SRE_OK)
     {
         return SRE_ERROR;
     }
-    if (sre_cuda_pike_exec_lines(cp, cp->io_buf, nullptr, nlines, pitch, linelen,
-                                 gate_with_thompson ? d_sel : nullptr, d_rc, d_ov, ovec_slots, 0) != SRE_OK)
+    if (sre_cuda_pike_exec_lines(cp, io.p, nullptr, nlines, pitch, linelen,
+                                 gate_with_thompson ? d_sel : nullptr, d_rc, d_ov, ovec_slots, st) != SRE_OK)
     {
         return SRE_ERROR;
     }
-    CUDA_TRY(cudaMemcpyAsync(host_rc, d_rc, nlines * 4, cudaMemcpyDeviceToHost, 0));
-    CUDA_TRY(cudaMemcpyAsync(host_ovec, d_ov, nlines * ovec_slots * 8, cudaMemcpyDeviceToHost, 0));
-    CUDA_TRY(cudaStreamSynchronize(0));
+    CUDA_TRY(cudaMemcpyAsync(host_rc, d_rc, nlines * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(host_ovec, d_ov, nlines * ovec_slots * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return SRE_OK;
 }
 
@@ -1159,6 +1249,11 @@ void pike_ctx_cleanup(void *data)
 
 const size_t THOMPSON_HDR = 4096 * 4 + 256;     /* state words + rc */
 
+/* The classic entry points have no stream argument: each host thread works on
+ * its own (per-thread default) stream, so contexts driven from different
+ * threads do not serialise on the legacy default stream. */
+const cudaStream_t CLASSIC_STREAM = cudaStreamPerThread;
+
 int thompson_reserve(sre_vm_thompson_ctx_t *ctx, size_t len)
 {
     if (ctx->d_mem && ctx->d_cap >= len) {
@@ -1210,7 +1305,8 @@ sre_vm_thompson_create_ctx(sre_pool_t *pool, sre_program_t *prog)
 /*
  * reference: sre_vm_thompson_exec, sre_vm_thompson.c:63-270.  Same contract:
  * SRE_OK as soon as a step of this call sees a live MATCH thread, SRE_AGAIN
- * when !eof, SRE_DECLINED at eof; state is carried on the device between calls.
+ * when !eof, SRE_DECLINED at eof; state is carried between calls (on the
+ * device; for the chunk-parallel path as one DFA state in the context).
  */
 SRE_API sre_int_t
 sre_vm_thompson_exec(sre_vm_thompson_ctx_t *ctx, sre_char *input, size_t size, unsigned eof)
@@ -1219,6 +1315,7 @@ sre_vm_thompson_exec(sre_vm_thompson_ctx_t *ctx, sre_char *input, size_t size, u
         return SRE_ERROR;
     }
     sre_cuda_program_t *cp = ctx->cp;
+    const cudaStream_t st = CLASSIC_STREAM;
     if (thompson_reserve(ctx, size) != SRE_OK) {
         return SRE_ERROR;
     }
@@ -1226,20 +1323,22 @@ sre_vm_thompson_exec(sre_vm_thompson_ctx_t *ctx, sre_char *input, size_t size, u
     int32_t *d_rc = reinterpret_cast<int32_t *>(ctx->d_mem + 4096 * 4);
     uint8_t *d_in = ctx->d_mem + THOMPSON_HDR;
     if (size) {
-        CUDA_TRY(cudaMemcpyAsync(d_in, input, size, cudaMemcpyHostToDevice, 0));
+        CUDA_TRY(cudaMemcpyAsync(d_in, input, size, cudaMemcpyHostToDevice, st));
     }
 
-    /* long buffers over a small DFA: the chunk-parallel scan */
-    if (stream_capable(cp) && size >= (1u << 16)) {
-        uint32_t st = SRE_CUDA_STATE_INIT;
+    /* long buffers over a determinised program: the chunk-parallel scan */
+    if (cp->has_dfa && cp->has_image && size >= (1u << 16)) {
+        uint32_t state = SRE_CUDA_STATE_INIT;
         if (ctx->started) {
-            CUDA_TRY(cudaMemcpy(&st, d_state, 4, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpyAsync(&state, d_state, 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
         }
-        const int rc = sre_cuda_thompson_exec_stream(cp, d_in, size, size, eof, &st, NULL, 0);
+        const int rc = sre_cuda_thompson_exec_stream(cp, d_in, size, size, eof, &state, NULL, st);
         if (rc == SRE_ERROR) {
             return SRE_ERROR;
         }
-        CUDA_TRY(cudaMemcpy(d_state, &st, 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpyAsync(d_state, &state, 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
         ctx->started = true;
         return rc;
     }
@@ -1248,10 +1347,10 @@ sre_vm_thompson_exec(sre_vm_thompson_ctx_t *ctx, sre_char *input, size_t size, u
     cudaError_t err;
     if (cp->has_dfa) {
         err = sre_launch_dfa_carry(cp->dfa, d_in, nullptr, 1, 0, size, d_state, !ctx->started, eof != 0,
-                                   d_rc, 0, &launches);
+                                   d_rc, st, &launches);
     } else {
         err = sre_launch_nfa_lines(cp->nfa, d_in, nullptr, 1, 0, size, d_state, !ctx->started, eof != 0,
-                                   d_rc, 0, &launches);
+                                   d_rc, st, &launches);
     }
     count_launches(launches);
     if (err != cudaSuccess) {
@@ -1259,7 +1358,8 @@ sre_vm_thompson_exec(sre_vm_thompson_ctx_t *ctx, sre_char *input, size_t size, u
     }
     ctx->started = true;
     int32_t rc = SRE_ERROR;
-    CUDA_TRY(cudaMemcpy(&rc, d_rc, 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpyAsync(&rc, d_rc, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return rc;
 }
 
@@ -1327,7 +1427,8 @@ sre_vm_pike_create_ctx(sre_pool_t *pool, sre_program_t *prog, sre_int_t *ovector
         || cudaMalloc(&ctx->d_ctx, cp->pike.ctx_stride) != cudaSuccess
         || cudaMalloc(&ctx->d_out, (4 + ctx->ovec_slots + 2) * 8) != cudaSuccess
         || cudaMalloc(&ctx->d_in, ctx->d_in_cap) != cudaSuccess
-        || sre_launch_pike_ctx_init(cp->pike, ctx->d_ctx, 0, &launches) != cudaSuccess
+        || sre_launch_pike_ctx_init(cp->pike, ctx->d_ctx, CLASSIC_STREAM, &launches) != cudaSuccess
+        || cudaStreamSynchronize(CLASSIC_STREAM) != cudaSuccess
         || sre_pool_add_cleanup(pool, pike_ctx_cleanup, ctx) != SRE_OK)
     {
         fail("creating the Pike context failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1353,18 +1454,20 @@ sre_vm_pike_exec(sre_vm_pike_ctx_t *ctx, sre_char *input, size_t size, unsigned 
         CUDA_TRY(cudaMalloc(&ctx->d_in, ctx->d_in_cap));
     }
     if (size) {
-        CUDA_TRY(cudaMemcpyAsync(ctx->d_in, input, size, cudaMemcpyHostToDevice, 0));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_in, input, size, cudaMemcpyHostToDevice, CLASSIC_STREAM));
     }
     int launches = 0;
     cudaError_t err = sre_launch_pike_stream(ctx->cp->pike, ctx->d_ctx, ctx->d_in, size, eof != 0,
                                              pending_matched != NULL, ctx->d_out,
-                                             (uint32_t) ctx->ovec_slots, 0, &launches);
+                                             (uint32_t) ctx->ovec_slots, CLASSIC_STREAM, &launches);
     count_launches(launches);
     if (err != cudaSuccess) {
         return fail("Pike kernel launch failed: %s", cudaGetErrorString(err));
     }
     std::vector<int64_t> &out = *ctx->h_out;
-    CUDA_TRY(cudaMemcpy(out.data(), ctx->d_out, (4 + ctx->ovec_slots) * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpyAsync(out.data(), ctx->d_out, (4 + ctx->ovec_slots) * 8, cudaMemcpyDeviceToHost,
+                             CLASSIC_STREAM));
+    CUDA_TRY(cudaStreamSynchronize(CLASSIC_STREAM));
 
     const sre_int_t rc = (sre_int_t) out[0];
     if (rc >= 0) {

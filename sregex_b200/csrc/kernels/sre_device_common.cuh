@@ -1,9 +1,9 @@
 /*
- * sre_device_common.cuh -- device helpers shared by the Thompson kernels:
- * cp.async wrappers, DFA step functors, the shared-memory plan of the DFA
- * tables, and the per-warp tile pipeline that stages 32 rows x TW bytes through
- * shared memory (rows = lines for k_dfa_lines, stream pieces for
- * k_stream_pieces).
+ * sre_device_common.cuh -- device helpers shared by the Thompson kernels: DFA
+ * step functors, the shared-memory plan of the DFA tables, TMA / mbarrier
+ * wrappers and the per-warp tile pipeline that stages 32 rows x 128 bytes
+ * through shared memory (rows = lines for the k_dfa_lines family, stream pieces
+ * for k_stream_pieces).
  */
 #ifndef SRE_DEVICE_COMMON_CUH
 #define SRE_DEVICE_COMMON_CUH
@@ -14,23 +14,6 @@
 namespace sre_dev {
 
 constexpr unsigned FULL = 0xffffffffu;
-
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
-{
-    unsigned s = (unsigned) __cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(s), "l"(gmem) : "memory");
-}
-
-__device__ __forceinline__ void cp_async_commit()
-{
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-}
-
-template <int N>
-__device__ __forceinline__ void cp_async_wait()
-{
-    asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory");
-}
 
 __host__ __device__ constexpr size_t align_up(size_t v, size_t a)
 {
@@ -158,126 +141,6 @@ __host__ __device__ inline dfa_smem_plan_t dfa_smem_plan(uint32_t nstates, uint3
 }
 
 
-template <int TW>
-__device__ __forceinline__ uint32_t swizzle(uint32_t row)
-{
-    /* 16-byte chunks per row; rows that share a 128-byte bank window get
-     * distinct XOR keys so that "lane l reads chunk c of row l" touches every
-     * bank once per quarter-warp */
-    constexpr int CPR = TW / 16;
-    if (CPR >= 8) return row & 7;
-    if (CPR == 4) return (row >> 1) & 3;
-    if (CPR == 2) return (row >> 2) & 1;
-    return 0;
-}
-
-/*
- * Per-warp tile pipeline.  The warp owns row groups g = gw, gw + warps_total,
- * ... (32 consecutive rows each; lane l consumes row g*32 + l).  Every row is
- * rowlen bytes at buf + row*pitch (16-byte aligned).  Tiles of TW bytes per row
- * travel through a STAGES-deep ring of cp.async groups that runs ahead across
- * group boundaries, so the copy engine never drains between groups.
- *
- * Consumer interface:
- *   void begin();                  a new row starts
- *   void chunk(const uint4 &v);    next 16 bytes of my row
- *   void byte(uint32_t b);         next single byte (ragged tail of a row)
- *   void end(size_t group);        my row of `group` is complete
- */
-template <int TW, int STAGES, class Consumer>
-__device__ __forceinline__ void tile_pipeline(Consumer &cons, const uint8_t *__restrict__ buf,
-    size_t nrows, size_t pitch, uint32_t rowlen, uint8_t *my_stage, size_t gw, size_t warps_total)
-{
-    constexpr int CPR = TW / 16;
-    constexpr int STAGE_BYTES = 32 * TW;
-    const uint32_t lane = threadIdx.x & 31;
-    const size_t ngroups = (nrows + 31) / 32;
-    if (gw >= ngroups) {
-        return;
-    }
-    const uint32_t my_groups = (uint32_t) ((ngroups - gw + warps_total - 1) / warps_total);
-    const uint32_t ntiles = (rowlen + TW - 1) / TW;
-
-    if (ntiles == 0) {
-        for (uint32_t gi = 0; gi < my_groups; gi++) {
-            cons.begin();
-            cons.end(gw + (size_t) gi * warps_total);
-        }
-        return;
-    }
-
-    const uint32_t total = my_groups * ntiles;
-
-    auto issue = [&](uint32_t k) {
-        const uint32_t gi = k / ntiles, t = k - gi * ntiles;
-        const size_t group = gw + (size_t) gi * warps_total;
-        uint8_t *dst = my_stage + (k % STAGES) * STAGE_BYTES;
-        const uint32_t tile_off = t * TW;
-        const uint32_t left = rowlen - tile_off;
-        const uint32_t valid = left >= (uint32_t) TW ? (uint32_t) TW : (left + 15) & ~15u;
-#pragma unroll
-        for (int j = 0; j < CPR; j++) {
-            const uint32_t q = lane + 32 * j, row = q / CPR, c = q % CPR;
-            size_t r = group * 32 + row;
-            if (r >= nrows) {
-                r = nrows - 1;
-            }
-            if (c * 16 < valid) {
-                cp_async16(dst + row * TW + ((c ^ swizzle<TW>(row)) << 4),
-                           buf + r * pitch + tile_off + c * 16);
-            }
-        }
-    };
-
-    uint32_t issued = 0;
-#pragma unroll
-    for (int i = 0; i < STAGES - 1; i++) {
-        if (issued < total) {
-            issue(issued);
-        }
-        cp_async_commit();
-        issued++;
-    }
-
-    uint32_t t = 0;
-    size_t group = gw;
-    const uint32_t swz = swizzle<TW>(lane);
-    cons.begin();
-
-    for (uint32_t k = 0; k < total; k++) {
-        if (issued < total) {
-            issue(issued);
-        }
-        cp_async_commit();
-        issued++;
-        cp_async_wait<STAGES - 1>();
-        __syncwarp();
-
-        const uint8_t *row = my_stage + (k % STAGES) * STAGE_BYTES + lane * TW;
-        const uint32_t left = rowlen - t * TW;
-        if (left >= (uint32_t) TW) {
-#pragma unroll
-            for (int c = 0; c < CPR; c++) {
-                cons.chunk(*reinterpret_cast<const uint4 *>(row + ((c ^ swz) << 4)));
-            }
-        } else {
-            for (uint32_t i = 0; i < left; i++) {
-                cons.byte(row[(((i >> 4) ^ swz) << 4) | (i & 15)]);
-            }
-        }
-        __syncwarp();
-
-        if (++t == ntiles) {
-            cons.end(group);
-            t = 0;
-            group += warps_total;
-            cons.begin();
-        }
-    }
-    cp_async_wait<0>();
-}
-
-
 /* ---- TMA (cp.async.bulk.tensor) + mbarrier helpers ------------------------- */
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -326,119 +189,28 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
 }
 
 /*
- * TMA flavour of the per-warp tile pipeline: the tensor map describes the
- * corpus as a 2-D byte tensor {pitch, nrows}; one elected lane asks the TMA
- * unit for a {TW bytes x 32 rows} box per tile, written with the hardware's
- * 32/64/128-byte swizzle (the same XOR pattern as swizzle<TW>() above, because
- * the stage buffers are aligned to the swizzle atom), and signals a per-stage
- * mbarrier.  Rows past nrows and bytes past the pitch are zero-filled by the
- * hardware.  All STAGES buffers can be in flight; a stage is re-armed as soon
- * as every lane has consumed it (__syncwarp).
+ * Per-warp tile pipeline (TMA, early stage release).  The tensor map describes
+ * the corpus as a 2-D byte tensor {pitch, nrows}; the warp owns row groups
+ * g = gw, gw + warps_total, ... (32 consecutive rows each; lane l consumes row
+ * g*32 + l).  One elected lane asks the TMA unit for a {128 bytes x 32 rows} box
+ * per tile, written with the hardware's 128-byte swizzle (so that "lane l reads
+ * 16-byte chunk c of row l" is bank-conflict free) and signalled on a per-stage
+ * mbarrier; rows past nrows and bytes past the pitch are zero-filled by the
+ * hardware.  A lane copies its row of the landed tile into registers in two
+ * 64-byte halves; as soon as the second half is in registers (half-way through
+ * the tile's processing time) the stage buffer is handed back to the TMA unit.
+ * The staging memory per row is therefore only STAGES x 128 bytes with STAGES =
+ * 1 or 2, which lets 32-48 warps per SM be resident: the per-byte dependent
+ * chain (PRMT -> LDS.U8, ~35 cycles) needs that many independent rows in
+ * flight to keep the shared-memory pipe busy.
+ *
+ * Consumer interface:
+ *   void begin(size_t group);      my row of `group` starts
+ *   void chunk(const uint4 &v);    next 16 bytes of my row
+ *   void byte(uint32_t b);         next single byte (ragged tail of a row)
+ *   void end(size_t group);        my row of `group` is complete
  */
-template <int TW, int STAGES, class Consumer>
-__device__ __forceinline__ void tile_pipeline_tma(Consumer &cons, const CUtensorMap *tmap, size_t nrows,
-    uint32_t rowlen, uint8_t *my_stage, uint64_t *my_bars, size_t gw, size_t warps_total)
-{
-    constexpr int CPR = TW / 16;
-    constexpr int STAGE_BYTES = 32 * TW;
-    const uint32_t lane = threadIdx.x & 31;
-    const size_t ngroups = (nrows + 31) / 32;
-    if (gw >= ngroups) {
-        return;
-    }
-    const uint32_t my_groups = (uint32_t) ((ngroups - gw + warps_total - 1) / warps_total);
-    const uint32_t ntiles = (rowlen + TW - 1) / TW;
-
-    if (ntiles == 0) {
-        for (uint32_t gi = 0; gi < my_groups; gi++) {
-            cons.begin();
-            cons.end(gw + (size_t) gi * warps_total);
-        }
-        return;
-    }
-
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < STAGES; i++) {
-            mbar_init(&my_bars[i], 1);
-        }
-        fence_mbar_init();
-    }
-    __syncwarp();
-
-    const uint32_t total = my_groups * ntiles;
-
-    /* lane 0 only */
-    auto issue = [&](uint32_t k, uint32_t gi, uint32_t t) {
-        const size_t group = gw + (size_t) gi * warps_total;
-        uint64_t *bar = &my_bars[k % STAGES];
-        mbar_arrive_expect_tx(bar, STAGE_BYTES);
-        tma_load_2d(my_stage + (k % STAGES) * STAGE_BYTES, tmap, (int32_t) (t * TW),
-                    (int32_t) (group * 32), bar);
-    };
-
-    /* producer cursor (tile index, group index, tile-in-row) */
-    uint32_t pk = 0, pgi = 0, pt = 0;
-    auto produce = [&]() {
-        if (pk < total) {
-            if (lane == 0) {
-                issue(pk, pgi, pt);
-            }
-            pk++;
-            if (++pt == ntiles) {
-                pt = 0;
-                pgi++;
-            }
-        }
-    };
-#pragma unroll
-    for (int i = 0; i < STAGES; i++) {
-        produce();
-    }
-
-    uint32_t t = 0;
-    size_t group = gw;
-    const uint32_t swz = swizzle<TW>(lane);
-    cons.begin();
-
-    for (uint32_t k = 0; k < total; k++) {
-        mbar_wait(&my_bars[k % STAGES], (k / STAGES) & 1);
-
-        const uint8_t *row = my_stage + (k % STAGES) * STAGE_BYTES + lane * TW;
-        const uint32_t left = rowlen - t * TW;
-        if (left >= (uint32_t) TW) {
-#pragma unroll
-            for (int c = 0; c < CPR; c++) {
-                cons.chunk(*reinterpret_cast<const uint4 *>(row + ((c ^ swz) << 4)));
-            }
-        } else {
-            for (uint32_t i = 0; i < left; i++) {
-                cons.byte(row[(((i >> 4) ^ swz) << 4) | (i & 15)]);
-            }
-        }
-        __syncwarp();       /* every lane is done with this stage */
-        produce();          /* ... so it can be re-armed */
-
-        if (++t == ntiles) {
-            cons.end(group);
-            t = 0;
-            group += warps_total;
-            cons.begin();
-        }
-    }
-}
-
-/*
- * Early-release flavour: a lane copies its row of the landed tile into
- * registers in two 64-byte halves; as soon as the second half is in registers
- * (i.e. half-way through the tile's processing time) the stage buffer is handed
- * back to the TMA unit.  The staging memory per line is therefore only
- * STAGES x 128 bytes with STAGES = 1 or 2, which lets 40-48 warps per SM be
- * resident: the per-byte dependent chain (PRMT -> LDS.U8, ~35 cycles) needs
- * that many independent lines in flight to keep the shared-memory pipe busy.
- * TW is fixed at 128 (the row width the TMA unit moves efficiently).
- */
-template <int STAGES, class Consumer, bool FULLCOPY = false>
+template <int STAGES, class Consumer>
 __device__ __forceinline__ void tile_pipeline_tma_early(Consumer &cons, const CUtensorMap *tmap, size_t nrows,
     uint32_t rowlen, uint8_t *my_stage, uint64_t *my_bars, size_t gw, size_t warps_total)
 {
@@ -454,7 +226,7 @@ __device__ __forceinline__ void tile_pipeline_tma_early(Consumer &cons, const CU
 
     if (ntiles == 0) {
         for (uint32_t gi = 0; gi < my_groups; gi++) {
-            cons.begin();
+            cons.begin(gw + (size_t) gi * warps_total);
             cons.end(gw + (size_t) gi * warps_total);
         }
         return;
@@ -494,7 +266,7 @@ __device__ __forceinline__ void tile_pipeline_tma_early(Consumer &cons, const CU
     uint32_t t = 0;
     size_t group = gw;
     const uint32_t swz = lane & 7;
-    cons.begin();
+    cons.begin(group);
 
     for (uint32_t k = 0; k < total; k++) {
         mbar_wait(&my_bars[k % STAGES], (k / STAGES) & 1);
@@ -507,31 +279,16 @@ __device__ __forceinline__ void tile_pipeline_tma_early(Consumer &cons, const CU
             a[c] = *reinterpret_cast<const uint4 *>(row + ((c ^ swz) << 4));
         }
         if (left >= (uint32_t) TW) {
-            if (FULLCOPY) {
-                /* whole row to registers first: the stage is re-armed before
-                 * any byte is processed (registers are the second buffer) */
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    b[c] = *reinterpret_cast<const uint4 *>(row + (((c + 4) ^ swz) << 4));
-                }
-                __syncwarp();
-                produce();
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    cons.chunk(a[c]);
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    cons.chunk(a[c]);
-                }
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    b[c] = *reinterpret_cast<const uint4 *>(row + (((c + 4) ^ swz) << 4));
-                }
-                __syncwarp();
-                produce();
+            for (int c = 0; c < 4; c++) {
+                cons.chunk(a[c]);
             }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                b[c] = *reinterpret_cast<const uint4 *>(row + (((c + 4) ^ swz) << 4));
+            }
+            __syncwarp();
+            produce();
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 cons.chunk(b[c]);
@@ -549,13 +306,15 @@ __device__ __forceinline__ void tile_pipeline_tma_early(Consumer &cons, const CU
             cons.end(group);
             t = 0;
             group += warps_total;
-            cons.begin();
+            if (k + 1 < total) {
+                cons.begin(group);
+            }
         }
     }
 }
 
 int num_sms();
-/* host: 2-D byte tensor {pitch, nrows}, box {tw, 32}, swizzle by tw */
+/* host: 2-D byte tensor {pitch, nrows}, box {128, 32}, 128-byte swizzle */
 cudaError_t make_row_tensor_map(CUtensorMap *map, const uint8_t *buf, size_t nrows, size_t pitch, int tw);
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 

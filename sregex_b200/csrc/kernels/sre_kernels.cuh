@@ -219,24 +219,42 @@ cudaError_t sre_launch_pike_stream(const sre_dev_pike_t &pk, uint8_t *ctx,
 cudaError_t sre_launch_pike_ctx_init(const sre_dev_pike_t &pk, uint8_t *ctx,
     cudaStream_t stream, int *launches);
 
-/* chunk-parallel DFA stream scan (nstates <= 64) ---------------------------- */
+/* chunk-parallel DFA stream scan (sre_stream.cu) ----------------------------- */
+
+#define SRE_STREAM_K         8              /* candidate entry states per record        */
+#define SRE_STREAM_FN_BYTES  32             /* one record: K candidates + K exit states */
+#define SRE_STREAM_HALO      256            /* bytes of the preceding part a part needs */
+#define SRE_STREAM_UNKNOWN   0xffffffffu    /* entry state not known                    */
+
+/* image automaton of the DFA (lower/sre_image.h), over the DFA's byte classes */
+struct sre_dev_image_t {
+    uint32_t         nstates, nclasses, K;
+    const uint16_t  *trans;     /* [nstates][nclasses]                        */
+    const uint16_t  *cand;      /* [nstates][K], 16-byte aligned rows         */
+    const uint8_t   *ncand;     /* [nstates] 0..K, 0xff: wide                 */
+};
+
 struct sre_stream_ws_t {        /* workspace owned by the caller              */
-    uint8_t  *fn[4];            /* transfer functions per level               */
+    uint8_t  *fn[4];            /* records per level                          */
     size_t    count[4];
-    uint8_t  *entry[4];         /* entry state per element per level          */
-    unsigned long long *first_acc;  /* first piece whose exit is ACC          */
+    unsigned long long *first_acc;  /* first piece in which ACC is entered    */
 };
 size_t sre_stream_piece_bytes(void);
-void sre_stream_set_piece_bytes(uint32_t bytes);   /* 1024, 2048, 4096 (default) or 8192 */
-cudaError_t sre_launch_dfa_stream_reduce(const sre_dev_dfa_t &dfa, const uint8_t *buf,
-    size_t len, const sre_stream_ws_t &ws, cudaStream_t stream, int *launches);
-cudaError_t sre_launch_dfa_stream_walk(const sre_dev_dfa_t &dfa, uint32_t entry_state,
-    const sre_stream_ws_t &ws, uint32_t *exit_state, cudaStream_t stream, int *launches);
-cudaError_t sre_launch_dfa_stream_locate(const sre_dev_dfa_t &dfa, const uint8_t *buf,
-    size_t len, const sre_stream_ws_t &ws, long long *dev_match_offset,
-    cudaStream_t stream, int *launches);
 uint32_t sre_stream_fan(void);
-uint32_t sre_stream_fn_stride(uint32_t nstates);
+cudaError_t sre_launch_dfa_stream_reduce(const sre_dev_dfa_t &dfa, const sre_dev_image_t &img,
+    const uint8_t *buf, size_t len, const uint8_t *halo, uint32_t entry, const sre_stream_ws_t &ws,
+    cudaStream_t stream, int *launches);
+cudaError_t sre_launch_dfa_stream_fix(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t len,
+    uint32_t entry_state, const sre_stream_ws_t &ws, unsigned long long *dev_fixed, cudaStream_t stream,
+    int *launches);
+cudaError_t sre_launch_dfa_stream_walk(const sre_dev_dfa_t &dfa, const sre_dev_image_t &img,
+    const uint8_t *buf, size_t len, uint32_t entry_state, const sre_stream_ws_t &ws, uint32_t *dev_out,
+    long long *dev_match_offset, cudaStream_t stream, int *launches);
+/* host side of the record format */
+uint32_t sre_stream_fn_apply(const uint8_t *fn, uint32_t state);    /* SRE_STREAM_UNKNOWN: not known */
+void sre_stream_fn_compose(uint8_t *fn, const uint8_t *then);       /* fn = then o fn                */
+void sre_stream_fn_identity(uint8_t *fn);
+int sre_stream_fn_unresolved(const uint8_t *fn);
 size_t sre_pike_ctx_bytes(uint32_t len, uint32_t nslots, uint32_t max_slots, uint32_t nthreads,
     uint32_t stack_cap);
 

@@ -6,16 +6,17 @@
  * thread-list loop becomes table look-ups over the lowered program
  * (../lower/sre_lower.h):
  *
- *   k_dfa_lines    one CUDA thread per line, determinised program.  Input
- *                  tiles (32 lines x TW bytes per warp) are staged through
- *                  shared memory with 16-byte cp.async copies (coalesced: the
- *                  lanes that share a row cover a contiguous 64/128-byte
- *                  segment), XOR-swizzled so that the per-lane 16-byte reads of
- *                  "my row" are bank-conflict free.  Per input byte the inner
- *                  loop is one PRMT (splice the byte under the state) and one
- *                  LDS.U8 into the [state][byte] table.  HBM-bound by design.
- *   k_dfa_generic  same automaton, any alignment / ragged offsets, optional
- *                  state carry (SRE_AGAIN) -- correctness tier.
+ *   k_dfa_lines_tma_early  one CUDA thread per line, determinised program.
+ *                  Input tiles (32 lines x 128 bytes per warp) are staged
+ *                  through shared memory by the TMA unit (128-byte swizzle: the
+ *                  per-lane 16-byte reads of "my row" are bank-conflict free).
+ *                  Per input byte the inner loop is one PRMT (splice the byte
+ *                  under the state) and one LDS.U8 into the [state][byte] table.
+ *   k_dfa_lines_skipw  the same with a warp-uniform word skip for automata whose
+ *                  start state is left by few byte values.  HBM-bound.
+ *   k_dfa_lines_hint[_skip]  verdict + Pike start hint.
+ *   k_dfa_generic  same automaton, any alignment / ragged offsets, any table
+ *                  size, optional state carry (SRE_AGAIN) -- correctness tier.
  *   k_nfa_lines    the general tier: one warp per line, the NFA thread set is a
  *                  warp-wide bitmask (lane l owns words l, l+32, ... of it, up
  *                  to 4096 states), successor sets come from a shift for
@@ -27,7 +28,7 @@ using namespace sre_dev;
 
 namespace {
 
-/* ---- k_dfa_lines ----------------------------------------------------------- */
+/* ---- k_dfa_lines_tma_early --------------------------------------------------- */
 
 template <bool CLS>
 struct line_consumer_t {
@@ -38,7 +39,7 @@ struct line_consumer_t {
     size_t          nlines;
     int32_t        *rc;
 
-    __device__ __forceinline__ void begin() { s = start; }
+    __device__ __forceinline__ void begin(size_t) { s = start; }
     __device__ __forceinline__ void chunk(const uint4 &v)
     {
         if (CLS) {
@@ -57,80 +58,6 @@ struct line_consumer_t {
         }
     }
 };
-
-template <int TW, int STAGES, bool CLS>
-__global__ void __launch_bounds__(1024, 1)
-k_dfa_lines(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t nlines, size_t pitch,
-            uint32_t linelen, int32_t *__restrict__ rc)
-{
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, CLS);
-    uint8_t *s_tab = smem;
-    uint8_t *s_fin = smem + plan.fin_ofs;
-    uint8_t *s_cls = smem + plan.cls_ofs;
-
-    load_table(s_tab, CLS ? reinterpret_cast<const uint8_t *>(dfa.tcls) : dfa.t256, plan.tab_bytes);
-    load_table(s_fin, dfa.fin, align_up(dfa.nstates, 16));
-    if (CLS) {
-        load_table(s_cls, dfa.clsmap, 256);
-    }
-    __syncthreads();
-
-    const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
-    line_consumer_t<CLS> cons;
-    cons.st256.tab = s_tab;
-    cons.stcls.tab = reinterpret_cast<const uint16_t *>(s_tab);
-    cons.stcls.cls = s_cls;
-    cons.stcls.ncls = dfa.nclasses;
-    cons.fin = s_fin;
-    cons.start = dfa.start;
-    cons.acc = dfa.acc;
-    cons.nlines = nlines;
-    cons.rc = rc;
-
-    tile_pipeline<TW, STAGES>(cons, buf, nlines, pitch, linelen,
-                              smem + plan.stage_ofs + (size_t) warp * STAGES * 32 * TW,
-                              (size_t) blockIdx.x * warps_per_block + warp,
-                              (size_t) gridDim.x * warps_per_block);
-}
-
-/* same consumer, input staged by the TMA unit instead of cp.async */
-template <int TW, int STAGES, bool CLS>
-__global__ void __launch_bounds__(1024, 1)
-k_dfa_lines_tma(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t nlines,
-                uint32_t linelen, int32_t *__restrict__ rc)
-{
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, CLS);
-    uint8_t *s_tab = smem;
-    uint8_t *s_fin = smem + plan.fin_ofs;
-    uint8_t *s_cls = smem + plan.cls_ofs;
-
-    load_table(s_tab, CLS ? reinterpret_cast<const uint8_t *>(dfa.tcls) : dfa.t256, plan.tab_bytes);
-    load_table(s_fin, dfa.fin, align_up(dfa.nstates, 16));
-    if (CLS) {
-        load_table(s_cls, dfa.clsmap, 256);
-    }
-    __syncthreads();
-
-    const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
-    line_consumer_t<CLS> cons;
-    cons.st256.tab = s_tab;
-    cons.stcls.tab = reinterpret_cast<const uint16_t *>(s_tab);
-    cons.stcls.cls = s_cls;
-    cons.stcls.ncls = dfa.nclasses;
-    cons.fin = s_fin;
-    cons.start = dfa.start;
-    cons.acc = dfa.acc;
-    cons.nlines = nlines;
-    cons.rc = rc;
-
-    tile_pipeline_tma<TW, STAGES>(cons, &tmap, nlines, linelen,
-                                  smem + plan.stage_ofs + (size_t) warp * STAGES * 32 * TW,
-                                  reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES,
-                                  (size_t) blockIdx.x * warps_per_block + warp,
-                                  (size_t) gridDim.x * warps_per_block);
-}
 
 /* TMA staging with early stage release (see tile_pipeline_tma_early) */
 template <int STAGES, bool CLS, int THREADS, int BLOCKS>
@@ -183,7 +110,7 @@ k_dfa_lines_tma_early(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tma
  * text this removes more than half of the LDS.U8 look-ups that bound
  * k_dfa_lines_tma_early (shared-memory pipe 90 % busy, profiles/).
  */
-template <int NPAT, bool CHUNKVOTE = false>
+template <int NPAT>
 struct skipw_consumer_t {
     step256_t       st256;
     const uint8_t  *fin;
@@ -192,8 +119,8 @@ struct skipw_consumer_t {
     size_t          nlines;
     int32_t        *rc;
 
-    __device__ __forceinline__ void begin() { s = start; }
-    __device__ __forceinline__ void word(uint32_t w)
+    __device__ __forceinline__ void begin(size_t) { s = start; }
+    __device__ __forceinline__ uint32_t leave(uint32_t w) const
     {
         uint32_t h = 0;
 #pragma unroll
@@ -201,30 +128,10 @@ struct skipw_consumer_t {
             const uint32_t x = w ^ pat[p];
             h |= (x - 0x01010101u) & ~x & 0x80808080u;     /* some byte of x is zero */
         }
-        const bool need = (s != acc) && ((s != start) || h != 0);
-        if (__any_sync(0xffffffffu, need)) {
-            s = st256.word(s, w);
-        }
-    }
-    __device__ __forceinline__ uint32_t leave(uint32_t w) const
-    {
-        uint32_t h = 0;
-#pragma unroll
-        for (int p = 0; p < NPAT; p++) {
-            const uint32_t x = w ^ pat[p];
-            h |= (x - 0x01010101u) & ~x & 0x80808080u;
-        }
         return h;
     }
     __device__ __forceinline__ void chunk(const uint4 &v)
     {
-        if (!CHUNKVOTE) {
-            word(v.x);
-            word(v.y);
-            word(v.z);
-            word(v.w);
-            return;
-        }
         /* one vote per 16 bytes: bit k = "word k must be looked up by some lane".
          * A looked-up word can leave lanes inside a partial match, so every word
          * after the first needed one is looked up as well. */
@@ -249,7 +156,7 @@ struct skipw_consumer_t {
     }
 };
 
-template <int STAGES, int NPAT, int THREADS, int BLOCKS, bool FULLCOPY, bool CHUNKVOTE = false>
+template <int NPAT, int THREADS, int BLOCKS>
 __global__ void __launch_bounds__(THREADS, BLOCKS)
 k_dfa_lines_skipw(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t nlines,
                   uint32_t linelen, uint4 pats, int32_t *__restrict__ rc)
@@ -261,7 +168,7 @@ k_dfa_lines_skipw(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, s
     __syncthreads();
 
     const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
-    skipw_consumer_t<NPAT, CHUNKVOTE> cons;
+    skipw_consumer_t<NPAT> cons;
     cons.st256.tab = smem;
     cons.fin = smem + plan.fin_ofs;
     cons.start = dfa.start;
@@ -272,201 +179,9 @@ k_dfa_lines_skipw(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, s
     cons.pat[3] = pats.w;
     cons.nlines = nlines;
     cons.rc = rc;
-    tile_pipeline_tma_early<STAGES, skipw_consumer_t<NPAT, CHUNKVOTE>, FULLCOPY>(
-        cons, &tmap, nlines, linelen, smem + plan.stage_ofs + (size_t) warp * STAGES * 32 * 128,
-        reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES,
-        (size_t) blockIdx.x * warps_per_block + warp, (size_t) gridDim.x * warps_per_block);
-}
-
-/* ---- k_tma_ceiling (measurement aid) ----------------------------------------- */
-
-/* The same TMA tile pipeline with a consumer that only XORs the bytes: the
- * memory-side ceiling of this access pattern (boxes of 32 rows x 128 B, one row
- * per line), to tell how much of the gap to the HBM peak is the automaton's. */
-struct null_consumer_t {
-    uint32_t  x;
-    int32_t  *rc;
-    size_t    nlines;
-    __device__ __forceinline__ void begin() { x = 0; }
-    __device__ __forceinline__ void chunk(const uint4 &v) { x ^= v.x ^ v.y ^ v.z ^ v.w; }
-    __device__ __forceinline__ void byte(uint32_t b) { x ^= b; }
-    __device__ __forceinline__ void end(size_t group)
-    {
-        const size_t line = group * 32 + (threadIdx.x & 31);
-        if (line < nlines) {
-            rc[line] = (int32_t) x;
-        }
-    }
-};
-
-template <int STAGES, int THREADS, bool EARLY>
-__global__ void __launch_bounds__(THREADS, 1)
-k_tma_ceiling(const __grid_constant__ CUtensorMap tmap, size_t nlines, uint32_t linelen, int32_t *rc)
-{
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
-    null_consumer_t cons;
-    cons.rc = rc;
-    cons.nlines = nlines;
-    uint8_t *stage = smem + 2048 + (size_t) warp * STAGES * 32 * 128;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem) + warp * MAX_STAGES;
-    if (EARLY) {
-        tile_pipeline_tma_early<STAGES>(cons, &tmap, nlines, linelen, stage, bars,
-                                        (size_t) blockIdx.x * warps_per_block + warp,
-                                        (size_t) gridDim.x * warps_per_block);
-    } else {
-        tile_pipeline_tma<128, STAGES>(cons, &tmap, nlines, linelen, stage, bars,
-                                       (size_t) blockIdx.x * warps_per_block + warp,
-                                       (size_t) gridDim.x * warps_per_block);
-    }
-}
-
-/* ---- k_dfa_lines_skip ------------------------------------------------------ */
-
-/*
- * Skip-scan flavour for automata whose start state is left by at most 4
- * distinct byte values (a literal-prefixed regex: /HTTP.../ leaves on 'H'
- * only).  While a line is in the start state, bytes outside that set cannot
- * change anything, so the lane does not look them up: phase 1 marks which of
- * the 32 words of its 128-byte row contain a leave byte (3 ALU ops per word and
- * byte value, no shared-memory traffic beyond the LDS.128 of the row); phase 2
- * walks the table only from marked words until the automaton is back in the
- * start state.  This is the reference's first-byte prefilter
- * (sre_vm_pike_find_first_byte, sre_vm_pike.c:992-1061) applied to the
- * Thompson path; results are identical to k_dfa_lines because T[start][b] ==
- * start for every skipped byte.  It removes most of the per-byte LDS.U8
- * look-ups that bound k_dfa_lines (see profiles/), leaving HBM as the limit.
- */
-template <int STAGES, int NPAT, int THREADS, int BLOCKS>
-__global__ void __launch_bounds__(THREADS, BLOCKS)
-k_dfa_lines_skip(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t nlines,
-                 uint32_t linelen, uint4 pats, int32_t *__restrict__ rc)
-{
-    extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr int TW = 128, STAGE_BYTES = 32 * TW;
-    const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, false);
-    const uint8_t *tab = smem, *fin = smem + plan.fin_ofs;
-    load_table(smem, dfa.t256, plan.tab_bytes);
-    load_table(smem + plan.fin_ofs, dfa.fin, align_up(dfa.nstates, 16));
-    __syncthreads();
-
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
-    const size_t gw = (size_t) blockIdx.x * warps_per_block + warp;
-    const size_t warps_total = (size_t) gridDim.x * warps_per_block;
-    uint8_t *my_stage = smem + plan.stage_ofs + (size_t) warp * STAGES * STAGE_BYTES;
-    uint64_t *my_bars = reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES;
-
-    const size_t ngroups = (nlines + 31) / 32;
-    if (gw >= ngroups) {
-        return;
-    }
-    const uint32_t my_groups = (uint32_t) ((ngroups - gw + warps_total - 1) / warps_total);
-    const uint32_t ntiles = (linelen + TW - 1) / TW;
-    const uint32_t start = dfa.start, acc = dfa.acc;
-
-    auto finish = [&](size_t group, uint32_t s) {
-        const size_t line = group * 32 + lane;
-        if (line < nlines) {
-            rc[line] = (s == acc || fin[s]) ? SRE_K_OK : SRE_K_DECLINED;
-        }
-    };
-    if (ntiles == 0) {
-        for (uint32_t gi = 0; gi < my_groups; gi++) {
-            finish(gw + (size_t) gi * warps_total, start);
-        }
-        return;
-    }
-
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < STAGES; i++) {
-            mbar_init(&my_bars[i], 1);
-        }
-        fence_mbar_init();
-    }
-    __syncwarp();
-
-    const uint32_t total = my_groups * ntiles;
-    uint32_t pk = 0, pgi = 0, pt = 0;
-    auto produce = [&]() {
-        if (pk < total) {
-            if (lane == 0) {
-                uint64_t *bar = &my_bars[pk % STAGES];
-                mbar_arrive_expect_tx(bar, STAGE_BYTES);
-                tma_load_2d(my_stage + (pk % STAGES) * STAGE_BYTES, &tmap, (int32_t) (pt * TW),
-                            (int32_t) ((gw + (size_t) pgi * warps_total) * 32), bar);
-            }
-            pk++;
-            if (++pt == ntiles) {
-                pt = 0;
-                pgi++;
-            }
-        }
-    };
-#pragma unroll
-    for (int i = 0; i < STAGES; i++) {
-        produce();
-    }
-
-    const uint32_t pat[4] = { pats.x, pats.y, pats.z, pats.w };
-    const uint32_t swz = lane & 7;
-    uint32_t s = start, t = 0;
-    size_t group = gw;
-
-    for (uint32_t k = 0; k < total; k++) {
-        mbar_wait(&my_bars[k % STAGES], (k / STAGES) & 1);
-        const uint8_t *row = my_stage + (k % STAGES) * STAGE_BYTES + lane * TW;
-        const uint32_t left = linelen - t * TW;
-        const uint32_t limit = left < (uint32_t) TW ? left : (uint32_t) TW;
-
-        /* phase 1: which words of my row hold a byte that leaves the start state */
-        uint32_t wm = 0;
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(row + ((c ^ swz) << 4));
-            const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                uint32_t h = 0;
-#pragma unroll
-                for (int p = 0; p < NPAT; p++) {
-                    const uint32_t x = w[i] ^ pat[p];
-                    h |= (x - 0x01010101u) & ~x & 0x80808080u;     /* some byte of x is zero */
-                }
-                wm |= (h ? 1u : 0u) << (c * 4 + i);
-            }
-        }
-
-        /* phase 2: walk only from marked words, until back in the start state */
-        uint32_t pos = 0;
-        while (pos < limit && s != acc) {
-            if (s == start) {
-                const uint32_t rem = wm & (0xffffffffu << (pos >> 2));
-                if (rem == 0) {
-                    break;
-                }
-                const uint32_t np = (uint32_t) (__ffs((int) rem) - 1) << 2;
-                if (np > pos) {
-                    pos = np;
-                    if (pos >= limit) {
-                        break;
-                    }
-                }
-            }
-            const uint32_t b = row[(((pos >> 4) ^ swz) << 4) | (pos & 15)];
-            s = tab[(s << 8) | b];
-            pos++;
-        }
-        __syncwarp();
-        produce();
-
-        if (++t == ntiles) {
-            finish(group, s);
-            t = 0;
-            s = start;
-            group += warps_total;
-        }
-    }
+    tile_pipeline_tma_early<1>(cons, &tmap, nlines, linelen, smem + plan.stage_ofs + (size_t) warp * 32 * 128,
+                               reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES,
+                               (size_t) blockIdx.x * warps_per_block + warp, (size_t) gridDim.x * warps_per_block);
 }
 
 /* ---- k_dfa_lines_hint ------------------------------------------------------ */
@@ -486,7 +201,7 @@ struct hint_consumer_t {
     size_t          nlines;
     int32_t        *rc, *hint;
 
-    __device__ __forceinline__ void begin() { s = 0; pos = 0; p0 = 0; }
+    __device__ __forceinline__ void begin(size_t) { s = 0; pos = 0; p0 = 0; }
     __device__ __forceinline__ void step(uint32_t addr)
     {
         s = tab[addr];
@@ -560,7 +275,7 @@ struct hint_skip_consumer_t {
     size_t          nlines;
     int32_t        *rc, *hint;
 
-    __device__ __forceinline__ void begin() { s = start; pos = 0; p0 = 0; }
+    __device__ __forceinline__ void begin(size_t) { s = start; pos = 0; p0 = 0; }
     __device__ __forceinline__ void step(uint32_t addr)
     {
         s = tab[addr];
@@ -970,9 +685,9 @@ k_nfa_lines(sre_dev_nfa_t nfa, const uint8_t *__restrict__ buf, const int64_t *_
 
 namespace sre_dev {
 static int g_num_sms = 0;
-int g_l2_promotion = 3;     /* 0 none, 1 64 B, 2 128 B, 3 256 B (sre_cuda_set_l2_promotion);
-                               256 B measured best on B200: the neighbouring 128 B of a row
-                               are the next tile of the same line */
+/* TMA L2 promotion 256 B: measured best on B200 (5.5 -> 6.1+ TB/s on the line kernels): the
+ * neighbouring 128 B of a row are the next tile of the same line */
+const CUtensorMapL2promotion g_l2_promotion = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
 
 cudaError_t make_row_tensor_map(CUtensorMap *map, const uint8_t *buf, size_t nrows, size_t pitch, int tw)
 {
@@ -1004,7 +719,7 @@ cudaError_t make_row_tensor_map(CUtensorMap *map, const uint8_t *buf, size_t nro
                                  : tw == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
     const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(buf), gdim, gstride,
                               box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                              (CUtensorMapL2promotion) g_l2_promotion, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              g_l2_promotion, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
@@ -1023,60 +738,6 @@ int num_sms()
 }  // namespace sre_dev
 
 namespace {
-
-/* how many warps per block / blocks per SM fit next to the tables */
-bool pick_shape(size_t fixed, size_t per_warp, int *warps, int *blocks_per_sm)
-{
-    *warps = 16;
-    *blocks_per_sm = 2;
-    while (*blocks_per_sm * (fixed + *warps * per_warp + 1024) > SMEM_LIMIT) {
-        if (*blocks_per_sm == 2) {
-            *blocks_per_sm = 1;
-            *warps = 32;
-        } else if (*warps > 4) {
-            *warps -= 4;
-        } else {
-            return false;
-        }
-    }
-    return true;
-}
-
-template <int TW, int STAGES, bool CLS>
-cudaError_t launch_dfa_lines_tma_t(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines,
-    size_t pitch, size_t linelen, int32_t *rc, cudaStream_t stream)
-{
-    static_assert(STAGES <= MAX_STAGES, "stages");
-    const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, CLS);
-    const size_t per_warp = (size_t) STAGES * 32 * TW;
-    int warps, blocks_per_sm;
-    if (!pick_shape(plan.stage_ofs, per_warp, &warps, &blocks_per_sm)) {
-        return cudaErrorInvalidConfiguration;
-    }
-    CUtensorMap tmap;
-    cudaError_t err = make_row_tensor_map(&tmap, buf, nlines, pitch, TW);
-    if (err != cudaSuccess) {
-        return err;
-    }
-    const size_t smem = plan.stage_ofs + warps * per_warp;
-    auto kern = k_dfa_lines_tma<TW, STAGES, CLS>;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        if (err != cudaSuccess) {
-            return err;
-        }
-        smem_set = smem;
-    }
-    const size_t ngroups = (nlines + 31) / 32;
-    size_t grid = (size_t) num_sms() * blocks_per_sm;
-    const size_t need = (ngroups + warps - 1) / warps;
-    if (grid > need) {
-        grid = need;
-    }
-    kern<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen, rc);
-    return cudaGetLastError();
-}
 
 template <int STAGES, bool CLS, int THREADS, int BLOCKS>
 cudaError_t launch_dfa_lines_early_t(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines,
@@ -1112,36 +773,6 @@ cudaError_t launch_dfa_lines_early_t(const sre_dev_dfa_t &dfa, const uint8_t *bu
     return cudaGetLastError();
 }
 
-template <int TW, int STAGES, bool CLS>
-cudaError_t launch_dfa_lines_t(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines,
-    size_t pitch, size_t linelen, int32_t *rc, cudaStream_t stream)
-{
-    const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, CLS);
-    const size_t per_warp = (size_t) STAGES * 32 * TW;
-    int warps, blocks_per_sm;
-    if (!pick_shape(plan.stage_ofs, per_warp, &warps, &blocks_per_sm)) {
-        return cudaErrorInvalidConfiguration;
-    }
-    const size_t smem = plan.stage_ofs + warps * per_warp;
-    auto kern = k_dfa_lines<TW, STAGES, CLS>;
-    static size_t smem_set = 0;         /* per template instance */
-    if (smem > smem_set) {
-        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        if (err != cudaSuccess) {
-            return err;
-        }
-        smem_set = smem;
-    }
-    const size_t ngroups = (nlines + 31) / 32;
-    size_t grid = (size_t) num_sms() * blocks_per_sm;
-    const size_t need = (ngroups + warps - 1) / warps;
-    if (grid > need) {
-        grid = need;
-    }
-    kern<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, buf, nlines, pitch, (uint32_t) linelen, rc);
-    return cudaGetLastError();
-}
-
 }  // namespace
 
 size_t sre_dfa_smem_table_bytes(uint32_t nstates, uint32_t nclasses, bool cls)
@@ -1159,46 +790,26 @@ cudaError_t sre_launch_dfa_lines(const sre_dev_dfa_t &dfa, const uint8_t *buf, s
     if (launches) {
         ++*launches;
     }
-#define SRE_LINES(FN, TW, ST)                                                                 \
-    (cls ? FN<TW, ST, true>(dfa, buf, nlines, pitch, linelen, rc, stream)                      \
-         : FN<TW, ST, false>(dfa, buf, nlines, pitch, linelen, rc, stream))
-    switch (variant) {
-    /* TMA-staged, whole-tile stage occupancy */
-    case 6:  return SRE_LINES(launch_dfa_lines_tma_t, 64, 4);
-    case 1:  return SRE_LINES(launch_dfa_lines_tma_t, 128, 2);
-    case 2:  return SRE_LINES(launch_dfa_lines_tma_t, 32, 4);
-    case 3:  return SRE_LINES(launch_dfa_lines_tma_t, 64, 3);
-    case 4:  return SRE_LINES(launch_dfa_lines_tma_t, 128, 3);
-    case 5:  return SRE_LINES(launch_dfa_lines_tma_t, 32, 6);
-    /* TMA-staged, early stage release: <stages, threads/block, blocks/SM> */
+    /* <stages, threads/block, blocks/SM> */
 #define SRE_EARLY(ST, TH, BL)                                                                  \
     (cls ? launch_dfa_lines_early_t<ST, true, TH, BL>(dfa, buf, nlines, pitch, linelen, rc, stream) \
          : launch_dfa_lines_early_t<ST, false, TH, BL>(dfa, buf, nlines, pitch, linelen, rc, stream))
-    case 0:                                     /* default: best measured on B200 */
-    case 23: return SRE_EARLY(1, 1024, 1);      /* 32 warps/SM */
-    case 20: return SRE_EARLY(1, 640, 2);       /* 40 warps/SM */
-    case 21: return SRE_EARLY(1, 768, 2);       /* 48 warps/SM */
-    case 22: return SRE_EARLY(2, 768, 1);       /* 24 warps/SM */
-    case 24: return SRE_EARLY(1, 512, 3);       /* 48 warps/SM */
-    case 25: return SRE_EARLY(2, 832, 1);       /* 26 warps/SM */
-#undef SRE_EARLY
-    /* cp.async-staged */
-    case 10: return SRE_LINES(launch_dfa_lines_t, 64, 3);
-    case 11: return SRE_LINES(launch_dfa_lines_t, 128, 2);
-    case 12: return SRE_LINES(launch_dfa_lines_t, 32, 4);
-    case 13: return SRE_LINES(launch_dfa_lines_t, 64, 4);
+    switch (variant) {
+    case 0:  return SRE_EARLY(1, 1024, 1);      /* 32 warps/SM: best measured on B200 */
+    case 1:  return SRE_EARLY(1, 768, 2);       /* 48 warps/SM */
+    case 2:  return SRE_EARLY(2, 768, 1);       /* 24 warps/SM, 2 stages */
     default: return cudaErrorInvalidValue;
     }
-#undef SRE_LINES
+#undef SRE_EARLY
 }
 
-template <int WORDSKIP, int STAGES, int NPAT, int THREADS, int BLOCKS>
+template <int NPAT, int THREADS, int BLOCKS>
 static cudaError_t launch_dfa_lines_skip_t(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines,
     size_t pitch, size_t linelen, int32_t *rc, const uint32_t *pats, cudaStream_t stream)
 {
     const dfa_smem_plan_t plan = dfa_smem_plan(dfa.nstates, dfa.nclasses, false);
     const int warps = THREADS / 32;
-    const size_t smem = plan.stage_ofs + (size_t) warps * STAGES * 32 * 128;
+    const size_t smem = plan.stage_ofs + (size_t) warps * 32 * 128;
     if (BLOCKS * (smem + 1024) > SMEM_LIMIT) {
         return cudaErrorInvalidConfiguration;
     }
@@ -1207,10 +818,7 @@ static cudaError_t launch_dfa_lines_skip_t(const sre_dev_dfa_t &dfa, const uint8
     if (err != cudaSuccess) {
         return err;
     }
-    auto kern = WORDSKIP == 3 ? k_dfa_lines_skipw<STAGES, NPAT, THREADS, BLOCKS, false, true>
-              : WORDSKIP == 2 ? k_dfa_lines_skipw<STAGES, NPAT, THREADS, BLOCKS, true>
-              : WORDSKIP == 1 ? k_dfa_lines_skipw<STAGES, NPAT, THREADS, BLOCKS, false>
-                              : k_dfa_lines_skip<STAGES, NPAT, THREADS, BLOCKS>;
+    auto kern = k_dfa_lines_skipw<NPAT, THREADS, BLOCKS>;
     static size_t smem_set = 0;
     if (smem > smem_set) {
         err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
@@ -1244,69 +852,17 @@ cudaError_t sre_launch_dfa_lines_skip(const sre_dev_dfa_t &dfa, const uint8_t *b
     if (launches) {
         ++*launches;
     }
-#define SRE_SKIP(WS, ST, TH, BL)                                                                      \
-    (npat == 1 ? launch_dfa_lines_skip_t<WS, ST, 1, TH, BL>(dfa, buf, nlines, pitch, linelen, rc, pats, stream) \
-     : npat == 2 ? launch_dfa_lines_skip_t<WS, ST, 2, TH, BL>(dfa, buf, nlines, pitch, linelen, rc, pats, stream) \
-                 : launch_dfa_lines_skip_t<WS, ST, 4, TH, BL>(dfa, buf, nlines, pitch, linelen, rc, pats, stream))
+#define SRE_SKIP(TH, BL)                                                                              \
+    (npat == 1 ? launch_dfa_lines_skip_t<1, TH, BL>(dfa, buf, nlines, pitch, linelen, rc, pats, stream) \
+     : npat == 2 ? launch_dfa_lines_skip_t<2, TH, BL>(dfa, buf, nlines, pitch, linelen, rc, pats, stream) \
+                 : launch_dfa_lines_skip_t<4, TH, BL>(dfa, buf, nlines, pitch, linelen, rc, pats, stream))
     switch (variant) {
-    /* divergent walk (k_dfa_lines_skip) */
-    case 30: return SRE_SKIP(0, 1, 1024, 1);
-    case 31: return SRE_SKIP(0, 2, 768, 1);
-    case 32: return SRE_SKIP(0, 1, 768, 2);
-    case 33: return SRE_SKIP(0, 2, 512, 1);
-    /* warp-uniform word skip (k_dfa_lines_skipw), half-row register copies */
-    case 41: return SRE_SKIP(1, 1, 768, 1);
-    case 42: return SRE_SKIP(1, 1, 640, 2);
-    case 43: return SRE_SKIP(1, 2, 768, 1);
-    case 44: return SRE_SKIP(1, 1, 512, 1);
-    /* ... whole-row register copy: the stage is re-armed before processing */
-    case 50: return SRE_SKIP(2, 1, 768, 1);
-    case 51: return SRE_SKIP(2, 1, 896, 1);
-    case 52: return SRE_SKIP(2, 1, 1024, 1);
-    case 53: return SRE_SKIP(2, 1, 640, 1);
-    /* ... one vote per 16-byte chunk instead of per word */
-    case 61: return SRE_SKIP(3, 1, 768, 1);
-    case 62: return SRE_SKIP(3, 1, 640, 2);
-    case 40: return SRE_SKIP(1, 1, 1024, 1);    /* one vote per word */
-    default: return SRE_SKIP(3, 1, 1024, 1);    /* best measured on B200: 94.9 % of the HBM copy peak */
+    case 0:  return SRE_SKIP(1024, 1);      /* best measured on B200: 94.9 % of the HBM copy peak */
+    case 1:  return SRE_SKIP(768, 1);
+    case 2:  return SRE_SKIP(640, 2);
+    default: return cudaErrorInvalidValue;
     }
 #undef SRE_SKIP
-}
-
-template <int STAGES, int THREADS, bool EARLY>
-static cudaError_t launch_ceiling_t(const uint8_t *buf, size_t nlines, size_t pitch, size_t linelen,
-    int32_t *rc, cudaStream_t stream)
-{
-    const size_t smem = 2048 + (size_t) (THREADS / 32) * STAGES * 32 * 128;
-    CUtensorMap tmap;
-    cudaError_t err = make_row_tensor_map(&tmap, buf, nlines, pitch, 128);
-    if (err != cudaSuccess) {
-        return err;
-    }
-    auto kern = k_tma_ceiling<STAGES, THREADS, EARLY>;
-    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (err != cudaSuccess) {
-        return err;
-    }
-    kern<<<(unsigned) num_sms(), THREADS, smem, stream>>>(tmap, nlines, (uint32_t) linelen, rc);
-    return cudaGetLastError();
-}
-
-void sre_dev_set_l2_promotion(int mode)
-{
-    sre_dev::g_l2_promotion = mode < 0 ? 0 : mode > 3 ? 3 : mode;
-}
-
-cudaError_t sre_launch_tma_ceiling(const uint8_t *buf, size_t nlines, size_t pitch, size_t linelen,
-    int32_t *rc, int variant, cudaStream_t stream)
-{
-    switch (variant) {
-    case 1:  return launch_ceiling_t<2, 768, false>(buf, nlines, pitch, linelen, rc, stream);
-    case 2:  return launch_ceiling_t<1, 1024, true>(buf, nlines, pitch, linelen, rc, stream);
-    case 3:  return launch_ceiling_t<1, 512, true>(buf, nlines, pitch, linelen, rc, stream);
-    case 4:  return launch_ceiling_t<3, 512, false>(buf, nlines, pitch, linelen, rc, stream);
-    default: return launch_ceiling_t<2, 768, true>(buf, nlines, pitch, linelen, rc, stream);
-    }
 }
 
 cudaError_t sre_launch_dfa_generic_hint(const sre_dev_dfa_t &dfa, const uint8_t *buf, const int64_t *offsets,

@@ -11,12 +11,22 @@ from . import capi
 
 ENGINE_AUTO, ENGINE_DFA_TILED, ENGINE_DFA_GENERIC, ENGINE_NFA, ENGINE_DFA_SKIP = 0, 1, 2, 3, 4
 STATE_INIT = 0xFFFFFFFF
+STATE_UNKNOWN = 0xFFFFFFFE
+STREAM_FN_BYTES = 32
+STREAM_HALO = 256
+
+
+def engine_variant(engine: int, variant: int) -> int:
+    """launch-shape variant of DFA_TILED / DFA_SKIP (tuning): engine | variant << 8"""
+    return engine | ((variant & 0xFF) << 8)
 
 
 class Info(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in (
         "prog_len", "nfa_states", "nfa_classes", "nfa_kinds", "nfa_shift_states", "dfa_states",
-        "dfa_classes", "dfa_byte_table", "dfa_leave_bytes", "nregexes", "pike_slots")] + [("pike_ctx_bytes", C.c_uint64)]
+        "dfa_classes", "dfa_byte_table", "dfa_leave_bytes", "nregexes", "pike_slots")] + [
+            ("pike_ctx_bytes", C.c_uint64)] + [(n, C.c_uint32) for n in (
+                "dfa_start", "dfa_acc", "image_states", "reserved")]
 
 
 _lib = None
@@ -38,19 +48,18 @@ def lib():
             "sre_cuda_pike_exec_lines_all": (C.c_int, [vp, vp, i64p, sz, sz, sz, sz, i32p, i64p, i32p, vp]),
             "sre_cuda_thompson_exec_stream": (C.c_int, [vp, vp, sz, sz, C.c_uint, C.POINTER(C.c_uint32),
                                                         C.POINTER(C.c_int64), vp]),
-            "sre_cuda_thompson_stream_reduce": (C.c_int, [vp, vp, sz, C.c_char_p, vp]),
+            "sre_cuda_thompson_stream_reduce": (vp, [vp, vp, sz, vp, C.c_uint32, C.c_char_p, vp]),
             "sre_cuda_thompson_stream_resolve": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_uint32),
-                                                           C.POINTER(C.c_int64), vp]),
+                                                           C.POINTER(C.c_int64), C.c_char_p]),
+            "sre_cuda_thompson_stream_free": (None, [vp]),
+            "sre_cuda_stream_fn_apply": (C.c_uint32, [C.c_char_p, C.c_uint32]),
             "sre_cuda_dfa_fin": (C.c_int, [vp, C.c_uint32]),
             "sre_cuda_thompson_exec_lines_host": (C.c_int, [vp, vp, sz, sz, sz, i32p, C.c_int]),
             "sre_cuda_pike_exec_lines_host": (C.c_int, [vp, vp, sz, sz, sz, C.c_int, i32p, i64p, sz]),
-            "sre_cuda_set_variant": (None, [C.c_int]),
-            "sre_cuda_set_l2_promotion": (None, [C.c_int]),
-            "sre_cuda_set_pike_general_only": (None, [C.c_int]),
-            "sre_cuda_pike_last_tier": (C.c_int, []),
+            "sre_cuda_program_set_pike_tier": (None, [vp, C.c_int]),
+            "sre_cuda_program_last_pike_tier": (C.c_int, [vp]),
             "sre_cuda_index_lines": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                                C.POINTER(C.c_size_t), C.c_void_p]),
-            "sre_cuda_set_stream_piece": (None, [C.c_int]),
             "sre_cuda_launch_count": (C.c_long, [C.c_int]),
             "sre_cuda_device_available": (C.c_int, []),
             "sre_cuda_last_error": (C.c_char_p, []),
@@ -147,17 +156,28 @@ class CudaProgram:
             raise SreCudaError(self.lib.L.sre_cuda_last_error().decode())
         return rc, st.value, mc.value
 
-    def stream_reduce(self, buf: torch.Tensor, length: int) -> bytes:
-        fn = C.create_string_buffer(max(self.info.dfa_states, 1))
-        _check(self.lib.L.sre_cuda_thompson_stream_reduce(self.cp, buf.data_ptr(), length, fn,
-                                                          _stream_ptr()))
-        return fn.raw[: self.info.dfa_states]
+    def stream_reduce(self, buf: torch.Tensor, length: int, halo: torch.Tensor | None = None,
+                      entry_state: int = STATE_UNKNOWN) -> "StreamScan":
+        """one part of a sharded stream -> scan handle with .fn, the part's record"""
+        fn = C.create_string_buffer(STREAM_FN_BYTES)
+        if halo is not None:
+            assert halo.is_cuda and halo.dtype == torch.uint8 and halo.numel() == STREAM_HALO
+        h = self.lib.L.sre_cuda_thompson_stream_reduce(
+            self.cp, buf.data_ptr(), length, halo.data_ptr() if halo is not None else None, entry_state, fn,
+            _stream_ptr())
+        if not h:
+            raise SreCudaError(self.lib.L.sre_cuda_last_error().decode())
+        return StreamScan(self, h, fn.raw, (buf, halo))
 
-    def stream_resolve(self, entry_state: int):
-        ex, off = C.c_uint32(0), C.c_int64(-1)
-        _check(self.lib.L.sre_cuda_thompson_stream_resolve(self.cp, entry_state, C.byref(ex),
-                                                           C.byref(off), _stream_ptr()))
-        return ex.value, off.value
+    def dfa_fin(self, state: int) -> bool:
+        """does the EOF step of the lowered DFA see a match in `state`"""
+        return bool(self.lib.L.sre_cuda_dfa_fin(self.cp, state))
+
+    def set_pike_tier(self, mode: int):
+        self.lib.L.sre_cuda_program_set_pike_tier(self.cp, mode)
+
+    def last_pike_tier(self) -> int:
+        return self.lib.L.sre_cuda_program_last_pike_tier(self.cp)
 
     # host-buffer (end-to-end) forms: H2D + kernels + D2H inside the call
     def thompson_lines_host(self, host_buf: torch.Tensor, nlines, pitch, linelen, host_rc: torch.Tensor,
@@ -172,6 +192,39 @@ class CudaProgram:
                                                         linelen, int(gate), host_rc.data_ptr(),
                                                         host_ovec.data_ptr(), self.nslots))
         return host_rc, host_ovec
+
+
+class StreamScan:
+    """a reduced stream part (sre_cuda_thompson_stream_reduce): its records stay
+    on the device until resolve() is given the part's true entry state"""
+
+    def __init__(self, prog, handle, fn: bytes, keep):
+        self.prog, self.handle, self.fn, self._keep = prog, handle, fn, keep
+
+    def resolve(self, entry_state: int):
+        """-> (exit state, offset of the first step that sees a match or -1); .fn is updated"""
+        ex, off = C.c_uint32(0), C.c_int64(-1)
+        fn = C.create_string_buffer(STREAM_FN_BYTES)
+        _check(self.prog.lib.L.sre_cuda_thompson_stream_resolve(self.handle, entry_state, C.byref(ex),
+                                                                C.byref(off), fn))
+        self.fn = fn.raw
+        return ex.value, off.value
+
+    def close(self):
+        if self.handle:
+            self.prog.lib.L.sre_cuda_thompson_stream_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def fn_apply(fn: bytes, state: int) -> int:
+    """state a part's record leads to from `state`; STATE_UNKNOWN when the record cannot tell"""
+    return lib().L.sre_cuda_stream_fn_apply(fn, state)
 
 
 def index_lines(buf: torch.Tensor, length: int | None = None, max_lines: int | None = None) -> torch.Tensor:
@@ -191,7 +244,3 @@ def index_lines(buf: torch.Tensor, length: int | None = None, max_lines: int | N
 
 def launch_count(reset=False) -> int:
     return lib().L.sre_cuda_launch_count(int(reset))
-
-
-def set_variant(v: int):
-    lib().L.sre_cuda_set_variant(v)

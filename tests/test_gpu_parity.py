@@ -28,7 +28,7 @@ def test_classic_thompson_golden(golden, cuda):
 
 
 def test_classic_thompson_jit_api_golden(golden, cuda):
-    for b in runnable(golden)[::7]:
+    for b in runnable(golden):
         p = cuda.compile(b["regexes_b"], b["flags"], multi=b["multi"])
         assert cuda.thompson(p, b["subject_b"], jit=True) == b["thompson"], (b["file"], b["name"])
         p.close()
@@ -36,7 +36,7 @@ def test_classic_thompson_jit_api_golden(golden, cuda):
 
 def test_classic_thompson_streaming_golden(golden, cuda):
     """1-byte chunks with SRE_AGAIN carry: whole rc sequence."""
-    for b in runnable(golden)[::3]:
+    for b in runnable(golden):
         p = cuda.compile(b["regexes_b"], b["flags"], multi=b["multi"])
         got = cuda.thompson(p, b["subject_b"], capi.split_chunks(b["subject_b"]))
         assert got == b["thompson_split"], (b["file"], b["name"])
@@ -53,7 +53,7 @@ def test_classic_pike_golden(golden, cuda):
 
 def test_classic_pike_streaming_golden(golden, cuda):
     """1-byte chunks: final rc/ovector and the temp-capture / pending trace."""
-    for b in runnable(golden)[::3]:
+    for b in runnable(golden):
         p = cuda.compile(b["regexes_b"], b["flags"], multi=b["multi"])
         trace, rc, ov = cuda.pike(p, b["subject_b"], capi.split_chunks(b["subject_b"]))
         want = b["pike_split"]
@@ -108,17 +108,14 @@ def test_batch_golden_pike_with_start_hint(golden, cu, general_only):
     the closure-table tier (k_pike_table, with k_pike_lines re-running what it
     gives up on), once through the general kernel alone (1) and once through the
     walking shared-memory tier (k_pike_small, 2)."""
-    cu.lib().L.sre_cuda_set_pike_general_only(general_only)
-    try:
-        _golden_pike_batch(golden, cu, step=1 if general_only != 1 else 2)
-    finally:
-        cu.lib().L.sre_cuda_set_pike_general_only(0)
+    _golden_pike_batch(golden, cu, general_only)
 
 
-def _golden_pike_batch(golden, cu, step):
+def _golden_pike_batch(golden, cu, tier_mode):
     bad = []
-    for b in runnable(golden)[::step]:
+    for b in runnable(golden):
         prog = cu.CudaProgram(b["regexes_b"], b["flags"], multi=b["multi"])
+        prog.set_pike_tier(tier_mode)
         s = b["subject_b"]
         pitch = max(16, (len(s) + 15) // 16 * 16)
         buf = torch.zeros(pitch, dtype=torch.uint8)
@@ -144,13 +141,11 @@ def test_thompson_tiers_vs_oracle(cu, nlines, linelen, pitch):
     prog = cu.CudaProgram(corpus.C2_REGEX)
     dev = lines.cuda()
     for engine in (cu.ENGINE_DFA_TILED, cu.ENGINE_DFA_GENERIC, cu.ENGINE_NFA, cu.ENGINE_DFA_SKIP, cu.ENGINE_AUTO):
-        variants = {cu.ENGINE_DFA_TILED: (0, 1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 20, 21, 22, 24, 25),
-                    cu.ENGINE_DFA_SKIP: (0, 30, 31, 32, 33, 40, 41, 42, 43, 44, 50, 51, 52, 53, 61, 62)}.get(engine, (0,))
+        variants = {cu.ENGINE_DFA_TILED: (0, 1, 2), cu.ENGINE_DFA_SKIP: (0, 1, 2)}.get(engine, (0,))
         for variant in variants:
-            cu.set_variant(variant)
-            got = prog.thompson_lines(dev, nlines, pitch, linelen, engine=engine).cpu().numpy()
+            got = prog.thompson_lines(dev, nlines, pitch, linelen,
+                                      engine=cu.engine_variant(engine, variant)).cpu().numpy()
             assert (got == want).all(), (engine, variant, int((got != want).sum()))
-    cu.set_variant(0)
     if linelen == 1024:
         assert 0 < (want == 0).sum() < nlines
 
@@ -255,14 +250,12 @@ def test_multi_regex_64_patterns_vs_oracle(cu):
     assert torch.equal(rc, rc2) and torch.equal(ov, ov2)
     assert len(set(want_rc.tolist())) > 8
     # the set runs on the closure-table kernel, not on the general fallback
-    assert cu.lib().L.sre_cuda_pike_last_tier() == 0
+    assert prog.last_pike_tier() == 0
     # ... and the general kernel alone gives the same rows
-    cu.lib().L.sre_cuda_set_pike_general_only(1)
-    try:
-        rc3, ov3 = prog.pike_lines(dev, n, 1024, 1024)
-        assert cu.lib().L.sre_cuda_pike_last_tier() == 1
-    finally:
-        cu.lib().L.sre_cuda_set_pike_general_only(0)
+    prog.set_pike_tier(1)
+    rc3, ov3 = prog.pike_lines(dev, n, 1024, 1024)
+    assert prog.last_pike_tier() == 1
+    prog.set_pike_tier(0)
     assert torch.equal(rc, rc3) and torch.equal(ov, ov3)
 
 
@@ -276,7 +269,7 @@ def test_pike_many_groups_on_the_table_tier(cu):
     _, want_rc, want_ov = baseline.run_lines("oracle", WIDE_REGEX, None, lines.numpy(), n, 1024, 1024,
                                              baseline.ENGINE_PIKE, nthreads=8, ovec_slots=prog.nslots)
     rc, ov = prog.pike_lines(lines.cuda(), n, 1024, 1024)
-    assert cu.lib().L.sre_cuda_pike_last_tier() == 0
+    assert prog.last_pike_tier() == 0
     assert (rc.cpu().numpy() == want_rc).all() and int((rc == 0).sum()) == n
     assert (ov.cpu().numpy() == want_ov).all()
 
@@ -309,7 +302,7 @@ def test_big_regex_set_with_assertions_vs_oracle(cu):
     _, want_rc, want_ov = baseline.run_lines("oracle", pats, None, lines, n, pitch, linelen,
                                              baseline.ENGINE_PIKE, nthreads=8, ovec_slots=prog.nslots)
     rc, ov = prog.pike_lines(torch.from_numpy(lines).cuda(), n, pitch, linelen)
-    assert cu.lib().L.sre_cuda_pike_last_tier() == 0
+    assert prog.last_pike_tier() == 0
     assert (rc.cpu().numpy() == want_rc).all()
     assert (ov.cpu().numpy() == want_ov).all()
     assert len(set(want_rc.tolist())) > 5
@@ -402,7 +395,7 @@ def test_pike_tier_selection(cu):
     dev = corpus.log_lines(n, 1024).cuda()
     prog = cu.CudaProgram(corpus.C3_REGEX)
     rc, _ = prog.pike_lines(dev, n, 1024, 1024)
-    assert cu.lib().L.sre_cuda_pike_last_tier() == 0
+    assert prog.last_pike_tier() == 0
     assert int((rc == 0).sum()) == n
 
 
@@ -431,16 +424,142 @@ def test_stream_scan_vs_oracle(cu):
     nomatch = corpus.gen_data_buffer(40000)[:-8].contiguous()
     rc, _, _ = prog.thompson_stream(nomatch.cuda(), nomatch.numel(), 65536, True)
     assert rc == capi.SRE_DECLINED == o.thompson(po, bytes(nomatch.numpy()))
-    # multi-GPU building blocks: reduce to a function, then resolve
+    # multi-GPU building blocks: reduce a part to a record, then resolve it
     # (the match ends on the last byte, so it is the EOF step that sees it:
     #  the exit state is not ACC and there is no in-stream match offset)
-    fn = prog.stream_reduce(dev, len(data))
-    ex, off = prog.stream_resolve(0)
-    assert fn[0] == ex != 1 and off == -1
+    acc = prog.info.dfa_acc
+    scan = prog.stream_reduce(dev, len(data), entry_state=cu.STATE_INIT)
+    ex, off = scan.resolve(cu.STATE_INIT)
+    assert cu.fn_apply(scan.fn, prog.info.dfa_start) == ex != acc and off == -1
+    scan.close()
     longer = torch.cat([buf, torch.tensor(list(b"xyz"), dtype=torch.uint8)]).cuda()
-    fn = prog.stream_reduce(longer, longer.numel())
-    ex, off = prog.stream_resolve(0)
-    assert fn[0] == ex == 1 and off == len(data)      # the step on 'x' sees the MATCH thread
+    scan = prog.stream_reduce(longer, longer.numel(), entry_state=cu.STATE_INIT)
+    ex, off = scan.resolve(cu.STATE_INIT)
+    assert cu.fn_apply(scan.fn, prog.info.dfa_start) == ex == acc and off == len(data)   # the step on 'x' sees the MATCH thread
+    scan.close()
+    # a part whose entry state is not known: candidates from the halo in front of it
+    cut = 100 * 4096 + 5 * 16
+    halo = dev[cut - cu.STREAM_HALO:cut].clone()
+    first = prog.stream_reduce(dev, cut, entry_state=cu.STATE_INIT)
+    second = prog.stream_reduce(longer[cut:], longer.numel() - cut, halo=halo)
+    mid = cu.fn_apply(first.fn, prog.info.dfa_start)
+    assert mid not in (acc, cu.STATE_UNKNOWN)
+    assert cu.fn_apply(second.fn, mid) == acc
+    ex2, off2 = second.resolve(mid)
+    assert ex2 == acc and cut + off2 == len(data)
+    first.close()
+    second.close()
+
+
+def _chunked_oracle(o, po, data, chunk):
+    pieces = [(data[i:i + chunk], i + chunk >= len(data)) for i in range(0, len(data), chunk)] or [(b"", True)]
+    rcs = o.thompson(po, data, pieces)
+    return rcs[-1], len(rcs) - 1
+
+
+@pytest.mark.parametrize("name", ["c3", "multi8", "multi64"])
+def test_stream_scan_large_automata(cu, name):
+    """the stream scan on programs beyond the old 32-state limit: C3's regex, the
+    8-pattern set and the 64-pattern set (2107 DFA states), over log text in 64 KB,
+    4 KB and 1000-byte chunks: last rc and the chunk in which the reference's call
+    sequence returns SRE_OK (oracle: sre_vm_thompson_exec fed the same chunks)"""
+    rx = {"c3": corpus.C3_REGEX, "multi8": MULTI, "multi64": corpus.multi_pattern_set(64)}[name]
+    prog = cu.CudaProgram(rx)
+    assert prog.info.dfa_states > (32 if name != "c3" else 16) and prog.info.image_states > 0
+    o = capi.load("oracle")
+    po = o.compile(rx)
+    lines = corpus.log_lines(320, 1024, hit_rate=0.0).numpy()
+    quiet = lines.tobytes()
+    for w in (b"GET", b"POST", b"PUT", b"HEAD", b"HTTP", b"08:47:0", b"10", b"11", b"12", b"13", b"14"):
+        quiet = quiet.replace(w, b"~" * len(w))
+    texts = [lines.tobytes(), quiet, quiet[:200000] + b' GET /x/123456 HTTP/1.1" 503 ' + quiet[200000:210000]]
+    for data in texts:
+        dev = torch.frombuffer(bytearray(data) + bytearray(16), dtype=torch.uint8).cuda()
+        for chunk in (65536, 4096, 1000):
+            want_rc, want_idx = _chunked_oracle(o, po, data, chunk)
+            rc, state, mchunk = prog.thompson_stream(dev, len(data), chunk, True)
+            assert rc == want_rc, (name, chunk)
+            if rc == capi.SRE_OK:
+                assert mchunk == want_idx, (name, chunk, mchunk, want_idx)
+        # carried across two calls at an odd (16-byte aligned) cut
+        cut = (len(data) // 3) // 16 * 16
+        rc1, st1, _ = prog.thompson_stream(dev, cut, 4096, False)
+        if rc1 == capi.SRE_AGAIN:
+            rc2, _, _ = prog.thompson_stream(dev[cut:], len(data) - cut, 4096, True, state=st1)
+            assert rc2 == o.thompson(po, data)
+
+
+def test_stream_scan_random_regex_fuzz(cu):
+    """>= 150 random regexes (with ^ $ \\b \\B \\A \\z) over random text of a few
+    pieces: last rc and match chunk for 64 KB, 4 KB and 1000-byte chunks against the
+    oracle's sre_vm_thompson_exec fed the same chunks, chunk edges falling anywhere"""
+    import random
+    rng = random.Random(4242)
+    atoms = ["a", "b", "ab", " ", "\\n", "_", ".", "^", "$", "\\b", "\\B", "\\A", "\\z", "|", "(", ")", "(?:", "*",
+             "+", "?", "*?", "+?", "??", "{2}", "{0,2}", "{1,}", "[ab]", "[^a]", "\\w", "\\W", "\\s", "\\d", "1"]
+    alphabet = b"ab \n_1."
+    o = capi.load("oracle")
+    done = late = 0
+    while done < 160:
+        rx = "".join(rng.choice(atoms) for _ in range(rng.randrange(2, 9))).encode()
+        try:
+            po = o.compile(rx, 0)
+        except capi.SreSyntaxError:
+            continue
+        prog = cu.CudaProgram(rx)
+        if not prog.info.dfa_states:
+            po.close()
+            continue
+        done += 1
+        n = rng.choice([0, 1, 100, 4096, 4097, 9000, 20000, 70000])
+        # text that tends not to match early: drop some letters; plant the rest late
+        alpha = bytes(rng.sample(list(alphabet), rng.randrange(2, 6)))
+        body = bytearray(rng.choice(alpha) for _ in range(n))
+        if n > 200 and rng.random() < 0.7:
+            at = rng.randrange(n // 2, n - 30)
+            body[at:at + 24] = bytes(rng.choice(alphabet) for _ in range(24))
+        data = bytes(body)
+        dev = torch.frombuffer(bytearray(data) + bytearray(16), dtype=torch.uint8).cuda()
+        for chunk in (65536, 4096, 1000):
+            want_rc, want_idx = _chunked_oracle(o, po, data, chunk)
+            rc, state, mchunk = prog.thompson_stream(dev, len(data), chunk, True)
+            assert rc == want_rc, (rx, n, chunk, rc, want_rc)
+            if rc == capi.SRE_OK:
+                assert mchunk == want_idx, (rx, n, chunk, mchunk, want_idx)
+                late += want_idx > 0
+        # without eof: AGAIN or OK, and the carried state continues exactly
+        if n >= 4096:
+            cut = rng.randrange(1, n // 16) * 16
+            rc1, st1, _ = prog.thompson_stream(dev, cut, 4096, False)
+            want1 = o.thompson(po, data, [(data[:cut], False)])[-1]
+            assert rc1 == want1, (rx, n, cut)
+            if rc1 == capi.SRE_AGAIN:
+                rc2, _, _ = prog.thompson_stream(dev[cut:], n - cut, 4096, True, state=st1)
+                assert rc2 == o.thompson(po, data), (rx, n, cut)
+        prog.program.close()
+        po.close()
+    assert late > 20
+
+
+def test_stream_scan_unresolved_pieces_are_repaired(cu):
+    """a regex whose automaton does not forget ([ab]{5} after an a) over text made of
+    a and b only: no window narrows the candidates, every piece is unresolved and
+    goes through the repair path -- still exact"""
+    rx = rb"a[ab]{5}c"
+    prog = cu.CudaProgram(rx)
+    o = capi.load("oracle")
+    po = o.compile(rx)
+    rs = np.random.RandomState(5)
+    body = rs.choice(np.frombuffer(b"ab", dtype=np.uint8), size=40000)
+    for plant in (None, 33333):
+        data = bytearray(body.tobytes())
+        if plant:
+            data[plant:plant + 7] = b"abbabac"
+        data = bytes(data)
+        dev = torch.frombuffer(bytearray(data) + bytearray(16), dtype=torch.uint8).cuda()
+        want_rc, want_idx = _chunked_oracle(o, po, data, 4096)
+        rc, _, mchunk = prog.thompson_stream(dev, len(data), 4096, True)
+        assert rc == want_rc and (rc != capi.SRE_OK or mchunk == want_idx)
 
 
 def test_classic_exec_large_buffer(cuda):
@@ -454,6 +573,10 @@ def test_classic_exec_large_buffer(cuda):
     assert cuda.thompson(p, data, [(data[:half], False), (data[half:], True)]) == [capi.SRE_AGAIN, capi.SRE_OK]
     rc, ov = cuda.pike(p, data[-4096:])
     assert (rc, ov) == (0, [4088, 4096])
+    # a program beyond the old 32-state limit takes the same path (C3's regex: no match in this text)
+    p3 = cuda.compile(corpus.C3_REGEX)
+    assert cuda.thompson(p3, data) == capi.SRE_DECLINED
+    assert cuda.thompson(p3, data + b" GET /x/1 HTTP/1.1 ") == capi.SRE_OK
 
 
 def test_full_size_properties(cu):
@@ -537,7 +660,7 @@ def test_global_scan_classic_and_batch(golden, cuda, cu):
     """all non-overlapping matches: the classic ctx continuation on the GPU and the
     batch entry point sre_cuda_pike_exec_lines_all, against the oracle"""
     o = capi.load("oracle")
-    for b in runnable(golden)[::40]:
+    for b in runnable(golden)[::4]:
         po = o.compile(b["regexes_b"], b["flags"], multi=b["multi"])
         pc = cuda.compile(b["regexes_b"], b["flags"], multi=b["multi"])
         s = b["subject_b"] * 3

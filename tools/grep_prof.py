@@ -43,4 +43,4 @@ p3 = cuda.CudaProgram(corpus.C3_REGEX)
 timed("thompson_ragged C2", lambda: p2.thompson_ragged(flat, off), flat.numel())
 timed("pike ragged C3 (4 groups)", lambda: p3.pike_lines(flat, n, 0, 0, offsets=off), flat.numel())
 rc, ov = p3.pike_lines(flat, n, 0, 0, offsets=off)
-print("matched", int((rc == 0).sum()), "tier", cuda.lib().L.sre_cuda_pike_last_tier())
+print("matched", int((rc == 0).sum()), "tier", prog.last_pike_tier())
