@@ -870,6 +870,8 @@ typedef struct {
     size_t          pitch, linelen, first, count, ovec_slots;
     int32_t        *rc;
     int64_t        *ovec;
+    int             reps;
+    pthread_barrier_t *ready, *done;
 } oj_job_t;
 
 static void *
@@ -882,6 +884,7 @@ oj_worker(void *arg)
     sre_uint_t      ncaps;
     sre_int_t       err_offset, err_id, rc, *ov;
     size_t          i, k, nslots;
+    int             rep;
 
     if (j->nregexes == 1) {
         re = sre_regex_parse(ppool, (sre_char *) j->regexes[0], &ncaps,
@@ -894,10 +897,16 @@ oj_worker(void *arg)
     prog = re ? sre_regex_compile(ppool, re) : NULL;
     if (prog == NULL) {
         j->failed = 1;
+    }
+    /* set-up is outside the timed region: the clock runs between the barriers */
+    pthread_barrier_wait(j->ready);
+    if (j->failed) {
+        pthread_barrier_wait(j->done);
         return NULL;
     }
     nslots = 2 * (ncaps + 1);
     ov = malloc(nslots * sizeof(sre_int_t));
+    for (rep = 0; rep < j->reps; rep++)
     for (i = j->first; i < j->first + j->count; i++) {
         const uint8_t *line = j->buf + i * j->pitch;
         pool = sre_create_pool(1024);
@@ -918,24 +927,27 @@ oj_worker(void *arg)
         j->rc[i] = (int32_t) rc;
         sre_destroy_pool(pool);
     }
+    pthread_barrier_wait(j->done);
     free(ov);
     sre_destroy_pool(ppool);
     return NULL;
 }
 
 SRE_API double
-ref_bench_lines(const char **regexes, const int *flags, int nregexes,
+ref_bench_lines_reps(const char **regexes, const int *flags, int nregexes,
     int engine, const uint8_t *buf, size_t nlines, size_t pitch,
-    size_t linelen, int nthreads, int32_t *rc, int64_t *ovec,
+    size_t linelen, int nthreads, int reps, int32_t *rc, int64_t *ovec,
     size_t ovec_slots)
 {
     pthread_t        *th = calloc(nthreads, sizeof(pthread_t));
     oj_job_t         *jobs = calloc(nthreads, sizeof(oj_job_t));
+    pthread_barrier_t ready, done;
     struct timespec   t0, t1;
     size_t            per = (nlines + nthreads - 1) / nthreads;
     int               t, failed = 0;
 
-    clock_gettime(CLOCK_MONOTONIC, &t0);
+    pthread_barrier_init(&ready, NULL, nthreads + 1);
+    pthread_barrier_init(&done, NULL, nthreads + 1);
     for (t = 0; t < nthreads; t++) {
         oj_job_t *j = &jobs[t];
         j->regexes = regexes; j->flags = flags; j->nregexes = nregexes;
@@ -945,14 +957,80 @@ ref_bench_lines(const char **regexes, const int *flags, int nregexes,
         j->count = j->first >= nlines ? 0
                    : (j->first + per > nlines ? nlines - j->first : per);
         j->rc = rc; j->ovec = ovec; j->ovec_slots = ovec_slots;
+        j->reps = reps; j->ready = &ready; j->done = &done;
         pthread_create(&th[t], NULL, oj_worker, j);
     }
+    pthread_barrier_wait(&ready);
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    pthread_barrier_wait(&done);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
     for (t = 0; t < nthreads; t++) {
         pthread_join(th[t], NULL);
         failed |= jobs[t].failed;
     }
-    clock_gettime(CLOCK_MONOTONIC, &t1);
+    pthread_barrier_destroy(&ready);
+    pthread_barrier_destroy(&done);
     free(th); free(jobs);
     return failed ? -1.0
                   : (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+SRE_API double
+ref_bench_lines(const char **regexes, const int *flags, int nregexes,
+    int engine, const uint8_t *buf, size_t nlines, size_t pitch,
+    size_t linelen, int nthreads, int32_t *rc, int64_t *ovec,
+    size_t ovec_slots)
+{
+    return ref_bench_lines_reps(regexes, flags, nregexes, engine, buf, nlines,
+                                pitch, linelen, nthreads, 1, rc, ovec,
+                                ovec_slots);
+}
+
+/* one stream in `chunk`-byte calls on one context (see ref_shim.c) */
+SRE_API double
+ref_bench_stream(const char **regexes, const int *flags, int nregexes,
+    int engine, const uint8_t *buf, size_t len, size_t chunk, int reps,
+    int *last_rc, long *last_call)
+{
+    sre_pool_t      *ppool = sre_create_pool(4096), *pool;
+    sre_regex_t     *re;
+    sre_program_t   *prog;
+    sre_uint_t       ncaps;
+    sre_int_t        err_offset, err_id;
+    struct timespec  t0, t1;
+    int              rep;
+
+    if (nregexes == 1) {
+        re = sre_regex_parse(ppool, (sre_char *) regexes[0], &ncaps,
+                             flags ? flags[0] : 0, &err_offset);
+    } else {
+        re = sre_regex_parse_multi(ppool, (sre_char **) regexes, nregexes,
+                                   &ncaps, (int *) flags, &err_offset, &err_id);
+    }
+    prog = re ? sre_regex_compile(ppool, re) : NULL;
+    if (prog == NULL || engine == 2) {
+        return -1.0;
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (rep = 0; rep < reps; rep++) {
+        sre_vm_thompson_ctx_t *ctx;
+        size_t                 at = 0;
+        long                   call = 0;
+        sre_int_t              rc = SRE_AGAIN;
+
+        pool = sre_create_pool(4096);
+        ctx = sre_vm_thompson_create_ctx(pool, prog);
+        do {
+            size_t n = len - at < chunk ? len - at : chunk;
+            rc = sre_vm_thompson_exec(ctx, (sre_char *) buf + at, n, at + n >= len);
+            at += n;
+            call++;
+        } while (rc == SRE_AGAIN && at < len);
+        *last_rc = (int) rc;
+        *last_call = call - 1;
+        sre_destroy_pool(pool);
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    sre_destroy_pool(ppool);
+    return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }

@@ -247,6 +247,10 @@ __device__ __forceinline__ void tile_pipeline_tma_early(Consumer &cons, const CU
         if (pk < total) {
             if (lane == 0) {
                 uint64_t *bar = &my_bars[pk % STAGES];
+                /* the lanes' (generic-proxy) reads of this stage are ordered before the
+                 * __syncwarp that precedes this call; the fence orders them before the
+                 * TMA unit's (async-proxy) write into the same bytes */
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                 mbar_arrive_expect_tx(bar, STAGE_BYTES);
                 tma_load_2d(my_stage + (pk % STAGES) * STAGE_BYTES, tmap, (int32_t) (pt * TW),
                             (int32_t) ((gw + (size_t) pgi * warps_total) * 32), bar);

@@ -438,7 +438,7 @@ def test_stream_scan_vs_oracle(cu):
     assert cu.fn_apply(scan.fn, prog.info.dfa_start) == ex == acc and off == len(data)   # the step on 'x' sees the MATCH thread
     scan.close()
     # a part whose entry state is not known: candidates from the halo in front of it
-    cut = 100 * 4096 + 5 * 16
+    cut = 30 * 4096 + 5 * 16
     halo = dev[cut - cu.STREAM_HALO:cut].clone()
     first = prog.stream_reduce(dev, cut, entry_state=cu.STATE_INIT)
     second = prog.stream_reduce(longer[cut:], longer.numel() - cut, halo=halo)
@@ -449,6 +449,11 @@ def test_stream_scan_vs_oracle(cu):
     assert ex2 == acc and cut + off2 == len(data)
     first.close()
     second.close()
+
+
+import re as _re
+_LOOKAHEAD = _re.compile(rb"\$|\\[bBz]")         # assertions that wait for the next byte
+_LOOKBEHIND = _re.compile(rb"\^|\\[AbB]")        # assertions that look at the previous one
 
 
 def _chunked_oracle(o, po, data, chunk):
@@ -500,6 +505,7 @@ def test_stream_scan_random_regex_fuzz(cu):
     alphabet = b"ab \n_1."
     o = capi.load("oracle")
     done = late = 0
+    diverged = set()
     while done < 160:
         rx = "".join(rng.choice(atoms) for _ in range(rng.randrange(2, 9))).encode()
         try:
@@ -523,9 +529,18 @@ def test_stream_scan_random_regex_fuzz(cu):
         for chunk in (65536, 4096, 1000):
             want_rc, want_idx = _chunked_oracle(o, po, data, chunk)
             rc, state, mchunk = prog.thompson_stream(dev, len(data), chunk, True)
-            assert rc == want_rc, (rx, n, chunk, rc, want_rc)
+            if (rc, mchunk if rc == capi.SRE_OK else 0) != (want_rc, want_idx if want_rc == capi.SRE_OK else 0):
+                # The one documented divergence: the reference's
+                # interpreter tests `sp == ctx->buffer` per CHUNK (sre_vm_thompson.c:79, 303,
+                # 312, 321), so a look-ahead assertion held over a chunk edge and followed by a
+                # look-behind one sees "start of input" at offset 0 of a later chunk.  The GPU
+                # path (like the reference's JIT) behaves as on one big buffer.
+                assert _LOOKAHEAD.search(rx) and _LOOKBEHIND.search(rx), (rx, n, chunk, rc, want_rc)
+                one_rc, one_idx = _chunked_oracle(o, po, data, max(len(data), 1))
+                assert rc == one_rc, (rx, n, chunk, rc, one_rc)
+                diverged.add(rx)
+                continue
             if rc == capi.SRE_OK:
-                assert mchunk == want_idx, (rx, n, chunk, mchunk, want_idx)
                 late += want_idx > 0
         # without eof: AGAIN or OK, and the carried state continues exactly
         if n >= 4096:
@@ -539,6 +554,7 @@ def test_stream_scan_random_regex_fuzz(cu):
         prog.program.close()
         po.close()
     assert late > 20
+    assert len(diverged) <= 8, diverged
 
 
 def test_stream_scan_unresolved_pieces_are_repaired(cu):
