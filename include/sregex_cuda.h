@@ -170,6 +170,13 @@ SRE_API uint32_t sre_cuda_stream_fn_apply(const uint8_t *fn, uint32_t state);
 SRE_API int sre_cuda_dfa_fin(sre_cuda_program_t *cp, uint32_t state);
 
 /* Host-buffer conveniences (the end-to-end path: H2D + kernels + D2H inside) */
+/* sre_cuda_thompson_exec_stream over a stream in host memory (pinned memory for
+ * full PCIe speed): slices of slice_bytes (0: 256 MiB; rounded to whole chunks)
+ * are copied while the previous slice is scanned; stops at the first match */
+SRE_API int sre_cuda_thompson_exec_stream_host(sre_cuda_program_t *cp,
+    const uint8_t *host_buf, size_t len, size_t chunk_bytes, unsigned eof,
+    uint32_t *state_io, int64_t *match_chunk, size_t slice_bytes);
+
 SRE_API int sre_cuda_thompson_exec_lines_host(sre_cuda_program_t *cp,
     const uint8_t *host_buf, size_t nlines, size_t pitch, size_t linelen,
     int32_t *host_rc, int engine);

@@ -1,12 +1,10 @@
 """ctypes binding of the sregex C API (reference src/sregex/sregex.h:82-171).
 
-The same binding drives three shared libraries that all export that API:
-
-* ``sregex_b200/libsregex_cuda.so`` -- the product (host front end + CUDA VMs),
-* ``oracle/liboracle.so``           -- the CPU restatement (test checker),
-* ``oracle/_ref/libsregex_ref.so``  -- the unmodified reference (test checker).
-
-so the parity tests read like the reference's own CLI driver
+The binding drives any shared library that exports that API.  The product
+knows one: ``sregex_b200/libsregex_cuda.so`` (host front end + CUDA VMs).  The
+test checkers (the CPU restatement and the unmodified reference) register their
+own libraries from ``oracle/__init__.py``; with the same binding over all three
+the parity tests read like the reference's own CLI driver
 (src/sre_cli.c:299-660): same calls, same argument meaning, same status codes.
 """
 from __future__ import annotations
@@ -20,8 +18,12 @@ SRE_REGEX_CASELESS, SRE_REGEX_NEWLINE = 1, 2
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CUDA_LIB = os.path.join(ROOT, "sregex_b200", "libsregex_cuda.so")
-ORACLE_LIB = os.path.join(ROOT, "oracle", "liboracle.so")
-REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libsregex_ref.so")
+_paths = {"cuda": CUDA_LIB}
+
+
+def register(name: str, path: str):
+    """make another implementation of the sregex API loadable by name (test checkers)"""
+    _paths[name] = path
 
 _intp = C.POINTER(C.c_ssize_t)
 
@@ -257,7 +259,10 @@ _cache: dict = {}
 
 
 def load(which: str) -> SreLib:
-    path = {"cuda": CUDA_LIB, "oracle": ORACLE_LIB, "ref": REF_LIB}[which]
+    if which not in _paths:
+        raise KeyError(f"no sregex library registered as {which!r} (the checkers register theirs on "
+                       f"`import oracle`)")
+    path = _paths[which]
     if path not in _cache:
         if not os.path.exists(path):
             raise FileNotFoundError(path)

@@ -1124,6 +1124,96 @@ sre_cuda_thompson_exec_stream(sre_cuda_program_t *cp, const uint8_t *dev_buf, si
     return SRE_AGAIN;
 }
 
+/*
+ * The same over a stream that lives in HOST memory: slices of slice_bytes are
+ * copied to the device on one CUDA stream while the previous slice is scanned
+ * on another; the automaton state is carried from slice to slice exactly as
+ * *state_io carries it from call to call.  Stops at the slice in which the
+ * match is seen, like a caller of the reference would stop feeding chunks.
+ */
+SRE_API int
+sre_cuda_thompson_exec_stream_host(sre_cuda_program_t *cp, const uint8_t *host_buf, size_t len,
+    size_t chunk_bytes, unsigned eof, uint32_t *state_io, int64_t *match_chunk, size_t slice_bytes)
+{
+    if (cp == NULL || state_io == NULL || (host_buf == NULL && len != 0)) {
+        return fail("NULL program, state or buffer");
+    }
+    if (slice_bytes == 0) {
+        slice_bytes = (size_t) 256 << 20;
+    }
+    if (chunk_bytes != 0) {
+        /* slices hold whole chunks, so that a chunk index is slice base + local index */
+        slice_bytes = slice_bytes < chunk_bytes ? chunk_bytes : slice_bytes / chunk_bytes * chunk_bytes;
+    }
+    slice_bytes = (slice_bytes + 15) & ~(size_t) 15;
+    if (chunk_bytes % 16 != 0 && len > slice_bytes) {
+        return fail("chunk_bytes must be a multiple of 16 for multi-slice host streams");
+    }
+    cudaStream_t copy_st = nullptr, scan_st = nullptr;
+    cudaEvent_t copied[2] = { nullptr, nullptr };
+    scratch_t slice[2];
+    int rc = SRE_ERROR;
+    cudaError_t err = cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&scan_st, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && err == cudaSuccess; i++) {
+        err = cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
+        if (err == cudaSuccess) {
+            err = slice[i].alloc(slice_bytes + 16, scan_st);
+        }
+    }
+    if (err == cudaSuccess) {
+        /* the slices are used by both streams: make the allocations visible to the copy stream */
+        err = cudaStreamSynchronize(scan_st);
+    }
+    const size_t nslices = len == 0 ? 1 : (len + slice_bytes - 1) / slice_bytes;
+    auto enqueue_copy = [&](size_t k) -> cudaError_t {
+        const size_t at = k * slice_bytes, n = len - at < slice_bytes ? len - at : slice_bytes;
+        cudaError_t e = n ? cudaMemcpyAsync(slice[k & 1].p, host_buf + at, n, cudaMemcpyHostToDevice, copy_st)
+                          : cudaSuccess;
+        return e == cudaSuccess ? cudaEventRecord(copied[k & 1], copy_st) : e;
+    };
+    if (err == cudaSuccess) {
+        err = enqueue_copy(0);
+    }
+    for (size_t k = 0; k < nslices && err == cudaSuccess; k++) {
+        const size_t at = k * slice_bytes, n = len - at < slice_bytes ? len - at : slice_bytes;
+        const bool last = k + 1 == nslices;
+        /* slice k+1 travels while slice k is scanned (its buffer was released when
+         * the scan of slice k-1 returned) */
+        if (!last && (err = enqueue_copy(k + 1)) != cudaSuccess) {
+            break;
+        }
+        if ((err = cudaStreamWaitEvent(scan_st, copied[k & 1], 0)) != cudaSuccess) {
+            break;
+        }
+        int64_t mc = -1;
+        rc = sre_cuda_thompson_exec_stream(cp, slice[k & 1].p, n, chunk_bytes, last ? eof : 0, state_io, &mc,
+                                           scan_st);
+        if (rc == SRE_OK && match_chunk) {
+            *match_chunk = (chunk_bytes ? (int64_t) (at / chunk_bytes) : 0) + (mc > 0 ? mc : 0);
+        }
+        if (rc != SRE_AGAIN) {
+            break;
+        }
+    }
+    if (err != cudaSuccess) {
+        fail("host stream scan failed: %s", cudaGetErrorString(err));
+        rc = SRE_ERROR;
+    }
+    /* copies still in flight (early stop) must be over before the slices go back to the pool */
+    if (copy_st) cudaStreamSynchronize(copy_st);
+    if (scan_st) cudaStreamSynchronize(scan_st);
+    slice[0].release();
+    slice[1].release();
+    if (scan_st) cudaStreamSynchronize(scan_st);
+    for (int i = 0; i < 2; i++) {
+        if (copied[i]) cudaEventDestroy(copied[i]);
+    }
+    if (copy_st) cudaStreamDestroy(copy_st);
+    if (scan_st) cudaStreamDestroy(scan_st);
+    return rc;
+}
+
 SRE_API int
 sre_cuda_dfa_fin(sre_cuda_program_t *cp, uint32_t state)
 {

@@ -52,6 +52,8 @@ def lib():
             "sre_cuda_thompson_stream_resolve": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_uint32),
                                                            C.POINTER(C.c_int64), C.c_char_p]),
             "sre_cuda_thompson_stream_free": (None, [vp]),
+            "sre_cuda_thompson_exec_stream_host": (C.c_int, [vp, vp, sz, sz, C.c_uint, C.POINTER(C.c_uint32),
+                                                             C.POINTER(C.c_int64), sz]),
             "sre_cuda_stream_fn_apply": (C.c_uint32, [C.c_char_p, C.c_uint32]),
             "sre_cuda_dfa_fin": (C.c_int, [vp, C.c_uint32]),
             "sre_cuda_thompson_exec_lines_host": (C.c_int, [vp, vp, sz, sz, sz, i32p, C.c_int]),
@@ -186,6 +188,17 @@ class CudaProgram:
         _check(self.lib.L.sre_cuda_thompson_exec_lines_host(self.cp, host_buf.data_ptr(), nlines, pitch,
                                                             linelen, host_rc.data_ptr(), engine))
         return host_rc
+
+    def thompson_stream_host(self, host_buf: torch.Tensor, length: int, chunk_bytes: int, eof: bool,
+                             state: int = STATE_INIT, slice_bytes: int = 0):
+        """a stream in host memory -> (rc, new_state, match_chunk)"""
+        assert not host_buf.is_cuda
+        st, mc = C.c_uint32(state), C.c_int64(-1)
+        rc = self.lib.L.sre_cuda_thompson_exec_stream_host(self.cp, host_buf.data_ptr(), length, chunk_bytes,
+                                                           int(eof), C.byref(st), C.byref(mc), slice_bytes)
+        if rc == capi.SRE_ERROR:
+            raise SreCudaError(self.lib.L.sre_cuda_last_error().decode())
+        return rc, st.value, mc.value
 
     def pike_lines_host(self, host_buf, nlines, pitch, linelen, host_rc, host_ovec, gate=True):
         _check(self.lib.L.sre_cuda_pike_exec_lines_host(self.cp, host_buf.data_ptr(), nlines, pitch,

@@ -17,10 +17,11 @@ def pytest_configure(config):
 def _ensure_built():
     """Build the checkers (and the product library) if they are not there yet.
     On the GPU box the prebuilt .so files travel with the snapshot."""
+    import oracle
     from sregex_b200 import capi
-    if not os.path.exists(capi.ORACLE_LIB):
+    if not os.path.exists(oracle.ORACLE_LIB):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
-    if not os.path.exists(capi.REF_LIB) and os.path.isdir("/root/reference/src/sregex"):
+    if not os.path.exists(oracle.REF_LIB) and os.path.isdir("/root/reference/src/sregex"):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
     if not os.path.exists(capi.CUDA_LIB) and os.path.exists(
             os.path.join(ROOT, "sregex_b200", "csrc", "Makefile")):
@@ -50,8 +51,9 @@ def oracle():
 
 @pytest.fixture(scope="session")
 def ref():
+    import oracle
     from sregex_b200 import capi
-    if not os.path.exists(capi.REF_LIB):
+    if not os.path.exists(oracle.REF_LIB):
         pytest.skip("oracle/_ref not built (reference sources absent)")
     return capi.load("ref")
 

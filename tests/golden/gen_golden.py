@@ -26,6 +26,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+import oracle  # noqa: F401  (registers the checker libraries with capi)
 from sregex_b200 import capi  # noqa: E402
 
 REF_T = "/root/reference/t"

@@ -10,6 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+import oracle  # noqa: F401  (registers the checker libraries with capi)
 from sregex_b200 import capi, corpus
 from sregex_b200 import dist as sdist
 

@@ -424,6 +424,15 @@ def test_stream_scan_vs_oracle(cu):
     nomatch = corpus.gen_data_buffer(40000)[:-8].contiguous()
     rc, _, _ = prog.thompson_stream(nomatch.cuda(), nomatch.numel(), 65536, True)
     assert rc == capi.SRE_DECLINED == o.thompson(po, bytes(nomatch.numpy()))
+    # the same stream from host memory, in slices that are copied while the previous one is scanned
+    for slice_bytes in (0, 65536, 8192):
+        rc, _, mchunk = prog.thompson_stream_host(buf, len(data), 4096, True, slice_bytes=slice_bytes)
+        assert rc == capi.SRE_OK and mchunk == (len(data) - 1) // 4096
+        rc, _, _ = prog.thompson_stream_host(nomatch, nomatch.numel(), 4096, True, slice_bytes=slice_bytes)
+        assert rc == capi.SRE_DECLINED
+    early = torch.cat([torch.tensor(list(b"xx aaabbccbx"), dtype=torch.uint8), buf])
+    rc, _, mchunk = prog.thompson_stream_host(early, early.numel(), 4096, True, slice_bytes=8192)
+    assert rc == capi.SRE_OK and mchunk == 0            # stops at the first slice
     # multi-GPU building blocks: reduce a part to a record, then resolve it
     # (the match ends on the last byte, so it is the EOF step that sees it:
     #  the exit state is not ACC and there is no in-stream match offset)
