@@ -200,12 +200,14 @@ SRE_API int sre_cuda_index_lines(const uint8_t *dev_buf, size_t len,
     int64_t *dev_offsets, size_t max_lines, size_t *nlines, void *stream);
 
 /* Tuning / introspection */
-/* Pike tier sre_cuda_pike_exec_lines may use for this program (tests): 0 =
- * closure-table kernel, then the general kernel for what it gives up on
- * (default); 1 = general kernel only; 2 = walking shared-memory kernel instead
- * of the table kernel */
+/* Pike tier sre_cuda_pike_exec_lines may use for this program (tests): 0 = best
+ * available (default): the determinised Pike VM when the program has one, else
+ * the closure-table kernel, each followed by the next tier for the lines it
+ * gives up on; 1 = general kernel only; 2 = walking shared-memory kernel; 3 =
+ * closure-table kernel also when the program has a determinised form */
 SRE_API void sre_cuda_program_set_pike_tier(sre_cuda_program_t *cp, int mode);
-/* which of those the last sre_cuda_pike_exec_lines call on the program used, -1: none yet */
+/* the first tier of the last sre_cuda_pike_exec_lines call on the program: 3 = determinised
+ * Pike VM (k_pike_lineage), 0 = closure tables, 2 = walking, 1 = general; -1: none yet */
 SRE_API int sre_cuda_program_last_pike_tier(sre_cuda_program_t *cp);
 SRE_API long sre_cuda_launch_count(int reset);      /* kernels launched so far   */
 SRE_API int sre_cuda_device_available(void);        /* 1 if a CUDA device works  */

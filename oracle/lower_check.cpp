@@ -480,3 +480,101 @@ extern "C" long long lc_stream_part_run(lc_t *lc, const uint8_t *buf, size_t len
     *exit_state = s;
     return first;
 }
+
+/*
+ * Host model of kernels/sre_pike_lineage.cu over the P-DFA (sre_pdfa.h): the
+ * forward pass (one table look-up per byte, the state of the last `ring`
+ * positions remembered, the last match event noted), then the backward walk
+ * along the winning thread's lineage.  Returns the matched regex id /
+ * SRE_DECLINED like lc_table_pike, -1000 when the program has no P-DFA, -1001
+ * when the lineage is older than the ring (the kernel hands such a line to the
+ * next tier).  out_info (may be NULL): [0] = P-DFA states, [1] = classes.
+ */
+#include "../sregex_b200/csrc/lower/sre_pdfa.h"
+
+extern "C" long lc_pdfa_pike(sre_program_t *prog, const uint8_t *input, long size, long start, long ring,
+    int64_t *ovec, unsigned *out_info)
+{
+    sre_closure_table_t T;
+    sre_pdfa_t D;
+    if (!sre_build_closure_table(prog, 4096, T) || !sre_build_pdfa(prog, T, 4096, D)) {
+        return -1000;
+    }
+    if (out_info) {
+        out_info[0] = D.nstates;
+        out_info[1] = D.nclasses;
+    }
+    const uint32_t C = D.nclasses;
+    const size_t nslots = T.max_slots;
+    std::vector<uint16_t> hist((size_t) ring, 0);
+    uint32_t s = D.init;
+    long pos = start, mpos = -1;
+    bool have = false, at_eof = false;
+    for (; pos < size && s != 0; pos++) {
+        const uint32_t c = D.clsmap[input[pos]];
+        hist[(size_t) (pos % ring)] = (uint16_t) s;
+        const uint16_t e = D.trans[(size_t) s * C + c];
+        if (e & 0x8000) {
+            have = true;
+            mpos = pos;
+        }
+        s = e & 0x7fff;
+    }
+    if (s != 0 && D.eof_idx[s] != 0xff) {
+        have = true;
+        at_eof = true;
+    }
+    for (size_t k = 0; k < nslots; k++) {
+        ovec[k] = -1;
+    }
+    if (!have) {
+        return SRE_DECLINED;
+    }
+    const long oldest = pos - ring;         /* positions > oldest are still in the ring */
+    uint32_t cur, j, rid;
+    long u;
+    uint32_t unset = nslots >= 32 ? 0xffffffffu : ((1u << nslots) - 1);
+    auto assign = [&](uint32_t mask, long where) {
+        uint32_t m = mask & unset;
+        unset &= ~mask;
+        for (size_t k = 0; k < nslots; k++) {
+            if ((m >> k) & 1) ovec[k] = where;
+        }
+    };
+    if (at_eof) {
+        cur = s;
+        j = D.eof_idx[s];
+        rid = D.eof_regex[s];
+        u = size - 1;
+    } else {
+        if (mpos <= oldest) return -1001;
+        cur = hist[(size_t) (mpos % ring)];
+        const size_t t = (size_t) cur * C + D.clsmap[input[mpos]];
+        j = D.mparent[t];
+        rid = D.mregex[t];
+        assign(D.mmask[t], mpos + 1);
+        u = mpos - 1;
+    }
+    /* j indexes the list of state `cur`, the state before step u + 1 */
+    for (;;) {
+        if (j == D.any_idx[cur]) {
+            break;                          /* the ".*?" thread carries no captures */
+        }
+        if (u < start) {
+            assign(D.init_mask[j], start);  /* a thread of the start closure */
+            break;
+        }
+        if (u <= oldest) return -1001;
+        const uint32_t before = hist[(size_t) (u % ring)];
+        const size_t idx = D.eofs[(size_t) before * C + D.clsmap[input[u]]] + j;
+        assign(D.emask[idx], u + 1);
+        j = D.eparent[idx];
+        cur = before;
+        u--;
+    }
+    const size_t cnt = 2 * (size_t) (prog->multi_ncaps[rid] + 1);
+    for (size_t k = cnt; k < nslots; k++) {
+        ovec[k] = -1;
+    }
+    return (long) rid;
+}

@@ -24,6 +24,7 @@
 #include "../lower/sre_lower.h"
 #include "../lower/sre_closure.h"
 #include "../lower/sre_image.h"
+#include "../lower/sre_pdfa.h"
 
 namespace {
 
@@ -146,6 +147,7 @@ struct sre_cuda_program_s {
     sre_dev_image_t     img;
     sre_dev_nfa_t       nfa;
     sre_dev_pike_t      pike;
+    sre_dev_pdfa_t      pdfa;                   /* nstates == 0: no determinised Pike */
     uint32_t            nfa_shift = 0;
     /* byte values that leave the DFA start state (skip-scan tier), <= 4 kept */
     int                 nleave = 0;             /* -1: more than 4               */
@@ -312,6 +314,25 @@ int upload(sre_cuda_program_t *cp)
         o_cbent = b.add(clo.bent.data(), clo.bent.size() * 4);
         o_cbofs = b.add(clo.bofs.data(), clo.bofs.size() * 2);
     }
+    /* the determinised Pike VM (programs without assertions, up to 4096 thread lists) */
+    sre_pdfa_t pd;
+    const bool has_pd = has_clo && sre_build_pdfa(prog, clo, 4096, pd);
+    size_t o_pcls = 0, o_ptrans = 0, o_peofs = 0, o_pepar = 0, o_pemask = 0, o_pmpar = 0, o_pmmask = 0,
+           o_pmreg = 0, o_pany = 0, o_peof = 0, o_peofr = 0, o_pinit = 0;
+    if (has_pd) {
+        o_pcls = b.add(pd.clsmap, 256);
+        o_ptrans = b.add(pd.trans.data(), pd.trans.size() * 2);
+        o_peofs = b.add(pd.eofs.data(), pd.eofs.size() * 4);
+        o_pepar = b.add(pd.eparent.data(), pd.eparent.size());
+        o_pemask = b.add(pd.emask.data(), pd.emask.size() * 4);
+        o_pmpar = b.add(pd.mparent.data(), pd.mparent.size());
+        o_pmmask = b.add(pd.mmask.data(), pd.mmask.size() * 4);
+        o_pmreg = b.add(pd.mregex.data(), pd.mregex.size() * 2);
+        o_pany = b.add(pd.any_idx.data(), pd.any_idx.size());
+        o_peof = b.add(pd.eof_idx.data(), pd.eof_idx.size());
+        o_peofr = b.add(pd.eof_regex.data(), pd.eof_regex.size() * 2);
+        o_pinit = b.add(pd.init_mask.data(), pd.init_mask.size() * 4);
+    }
     std::vector<uint32_t> start_ofs;
     static_assert(sizeof(sre_start_ent_t) == sizeof(sre_dev_start_t), "start entry layout");
     std::vector<sre_start_ent_t> start_ent;
@@ -389,6 +410,27 @@ int upload(sre_cuda_program_t *cp)
         cp->nfa.complex_mask = reinterpret_cast<const uint32_t *>(base + o_cmask);
         cp->nfa.match_mask = reinterpret_cast<const uint32_t *>(base + o_mmask);
         cp->nfa.match_lookahead = n.has_match_lookahead ? 1 : 0;
+    }
+
+    memset(&cp->pdfa, 0, sizeof(cp->pdfa));
+    if (has_pd) {
+        sre_dev_pdfa_t &d = cp->pdfa;
+        d.nstates = pd.nstates;
+        d.nclasses = pd.nclasses;
+        d.init = pd.init;
+        d.max_slots = pd.max_slots;
+        d.clsmap = base + o_pcls;
+        d.trans = reinterpret_cast<const uint16_t *>(base + o_ptrans);
+        d.eofs = reinterpret_cast<const uint32_t *>(base + o_peofs);
+        d.eparent = base + o_pepar;
+        d.emask = reinterpret_cast<const uint32_t *>(base + o_pemask);
+        d.mparent = base + o_pmpar;
+        d.mmask = reinterpret_cast<const uint32_t *>(base + o_pmmask);
+        d.mregex = reinterpret_cast<const uint16_t *>(base + o_pmreg);
+        d.any_idx = base + o_pany;
+        d.eof_idx = base + o_peof;
+        d.eof_regex = reinterpret_cast<const uint16_t *>(base + o_peofr);
+        d.init_mask = reinterpret_cast<const uint32_t *>(base + o_pinit);
     }
 
     static_assert(sizeof(sre_instruction_t) == sizeof(sre_dev_inst_t), "instruction layout");
@@ -947,16 +989,36 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         k2 = k2 - 4 > k1 ? k2 - 4 : k1;
     }
     const int tier_mode = cp->pike_tier_mode.load();
-    const bool use_table = sre_pike_table_applicable(cp->pike, dev_offsets, linelen, k2 > k1 ? k2 : k1, h2)
-                           && linelen < (1ull << 31) && tier_mode == 0;
-    const bool use_small = !use_table && sre_pike_small_applicable(cp->pike) && linelen < (1ull << 31)
-                           && tier_mode != 1;
+    const bool table_ok = sre_pike_table_applicable(cp->pike, dev_offsets, linelen, k2 > k1 ? k2 : k1, h2)
+                          && linelen < (1ull << 31);
+    /* the determinised Pike VM first when the program has one; the closure-table
+     * kernel (with its larger lists) re-runs the lines whose match outlives the ring */
+    const bool use_lineage = tier_mode == 0 && sre_pike_lineage_applicable(cp->pdfa, linelen) && table_ok;
+    const bool use_table = !use_lineage && table_ok && (tier_mode == 0 || tier_mode == 3);
+    const bool use_small = !use_lineage && !use_table && sre_pike_small_applicable(cp->pike)
+                           && linelen < (1ull << 31) && tier_mode != 1;
     /* global-memory contexts of k_pike_lines: one per concurrent line when it
      * does all the work, a few thousand when it only re-runs what a
      * shared-memory tier gave up on */
-    const size_t nctx = pike_contexts(cp, (use_table || use_small) ? (nlines < 16384 ? nlines : 16384) : nlines);
+    const size_t nctx = pike_contexts(cp, (use_lineage || use_table || use_small) ? (nlines < 16384 ? nlines : 16384)
+                                                                                   : nlines);
     scratch_t pike_scratch;
     CUDA_TRY(pike_scratch.alloc(pike_scratch_bytes(cp, nctx), st));
+    if (use_lineage) {
+        cp->pike_last_tier = 3;
+        err = sre_launch_pike_lineage(cp->pdfa, cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
+                                      dev_rc, dev_ovec, (uint32_t) ovec_slots, work, st, &launches);
+        if (err == cudaSuccess) {
+            err = sre_launch_pike_table(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
+                                        dev_rc, dev_ovec, (uint32_t) ovec_slots, k2 > k1 ? k2 : k1, h2, 1, work, st,
+                                        &launches);
+        }
+        if (err == cudaSuccess) {
+            err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines,
+                                        start, dev_rc, dev_ovec, (uint32_t) ovec_slots, pike_scratch.p,
+                                        nctx, 1, st, &launches, &work->given_up[1]);
+        }
+    } else
     if (use_table) {
         /* the general kernel re-runs what the table kernel gave up on */
         cp->pike_last_tier = 0;

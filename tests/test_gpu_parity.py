@@ -101,13 +101,14 @@ def test_batch_golden_dfa_skip(golden, cu):
     _golden_batch(golden, cu, cu.ENGINE_DFA_SKIP)
 
 
-@pytest.mark.parametrize("general_only", [0, 1, 2])
+@pytest.mark.parametrize("general_only", [0, 1, 2, 3])
 def test_batch_golden_pike_with_start_hint(golden, cu, general_only):
     """every golden block as a 1-line batch through sre_cuda_pike_exec_lines with
     its internal gate + start-hint pass: rc and the whole ovector.  Once through
-    the closure-table tier (k_pike_table, with k_pike_lines re-running what it
-    gives up on), once through the general kernel alone (1) and once through the
-    walking shared-memory tier (k_pike_small, 2)."""
+    the default tiers (0: the determinised Pike VM k_pike_lineage where the program
+    has one, else the closure-table kernel), once through the general kernel alone
+    (1), once through the walking shared-memory tier (k_pike_small, 2) and once
+    through the closure-table tier for every program (k_pike_table, 3)."""
     _golden_pike_batch(golden, cu, general_only)
 
 
@@ -249,29 +250,33 @@ def test_multi_regex_64_patterns_vs_oracle(cu):
     rc2, ov2 = prog.pike_lines(dev, n, 1024, 1024)          # internal gate
     assert torch.equal(rc, rc2) and torch.equal(ov, ov2)
     assert len(set(want_rc.tolist())) > 8
-    # the set runs on the closure-table kernel, not on the general fallback
-    assert prog.last_pike_tier() == 0
-    # ... and the general kernel alone gives the same rows
-    prog.set_pike_tier(1)
-    rc3, ov3 = prog.pike_lines(dev, n, 1024, 1024)
-    assert prog.last_pike_tier() == 1
+    # the set runs on the determinised Pike VM, not on a fallback
+    assert prog.last_pike_tier() == 3
+    # ... and the closure-table kernel and the general kernel alone give the same rows
+    for mode, tier in ((3, 0), (1, 1)):
+        prog.set_pike_tier(mode)
+        rc3, ov3 = prog.pike_lines(dev, n, 1024, 1024)
+        assert prog.last_pike_tier() == tier
+        assert torch.equal(rc, rc3) and torch.equal(ov, ov3)
     prog.set_pike_tier(0)
     assert torch.equal(rc, rc3) and torch.equal(ov, ov3)
 
 
 def test_pike_many_groups_on_the_table_tier(cu):
     """a 14-group log regex (30 capture slots): full ovectors against the oracle,
-    and it runs on the closure-table kernel"""
+    on the determinised Pike VM and on the closure-table kernel"""
     from test_lowering import WIDE_REGEX
     n = 512
     lines = corpus.log_lines(n, 1024)
     prog = cu.CudaProgram(WIDE_REGEX)
     _, want_rc, want_ov = baseline.run_lines("oracle", WIDE_REGEX, None, lines.numpy(), n, 1024, 1024,
                                              baseline.ENGINE_PIKE, nthreads=8, ovec_slots=prog.nslots)
-    rc, ov = prog.pike_lines(lines.cuda(), n, 1024, 1024)
-    assert prog.last_pike_tier() == 0
-    assert (rc.cpu().numpy() == want_rc).all() and int((rc == 0).sum()) == n
-    assert (ov.cpu().numpy() == want_ov).all()
+    for mode, tier in ((0, 3), (3, 0)):
+        prog.set_pike_tier(mode)
+        rc, ov = prog.pike_lines(lines.cuda(), n, 1024, 1024)
+        assert prog.last_pike_tier() == tier
+        assert (rc.cpu().numpy() == want_rc).all() and int((rc == 0).sum()) == n
+        assert (ov.cpu().numpy() == want_ov).all()
 
 
 def test_big_regex_set_with_assertions_vs_oracle(cu):
@@ -390,13 +395,35 @@ def test_pike_with_word_skipping_hint_pass(cu, rx):
 
 def test_pike_tier_selection(cu):
     """the configurations the bench reports must run on the fast tier: C3 (4
-    groups, 10 slots, 1 KB lines) on the closure-table kernel"""
+    groups, 10 slots, 1 KB lines) on the determinised Pike VM"""
     n = 256
     dev = corpus.log_lines(n, 1024).cuda()
     prog = cu.CudaProgram(corpus.C3_REGEX)
     rc, _ = prog.pike_lines(dev, n, 1024, 1024)
-    assert prog.last_pike_tier() == 0
+    assert prog.last_pike_tier() == 3
     assert int((rc == 0).sum()) == n
+
+
+def test_pike_lineage_long_matches_fall_through(cu):
+    """matches longer than the lineage kernel's 64-position ring are handed to the
+    closure-table kernel: same rows as the oracle either way"""
+    rx = rb"(x+)(y*) (\d+)"
+    n, linelen = 512, 256
+    rs = np.random.RandomState(9)
+    lines = np.full((n, linelen), ord("."), dtype=np.uint8)
+    for i in range(n):
+        k = int(rs.randint(1, 200))
+        at = int(rs.randint(0, 20))
+        body = b"x" * k + b"y" * int(rs.randint(0, 10)) + b" " + b"7" * int(rs.randint(1, 5))
+        body = body[: linelen - at]
+        lines[i, at:at + len(body)] = np.frombuffer(body, dtype=np.uint8)
+    prog = cu.CudaProgram(rx)
+    _, want_rc, want_ov = baseline.run_lines("oracle", rx, None, lines, n, linelen, linelen, baseline.ENGINE_PIKE,
+                                             nthreads=8, ovec_slots=prog.nslots)
+    rc, ov = prog.pike_lines(torch.from_numpy(lines).cuda(), n, linelen, linelen)
+    assert prog.last_pike_tier() == 3
+    assert (rc.cpu().numpy() == want_rc).all() and (ov.cpu().numpy() == want_ov).all()
+    assert int((want_ov[:, 1] - want_ov[:, 0] > 70).sum()) > 100 and int((want_rc == 0).sum()) > 400
 
 
 def test_stream_scan_vs_oracle(cu):

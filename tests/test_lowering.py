@@ -269,3 +269,71 @@ def test_closure_table_pike_many_groups(oracle, lc):
         hits += want[0] >= 0
     assert hits == 200
     po.close()
+
+
+def _pdfa_pike(lc, prog, s, start=0, ring=4096):
+    """the P-DFA Pike (CPU model of k_pike_lineage) -> (rc, ovector), None (no P-DFA) or "ring" """
+    ov = (C.c_int64 * prog.nslots)()
+    info = (C.c_uint * 2)()
+    rc = lc.lc_pdfa_pike(prog.prog, s, len(s), start, ring, ov, info)
+    if rc == -1000:
+        return None
+    if rc == -1001:
+        return "ring"
+    return rc, (list(ov) if rc >= 0 else None)
+
+
+def _bind_pdfa(lc):
+    lc.lc_pdfa_pike.restype = C.c_long
+    lc.lc_pdfa_pike.argtypes = [C.c_void_p, C.c_char_p, C.c_long, C.c_long, C.c_long, C.POINTER(C.c_int64),
+                                C.POINTER(C.c_uint)]
+
+
+def test_pdfa_pike_against_golden(golden, oracle, lc):
+    """The determinised Pike VM (ordered thread lists as DFA states + lineage walk,
+    lower/sre_pdfa.cpp) on every golden block it applies to (no assertions): rc and
+    the whole ovector; with a short ring it either agrees or asks for the next tier."""
+    _bind_pdfa(lc)
+    n = short = 0
+    for b in runnable(golden):
+        p = oracle.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        s = b["subject_b"]
+        got = _pdfa_pike(lc, p, s)
+        if got is not None:
+            n += 1
+            assert got == (b["pike"]["rc"], b["pike"]["ov"]), (b["file"], b["name"], got, b["pike"])
+            got8 = _pdfa_pike(lc, p, s, ring=8)
+            assert got8 == "ring" or got8 == got, (b["file"], b["name"])
+            short += got8 == "ring"
+        p.close()
+    assert n > 1000 and short > 20, (n, short)
+
+
+def test_pdfa_pike_fuzz_vs_oracle(oracle, lc):
+    """random assertion-free regexes (nested groups, lazy and greedy repetition,
+    alternation, empty loops) and sets of them x random subjects, searched from
+    offset 0 and from a later start: rc + ovector == the oracle's Pike"""
+    import random
+    _bind_pdfa(lc)
+    rng = random.Random(31337)
+    atoms = ["a", "b", "ab", " ", "_", ".", "|", "(", ")", "(?:", "*", "+", "?", "*?", "+?", "??", "{2}", "{0,2}",
+             "{1,}", "[ab]", "[^a]", "\\w", "\\W", "\\s", "\\d", "1", "(a)", "(b*)", "(a|ab)", "(\\w+)"]
+    alphabet = b"ab _1."
+    done = applicable = 0
+    while done < 1500:
+        k = 1 if rng.random() < 0.7 else rng.randrange(2, 5)
+        rxs = ["".join(rng.choice(atoms) for _ in range(rng.randrange(1, 9))).encode() for _ in range(k)]
+        try:
+            p = oracle.compile(rxs if k > 1 else rxs[0], 0)
+        except capi.SreSyntaxError:
+            continue
+        done += 1
+        for _ in range(3):
+            s = bytes(rng.choice(alphabet) for _ in range(rng.randrange(0, 40)))
+            got = _pdfa_pike(lc, p, s)
+            if got is None:
+                break
+            applicable += 1
+            assert got == oracle.pike(p, s), (rxs, s, got)
+        p.close()
+    assert applicable > 2000
