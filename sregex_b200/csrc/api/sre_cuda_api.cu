@@ -317,20 +317,33 @@ int upload(sre_cuda_program_t *cp)
     /* the determinised Pike VM (programs without assertions, up to 4096 thread lists) */
     sre_pdfa_t pd;
     const bool has_pd = has_clo && sre_build_pdfa(prog, clo, 4096, pd);
-    size_t o_pcls = 0, o_ptrans = 0, o_peofs = 0, o_pepar = 0, o_pemask = 0, o_pmpar = 0, o_pmmask = 0,
-           o_pmreg = 0, o_pany = 0, o_peof = 0, o_peofr = 0, o_pinit = 0;
+    size_t o_pcls = 0, o_ptrans = 0, o_peofs = 0, o_pent = 0, o_pmev = 0, o_peof = 0, o_pinit = 0;
+    uint32_t pd_nent = 0, pd_init_any = 0xff;
     if (has_pd) {
+        /* device form of the provenance records (see sre_dev_pdfa_t) */
+        const uint32_t C = pd.nclasses;
+        std::vector<uint32_t> ent(2 * pd.eparent.size() + 2, 0), mev(2 * (size_t) pd.nstates * C, 0), eofv(pd.nstates);
+        for (uint32_t st = 0; st < pd.nstates; st++) {
+            for (uint32_t c = 0; c < C; c++) {
+                const size_t t = (size_t) st * C + c;
+                for (uint32_t i = pd.eofs[t]; i < pd.eofs[t + 1]; i++) {
+                    ent[2 * (size_t) i] = pd.emask[i];
+                    ent[2 * (size_t) i + 1] = pd.eparent[i] | (pd.eparent[i] == pd.any_idx[st] ? 0x100u : 0u);
+                }
+                mev[2 * t] = pd.mmask[t];
+                mev[2 * t + 1] = pd.mparent[t] | (pd.mparent[t] == pd.any_idx[st] ? 0x100u : 0u)
+                                 | ((uint32_t) pd.mregex[t] << 16);
+            }
+            eofv[st] = pd.eof_idx[st] | ((uint32_t) pd.eof_regex[st] << 16);
+        }
+        pd_nent = (uint32_t) pd.eparent.size();
+        pd_init_any = pd.any_idx[pd.init];
         o_pcls = b.add(pd.clsmap, 256);
         o_ptrans = b.add(pd.trans.data(), pd.trans.size() * 2);
         o_peofs = b.add(pd.eofs.data(), pd.eofs.size() * 4);
-        o_pepar = b.add(pd.eparent.data(), pd.eparent.size());
-        o_pemask = b.add(pd.emask.data(), pd.emask.size() * 4);
-        o_pmpar = b.add(pd.mparent.data(), pd.mparent.size());
-        o_pmmask = b.add(pd.mmask.data(), pd.mmask.size() * 4);
-        o_pmreg = b.add(pd.mregex.data(), pd.mregex.size() * 2);
-        o_pany = b.add(pd.any_idx.data(), pd.any_idx.size());
-        o_peof = b.add(pd.eof_idx.data(), pd.eof_idx.size());
-        o_peofr = b.add(pd.eof_regex.data(), pd.eof_regex.size() * 2);
+        o_pent = b.add(ent.data(), ent.size() * 4);
+        o_pmev = b.add(mev.data(), mev.size() * 4);
+        o_peof = b.add(eofv.data(), eofv.size() * 4);
         o_pinit = b.add(pd.init_mask.data(), pd.init_mask.size() * 4);
     }
     std::vector<uint32_t> start_ofs;
@@ -419,17 +432,14 @@ int upload(sre_cuda_program_t *cp)
         d.nclasses = pd.nclasses;
         d.init = pd.init;
         d.max_slots = pd.max_slots;
+        d.nent = pd_nent;
+        d.init_any = pd_init_any;
         d.clsmap = base + o_pcls;
         d.trans = reinterpret_cast<const uint16_t *>(base + o_ptrans);
         d.eofs = reinterpret_cast<const uint32_t *>(base + o_peofs);
-        d.eparent = base + o_pepar;
-        d.emask = reinterpret_cast<const uint32_t *>(base + o_pemask);
-        d.mparent = base + o_pmpar;
-        d.mmask = reinterpret_cast<const uint32_t *>(base + o_pmmask);
-        d.mregex = reinterpret_cast<const uint16_t *>(base + o_pmreg);
-        d.any_idx = base + o_pany;
-        d.eof_idx = base + o_peof;
-        d.eof_regex = reinterpret_cast<const uint16_t *>(base + o_peofr);
+        d.ent = reinterpret_cast<const uint2 *>(base + o_pent);
+        d.mev = reinterpret_cast<const uint2 *>(base + o_pmev);
+        d.eof = reinterpret_cast<const uint32_t *>(base + o_peof);
         d.init_mask = reinterpret_cast<const uint32_t *>(base + o_pinit);
     }
 
@@ -1006,8 +1016,10 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
     CUDA_TRY(pike_scratch.alloc(pike_scratch_bytes(cp, nctx), st));
     if (use_lineage) {
         cp->pike_last_tier = 3;
-        err = sre_launch_pike_lineage(cp->pdfa, cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
-                                      dev_rc, dev_ovec, (uint32_t) ovec_slots, work, st, &launches);
+        /* rows of a gated batch were set to -1 by the memset above */
+        err = sre_launch_pike_lineage(cp->pdfa, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
+                                      dev_rc, dev_ovec, (uint32_t) ovec_slots, lines.list != nullptr, work, st,
+                                      &launches);
         if (err == cudaSuccess) {
             err = sre_launch_pike_table(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
                                         dev_rc, dev_ovec, (uint32_t) ovec_slots, k2 > k1 ? k2 : k1, h2, 1, work, st,

@@ -201,24 +201,24 @@ cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf,
  * (sre_pike_lineage.cu): same contract as sre_launch_pike_table, pass 0 */
 struct sre_dev_pdfa_t {
     uint32_t         nstates, nclasses, init, max_slots;
+    uint32_t         nent;          /* provenance records                      */
+    uint32_t         init_any;      /* index of the ".*?" thread in the start closure, 0xff: none */
     const uint8_t   *clsmap;        /* [256]                                   */
     const uint16_t  *trans;         /* [nstates][nclasses] next | 0x8000 match */
+    /* provenance of the threads of a transition's next list: record eofs[t] + j =
+     * { slots SAVEd (they take the position after the consumed byte),
+     *   parent index | 0x100 when the parent is the ".*?" thread (the lineage ends) } */
     const uint32_t  *eofs;          /* [nstates * nclasses + 1]                */
-    const uint8_t   *eparent;
-    const uint32_t  *emask;
-    const uint8_t   *mparent;       /* [nstates * nclasses]                    */
-    const uint32_t  *mmask;
-    const uint16_t  *mregex;
-    const uint8_t   *any_idx;       /* [nstates]                               */
-    const uint8_t   *eof_idx;       /* [nstates]                               */
-    const uint16_t  *eof_regex;     /* [nstates]                               */
-    const uint32_t  *init_mask;
+    const uint2     *ent;           /* [nent]                                  */
+    /* the thread that matched in a transition with bit 15: { slots, parent | 0x100 | regex << 16 } */
+    const uint2     *mev;           /* [nstates * nclasses]                    */
+    const uint32_t  *eof;           /* [nstates] first parked MATCH thread (EOF step): index | regex << 16, 0xff: none */
+    const uint32_t  *init_mask;     /* slots SAVEd by the start closure, per thread */
 };
 bool sre_pike_lineage_applicable(const sre_dev_pdfa_t &d, size_t linelen);
-cudaError_t sre_launch_pike_lineage(const sre_dev_pdfa_t &d, const sre_dev_pike_t &pk, const uint8_t *buf,
-    const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines,
-    const int32_t *start, int32_t *rc, int64_t *ovec, uint32_t ovec_slots, sre_pike_work_t *work,
-    cudaStream_t stream, int *launches);
+cudaError_t sre_launch_pike_lineage(const sre_dev_pdfa_t &d, const uint8_t *buf, const int64_t *offsets,
+    size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines, const int32_t *start, int32_t *rc,
+    int64_t *ovec, uint32_t ovec_slots, int prefilled, sre_pike_work_t *work, cudaStream_t stream, int *launches);
 
 /* all non-overlapping matches per line (post-match continuation, global scan)  */
 cudaError_t sre_launch_pike_lines_all(const sre_dev_pike_t &pk, const uint8_t *buf,
