@@ -1383,6 +1383,7 @@ struct sre_vm_pike_ctx_s {
     size_t               d_in_cap;
     std::vector<int64_t> *h_out;
     sre_int_t            pending[2];
+    bool                 started;       /* an exec call has been made */
 };
 
 struct sre_vm_thompson_code_s {
@@ -1621,7 +1622,54 @@ sre_vm_pike_exec(sre_vm_pike_ctx_t *ctx, sre_char *input, size_t size, unsigned 
         CUDA_TRY(cudaMemcpyAsync(ctx->d_in, input, size, cudaMemcpyHostToDevice, CLASSIC_STREAM));
     }
     int launches = 0;
-    cudaError_t err = sre_launch_pike_stream(ctx->cp->pike, ctx->d_ctx, ctx->d_in, size, eof != 0,
+    size_t skip = 0;
+    /*
+     * One long buffer on a fresh context (bench/sregex.c:330-334): the Pike VM need not walk
+     * what cannot be part of the match.  The chunk-parallel Thompson scan says whether and at
+     * which step a match is first seen; the restart flags of the hint automaton give, from
+     * there backwards, the last position before it at which no thread was alive; the Pike VM
+     * runs from that position (as if the bytes before had been fed earlier) until its list is
+     * empty.  Same rc and ovector: leftmost-first cannot begin before a position at which
+     * every thread is dead.
+     */
+    sre_cuda_program_t *cp = ctx->cp;
+    if (!ctx->started && eof && size >= (1u << 16) && cp->has_dfa && cp->has_image && cp->dfa.hcls != nullptr) {
+        sre_cuda_stream_scan_t *sc = nullptr;
+        if (stream_reduce(cp, ctx->d_in, size, nullptr, cp->dfa.start, CLASSIC_STREAM, &sc) != SRE_OK) {
+            return SRE_ERROR;
+        }
+        uint32_t exit_state = 0;
+        int64_t off = -1;
+        int r = stream_resolve(sc, cp->dfa.start, &exit_state, &off, nullptr);
+        if (r == SRE_OK && exit_state != cp->dfa.acc && !cp->low.dfa.fin[exit_state]) {
+            delete sc;
+            ctx->started = true;
+            return SRE_DECLINED;        /* no thread ever matches: the Pike VM would walk it all to say so */
+        }
+        long long p0 = 0;
+        if (r == SRE_OK) {
+            const size_t limit = exit_state == cp->dfa.acc && off >= 0 ? (size_t) off + 1 : size;
+            cudaError_t e = sre_launch_dfa_stream_restart(cp->dfa, ctx->d_in, size, cp->dfa.start, limit, sc->ws,
+                                                          reinterpret_cast<long long *>(sc->d_res), CLASSIC_STREAM,
+                                                          &launches);
+            if (e == cudaSuccess) {
+                e = cudaMemcpyAsync(&p0, sc->d_res, sizeof(p0), cudaMemcpyDeviceToHost, CLASSIC_STREAM);
+            }
+            if (e == cudaSuccess) {
+                e = cudaStreamSynchronize(CLASSIC_STREAM);
+            }
+            if (e != cudaSuccess) {
+                r = fail("restart kernel failed: %s", cudaGetErrorString(e));
+            }
+        }
+        delete sc;
+        if (r != SRE_OK) {
+            return SRE_ERROR;
+        }
+        skip = p0 > 0 && (size_t) p0 <= size ? (size_t) p0 : 0;
+    }
+    ctx->started = true;
+    cudaError_t err = sre_launch_pike_stream(ctx->cp->pike, ctx->d_ctx, ctx->d_in, size, skip, eof != 0,
                                              pending_matched != NULL, ctx->d_out,
                                              (uint32_t) ctx->ovec_slots, CLASSIC_STREAM, &launches);
     count_launches(launches);

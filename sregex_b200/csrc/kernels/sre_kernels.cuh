@@ -236,8 +236,10 @@ cudaError_t sre_launch_index_lines(const uint8_t *buf, size_t len, int64_t *offs
     unsigned long long *workspace, cudaStream_t stream, int *launches);
 
 /* Pike VM streaming step on one persistent context (classic API)             */
+/* skip: with a fresh context, begin at buf + skip as if the bytes before had been fed in an
+ * earlier call and left no thread alive (offsets stay relative to buf) */
 cudaError_t sre_launch_pike_stream(const sre_dev_pike_t &pk, uint8_t *ctx,
-    const uint8_t *buf, size_t len, int eof, int want_pending, int64_t *out,
+    const uint8_t *buf, size_t len, size_t skip, int eof, int want_pending, int64_t *out,
     uint32_t ovec_slots, cudaStream_t stream, int *launches);
 cudaError_t sre_launch_pike_ctx_init(const sre_dev_pike_t &pk, uint8_t *ctx,
     cudaStream_t stream, int *launches);
@@ -273,6 +275,9 @@ cudaError_t sre_launch_dfa_stream_fix(const sre_dev_dfa_t &dfa, const uint8_t *b
 cudaError_t sre_launch_dfa_stream_walk(const sre_dev_dfa_t &dfa, const sre_dev_image_t &img,
     const uint8_t *buf, size_t len, uint32_t entry_state, const sre_stream_ws_t &ws, uint32_t *dev_out,
     long long *dev_match_offset, cudaStream_t stream, int *launches);
+cudaError_t sre_launch_dfa_stream_restart(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t len,
+    uint32_t entry_state, size_t limit, const sre_stream_ws_t &ws, long long *dev_out, cudaStream_t stream,
+    int *launches);
 /* host side of the record format */
 uint32_t sre_stream_fn_apply(const uint8_t *fn, uint32_t state);    /* SRE_STREAM_UNKNOWN: not known */
 void sre_stream_fn_compose(uint8_t *fn, const uint8_t *then);       /* fn = then o fn                */

@@ -1023,14 +1023,24 @@ __global__ void k_pike_ctx_init(sre_dev_pike_t pk, uint8_t *ctx)
 }
 
 /* out[0] = rc, out[1] = pending flag, out[2..3] = pending, out[4..] = ovector */
-__global__ void k_pike_stream(sre_dev_pike_t pk, uint8_t *ctx, const uint8_t *buf, size_t len, int eof,
-                              int64_t *out, uint32_t ovec_slots, int parts)
+__global__ void k_pike_stream(sre_dev_pike_t pk, uint8_t *ctx, const uint8_t *buf, size_t len, size_t skip,
+                              int eof, int64_t *out, uint32_t ovec_slots, int parts)
 {
     extern __shared__ uint32_t smem_ctx[];
     pike_ctx_t c;
     pike_attach(c, pk, reinterpret_cast<uint32_t *>(ctx), 1, smem_ctx, parts, 0, 1);
     pike_hdr_load(pk, c);
     c.cap_reset();      /* between calls the working capture is all -1 */
+    if (skip > 0 && skip <= len && c.h->first_buf && c.h->processed_bytes == 0) {
+        /* the state a context is in after `skip` bytes that left no thread alive: the offsets
+         * go on from there, and the look-behind assertions of the threads added at the new
+         * offset 0 see the byte before it (sre_vm_pike.c:839-887 read these fields) */
+        c.h->processed_bytes = (int64_t) skip;
+        c.h->seen_newline = buf[skip - 1] == '\n';
+        c.h->seen_word = isword(buf[skip - 1]);
+        buf += skip;
+        len -= skip;
+    }
     int pending = 0;
     const int r = pike_exec(pk, c, buf, (int64_t) len, eof != 0, out + 4, ovec_slots, &pending);
     pike_hdr_store(pk, c);
@@ -1148,7 +1158,7 @@ cudaError_t sre_launch_pike_ctx_init(const sre_dev_pike_t &pk, uint8_t *ctx, cud
 }
 
 cudaError_t sre_launch_pike_stream(const sre_dev_pike_t &pk, uint8_t *ctx, const uint8_t *buf,
-    size_t len, int eof, int want_pending, int64_t *out, uint32_t ovec_slots, cudaStream_t stream,
+    size_t len, size_t skip, int eof, int want_pending, int64_t *out, uint32_t ovec_slots, cudaStream_t stream,
     int *launches)
 {
     (void) want_pending;
@@ -1158,6 +1168,6 @@ cudaError_t sre_launch_pike_stream(const sre_dev_pike_t &pk, uint8_t *ctx, const
     /* the marks persist between calls, so they stay in the ctx block */
     size_t smem;
     const int parts = smem_parts(pk, 1, false, &smem);
-    k_pike_stream<<<1, 1, smem, stream>>>(pk, ctx, buf, len, eof, out, ovec_slots, parts);
+    k_pike_stream<<<1, 1, smem, stream>>>(pk, ctx, buf, len, skip, eof, out, ovec_slots, parts);
     return cudaGetLastError();
 }

@@ -776,6 +776,68 @@ k_stream_locate(sre_dev_dfa_t dfa, sre_dev_image_t img, stream_src_t src, const 
     }
 }
 
+/* state in which `piece` is entered when the stream part is entered in root_state (whole warp;
+ * every record left of the piece must be resolved) */
+__device__ __forceinline__ uint32_t state_before_piece(const stream_levels_t &lv, uint32_t root_state, size_t piece)
+{
+    size_t parent = 0, span = 1;
+    for (int l = 0; l < lv.top; l++) {
+        span *= FAN;
+    }
+    uint32_t s = root_state;
+    for (int l = lv.top; l >= 0; l--, span /= FAN) {
+        const size_t child = piece / span;      /* the ancestor of the piece at level l */
+        uint32_t mine;
+        s = walk_children(lv, l, parent, child, s, mine);
+        parent = child;
+    }
+    return s;
+}
+
+/*
+ * Restart point for a leftmost-first (Pike) search of a long buffer whose match the scan has
+ * located: the last position p0 < limit after a byte that only the ".*?" thread consumed (the
+ * restart flag of the hint table, see k_dfa_lines_hint) -- no thread alive at p0 started before
+ * it, so the Pike VM may begin there.  Walks back piece by piece from the one that holds
+ * limit - 1; gives 0 after max_back pieces without a flag (always a valid place to begin).
+ */
+__global__ void __launch_bounds__(32)
+k_stream_restart(sre_dev_dfa_t dfa, stream_src_t src, stream_levels_t lv, uint32_t root_state, size_t limit,
+                 uint32_t max_back, long long *out)
+{
+    const uint32_t lane = threadIdx.x;
+    if (limit == 0 || dfa.hcls == nullptr) {
+        if (lane == 0) {
+            *out = 0;
+        }
+        return;
+    }
+    size_t piece = (limit - 1) / PIECE;
+    for (uint32_t back = 0;; back++) {
+        const uint32_t s_in = state_before_piece(lv, root_state, piece);
+        long long found = -1;
+        if (lane == 0 && s_in != NONE) {
+            const size_t b = piece * PIECE, e = b + PIECE < limit ? b + PIECE : limit;
+            uint32_t s = s_in;
+            for (size_t i = b; i < e && s != ACC; i++) {
+                const uint32_t t = __ldg(dfa.hcls + s * dfa.hncls + __ldg(dfa.hclsmap + __ldg(src.buf + i)));
+                s = t & 0x7fffu;
+                if (t & 0x8000u) {
+                    found = (long long) i + 1;
+                }
+            }
+        }
+        found = __shfl_sync(FULL, found, 0);
+        if (found >= 0 || piece == 0 || back >= max_back || s_in == NONE) {
+            if (lane == 0) {
+                *out = found >= 0 ? found : 0;
+            }
+            return;
+        }
+        piece--;
+    }
+}
+
 int top_level(const sre_stream_ws_t &ws)
 {
     int top = 0;
@@ -956,5 +1018,18 @@ cudaError_t sre_launch_dfa_stream_walk(const sre_dev_dfa_t &dfa, const sre_dev_i
         return err;
     }
     k_stream_locate<<<1, 32, 0, stream>>>(dfa, img, src, ws.first_acc, dev_out, dev_match_offset);
+    return cudaGetLastError();
+}
+
+/* restart point of a Pike search that must find the match the scan saw at step `limit - 1`
+ * (or at the EOF step: limit = len); the records must be resolved (sre_launch_dfa_stream_walk ran) */
+cudaError_t sre_launch_dfa_stream_restart(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t len,
+    uint32_t entry_state, size_t limit, const sre_stream_ws_t &ws, long long *dev_out, cudaStream_t stream,
+    int *launches)
+{
+    const stream_levels_t lv = levels_of(ws);
+    const stream_src_t src = { buf, len, nullptr, entry_state };
+    if (launches) ++*launches;
+    k_stream_restart<<<1, 32, 0, stream>>>(dfa, src, lv, entry_state, limit, 256, dev_out);
     return cudaGetLastError();
 }

@@ -90,3 +90,85 @@ def test_cli_over_libsregex_cuda(golden):
     blocks = [b for b in runnable(golden) if _usable(b)]
     for b in blocks[::160]:
         _run_block(cli, b, jit=True)
+
+
+# ---- the reference's own callers, compiled unmodified against libsregex_cuda -----------------
+# (oracle/Makefile `callers`: /root/reference/src/sre_cli.c and bench/sregex.c, binaries under
+# the git-ignored oracle/_ref/; built in the build container, they travel to the GPU box)
+
+REF_BIN = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _caller(name):
+    path = os.path.join(REF_BIN, name)
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not built (reference sources absent)")
+    return path
+
+
+@pytest.mark.gpu
+def test_unmodified_reference_cli_over_libsregex_cuda(golden):
+    """src/sre_cli.c itself (what t/SRegex.pm drives), re-linked with -lsregex_cuda: the six
+    modes per subject print what the reference's own build prints"""
+    cli = _caller("sre-cli-cuda")
+    blocks = [b for b in runnable(golden) if _usable(b)]
+    for b in blocks[::40]:
+        _run_block(cli, b, jit=True)
+
+
+def _gen_data(path, repeat):
+    with open(path, "wb") as f:                 # bench/gen-data.pl:9
+        f.write(b"abccc" * repeat + b"aaabbccb")
+    return 5 * repeat + 8
+
+
+def _bench_times(out):
+    import re
+    t = {}
+    for line in out.splitlines():
+        m = re.match(r"sregex (Thompson JIT|Thompson|Pike) (.*): ([0-9.]+) ms elapsed\.", line)
+        assert m, line
+        t[m.group(1)] = (m.group(2), float(m.group(3)))
+    return t
+
+
+@pytest.mark.gpu
+def test_unmodified_reference_bench_over_libsregex_cuda(tmp_path):
+    """bench/sregex.c itself (BASELINE configs[0]), re-linked with -lsregex_cuda, over the
+    bench/gen-data.pl buffer at its shipped size and scaled to 16 MiB: same verdicts and the same
+    Pike offsets as the reference; the times go to gpurun_out/ beside the CPU's"""
+    import json
+    bench, ref = _caller("bench-sregex-cuda"), _caller("bench-sregex-ref")
+    regex = "(?:a|b)aa(?:aa|bb)cc(?:a|b)"       # bench/Makefile:62
+    report = {}
+    for repeat in (1048576, 3355443):
+        n = _gen_data(tmp_path / "abc.txt", repeat)
+        row = {}
+        for name, exe in (("gpu", bench), ("cpu", ref)):
+            res = subprocess.run([exe, "--thompson", "--thompson-jit", "--pike", regex, str(tmp_path / "abc.txt")],
+                                 capture_output=True, timeout=600)
+            assert res.returncode == 0, res.stderr
+            t = _bench_times(res.stdout.decode())
+            assert t["Thompson"][0] == "match" and t["Thompson JIT"][0] == "match", t
+            assert t["Pike"][0] == f"match ({n - 8}, {n})", t
+            row[name] = {k: {"ms": v[1], "MB_per_s": n / v[1] / 1e3} for k, v in t.items()}
+        report[str(n)] = row
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "reference_bench_unmodified.json"), "w") as f:
+        json.dump(report, f, indent=1)
+
+
+def test_unmodified_reference_bench_builds_against_the_product_header():
+    """CPU tier: the binaries exist after build() in the build container and are linked against
+    libsregex_cuda.so (not against the reference library)"""
+    bench = _caller("bench-sregex-cuda")
+    out = subprocess.run(["ldd", bench], capture_output=True).stdout.decode()
+    assert "libsregex_cuda.so" in out and "libsregex_ref" not in out
+    # the same source against the reference library prints the reference's answer (tiny buffer)
+    ref = _caller("bench-sregex-ref")
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        n = _gen_data(os.path.join(d, "abc.txt"), 1000)
+        res = subprocess.run([ref, "--thompson", "--pike", "(?:a|b)aa(?:aa|bb)cc(?:a|b)", os.path.join(d, "abc.txt")],
+                             capture_output=True)
+        assert res.returncode == 0 and f"match ({n - 8}, {n})" in res.stdout.decode()

@@ -631,8 +631,18 @@ def test_classic_exec_large_buffer(cuda):
     assert cuda.thompson(p, data[:-8]) == capi.SRE_DECLINED
     half = len(data) // 2
     assert cuda.thompson(p, data, [(data[:half], False), (data[half:], True)]) == [capi.SRE_AGAIN, capi.SRE_OK]
-    rc, ov = cuda.pike(p, data[-4096:])
-    assert (rc, ov) == (0, [4088, 4096])
+    # sre_vm_pike_exec over the whole buffer: the scan locates the match, the Pike VM runs from
+    # the last position before it at which no thread was alive (bench/sregex.c:330-334)
+    rc, ov = cuda.pike(p, data)
+    assert (rc, ov) == (0, [len(data) - 8, len(data)])
+    assert cuda.pike(p, data[:-8])[0] == capi.SRE_DECLINED
+    mid = data[:3000000] + b"baabbccaxyz" + data[3000000:]        # an earlier match in the middle
+    assert cuda.pike(p, mid) == (0, [3000000, 3000008])
+    o = capi.load("oracle")
+    for rx, text in ((rb"(c+)(a|b)(\w*)", data[:300000]), (rb"^(abc+)+$", data[:100000 - 3]),
+                     (rb"\b(\w+)\b", b"." * 200000 + b"word" + b"." * 100000), (rb"x*", data[:70000])):
+        po, pc = o.compile(rx), cuda.compile(rx)
+        assert cuda.pike(pc, text) == o.pike(po, text), rx
     # a program beyond the old 32-state limit takes the same path (C3's regex: no match in this text)
     p3 = cuda.compile(corpus.C3_REGEX)
     assert cuda.thompson(p3, data) == capi.SRE_DECLINED
@@ -740,3 +750,53 @@ def test_global_scan_classic_and_batch(golden, cuda, cu):
         got = [(int(ids[i, k]), int(spans[i, k, 0]), int(spans[i, k, 1])) for k in range(len(want))]
         assert got == want, i
     assert int(count.max()) >= 5
+
+
+def test_one_program_from_two_threads_and_two_streams(cu):
+    """re-entrancy at the boundary (the reference's JIT run time is re-entrant): ONE
+    lowered program driven from 2 host threads x 2 CUDA streams at once -- Thompson lines, Pike
+    lines and the stream scan -- with different inputs per thread; every result bit-exact"""
+    import threading
+    n = 8192
+    prog2 = cu.CudaProgram(corpus.C2_REGEX)
+    prog3 = cu.CudaProgram(corpus.C3_REGEX)
+    progs = cu.CudaProgram(corpus.BENCH_REGEX)
+    inputs, want = [], []
+    for t in range(4):
+        lines = corpus.log_lines(n, 1024, first_line=t * n)
+        host = lines.numpy()
+        _, w2, _ = baseline.run_lines("oracle", corpus.C2_REGEX, None, host, n, 1024, 1024, baseline.ENGINE_THOMPSON,
+                                      nthreads=8)
+        _, w3rc, w3ov = baseline.run_lines("oracle", corpus.C3_REGEX, None, host, n, 1024, 1024, baseline.ENGINE_PIKE,
+                                           nthreads=8, ovec_slots=prog3.nslots)
+        stream = corpus.gen_data_buffer(30000 + 777 * t)
+        if t % 2:
+            stream = stream[:-8].contiguous()
+        inputs.append((lines.cuda(), stream.cuda(), stream.numel()))
+        want.append((w2, w3rc, w3ov, capi.SRE_DECLINED if t % 2 else capi.SRE_OK))
+    errors = []
+
+    def worker(t):
+        try:
+            torch.cuda.set_device(0)
+            st = torch.cuda.Stream()
+            dev, sdev, slen = inputs[t]
+            w2, w3rc, w3ov, wst = want[t]
+            with torch.cuda.stream(st):
+                for _ in range(25):
+                    rc = prog2.thompson_lines(dev, n, 1024, 1024)
+                    prc, pov = prog3.pike_lines(dev, n, 1024, 1024)
+                    src, _, _ = progs.thompson_stream(sdev, slen, 4096, True)
+                    st.synchronize()
+                    assert (rc.cpu().numpy() == w2).all(), "thompson"
+                    assert (prc.cpu().numpy() == w3rc).all() and (pov.cpu().numpy() == w3ov).all(), "pike"
+                    assert src == wst, "stream"
+        except Exception as e:      # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
