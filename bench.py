@@ -13,6 +13,8 @@ host buffers, the reference's CPU path beside it), at every N:
       across the GPUs: which pattern matched (Thompson gate + Pike id)     (strong)
   c5  one 32 GiB stream in 64 KB chunks with SRE_AGAIN state carry,
       chunk-parallel scan; sharded: halo + record all-gather over NCCL     (strong)
+  text  Thompson boolean per line of newline-delimited text (ragged lines,
+      no line index beforehand), 1 GiB per GPU, one pass                   (weak)
 
   python bench.py --gpus N --steps K --warmup W            (our arm)
   python bench.py --impl reference ...                      (reference CPU arm)
@@ -45,6 +47,7 @@ METRICS = {
     "c3": "input GB/s scanned (Pike + 4 capture groups, rc + ovector per line, 1M x 1 KB lines per GPU)",
     "c4": "input GB/s scanned (64-pattern set, matched id per line, 8 GiB corpus sharded over the GPUs)",
     "c5": "input GB/s scanned (one 32 GiB stream, 64 KB chunks with SRE_AGAIN carry, sharded over the GPUs)",
+    "text": "input GB/s scanned (Thompson boolean per line of newline-delimited text, 1 GiB per GPU, one pass)",
 }
 
 
@@ -533,6 +536,71 @@ def bench_c4(h, steps, warmup):
     return out
 
 
+def bench_text(h, steps, warmup, dev):
+    """grep: every line of '\\n'-delimited text (ragged lines, no index beforehand) in one pass"""
+    from oracle import cpu_baseline as baseline
+    from sregex_b200 import capi, corpus, cuda
+    torch = h.torch
+    flat = dev.view(-1).clone()
+    n = flat.numel()
+    # newlines at pseudo-random places: line lengths geometric with mean ~180 bytes
+    blk = 1 << 27
+    for i in range(0, n, blk):
+        m = min(blk, n - i)
+        pos = torch.arange(i, i + m, dtype=torch.int64, device="cuda")
+        hsh = (pos * -7046029254386353131) ^ (pos >> 13)
+        flat[i:i + m][((hsh >> 17) & 0xFFFF) % 180 == 0] = 10
+        del pos, hsh
+    prog = cuda.CudaProgram(corpus.C2_REGEX)
+    nl = int((flat == 10).sum()) + (1 if int(flat[-1]) != 10 else 0)
+    rc = torch.empty(nl, dtype=torch.int32, device="cuda")
+    off = torch.empty(nl + 1, dtype=torch.int64, device="cuda")
+    found = [0]
+
+    def step():
+        cnt = __import__("ctypes").c_size_t(0)
+        r = prog.lib.L.sre_cuda_thompson_exec_text(prog.cp, flat.data_ptr(), n, off.data_ptr(), rc.data_ptr(), nl,
+                                                   __import__("ctypes").byref(cnt),
+                                                   torch.cuda.current_stream().cuda_stream)
+        assert r == capi.SRE_OK
+        found[0] = cnt.value
+
+    total_ms, call_ms, clocks, launches = h.timed(step, steps, warmup)
+    assert found[0] == nl, (found[0], nl)
+    # parity at full size: the line index + ragged route must give the same rows
+    off2 = cuda.index_lines(flat)
+    assert torch.equal(off2, off)
+    rc2 = prog.thompson_ragged(flat, off2)
+    assert torch.equal(rc2, rc), "text: one-pass rows differ from index + ragged"
+    out = {
+        "metric": METRICS["text"], "value": h.world * n * steps / (total_ms * 1e-3) / 1e9, "unit": "GB/s",
+        "steps": steps, "ms_per_step": total_ms / steps, "scaling": "weak",
+        "config": {"workload": "newline-delimited log text (ragged lines, mean ~180 B, no index beforehand): "
+                               "sre_vm_thompson_exec per line, regex " + REGEX_NAME,
+                   "bytes_per_gpu": n, "lines": nl, "matched_lines": int((rc == 0).sum())},
+        # 1 B per input byte + 4 B verdict + 8 B offset per line
+        "roofline": h.roofline(n + 12 * nl, call_ms, "sre_cuda_thompson_exec_text: k_text_pieces + scan + write",
+                               note="whole call (3 launches + the read-back of the line count)"),
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    if h.rank == 0 and h.world == 1:
+        which = ref_kind()
+        m = 20000
+        host_off = off[: m + 1].cpu().numpy()
+        text = flat[: int(host_off[-1])].cpu().numpy().tobytes()
+        o = capi.load("oracle" if which == "oracle" else "ref")
+        po = o.compile(corpus.C2_REGEX)
+        t0 = time.perf_counter()
+        want = [o.thompson(po, text[host_off[i]:host_off[i + 1]], jit=(which == "ref")) for i in range(m)]
+        dt = time.perf_counter() - t0
+        assert want == rc[:m].cpu().tolist(), "text: GPU rows differ from the CPU reference"
+        out["cpu_baseline"] = {"value": len(text) / dt / 1e9, "unit": "GB/s", "cores": 1,
+                               "kind": "reference" if which == "ref" else "port",
+                               "sample": f"first {m} lines, one exec per line through the C API from Python "
+                                         f"(a parity check more than a timing)"}
+    return out
+
+
 def c5_shard(h, total, first, count):
     """bytes [first, first+count) of "abccc" x N + "aaabbccb" (bench/gen-data.pl:9 scaled to `total`)"""
     torch = h.torch
@@ -635,7 +703,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--config", default="all", choices=["all", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--config", default="all", choices=["all", "c2", "c3", "c4", "c5", "text"])
     ap.add_argument("--variant", type=int, default=int(os.environ.get("SRE_VARIANT", "0")))
     ap.add_argument("--lines", type=int, default=NLINES)
     ap.add_argument("--c4-lines", type=int, default=C4_TOTAL_LINES)
@@ -653,13 +721,18 @@ def main():
     few = max(3, min(steps, 20))        # the heavier configs: fewer steps, same rules
     extra = {}
     out = None
-    if args.config in ("all", "c2", "c3"):
-        out, dev, host = bench_c2(h, steps if args.config != "c3" else few, warmup)
+    if args.config in ("all", "c2", "c3", "text"):
+        out, dev, host = bench_c2(h, steps if args.config in ("all", "c2") else few, warmup)
         if args.config == "c3" or (args.config == "all" and not args.no_extras):
             try:
                 extra["c3"] = bench_c3(h, few, warmup, dev, host)
             except Exception as e:
                 extra["c3"] = {"error": repr(e)}
+        if args.config == "text" or (args.config == "all" and not args.no_extras):
+            try:
+                extra["text"] = bench_text(h, few, warmup, dev)
+            except Exception as e:
+                extra["text"] = {"error": repr(e)}
         del dev, host
         h.torch.cuda.empty_cache()
     if args.config == "c4" or (args.config == "all" and not args.no_extras):
@@ -675,7 +748,7 @@ def main():
             extra["c5"] = {"error": repr(e)}
     h.sampler.stop_flag = True
     h.sampler.join()
-    if args.config in ("c3", "c4", "c5") and "error" not in extra[args.config]:
+    if args.config in ("c3", "c4", "c5", "text") and "error" not in extra[args.config]:
         # one config as the headline (profiling runs)
         head = extra.pop(args.config)
         base = {"n_gpus": h.world, "warmup": warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "u8",

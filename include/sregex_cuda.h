@@ -199,6 +199,23 @@ SRE_API int sre_cuda_pike_exec_lines_host(sre_cuda_program_t *cp,
 SRE_API int sre_cuda_index_lines(const uint8_t *dev_buf, size_t len,
     int64_t *dev_offsets, size_t max_lines, size_t *nlines, void *stream);
 
+/*
+ * grep: the Thompson verdict of EVERY line of a '\n'-delimited device buffer in one
+ * pass over the text -- sre_vm_thompson_exec(ctx, line, len, eof=1) with a fresh
+ * ctx per line, without a line index made beforehand.  dev_rc[i] = SRE_OK or
+ * SRE_DECLINED for line i < max_lines; dev_offsets (may be NULL; room for
+ * max_lines + 1) receives what sre_cuda_index_lines would: line i =
+ * [dev_offsets[i], dev_offsets[i+1]) with its terminator, a last line without
+ * '\n' ends at len.  *nlines = lines found (may exceed max_lines: then only the
+ * first max_lines rows are written).  Programs whose DFA has a byte table of at
+ * most 128 states take the one-pass kernel (dev_buf 16-byte aligned); the others
+ * go through sre_cuda_index_lines + sre_cuda_thompson_exec_ragged.  Synchronises
+ * the stream.
+ */
+SRE_API int sre_cuda_thompson_exec_text(sre_cuda_program_t *cp, const uint8_t *dev_buf,
+    size_t len, int64_t *dev_offsets, int32_t *dev_rc, size_t max_lines, size_t *nlines,
+    void *stream);
+
 /* Tuning / introspection */
 /* Pike tier sre_cuda_pike_exec_lines may use for this program (tests): 0 = best
  * available (default): the determinised Pike VM when the program has one, else

@@ -175,7 +175,8 @@ int upload(sre_cuda_program_t *cp)
     const sre_nfa_t &n = cp->low.nfa;
     blob_t b;
     size_t o_t256 = 0, o_tcls = 0, o_dcls = 0, o_fin = 0, o_h256 = 0, o_hcls = 0, o_hmap = 0;
-    size_t o_itrans = 0, o_icand = 0, o_incand = 0;
+    size_t o_itrans = 0, o_icand = 0, o_incand = 0, o_x256 = 0;
+    bool has_x256 = false;
 
     cp->has_dfa = cp->low.has_dfa;
     if (cp->has_dfa) {
@@ -189,6 +190,23 @@ int upload(sre_cuda_program_t *cp)
         if (!d.hcls.empty()) {
             o_hcls = b.add(d.hcls.data(), d.hcls.size() * 2);
             o_hmap = b.add(d.hclsmap, 256);
+        }
+        if (!d.t256.empty() && d.nstates <= 128) {
+            /* text table (kernels/sre_text.cu): '\n' ends a line -- the verdict of the line (the
+             * EOF step after its terminator) rides in bit 7 and the next line starts afresh */
+            std::vector<uint8_t> x256((size_t) 256 * 256, 0);
+            for (uint32_t st = 0; st < d.nstates; st++) {
+                for (unsigned bv = 0; bv < 256; bv++) {
+                    uint8_t e = d.t256[(size_t) st * 256 + bv];
+                    if (bv == '\n') {
+                        e = (uint8_t) (d.start | ((e == d.acc || d.fin[e]) ? 0x80u : 0u));
+                    }
+                    x256[(size_t) st * 256 + bv] = e;
+                    x256[(size_t) (st + 128) * 256 + bv] = e;
+                }
+            }
+            o_x256 = b.add(x256.data(), x256.size());
+            has_x256 = true;
         }
         o_tcls = b.add(d.trans.data(), d.trans.size() * 2);
         o_dcls = b.add(d.clsmap, 256);
@@ -378,6 +396,7 @@ int upload(sre_cuda_program_t *cp)
         cp->dfa.hcls = d.hcls.empty() ? nullptr : reinterpret_cast<const uint16_t *>(base + o_hcls);
         cp->dfa.hclsmap = d.hcls.empty() ? nullptr : base + o_hmap;
         cp->dfa.hncls = d.hncls;
+        cp->dfa.x256 = has_x256 ? base + o_x256 : nullptr;
         if (cp->has_image) {
             cp->img.nstates = cp->image.nstates;
             cp->img.nclasses = cp->image.nclasses;
@@ -787,6 +806,52 @@ sre_cuda_index_lines(const uint8_t *dev_buf, size_t len, int64_t *dev_offsets, s
     }
     *nlines = (size_t) found;
     return SRE_OK;
+}
+
+/* grep: see include/sregex_cuda.h */
+SRE_API int
+sre_cuda_thompson_exec_text(sre_cuda_program_t *cp, const uint8_t *dev_buf, size_t len, int64_t *dev_offsets,
+    int32_t *dev_rc, size_t max_lines, size_t *nlines, void *stream)
+{
+    if (cp == NULL || nlines == NULL || (dev_buf == NULL && len != 0) || (dev_rc == NULL && max_lines != 0)) {
+        return fail("NULL program, buffer, rc or nlines");
+    }
+    cudaStream_t st = as_stream(stream);
+    int launches = 0;
+    unsigned long long found = 0;
+    if (cp->has_dfa && cp->dfa.x256 != nullptr && (reinterpret_cast<uintptr_t>(dev_buf) & 15) == 0) {
+        /* one pass: pieces through the TMA pipeline, line structure folded into the table */
+        scratch_t ws;
+        CUDA_TRY(ws.alloc(sre_text_workspace_bytes(len), st));
+        cudaError_t err = sre_launch_text(cp->dfa, dev_buf, len, dev_rc, dev_offsets, max_lines, ws.p, st, &launches);
+        count_launches(launches);
+        if (err == cudaSuccess) {
+            err = cudaMemcpyAsync(&found, ws.p + sre_text_count_offset(len), sizeof(found), cudaMemcpyDeviceToHost,
+                                  st);
+        }
+        if (err == cudaSuccess) {
+            err = cudaStreamSynchronize(st);
+        }
+        if (err != cudaSuccess) {
+            return fail("text kernels failed: %s", cudaGetErrorString(err));
+        }
+        *nlines = (size_t) found;
+        return SRE_OK;
+    }
+    /* larger automata / unaligned buffers: line index, then the ragged tier */
+    scratch_t own;
+    int64_t *offs = dev_offsets;
+    if (offs == NULL) {
+        CUDA_TRY(own.alloc((max_lines + 1) * sizeof(int64_t), st));
+        offs = reinterpret_cast<int64_t *>(own.p);
+    }
+    size_t n = 0;
+    if (sre_cuda_index_lines(dev_buf, len, offs, max_lines, &n, stream) != SRE_OK) {
+        return SRE_ERROR;
+    }
+    *nlines = n;
+    const size_t run = n < max_lines ? n : max_lines;
+    return run ? sre_cuda_thompson_exec_ragged(cp, dev_buf, offs, run, dev_rc, SRE_CUDA_ENGINE_AUTO, stream) : SRE_OK;
 }
 
 SRE_API void

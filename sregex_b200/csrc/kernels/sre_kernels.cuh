@@ -24,6 +24,8 @@ struct sre_dev_dfa_t {
     const uint8_t   *clsmap;    /* [256]                                      */
     const uint8_t   *fin;       /* [nstates]                                  */
     const uint8_t   *h256;      /* [256][256] next | restart flag, or NULL    */
+    const uint8_t   *x256;      /* [256][256] text table (sre_text.cu), or NULL: as t256, but '\n' leads to
+                                   start | 0x80 when the line that ends there matched */
     const uint16_t  *hcls;      /* [nstates][hncls] next | 0x8000 restart, or NULL */
     const uint8_t   *hclsmap;   /* [256]                                      */
     uint32_t         hncls;
@@ -234,6 +236,14 @@ cudaError_t sre_launch_pike_lines_all(const sre_dev_pike_t &pk, const uint8_t *b
 size_t sre_lines_workspace_bytes(size_t len);
 cudaError_t sre_launch_index_lines(const uint8_t *buf, size_t len, int64_t *offsets, size_t max_lines,
     unsigned long long *workspace, cudaStream_t stream, int *launches);
+
+/* every line of a '\n'-delimited buffer in one pass (sre_text.cu; needs dfa.x256, buf 16-byte
+ * aligned): rc[line], offsets[line + 1] (offsets may be NULL) for line < max_lines; the number
+ * of lines is left at workspace + sre_text_count_offset(len) (8 bytes) */
+size_t sre_text_workspace_bytes(size_t len);
+size_t sre_text_count_offset(size_t len);
+cudaError_t sre_launch_text(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t len, int32_t *rc,
+    int64_t *offsets, size_t max_lines, uint8_t *workspace, cudaStream_t stream, int *launches);
 
 /* Pike VM streaming step on one persistent context (classic API)             */
 /* skip: with a fresh context, begin at buf + skip as if the bytes before had been fed in an

@@ -1,0 +1,372 @@
+/*
+ * sre_text.cu -- Thompson matching of every line of a '\n'-delimited buffer in
+ * ONE pass over the text (what grep does with a log file).
+ *
+ * What it replaces: sre_vm_thompson_exec(ctx, line, len, eof=1) with a fresh
+ * context per line (sre_vm_thompson.c:63-270), for lines that are not laid out
+ * at a fixed pitch.  The older route -- sre_cuda_index_lines (two passes) and
+ * then the ragged thread-per-line kernel (uncoalesced) -- read the text three
+ * times at ~0.7 TB/s.  Here the text goes once through the TMA tile pipeline
+ * of k_dfa_lines_tma_early, cut into PIECE-byte pieces (one CUDA thread each):
+ *
+ *   k_text_pieces   The automaton table has the line structure folded in: on
+ *                   '\n' every state goes to the START state, with bit 7 set
+ *                   when the line that just ended matched (the verdict of the
+ *                   reference's EOF step after the terminator; rows r and r+128
+ *                   of the table are the same row).  So a thread simply runs its
+ *                   piece from the start state: whatever it computes before the
+ *                   first '\n' is thrown away (that line began in an earlier
+ *                   piece and belongs to the thread of that piece), every later
+ *                   line is exact, and the line that is still open at the end
+ *                   of the piece is finished by reading on past it.  Per input
+ *                   byte the loop is the PRMT + LDS.U8 of the line kernels plus
+ *                   a newline test per word; the states after each byte of a
+ *                   word stay in registers, so a word that holds a '\n' only
+ *                   adds the bookkeeping.  Line ends and verdicts go to a small
+ *                   per-piece staging area.
+ *   k_text_scan     exclusive scan of the per-piece line counts.
+ *   k_text_write    staging -> rc[line] and offsets[line + 1] (a piece with more
+ *                   lines than its staging holds is scanned again, serially).
+ *
+ * Line i = buf[offsets[i], offsets[i+1]) includes its terminator, as for
+ * sre_cuda_index_lines; a last line without '\n' ends at len.
+ */
+#include "sre_device_common.cuh"
+
+using namespace sre_dev;
+
+namespace {
+
+constexpr uint32_t PIECE = 4096;
+constexpr uint32_t CAP = 64;            /* staged lines per piece */
+
+/* bit 7 of every byte of x that equals '\n' (exact: no carry between bytes) */
+__device__ __forceinline__ uint32_t nl_mask(uint32_t x)
+{
+    const uint32_t y = x ^ 0x0a0a0a0au;
+    return ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y | 0x7f7f7f7fu);
+}
+
+struct text_out_t {
+    uint32_t       *stage;      /* [npieces][CAP] (end offset within the span << 1) | matched */
+    uint32_t       *count;      /* [npieces] lines that start in the piece                  */
+};
+
+/* does a line start at the first byte of `piece`? */
+__device__ __forceinline__ bool starts_line(const uint8_t *buf, size_t piece)
+{
+    return piece == 0 || __ldg(buf + piece * PIECE - 1) == '\n';
+}
+
+/*
+ * Serial form over the table in global memory (the tail piece, and pieces with
+ * more than CAP lines): the lines that START in [begin, end), each followed to
+ * its end (at most `len`).  emit(end offset relative to begin, matched).
+ */
+template <class Emit>
+__device__ __forceinline__ uint32_t serial_piece(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t len,
+                                                 size_t begin, size_t end, bool first_is_ours, Emit emit)
+{
+    const uint8_t *tx = dfa.x256;
+    uint32_t s = dfa.start, n = 0;
+    bool ours = first_is_ours;          /* the line that is open now started in [begin, end) */
+    size_t p = begin;
+    for (; p < len && (p < end || ours); p++) {
+        const uint32_t b = __ldg(buf + p);
+        s = __ldg(tx + ((s << 8) | b));
+        if (b == '\n') {
+            if (ours) {
+                emit((uint32_t) (p + 1 - begin), s >> 7, n);
+                n++;
+            }
+            ours = p + 1 < end;         /* where the next line starts */
+        }
+    }
+    if (p == len && ours && len > begin && __ldg(buf + len - 1) != '\n') {
+        /* a last line without terminator: the EOF step of the reference decides */
+        const uint32_t st = s & 0x7f;
+        emit((uint32_t) (len - begin), (st == dfa.acc || __ldg(dfa.fin + st)) ? 1u : 0u, n);
+        n++;
+    }
+    return n;
+}
+
+struct text_consumer_t {
+    const uint8_t      *tab;        /* x256 in shared memory */
+    sre_dev_dfa_t       dfa;
+    const uint8_t      *buf;
+    size_t              len, npieces;
+    text_out_t          out;
+    uint32_t            s, pos, cnt;
+    uint32_t           *stage;
+    bool                skip_first;
+
+    __device__ __forceinline__ void begin(size_t group)
+    {
+        const size_t piece = group * 32 + (threadIdx.x & 31);
+        s = dfa.start;
+        pos = 0;
+        cnt = 0;
+        skip_first = true;
+        stage = out.stage;
+        if (piece < npieces) {
+            skip_first = !starts_line(buf, piece);
+            stage = out.stage + piece * CAP;
+        }
+    }
+    __device__ __forceinline__ void record(uint32_t end_off, uint32_t matched)
+    {
+        if (skip_first) {
+            skip_first = false;         /* the line that ends here began in an earlier piece */
+            return;
+        }
+        if (cnt < CAP) {
+            stage[cnt] = (end_off << 1) | matched;
+        }
+        cnt++;
+    }
+    __device__ __forceinline__ void word(uint32_t w, uint32_t at)
+    {
+        const uint32_t a0 = tab[__byte_perm(w, s, 0x5540)];
+        const uint32_t a1 = tab[__byte_perm(w, a0, 0x5541)];
+        const uint32_t a2 = tab[__byte_perm(w, a1, 0x5542)];
+        const uint32_t a3 = tab[__byte_perm(w, a2, 0x5543)];
+        s = a3;
+        uint32_t m = nl_mask(w);
+        if (m) {
+            /* the states after each byte are still in registers: only bookkeeping here */
+            if (m & 0x00000080u) record(at + 1, a0 >> 7);
+            if (m & 0x00008000u) record(at + 2, a1 >> 7);
+            if (m & 0x00800000u) record(at + 3, a2 >> 7);
+            if (m & 0x80000000u) record(at + 4, a3 >> 7);
+        }
+    }
+    __device__ __forceinline__ void chunk(const uint4 &v)
+    {
+        word(v.x, pos);
+        word(v.y, pos + 4);
+        word(v.z, pos + 8);
+        word(v.w, pos + 12);
+        pos += 16;
+    }
+    __device__ __forceinline__ void byte(uint32_t b)
+    {
+        s = tab[(s << 8) | b];
+        pos++;
+        if (b == '\n') {
+            record(pos, s >> 7);
+        }
+    }
+    __device__ __forceinline__ void end(size_t group)
+    {
+        const size_t piece = group * 32 + (threadIdx.x & 31);
+        if (piece >= npieces) {
+            return;
+        }
+        /* the line still open at the end of the piece (it began here): read on */
+        size_t p = (piece + 1) * PIECE;
+        if (!skip_first && __ldg(buf + p - 1) != '\n') {
+            bool done = false;
+            for (; p < len && !done; p++) {
+                const uint32_t b = __ldg(buf + p);
+                s = tab[(s << 8) | b];
+                if (b == '\n') {
+                    record((uint32_t) (p + 1 - piece * PIECE), s >> 7);
+                    done = true;
+                }
+            }
+            if (!done) {
+                /* the buffer ended first: a last line without terminator (EOF step) */
+                const uint32_t st = s & 0x7f;
+                record((uint32_t) (len - piece * PIECE), (st == dfa.acc || __ldg(dfa.fin + st)) ? 1u : 0u);
+            }
+        }
+        out.count[piece] = cnt;
+    }
+};
+
+__global__ void __launch_bounds__(1024, 1)
+k_text_pieces(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ buf, size_t len,
+              size_t npieces, text_out_t out)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const dfa_smem_plan_t plan = dfa_smem_plan(256, 0, false);
+    load_table(smem, dfa.x256, 65536);
+    __syncthreads();
+
+    const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    text_consumer_t cons;
+    cons.tab = smem;
+    cons.dfa = dfa;
+    cons.buf = buf;
+    cons.len = len;
+    cons.npieces = npieces;
+    cons.out = out;
+    tile_pipeline_tma_early<1>(cons, &tmap, npieces, PIECE,
+                               smem + plan.stage_ofs + (size_t) warp * 32 * 128,
+                               reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES,
+                               (size_t) warp * gridDim.x + blockIdx.x, (size_t) gridDim.x * warps_per_block);
+}
+
+/* the ragged tail piece [nfull * PIECE, len): one thread, table from global memory */
+__global__ void k_text_tail(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, size_t piece,
+                            text_out_t out)
+{
+    uint32_t *stage = out.stage + piece * CAP;
+    out.count[piece] = serial_piece(dfa, buf, len, piece * PIECE, len, starts_line(buf, piece),
+                                    [&](uint32_t end_off, uint32_t matched, uint32_t k) {
+                                        if (k < CAP) {
+                                            stage[k] = (end_off << 1) | matched;
+                                        }
+                                    });
+}
+
+/* base[i] <- lines that start before piece i; base[n] <- all lines.  One block. */
+__global__ void __launch_bounds__(1024)
+k_text_scan(const uint32_t *__restrict__ count, unsigned long long *__restrict__ base, size_t n)
+{
+    __shared__ unsigned long long carry, sums[32];
+    if (threadIdx.x == 0) {
+        carry = 0;
+    }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (size_t first = 0; first < n; first += 1024) {
+        const size_t i = first + threadIdx.x;
+        const unsigned long long v = i < n ? count[i] : 0;
+        unsigned long long incl = v;
+#pragma unroll
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            const unsigned long long up = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) {
+                incl += up;
+            }
+        }
+        if (lane == 31) {
+            sums[warp] = incl;
+        }
+        __syncthreads();
+        unsigned long long before = 0, all = 0;
+        for (uint32_t w = 0; w < 32; w++) {
+            before += w < warp ? sums[w] : 0;
+            all += sums[w];
+        }
+        const unsigned long long c = carry;
+        if (i < n) {
+            base[i] = c + before + incl - v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            carry = c + all;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        base[n] = carry;
+    }
+}
+
+/* staging -> rc[] / offsets[]; one thread per piece */
+__global__ void __launch_bounds__(256)
+k_text_write(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, size_t npieces, text_out_t out,
+             const unsigned long long *__restrict__ base, int32_t *__restrict__ rc, int64_t *__restrict__ offsets,
+             size_t max_lines)
+{
+    const size_t piece = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (piece == 0 && offsets != nullptr) {
+        offsets[0] = 0;
+    }
+    if (piece >= npieces) {
+        return;
+    }
+    const size_t first = (size_t) base[piece], begin = piece * PIECE;
+    const uint32_t n = out.count[piece];
+    auto put = [&](uint32_t end_off, uint32_t matched, uint32_t k) {
+        const size_t line = first + k;
+        if (line < max_lines) {
+            rc[line] = matched ? SRE_K_OK : SRE_K_DECLINED;
+            if (offsets != nullptr) {
+                offsets[line + 1] = (int64_t) (begin + end_off);
+            }
+        }
+    };
+    if (n <= CAP) {
+        const uint32_t *stage = out.stage + piece * CAP;
+        for (uint32_t k = 0; k < n; k++) {
+            const uint32_t r = stage[k];
+            put(r >> 1, r & 1, k);
+        }
+    } else {
+        /* more lines than the staging holds: once more, serially, straight to the output */
+        const size_t end = begin + PIECE < len ? begin + PIECE : len;
+        serial_piece(dfa, buf, len, begin, end, starts_line(buf, piece), put);
+    }
+}
+
+}  // namespace
+
+size_t sre_text_workspace_bytes(size_t len)
+{
+    const size_t npieces = (len + PIECE - 1) / PIECE + 1;
+    return npieces * (CAP * 4 + 4 + 8) + 1024;
+}
+
+/* workspace: sre_text_workspace_bytes(len) bytes, 256-byte aligned; its first 8 bytes receive the
+ * number of lines */
+cudaError_t sre_launch_text(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t len, int32_t *rc,
+    int64_t *offsets, size_t max_lines, uint8_t *workspace, cudaStream_t stream, int *launches)
+{
+    if (dfa.x256 == nullptr || (reinterpret_cast<uintptr_t>(buf) & 15)) {
+        return cudaErrorInvalidValue;
+    }
+    const size_t nfull = len / PIECE, npieces = nfull + (len % PIECE ? 1 : 0);
+    unsigned long long *base = reinterpret_cast<unsigned long long *>(workspace);   /* [npieces + 1] */
+    uint8_t *p = workspace + ((npieces + 2) * 8 + 255) / 256 * 256;
+    text_out_t out;
+    out.count = reinterpret_cast<uint32_t *>(p);
+    p += (npieces * 4 + 255) / 256 * 256 + 256;
+    out.stage = reinterpret_cast<uint32_t *>(p);
+    cudaError_t err;
+    if (npieces == 0) {
+        if ((err = cudaMemsetAsync(workspace, 0, 8, stream)) != cudaSuccess) return err;
+        return offsets ? cudaMemsetAsync(offsets, 0, 8, stream) : cudaSuccess;
+    }
+    if (nfull) {
+        const dfa_smem_plan_t plan = dfa_smem_plan(256, 0, false);
+        const int warps = 32;
+        const size_t smem = plan.stage_ofs + (size_t) warps * 32 * 128;
+        CUtensorMap tmap;
+        if ((err = make_row_tensor_map(&tmap, buf, nfull, PIECE, 128)) != cudaSuccess) return err;
+        static bool attr_set = false;
+        if (!attr_set) {
+            err = cudaFuncSetAttribute(k_text_pieces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            if (err != cudaSuccess) return err;
+            attr_set = true;
+        }
+        const size_t ngroups = (nfull + 31) / 32;
+        size_t grid = (size_t) num_sms();
+        const size_t need = (ngroups + warps - 1) / warps;
+        if (grid > need) {
+            grid = need;
+        }
+        if (launches) ++*launches;
+        k_text_pieces<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, out);
+        if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    }
+    if (npieces > nfull) {
+        if (launches) ++*launches;
+        k_text_tail<<<1, 1, 0, stream>>>(dfa, buf, len, nfull, out);
+        if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    }
+    if (launches) *launches += 2;
+    k_text_scan<<<1, 1024, 0, stream>>>(out.count, base, npieces);
+    k_text_write<<<(unsigned) ((npieces + 255) / 256), 256, 0, stream>>>(dfa, buf, len, npieces, out, base, rc, offsets,
+                                                                       max_lines);
+    return cudaGetLastError();
+}
+
+/* where in the workspace the number of lines is left (8 bytes) */
+size_t sre_text_count_offset(size_t len)
+{
+    return (len / PIECE + (len % PIECE ? 1 : 0)) * 8;
+}

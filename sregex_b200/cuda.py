@@ -60,6 +60,7 @@ def lib():
             "sre_cuda_pike_exec_lines_host": (C.c_int, [vp, vp, sz, sz, sz, C.c_int, i32p, i64p, sz]),
             "sre_cuda_program_set_pike_tier": (None, [vp, C.c_int]),
             "sre_cuda_program_last_pike_tier": (C.c_int, [vp]),
+            "sre_cuda_thompson_exec_text": (C.c_int, [vp, vp, sz, i64p, i32p, sz, C.POINTER(C.c_size_t), vp]),
             "sre_cuda_index_lines": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                                C.POINTER(C.c_size_t), C.c_void_p]),
             "sre_cuda_launch_count": (C.c_long, [C.c_int]),
@@ -170,6 +171,24 @@ class CudaProgram:
         if not h:
             raise SreCudaError(self.lib.L.sre_cuda_last_error().decode())
         return StreamScan(self, h, fn.raw, (buf, halo))
+
+    def thompson_text(self, buf: torch.Tensor, length: int | None = None, max_lines: int | None = None,
+                      want_offsets: bool = True):
+        """grep: the verdict of every line of a '\\n'-delimited device buffer in one pass
+        -> (rc int32[nlines], offsets int64[nlines + 1] or None)"""
+        length = buf.numel() if length is None else length
+        cap = max_lines if max_lines is not None else max(1024, length // 48)
+        while True:
+            rc = torch.empty(cap, dtype=torch.int32, device=buf.device)
+            off = torch.empty(cap + 1, dtype=torch.int64, device=buf.device) if want_offsets else None
+            n = C.c_size_t(0)
+            _check(self.lib.L.sre_cuda_thompson_exec_text(self.cp, buf.data_ptr(), length,
+                                                          off.data_ptr() if off is not None else None,
+                                                          rc.data_ptr(), cap, C.byref(n), _stream_ptr()))
+            if n.value <= cap or max_lines is not None:
+                k = min(n.value, cap)
+                return rc[:k], (off[: k + 1] if off is not None else None)
+            cap = n.value
 
     def dfa_fin(self, state: int) -> bool:
         """does the EOF step of the lowered DFA see a match in `state`"""

@@ -800,3 +800,71 @@ def test_one_program_from_two_threads_and_two_streams(cu):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+def test_text_grep_one_pass_vs_oracle(cu):
+    """sre_cuda_thompson_exec_text: the verdict of every line of a '\\n'-delimited buffer in one pass
+    (pieces through the TMA pipeline, line structure folded into the table) against the oracle run
+    line by line -- ragged log lines, empty lines, lines longer than a piece, pieces with more lines
+    than the staging holds, a last line with and without terminator, anchors at line ends"""
+    rs = np.random.RandomState(123)
+    oracle = capi.load("oracle")
+    src = corpus.log_lines(6000, 1024).numpy()
+
+    def build(kind, trailing_newline):
+        parts = []
+        for i in range(6000):
+            if kind == "log":
+                n = int(rs.randint(0, 400))
+            elif kind == "tiny":
+                n = int(rs.randint(0, 12))                  # > 64 lines per 4 KB piece
+            else:
+                n = int(rs.choice([0, 30, 200, 5000, 9000]))  # lines that span pieces
+            row = src[i]
+            body = bytes(np.resize(row[1024 - 60 - min(n, 900): 1024 - 60], n)) if n else b""
+            parts.append(body.replace(b"\n", b" ") + b"\n")
+        data = b"".join(parts)
+        if not trailing_newline:
+            data += b'GET /x/1 HTTP/1.1" 503 '
+        return data
+
+    regexes = [corpus.C2_REGEX, corpus.C3_REGEX, rb"5\d\d $", rb"^\w+[./-]", rb"^$", rb"x*"]
+    for kind in ("log", "tiny", "long"):
+        for trailing in (True, False):
+            data = build(kind, trailing)
+            host = np.frombuffer(data, dtype=np.uint8)
+            want_off = np.concatenate([[0], np.flatnonzero(host == 10) + 1]).astype(np.int64)
+            if not trailing:
+                want_off = np.concatenate([want_off, [len(data)]])
+            dev = torch.from_numpy(np.concatenate([host, np.zeros(16, np.uint8)])).cuda()
+            for rx in regexes if kind == "log" else regexes[:3]:
+                prog = cu.CudaProgram(rx)
+                assert prog.info.dfa_states and prog.info.dfa_states <= 128
+                rc, off = prog.thompson_text(dev, len(data))
+                assert np.array_equal(off.cpu().numpy(), want_off), (kind, trailing, rx)
+                po = oracle.compile(rx, 0)
+                n = len(want_off) - 1
+                step = 1 if kind != "tiny" else 3
+                idx = list(range(0, n, step))
+                want = np.array([oracle.thompson(po, data[want_off[i]:want_off[i + 1]]) for i in idx])
+                assert np.array_equal(rc.cpu().numpy()[idx], want), (kind, trailing, rx)
+                po.close()
+                # too small an output: the count is still reported, the prefix is right
+                rc2, off2 = prog.thompson_text(dev, len(data), max_lines=100)
+                assert torch.equal(rc2, rc[:100]) and torch.equal(off2, off[:101])
+    # empty buffer, and a buffer that is a single unterminated line
+    prog = cu.CudaProgram(corpus.C2_REGEX)
+    rc, off = prog.thompson_text(torch.zeros(16, dtype=torch.uint8, device="cuda"), 0)
+    assert rc.numel() == 0 and off.cpu().tolist() == [0]
+    one = b'zz HTTP/1.1" 503 '
+    rc, off = prog.thompson_text(torch.frombuffer(bytearray(one) + bytearray(16), dtype=torch.uint8).cuda(), len(one))
+    assert rc.cpu().tolist() == [0] and off.cpu().tolist() == [0, len(one)]
+    # a larger automaton (64 patterns, 2107 states) takes the index + ragged route: same answers
+    pats = corpus.multi_pattern_set(64)
+    data = build("log", True)
+    host = np.frombuffer(data, dtype=np.uint8)
+    dev = torch.from_numpy(np.concatenate([host, np.zeros(16, np.uint8)])).cuda()
+    progm = cu.CudaProgram(pats)
+    rc, off = progm.thompson_text(dev, len(data))
+    want = progm.thompson_ragged(dev, off)
+    assert torch.equal(rc, want) and 0 < int((rc == 0).sum()) < rc.numel()
