@@ -175,8 +175,8 @@ int upload(sre_cuda_program_t *cp)
     const sre_nfa_t &n = cp->low.nfa;
     blob_t b;
     size_t o_t256 = 0, o_tcls = 0, o_dcls = 0, o_fin = 0, o_h256 = 0, o_hcls = 0, o_hmap = 0;
-    size_t o_itrans = 0, o_icand = 0, o_incand = 0, o_x256 = 0;
-    bool has_x256 = false;
+    size_t o_itrans = 0, o_icand = 0, o_incand = 0, o_x256 = 0, o_x256m = 0;
+    bool has_x256 = false, has_x256m = false;
 
     cp->has_dfa = cp->low.has_dfa;
     if (cp->has_dfa) {
@@ -207,6 +207,23 @@ int upload(sre_cuda_program_t *cp)
             }
             o_x256 = b.add(x256.data(), x256.size());
             has_x256 = true;
+            if (d.nstates <= 64) {
+                /* ... with the newline marked in bit 6 (rows r, r+64, r+128, r+192 alike) */
+                std::vector<uint8_t> xm((size_t) 256 * 256, 0);
+                for (uint32_t st = 0; st < d.nstates; st++) {
+                    for (unsigned bv = 0; bv < 256; bv++) {
+                        uint8_t e = x256[(size_t) st * 256 + bv];
+                        if (bv == '\n') {
+                            e |= 0x40;
+                        }
+                        for (uint32_t k = 0; k < 4; k++) {
+                            xm[(size_t) (st + 64 * k) * 256 + bv] = e;
+                        }
+                    }
+                }
+                o_x256m = b.add(xm.data(), xm.size());
+                has_x256m = true;
+            }
         }
         o_tcls = b.add(d.trans.data(), d.trans.size() * 2);
         o_dcls = b.add(d.clsmap, 256);
@@ -397,6 +414,7 @@ int upload(sre_cuda_program_t *cp)
         cp->dfa.hclsmap = d.hcls.empty() ? nullptr : base + o_hmap;
         cp->dfa.hncls = d.hncls;
         cp->dfa.x256 = has_x256 ? base + o_x256 : nullptr;
+        cp->dfa.x256m = has_x256m ? base + o_x256m : nullptr;
         if (cp->has_image) {
             cp->img.nstates = cp->image.nstates;
             cp->img.nclasses = cp->image.nclasses;

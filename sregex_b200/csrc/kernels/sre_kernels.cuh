@@ -26,6 +26,7 @@ struct sre_dev_dfa_t {
     const uint8_t   *h256;      /* [256][256] next | restart flag, or NULL    */
     const uint8_t   *x256;      /* [256][256] text table (sre_text.cu), or NULL: as t256, but '\n' leads to
                                    start | 0x80 when the line that ends there matched */
+    const uint8_t   *x256m;     /* the same for <= 64 states, '\n' also sets bit 6 (rows r + 64k alike), or NULL */
     const uint16_t  *hcls;      /* [nstates][hncls] next | 0x8000 restart, or NULL */
     const uint8_t   *hclsmap;   /* [256]                                      */
     uint32_t         hncls;

@@ -91,36 +91,36 @@ __device__ __forceinline__ uint32_t serial_piece(const sre_dev_dfa_t &dfa, const
     return n;
 }
 
+/* MARK: the automaton has at most 64 states, and the table marks "this byte was a '\n'" in bit 6
+ * of the state (rows r, r+64, r+128, r+192 are the same row): one OR + one test per word
+ * replaces the newline search */
+template <bool MARK>
 struct text_consumer_t {
     const uint8_t      *tab;        /* x256 in shared memory */
     sre_dev_dfa_t       dfa;
     const uint8_t      *buf;
     size_t              len, npieces;
     text_out_t          out;
-    uint32_t            s, pos, cnt;
+    uint32_t            s, pos;
+    uint32_t            cnt;        /* lines recorded; 0xffffffff: the next line end is not ours */
     uint32_t           *stage;
-    bool                skip_first;
 
     __device__ __forceinline__ void begin(size_t group)
     {
         const size_t piece = group * 32 + (threadIdx.x & 31);
         s = dfa.start;
         pos = 0;
-        cnt = 0;
-        skip_first = true;
+        cnt = 0xffffffffu;
         stage = out.stage;
         if (piece < npieces) {
-            skip_first = !starts_line(buf, piece);
+            /* the first line end seen belongs to an earlier piece unless a line starts here */
+            cnt = starts_line(buf, piece) ? 0u : 0xffffffffu;
             stage = out.stage + piece * CAP;
         }
     }
     __device__ __forceinline__ void record(uint32_t end_off, uint32_t matched)
     {
-        if (skip_first) {
-            skip_first = false;         /* the line that ends here began in an earlier piece */
-            return;
-        }
-        if (cnt < CAP) {
+        if (cnt < CAP) {            /* (not for 0xffffffff: that line began in an earlier piece) */
             stage[cnt] = (end_off << 1) | matched;
         }
         cnt++;
@@ -132,13 +132,23 @@ struct text_consumer_t {
         const uint32_t a2 = tab[__byte_perm(w, a1, 0x5542)];
         const uint32_t a3 = tab[__byte_perm(w, a2, 0x5543)];
         s = a3;
-        uint32_t m = nl_mask(w);
-        if (m) {
-            /* the states after each byte are still in registers: only bookkeeping here */
-            if (m & 0x00000080u) record(at + 1, a0 >> 7);
-            if (m & 0x00008000u) record(at + 2, a1 >> 7);
-            if (m & 0x00800000u) record(at + 3, a2 >> 7);
-            if (m & 0x80000000u) record(at + 4, a3 >> 7);
+        /* the states after each byte are still in registers: a word that holds a '\n' only adds
+         * the bookkeeping */
+        if (MARK) {
+            if ((a0 | a1 | a2 | a3) & 0x40u) {
+                if (a0 & 0x40u) record(at + 1, a0 >> 7);
+                if (a1 & 0x40u) record(at + 2, a1 >> 7);
+                if (a2 & 0x40u) record(at + 3, a2 >> 7);
+                if (a3 & 0x40u) record(at + 4, a3 >> 7);
+            }
+        } else {
+            const uint32_t m = nl_mask(w);
+            if (m) {
+                if (m & 0x00000080u) record(at + 1, a0 >> 7);
+                if (m & 0x00008000u) record(at + 2, a1 >> 7);
+                if (m & 0x00800000u) record(at + 3, a2 >> 7);
+                if (m & 0x80000000u) record(at + 4, a3 >> 7);
+            }
         }
     }
     __device__ __forceinline__ void chunk(const uint4 &v)
@@ -163,39 +173,59 @@ struct text_consumer_t {
         if (piece >= npieces) {
             return;
         }
-        /* the line still open at the end of the piece (it began here): read on */
-        size_t p = (piece + 1) * PIECE;
-        if (!skip_first && __ldg(buf + p - 1) != '\n') {
+        /* the line still open at the end of the piece (if it began here): read on, 16 aligned
+         * bytes at a time (the piece ends on a 16-byte boundary), the next block requested
+         * before this one is walked */
+        const size_t base = piece * PIECE;
+        size_t p = base + PIECE;
+        if (cnt != 0xffffffffu && __ldg(buf + p - 1) != '\n') {
             bool done = false;
-            for (; p < len && !done; p++) {
-                const uint32_t b = __ldg(buf + p);
-                s = tab[(s << 8) | b];
-                if (b == '\n') {
-                    record((uint32_t) (p + 1 - piece * PIECE), s >> 7);
-                    done = true;
+            uint4 vnext = make_uint4(0, 0, 0, 0);
+            if (p < len) {
+                vnext = __ldg(reinterpret_cast<const uint4 *>(buf + p));
+            }
+            while (p < len && !done) {
+                const uint4 v = vnext;
+                if (p + 16 < len) {
+                    vnext = __ldg(reinterpret_cast<const uint4 *>(buf + p + 16));
                 }
+                const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+                const uint32_t n = len - p < 16 ? (uint32_t) (len - p) : 16u;
+#pragma unroll
+                for (uint32_t q = 0; q < 16; q++) {
+                    if (q < n && !done) {
+                        const uint32_t b = (w[q >> 2] >> ((q & 3) * 8)) & 0xff;
+                        s = tab[(s << 8) | b];
+                        if (b == '\n') {
+                            record((uint32_t) (p + q + 1 - base), s >> 7);
+                            done = true;
+                        }
+                    }
+                }
+                p += 16;
             }
             if (!done) {
                 /* the buffer ended first: a last line without terminator (EOF step) */
-                const uint32_t st = s & 0x7f;
-                record((uint32_t) (len - piece * PIECE), (st == dfa.acc || __ldg(dfa.fin + st)) ? 1u : 0u);
+                const uint32_t st = s & (MARK ? 0x3fu : 0x7fu);
+                record((uint32_t) (len - base), (st == dfa.acc || __ldg(dfa.fin + st)) ? 1u : 0u);
             }
         }
-        out.count[piece] = cnt;
+        out.count[piece] = cnt == 0xffffffffu ? 0u : cnt;
     }
 };
 
+template <bool MARK>
 __global__ void __launch_bounds__(1024, 1)
 k_text_pieces(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ buf, size_t len,
               size_t npieces, text_out_t out)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const dfa_smem_plan_t plan = dfa_smem_plan(256, 0, false);
-    load_table(smem, dfa.x256, 65536);
+    load_table(smem, MARK ? dfa.x256m : dfa.x256, 65536);
     __syncthreads();
 
     const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
-    text_consumer_t cons;
+    text_consumer_t<MARK> cons;
     cons.tab = smem;
     cons.dfa = dfa;
     cons.buf = buf;
@@ -221,19 +251,62 @@ __global__ void k_text_tail(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, 
                                     });
 }
 
-/* base[i] <- lines that start before piece i; base[n] <- all lines.  One block. */
-__global__ void __launch_bounds__(1024)
-k_text_scan(const uint32_t *__restrict__ count, unsigned long long *__restrict__ base, size_t n)
+constexpr uint32_t WB = 1024;       /* pieces per block of the scan / write kernels */
+
+/* block-wide exclusive prefix sum over WB threads; *total = the block's sum */
+__device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t *total)
 {
-    __shared__ unsigned long long carry, sums[32];
+    __shared__ uint32_t warp_sums[WB / 32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) {
+            incl += up;
+        }
+    }
+    if (lane == 31) {
+        warp_sums[warp] = incl;
+    }
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < WB / 32; w++) {
+        const uint32_t x = warp_sums[w];
+        before += w < warp ? x : 0;
+        all += x;
+    }
+    __syncthreads();
+    *total = all;
+    return before + incl - v;
+}
+
+/* sums[b] <- lines that start in the WB pieces of block b */
+__global__ void __launch_bounds__(WB)
+k_text_sums(const uint32_t *__restrict__ count, size_t n, unsigned long long *__restrict__ sums)
+{
+    const size_t i = (size_t) blockIdx.x * WB + threadIdx.x;
+    uint32_t total;
+    block_exclusive(i < n ? count[i] : 0u, &total);
+    if (threadIdx.x == 0) {
+        sums[blockIdx.x] = total;
+    }
+}
+
+/* sums[b] <- lines before block b; sums[nb] <- all lines.  One block (nb = pieces / 1024). */
+__global__ void __launch_bounds__(1024)
+k_text_scan(unsigned long long *__restrict__ sums, size_t nb)
+{
+    __shared__ unsigned long long carry, part[32];
     if (threadIdx.x == 0) {
         carry = 0;
     }
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (size_t first = 0; first < n; first += 1024) {
+    for (size_t first = 0; first < nb; first += 1024) {
         const size_t i = first + threadIdx.x;
-        const unsigned long long v = i < n ? count[i] : 0;
+        const unsigned long long v = i < nb ? sums[i] : 0;
         unsigned long long incl = v;
 #pragma unroll
         for (uint32_t d = 1; d < 32; d <<= 1) {
@@ -243,17 +316,17 @@ k_text_scan(const uint32_t *__restrict__ count, unsigned long long *__restrict__
             }
         }
         if (lane == 31) {
-            sums[warp] = incl;
+            part[warp] = incl;
         }
         __syncthreads();
         unsigned long long before = 0, all = 0;
         for (uint32_t w = 0; w < 32; w++) {
-            before += w < warp ? sums[w] : 0;
-            all += sums[w];
+            before += w < warp ? part[w] : 0;
+            all += part[w];
         }
         const unsigned long long c = carry;
-        if (i < n) {
-            base[i] = c + before + incl - v;
+        if (i < nb) {
+            sums[i] = c + before + incl - v;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -262,44 +335,75 @@ k_text_scan(const uint32_t *__restrict__ count, unsigned long long *__restrict__
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        base[n] = carry;
+        sums[nb] = carry;
     }
 }
 
-/* staging -> rc[] / offsets[]; one thread per piece */
-__global__ void __launch_bounds__(256)
+/*
+ * staging -> rc[] / offsets[].  A block takes WB pieces (one per thread for the
+ * prefix sums); then every warp writes the lines of its 32 pieces together: lane
+ * after lane takes the next line of the warp's run (the piece it belongs to found
+ * by a search over the 32 prefix sums), so that consecutive lanes write
+ * consecutive rows.
+ */
+__global__ void __launch_bounds__(WB)
 k_text_write(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, size_t npieces, text_out_t out,
-             const unsigned long long *__restrict__ base, int32_t *__restrict__ rc, int64_t *__restrict__ offsets,
+             const unsigned long long *__restrict__ sums, int32_t *__restrict__ rc, int64_t *__restrict__ offsets,
              size_t max_lines)
 {
-    const size_t piece = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint32_t pre[WB];            /* lines of the block before each piece */
+    const size_t piece = (size_t) blockIdx.x * WB + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, wfirst = threadIdx.x & ~31u;
     if (piece == 0 && offsets != nullptr) {
         offsets[0] = 0;
     }
-    if (piece >= npieces) {
-        return;
-    }
-    const size_t first = (size_t) base[piece], begin = piece * PIECE;
-    const uint32_t n = out.count[piece];
-    auto put = [&](uint32_t end_off, uint32_t matched, uint32_t k) {
-        const size_t line = first + k;
-        if (line < max_lines) {
-            rc[line] = matched ? SRE_K_OK : SRE_K_DECLINED;
-            if (offsets != nullptr) {
-                offsets[line + 1] = (int64_t) (begin + end_off);
+    const uint32_t n = piece < npieces ? out.count[piece] : 0u;
+    uint32_t total;
+    const uint32_t before = block_exclusive(n, &total);
+    pre[threadIdx.x] = before;
+    __syncwarp();
+    const size_t block_first = (size_t) sums[blockIdx.x];
+    /* the warp's run of lines: [run0, run0 + run) of the block */
+    const uint32_t run0 = __shfl_sync(FULL, before, 0);
+    const uint32_t run = __shfl_sync(FULL, before + n, 31) - run0;
+    const bool over = n > CAP;
+    const bool any_over = __any_sync(FULL, over);
+    for (uint32_t f = lane; f < run; f += 32) {
+        /* the piece of the warp that line run0 + f belongs to: last one with pre <= run0 + f */
+        uint32_t lo = 0, hi = 31;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (pre[wfirst + mid] <= run0 + f) {
+                lo = mid;
+            } else {
+                hi = mid - 1;
             }
         }
-    };
-    if (n <= CAP) {
-        const uint32_t *stage = out.stage + piece * CAP;
-        for (uint32_t k = 0; k < n; k++) {
-            const uint32_t r = stage[k];
-            put(r >> 1, r & 1, k);
+        const uint32_t k = run0 + f - pre[wfirst + lo];
+        const size_t pc = (size_t) blockIdx.x * WB + wfirst + lo, line = block_first + run0 + f;
+        if (k < CAP && line < max_lines) {
+            /* (rows of a piece with more than CAP lines are written again below) */
+            const uint32_t r = out.stage[pc * CAP + k];
+            rc[line] = (r & 1) ? SRE_K_OK : SRE_K_DECLINED;
+            if (offsets != nullptr) {
+                offsets[line + 1] = (int64_t) (pc * PIECE + (r >> 1));
+            }
         }
-    } else {
+    }
+    if (any_over && over) {
         /* more lines than the staging holds: once more, serially, straight to the output */
-        const size_t end = begin + PIECE < len ? begin + PIECE : len;
-        serial_piece(dfa, buf, len, begin, end, starts_line(buf, piece), put);
+        const size_t begin = piece * PIECE, end = begin + PIECE < len ? begin + PIECE : len;
+        const size_t first = block_first + before;
+        serial_piece(dfa, buf, len, begin, end, starts_line(buf, piece),
+                     [&](uint32_t end_off, uint32_t matched, uint32_t k) {
+                         const size_t line = first + k;
+                         if (line < max_lines) {
+                             rc[line] = matched ? SRE_K_OK : SRE_K_DECLINED;
+                             if (offsets != nullptr) {
+                                 offsets[line + 1] = (int64_t) (begin + end_off);
+                             }
+                         }
+                     });
     }
 }
 
@@ -307,21 +411,27 @@ k_text_write(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, siz
 
 size_t sre_text_workspace_bytes(size_t len)
 {
-    const size_t npieces = (len + PIECE - 1) / PIECE + 1;
-    return npieces * (CAP * 4 + 4 + 8) + 1024;
+    const size_t npieces = (len + PIECE - 1) / PIECE + 1, nb = (npieces + WB - 1) / WB;
+    return (nb + 2) * 8 + npieces * (CAP * 4 + 4) + 1024;
 }
 
-/* workspace: sre_text_workspace_bytes(len) bytes, 256-byte aligned; its first 8 bytes receive the
- * number of lines */
+/* where in the workspace the number of lines is left (8 bytes) */
+size_t sre_text_count_offset(size_t len)
+{
+    const size_t npieces = len / PIECE + (len % PIECE ? 1 : 0);
+    return (npieces + WB - 1) / WB * 8;
+}
+
+/* workspace: sre_text_workspace_bytes(len) bytes, 256-byte aligned */
 cudaError_t sre_launch_text(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t len, int32_t *rc,
     int64_t *offsets, size_t max_lines, uint8_t *workspace, cudaStream_t stream, int *launches)
 {
     if (dfa.x256 == nullptr || (reinterpret_cast<uintptr_t>(buf) & 15)) {
         return cudaErrorInvalidValue;
     }
-    const size_t nfull = len / PIECE, npieces = nfull + (len % PIECE ? 1 : 0);
-    unsigned long long *base = reinterpret_cast<unsigned long long *>(workspace);   /* [npieces + 1] */
-    uint8_t *p = workspace + ((npieces + 2) * 8 + 255) / 256 * 256;
+    const size_t nfull = len / PIECE, npieces = nfull + (len % PIECE ? 1 : 0), nb = (npieces + WB - 1) / WB;
+    unsigned long long *sums = reinterpret_cast<unsigned long long *>(workspace);   /* [nb + 1] */
+    uint8_t *p = workspace + ((nb + 2) * 8 + 255) / 256 * 256;
     text_out_t out;
     out.count = reinterpret_cast<uint32_t *>(p);
     p += (npieces * 4 + 255) / 256 * 256 + 256;
@@ -339,7 +449,11 @@ cudaError_t sre_launch_text(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t
         if ((err = make_row_tensor_map(&tmap, buf, nfull, PIECE, 128)) != cudaSuccess) return err;
         static bool attr_set = false;
         if (!attr_set) {
-            err = cudaFuncSetAttribute(k_text_pieces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            err = cudaFuncSetAttribute(k_text_pieces<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            if (err == cudaSuccess) {
+                err = cudaFuncSetAttribute(k_text_pieces<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int) smem);
+            }
             if (err != cudaSuccess) return err;
             attr_set = true;
         }
@@ -350,7 +464,11 @@ cudaError_t sre_launch_text(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t
             grid = need;
         }
         if (launches) ++*launches;
-        k_text_pieces<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, out);
+        if (dfa.x256m != nullptr) {
+            k_text_pieces<true><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, out);
+        } else {
+            k_text_pieces<false><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, out);
+        }
         if ((err = cudaGetLastError()) != cudaSuccess) return err;
     }
     if (npieces > nfull) {
@@ -358,15 +476,9 @@ cudaError_t sre_launch_text(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t
         k_text_tail<<<1, 1, 0, stream>>>(dfa, buf, len, nfull, out);
         if ((err = cudaGetLastError()) != cudaSuccess) return err;
     }
-    if (launches) *launches += 2;
-    k_text_scan<<<1, 1024, 0, stream>>>(out.count, base, npieces);
-    k_text_write<<<(unsigned) ((npieces + 255) / 256), 256, 0, stream>>>(dfa, buf, len, npieces, out, base, rc, offsets,
-                                                                       max_lines);
+    if (launches) *launches += 3;
+    k_text_sums<<<(unsigned) nb, WB, 0, stream>>>(out.count, npieces, sums);
+    k_text_scan<<<1, 1024, 0, stream>>>(sums, nb);
+    k_text_write<<<(unsigned) nb, WB, 0, stream>>>(dfa, buf, len, npieces, out, sums, rc, offsets, max_lines);
     return cudaGetLastError();
-}
-
-/* where in the workspace the number of lines is left (8 bytes) */
-size_t sre_text_count_offset(size_t len)
-{
-    return (len / PIECE + (len % PIECE ? 1 : 0)) * 8;
 }
