@@ -15,6 +15,8 @@ host buffers, the reference's CPU path beside it), at every N:
       chunk-parallel scan; sharded: halo + record all-gather over NCCL     (strong)
   text  Thompson boolean per line of newline-delimited text (ragged lines,
       no line index beforehand), 1 GiB per GPU, one pass                   (weak)
+  nfa   a regex whose subset construction blows up: the bit-parallel NFA tier
+      over the C2 lines                                                    (weak)
 
   python bench.py --gpus N --steps K --warmup W            (our arm)
   python bench.py --impl reference ...                      (reference CPU arm)
@@ -48,6 +50,7 @@ METRICS = {
     "c4": "input GB/s scanned (64-pattern set, matched id per line, 8 GiB corpus sharded over the GPUs)",
     "c5": "input GB/s scanned (one 32 GiB stream, 64 KB chunks with SRE_AGAIN carry, sharded over the GPUs)",
     "text": "input GB/s scanned (Thompson boolean per line of newline-delimited text, 1 GiB per GPU, one pass)",
+    "nfa": "input GB/s scanned (Thompson boolean, a regex with no DFA: bit-parallel NFA tier, 1M x 1 KB lines per GPU)",
 }
 
 
@@ -601,6 +604,54 @@ def bench_text(h, steps, warmup, dev):
     return out
 
 
+NFA_REGEX = rb"[ab]*a[ab]{15}c"      # 2^16 subsets: the subset construction gives up, the NFA tier runs
+
+
+def bench_nfa(h, steps, warmup, dev, host):
+    """the general Thompson tier: a regex that defeats determinisation, over the C2 lines"""
+    from oracle import cpu_baseline as baseline
+    from sregex_b200 import cuda
+    torch = h.torch
+    n = dev.shape[0]
+    prog = cuda.CudaProgram(NFA_REGEX)
+    assert prog.info.dfa_states == 0
+    rc = torch.empty(n, dtype=torch.int32, device="cuda")
+    total_ms, call_ms, clocks, launches = h.timed(lambda: prog.thompson_lines(dev, n, PITCH, PITCH, out=rc), steps,
+                                                  warmup)
+    # the warp-per-line kernel (the tier for more than 64 lowered states) on a slice, for comparison
+    m = min(n, 1 << 16)
+    rcw = torch.empty(m, dtype=torch.int32, device="cuda")
+    w_ms, _, _, _ = h.timed(lambda: prog.thompson_lines(dev, m, PITCH, PITCH, engine=cuda.ENGINE_NFA_WARP, out=rcw),
+                            3, 3)
+    assert torch.equal(rcw, rc[:m]), "NFA tiers disagree"
+    bytes_per_step = n * PITCH
+    out = {
+        "metric": METRICS["nfa"], "value": h.world * bytes_per_step * steps / (total_ms * 1e-3) / 1e9, "unit": "GB/s",
+        "steps": steps, "ms_per_step": total_ms / steps, "scaling": "weak",
+        "warp_per_line_kernel_gbs": h.world * m * PITCH * 3 / (w_ms * 1e-3) / 1e9,
+        "config": {"workload": "Thompson boolean, regex [ab]*a[ab]{15}c (no DFA within 16384 states), "
+                               "1,048,576 x 1 KB log lines per GPU", "lines_per_gpu": n,
+                   "nfa_states": prog.info.nfa_states, "dfa_states": prog.info.dfa_states,
+                   "matched_lines": int((rc == 0).sum())},
+        "roofline": h.roofline(bytes_per_step + 4 * n, call_ms, "k_nfa64_lines",
+                               note="issue-bound by design: ~35 thread-instructions per byte"),
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    if h.rank == 0 and h.world == 1:
+        cores = host_cores()
+        which = ref_kind()
+        ns = min(n, 2048 * cores)
+        eng = baseline.ENGINE_JIT if which == "ref" else baseline.ENGINE_THOMPSON
+        secs, crc, _ = baseline.run_lines(which, NFA_REGEX, None, host[:ns].numpy(), ns, PITCH, PITCH, eng,
+                                          nthreads=cores)
+        assert (crc == rc[:ns].cpu().numpy()).all(), "NFA tier: GPU verdicts differ from the CPU reference"
+        out["cpu_baseline"] = {"value": ns * PITCH / secs / 1e9, "unit": "GB/s", "cores": cores,
+                               "kind": "reference" if which == "ref" else "port",
+                               "sample": f"Thompson {'JIT' if which == 'ref' else 'interpreter port'} over the first "
+                                         f"{ns} lines, verdicts compared"}
+    return out
+
+
 def c5_shard(h, total, first, count):
     """bytes [first, first+count) of "abccc" x N + "aaabbccb" (bench/gen-data.pl:9 scaled to `total`)"""
     torch = h.torch
@@ -703,7 +754,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--config", default="all", choices=["all", "c2", "c3", "c4", "c5", "text"])
+    ap.add_argument("--config", default="all", choices=["all", "c2", "c3", "c4", "c5", "text", "nfa"])
     ap.add_argument("--variant", type=int, default=int(os.environ.get("SRE_VARIANT", "0")))
     ap.add_argument("--lines", type=int, default=NLINES)
     ap.add_argument("--c4-lines", type=int, default=C4_TOTAL_LINES)
@@ -721,7 +772,7 @@ def main():
     few = max(3, min(steps, 20))        # the heavier configs: fewer steps, same rules
     extra = {}
     out = None
-    if args.config in ("all", "c2", "c3", "text"):
+    if args.config in ("all", "c2", "c3", "text", "nfa"):
         out, dev, host = bench_c2(h, steps if args.config in ("all", "c2") else few, warmup)
         if args.config == "c3" or (args.config == "all" and not args.no_extras):
             try:
@@ -733,6 +784,11 @@ def main():
                 extra["text"] = bench_text(h, few, warmup, dev)
             except Exception as e:
                 extra["text"] = {"error": repr(e)}
+        if args.config == "nfa" or (args.config == "all" and not args.no_extras):
+            try:
+                extra["nfa"] = bench_nfa(h, max(3, min(steps, 10)), warmup, dev, host)
+            except Exception as e:
+                extra["nfa"] = {"error": repr(e)}
         del dev, host
         h.torch.cuda.empty_cache()
     if args.config == "c4" or (args.config == "all" and not args.no_extras):
@@ -748,7 +804,7 @@ def main():
             extra["c5"] = {"error": repr(e)}
     h.sampler.stop_flag = True
     h.sampler.join()
-    if args.config in ("c3", "c4", "c5", "text") and "error" not in extra[args.config]:
+    if args.config in ("c3", "c4", "c5", "text", "nfa") and "error" not in extra[args.config]:
         # one config as the headline (profiling runs)
         head = extra.pop(args.config)
         base = {"n_gpus": h.world, "warmup": warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "u8",

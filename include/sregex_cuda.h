@@ -37,10 +37,14 @@ enum {
     SRE_CUDA_ENGINE_AUTO        = 0,    /* best tier available                       */
     SRE_CUDA_ENGINE_DFA_TILED   = 1,    /* smem-staged thread-per-line DFA           */
     SRE_CUDA_ENGINE_DFA_GENERIC = 2,    /* thread-per-line DFA, any alignment        */
-    SRE_CUDA_ENGINE_NFA         = 3,    /* warp-per-line bit-parallel NFA            */
-    SRE_CUDA_ENGINE_DFA_SKIP    = 4     /* DFA_TILED + word skip; needs a start state
+    SRE_CUDA_ENGINE_NFA         = 3,    /* bit-parallel NFA: thread per line for <=
+                                           64 lowered states (aligned lines), else
+                                           warp per line                             */
+    SRE_CUDA_ENGINE_DFA_SKIP    = 4,    /* DFA_TILED + word skip; needs a start state
                                            left by <= 4 byte values (AUTO picks it
                                            when 1 or 2 byte values leave it)          */
+    SRE_CUDA_ENGINE_NFA_WARP    = 5     /* warp-per-line bit-parallel NFA (any size
+                                           up to 4096 lowered states)                */
 };
 /* tuning: launch shape of DFA_TILED / DFA_SKIP (0 = default); pass
  * engine | SRE_CUDA_ENGINE_VARIANT(v) */

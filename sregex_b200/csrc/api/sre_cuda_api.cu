@@ -146,6 +146,7 @@ struct sre_cuda_program_s {
     sre_dev_dfa_t       dfa;
     sre_dev_image_t     img;
     sre_dev_nfa_t       nfa;
+    sre_dev_nfa64_t     nfa64;                  /* nstates == 0: more than 64 lowered states */
     sre_dev_pike_t      pike;
     sre_dev_pdfa_t      pdfa;                   /* nstates == 0: no determinised Pike */
     uint32_t            nfa_shift = 0;
@@ -242,6 +243,9 @@ int upload(sre_cuda_program_t *cp)
     size_t o_ncls = 0, o_kind = 0, o_mv = 0, o_mt = 0, o_eof = 0, o_init = 0, o_shift = 0, o_follow = 0,
            o_rowidx = 0, o_any = 0, o_cmask = 0, o_mmask = 0;
     uint32_t WP = 32, nrows = 0;
+    size_t o_mv64 = 0, o_mt64 = 0, o_fol64 = 0;
+    uint64_t nfa64_any[3] = { 0, 0, 0 }, nfa64_shift = 0, nfa64_complex = 0, nfa64_init = 0, nfa64_eof = 0;
+    bool has_nfa64 = false;
     if (cp->has_nfa) {
         const uint32_t wpl = (n.nwords + 31) / 32;
         WP = 32 * (wpl <= 1 ? 1 : wpl <= 2 ? 2 : 4);
@@ -304,6 +308,33 @@ int upload(sre_cuda_program_t *cp)
         o_any = b.add(anyrow.data(), anyrow.size() * 4);
         o_cmask = b.add(cmask.data(), cmask.size() * 4);
         o_mmask = b.add(mmask.data(), mmask.size() * 4);
+        if (n.nstates <= 64) {
+            /* 64-bit form for the thread-per-line kernel */
+            auto w64 = [&](const uint32_t *row) -> uint64_t {
+                return (uint64_t) row[0] | (W > 1 ? (uint64_t) row[1] << 32 : 0);
+            };
+            std::vector<uint64_t> mv64(n.nclasses), mt64(n.nclasses), fol64((size_t) n.nkinds * 64, 0);
+            for (uint32_t c = 0; c < n.nclasses; c++) {
+                mv64[c] = w64(&n.mv[(size_t) c * W]);
+                mt64[c] = w64(&n.mt[(size_t) c * W]);
+            }
+            for (uint32_t k = 0; k < n.nkinds; k++) {
+                for (uint32_t st = 0; st < n.nstates; st++) {
+                    fol64[(size_t) k * 64 + st] = w64(n.follow_row(k, st));
+                }
+                nfa64_any[k] = w64(n.follow_row(k, (uint32_t) any_state));
+            }
+            nfa64_any[1] = n.nkinds > 1 ? nfa64_any[1] : nfa64_any[0];
+            nfa64_any[2] = n.nkinds > 2 ? nfa64_any[2] : nfa64_any[0];
+            nfa64_shift = w64(shift.data());
+            nfa64_complex = w64(cmask.data());
+            nfa64_init = w64(n.init.data());
+            nfa64_eof = w64(n.mt_eof.data());
+            o_mv64 = b.add(mv64.data(), mv64.size() * 8);
+            o_mt64 = b.add(mt64.data(), mt64.size() * 8);
+            o_fol64 = b.add(fol64.data(), fol64.size() * 8);
+            has_nfa64 = true;
+        }
     }
 
     /* Pike: the bytecode itself */
@@ -461,6 +492,25 @@ int upload(sre_cuda_program_t *cp)
         cp->nfa.match_mask = reinterpret_cast<const uint32_t *>(base + o_mmask);
         cp->nfa.match_lookahead = n.has_match_lookahead ? 1 : 0;
     }
+    memset(&cp->nfa64, 0, sizeof(cp->nfa64));
+    if (has_nfa64) {
+        sre_dev_nfa64_t &q = cp->nfa64;
+        q.nstates = n.nstates;
+        q.nclasses = n.nclasses;
+        q.nkinds = n.nkinds;
+        q.clsmap = base + o_ncls;
+        q.cls_kind = base + o_kind;
+        q.mv = reinterpret_cast<const uint64_t *>(base + o_mv64);
+        q.mt = reinterpret_cast<const uint64_t *>(base + o_mt64);
+        q.follow = reinterpret_cast<const uint64_t *>(base + o_fol64);
+        q.init = nfa64_init;
+        q.mt_eof = nfa64_eof;
+        q.shift_mask = nfa64_shift;
+        q.complex_mask = nfa64_complex;
+        q.any_follow[0] = nfa64_any[0];
+        q.any_follow[1] = nfa64_any[1];
+        q.any_follow[2] = nfa64_any[2];
+    }
 
     memset(&cp->pdfa, 0, sizeof(cp->pdfa));
     if (has_pd) {
@@ -595,6 +645,16 @@ int thompson_dispatch(sre_cuda_program_t *cp, const uint8_t *dev_buf, const int6
                                     &launches);
         break;
     case SRE_CUDA_ENGINE_NFA:
+        if (!cp->has_nfa) {
+            return fail("program has more than %u lowered states", MAX_NFA_STATES);
+        }
+        if (cp->nfa64.nstates != 0 && aligned && linelen >= 16) {
+            /* up to 64 lowered states: one thread per line, the set in a 64-bit register */
+            err = sre_launch_nfa64_lines(cp->nfa64, dev_buf, nlines, pitch, linelen, dev_rc, st, &launches);
+            break;
+        }
+        /* fall through */
+    case SRE_CUDA_ENGINE_NFA_WARP:
         if (!cp->has_nfa) {
             return fail("program has more than %u lowered states", MAX_NFA_STATES);
         }

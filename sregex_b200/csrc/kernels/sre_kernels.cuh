@@ -51,6 +51,19 @@ struct sre_dev_nfa_t {
     uint32_t         match_lookahead;  /* some MATCH state has a pending look-ahead     */
 };
 
+/* the same for programs of at most 64 lowered states: bitsets as 64-bit words
+ * (thread-per-line kernel k_nfa64_lines; nstates == 0: not available) */
+struct sre_dev_nfa64_t {
+    uint32_t          nstates, nclasses, nkinds;
+    const uint8_t    *clsmap;       /* [256]                                   */
+    const uint8_t    *cls_kind;     /* [nclasses]                              */
+    const uint64_t   *mv, *mt;      /* [nclasses]                              */
+    const uint64_t   *follow;       /* [nkinds][64] rows of the non-shift movers */
+    uint64_t          init, mt_eof, shift_mask, complex_mask, any_follow[3];
+};
+cudaError_t sre_launch_nfa64_lines(const sre_dev_nfa64_t &nfa, const uint8_t *buf, size_t nlines, size_t pitch,
+    size_t linelen, int32_t *rc, cudaStream_t stream, int *launches);
+
 /* ---- Pike tier (runs the bytecode itself) -------------------------------- */
 struct sre_dev_inst_t {         /* == host sre_instruction_t, 16 bytes        */
     uint8_t   opcode, ch;

@@ -500,6 +500,114 @@ k_dfa_generic_hint(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, const int
     }
 }
 
+/* ---- k_nfa64_lines ---------------------------------------------------------- */
+
+/*
+ * The bit-parallel NFA for programs of at most 64 lowered states whose subset
+ * construction blows up (counted repetitions: /[ab]*a[ab]{15}c/ has 20 states
+ * and 2^16 subsets): ONE THREAD per line, the thread set in a 64-bit register,
+ * input staged by the same TMA tile pipeline as the DFA kernels.  Per byte (step
+ * rule of lower/sre_lower.h):  hit |= S & mt[c];  M = S & mv[c];
+ * S' = any_row | (M & shift) << 1 | OR of follow[s] over the other movers s.
+ * The warp-per-line kernel below spends a whole warp on the same 64 bits.
+ */
+struct nfa64_consumer_t {
+    const uint64_t *mv, *mt, *follow;   /* shared memory: [nclasses], [nclasses], [nkinds][64] */
+    const uint8_t  *cls, *kind;         /* shared memory: [256], [nclasses]                    */
+    uint64_t        init, mt_eof, shiftm, complexm, anyrow[3];
+    uint64_t        S, hit;
+    uint32_t        nkinds;
+    size_t          nlines;
+    int32_t        *rc;
+
+    __device__ __forceinline__ void begin(size_t) { S = init; hit = 0; }
+    __device__ __forceinline__ void byte(uint32_t b)
+    {
+        const uint32_t c = cls[b];
+        const uint32_t k = nkinds == 1 ? 0u : kind[c];
+        hit |= S & mt[c];
+        const uint64_t m = S & mv[c];
+        uint64_t nxt = anyrow[0];
+        if (nkinds != 1) {
+            nxt = k == 0 ? anyrow[0] : k == 1 ? anyrow[1] : anyrow[2];
+        }
+        nxt |= (m & shiftm) << 1;
+        uint64_t cm = m & complexm;
+        while (cm) {
+            const uint32_t i = __ffsll((long long) cm) - 1;
+            cm &= cm - 1;
+            nxt |= follow[k * 64 + i];
+        }
+        S = nxt;
+    }
+    __device__ __forceinline__ void chunk(const uint4 &v)
+    {
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                byte((w[i] >> (8 * q)) & 0xff);
+            }
+        }
+    }
+    __device__ __forceinline__ void end(size_t group)
+    {
+        const size_t line = group * 32 + (threadIdx.x & 31);
+        if (line < nlines) {
+            rc[line] = (hit != 0 || (S & mt_eof) != 0) ? SRE_K_OK : SRE_K_DECLINED;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(1024, 1)
+k_nfa64_lines(sre_dev_nfa64_t nfa, const __grid_constant__ CUtensorMap tmap, size_t nlines, uint32_t linelen,
+              int32_t *__restrict__ rc)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    /* [mv C*8][mt C*8][follow nkinds*64*8][cls 256][kind 256][barriers][stages] */
+    uint64_t *s_mv = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *s_mt = s_mv + 256;
+    uint64_t *s_follow = s_mt + 256;
+    uint8_t *s_cls = reinterpret_cast<uint8_t *>(s_follow + 3 * 64);
+    uint8_t *s_kind = s_cls + 256;
+    for (uint32_t i = threadIdx.x; i < nfa.nclasses; i += blockDim.x) {
+        s_mv[i] = nfa.mv[i];
+        s_mt[i] = nfa.mt[i];
+        s_kind[i] = nfa.cls_kind[i];
+    }
+    for (uint32_t i = threadIdx.x; i < nfa.nkinds * 64; i += blockDim.x) {
+        s_follow[i] = nfa.follow[i];
+    }
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        s_cls[i] = nfa.clsmap[i];
+    }
+    __syncthreads();
+    constexpr size_t BAR_OFS = 2 * 256 * 8 + 3 * 64 * 8 + 512, STAGE_OFS = 8192;
+    static_assert(BAR_OFS + MAX_WARPS * MAX_STAGES * 8 <= STAGE_OFS, "layout");
+
+    const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    nfa64_consumer_t cons;
+    cons.mv = s_mv;
+    cons.mt = s_mt;
+    cons.follow = s_follow;
+    cons.cls = s_cls;
+    cons.kind = s_kind;
+    cons.init = nfa.init;
+    cons.mt_eof = nfa.mt_eof;
+    cons.shiftm = nfa.shift_mask;
+    cons.complexm = nfa.complex_mask;
+    cons.anyrow[0] = nfa.any_follow[0];
+    cons.anyrow[1] = nfa.any_follow[1];
+    cons.anyrow[2] = nfa.any_follow[2];
+    cons.nkinds = nfa.nkinds;
+    cons.nlines = nlines;
+    cons.rc = rc;
+    tile_pipeline_tma_early<1>(cons, &tmap, nlines, linelen, smem + STAGE_OFS + (size_t) warp * 32 * 128,
+                               reinterpret_cast<uint64_t *>(smem + BAR_OFS) + warp * MAX_STAGES,
+                               (size_t) blockIdx.x * warps_per_block + warp, (size_t) gridDim.x * warps_per_block);
+}
+
 /* ---- k_nfa_lines ----------------------------------------------------------- */
 
 /*
@@ -1053,5 +1161,40 @@ cudaError_t sre_launch_nfa_lines(const sre_dev_nfa_t &nfa, const uint8_t *buf,
         return cudaErrorInvalidValue;
     }
 #undef SRE_NFA
+    return cudaGetLastError();
+}
+
+/* thread-per-line NFA for <= 64 lowered states; 16-byte aligned fixed-pitch lines */
+cudaError_t sre_launch_nfa64_lines(const sre_dev_nfa64_t &nfa, const uint8_t *buf, size_t nlines, size_t pitch,
+    size_t linelen, int32_t *rc, cudaStream_t stream, int *launches)
+{
+    if (nlines == 0) {
+        return cudaSuccess;
+    }
+    const int warps = 32;
+    const size_t smem = 8192 + (size_t) warps * 32 * 128;
+    CUtensorMap tmap;
+    cudaError_t err = make_row_tensor_map(&tmap, buf, nlines, pitch, 128);
+    if (err != cudaSuccess) {
+        return err;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        err = cudaFuncSetAttribute(k_nfa64_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (err != cudaSuccess) {
+            return err;
+        }
+        attr_set = true;
+    }
+    const size_t ngroups = (nlines + 31) / 32;
+    size_t grid = (size_t) num_sms();
+    const size_t need = (ngroups + warps - 1) / warps;
+    if (grid > need) {
+        grid = need;
+    }
+    if (launches) {
+        ++*launches;
+    }
+    k_nfa64_lines<<<(unsigned) grid, warps * 32, smem, stream>>>(nfa, tmap, nlines, (uint32_t) linelen, rc);
     return cudaGetLastError();
 }

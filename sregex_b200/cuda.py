@@ -9,7 +9,7 @@ import torch
 
 from . import capi
 
-ENGINE_AUTO, ENGINE_DFA_TILED, ENGINE_DFA_GENERIC, ENGINE_NFA, ENGINE_DFA_SKIP = 0, 1, 2, 3, 4
+ENGINE_AUTO, ENGINE_DFA_TILED, ENGINE_DFA_GENERIC, ENGINE_NFA, ENGINE_DFA_SKIP, ENGINE_NFA_WARP = 0, 1, 2, 3, 4, 5
 STATE_INIT = 0xFFFFFFFF
 STATE_UNKNOWN = 0xFFFFFFFE
 STREAM_FN_BYTES = 32

@@ -93,7 +93,12 @@ def test_batch_golden_dfa_generic(golden, cu):
 
 
 def test_batch_golden_nfa(golden, cu):
+    """(1-line batches shorter than 16 bytes take the warp kernel either way)"""
     _golden_batch(golden, cu, cu.ENGINE_NFA)
+
+
+def test_batch_golden_nfa_warp(golden, cu):
+    _golden_batch(golden, cu, cu.ENGINE_NFA_WARP)
 
 
 def test_batch_golden_dfa_skip(golden, cu):
@@ -141,7 +146,8 @@ def test_thompson_tiers_vs_oracle(cu, nlines, linelen, pitch):
                                     baseline.ENGINE_THOMPSON)
     prog = cu.CudaProgram(corpus.C2_REGEX)
     dev = lines.cuda()
-    for engine in (cu.ENGINE_DFA_TILED, cu.ENGINE_DFA_GENERIC, cu.ENGINE_NFA, cu.ENGINE_DFA_SKIP, cu.ENGINE_AUTO):
+    for engine in (cu.ENGINE_DFA_TILED, cu.ENGINE_DFA_GENERIC, cu.ENGINE_NFA, cu.ENGINE_NFA_WARP, cu.ENGINE_DFA_SKIP,
+                   cu.ENGINE_AUTO):
         variants = {cu.ENGINE_DFA_TILED: (0, 1, 2), cu.ENGINE_DFA_SKIP: (0, 1, 2)}.get(engine, (0,))
         for variant in variants:
             got = prog.thompson_lines(dev, nlines, pitch, linelen,
@@ -697,7 +703,7 @@ def test_random_regex_fuzz_gpu_vs_oracle(cu):
         _, want_rc, want_ov = baseline.run_lines("oracle", rx, None, host, nlines, pitch, linelen,
                                                  baseline.ENGINE_PIKE, ovec_slots=prog.nslots)
         dev = torch.from_numpy(host).cuda()
-        engines = [cu.ENGINE_AUTO, cu.ENGINE_NFA]
+        engines = [cu.ENGINE_AUTO, cu.ENGINE_NFA, cu.ENGINE_NFA_WARP]
         if prog.info.dfa_states:
             engines += [cu.ENGINE_DFA_TILED, cu.ENGINE_DFA_GENERIC]
         if prog.info.dfa_leave_bytes:
@@ -868,3 +874,28 @@ def test_text_grep_one_pass_vs_oracle(cu):
     rc, off = progm.thompson_text(dev, len(data))
     want = progm.thompson_ragged(dev, off)
     assert torch.equal(rc, want) and 0 < int((rc == 0).sum()) < rc.numel()
+
+
+def test_nfa_tier_on_a_regex_that_defeats_determinisation(cu):
+    """/[ab]*a[ab]{15}c/: 20-odd NFA states, 2^16 subsets -- no DFA, so AUTO takes the
+    bit-parallel NFA (thread per line, 64-bit set); same verdicts as the warp-per-line kernel
+    and as the oracle, on text over {a, b, c} where partial matches are alive all the time"""
+    rx = rb"[ab]*a[ab]{15}c"
+    prog = cu.CudaProgram(rx)
+    assert prog.info.dfa_states == 0 and prog.info.nfa_states <= 64
+    n, linelen = 3000, 256
+    rs = np.random.RandomState(17)
+    lines = np.frombuffer(b"abc", dtype=np.uint8)[rs.choice(3, size=(n, linelen), p=[0.48, 0.48, 0.04])].copy()
+    lines[::3] = np.frombuffer(b"ab", dtype=np.uint8)[rs.randint(0, 2, size=(len(lines[::3]), linelen))]   # no 'c': no match
+    _, want, _ = baseline.run_lines("oracle", rx, None, lines, n, linelen, linelen, baseline.ENGINE_THOMPSON, nthreads=8)
+    dev = torch.from_numpy(lines).cuda()
+    for engine in (cu.ENGINE_AUTO, cu.ENGINE_NFA, cu.ENGINE_NFA_WARP):
+        got = prog.thompson_lines(dev, n, linelen, linelen, engine=engine).cpu().numpy()
+        assert (got == want).all(), engine
+    assert 0.2 < (want == 0).mean() < 0.8
+    # log text: the same through AUTO on 1 KB lines
+    log = corpus.log_lines(2048, 1024)
+    _, want, _ = baseline.run_lines("oracle", rx, None, log.numpy(), 2048, 1024, 1024, baseline.ENGINE_THOMPSON,
+                                    nthreads=8)
+    got = prog.thompson_lines(log.cuda(), 2048, 1024, 1024).cpu().numpy()
+    assert (got == want).all()
