@@ -631,9 +631,13 @@ int thompson_dispatch(sre_cuda_program_t *cp, const uint8_t *dev_buf, const int6
         }
         err = sre_launch_dfa_lines(cp->dfa, dev_buf, nlines, pitch, linelen, dev_rc, variant, st, &launches);
         if (err == cudaErrorInvalidConfiguration) {
-            /* table too large for shared memory next to the staging rings */
-            err = sre_launch_dfa_ragged(cp->dfa, dev_buf, dev_offsets, nlines, pitch, linelen, dev_rc,
-                                        st, &launches);
+            /* table too large for shared memory next to the staging rings: tiled input, table
+             * through L1/L2 */
+            launches = 0;
+            err = linelen >= 128 ? sre_launch_dfa_lines_big(cp->dfa, dev_buf, nlines, pitch, linelen, dev_rc, nullptr,
+                                                            variant, st, &launches)
+                                 : sre_launch_dfa_ragged(cp->dfa, dev_buf, dev_offsets, nlines, pitch, linelen,
+                                                         dev_rc, st, &launches);
         }
         break;
     case SRE_CUDA_ENGINE_DFA_GENERIC:
@@ -1078,6 +1082,8 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
                                         (cp->nleave >= 1 && cp->nleave <= 2 && linelen >= 128) ? cp->leave_pats
                                                                                                 : nullptr,
                                         cp->nleave, st, &launches)
+            : (aligned && linelen >= 128)
+            ? sre_launch_dfa_lines_big(cp->dfa, dev_buf, nlines, pitch, linelen, gate, hint, 0, st, &launches)
             : sre_launch_dfa_generic_hint(cp->dfa, dev_buf, dev_offsets, nlines, pitch, linelen, gate, hint, st,
                                           &launches);
         if (e != cudaSuccess) {

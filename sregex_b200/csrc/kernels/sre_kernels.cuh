@@ -164,6 +164,10 @@ cudaError_t sre_launch_dfa_generic_hint(const sre_dev_dfa_t &dfa, const uint8_t 
     const int64_t *offsets, size_t nlines, size_t pitch, size_t linelen, int32_t *rc,
     int32_t *hint, cudaStream_t stream, int *launches);
 
+/* TMA-tiled lines, class table through L1/L2 (tables beyond shared memory); hint may be NULL */
+cudaError_t sre_launch_dfa_lines_big(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines, size_t pitch,
+    size_t linelen, int32_t *rc, int32_t *hint, int variant, cudaStream_t stream, int *launches);
+
 /* the lines a Pike pass works on: list[0 .. *count) (device memory), or every
  * line 0 .. nlines-1 when list == NULL */
 struct sre_line_list_t {
