@@ -364,6 +364,96 @@ k_dfa_lines_hint_skip(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tma
                                (size_t) gridDim.x * warps_per_block);
 }
 
+/* ---- k_dfa_lines_big -------------------------------------------------------- */
+
+/*
+ * Determinised programs whose table does not fit in shared memory (the
+ * 64-pattern set: 2107 states x 48 classes x 2 bytes = 202 KB): the lines
+ * still come through the TMA tile pipeline (coalesced, no L1 traffic for the
+ * input), the class-compressed table is read through L1/L2 (the rows of the few
+ * states a line spends its time in stay in L1).  HINT: the restart table of the
+ * Pike start hint instead (entry | 0x8000 = "only the .*? thread consumed this
+ * byte"), with the hint offset kept per line.  (Serving the start state's row
+ * from shared memory was measured slower: 1.7 vs 2.3 TB/s -- a warp with lanes
+ * in both kinds of state executes both paths.)
+ */
+template <bool HINT>
+struct big_consumer_t {
+    const uint16_t *tab;        /* global: tcls, or hcls when HINT */
+    const uint8_t  *cls;        /* shared memory */
+    const uint8_t  *fin;        /* global */
+    uint32_t        ncls, start, acc, s, pos, p0;
+    size_t          nlines;
+    int32_t        *rc, *hint;
+
+    __device__ __forceinline__ void begin(size_t) { s = start; pos = 0; p0 = 0; }
+    __device__ __forceinline__ void byte(uint32_t b)
+    {
+        const uint32_t e = __ldg(tab + s * ncls + cls[b]);
+        if (HINT) {
+            s = e & 0x7fffu;
+            pos++;
+            p0 = (e & 0x8000u) ? pos : p0;
+        } else {
+            s = e;
+        }
+    }
+    __device__ __forceinline__ void chunk(const uint4 &v)
+    {
+        if (s == acc) {
+            /* absorbing: nothing can change any more (and the hint is frozen) */
+            pos += 16;
+            return;
+        }
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                byte((w[i] >> (8 * q)) & 0xff);
+            }
+        }
+    }
+    __device__ __forceinline__ void end(size_t group)
+    {
+        const size_t line = group * 32 + (threadIdx.x & 31);
+        if (line < nlines) {
+            rc[line] = (s == acc || __ldg(fin + s)) ? SRE_K_OK : SRE_K_DECLINED;
+            if (HINT) {
+                hint[line] = (int32_t) p0;
+            }
+        }
+    }
+};
+
+template <bool HINT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_dfa_lines_big(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t nlines, uint32_t linelen,
+                int32_t *__restrict__ rc, int32_t *__restrict__ hint)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    /* [cls 256][barriers][stages] */
+    const uint8_t *map = HINT ? dfa.hclsmap : dfa.clsmap;
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        smem[i] = map[i];
+    }
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    big_consumer_t<HINT> cons;
+    cons.tab = HINT ? dfa.hcls : dfa.tcls;
+    cons.cls = smem;
+    cons.fin = dfa.fin;
+    cons.ncls = HINT ? dfa.hncls : dfa.nclasses;
+    cons.start = dfa.start;
+    cons.acc = dfa.acc;
+    cons.nlines = nlines;
+    cons.rc = rc;
+    cons.hint = hint;
+    tile_pipeline_tma_early<1>(cons, &tmap, nlines, linelen, smem + 4096 + (size_t) warp * 32 * 128,
+                               reinterpret_cast<uint64_t *>(smem + 256) + warp * MAX_STAGES,
+                               (size_t) blockIdx.x * warps_per_block + warp, (size_t) gridDim.x * warps_per_block);
+}
+
 /* ---- k_dfa_generic --------------------------------------------------------- */
 
 template <bool CLS, bool SMEM_TAB>
@@ -1197,4 +1287,56 @@ cudaError_t sre_launch_nfa64_lines(const sre_dev_nfa64_t &nfa, const uint8_t *bu
     }
     k_nfa64_lines<<<(unsigned) grid, warps * 32, smem, stream>>>(nfa, tmap, nlines, (uint32_t) linelen, rc);
     return cudaGetLastError();
+}
+
+/* tiled input, class table through L1/L2: verdict (and, with hint != NULL, the Pike start hint)
+ * for DFAs whose table exceeds shared memory; 16-byte aligned fixed-pitch lines */
+template <bool HINT, int WARPS>
+static cudaError_t launch_dfa_lines_big_t(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines, size_t pitch,
+    size_t linelen, int32_t *rc, int32_t *hint, cudaStream_t stream)
+{
+    const size_t smem = 4096 + (size_t) WARPS * 32 * 128;
+    CUtensorMap tmap;
+    cudaError_t err = make_row_tensor_map(&tmap, buf, nlines, pitch, 128);
+    if (err != cudaSuccess) {
+        return err;
+    }
+    auto kern = k_dfa_lines_big<HINT, WARPS>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (err != cudaSuccess) {
+            return err;
+        }
+        attr_set = true;
+    }
+    const size_t ngroups = (nlines + 31) / 32;
+    size_t grid = (size_t) num_sms();
+    const size_t need = (ngroups + WARPS - 1) / WARPS;
+    if (grid > need) {
+        grid = need;
+    }
+    kern<<<(unsigned) grid, WARPS * 32, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen, rc, hint);
+    return cudaGetLastError();
+}
+
+cudaError_t sre_launch_dfa_lines_big(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines, size_t pitch,
+    size_t linelen, int32_t *rc, int32_t *hint, int variant, cudaStream_t stream, int *launches)
+{
+    if (nlines == 0) {
+        return cudaSuccess;
+    }
+    if (hint != nullptr && dfa.hcls == nullptr) {
+        return cudaErrorInvalidValue;
+    }
+    if (launches) {
+        ++*launches;
+    }
+    /* 32 warps per SM (128 KB of staging, ~100 KB left to L1: measured best) or 16 (64 KB, more L1) */
+    if (hint != nullptr) {
+        return variant == 1 ? launch_dfa_lines_big_t<true, 16>(dfa, buf, nlines, pitch, linelen, rc, hint, stream)
+                            : launch_dfa_lines_big_t<true, 32>(dfa, buf, nlines, pitch, linelen, rc, hint, stream);
+    }
+    return variant == 1 ? launch_dfa_lines_big_t<false, 16>(dfa, buf, nlines, pitch, linelen, rc, hint, stream)
+                        : launch_dfa_lines_big_t<false, 32>(dfa, buf, nlines, pitch, linelen, rc, hint, stream);
 }
