@@ -91,8 +91,9 @@ def stream_match_sharded(prog, shard: torch.Tensor, shard_len: int, shard_base: 
     # the ranks behind it learn their entry states in the next round).
     entry, off, final = None, -1, UNKNOWN
     for _ in range(world):
-        mine = torch.tensor(list(scan.fn), dtype=torch.uint8, device=shard.device)
-        fns = [bytes(t.cpu().tolist()) for t in allgather_bytes(mine)]
+        mine = torch.frombuffer(bytearray(scan.fn), dtype=torch.uint8).to(shard.device, non_blocking=True)
+        gathered = torch.stack(allgather_bytes(mine)).cpu()         # one read-back for all ranks' records
+        fns = [bytes(row.numpy().tobytes()) for row in gathered]
         entries, final = chain_entries(fns, start, apply)
         if entry is None and entries[rank] != UNKNOWN:
             entry = entries[rank]
