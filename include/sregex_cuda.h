@@ -122,6 +122,27 @@ SRE_API int sre_cuda_pike_exec_lines_all(sre_cuda_program_t *cp,
     int64_t *dev_spans, int32_t *dev_ids, void *stream);
 
 /*
+ * Many concurrent streams on the Pike VM -- the ngx_replace_filter shape: one
+ * sre_vm_pike_ctx_t per connection, fed chunk by chunk with SRE_AGAIN, temp
+ * captures and pending matches (sre_vm_pike.c:148-689, :624-658, :692-735).
+ * _create makes nstreams persistent contexts on the device; every _exec call is
+ * one sre_vm_pike_exec(ctx_i, chunk_i, len_i, eof_i, &pending) per stream,
+ * chunk_i = dev_buf[dev_offsets[i], dev_offsets[i+1]) (may be empty), eof_i =
+ * eof_all || dev_eof[i] (dev_eof may be NULL).  Row i of dev_out (4 + ovec_slots
+ * values): rc; 1 if a pending match is reported; its span ($0 start, end); then
+ * the ovector as the reference leaves it (whole on a match, slots 0-1 = the temp
+ * capture on SRE_AGAIN).  A stream that has returned a match continues after it
+ * on its next call, like the reference's ctx.
+ */
+typedef struct sre_cuda_pike_streams_s  sre_cuda_pike_streams_t;
+SRE_API sre_cuda_pike_streams_t *sre_cuda_pike_streams_create(sre_cuda_program_t *cp,
+    size_t nstreams, void *stream);
+SRE_API int sre_cuda_pike_streams_exec(sre_cuda_pike_streams_t *streams,
+    const uint8_t *dev_buf, const int64_t *dev_offsets, const uint8_t *dev_eof,
+    unsigned eof_all, int64_t *dev_out, size_t ovec_slots, void *stream);
+SRE_API void sre_cuda_pike_streams_free(sre_cuda_pike_streams_t *streams);
+
+/*
  * Chunk-parallel form of a sequence of sre_vm_thompson_exec(ctx, chunk_k,
  * chunk_bytes, eof) calls over one long stream resident on the device
  * (sre_vm_thompson.c:63-270; the carried thread lists are one DFA state here).

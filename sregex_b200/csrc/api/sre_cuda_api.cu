@@ -1437,6 +1437,68 @@ sre_cuda_thompson_exec_stream_host(sre_cuda_program_t *cp, const uint8_t *host_b
     return rc;
 }
 
+/* ---- batched streaming Pike contexts ------------------------------------------ */
+
+}  /* extern "C" */
+
+struct sre_cuda_pike_streams_s {
+    sre_cuda_program_t *cp = nullptr;
+    size_t              nstreams = 0;
+    uint8_t            *d_ctx = nullptr;
+};
+
+extern "C" {
+
+SRE_API sre_cuda_pike_streams_t *
+sre_cuda_pike_streams_create(sre_cuda_program_t *cp, size_t nstreams, void *stream)
+{
+    if (cp == NULL || nstreams == 0) {
+        fail("NULL program or no streams");
+        return NULL;
+    }
+    sre_cuda_pike_streams_t *h = new (std::nothrow) sre_cuda_pike_streams_t();
+    if (h == NULL) {
+        return NULL;
+    }
+    h->cp = cp;
+    h->nstreams = nstreams;
+    int launches = 0;
+    if (cudaMalloc(&h->d_ctx, nstreams * cp->pike.ctx_stride) != cudaSuccess
+        || sre_launch_pike_streams_init(cp->pike, h->d_ctx, nstreams, as_stream(stream), &launches) != cudaSuccess)
+    {
+        fail("creating %zu Pike contexts failed: %s", nstreams, cudaGetErrorString(cudaGetLastError()));
+        cudaFree(h->d_ctx);
+        delete h;
+        return NULL;
+    }
+    count_launches(launches);
+    return h;
+}
+
+SRE_API int
+sre_cuda_pike_streams_exec(sre_cuda_pike_streams_t *h, const uint8_t *dev_buf, const int64_t *dev_offsets,
+    const uint8_t *dev_eof, unsigned eof_all, int64_t *dev_out, size_t ovec_slots, void *stream)
+{
+    if (h == NULL || dev_offsets == NULL || dev_out == NULL) {
+        return fail("NULL handle, offsets or output");
+    }
+    int launches = 0;
+    cudaError_t err = sre_launch_pike_streams(h->cp->pike, h->d_ctx, h->nstreams, dev_buf, dev_offsets, dev_eof,
+                                              eof_all != 0, dev_out, (uint32_t) ovec_slots, as_stream(stream),
+                                              &launches);
+    count_launches(launches);
+    return err == cudaSuccess ? SRE_OK : fail("Pike stream kernel launch failed: %s", cudaGetErrorString(err));
+}
+
+SRE_API void
+sre_cuda_pike_streams_free(sre_cuda_pike_streams_t *h)
+{
+    if (h) {
+        cudaFree(h->d_ctx);
+        delete h;
+    }
+}
+
 SRE_API int
 sre_cuda_dfa_fin(sre_cuda_program_t *cp, uint32_t state)
 {

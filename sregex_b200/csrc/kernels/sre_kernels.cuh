@@ -271,6 +271,13 @@ cudaError_t sre_launch_pike_stream(const sre_dev_pike_t &pk, uint8_t *ctx,
     uint32_t ovec_slots, cudaStream_t stream, int *launches);
 cudaError_t sre_launch_pike_ctx_init(const sre_dev_pike_t &pk, uint8_t *ctx,
     cudaStream_t stream, int *launches);
+/* many persistent contexts at once (ctxs: nstreams * pk.ctx_stride bytes): stream i is fed
+ * buf[offsets[i], offsets[i+1]); out row i = { rc, pending flag, pending[2], ovector[ovec_slots] } */
+cudaError_t sre_launch_pike_streams_init(const sre_dev_pike_t &pk, uint8_t *ctxs, size_t nstreams,
+    cudaStream_t stream, int *launches);
+cudaError_t sre_launch_pike_streams(const sre_dev_pike_t &pk, uint8_t *ctxs, size_t nstreams, const uint8_t *buf,
+    const int64_t *offsets, const uint8_t *eofs, int eof_all, int64_t *out, uint32_t ovec_slots,
+    cudaStream_t stream, int *launches);
 
 /* chunk-parallel DFA stream scan (sre_stream.cu) ----------------------------- */
 

@@ -1050,6 +1050,50 @@ __global__ void k_pike_stream(sre_dev_pike_t pk, uint8_t *ctx, const uint8_t *bu
     out[3] = c.h->pending[1];
 }
 
+/* a batch of persistent contexts, one thread each: stream i is fed buf[off[i], off[i+1]);
+ * out row i = { rc, pending flag, pending[0], pending[1], ovector... } as k_pike_stream's */
+__global__ void __launch_bounds__(64)
+k_pike_streams(sre_dev_pike_t pk, uint8_t *ctxs, size_t nstreams, const uint8_t *__restrict__ buf,
+               const int64_t *__restrict__ off, const uint8_t *__restrict__ eofs, int eof_all, int64_t *out,
+               uint32_t ovec_slots, int parts)
+{
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nstreams) {
+        return;
+    }
+    extern __shared__ uint32_t smem_ctx[];
+    pike_ctx_t c;
+    pike_attach(c, pk, reinterpret_cast<uint32_t *>(ctxs + i * pk.ctx_stride), 1, smem_ctx, parts, threadIdx.x,
+                blockDim.x);
+    pike_hdr_load(pk, c);
+    c.cap_reset();
+    int64_t *o = out + i * (4 + (size_t) ovec_slots);
+    int pending = 0;
+    const bool eof = eof_all || (eofs != nullptr && eofs[i] != 0);
+    const int r = pike_exec(pk, c, buf + off[i], off[i + 1] - off[i], eof, o + 4, ovec_slots, &pending);
+    pike_hdr_store(pk, c);
+    o[0] = r;
+    o[1] = pending;
+    o[2] = c.h->pending[0];
+    o[3] = c.h->pending[1];
+}
+
+__global__ void __launch_bounds__(64)
+k_pike_streams_init(sre_dev_pike_t pk, uint8_t *ctxs, size_t nstreams)
+{
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nstreams) {
+        return;
+    }
+    extern __shared__ uint32_t smem_ctx[];
+    pike_ctx_t c;
+    pike_attach(c, pk, reinterpret_cast<uint32_t *>(ctxs + i * pk.ctx_stride), 1, smem_ctx, 0, threadIdx.x, blockDim.x);
+    c.tag_open(0);
+    c.tag_open(1);
+    pike_reset(c, true);
+    pike_hdr_store(pk, c);
+}
+
 }  // namespace
 
 /* per-context (1, default) or warp-interleaved (32) scratch; SRE_PIKE_INTERLEAVE=1
@@ -1169,5 +1213,43 @@ cudaError_t sre_launch_pike_stream(const sre_dev_pike_t &pk, uint8_t *ctx, const
     size_t smem;
     const int parts = smem_parts(pk, 1, false, &smem);
     k_pike_stream<<<1, 1, smem, stream>>>(pk, ctx, buf, len, skip, eof, out, ovec_slots, parts);
+    return cudaGetLastError();
+}
+
+/* batched streaming Pike: nstreams persistent contexts of pk.ctx_stride bytes each */
+cudaError_t sre_launch_pike_streams_init(const sre_dev_pike_t &pk, uint8_t *ctxs, size_t nstreams,
+    cudaStream_t stream, int *launches)
+{
+    if (nstreams == 0) {
+        return cudaSuccess;
+    }
+    if (launches) {
+        ++*launches;
+    }
+    k_pike_streams_init<<<(unsigned) ((nstreams + 63) / 64), 64, pike_smem_words(pk, 0, 64) * 4, stream>>>(pk, ctxs,
+                                                                                                          nstreams);
+    return cudaGetLastError();
+}
+
+cudaError_t sre_launch_pike_streams(const sre_dev_pike_t &pk, uint8_t *ctxs, size_t nstreams, const uint8_t *buf,
+    const int64_t *offsets, const uint8_t *eofs, int eof_all, int64_t *out, uint32_t ovec_slots,
+    cudaStream_t stream, int *launches)
+{
+    if (nstreams == 0) {
+        return cudaSuccess;
+    }
+    if (launches) {
+        ++*launches;
+    }
+    static bool opted = false;
+    if (!opted) {
+        opted = true;
+        cudaFuncSetAttribute(k_pike_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    }
+    /* the marks persist between calls, so they stay in the context blocks */
+    size_t smem;
+    const int parts = smem_parts(pk, 64, false, &smem);
+    k_pike_streams<<<(unsigned) ((nstreams + 63) / 64), 64, smem, stream>>>(pk, ctxs, nstreams, buf, offsets, eofs,
+                                                                           eof_all, out, ovec_slots, parts);
     return cudaGetLastError();
 }

@@ -60,6 +60,9 @@ def lib():
             "sre_cuda_pike_exec_lines_host": (C.c_int, [vp, vp, sz, sz, sz, C.c_int, i32p, i64p, sz]),
             "sre_cuda_program_set_pike_tier": (None, [vp, C.c_int]),
             "sre_cuda_program_last_pike_tier": (C.c_int, [vp]),
+            "sre_cuda_pike_streams_create": (vp, [vp, sz, vp]),
+            "sre_cuda_pike_streams_exec": (C.c_int, [vp, vp, i64p, vp, C.c_uint, i64p, sz, vp]),
+            "sre_cuda_pike_streams_free": (None, [vp]),
             "sre_cuda_thompson_exec_text": (C.c_int, [vp, vp, sz, i64p, i32p, sz, C.POINTER(C.c_size_t), vp]),
             "sre_cuda_index_lines": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                                C.POINTER(C.c_size_t), C.c_void_p]),
@@ -224,6 +227,36 @@ class CudaProgram:
                                                         linelen, int(gate), host_rc.data_ptr(),
                                                         host_ovec.data_ptr(), self.nslots))
         return host_rc, host_ovec
+
+
+class PikeStreams:
+    """nstreams persistent Pike contexts on the device (sre_cuda_pike_streams_*): each exec() call
+    feeds every stream its next chunk, like sre_vm_pike_exec on one ctx per connection"""
+
+    def __init__(self, prog: "CudaProgram", nstreams: int):
+        self.prog, self.n = prog, nstreams
+        self.handle = prog.lib.L.sre_cuda_pike_streams_create(prog.cp, nstreams, _stream_ptr())
+        if not self.handle:
+            raise SreCudaError(prog.lib.L.sre_cuda_last_error().decode())
+
+    def exec(self, buf: torch.Tensor, offsets: torch.Tensor, eof=None, eof_all: bool = False) -> torch.Tensor:
+        """-> int64[nstreams, 4 + nslots]: rc, pending flag, pending span, ovector"""
+        out = torch.full((self.n, 4 + self.prog.nslots), -99, dtype=torch.int64, device=buf.device)
+        _check(self.prog.lib.L.sre_cuda_pike_streams_exec(
+            self.handle, buf.data_ptr(), offsets.data_ptr(), eof.data_ptr() if eof is not None else None,
+            int(eof_all), out.data_ptr(), self.prog.nslots, _stream_ptr()))
+        return out
+
+    def close(self):
+        if self.handle:
+            self.prog.lib.L.sre_cuda_pike_streams_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class StreamScan:

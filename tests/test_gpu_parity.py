@@ -899,3 +899,69 @@ def test_nfa_tier_on_a_regex_that_defeats_determinisation(cu):
                                     nthreads=8)
     got = prog.thompson_lines(log.cuda(), 2048, 1024, 1024).cpu().numpy()
     assert (got == want).all()
+
+
+def test_batched_streaming_pike_contexts(cu):
+    """sre_cuda_pike_streams_*: many persistent Pike contexts fed chunk by chunk at the same time
+    (one ctx per connection, the ngx_replace_filter shape): per stream the whole trace of
+    (rc, temp capture, pending match) and the final rc + ovector equal the oracle's
+    sre_vm_pike_exec driven with the same chunks, continuation after a match included"""
+    import random
+    rng = random.Random(2024)
+    o = capi.load("oracle")
+    for rx in (rb"(a+)(b|c)", rb"(\w+) (\S+) HTTP/(\d)\.(\d)", [rb"ab+c", rb"(x|y)z", rb"\bGET\b"]):
+        prog = cu.CudaProgram(rx)
+        po = o.compile(rx)
+        n = 200
+        subjects = []
+        for i in range(n):
+            k = rng.randrange(0, 60)
+            if isinstance(rx, list) or rx.startswith(b"(a+)"):
+                body = bytes(rng.choice(b"abcxyz GET") for _ in range(k))
+            else:
+                body = bytes(corpus.log_lines(1, 1024, first_line=i).numpy()[0, 1024 - 60 - k:1024 - 40])
+            subjects.append(body)
+        # per stream: chunks of random sizes (some empty), eof on the last
+        plans = []
+        for sbj in subjects:
+            cuts, at = [], 0
+            while at < len(sbj):
+                m = rng.choice([0, 1, 1, 2, 5, 13])
+                cuts.append(sbj[at:at + m])
+                at += m
+            cuts.append(b"")
+            plans.append([(c, j == len(cuts) - 1) for j, c in enumerate(cuts)])
+        want = [o.pike(po, sbj, plan) for sbj, plan in zip(subjects, plans)]     # (trace, rc, ov)
+        streams = cu.PikeStreams(prog, n)
+        traces = [[] for _ in range(n)]
+        final = [None] * n
+        rounds = max(len(p) for p in plans)
+        for r in range(rounds):
+            parts, off, eofs = [], [0], []
+            for i in range(n):
+                if final[i] is None and r < len(plans[i]):
+                    chunk, eof = plans[i][r]
+                else:
+                    chunk, eof = b"", False          # nothing more for this stream in this round
+                parts.append(chunk)
+                off.append(off[-1] + len(chunk))
+                eofs.append(1 if eof else 0)
+            blob = b"".join(parts) + bytes(16)
+            out = streams.exec(torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda(),
+                               torch.tensor(off, dtype=torch.int64, device="cuda"),
+                               eof=torch.tensor(eofs, dtype=torch.uint8, device="cuda")).cpu().tolist()
+            for i in range(n):
+                if final[i] is not None or r >= len(plans[i]):
+                    continue
+                row = out[i]
+                if row[0] == capi.SRE_AGAIN:
+                    traces[i].append((capi.SRE_AGAIN, row[4], row[5], row[2] if row[1] else None,
+                                      row[3] if row[1] else None))
+                else:
+                    final[i] = (row[0], row[4:4 + prog.nslots] if row[0] >= 0 else None)
+        streams.close()
+        for i in range(n):
+            wt, wrc, wov = want[i]
+            assert final[i] == (wrc, wov), (rx, subjects[i], final[i], wrc, wov)
+            assert traces[i] == [tuple(t) for t in wt], (rx, subjects[i])
+        assert sum(1 for f in final if f[0] >= 0) > 20
