@@ -568,8 +568,21 @@ def bench_text(h, steps, warmup, dev):
         assert r == capi.SRE_OK
         found[0] = cnt.value
 
-    total_ms, call_ms, clocks, launches = h.timed(step, steps, warmup)
+    off_ms, off_call_ms, _, _ = h.timed(step, steps, warmup)
     assert found[0] == nl, (found[0], nl)
+    rc_all = rc.clone()
+
+    def step_rc():
+        # verdicts only (what C2 delivers per line): no offsets wanted
+        cnt = __import__("ctypes").c_size_t(0)
+        r = prog.lib.L.sre_cuda_thompson_exec_text(prog.cp, flat.data_ptr(), n, None, rc.data_ptr(), nl,
+                                                   __import__("ctypes").byref(cnt),
+                                                   torch.cuda.current_stream().cuda_stream)
+        assert r == capi.SRE_OK
+        found[0] = cnt.value
+
+    total_ms, call_ms, clocks, launches = h.timed(step_rc, steps, warmup)
+    assert found[0] == nl and torch.equal(rc, rc_all), "text: verdict-only rows differ from the rows with offsets"
     # parity at full size: the line index + ragged route must give the same rows
     off2 = cuda.index_lines(flat)
     assert torch.equal(off2, off)
@@ -578,12 +591,15 @@ def bench_text(h, steps, warmup, dev):
     out = {
         "metric": METRICS["text"], "value": h.world * n * steps / (total_ms * 1e-3) / 1e9, "unit": "GB/s",
         "steps": steps, "ms_per_step": total_ms / steps, "scaling": "weak",
+        "with_line_offsets_gbs": h.world * n * steps / (off_ms * 1e-3) / 1e9,
         "config": {"workload": "newline-delimited log text (ragged lines, mean ~180 B, no index beforehand): "
                                "sre_vm_thompson_exec per line, regex " + REGEX_NAME,
                    "bytes_per_gpu": n, "lines": nl, "matched_lines": int((rc == 0).sum())},
-        # 1 B per input byte + 4 B verdict + 8 B offset per line
-        "roofline": h.roofline(n + 12 * nl, call_ms, "sre_cuda_thompson_exec_text: k_text_pieces + scan + write",
-                               note="whole call (3 launches + the read-back of the line count)"),
+        # 1 B per input byte + 4 B verdict per line (+ 8 B offset per line in the second form)
+        "roofline": h.roofline(n + 4 * nl, call_ms, "sre_cuda_thompson_exec_text: k_text_pieces + sums/scan/fill/scatter",
+                               note="whole call, verdict per line (5 launches + the read-back of the line count)"),
+        "with_line_offsets_roofline": h.roofline(n + 12 * nl, off_call_ms,
+                                                 "sre_cuda_thompson_exec_text: k_text_pieces + sums/scan/write"),
         "gpu_launches": launches, "clocks": clocks,
     }
     if h.rank == 0 and h.world == 1:

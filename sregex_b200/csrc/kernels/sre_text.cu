@@ -48,8 +48,10 @@ __device__ __forceinline__ uint32_t nl_mask(uint32_t x)
 }
 
 struct text_out_t {
-    uint32_t       *stage;      /* [npieces][CAP] (end offset within the span << 1) | matched */
+    uint32_t       *stage;      /* [npieces][CAP] (end offset within the span << 1) | matched; in
+                                   verdict-only mode: the piece-local numbers of the matched lines */
     uint32_t       *count;      /* [npieces] lines that start in the piece                  */
+    uint32_t       *mcount;     /* [npieces] verdict-only mode: how many of them matched    */
 };
 
 /* does a line start at the first byte of `piece`? */
@@ -94,7 +96,9 @@ __device__ __forceinline__ uint32_t serial_piece(const sre_dev_dfa_t &dfa, const
 /* MARK: the automaton has at most 64 states, and the table marks "this byte was a '\n'" in bit 6
  * of the state (rows r, r+64, r+128, r+192 are the same row): one OR + one test per word
  * replaces the newline search */
-template <bool MARK>
+/* ALL: every line end is staged (offsets wanted); else only the matched lines' numbers are, and a
+ * word that holds a '\n' but no match just counts it */
+template <bool MARK, bool ALL>
 struct text_consumer_t {
     const uint8_t      *tab;        /* x256 in shared memory */
     sre_dev_dfa_t       dfa;
@@ -103,6 +107,7 @@ struct text_consumer_t {
     text_out_t          out;
     uint32_t            s, pos;
     uint32_t            cnt;        /* lines recorded; 0xffffffff: the next line end is not ours */
+    uint32_t            mcnt;       /* matched lines recorded (verdict-only mode)               */
     uint32_t           *stage;
 
     __device__ __forceinline__ void begin(size_t group)
@@ -110,6 +115,7 @@ struct text_consumer_t {
         const size_t piece = group * 32 + (threadIdx.x & 31);
         s = dfa.start;
         pos = 0;
+        mcnt = 0;
         cnt = 0xffffffffu;
         stage = out.stage;
         if (piece < npieces) {
@@ -120,8 +126,15 @@ struct text_consumer_t {
     }
     __device__ __forceinline__ void record(uint32_t end_off, uint32_t matched)
     {
-        if (cnt < CAP) {            /* (not for 0xffffffff: that line began in an earlier piece) */
-            stage[cnt] = (end_off << 1) | matched;
+        if (ALL) {
+            if (cnt < CAP) {        /* (not for 0xffffffff: that line began in an earlier piece) */
+                stage[cnt] = (end_off << 1) | matched;
+            }
+        } else if (matched && cnt != 0xffffffffu) {
+            if (mcnt < CAP) {
+                stage[mcnt] = cnt;
+            }
+            mcnt++;
         }
         cnt++;
     }
@@ -134,7 +147,21 @@ struct text_consumer_t {
         s = a3;
         /* the states after each byte are still in registers: a word that holds a '\n' only adds
          * the bookkeeping */
-        if (MARK) {
+        if (MARK && !ALL) {
+            /* verdict only: a '\n' without a match (bit 7 is only ever set on a '\n') is counted,
+             * nothing else; 0xffffffff + 1 = 0 takes care of the line end that is not ours */
+            const uint32_t any = a0 | a1 | a2 | a3;
+            if (any & 0x40u) {
+                if (any & 0x80u) {
+                    if (a0 & 0x40u) record(at + 1, a0 >> 7);
+                    if (a1 & 0x40u) record(at + 2, a1 >> 7);
+                    if (a2 & 0x40u) record(at + 3, a2 >> 7);
+                    if (a3 & 0x40u) record(at + 4, a3 >> 7);
+                } else {
+                    cnt += ((a0 >> 6) & 1u) + ((a1 >> 6) & 1u) + ((a2 >> 6) & 1u) + ((a3 >> 6) & 1u);
+                }
+            }
+        } else if (MARK) {
             if ((a0 | a1 | a2 | a3) & 0x40u) {
                 if (a0 & 0x40u) record(at + 1, a0 >> 7);
                 if (a1 & 0x40u) record(at + 2, a1 >> 7);
@@ -211,10 +238,13 @@ struct text_consumer_t {
             }
         }
         out.count[piece] = cnt == 0xffffffffu ? 0u : cnt;
+        if (!ALL) {
+            out.mcount[piece] = mcnt;
+        }
     }
 };
 
-template <bool MARK>
+template <bool MARK, bool ALL>
 __global__ void __launch_bounds__(1024, 1)
 k_text_pieces(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ buf, size_t len,
               size_t npieces, text_out_t out)
@@ -225,7 +255,7 @@ k_text_pieces(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, const
     __syncthreads();
 
     const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
-    text_consumer_t<MARK> cons;
+    text_consumer_t<MARK, ALL> cons;
     cons.tab = smem;
     cons.dfa = dfa;
     cons.buf = buf;
@@ -240,15 +270,26 @@ k_text_pieces(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, const
 
 /* the ragged tail piece [nfull * PIECE, len): one thread, table from global memory */
 __global__ void k_text_tail(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, size_t piece,
-                            text_out_t out)
+                            text_out_t out, int all)
 {
     uint32_t *stage = out.stage + piece * CAP;
+    uint32_t m = 0;
     out.count[piece] = serial_piece(dfa, buf, len, piece * PIECE, len, starts_line(buf, piece),
                                     [&](uint32_t end_off, uint32_t matched, uint32_t k) {
-                                        if (k < CAP) {
-                                            stage[k] = (end_off << 1) | matched;
+                                        if (all) {
+                                            if (k < CAP) {
+                                                stage[k] = (end_off << 1) | matched;
+                                            }
+                                        } else if (matched) {
+                                            if (m < CAP) {
+                                                stage[m] = k;
+                                            }
+                                            m++;
                                         }
                                     });
+    if (!all) {
+        out.mcount[piece] = m;
+    }
 }
 
 constexpr uint32_t WB = 1024;       /* pieces per block of the scan / write kernels */
@@ -407,12 +448,55 @@ k_text_write(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, siz
     }
 }
 
+/* verdict-only mode: rc[0 .. min(lines, max_lines)) <- SRE_DECLINED */
+__global__ void __launch_bounds__(256)
+k_text_fill(const unsigned long long *__restrict__ total, int32_t *__restrict__ rc, size_t max_lines)
+{
+    const size_t n = *total < max_lines ? (size_t) *total : max_lines;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        rc[i] = SRE_K_DECLINED;
+    }
+}
+
+/* ... then rc[line] <- SRE_OK for the staged matched lines; one thread per piece */
+__global__ void __launch_bounds__(WB)
+k_text_scatter(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, size_t npieces, text_out_t out,
+               const unsigned long long *__restrict__ sums, int32_t *__restrict__ rc, size_t max_lines)
+{
+    const size_t piece = (size_t) blockIdx.x * WB + threadIdx.x;
+    const uint32_t n = piece < npieces ? out.count[piece] : 0u;
+    uint32_t total;
+    const uint32_t before = block_exclusive(n, &total);
+    if (piece >= npieces) {
+        return;
+    }
+    const size_t first = (size_t) sums[blockIdx.x] + before;
+    const uint32_t m = out.mcount[piece];
+    if (m <= CAP) {
+        const uint32_t *stage = out.stage + piece * CAP;
+        for (uint32_t k = 0; k < m; k++) {
+            const size_t line = first + stage[k];
+            if (line < max_lines) {
+                rc[line] = SRE_K_OK;
+            }
+        }
+    } else {
+        const size_t begin = piece * PIECE, end = begin + PIECE < len ? begin + PIECE : len;
+        serial_piece(dfa, buf, len, begin, end, starts_line(buf, piece),
+                     [&](uint32_t, uint32_t matched, uint32_t k) {
+                         if (matched && first + k < max_lines) {
+                             rc[first + k] = SRE_K_OK;
+                         }
+                     });
+    }
+}
+
 }  // namespace
 
 size_t sre_text_workspace_bytes(size_t len)
 {
     const size_t npieces = (len + PIECE - 1) / PIECE + 1, nb = (npieces + WB - 1) / WB;
-    return (nb + 2) * 8 + npieces * (CAP * 4 + 4) + 1024;
+    return (nb + 2) * 8 + npieces * (CAP * 4 + 8) + 2048;
 }
 
 /* where in the workspace the number of lines is left (8 bytes) */
@@ -435,7 +519,11 @@ cudaError_t sre_launch_text(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t
     text_out_t out;
     out.count = reinterpret_cast<uint32_t *>(p);
     p += (npieces * 4 + 255) / 256 * 256 + 256;
+    out.mcount = reinterpret_cast<uint32_t *>(p);
+    p += (npieces * 4 + 255) / 256 * 256 + 256;
     out.stage = reinterpret_cast<uint32_t *>(p);
+    /* every line end staged when the offsets are wanted; else (small automata) only the matches */
+    const bool all = offsets != nullptr || dfa.x256m == nullptr;
     cudaError_t err;
     if (npieces == 0) {
         if ((err = cudaMemsetAsync(workspace, 0, 8, stream)) != cudaSuccess) return err;
@@ -449,9 +537,14 @@ cudaError_t sre_launch_text(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t
         if ((err = make_row_tensor_map(&tmap, buf, nfull, PIECE, 128)) != cudaSuccess) return err;
         static bool attr_set = false;
         if (!attr_set) {
-            err = cudaFuncSetAttribute(k_text_pieces<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            err = cudaFuncSetAttribute(k_text_pieces<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int) smem);
             if (err == cudaSuccess) {
-                err = cudaFuncSetAttribute(k_text_pieces<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                err = cudaFuncSetAttribute(k_text_pieces<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int) smem);
+            }
+            if (err == cudaSuccess) {
+                err = cudaFuncSetAttribute(k_text_pieces<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int) smem);
             }
             if (err != cudaSuccess) return err;
@@ -464,21 +557,31 @@ cudaError_t sre_launch_text(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t
             grid = need;
         }
         if (launches) ++*launches;
-        if (dfa.x256m != nullptr) {
-            k_text_pieces<true><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, out);
+        if (!all) {
+            k_text_pieces<true, false><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, out);
+        } else if (dfa.x256m != nullptr) {
+            k_text_pieces<true, true><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, out);
         } else {
-            k_text_pieces<false><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, out);
+            k_text_pieces<false, true><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, out);
         }
         if ((err = cudaGetLastError()) != cudaSuccess) return err;
     }
     if (npieces > nfull) {
         if (launches) ++*launches;
-        k_text_tail<<<1, 1, 0, stream>>>(dfa, buf, len, nfull, out);
+        k_text_tail<<<1, 1, 0, stream>>>(dfa, buf, len, nfull, out, all ? 1 : 0);
         if ((err = cudaGetLastError()) != cudaSuccess) return err;
     }
-    if (launches) *launches += 3;
+    if (launches) *launches += all ? 3 : 4;
     k_text_sums<<<(unsigned) nb, WB, 0, stream>>>(out.count, npieces, sums);
     k_text_scan<<<1, 1024, 0, stream>>>(sums, nb);
-    k_text_write<<<(unsigned) nb, WB, 0, stream>>>(dfa, buf, len, npieces, out, sums, rc, offsets, max_lines);
+    if (all) {
+        k_text_write<<<(unsigned) nb, WB, 0, stream>>>(dfa, buf, len, npieces, out, sums, rc, offsets, max_lines);
+    } else {
+        const size_t most = max_lines < len + 1 ? max_lines : len + 1;
+        size_t fgrid = (most + 255) / 256;
+        fgrid = fgrid > 4096 ? 4096 : fgrid < 1 ? 1 : fgrid;
+        k_text_fill<<<(unsigned) fgrid, 256, 0, stream>>>(sums + nb, rc, max_lines);
+        k_text_scatter<<<(unsigned) nb, WB, 0, stream>>>(dfa, buf, len, npieces, out, sums, rc, max_lines);
+    }
     return cudaGetLastError();
 }

@@ -195,33 +195,52 @@ k_dfa_lines_skipw(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, s
  * exact by the automaton instead of a thread-list comparison.
  */
 struct hint_consumer_t {
-    const uint8_t  *tab;        /* h256 in shared memory */
+    uint32_t        tab_s;      /* h256 in shared memory, rows of ROW260 bytes (shared-window address) */
     const uint8_t  *fin;
     uint32_t        acc, s, pos, p0;
     size_t          nlines;
     int32_t        *rc, *hint;
 
     __device__ __forceinline__ void begin(size_t) { s = 0; pos = 0; p0 = 0; }
-    __device__ __forceinline__ void step(uint32_t addr)
+    /*
+     * A word at a time.  The rows are padded to 260 bytes (ncu, round 2: with 256-byte rows 42 %
+     * of this kernel's shared-memory wavefronts were bank conflicts -- lanes in different states
+     * reading bytes of the same 4-byte group -- and the pipe was 91 % busy); the byte's address
+     * within row 0 is computed off the state chain (one IMAD + one LDS per byte on it).  The four
+     * states are packed into one register and the restart flags tested together: the last
+     * flagged byte of the word moves the hint.
+     */
+    __device__ __forceinline__ void word(uint32_t w)
     {
-        s = tab[addr];
+        step260_t st = { tab_s };
+        const uint32_t b0 = st.row0(__byte_perm(w, 0, 0x4440)), b1 = st.row0(__byte_perm(w, 0, 0x4441));
+        const uint32_t b2 = st.row0(__byte_perm(w, 0, 0x4442)), b3 = st.row0(__byte_perm(w, 0, 0x4443));
+        const uint32_t a0 = step260_t::lds_u8(s * ROW260 + b0);
+        const uint32_t a1 = step260_t::lds_u8(a0 * ROW260 + b1);
+        const uint32_t a2 = step260_t::lds_u8(a1 * ROW260 + b2);
+        const uint32_t a3 = step260_t::lds_u8(a2 * ROW260 + b3);
+        s = a3;
+        const uint32_t m = __byte_perm(__byte_perm(a0, a1, 0x0040), __byte_perm(a2, a3, 0x0040), 0x5410) & 0x80808080u;
+        if (m) {
+            p0 = pos + 4 - ((uint32_t) __clz((int) m) >> 3);
+        }
+        pos += 4;
+    }
+    __device__ __forceinline__ void chunk(const uint4 &v)
+    {
+        word(v.x);
+        word(v.y);
+        word(v.z);
+        word(v.w);
+    }
+    __device__ __forceinline__ void byte(uint32_t b)
+    {
+        s = step260_t::lds_u8(s * ROW260 + tab_s + b);
         pos++;
         if (s & 0x80) {
             p0 = pos;
         }
     }
-    __device__ __forceinline__ void chunk(const uint4 &v)
-    {
-        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            step(__byte_perm(w[i], s, 0x5540));
-            step(__byte_perm(w[i], s, 0x5541));
-            step(__byte_perm(w[i], s, 0x5542));
-            step(__byte_perm(w[i], s, 0x5543));
-        }
-    }
-    __device__ __forceinline__ void byte(uint32_t b) { step((s << 8) | b); }
     __device__ __forceinline__ void end(size_t group)
     {
         const size_t line = group * 32 + (threadIdx.x & 31);
@@ -233,28 +252,30 @@ struct hint_consumer_t {
     }
 };
 
+/* shared memory of the hint kernels: [256 rows x 260 B][fin 256][barriers][stages] */
+constexpr size_t HINT_FIN_OFS = 256 * ROW260, HINT_BAR_OFS = HINT_FIN_OFS + 256,
+                 HINT_STAGE_OFS = (HINT_BAR_OFS + MAX_WARPS * MAX_STAGES * 8 + 1023) / 1024 * 1024;
+
 __global__ void __launch_bounds__(1024, 1)
 k_dfa_lines_hint(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t nlines,
                  uint32_t linelen, int32_t *__restrict__ rc, int32_t *__restrict__ hint)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    /* plan as for a 256-state byte table */
-    const dfa_smem_plan_t plan = dfa_smem_plan(256, 0, false);
-    load_table(smem, dfa.h256, 65536);
-    load_table(smem + plan.fin_ofs, dfa.fin, align_up(dfa.nstates, 16));
+    load_table260(smem, dfa.h256, 256);
+    load_table(smem + HINT_FIN_OFS, dfa.fin, align_up(dfa.nstates, 16));
     __syncthreads();
 
     const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
     hint_consumer_t cons;
-    cons.tab = smem;
-    cons.fin = smem + plan.fin_ofs;
+    cons.tab_s = (uint32_t) __cvta_generic_to_shared(smem);
+    cons.fin = smem + HINT_FIN_OFS;
     cons.acc = dfa.acc;
     cons.nlines = nlines;
     cons.rc = rc;
     cons.hint = hint;
     tile_pipeline_tma_early<1>(cons, &tmap, nlines, linelen,
-                               smem + plan.stage_ofs + (size_t) warp * 32 * 128,
-                               reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES,
+                               smem + HINT_STAGE_OFS + (size_t) warp * 32 * 128,
+                               reinterpret_cast<uint64_t *>(smem + HINT_BAR_OFS) + warp * MAX_STAGES,
                                (size_t) blockIdx.x * warps_per_block + warp,
                                (size_t) gridDim.x * warps_per_block);
 }
@@ -1114,6 +1135,7 @@ cudaError_t sre_launch_dfa_lines_hint(const sre_dev_dfa_t &dfa, const uint8_t *b
     const dfa_smem_plan_t plan = dfa_smem_plan(256, 0, false);
     const int warps = 32;
     const size_t smem = plan.stage_ofs + (size_t) warps * 32 * 128;
+    const size_t smem_plain = HINT_STAGE_OFS + (size_t) warps * 32 * 128;      /* padded rows */
     CUtensorMap tmap;
     cudaError_t err = make_row_tensor_map(&tmap, buf, nlines, pitch, 128);
     if (err != cudaSuccess) {
@@ -1121,7 +1143,7 @@ cudaError_t sre_launch_dfa_lines_hint(const sre_dev_dfa_t &dfa, const uint8_t *b
     }
     static bool attr_set = false;
     if (!attr_set) {
-        err = cudaFuncSetAttribute(k_dfa_lines_hint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        err = cudaFuncSetAttribute(k_dfa_lines_hint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_plain);
         if (err == cudaSuccess) {
             err = cudaFuncSetAttribute(k_dfa_lines_hint_skip<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int) smem);
@@ -1152,8 +1174,8 @@ cudaError_t sre_launch_dfa_lines_hint(const sre_dev_dfa_t &dfa, const uint8_t *b
         k_dfa_lines_hint_skip<2><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen,
                                                                                pats[0], pats[1], rc, hint);
     } else {
-        k_dfa_lines_hint<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen, rc,
-                                                                      hint);
+        k_dfa_lines_hint<<<(unsigned) grid, warps * 32, smem_plain, stream>>>(dfa, tmap, nlines, (uint32_t) linelen,
+                                                                            rc, hint);
     }
     return cudaGetLastError();
 }
