@@ -423,10 +423,35 @@ int upload(sre_cuda_program_t *cp)
         o_sent = b.add(start_ent.data(), start_ent.size() * sizeof(sre_start_ent_t));
     }
 
-    if (cudaMalloc(&cp->d_blob, b.bytes.size() + 256) != cudaSuccess
-        || cudaMemcpy(cp->d_blob, b.bytes.data(), b.bytes.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+    /* the tables never straddle a 4 GiB boundary: kernels that chase a table through L1/L2
+     * (k_dfa_lines_big) keep the high word of its addresses in a uniform register and do the
+     * per-byte address arithmetic in 32 bits */
     {
-        return fail("uploading program tables failed: %s", cudaGetErrorString(cudaGetLastError()));
+        std::vector<void *> rejected;
+        cudaError_t err = cudaSuccess;
+        for (int attempt = 0; attempt < 8; attempt++) {
+            void *ptr = nullptr;
+            if ((err = cudaMalloc(&ptr, b.bytes.size() + 256)) != cudaSuccess) {
+                break;
+            }
+            const uint64_t lo = reinterpret_cast<uint64_t>(ptr), hi = lo + b.bytes.size() + 255;
+            if ((lo >> 32) == (hi >> 32)) {
+                cp->d_blob = static_cast<uint8_t *>(ptr);
+                break;
+            }
+            rejected.push_back(ptr);
+        }
+        for (void *ptr : rejected) {
+            cudaFree(ptr);
+        }
+        if (err == cudaSuccess && cp->d_blob == nullptr) {
+            return fail("uploading program tables failed: no allocation within one 4 GiB window");
+        }
+        if (err != cudaSuccess
+            || cudaMemcpy(cp->d_blob, b.bytes.data(), b.bytes.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+        {
+            return fail("uploading program tables failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
     }
     uint8_t *base = cp->d_blob;
 

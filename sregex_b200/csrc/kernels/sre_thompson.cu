@@ -394,46 +394,102 @@ k_dfa_lines_hint_skip(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tma
  * input), the class-compressed table is read through L1/L2 (the rows of the few
  * states a line spends its time in stay in L1).  HINT: the restart table of the
  * Pike start hint instead (entry | 0x8000 = "only the .*? thread consumed this
- * byte"), with the hint offset kept per line.  (Serving the start state's row
- * from shared memory was measured slower: 1.7 vs 2.3 TB/s -- a warp with lanes
- * in both kinds of state executes both paths.)
+ * byte"), with the hint offset kept per line.
+ *
+ * What bounds it (ncu, profiles/r02_ncu_summary.txt): the L1/shared DATA PIPE --
+ * l1tex__data_pipe_lsu_wavefronts at 94 % of its peak of one wavefront per cycle
+ * and SM.  Per 32 input bytes (one byte of every lane) the pipe sees one
+ * wavefront for the class look-up and ~2.4 for the table look-up (the lanes of
+ * a warp sit in ~8 different states, i.e. ~11 different 32-byte sectors, of
+ * which L1 serves ~4 per wavefront); the state -> state latency chain (now ONE
+ * 32-bit IMAD + the load) is hidden by the 32 warps.  Measured and rejected:
+ * rows padded to 128 bytes (more distinct lines: 2.13 vs 2.40 TB/s), a table of
+ * 256 column addresses instead of the class bytes (3 instead of 1 wavefront per
+ * class look-up: 2.0 TB/s), the start state's row in shared memory (both paths
+ * execute in a mixed warp: 1.7 TB/s).  On the bench corpus 98.8 % of the
+ * look-ups fall into the 64 states nearest to the start, but serving those from
+ * shared memory only trades sectors for bank conflicts (~2.5 wavefronts either
+ * way).
  */
 template <bool HINT>
 struct big_consumer_t {
-    const uint16_t *tab;        /* global: tcls, or hcls when HINT */
-    const uint8_t  *cls;        /* shared memory */
+    uint32_t        cls_s;      /* shared-window address of the byte-class map [256] */
+    uint32_t        tab_lo, tab_hi; /* the table's address; the high word is that of every address inside
+                                   it (the tables do not straddle a 4 GiB boundary: checked where they
+                                   are uploaded) */
     const uint8_t  *fin;        /* global */
-    uint32_t        ncls, start, acc, s, pos, p0;
+    uint32_t        pitch, start, acc, s, pos, p0;
     size_t          nlines;
     int32_t        *rc, *hint;
 
     __device__ __forceinline__ void begin(size_t) { s = start; pos = 0; p0 = 0; }
-    __device__ __forceinline__ void byte(uint32_t b)
+    /* cls[b].  The class map stays a 256-BYTE table: text bytes then fall into distinct banks, one
+     * wavefront per look-up -- the L1/shared data pipe is what saturates in this kernel
+     * (l1tex__data_pipe_lsu_wavefronts 94 %); a table of 256 words costs ~3 wavefronts (measured:
+     * 2.0 instead of 2.4 TB/s) */
+    __device__ __forceinline__ uint32_t cls(uint32_t b) const
     {
-        const uint32_t e = __ldg(tab + s * ncls + cls[b]);
+        uint32_t c;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c) : "r"(cls_s + b));
+        return c;
+    }
+    /* the state -> state chain is ONE 32-bit multiply-add (row offset + column address) and the
+     * load; the column address does not depend on the state */
+    __device__ __forceinline__ void step(uint32_t c, uint32_t at)
+    {
+        uint64_t a;
+        uint16_t e16;
+        uint32_t col;
+        asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(col) : "r"(c), "r"(tab_lo));
+        const uint32_t lo = s * pitch + col;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(lo), "r"(tab_hi));
+        asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(e16) : "l"(a));
+        const uint32_t e = e16;
         if (HINT) {
             s = e & 0x7fffu;
-            pos++;
-            p0 = (e & 0x8000u) ? pos : p0;
+            p0 = (e & 0x8000u) ? at : p0;
         } else {
             s = e;
         }
     }
+    __device__ __forceinline__ void byte(uint32_t b)
+    {
+        pos++;
+        step(cls(b), pos);
+    }
+    struct cls4_t {
+        uint32_t c0, c1, c2, c3;
+    };
+    __device__ __forceinline__ cls4_t classes(uint32_t w) const
+    {
+        cls4_t r;
+        r.c0 = cls(__byte_perm(w, 0, 0x4440));
+        r.c1 = cls(__byte_perm(w, 0, 0x4441));
+        r.c2 = cls(__byte_perm(w, 0, 0x4442));
+        r.c3 = cls(__byte_perm(w, 0, 0x4443));
+        return r;
+    }
+    __device__ __forceinline__ void word(const cls4_t &c, uint32_t at)
+    {
+        step(c.c0, at + 1);
+        step(c.c1, at + 2);
+        step(c.c2, at + 3);
+        step(c.c3, at + 4);
+    }
     __device__ __forceinline__ void chunk(const uint4 &v)
     {
-        if (s == acc) {
-            /* absorbing: nothing can change any more (and the hint is frozen) */
-            pos += 16;
-            return;
+        if (s != acc) {         /* absorbing: nothing can change any more (and the hint is frozen) */
+            /* the class look-ups of a word are issued before the table chain of the word in front of
+             * it (the asm statements are volatile: their order is the program's) */
+            const cls4_t cx = classes(v.x), cy = classes(v.y);
+            word(cx, pos);
+            const cls4_t cz = classes(v.z);
+            word(cy, pos + 4);
+            const cls4_t cw = classes(v.w);
+            word(cz, pos + 8);
+            word(cw, pos + 12);
         }
-        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                byte((w[i] >> (8 * q)) & 0xff);
-            }
-        }
+        pos += 16;
     }
     __device__ __forceinline__ void end(size_t group)
     {
@@ -453,25 +509,29 @@ k_dfa_lines_big(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, siz
                 int32_t *__restrict__ rc, int32_t *__restrict__ hint)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    /* [cls 256][barriers][stages] */
-    const uint8_t *map = HINT ? dfa.hclsmap : dfa.clsmap;
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
-        smem[i] = map[i];
+    /* [byte-class map 256][barriers][stages] */
+    const uint16_t *tab = HINT ? dfa.hcls : dfa.tcls;
+    {
+        const uint8_t *map = HINT ? dfa.hclsmap : dfa.clsmap;
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+            smem[i] = map[i];
+        }
     }
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
     big_consumer_t<HINT> cons;
-    cons.tab = HINT ? dfa.hcls : dfa.tcls;
-    cons.cls = smem;
+    cons.cls_s = smem_u32(smem);
+    cons.tab_lo = (uint32_t) reinterpret_cast<uint64_t>(tab);
+    cons.tab_hi = (uint32_t) (reinterpret_cast<uint64_t>(tab) >> 32);
+    cons.pitch = 2 * (HINT ? dfa.hncls : dfa.nclasses);
     cons.fin = dfa.fin;
-    cons.ncls = HINT ? dfa.hncls : dfa.nclasses;
     cons.start = dfa.start;
     cons.acc = dfa.acc;
     cons.nlines = nlines;
     cons.rc = rc;
     cons.hint = hint;
     tile_pipeline_tma_early<1>(cons, &tmap, nlines, linelen, smem + 4096 + (size_t) warp * 32 * 128,
-                               reinterpret_cast<uint64_t *>(smem + 256) + warp * MAX_STAGES,
+                               reinterpret_cast<uint64_t *>(smem + 2048) + warp * MAX_STAGES,
                                (size_t) blockIdx.x * warps_per_block + warp, (size_t) gridDim.x * warps_per_block);
 }
 
