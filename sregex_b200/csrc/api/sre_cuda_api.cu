@@ -178,6 +178,7 @@ int upload(sre_cuda_program_t *cp)
     size_t o_t256 = 0, o_tcls = 0, o_dcls = 0, o_fin = 0, o_h256 = 0, o_hcls = 0, o_hmap = 0;
     size_t o_itrans = 0, o_icand = 0, o_incand = 0, o_x256 = 0, o_x256m = 0;
     bool has_x256 = false, has_x256m = false;
+    uint32_t xguess = 0;
 
     cp->has_dfa = cp->low.has_dfa;
     if (cp->has_dfa) {
@@ -224,6 +225,23 @@ int upload(sre_cuda_program_t *cp)
                 }
                 o_x256m = b.add(xm.data(), xm.size());
                 has_x256m = true;
+                /* the state the automaton idles in on ordinary text (k_text_verdicts enters a
+                 * piece with it when a line is open there; a wrong guess only costs time): where
+                 * most printable bytes, repeated, take the start state */
+                uint32_t votes[64] = { 0 };
+                for (unsigned bv = 0x20; bv < 0x7f; bv++) {
+                    uint32_t st = d.start;
+                    for (int k = 0; k < 64; k++) {
+                        st = d.t256[(size_t) st * 256 + bv];
+                    }
+                    votes[st]++;
+                }
+                xguess = d.start;
+                for (uint32_t st = 0; st < d.nstates; st++) {
+                    if (votes[st] > votes[xguess]) {
+                        xguess = st;
+                    }
+                }
             }
         }
         o_tcls = b.add(d.trans.data(), d.trans.size() * 2);
@@ -471,6 +489,7 @@ int upload(sre_cuda_program_t *cp)
         cp->dfa.hncls = d.hncls;
         cp->dfa.x256 = has_x256 ? base + o_x256 : nullptr;
         cp->dfa.x256m = has_x256m ? base + o_x256m : nullptr;
+        cp->dfa.xguess = xguess;
         if (cp->has_image) {
             cp->img.nstates = cp->image.nstates;
             cp->img.nclasses = cp->image.nclasses;

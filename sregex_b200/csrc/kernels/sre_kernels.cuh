@@ -27,6 +27,8 @@ struct sre_dev_dfa_t {
     const uint8_t   *x256;      /* [256][256] text table (sre_text.cu), or NULL: as t256, but '\n' leads to
                                    start | 0x80 when the line that ends there matched */
     const uint8_t   *x256m;     /* the same for <= 64 states, '\n' also sets bit 6 (rows r + 64k alike), or NULL */
+    uint32_t         xguess;    /* the state the automaton idles in on ordinary text: what k_text_verdicts
+                                   enters a piece with when a line is open there (a guess, checked later) */
     const uint16_t  *hcls;      /* [nstates][hncls] next | 0x8000 restart, or NULL */
     const uint8_t   *hclsmap;   /* [256]                                      */
     uint32_t         hncls;

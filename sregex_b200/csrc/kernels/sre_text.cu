@@ -48,10 +48,8 @@ __device__ __forceinline__ uint32_t nl_mask(uint32_t x)
 }
 
 struct text_out_t {
-    uint32_t       *stage;      /* [npieces][CAP] (end offset within the span << 1) | matched; in
-                                   verdict-only mode: the piece-local numbers of the matched lines */
+    uint32_t       *stage;      /* [npieces][CAP] (end offset within the span << 1) | matched */
     uint32_t       *count;      /* [npieces] lines that start in the piece                  */
-    uint32_t       *mcount;     /* [npieces] verdict-only mode: how many of them matched    */
 };
 
 /* does a line start at the first byte of `piece`? */
@@ -96,9 +94,7 @@ __device__ __forceinline__ uint32_t serial_piece(const sre_dev_dfa_t &dfa, const
 /* MARK: the automaton has at most 64 states, and the table marks "this byte was a '\n'" in bit 6
  * of the state (rows r, r+64, r+128, r+192 are the same row): one OR + one test per word
  * replaces the newline search */
-/* ALL: every line end is staged (offsets wanted); else only the matched lines' numbers are, and a
- * word that holds a '\n' but no match just counts it */
-template <bool MARK, bool ALL>
+template <bool MARK>
 struct text_consumer_t {
     const uint8_t      *tab;        /* x256 in shared memory */
     sre_dev_dfa_t       dfa;
@@ -107,7 +103,6 @@ struct text_consumer_t {
     text_out_t          out;
     uint32_t            s, pos;
     uint32_t            cnt;        /* lines recorded; 0xffffffff: the next line end is not ours */
-    uint32_t            mcnt;       /* matched lines recorded (verdict-only mode)               */
     uint32_t           *stage;
 
     __device__ __forceinline__ void begin(size_t group)
@@ -115,7 +110,6 @@ struct text_consumer_t {
         const size_t piece = group * 32 + (threadIdx.x & 31);
         s = dfa.start;
         pos = 0;
-        mcnt = 0;
         cnt = 0xffffffffu;
         stage = out.stage;
         if (piece < npieces) {
@@ -126,15 +120,8 @@ struct text_consumer_t {
     }
     __device__ __forceinline__ void record(uint32_t end_off, uint32_t matched)
     {
-        if (ALL) {
-            if (cnt < CAP) {        /* (not for 0xffffffff: that line began in an earlier piece) */
-                stage[cnt] = (end_off << 1) | matched;
-            }
-        } else if (matched && cnt != 0xffffffffu) {
-            if (mcnt < CAP) {
-                stage[mcnt] = cnt;
-            }
-            mcnt++;
+        if (cnt < CAP) {            /* (not for 0xffffffff: that line began in an earlier piece) */
+            stage[cnt] = (end_off << 1) | matched;
         }
         cnt++;
     }
@@ -147,21 +134,7 @@ struct text_consumer_t {
         s = a3;
         /* the states after each byte are still in registers: a word that holds a '\n' only adds
          * the bookkeeping */
-        if (MARK && !ALL) {
-            /* verdict only: a '\n' without a match (bit 7 is only ever set on a '\n') is counted,
-             * nothing else; 0xffffffff + 1 = 0 takes care of the line end that is not ours */
-            const uint32_t any = a0 | a1 | a2 | a3;
-            if (any & 0x40u) {
-                if (any & 0x80u) {
-                    if (a0 & 0x40u) record(at + 1, a0 >> 7);
-                    if (a1 & 0x40u) record(at + 2, a1 >> 7);
-                    if (a2 & 0x40u) record(at + 3, a2 >> 7);
-                    if (a3 & 0x40u) record(at + 4, a3 >> 7);
-                } else {
-                    cnt += ((a0 >> 6) & 1u) + ((a1 >> 6) & 1u) + ((a2 >> 6) & 1u) + ((a3 >> 6) & 1u);
-                }
-            }
-        } else if (MARK) {
+        if (MARK) {
             if ((a0 | a1 | a2 | a3) & 0x40u) {
                 if (a0 & 0x40u) record(at + 1, a0 >> 7);
                 if (a1 & 0x40u) record(at + 2, a1 >> 7);
@@ -238,13 +211,10 @@ struct text_consumer_t {
             }
         }
         out.count[piece] = cnt == 0xffffffffu ? 0u : cnt;
-        if (!ALL) {
-            out.mcount[piece] = mcnt;
-        }
     }
 };
 
-template <bool MARK, bool ALL>
+template <bool MARK>
 __global__ void __launch_bounds__(1024, 1)
 k_text_pieces(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ buf, size_t len,
               size_t npieces, text_out_t out)
@@ -255,7 +225,7 @@ k_text_pieces(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, const
     __syncthreads();
 
     const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
-    text_consumer_t<MARK, ALL> cons;
+    text_consumer_t<MARK> cons;
     cons.tab = smem;
     cons.dfa = dfa;
     cons.buf = buf;
@@ -270,26 +240,15 @@ k_text_pieces(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, const
 
 /* the ragged tail piece [nfull * PIECE, len): one thread, table from global memory */
 __global__ void k_text_tail(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, size_t piece,
-                            text_out_t out, int all)
+                            text_out_t out)
 {
     uint32_t *stage = out.stage + piece * CAP;
-    uint32_t m = 0;
     out.count[piece] = serial_piece(dfa, buf, len, piece * PIECE, len, starts_line(buf, piece),
                                     [&](uint32_t end_off, uint32_t matched, uint32_t k) {
-                                        if (all) {
-                                            if (k < CAP) {
-                                                stage[k] = (end_off << 1) | matched;
-                                            }
-                                        } else if (matched) {
-                                            if (m < CAP) {
-                                                stage[m] = k;
-                                            }
-                                            m++;
+                                        if (k < CAP) {
+                                            stage[k] = (end_off << 1) | matched;
                                         }
                                     });
-    if (!all) {
-        out.mcount[piece] = m;
-    }
 }
 
 constexpr uint32_t WB = 1024;       /* pieces per block of the scan / write kernels */
@@ -325,11 +284,11 @@ __device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t *total)
 
 /* sums[b] <- lines that start in the WB pieces of block b */
 __global__ void __launch_bounds__(WB)
-k_text_sums(const uint32_t *__restrict__ count, size_t n, unsigned long long *__restrict__ sums)
+k_text_sums(const uint32_t *__restrict__ count, size_t n, unsigned long long *__restrict__ sums, uint32_t mask)
 {
     const size_t i = (size_t) blockIdx.x * WB + threadIdx.x;
     uint32_t total;
-    block_exclusive(i < n ? count[i] : 0u, &total);
+    block_exclusive(i < n ? (count[i] & mask) : 0u, &total);
     if (threadIdx.x == 0) {
         sums[blockIdx.x] = total;
     }
@@ -337,7 +296,7 @@ k_text_sums(const uint32_t *__restrict__ count, size_t n, unsigned long long *__
 
 /* sums[b] <- lines before block b; sums[nb] <- all lines.  One block (nb = pieces / 1024). */
 __global__ void __launch_bounds__(1024)
-k_text_scan(unsigned long long *__restrict__ sums, size_t nb)
+k_text_scan(unsigned long long *__restrict__ sums, size_t nb, unsigned long long *__restrict__ total_out)
 {
     __shared__ unsigned long long carry, part[32];
     if (threadIdx.x == 0) {
@@ -377,6 +336,7 @@ k_text_scan(unsigned long long *__restrict__ sums, size_t nb)
     }
     if (threadIdx.x == 0) {
         sums[nb] = carry;
+        *total_out = carry;
     }
 }
 
@@ -448,7 +408,7 @@ k_text_write(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, siz
     }
 }
 
-/* verdict-only mode: rc[0 .. min(lines, max_lines)) <- SRE_DECLINED */
+/* rc[0 .. min(lines, max_lines)) <- SRE_DECLINED (k_text_apply then marks the matched lines) */
 __global__ void __launch_bounds__(256)
 k_text_fill(const unsigned long long *__restrict__ total, int32_t *__restrict__ rc, size_t max_lines)
 {
@@ -458,20 +418,241 @@ k_text_fill(const unsigned long long *__restrict__ total, int32_t *__restrict__ 
     }
 }
 
-/* ... then rc[line] <- SRE_OK for the staged matched lines; one thread per piece */
+
+/* ==== verdicts only, automata of at most 64 states: the count-only hot loop ==== */
+
+/*
+ * Every newline is numbered by the piece it lies in (line = newlines in the
+ * pieces before + its index in the piece), so a thread never reads past its piece
+ * and never tells "my" line ends from foreign ones.  The hot loop has no branch per
+ * newline: the states after the four bytes of a word are packed into one register
+ * (bit 6 = "this byte was a '\n'", bit 7 = "... and the line matched"), newlines
+ * are counted with one POPC per 16 bytes and only a match bit (rare) leaves the
+ * straight line.
+ *
+ * The line that is open where a piece begins was started by an earlier piece, so
+ * the thread does not know the state it is entered with.  It GUESSES dfa.xguess
+ * (the state the automaton idles in on ordinary text), and the thread of the piece
+ * in front checks the guess when it gets there: exit state == guess -> the
+ * neighbour's run IS the continuation and nothing is left to do; sticky ACC -> the
+ * line matched whatever follows; anything else (a partial match hanging over the
+ * boundary) -> it finishes the line itself, byte by byte, and leaves the verdict as
+ * a correction in its info word, which k_text_apply applies to the first line of
+ * the next piece that holds a newline.  A correct guess is a matter of speed only.
+ */
+constexpr uint32_t INFO_CNT = 0x1fffu;          /* newlines in the piece (<= 4097)            */
+constexpr uint32_t INFO_MSHIFT = 13;            /* matched ones among them                     */
+constexpr uint32_t INFO_FSHIFT = 26;            /* verdict of the line open at the piece's end */
+constexpr uint32_t FIX_NONE = 0, FIX_UNMATCHED = 1, FIX_MATCHED = 2;
+constexpr uint32_t NLBITS = 0x40404040u, MBITS = 0x80808080u;
+
+struct verdict_out_t {
+    uint32_t *info;         /* [nfull + 1] */
+    uint32_t *stage;        /* [nfull + 1][CAP] piece-local numbers of the matched newlines */
+};
+
+struct verdict_consumer_t {
+    const uint8_t      *tab;        /* x256m in shared memory */
+    uint32_t            tab_s;      /* ... its shared-window address */
+    const uint8_t      *buf, *fin;
+    size_t              len, nfull;
+    verdict_out_t       out;
+    uint32_t            start, guess, acc;
+    uint32_t            s, cnt, mcnt;
+    uint32_t           *stage;
+
+    __device__ __forceinline__ void begin(size_t group)
+    {
+        const size_t piece = group * 32 + (threadIdx.x & 31);
+        cnt = 0;
+        mcnt = 0;
+        s = guess;
+        stage = out.stage;
+        if (piece < nfull) {
+            s = starts_line(buf, piece) ? start : guess;
+            stage = out.stage + piece * CAP;
+        }
+    }
+    /* the four bytes of w; -> the states after each of them, one per byte */
+    __device__ __forceinline__ uint32_t word(uint32_t w)
+    {
+        const uint32_t a0 = step260_t::lds_u8(tab_s + __byte_perm(w, s, 0x5540));
+        const uint32_t a1 = step260_t::lds_u8(tab_s + __byte_perm(w, a0, 0x5541));
+        const uint32_t a2 = step260_t::lds_u8(tab_s + __byte_perm(w, a1, 0x5542));
+        const uint32_t a3 = step260_t::lds_u8(tab_s + __byte_perm(w, a2, 0x5543));
+        s = a3;
+        return (a3 * 256u + a2) * 65536u + (a1 * 256u + a0);
+    }
+    /* some line that ends in these 16 bytes matched: stage the numbers of those newlines */
+    __device__ __forceinline__ void matches(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3)
+    {
+        const uint32_t p[4] = { p0, p1, p2, p3 };
+        uint32_t k = cnt;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t e = p[i] >> (8 * q);
+                if (e & 0x40u) {
+                    if (e & 0x80u) {
+                        if (mcnt < CAP) {
+                            stage[mcnt] = k;
+                        }
+                        mcnt++;
+                    }
+                    k++;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void chunk(const uint4 &v)
+    {
+        const uint32_t p0 = word(v.x), p1 = word(v.y), p2 = word(v.z), p3 = word(v.w);
+        if ((p0 | p1 | p2 | p3) & MBITS) {
+            matches(p0, p1, p2, p3);
+        }
+        /* the sixteen newline bits side by side, one POPC */
+        const uint32_t nl = (p0 & NLBITS) | ((p1 >> 1) & (NLBITS >> 1)) | ((p2 >> 2) & (NLBITS >> 2))
+                            | ((p3 >> 3) & (NLBITS >> 3));
+        cnt += __popc(nl);
+    }
+    __device__ __forceinline__ void byte(uint32_t b)
+    {
+        s = tab[(s << 8) | b];
+        if (s & 0x40u) {
+            if (s & 0x80u) {
+                if (mcnt < CAP) {
+                    stage[mcnt] = cnt;
+                }
+                mcnt++;
+            }
+            cnt++;
+        }
+    }
+    __device__ __forceinline__ void end(size_t group)
+    {
+        const size_t piece = group * 32 + (threadIdx.x & 31);
+        if (piece >= nfull) {
+            return;
+        }
+        uint32_t fix = FIX_NONE;
+        const uint32_t st = s & 0x3fu;
+        if (!(s & 0x40u) && st != guess) {
+            /* a line is open here and the next piece's thread did not start from this state */
+            if (st == acc) {
+                fix = FIX_MATCHED;
+            } else {
+                /* a partial match hangs over the boundary: finish the line */
+                size_t p = (piece + 1) * PIECE;
+                uint32_t t = s;
+                for (; p < len; p++) {
+                    t = tab[(t << 8) | __ldg(buf + p)];
+                    if (t & 0x40u) {
+                        break;
+                    }
+                }
+                if (p < len) {
+                    fix = (t & 0x80u) ? FIX_MATCHED : FIX_UNMATCHED;
+                } else {
+                    /* the buffer ended first: the EOF step of the reference decides */
+                    const uint32_t e = t & 0x3fu;
+                    fix = (e == acc || __ldg(fin + e)) ? FIX_MATCHED : FIX_UNMATCHED;
+                }
+            }
+        }
+        out.info[piece] = cnt | (mcnt << INFO_MSHIFT) | (fix << INFO_FSHIFT);
+    }
+};
+
+__global__ void __launch_bounds__(1024, 1)
+k_text_verdicts(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ buf, size_t len,
+                size_t nfull, verdict_out_t out)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const dfa_smem_plan_t plan = dfa_smem_plan(256, 0, false);
+    load_table(smem, dfa.x256m, 65536);
+    __syncthreads();
+
+    const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    verdict_consumer_t cons;
+    cons.tab = smem;
+    cons.tab_s = smem_u32(smem);
+    cons.buf = buf;
+    cons.fin = dfa.fin;
+    cons.len = len;
+    cons.nfull = nfull;
+    cons.out = out;
+    cons.start = dfa.start;
+    cons.guess = dfa.xguess;
+    cons.acc = dfa.acc;
+    tile_pipeline_tma_early<1>(cons, &tmap, nfull, PIECE,
+                               smem + plan.stage_ofs + (size_t) warp * 32 * 128,
+                               reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES,
+                               (size_t) warp * gridDim.x + blockIdx.x, (size_t) gridDim.x * warps_per_block);
+}
+
+/*
+ * The same walk, serially, over the table in global memory: the newlines of
+ * [begin, end), emit(piece-local number) for those that end a matched line.  With
+ * `eof` (the tail piece) a last line without terminator counts as one more newline,
+ * its verdict the reference's EOF step.  -> newlines counted
+ */
+template <class Emit>
+__device__ __forceinline__ uint32_t serial_marks(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t len, size_t begin,
+                                                 size_t end, bool eof, Emit emit)
+{
+    const uint8_t *tx = dfa.x256m;
+    uint32_t s = (begin == 0 || __ldg(buf + begin - 1) == '\n') ? dfa.start : dfa.xguess, n = 0;
+    for (size_t p = begin; p < end; p++) {
+        s = __ldg(tx + ((s << 8) | __ldg(buf + p)));
+        if (s & 0x40u) {
+            if (s & 0x80u) {
+                emit(n);
+            }
+            n++;
+        }
+    }
+    if (eof && len > 0 && __ldg(buf + len - 1) != '\n') {
+        const uint32_t st = s & 0x3fu;
+        if (st == dfa.acc || __ldg(dfa.fin + st)) {
+            emit(n);
+        }
+        n++;
+    }
+    return n;
+}
+
+/* the tail piece [nfull * PIECE, len) (possibly empty) and the end of the buffer: one thread */
+__global__ void k_text_verdicts_tail(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, size_t nfull,
+                                     verdict_out_t out)
+{
+    uint32_t *stage = out.stage + nfull * CAP;
+    uint32_t m = 0;
+    const uint32_t n = serial_marks(dfa, buf, len, nfull * PIECE, len, true, [&](uint32_t k) {
+        if (m < CAP) {
+            stage[m] = k;
+        }
+        m++;
+    });
+    out.info[nfull] = n | (m << INFO_MSHIFT);
+}
+
+/* rc[line] <- SRE_OK for the staged matched lines, then the corrections; one thread per piece
+ * (after k_text_fill) */
 __global__ void __launch_bounds__(WB)
-k_text_scatter(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, size_t npieces, text_out_t out,
-               const unsigned long long *__restrict__ sums, int32_t *__restrict__ rc, size_t max_lines)
+k_text_apply(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, size_t nfull, verdict_out_t out,
+             const unsigned long long *__restrict__ sums, int32_t *__restrict__ rc, size_t max_lines)
 {
     const size_t piece = (size_t) blockIdx.x * WB + threadIdx.x;
-    const uint32_t n = piece < npieces ? out.count[piece] : 0u;
+    const uint32_t info = piece <= nfull ? out.info[piece] : 0u;
+    const uint32_t n = info & INFO_CNT;
     uint32_t total;
     const uint32_t before = block_exclusive(n, &total);
-    if (piece >= npieces) {
+    if (piece > nfull || n == 0) {
         return;
     }
     const size_t first = (size_t) sums[blockIdx.x] + before;
-    const uint32_t m = out.mcount[piece];
+    const uint32_t m = (info >> INFO_MSHIFT) & INFO_CNT;
     if (m <= CAP) {
         const uint32_t *stage = out.stage + piece * CAP;
         for (uint32_t k = 0; k < m; k++) {
@@ -481,13 +662,28 @@ k_text_scatter(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, s
             }
         }
     } else {
-        const size_t begin = piece * PIECE, end = begin + PIECE < len ? begin + PIECE : len;
-        serial_piece(dfa, buf, len, begin, end, starts_line(buf, piece),
-                     [&](uint32_t, uint32_t matched, uint32_t k) {
-                         if (matched && first + k < max_lines) {
-                             rc[first + k] = SRE_K_OK;
-                         }
-                     });
+        const size_t begin = piece * PIECE, end = piece < nfull ? begin + PIECE : len;
+        serial_marks(dfa, buf, len, begin, end, piece == nfull, [&](uint32_t k) {
+            if (first + k < max_lines) {
+                rc[first + k] = SRE_K_OK;
+            }
+        });
+    }
+    /* my first newline ends a line that an earlier piece began: the first correction left by the
+     * pieces from its owner on (the owner = the nearest piece before me that holds a newline or
+     * begins a line; the pieces between are all inside the line) decides; none: the guess held */
+    if (piece > 0 && first < max_lines && !starts_line(buf, piece)) {
+        size_t k = piece - 1;
+        while (k > 0 && (out.info[k] & INFO_CNT) == 0 && !starts_line(buf, k)) {
+            k--;
+        }
+        for (; k < piece; k++) {
+            const uint32_t fix = out.info[k] >> INFO_FSHIFT;
+            if (fix != FIX_NONE) {
+                rc[first] = fix == FIX_MATCHED ? SRE_K_OK : SRE_K_DECLINED;
+                break;
+            }
+        }
     }
 }
 
@@ -496,14 +692,60 @@ k_text_scatter(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, s
 size_t sre_text_workspace_bytes(size_t len)
 {
     const size_t npieces = (len + PIECE - 1) / PIECE + 1, nb = (npieces + WB - 1) / WB;
-    return (nb + 2) * 8 + npieces * (CAP * 4 + 8) + 2048;
+    return 256 + (nb + 2) * 8 + npieces * (CAP * 4 + 8) + 2048;
 }
 
 /* where in the workspace the number of lines is left (8 bytes) */
-size_t sre_text_count_offset(size_t len)
+size_t sre_text_count_offset(size_t)
 {
-    const size_t npieces = len / PIECE + (len % PIECE ? 1 : 0);
-    return (npieces + WB - 1) / WB * 8;
+    return 0;
+}
+
+/* verdicts only, <= 64 states: count-only hot loop (k_text_verdicts) */
+static cudaError_t launch_text_verdicts(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t len, int32_t *rc,
+    size_t max_lines, uint8_t *workspace, cudaStream_t stream, int *launches)
+{
+    const size_t nfull = len / PIECE, npieces = nfull + 1, nb = (npieces + WB - 1) / WB;
+    unsigned long long *total = reinterpret_cast<unsigned long long *>(workspace);
+    unsigned long long *sums = reinterpret_cast<unsigned long long *>(workspace + 256);     /* [nb + 1] */
+    uint8_t *p = workspace + 256 + ((nb + 2) * 8 + 255) / 256 * 256;
+    verdict_out_t out;
+    out.info = reinterpret_cast<uint32_t *>(p);
+    p += (npieces * 4 + 255) / 256 * 256;
+    out.stage = reinterpret_cast<uint32_t *>(p);
+    cudaError_t err;
+    if (nfull) {
+        const dfa_smem_plan_t plan = dfa_smem_plan(256, 0, false);
+        const int warps = 32;
+        const size_t smem = plan.stage_ofs + (size_t) warps * 32 * 128;
+        CUtensorMap tmap;
+        if ((err = make_row_tensor_map(&tmap, buf, nfull, PIECE, 128)) != cudaSuccess) return err;
+        static bool attr_set = false;
+        if (!attr_set) {
+            err = cudaFuncSetAttribute(k_text_verdicts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            if (err != cudaSuccess) return err;
+            attr_set = true;
+        }
+        const size_t ngroups = (nfull + 31) / 32;
+        size_t grid = (size_t) num_sms();
+        const size_t need = (ngroups + warps - 1) / warps;
+        if (grid > need) {
+            grid = need;
+        }
+        if (launches) ++*launches;
+        k_text_verdicts<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, out);
+        if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    }
+    if (launches) *launches += 5;
+    k_text_verdicts_tail<<<1, 1, 0, stream>>>(dfa, buf, len, nfull, out);
+    k_text_sums<<<(unsigned) nb, WB, 0, stream>>>(out.info, npieces, sums, INFO_CNT);
+    k_text_scan<<<1, 1024, 0, stream>>>(sums, nb, total);
+    const size_t most = max_lines < len + 1 ? max_lines : len + 1;
+    size_t fgrid = (most + 255) / 256;
+    fgrid = fgrid > 4096 ? 4096 : fgrid < 1 ? 1 : fgrid;
+    k_text_fill<<<(unsigned) fgrid, 256, 0, stream>>>(total, rc, max_lines);
+    k_text_apply<<<(unsigned) nb, WB, 0, stream>>>(dfa, buf, len, nfull, out, sums, rc, max_lines);
+    return cudaGetLastError();
 }
 
 /* workspace: sre_text_workspace_bytes(len) bytes, 256-byte aligned */
@@ -513,17 +755,17 @@ cudaError_t sre_launch_text(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t
     if (dfa.x256 == nullptr || (reinterpret_cast<uintptr_t>(buf) & 15)) {
         return cudaErrorInvalidValue;
     }
+    if (offsets == nullptr && dfa.x256m != nullptr) {
+        return launch_text_verdicts(dfa, buf, len, rc, max_lines, workspace, stream, launches);
+    }
     const size_t nfull = len / PIECE, npieces = nfull + (len % PIECE ? 1 : 0), nb = (npieces + WB - 1) / WB;
-    unsigned long long *sums = reinterpret_cast<unsigned long long *>(workspace);   /* [nb + 1] */
-    uint8_t *p = workspace + ((nb + 2) * 8 + 255) / 256 * 256;
+    unsigned long long *total = reinterpret_cast<unsigned long long *>(workspace);
+    unsigned long long *sums = reinterpret_cast<unsigned long long *>(workspace + 256);     /* [nb + 1] */
+    uint8_t *p = workspace + 256 + ((nb + 2) * 8 + 255) / 256 * 256;
     text_out_t out;
     out.count = reinterpret_cast<uint32_t *>(p);
     p += (npieces * 4 + 255) / 256 * 256 + 256;
-    out.mcount = reinterpret_cast<uint32_t *>(p);
-    p += (npieces * 4 + 255) / 256 * 256 + 256;
     out.stage = reinterpret_cast<uint32_t *>(p);
-    /* every line end staged when the offsets are wanted; else (small automata) only the matches */
-    const bool all = offsets != nullptr || dfa.x256m == nullptr;
     cudaError_t err;
     if (npieces == 0) {
         if ((err = cudaMemsetAsync(workspace, 0, 8, stream)) != cudaSuccess) return err;
@@ -537,14 +779,9 @@ cudaError_t sre_launch_text(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t
         if ((err = make_row_tensor_map(&tmap, buf, nfull, PIECE, 128)) != cudaSuccess) return err;
         static bool attr_set = false;
         if (!attr_set) {
-            err = cudaFuncSetAttribute(k_text_pieces<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int) smem);
+            err = cudaFuncSetAttribute(k_text_pieces<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
             if (err == cudaSuccess) {
-                err = cudaFuncSetAttribute(k_text_pieces<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int) smem);
-            }
-            if (err == cudaSuccess) {
-                err = cudaFuncSetAttribute(k_text_pieces<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                err = cudaFuncSetAttribute(k_text_pieces<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int) smem);
             }
             if (err != cudaSuccess) return err;
@@ -557,31 +794,21 @@ cudaError_t sre_launch_text(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t
             grid = need;
         }
         if (launches) ++*launches;
-        if (!all) {
-            k_text_pieces<true, false><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, out);
-        } else if (dfa.x256m != nullptr) {
-            k_text_pieces<true, true><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, out);
+        if (dfa.x256m != nullptr) {
+            k_text_pieces<true><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, out);
         } else {
-            k_text_pieces<false, true><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, out);
+            k_text_pieces<false><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, out);
         }
         if ((err = cudaGetLastError()) != cudaSuccess) return err;
     }
     if (npieces > nfull) {
         if (launches) ++*launches;
-        k_text_tail<<<1, 1, 0, stream>>>(dfa, buf, len, nfull, out, all ? 1 : 0);
+        k_text_tail<<<1, 1, 0, stream>>>(dfa, buf, len, nfull, out);
         if ((err = cudaGetLastError()) != cudaSuccess) return err;
     }
-    if (launches) *launches += all ? 3 : 4;
-    k_text_sums<<<(unsigned) nb, WB, 0, stream>>>(out.count, npieces, sums);
-    k_text_scan<<<1, 1024, 0, stream>>>(sums, nb);
-    if (all) {
-        k_text_write<<<(unsigned) nb, WB, 0, stream>>>(dfa, buf, len, npieces, out, sums, rc, offsets, max_lines);
-    } else {
-        const size_t most = max_lines < len + 1 ? max_lines : len + 1;
-        size_t fgrid = (most + 255) / 256;
-        fgrid = fgrid > 4096 ? 4096 : fgrid < 1 ? 1 : fgrid;
-        k_text_fill<<<(unsigned) fgrid, 256, 0, stream>>>(sums + nb, rc, max_lines);
-        k_text_scatter<<<(unsigned) nb, WB, 0, stream>>>(dfa, buf, len, npieces, out, sums, rc, max_lines);
-    }
+    if (launches) *launches += 3;
+    k_text_sums<<<(unsigned) nb, WB, 0, stream>>>(out.count, npieces, sums, 0xffffffffu);
+    k_text_scan<<<1, 1024, 0, stream>>>(sums, nb, total);
+    k_text_write<<<(unsigned) nb, WB, 0, stream>>>(dfa, buf, len, npieces, out, sums, rc, offsets, max_lines);
     return cudaGetLastError();
 }

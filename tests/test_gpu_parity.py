@@ -861,6 +861,36 @@ def test_text_grep_one_pass_vs_oracle(cu):
                 # too small an output: the count is still reported, the prefix is right
                 rc2, off2 = prog.thompson_text(dev, len(data), max_lines=100)
                 assert torch.equal(rc2, rc[:100]) and torch.equal(off2, off[:101])
+    # lines that end exactly at piece boundaries (4 KB) or one byte off, every line matching (more
+    # matched lines per piece than the staging holds), partial matches hanging over piece boundaries,
+    # very long lines spanning several pieces with a match before / after / across the boundaries
+    hit = b'HTTP/1.1" 503 '
+    cases = {
+        "piece-aligned": b"".join((b"a" * (4095 - len(hit)) + hit + b"\n") if i % 3 else (b"b" * 4095 + b"\n")
+                                  for i in range(40)),
+        "off-by-one": b"".join(b"c" * int(n) + b"\n" for n in [4094, 4096, 0, 4095, 8191, 1, 4097, 12287, 5]),
+        "all-match": (b"x" + hit + b"\n") * 3000,
+        "straddle": b"".join(b"z" * int(4096 * (1 + i % 3) - 20 - k) + hit + b"q" * 3 + b"\n"
+                             for i, k in enumerate(range(0, 30))),
+        "long": b"".join(b"y" * 9000 + (hit if i % 2 else b"") + b"w" * 7000 + b"\n" for i in range(12))
+                + b"tail without newline " + hit,
+    }
+    for name, data in cases.items():
+        host = np.frombuffer(data, dtype=np.uint8)
+        dev = torch.from_numpy(np.concatenate([host, np.zeros(16, np.uint8)])).cuda()
+        lines = data.split(b"\n")
+        if lines[-1] == b"":
+            lines.pop()
+        for rx in (corpus.C2_REGEX, rb"^[a-z]+HTTP", rb"5\d\d q*$", rb"[xz]+H"):
+            prog = cu.CudaProgram(rx)
+            po = oracle.compile(rx, 0)
+            want = np.array([oracle.thompson(po, ln + b"\n") for ln in lines[:-1]]
+                            + [oracle.thompson(po, lines[-1] + (b"\n" if data.endswith(b"\n") else b""))])
+            po.close()
+            rc_only, _ = prog.thompson_text(dev, len(data), want_offsets=False)
+            assert np.array_equal(rc_only.cpu().numpy(), want), (name, rx)
+            rc, _ = prog.thompson_text(dev, len(data))
+            assert np.array_equal(rc.cpu().numpy(), want), (name, rx)
     # empty buffer, and a buffer that is a single unterminated line
     prog = cu.CudaProgram(corpus.C2_REGEX)
     rc, off = prog.thompson_text(torch.zeros(16, dtype=torch.uint8, device="cuda"), 0)
