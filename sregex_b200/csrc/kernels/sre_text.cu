@@ -31,6 +31,8 @@
  * Line i = buf[offsets[i], offsets[i+1]) includes its terminator, as for
  * sre_cuda_index_lines; a last line without '\n' ends at len.
  */
+#include <cstdlib>
+
 #include "sre_device_common.cuh"
 
 using namespace sre_dev;
@@ -38,6 +40,7 @@ using namespace sre_dev;
 namespace {
 
 constexpr uint32_t PIECE = 4096;
+constexpr uint32_t MIN_PIECE = 2048;    /* smallest piece the verdict path can be told to cut (text_piece_bytes) */
 constexpr uint32_t CAP = 64;            /* staged lines per piece */
 
 /* bit 7 of every byte of x that equals '\n' (exact: no carry between bytes) */
@@ -452,12 +455,13 @@ struct verdict_out_t {
 };
 
 struct verdict_consumer_t {
-    const uint8_t      *tab;        /* x256m in shared memory */
-    uint32_t            tab_s;      /* ... its shared-window address */
+    uint32_t            tab_s;      /* x256m in shared memory, rows padded to ROW260 bytes (row v starts v
+                                       banks further on: lanes in different states do not collide on the
+                                       bank of the byte they read); shared-window address, low byte 0 */
     const uint8_t      *buf, *fin;
     size_t              len, nfull;
     verdict_out_t       out;
-    uint32_t            start, guess, acc;
+    uint32_t            piece_bytes, start, guess, acc;
     uint32_t            s, cnt, mcnt;
     uint32_t           *stage;
 
@@ -469,17 +473,24 @@ struct verdict_consumer_t {
         s = guess;
         stage = out.stage;
         if (piece < nfull) {
-            s = starts_line(buf, piece) ? start : guess;
+            s = (piece == 0 || __ldg(buf + piece * piece_bytes - 1) == '\n') ? start : guess;
             stage = out.stage + piece * CAP;
         }
     }
-    /* the four bytes of w; -> the states after each of them, one per byte */
+    __device__ __forceinline__ uint32_t look(uint32_t state, uint32_t b) const
+    {
+        return step260_t::lds_u8(state * ROW260 + tab_s + b);
+    }
+    /* the four bytes of w; -> the states after each of them, one per byte.  The byte's address in
+     * row 0 (PRMT, off the chain) leaves one IMAD + one LDS per byte on the state -> state chain. */
     __device__ __forceinline__ uint32_t word(uint32_t w)
     {
-        const uint32_t a0 = step260_t::lds_u8(tab_s + __byte_perm(w, s, 0x5540));
-        const uint32_t a1 = step260_t::lds_u8(tab_s + __byte_perm(w, a0, 0x5541));
-        const uint32_t a2 = step260_t::lds_u8(tab_s + __byte_perm(w, a1, 0x5542));
-        const uint32_t a3 = step260_t::lds_u8(tab_s + __byte_perm(w, a2, 0x5543));
+        const uint32_t b0 = __byte_perm(w, tab_s, 0x7650), b1 = __byte_perm(w, tab_s, 0x7651);
+        const uint32_t b2 = __byte_perm(w, tab_s, 0x7652), b3 = __byte_perm(w, tab_s, 0x7653);
+        const uint32_t a0 = step260_t::lds_u8(s * ROW260 + b0);
+        const uint32_t a1 = step260_t::lds_u8(a0 * ROW260 + b1);
+        const uint32_t a2 = step260_t::lds_u8(a1 * ROW260 + b2);
+        const uint32_t a3 = step260_t::lds_u8(a2 * ROW260 + b3);
         s = a3;
         return (a3 * 256u + a2) * 65536u + (a1 * 256u + a0);
     }
@@ -518,7 +529,7 @@ struct verdict_consumer_t {
     }
     __device__ __forceinline__ void byte(uint32_t b)
     {
-        s = tab[(s << 8) | b];
+        s = look(s, b);
         if (s & 0x40u) {
             if (s & 0x80u) {
                 if (mcnt < CAP) {
@@ -543,10 +554,10 @@ struct verdict_consumer_t {
                 fix = FIX_MATCHED;
             } else {
                 /* a partial match hangs over the boundary: finish the line */
-                size_t p = (piece + 1) * PIECE;
+                size_t p = (piece + 1) * piece_bytes;
                 uint32_t t = s;
                 for (; p < len; p++) {
-                    t = tab[(t << 8) | __ldg(buf + p)];
+                    t = look(t, __ldg(buf + p));
                     if (t & 0x40u) {
                         break;
                     }
@@ -564,30 +575,32 @@ struct verdict_consumer_t {
     }
 };
 
+/* shared memory: [table 256 x ROW260][barriers][stages] */
+constexpr size_t VTAB_BYTES = align_up((size_t) 256 * ROW260, 1024);
+constexpr size_t VBAR_OFS = VTAB_BYTES, VSTAGE_OFS = VTAB_BYTES + 2048;
+
 __global__ void __launch_bounds__(1024, 1)
 k_text_verdicts(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ buf, size_t len,
-                size_t nfull, verdict_out_t out)
+                size_t nfull, uint32_t piece_bytes, verdict_out_t out)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const dfa_smem_plan_t plan = dfa_smem_plan(256, 0, false);
-    load_table(smem, dfa.x256m, 65536);
+    load_table260(smem, dfa.x256m, 256);
     __syncthreads();
 
     const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
     verdict_consumer_t cons;
-    cons.tab = smem;
     cons.tab_s = smem_u32(smem);
     cons.buf = buf;
     cons.fin = dfa.fin;
     cons.len = len;
     cons.nfull = nfull;
     cons.out = out;
+    cons.piece_bytes = piece_bytes;
     cons.start = dfa.start;
     cons.guess = dfa.xguess;
     cons.acc = dfa.acc;
-    tile_pipeline_tma_early<1>(cons, &tmap, nfull, PIECE,
-                               smem + plan.stage_ofs + (size_t) warp * 32 * 128,
-                               reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES,
+    tile_pipeline_tma_early<1>(cons, &tmap, nfull, piece_bytes, smem + VSTAGE_OFS + (size_t) warp * 32 * 128,
+                               reinterpret_cast<uint64_t *>(smem + VBAR_OFS) + warp * MAX_STAGES,
                                (size_t) warp * gridDim.x + blockIdx.x, (size_t) gridDim.x * warps_per_block);
 }
 
@@ -624,11 +637,11 @@ __device__ __forceinline__ uint32_t serial_marks(const sre_dev_dfa_t &dfa, const
 
 /* the tail piece [nfull * PIECE, len) (possibly empty) and the end of the buffer: one thread */
 __global__ void k_text_verdicts_tail(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, size_t nfull,
-                                     verdict_out_t out)
+                                     uint32_t piece_bytes, verdict_out_t out)
 {
     uint32_t *stage = out.stage + nfull * CAP;
     uint32_t m = 0;
-    const uint32_t n = serial_marks(dfa, buf, len, nfull * PIECE, len, true, [&](uint32_t k) {
+    const uint32_t n = serial_marks(dfa, buf, len, nfull * piece_bytes, len, true, [&](uint32_t k) {
         if (m < CAP) {
             stage[m] = k;
         }
@@ -640,9 +653,11 @@ __global__ void k_text_verdicts_tail(sre_dev_dfa_t dfa, const uint8_t *__restric
 /* rc[line] <- SRE_OK for the staged matched lines, then the corrections; one thread per piece
  * (after k_text_fill) */
 __global__ void __launch_bounds__(WB)
-k_text_apply(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, size_t nfull, verdict_out_t out,
-             const unsigned long long *__restrict__ sums, int32_t *__restrict__ rc, size_t max_lines)
+k_text_apply(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, size_t nfull, uint32_t piece_bytes,
+             verdict_out_t out, const unsigned long long *__restrict__ sums, int32_t *__restrict__ rc,
+             size_t max_lines)
 {
+    auto begins_line = [&](size_t pc) { return pc == 0 || __ldg(buf + pc * piece_bytes - 1) == '\n'; };
     const size_t piece = (size_t) blockIdx.x * WB + threadIdx.x;
     const uint32_t info = piece <= nfull ? out.info[piece] : 0u;
     const uint32_t n = info & INFO_CNT;
@@ -662,7 +677,7 @@ k_text_apply(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, siz
             }
         }
     } else {
-        const size_t begin = piece * PIECE, end = piece < nfull ? begin + PIECE : len;
+        const size_t begin = piece * piece_bytes, end = piece < nfull ? begin + piece_bytes : len;
         serial_marks(dfa, buf, len, begin, end, piece == nfull, [&](uint32_t k) {
             if (first + k < max_lines) {
                 rc[first + k] = SRE_K_OK;
@@ -672,9 +687,9 @@ k_text_apply(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, siz
     /* my first newline ends a line that an earlier piece began: the first correction left by the
      * pieces from its owner on (the owner = the nearest piece before me that holds a newline or
      * begins a line; the pieces between are all inside the line) decides; none: the guess held */
-    if (piece > 0 && first < max_lines && !starts_line(buf, piece)) {
+    if (piece > 0 && first < max_lines && !begins_line(piece)) {
         size_t k = piece - 1;
-        while (k > 0 && (out.info[k] & INFO_CNT) == 0 && !starts_line(buf, k)) {
+        while (k > 0 && (out.info[k] & INFO_CNT) == 0 && !begins_line(k)) {
             k--;
         }
         for (; k < piece; k++) {
@@ -691,7 +706,8 @@ k_text_apply(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, siz
 
 size_t sre_text_workspace_bytes(size_t len)
 {
-    const size_t npieces = (len + PIECE - 1) / PIECE + 1, nb = (npieces + WB - 1) / WB;
+    /* (the verdict path may cut pieces as small as MIN_PIECE) */
+    const size_t npieces = len / MIN_PIECE + 2, nb = (npieces + WB - 1) / WB;
     return 256 + (nb + 2) * 8 + npieces * (CAP * 4 + 8) + 2048;
 }
 
@@ -701,11 +717,33 @@ size_t sre_text_count_offset(size_t)
     return 0;
 }
 
+/*
+ * The piece size of the verdict path: PIECE, or SRE_CUDA_TEXT_PIECE (a multiple of 128 in
+ * [MIN_PIECE, PIECE]; tests run the boundary cases at several sizes).  Fitting the size to the
+ * input so that the pieces fill the resident warps in equal rounds (1 GiB in 4 KB pieces is 1.73
+ * rounds of 148 x 32 warps; 3584-byte pieces make it 1.98) was measured SLOWER, 3.0 vs 3.4 TB/s:
+ * the kernel is bound by the shared-memory pipe, not by latency, so a thinner last round simply
+ * runs faster, and smaller pieces only add per-piece work.
+ */
+static uint32_t text_piece_bytes()
+{
+    const char *e = getenv("SRE_CUDA_TEXT_PIECE");
+    if (e != nullptr) {
+        const long v = atol(e);
+        if (v >= (long) MIN_PIECE && v <= (long) PIECE && v % 128 == 0) {
+            return (uint32_t) v;
+        }
+    }
+    return PIECE;
+}
+
 /* verdicts only, <= 64 states: count-only hot loop (k_text_verdicts) */
 static cudaError_t launch_text_verdicts(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t len, int32_t *rc,
     size_t max_lines, uint8_t *workspace, cudaStream_t stream, int *launches)
 {
-    const size_t nfull = len / PIECE, npieces = nfull + 1, nb = (npieces + WB - 1) / WB;
+    const int warps = 32;
+    const uint32_t piece = text_piece_bytes();
+    const size_t nfull = len / piece, npieces = nfull + 1, nb = (npieces + WB - 1) / WB;
     unsigned long long *total = reinterpret_cast<unsigned long long *>(workspace);
     unsigned long long *sums = reinterpret_cast<unsigned long long *>(workspace + 256);     /* [nb + 1] */
     uint8_t *p = workspace + 256 + ((nb + 2) * 8 + 255) / 256 * 256;
@@ -715,11 +753,9 @@ static cudaError_t launch_text_verdicts(const sre_dev_dfa_t &dfa, const uint8_t 
     out.stage = reinterpret_cast<uint32_t *>(p);
     cudaError_t err;
     if (nfull) {
-        const dfa_smem_plan_t plan = dfa_smem_plan(256, 0, false);
-        const int warps = 32;
-        const size_t smem = plan.stage_ofs + (size_t) warps * 32 * 128;
+        const size_t smem = VSTAGE_OFS + (size_t) warps * 32 * 128;
         CUtensorMap tmap;
-        if ((err = make_row_tensor_map(&tmap, buf, nfull, PIECE, 128)) != cudaSuccess) return err;
+        if ((err = make_row_tensor_map(&tmap, buf, nfull, piece, 128)) != cudaSuccess) return err;
         static bool attr_set = false;
         if (!attr_set) {
             err = cudaFuncSetAttribute(k_text_verdicts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
@@ -733,18 +769,18 @@ static cudaError_t launch_text_verdicts(const sre_dev_dfa_t &dfa, const uint8_t 
             grid = need;
         }
         if (launches) ++*launches;
-        k_text_verdicts<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, out);
+        k_text_verdicts<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, piece, out);
         if ((err = cudaGetLastError()) != cudaSuccess) return err;
     }
     if (launches) *launches += 5;
-    k_text_verdicts_tail<<<1, 1, 0, stream>>>(dfa, buf, len, nfull, out);
+    k_text_verdicts_tail<<<1, 1, 0, stream>>>(dfa, buf, len, nfull, piece, out);
     k_text_sums<<<(unsigned) nb, WB, 0, stream>>>(out.info, npieces, sums, INFO_CNT);
     k_text_scan<<<1, 1024, 0, stream>>>(sums, nb, total);
     const size_t most = max_lines < len + 1 ? max_lines : len + 1;
     size_t fgrid = (most + 255) / 256;
     fgrid = fgrid > 4096 ? 4096 : fgrid < 1 ? 1 : fgrid;
     k_text_fill<<<(unsigned) fgrid, 256, 0, stream>>>(total, rc, max_lines);
-    k_text_apply<<<(unsigned) nb, WB, 0, stream>>>(dfa, buf, len, nfull, out, sums, rc, max_lines);
+    k_text_apply<<<(unsigned) nb, WB, 0, stream>>>(dfa, buf, len, nfull, piece, out, sums, rc, max_lines);
     return cudaGetLastError();
 }
 

@@ -1,5 +1,7 @@
 """GPU parity tests proper: libsregex_cuda (through its C ABI) against the
 reference's golden vectors and against the CPU oracle on seeded inputs."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -887,8 +889,14 @@ def test_text_grep_one_pass_vs_oracle(cu):
             want = np.array([oracle.thompson(po, ln + b"\n") for ln in lines[:-1]]
                             + [oracle.thompson(po, lines[-1] + (b"\n" if data.endswith(b"\n") else b""))])
             po.close()
-            rc_only, _ = prog.thompson_text(dev, len(data), want_offsets=False)
-            assert np.array_equal(rc_only.cpu().numpy(), want), (name, rx)
+            # (the verdict path fits its piece size to the input; force a few, the default last)
+            for piece in ("2048", "2176", "3584", "4096", None):
+                if piece is None:
+                    os.environ.pop("SRE_CUDA_TEXT_PIECE", None)
+                else:
+                    os.environ["SRE_CUDA_TEXT_PIECE"] = piece
+                rc_only, _ = prog.thompson_text(dev, len(data), want_offsets=False)
+                assert np.array_equal(rc_only.cpu().numpy(), want), (name, rx, piece)
             rc, _ = prog.thompson_text(dev, len(data))
             assert np.array_equal(rc.cpu().numpy(), want), (name, rx)
     # empty buffer, and a buffer that is a single unterminated line
