@@ -679,7 +679,7 @@ int thompson_dispatch(sre_cuda_program_t *cp, const uint8_t *dev_buf, const int6
              * through L1/L2 */
             launches = 0;
             err = linelen >= 128 ? sre_launch_dfa_lines_big(cp->dfa, dev_buf, nlines, pitch, linelen, dev_rc, nullptr,
-                                                            variant, st, &launches)
+                                                            nullptr, nullptr, variant, st, &launches)
                                  : sre_launch_dfa_ragged(cp->dfa, dev_buf, dev_offsets, nlines, pitch, linelen,
                                                          dev_rc, st, &launches);
         }
@@ -1118,16 +1118,32 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
     const bool aligned = dev_offsets == nullptr && (reinterpret_cast<uintptr_t>(dev_buf) & 15) == 0
                          && (pitch & 15) == 0 && linelen <= pitch && linelen < (1ull << 31);
     const bool tiled_hint = cp->has_dfa && cp->dfa.h256 != nullptr && aligned;
+    /* packed list of the lines to run + its count (behind the gate and the hints) */
+    if (nlines > 0xffffffffull) {
+        return fail("too many lines for one call");
+    }
+    uint32_t *list = reinterpret_cast<uint32_t *>(line_ws.p + 2 * half);
+    uint32_t *count = reinterpret_cast<uint32_t *>(line_ws.p + 3 * half);
+    bool packed = false;        /* the gate kernel packed the list itself */
     if (tiled_hint || (cp->has_dfa && cp->dfa.hcls != nullptr)) {
         int32_t *gate = reinterpret_cast<int32_t *>(line_ws.p);
         int32_t *hint = reinterpret_cast<int32_t *>(line_ws.p + half);
+        /* our own gate on tiled lines: the verdicts go straight to dev_rc (final for the lines that
+         * do not match) and the kernel appends the matching lines to the list as it goes */
+        const bool tiled = tiled_hint || (aligned && linelen >= 128);
+        packed = tiled && dev_select == nullptr;
+        if (packed) {
+            CUDA_TRY(cudaMemsetAsync(count, 0, 4, st));
+            gate = dev_rc;
+        }
         cudaError_t e = tiled_hint
             ? sre_launch_dfa_lines_hint(cp->dfa, dev_buf, nlines, pitch, linelen, gate, hint,
                                         (cp->nleave >= 1 && cp->nleave <= 2 && linelen >= 128) ? cp->leave_pats
                                                                                                 : nullptr,
-                                        cp->nleave, st, &launches)
+                                        cp->nleave, packed ? list : nullptr, count, st, &launches)
             : (aligned && linelen >= 128)
-            ? sre_launch_dfa_lines_big(cp->dfa, dev_buf, nlines, pitch, linelen, gate, hint, 0, st, &launches)
+            ? sre_launch_dfa_lines_big(cp->dfa, dev_buf, nlines, pitch, linelen, gate, hint,
+                                       packed ? list : nullptr, count, 0, st, &launches)
             : sre_launch_dfa_generic_hint(cp->dfa, dev_buf, dev_offsets, nlines, pitch, linelen, gate, hint, st,
                                           &launches);
         if (e != cudaSuccess) {
@@ -1147,19 +1163,16 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
      * (rc from the gate, ovector all -1 = all 0xff bytes) */
     sre_line_list_t lines = { nullptr, nullptr };
     if (dev_select != nullptr) {
-        if (nlines > 0xffffffffull) {
-            return fail("too many lines for one call");
-        }
-        uint32_t *list = reinterpret_cast<uint32_t *>(line_ws.p + 2 * half);
-        uint32_t *count = reinterpret_cast<uint32_t *>(line_ws.p + 3 * half);
-        CUDA_TRY(cudaMemsetAsync(count, 0, 4, st));
         if (dev_ovec != nullptr && ovec_slots != 0) {
             CUDA_TRY(cudaMemsetAsync(dev_ovec, 0xff, nlines * ovec_slots * sizeof(int64_t), st));
         }
-        err = sre_launch_pike_compact(dev_select, nlines, dev_rc, list, count, st, &launches);
-        if (err != cudaSuccess) {
-            count_launches(launches);
-            return fail("compaction kernel launch failed: %s", cudaGetErrorString(err));
+        if (!packed) {
+            CUDA_TRY(cudaMemsetAsync(count, 0, 4, st));
+            err = sre_launch_pike_compact(dev_select, nlines, dev_rc, list, count, st, &launches);
+            if (err != cudaSuccess) {
+                count_launches(launches);
+                return fail("compaction kernel launch failed: %s", cudaGetErrorString(err));
+            }
         }
         lines.list = list;
         lines.count = count;

@@ -184,6 +184,25 @@ k_dfa_lines_skipw(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, s
                                (size_t) blockIdx.x * warps_per_block + warp, (size_t) gridDim.x * warps_per_block);
 }
 
+/* the lines the gate lets through, appended to the packed list the Pike kernels work from (warp-
+ * aggregated; the order is irrelevant) -- called by all 32 lanes */
+__device__ __forceinline__ void append_line(bool take, size_t line, uint32_t *list, uint32_t *count)
+{
+    const uint32_t m = __ballot_sync(FULL, take);
+    if (m == 0) {
+        return;
+    }
+    const uint32_t lane = threadIdx.x & 31, leader = (uint32_t) __ffs((int) m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) {
+        base = atomicAdd(count, (uint32_t) __popc(m));
+    }
+    base = __shfl_sync(FULL, base, leader);
+    if (take) {
+        list[base + __popc(m & ((1u << lane) - 1))] = (uint32_t) line;
+    }
+}
+
 /* ---- k_dfa_lines_hint ------------------------------------------------------ */
 
 /*
@@ -195,59 +214,68 @@ k_dfa_lines_skipw(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, s
  * exact by the automaton instead of a thread-list comparison.
  */
 struct hint_consumer_t {
-    uint32_t        tab_s;      /* h256 in shared memory, rows of ROW260 bytes (shared-window address) */
+    uint32_t        tab_s;      /* h256 in shared memory, rows of ROW260 bytes (shared-window address,
+                                   low byte 0) */
     const uint8_t  *fin;
-    uint32_t        acc, s, pos, p0;
+    uint32_t        acc, s, pos;
+    uint32_t        fw, fpos;   /* restart flags of the last word that had any, offset just after it */
     size_t          nlines;
     int32_t        *rc, *hint;
+    uint32_t       *list, *count;   /* packed list of the matching lines, or NULL */
 
-    __device__ __forceinline__ void begin(size_t) { s = 0; pos = 0; p0 = 0; }
+    __device__ __forceinline__ void begin(size_t) { s = 0; pos = 0; fw = 0; fpos = 0; }
     /*
      * A word at a time.  The rows are padded to 260 bytes (ncu, round 2: with 256-byte rows 42 %
      * of this kernel's shared-memory wavefronts were bank conflicts -- lanes in different states
      * reading bytes of the same 4-byte group -- and the pipe was 91 % busy); the byte's address
-     * within row 0 is computed off the state chain (one IMAD + one LDS per byte on it).  The four
-     * states are packed into one register and the restart flags tested together: the last
-     * flagged byte of the word moves the hint.
+     * within row 0 is one PRMT off the state chain (one IMAD + one LDS per byte on it).  The four
+     * states are packed into one register (IMADs: the fma pipe is the idle one) and the restart
+     * flags tested together; a word that has any is remembered with two predicated moves, and
+     * the hint is worked out of it once, at the end of the line.
      */
-    __device__ __forceinline__ void word(uint32_t w)
+    __device__ __forceinline__ void word(uint32_t w, uint32_t after)
     {
-        step260_t st = { tab_s };
-        const uint32_t b0 = st.row0(__byte_perm(w, 0, 0x4440)), b1 = st.row0(__byte_perm(w, 0, 0x4441));
-        const uint32_t b2 = st.row0(__byte_perm(w, 0, 0x4442)), b3 = st.row0(__byte_perm(w, 0, 0x4443));
+        const uint32_t b0 = __byte_perm(w, tab_s, 0x7650), b1 = __byte_perm(w, tab_s, 0x7651);
+        const uint32_t b2 = __byte_perm(w, tab_s, 0x7652), b3 = __byte_perm(w, tab_s, 0x7653);
         const uint32_t a0 = step260_t::lds_u8(s * ROW260 + b0);
         const uint32_t a1 = step260_t::lds_u8(a0 * ROW260 + b1);
         const uint32_t a2 = step260_t::lds_u8(a1 * ROW260 + b2);
         const uint32_t a3 = step260_t::lds_u8(a2 * ROW260 + b3);
         s = a3;
-        const uint32_t m = __byte_perm(__byte_perm(a0, a1, 0x0040), __byte_perm(a2, a3, 0x0040), 0x5410) & 0x80808080u;
-        if (m) {
-            p0 = pos + 4 - ((uint32_t) __clz((int) m) >> 3);
-        }
-        pos += 4;
+        const uint32_t m = ((a3 * 256u + a2) * 65536u + (a1 * 256u + a0)) & 0x80808080u;
+        fw = m ? m : fw;
+        fpos = m ? after : fpos;
     }
     __device__ __forceinline__ void chunk(const uint4 &v)
     {
-        word(v.x);
-        word(v.y);
-        word(v.z);
-        word(v.w);
+        word(v.x, pos + 4);
+        word(v.y, pos + 8);
+        word(v.z, pos + 12);
+        word(v.w, pos + 16);
+        pos += 16;
     }
     __device__ __forceinline__ void byte(uint32_t b)
     {
         s = step260_t::lds_u8(s * ROW260 + tab_s + b);
         pos++;
         if (s & 0x80) {
-            p0 = pos;
+            fw = 0x80000000u;
+            fpos = pos;
         }
     }
     __device__ __forceinline__ void end(size_t group)
     {
         const size_t line = group * 32 + (threadIdx.x & 31);
+        bool ok = false;
         if (line < nlines) {
             const uint32_t st = s & 0x7f;
-            rc[line] = (st == acc || fin[st]) ? SRE_K_OK : SRE_K_DECLINED;
-            hint[line] = (int32_t) p0;
+            ok = st == acc || fin[st];
+            rc[line] = ok ? SRE_K_OK : SRE_K_DECLINED;
+            /* just after the last flagged byte of that word */
+            hint[line] = fw ? (int32_t) (fpos - ((uint32_t) __clz((int) fw) >> 3)) : 0;
+        }
+        if (list != nullptr) {
+            append_line(ok, line, list, count);
         }
     }
 };
@@ -258,7 +286,8 @@ constexpr size_t HINT_FIN_OFS = 256 * ROW260, HINT_BAR_OFS = HINT_FIN_OFS + 256,
 
 __global__ void __launch_bounds__(1024, 1)
 k_dfa_lines_hint(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t nlines,
-                 uint32_t linelen, int32_t *__restrict__ rc, int32_t *__restrict__ hint)
+                 uint32_t linelen, int32_t *__restrict__ rc, int32_t *__restrict__ hint,
+                 uint32_t *__restrict__ list, uint32_t *__restrict__ count)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     load_table260(smem, dfa.h256, 256);
@@ -273,6 +302,8 @@ k_dfa_lines_hint(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, si
     cons.nlines = nlines;
     cons.rc = rc;
     cons.hint = hint;
+    cons.list = list;
+    cons.count = count;
     tile_pipeline_tma_early<1>(cons, &tmap, nlines, linelen,
                                smem + HINT_STAGE_OFS + (size_t) warp * 32 * 128,
                                reinterpret_cast<uint64_t *>(smem + HINT_BAR_OFS) + warp * MAX_STAGES,
@@ -295,6 +326,7 @@ struct hint_skip_consumer_t {
     uint32_t        pat[2];
     size_t          nlines;
     int32_t        *rc, *hint;
+    uint32_t       *list, *count;
 
     __device__ __forceinline__ void begin(size_t) { s = start; pos = 0; p0 = 0; }
     __device__ __forceinline__ void step(uint32_t addr)
@@ -347,10 +379,15 @@ struct hint_skip_consumer_t {
     __device__ __forceinline__ void end(size_t group)
     {
         const size_t line = group * 32 + (threadIdx.x & 31);
+        bool ok = false;
         if (line < nlines) {
             const uint32_t st = s & 0x7f;
-            rc[line] = (st == acc || fin[st]) ? SRE_K_OK : SRE_K_DECLINED;
+            ok = st == acc || fin[st];
+            rc[line] = ok ? SRE_K_OK : SRE_K_DECLINED;
             hint[line] = (int32_t) p0;
+        }
+        if (list != nullptr) {
+            append_line(ok, line, list, count);
         }
     }
 };
@@ -359,7 +396,7 @@ template <int NPAT>
 __global__ void __launch_bounds__(1024, 1)
 k_dfa_lines_hint_skip(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t nlines,
                       uint32_t linelen, uint32_t pat0, uint32_t pat1, int32_t *__restrict__ rc,
-                      int32_t *__restrict__ hint)
+                      int32_t *__restrict__ hint, uint32_t *__restrict__ list, uint32_t *__restrict__ count)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const dfa_smem_plan_t plan = dfa_smem_plan(256, 0, false);
@@ -378,6 +415,8 @@ k_dfa_lines_hint_skip(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tma
     cons.nlines = nlines;
     cons.rc = rc;
     cons.hint = hint;
+    cons.list = list;
+    cons.count = count;
     tile_pipeline_tma_early<1>(cons, &tmap, nlines, linelen,
                                smem + plan.stage_ofs + (size_t) warp * 32 * 128,
                                reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES,
@@ -421,6 +460,7 @@ struct big_consumer_t {
     uint32_t        pitch, start, acc, s, pos, p0;
     size_t          nlines;
     int32_t        *rc, *hint;
+    uint32_t       *list, *count;   /* HINT: packed list of the matching lines, or NULL */
 
     __device__ __forceinline__ void begin(size_t) { s = start; pos = 0; p0 = 0; }
     /* cls[b].  The class map stays a 256-BYTE table: text bytes then fall into distinct banks, one
@@ -494,11 +534,16 @@ struct big_consumer_t {
     __device__ __forceinline__ void end(size_t group)
     {
         const size_t line = group * 32 + (threadIdx.x & 31);
+        bool ok = false;
         if (line < nlines) {
-            rc[line] = (s == acc || __ldg(fin + s)) ? SRE_K_OK : SRE_K_DECLINED;
+            ok = s == acc || __ldg(fin + s);
+            rc[line] = ok ? SRE_K_OK : SRE_K_DECLINED;
             if (HINT) {
                 hint[line] = (int32_t) p0;
             }
+        }
+        if (HINT && list != nullptr) {
+            append_line(ok, line, list, count);
         }
     }
 };
@@ -506,7 +551,8 @@ struct big_consumer_t {
 template <bool HINT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 k_dfa_lines_big(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t nlines, uint32_t linelen,
-                int32_t *__restrict__ rc, int32_t *__restrict__ hint)
+                int32_t *__restrict__ rc, int32_t *__restrict__ hint, uint32_t *__restrict__ list,
+                uint32_t *__restrict__ count)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     /* [byte-class map 256][barriers][stages] */
@@ -530,6 +576,8 @@ k_dfa_lines_big(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, siz
     cons.nlines = nlines;
     cons.rc = rc;
     cons.hint = hint;
+    cons.list = list;
+    cons.count = count;
     tile_pipeline_tma_early<1>(cons, &tmap, nlines, linelen, smem + 4096 + (size_t) warp * 32 * 128,
                                reinterpret_cast<uint64_t *>(smem + 2048) + warp * MAX_STAGES,
                                (size_t) blockIdx.x * warps_per_block + warp, (size_t) gridDim.x * warps_per_block);
@@ -1184,7 +1232,7 @@ cudaError_t sre_launch_dfa_generic_hint(const sre_dev_dfa_t &dfa, const uint8_t 
 
 cudaError_t sre_launch_dfa_lines_hint(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines,
     size_t pitch, size_t linelen, int32_t *rc, int32_t *hint, const uint32_t *pats, int npat,
-    cudaStream_t stream, int *launches)
+    uint32_t *list, uint32_t *count, cudaStream_t stream, int *launches)
 {
     if (nlines == 0) {
         return cudaSuccess;
@@ -1229,13 +1277,13 @@ cudaError_t sre_launch_dfa_lines_hint(const sre_dev_dfa_t &dfa, const uint8_t *b
     /* word skip when the start state is left by one or two byte values */
     if (pats != nullptr && npat == 1) {
         k_dfa_lines_hint_skip<1><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen,
-                                                                               pats[0], pats[0], rc, hint);
+                                                                               pats[0], pats[0], rc, hint, list, count);
     } else if (pats != nullptr && npat == 2) {
         k_dfa_lines_hint_skip<2><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen,
-                                                                               pats[0], pats[1], rc, hint);
+                                                                               pats[0], pats[1], rc, hint, list, count);
     } else {
         k_dfa_lines_hint<<<(unsigned) grid, warps * 32, smem_plain, stream>>>(dfa, tmap, nlines, (uint32_t) linelen,
-                                                                            rc, hint);
+                                                                            rc, hint, list, count);
     }
     return cudaGetLastError();
 }
@@ -1375,7 +1423,7 @@ cudaError_t sre_launch_nfa64_lines(const sre_dev_nfa64_t &nfa, const uint8_t *bu
  * for DFAs whose table exceeds shared memory; 16-byte aligned fixed-pitch lines */
 template <bool HINT, int WARPS>
 static cudaError_t launch_dfa_lines_big_t(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines, size_t pitch,
-    size_t linelen, int32_t *rc, int32_t *hint, cudaStream_t stream)
+    size_t linelen, int32_t *rc, int32_t *hint, uint32_t *list, uint32_t *count, cudaStream_t stream)
 {
     const size_t smem = 4096 + (size_t) WARPS * 32 * 128;
     CUtensorMap tmap;
@@ -1398,12 +1446,13 @@ static cudaError_t launch_dfa_lines_big_t(const sre_dev_dfa_t &dfa, const uint8_
     if (grid > need) {
         grid = need;
     }
-    kern<<<(unsigned) grid, WARPS * 32, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen, rc, hint);
+    kern<<<(unsigned) grid, WARPS * 32, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen, rc, hint, list, count);
     return cudaGetLastError();
 }
 
 cudaError_t sre_launch_dfa_lines_big(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines, size_t pitch,
-    size_t linelen, int32_t *rc, int32_t *hint, int variant, cudaStream_t stream, int *launches)
+    size_t linelen, int32_t *rc, int32_t *hint, uint32_t *list, uint32_t *count, int variant, cudaStream_t stream,
+    int *launches)
 {
     if (nlines == 0) {
         return cudaSuccess;
@@ -1416,9 +1465,9 @@ cudaError_t sre_launch_dfa_lines_big(const sre_dev_dfa_t &dfa, const uint8_t *bu
     }
     /* 32 warps per SM (128 KB of staging, ~100 KB left to L1: measured best) or 16 (64 KB, more L1) */
     if (hint != nullptr) {
-        return variant == 1 ? launch_dfa_lines_big_t<true, 16>(dfa, buf, nlines, pitch, linelen, rc, hint, stream)
-                            : launch_dfa_lines_big_t<true, 32>(dfa, buf, nlines, pitch, linelen, rc, hint, stream);
+        return variant == 1 ? launch_dfa_lines_big_t<true, 16>(dfa, buf, nlines, pitch, linelen, rc, hint, list, count, stream)
+                            : launch_dfa_lines_big_t<true, 32>(dfa, buf, nlines, pitch, linelen, rc, hint, list, count, stream);
     }
-    return variant == 1 ? launch_dfa_lines_big_t<false, 16>(dfa, buf, nlines, pitch, linelen, rc, hint, stream)
-                        : launch_dfa_lines_big_t<false, 32>(dfa, buf, nlines, pitch, linelen, rc, hint, stream);
+    return variant == 1 ? launch_dfa_lines_big_t<false, 16>(dfa, buf, nlines, pitch, linelen, rc, hint, list, count, stream)
+                        : launch_dfa_lines_big_t<false, 32>(dfa, buf, nlines, pitch, linelen, rc, hint, list, count, stream);
 }
