@@ -679,7 +679,8 @@ int thompson_dispatch(sre_cuda_program_t *cp, const uint8_t *dev_buf, const int6
              * through L1/L2 */
             launches = 0;
             err = linelen >= 128 ? sre_launch_dfa_lines_big(cp->dfa, dev_buf, nlines, pitch, linelen, dev_rc, nullptr,
-                                                            nullptr, nullptr, variant, st, &launches)
+                                                            sre_gate_pack_t{ nullptr, nullptr, nullptr, 0 }, variant, st,
+                                                            &launches)
                                  : sre_launch_dfa_ragged(cp->dfa, dev_buf, dev_offsets, nlines, pitch, linelen,
                                                          dev_rc, st, &launches);
         }
@@ -1132,18 +1133,19 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
          * do not match) and the kernel appends the matching lines to the list as it goes */
         const bool tiled = tiled_hint || (aligned && linelen >= 128);
         packed = tiled && dev_select == nullptr;
+        sre_gate_pack_t pack = { nullptr, nullptr, nullptr, 0 };
         if (packed) {
             CUDA_TRY(cudaMemsetAsync(count, 0, 4, st));
             gate = dev_rc;
+            pack = sre_gate_pack_t{ list, count, dev_ovec, (uint32_t) ovec_slots };
         }
         cudaError_t e = tiled_hint
             ? sre_launch_dfa_lines_hint(cp->dfa, dev_buf, nlines, pitch, linelen, gate, hint,
                                         (cp->nleave >= 1 && cp->nleave <= 2 && linelen >= 128) ? cp->leave_pats
                                                                                                 : nullptr,
-                                        cp->nleave, packed ? list : nullptr, count, st, &launches)
+                                        cp->nleave, pack, st, &launches)
             : (aligned && linelen >= 128)
-            ? sre_launch_dfa_lines_big(cp->dfa, dev_buf, nlines, pitch, linelen, gate, hint,
-                                       packed ? list : nullptr, count, 0, st, &launches)
+            ? sre_launch_dfa_lines_big(cp->dfa, dev_buf, nlines, pitch, linelen, gate, hint, pack, 0, st, &launches)
             : sre_launch_dfa_generic_hint(cp->dfa, dev_buf, dev_offsets, nlines, pitch, linelen, gate, hint, st,
                                           &launches);
         if (e != cudaSuccess) {
@@ -1163,10 +1165,11 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
      * (rc from the gate, ovector all -1 = all 0xff bytes) */
     sre_line_list_t lines = { nullptr, nullptr };
     if (dev_select != nullptr) {
-        if (dev_ovec != nullptr && ovec_slots != 0) {
-            CUDA_TRY(cudaMemsetAsync(dev_ovec, 0xff, nlines * ovec_slots * sizeof(int64_t), st));
-        }
         if (!packed) {
+            /* (a gate kernel that packs the list sets the rows of the other lines itself) */
+            if (dev_ovec != nullptr && ovec_slots != 0) {
+                CUDA_TRY(cudaMemsetAsync(dev_ovec, 0xff, nlines * ovec_slots * sizeof(int64_t), st));
+            }
             CUDA_TRY(cudaMemsetAsync(count, 0, 4, st));
             err = sre_launch_pike_compact(dev_select, nlines, dev_rc, list, count, st, &launches);
             if (err != cudaSuccess) {
@@ -1224,8 +1227,8 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
         cp->pike_last_tier = 3;
         /* rows of a gated batch were set to -1 by the memset above */
         err = sre_launch_pike_lineage(cp->pdfa, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
-                                      dev_rc, dev_ovec, (uint32_t) ovec_slots, lines.list != nullptr, work, st,
-                                      &launches);
+                                      dev_rc, dev_ovec, (uint32_t) ovec_slots, lines.list != nullptr && !packed, work,
+                                      st, &launches);
         if (err == cudaSuccess) {
             err = sre_launch_pike_table(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
                                         dev_rc, dev_ovec, (uint32_t) ovec_slots, k2 > k1 ? k2 : k1, h2, 1, work, st,

@@ -157,10 +157,17 @@ cudaError_t sre_launch_dfa_lines_skip(const sre_dev_dfa_t &dfa, const uint8_t *b
  * hint[i] = offset after which no earlier-started thread is alive; pats / npat
  * (may be NULL / 0): the 1 or 2 byte values that leave the start state, as
  * for sre_launch_dfa_lines_skip, to skip words no lane needs                  */
-/* list / count (may be NULL): the lines whose verdict is SRE_OK are appended to list[*count ...]   */
+/* What a gate kernel does for the Pike pass behind it besides verdict and hint (list == NULL:
+ * nothing): the lines whose verdict is SRE_OK are appended to list[*count ...] (any order), the
+ * ovector rows of the others are set to -1 (ovec may be NULL). */
+struct sre_gate_pack_t {
+    uint32_t *list, *count;
+    int64_t  *ovec;
+    uint32_t  ovec_slots;
+};
 cudaError_t sre_launch_dfa_lines_hint(const sre_dev_dfa_t &dfa, const uint8_t *buf,
     size_t nlines, size_t pitch, size_t linelen, int32_t *rc, int32_t *hint,
-    const uint32_t *pats, int npat, uint32_t *list, uint32_t *count, cudaStream_t stream, int *launches);
+    const uint32_t *pats, int npat, sre_gate_pack_t pack, cudaStream_t stream, int *launches);
 
 /* same for any DFA size / alignment / ragged offsets (thread per line, dfa.hcls) */
 cudaError_t sre_launch_dfa_generic_hint(const sre_dev_dfa_t &dfa, const uint8_t *buf,
@@ -169,7 +176,7 @@ cudaError_t sre_launch_dfa_generic_hint(const sre_dev_dfa_t &dfa, const uint8_t 
 
 /* TMA-tiled lines, class table through L1/L2 (tables beyond shared memory); hint may be NULL */
 cudaError_t sre_launch_dfa_lines_big(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines, size_t pitch,
-    size_t linelen, int32_t *rc, int32_t *hint, uint32_t *list, uint32_t *count, int variant, cudaStream_t stream,
+    size_t linelen, int32_t *rc, int32_t *hint, sre_gate_pack_t pack, int variant, cudaStream_t stream,
     int *launches);
 
 /* the lines a Pike pass works on: list[0 .. *count) (device memory), or every

@@ -185,9 +185,16 @@ k_dfa_lines_skipw(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, s
 }
 
 /* the lines the gate lets through, appended to the packed list the Pike kernels work from (warp-
- * aggregated; the order is irrelevant) -- called by all 32 lanes */
-__device__ __forceinline__ void append_line(bool take, size_t line, uint32_t *list, uint32_t *count)
+ * aggregated; the order is irrelevant); the ovector rows of the others are final: all -1.
+ * Called by all 32 lanes. */
+__device__ __forceinline__ void gate_pack(const sre_gate_pack_t &pk, bool take, bool valid, size_t line)
 {
+    if (valid && !take && pk.ovec != nullptr) {
+        int64_t *row = pk.ovec + line * pk.ovec_slots;
+        for (uint32_t i = 0; i < pk.ovec_slots; i++) {
+            row[i] = -1;
+        }
+    }
     const uint32_t m = __ballot_sync(FULL, take);
     if (m == 0) {
         return;
@@ -195,11 +202,11 @@ __device__ __forceinline__ void append_line(bool take, size_t line, uint32_t *li
     const uint32_t lane = threadIdx.x & 31, leader = (uint32_t) __ffs((int) m) - 1;
     uint32_t base = 0;
     if (lane == leader) {
-        base = atomicAdd(count, (uint32_t) __popc(m));
+        base = atomicAdd(pk.count, (uint32_t) __popc(m));
     }
     base = __shfl_sync(FULL, base, leader);
     if (take) {
-        list[base + __popc(m & ((1u << lane) - 1))] = (uint32_t) line;
+        pk.list[base + __popc(m & ((1u << lane) - 1))] = (uint32_t) line;
     }
 }
 
@@ -221,7 +228,7 @@ struct hint_consumer_t {
     uint32_t        fw, fpos;   /* restart flags of the last word that had any, offset just after it */
     size_t          nlines;
     int32_t        *rc, *hint;
-    uint32_t       *list, *count;   /* packed list of the matching lines, or NULL */
+    sre_gate_pack_t pack;
 
     __device__ __forceinline__ void begin(size_t) { s = 0; pos = 0; fw = 0; fpos = 0; }
     /*
@@ -274,8 +281,8 @@ struct hint_consumer_t {
             /* just after the last flagged byte of that word */
             hint[line] = fw ? (int32_t) (fpos - ((uint32_t) __clz((int) fw) >> 3)) : 0;
         }
-        if (list != nullptr) {
-            append_line(ok, line, list, count);
+        if (pack.list != nullptr) {
+            gate_pack(pack, ok, line < nlines, line);
         }
     }
 };
@@ -286,8 +293,7 @@ constexpr size_t HINT_FIN_OFS = 256 * ROW260, HINT_BAR_OFS = HINT_FIN_OFS + 256,
 
 __global__ void __launch_bounds__(1024, 1)
 k_dfa_lines_hint(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t nlines,
-                 uint32_t linelen, int32_t *__restrict__ rc, int32_t *__restrict__ hint,
-                 uint32_t *__restrict__ list, uint32_t *__restrict__ count)
+                 uint32_t linelen, int32_t *__restrict__ rc, int32_t *__restrict__ hint, sre_gate_pack_t pack)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     load_table260(smem, dfa.h256, 256);
@@ -302,8 +308,7 @@ k_dfa_lines_hint(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, si
     cons.nlines = nlines;
     cons.rc = rc;
     cons.hint = hint;
-    cons.list = list;
-    cons.count = count;
+    cons.pack = pack;
     tile_pipeline_tma_early<1>(cons, &tmap, nlines, linelen,
                                smem + HINT_STAGE_OFS + (size_t) warp * 32 * 128,
                                reinterpret_cast<uint64_t *>(smem + HINT_BAR_OFS) + warp * MAX_STAGES,
@@ -326,7 +331,7 @@ struct hint_skip_consumer_t {
     uint32_t        pat[2];
     size_t          nlines;
     int32_t        *rc, *hint;
-    uint32_t       *list, *count;
+    sre_gate_pack_t pack;
 
     __device__ __forceinline__ void begin(size_t) { s = start; pos = 0; p0 = 0; }
     __device__ __forceinline__ void step(uint32_t addr)
@@ -386,8 +391,8 @@ struct hint_skip_consumer_t {
             rc[line] = ok ? SRE_K_OK : SRE_K_DECLINED;
             hint[line] = (int32_t) p0;
         }
-        if (list != nullptr) {
-            append_line(ok, line, list, count);
+        if (pack.list != nullptr) {
+            gate_pack(pack, ok, line < nlines, line);
         }
     }
 };
@@ -396,7 +401,7 @@ template <int NPAT>
 __global__ void __launch_bounds__(1024, 1)
 k_dfa_lines_hint_skip(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t nlines,
                       uint32_t linelen, uint32_t pat0, uint32_t pat1, int32_t *__restrict__ rc,
-                      int32_t *__restrict__ hint, uint32_t *__restrict__ list, uint32_t *__restrict__ count)
+                      int32_t *__restrict__ hint, sre_gate_pack_t pack)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const dfa_smem_plan_t plan = dfa_smem_plan(256, 0, false);
@@ -415,8 +420,7 @@ k_dfa_lines_hint_skip(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tma
     cons.nlines = nlines;
     cons.rc = rc;
     cons.hint = hint;
-    cons.list = list;
-    cons.count = count;
+    cons.pack = pack;
     tile_pipeline_tma_early<1>(cons, &tmap, nlines, linelen,
                                smem + plan.stage_ofs + (size_t) warp * 32 * 128,
                                reinterpret_cast<uint64_t *>(smem + plan.bar_ofs) + warp * MAX_STAGES,
@@ -460,7 +464,7 @@ struct big_consumer_t {
     uint32_t        pitch, start, acc, s, pos, p0;
     size_t          nlines;
     int32_t        *rc, *hint;
-    uint32_t       *list, *count;   /* HINT: packed list of the matching lines, or NULL */
+    sre_gate_pack_t pack;       /* HINT only */
 
     __device__ __forceinline__ void begin(size_t) { s = start; pos = 0; p0 = 0; }
     /* cls[b].  The class map stays a 256-BYTE table: text bytes then fall into distinct banks, one
@@ -542,8 +546,8 @@ struct big_consumer_t {
                 hint[line] = (int32_t) p0;
             }
         }
-        if (HINT && list != nullptr) {
-            append_line(ok, line, list, count);
+        if (HINT && pack.list != nullptr) {
+            gate_pack(pack, ok, line < nlines, line);
         }
     }
 };
@@ -551,8 +555,7 @@ struct big_consumer_t {
 template <bool HINT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 k_dfa_lines_big(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, size_t nlines, uint32_t linelen,
-                int32_t *__restrict__ rc, int32_t *__restrict__ hint, uint32_t *__restrict__ list,
-                uint32_t *__restrict__ count)
+                int32_t *__restrict__ rc, int32_t *__restrict__ hint, sre_gate_pack_t pack)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     /* [byte-class map 256][barriers][stages] */
@@ -576,8 +579,7 @@ k_dfa_lines_big(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, siz
     cons.nlines = nlines;
     cons.rc = rc;
     cons.hint = hint;
-    cons.list = list;
-    cons.count = count;
+    cons.pack = pack;
     tile_pipeline_tma_early<1>(cons, &tmap, nlines, linelen, smem + 4096 + (size_t) warp * 32 * 128,
                                reinterpret_cast<uint64_t *>(smem + 2048) + warp * MAX_STAGES,
                                (size_t) blockIdx.x * warps_per_block + warp, (size_t) gridDim.x * warps_per_block);
@@ -1232,7 +1234,7 @@ cudaError_t sre_launch_dfa_generic_hint(const sre_dev_dfa_t &dfa, const uint8_t 
 
 cudaError_t sre_launch_dfa_lines_hint(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines,
     size_t pitch, size_t linelen, int32_t *rc, int32_t *hint, const uint32_t *pats, int npat,
-    uint32_t *list, uint32_t *count, cudaStream_t stream, int *launches)
+    sre_gate_pack_t pack, cudaStream_t stream, int *launches)
 {
     if (nlines == 0) {
         return cudaSuccess;
@@ -1277,13 +1279,13 @@ cudaError_t sre_launch_dfa_lines_hint(const sre_dev_dfa_t &dfa, const uint8_t *b
     /* word skip when the start state is left by one or two byte values */
     if (pats != nullptr && npat == 1) {
         k_dfa_lines_hint_skip<1><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen,
-                                                                               pats[0], pats[0], rc, hint, list, count);
+                                                                               pats[0], pats[0], rc, hint, pack);
     } else if (pats != nullptr && npat == 2) {
         k_dfa_lines_hint_skip<2><<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen,
-                                                                               pats[0], pats[1], rc, hint, list, count);
+                                                                               pats[0], pats[1], rc, hint, pack);
     } else {
         k_dfa_lines_hint<<<(unsigned) grid, warps * 32, smem_plain, stream>>>(dfa, tmap, nlines, (uint32_t) linelen,
-                                                                            rc, hint, list, count);
+                                                                            rc, hint, pack);
     }
     return cudaGetLastError();
 }
@@ -1423,7 +1425,7 @@ cudaError_t sre_launch_nfa64_lines(const sre_dev_nfa64_t &nfa, const uint8_t *bu
  * for DFAs whose table exceeds shared memory; 16-byte aligned fixed-pitch lines */
 template <bool HINT, int WARPS>
 static cudaError_t launch_dfa_lines_big_t(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines, size_t pitch,
-    size_t linelen, int32_t *rc, int32_t *hint, uint32_t *list, uint32_t *count, cudaStream_t stream)
+    size_t linelen, int32_t *rc, int32_t *hint, sre_gate_pack_t pack, cudaStream_t stream)
 {
     const size_t smem = 4096 + (size_t) WARPS * 32 * 128;
     CUtensorMap tmap;
@@ -1446,12 +1448,12 @@ static cudaError_t launch_dfa_lines_big_t(const sre_dev_dfa_t &dfa, const uint8_
     if (grid > need) {
         grid = need;
     }
-    kern<<<(unsigned) grid, WARPS * 32, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen, rc, hint, list, count);
+    kern<<<(unsigned) grid, WARPS * 32, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen, rc, hint, pack);
     return cudaGetLastError();
 }
 
 cudaError_t sre_launch_dfa_lines_big(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t nlines, size_t pitch,
-    size_t linelen, int32_t *rc, int32_t *hint, uint32_t *list, uint32_t *count, int variant, cudaStream_t stream,
+    size_t linelen, int32_t *rc, int32_t *hint, sre_gate_pack_t pack, int variant, cudaStream_t stream,
     int *launches)
 {
     if (nlines == 0) {
@@ -1465,9 +1467,9 @@ cudaError_t sre_launch_dfa_lines_big(const sre_dev_dfa_t &dfa, const uint8_t *bu
     }
     /* 32 warps per SM (128 KB of staging, ~100 KB left to L1: measured best) or 16 (64 KB, more L1) */
     if (hint != nullptr) {
-        return variant == 1 ? launch_dfa_lines_big_t<true, 16>(dfa, buf, nlines, pitch, linelen, rc, hint, list, count, stream)
-                            : launch_dfa_lines_big_t<true, 32>(dfa, buf, nlines, pitch, linelen, rc, hint, list, count, stream);
+        return variant == 1 ? launch_dfa_lines_big_t<true, 16>(dfa, buf, nlines, pitch, linelen, rc, hint, pack, stream)
+                            : launch_dfa_lines_big_t<true, 32>(dfa, buf, nlines, pitch, linelen, rc, hint, pack, stream);
     }
-    return variant == 1 ? launch_dfa_lines_big_t<false, 16>(dfa, buf, nlines, pitch, linelen, rc, hint, list, count, stream)
-                        : launch_dfa_lines_big_t<false, 32>(dfa, buf, nlines, pitch, linelen, rc, hint, list, count, stream);
+    return variant == 1 ? launch_dfa_lines_big_t<false, 16>(dfa, buf, nlines, pitch, linelen, rc, hint, pack, stream)
+                        : launch_dfa_lines_big_t<false, 32>(dfa, buf, nlines, pitch, linelen, rc, hint, pack, stream);
 }
