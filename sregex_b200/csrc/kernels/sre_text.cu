@@ -40,7 +40,7 @@ using namespace sre_dev;
 namespace {
 
 constexpr uint32_t PIECE = 4096;
-constexpr uint32_t MIN_PIECE = 2048;    /* smallest piece the verdict path can be told to cut (text_piece_bytes) */
+constexpr uint32_t MIN_PIECE = 512;     /* smallest piece the verdict path cuts (text_piece_bytes) */
 constexpr uint32_t CAP = 64;            /* staged lines per piece */
 
 /* bit 7 of every byte of x that equals '\n' (exact: no carry between bytes) */
@@ -553,16 +553,36 @@ struct verdict_consumer_t {
             if (st == acc) {
                 fix = FIX_MATCHED;
             } else {
-                /* a partial match hangs over the boundary: finish the line */
+                /* a partial match hangs over the boundary: finish the line -- 16 aligned bytes at
+                 * a time (pieces end on 128-byte boundaries), the next block requested before this
+                 * one is walked */
                 size_t p = (piece + 1) * piece_bytes;
                 uint32_t t = s;
-                for (; p < len; p++) {
-                    t = look(t, __ldg(buf + p));
-                    if (t & 0x40u) {
-                        break;
-                    }
+                bool done = false;
+                uint4 vnext = make_uint4(0, 0, 0, 0);
+                if (p + 16 <= len) {
+                    vnext = __ldg(reinterpret_cast<const uint4 *>(buf + p));
                 }
-                if (p < len) {
+                while (p + 16 <= len && !done) {
+                    const uint4 v = vnext;
+                    if (p + 32 <= len) {
+                        vnext = __ldg(reinterpret_cast<const uint4 *>(buf + p + 16));
+                    }
+                    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                    for (uint32_t q = 0; q < 16; q++) {
+                        if (!done) {
+                            t = look(t, (w[q >> 2] >> ((q & 3) * 8)) & 0xff);
+                            done = (t & 0x40u) != 0;
+                        }
+                    }
+                    p += 16;
+                }
+                for (; p < len && !done; p++) {
+                    t = look(t, __ldg(buf + p));
+                    done = (t & 0x40u) != 0;
+                }
+                if (done) {
                     fix = (t & 0x80u) ? FIX_MATCHED : FIX_UNMATCHED;
                 } else {
                     /* the buffer ended first: the EOF step of the reference decides */
@@ -718,14 +738,15 @@ size_t sre_text_count_offset(size_t)
 }
 
 /*
- * The piece size of the verdict path: PIECE, or SRE_CUDA_TEXT_PIECE (a multiple of 128 in
- * [MIN_PIECE, PIECE]; tests run the boundary cases at several sizes).  Fitting the size to the
- * input so that the pieces fill the resident warps in equal rounds (1 GiB in 4 KB pieces is 1.73
- * rounds of 148 x 32 warps; 3584-byte pieces make it 1.98) was measured SLOWER, 3.0 vs 3.4 TB/s:
- * the kernel is bound by the shared-memory pipe, not by latency, so a thinner last round simply
- * runs faster, and smaller pieces only add per-piece work.
+ * The piece size of the verdict path.  A thread walks its piece serially (~40 cycles per byte),
+ * so below ~600 MB -- one 4 KB piece per resident thread -- the call takes the time of ONE piece
+ * however small the input: pieces are cut so that every resident thread gets one (measured:
+ * 64 MiB in 4 KB pieces 0.18 ms, in 1 KB pieces 0.08 ms), down to MIN_PIECE.  Above that the
+ * kernel is bound by the shared-memory pipe, not by latency, and a thinner last round simply runs
+ * faster (1 GiB = 1.73 rounds of 4 KB pieces: 3.5 TB/s).  SRE_CUDA_TEXT_PIECE overrides (tuning /
+ * tests): a multiple of 128.
  */
-static uint32_t text_piece_bytes()
+static uint32_t text_piece_bytes(size_t len, size_t threads_total)
 {
     const char *e = getenv("SRE_CUDA_TEXT_PIECE");
     if (e != nullptr) {
@@ -734,7 +755,14 @@ static uint32_t text_piece_bytes()
             return (uint32_t) v;
         }
     }
-    return PIECE;
+    /* the smallest power of two that gives every resident thread at most one piece.  (Powers of
+     * two only: pieces of 7, 9, 14, 28 or 31 tiles were measured up to 1.8x slower than the next
+     * power of two at the same input size -- 512 MiB: 3584 bytes 0.31 ms, 4096 bytes 0.20 ms.) */
+    uint32_t per = MIN_PIECE;
+    while (per < PIECE && (size_t) per * threads_total < len) {
+        per *= 2;
+    }
+    return per;
 }
 
 /* verdicts only, <= 64 states: count-only hot loop (k_text_verdicts) */
@@ -742,7 +770,7 @@ static cudaError_t launch_text_verdicts(const sre_dev_dfa_t &dfa, const uint8_t 
     size_t max_lines, uint8_t *workspace, cudaStream_t stream, int *launches)
 {
     const int warps = 32;
-    const uint32_t piece = text_piece_bytes();
+    const uint32_t piece = text_piece_bytes(len, (size_t) num_sms() * warps * 32);
     const size_t nfull = len / piece, npieces = nfull + 1, nb = (npieces + WB - 1) / WB;
     unsigned long long *total = reinterpret_cast<unsigned long long *>(workspace);
     unsigned long long *sums = reinterpret_cast<unsigned long long *>(workspace + 256);     /* [nb + 1] */

@@ -890,7 +890,7 @@ def test_text_grep_one_pass_vs_oracle(cu):
                             + [oracle.thompson(po, lines[-1] + (b"\n" if data.endswith(b"\n") else b""))])
             po.close()
             # (the verdict path fits its piece size to the input; force a few, the default last)
-            for piece in ("2048", "2176", "3584", "4096", None):
+            for piece in ("512", "2176", "3584", "4096", None):
                 if piece is None:
                     os.environ.pop("SRE_CUDA_TEXT_PIECE", None)
                 else:
