@@ -411,17 +411,6 @@ k_text_write(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, siz
     }
 }
 
-/* rc[0 .. min(lines, max_lines)) <- SRE_DECLINED (k_text_apply then marks the matched lines) */
-__global__ void __launch_bounds__(256)
-k_text_fill(const unsigned long long *__restrict__ total, int32_t *__restrict__ rc, size_t max_lines)
-{
-    const size_t n = *total < max_lines ? (size_t) *total : max_lines;
-    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
-        rc[i] = SRE_K_DECLINED;
-    }
-}
-
-
 /* ==== verdicts only, automata of at most 64 states: the count-only hot loop ==== */
 
 /*
@@ -440,7 +429,7 @@ k_text_fill(const unsigned long long *__restrict__ total, int32_t *__restrict__ 
  * neighbour's run IS the continuation and nothing is left to do; sticky ACC -> the
  * line matched whatever follows; anything else (a partial match hanging over the
  * boundary) -> it finishes the line itself, byte by byte, and leaves the verdict as
- * a correction in its info word, which k_text_apply applies to the first line of
+ * a correction in its info word, which k_text_finish applies to the first line of
  * the next piece that holds a newline.  A correct guess is a matter of speed only.
  */
 constexpr uint32_t INFO_CNT = 0x1fffu;          /* newlines in the piece (<= 4097)            */
@@ -636,14 +625,36 @@ __device__ __forceinline__ uint32_t serial_marks(const sre_dev_dfa_t &dfa, const
 {
     const uint8_t *tx = dfa.x256m;
     uint32_t s = (begin == 0 || __ldg(buf + begin - 1) == '\n') ? dfa.start : dfa.xguess, n = 0;
-    for (size_t p = begin; p < end; p++) {
-        s = __ldg(tx + ((s << 8) | __ldg(buf + p)));
+    auto step = [&](uint32_t b) {
+        s = __ldg(tx + ((s << 8) | b));
         if (s & 0x40u) {
             if (s & 0x80u) {
                 emit(n);
             }
             n++;
         }
+    };
+    /* 16 aligned bytes at a time (pieces begin on 128-byte boundaries), the next block requested
+     * before this one is walked: the table look-ups (L1) are the chain, not the input */
+    size_t p = begin;
+    uint4 vnext = make_uint4(0, 0, 0, 0);
+    if (p + 16 <= end) {
+        vnext = __ldg(reinterpret_cast<const uint4 *>(buf + p));
+    }
+    while (p + 16 <= end) {
+        const uint4 v = vnext;
+        if (p + 32 <= end) {
+            vnext = __ldg(reinterpret_cast<const uint4 *>(buf + p + 16));
+        }
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (uint32_t q = 0; q < 16; q++) {
+            step((w[q >> 2] >> ((q & 3) * 8)) & 0xff);
+        }
+        p += 16;
+    }
+    for (; p < end; p++) {
+        step(__ldg(buf + p));
     }
     if (eof && len > 0 && __ldg(buf + len - 1) != '\n') {
         const uint32_t st = s & 0x3fu;
@@ -655,10 +666,18 @@ __device__ __forceinline__ uint32_t serial_marks(const sre_dev_dfa_t &dfa, const
     return n;
 }
 
-/* the tail piece [nfull * PIECE, len) (possibly empty) and the end of the buffer: one thread */
-__global__ void k_text_verdicts_tail(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, size_t nfull,
-                                     uint32_t piece_bytes, verdict_out_t out)
+/* the tail piece [nfull * piece_bytes, len) (possibly empty) and the end of the buffer: thread 0;
+ * the others clear the ticket and the look-back words of k_text_finish */
+__global__ void __launch_bounds__(256)
+k_text_verdicts_tail(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, size_t nfull,
+                     uint32_t piece_bytes, verdict_out_t out, unsigned long long *__restrict__ status, size_t nstatus)
 {
+    for (size_t i = threadIdx.x; i < nstatus; i += blockDim.x) {
+        status[i] = 0;
+    }
+    if (threadIdx.x != 0) {
+        return;
+    }
     uint32_t *stage = out.stage + nfull * CAP;
     uint32_t m = 0;
     const uint32_t n = serial_marks(dfa, buf, len, nfull * piece_bytes, len, true, [&](uint32_t k) {
@@ -670,23 +689,67 @@ __global__ void k_text_verdicts_tail(sre_dev_dfa_t dfa, const uint8_t *__restric
     out.info[nfull] = n | (m << INFO_MSHIFT);
 }
 
-/* rc[line] <- SRE_OK for the staged matched lines, then the corrections; one thread per piece
- * (after k_text_fill) */
+/*
+ * Everything after the pieces in one launch: line numbers (a chained scan over the blocks: each
+ * block publishes its count, then the count of all blocks up to it; a block looks back until it
+ * meets such a total -- tiles are handed out by ticket, so the blocks it waits for are running),
+ * rc <- SRE_DECLINED for the block's lines, SRE_OK for the staged matched ones, then the
+ * corrections.  One thread per piece.  status[0] = ticket, status[1 + b] = (count << 2) | 1 (the
+ * block's own lines) or | 2 (all lines up to and including block b).
+ */
 __global__ void __launch_bounds__(WB)
-k_text_apply(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, size_t nfull, uint32_t piece_bytes,
-             verdict_out_t out, const unsigned long long *__restrict__ sums, int32_t *__restrict__ rc,
-             size_t max_lines)
+k_text_finish(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, size_t nfull, uint32_t piece_bytes,
+              verdict_out_t out, unsigned long long *status, unsigned long long *__restrict__ total_out,
+              int32_t *__restrict__ rc, size_t max_lines)
 {
+    __shared__ unsigned long long s_first;
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) {
+        s_tile = (uint32_t) atomicAdd(&status[0], 1ull);
+    }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const size_t piece = (size_t) tile * WB + threadIdx.x;
     auto begins_line = [&](size_t pc) { return pc == 0 || __ldg(buf + pc * piece_bytes - 1) == '\n'; };
-    const size_t piece = (size_t) blockIdx.x * WB + threadIdx.x;
     const uint32_t info = piece <= nfull ? out.info[piece] : 0u;
     const uint32_t n = info & INFO_CNT;
     uint32_t total;
     const uint32_t before = block_exclusive(n, &total);
+    if (threadIdx.x == 0) {
+        volatile unsigned long long *st = status + 1;
+        unsigned long long excl = 0;
+        if (tile != 0) {
+            st[tile] = ((unsigned long long) total << 2) | 1ull;
+            __threadfence();
+            for (uint32_t j = tile; j-- > 0;) {
+                unsigned long long v;
+                while (((v = st[j]) & 3ull) == 0) {
+                }
+                excl += v >> 2;
+                if ((v & 3ull) == 2ull) {
+                    break;
+                }
+            }
+        }
+        st[tile] = ((excl + total) << 2) | 2ull;
+        __threadfence();
+        s_first = excl;
+        if ((size_t) tile == nfull / WB) {          /* the block that holds the tail piece */
+            *total_out = excl + total;
+        }
+    }
+    __syncthreads();
+    const size_t block_first = (size_t) s_first;
+    for (size_t i = threadIdx.x; i < total; i += WB) {
+        if (block_first + i < max_lines) {
+            rc[block_first + i] = SRE_K_DECLINED;
+        }
+    }
+    __syncthreads();
     if (piece > nfull || n == 0) {
         return;
     }
-    const size_t first = (size_t) sums[blockIdx.x] + before;
+    const size_t first = block_first + before;
     const uint32_t m = (info >> INFO_MSHIFT) & INFO_CNT;
     if (m <= CAP) {
         const uint32_t *stage = out.stage + piece * CAP;
@@ -800,15 +863,10 @@ static cudaError_t launch_text_verdicts(const sre_dev_dfa_t &dfa, const uint8_t 
         k_text_verdicts<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, piece, out);
         if ((err = cudaGetLastError()) != cudaSuccess) return err;
     }
-    if (launches) *launches += 5;
-    k_text_verdicts_tail<<<1, 1, 0, stream>>>(dfa, buf, len, nfull, piece, out);
-    k_text_sums<<<(unsigned) nb, WB, 0, stream>>>(out.info, npieces, sums, INFO_CNT);
-    k_text_scan<<<1, 1024, 0, stream>>>(sums, nb, total);
-    const size_t most = max_lines < len + 1 ? max_lines : len + 1;
-    size_t fgrid = (most + 255) / 256;
-    fgrid = fgrid > 4096 ? 4096 : fgrid < 1 ? 1 : fgrid;
-    k_text_fill<<<(unsigned) fgrid, 256, 0, stream>>>(total, rc, max_lines);
-    k_text_apply<<<(unsigned) nb, WB, 0, stream>>>(dfa, buf, len, nfull, piece, out, sums, rc, max_lines);
+    if (launches) *launches += 2;
+    /* (sums[] serves as the ticket + look-back words of k_text_finish) */
+    k_text_verdicts_tail<<<1, 256, 0, stream>>>(dfa, buf, len, nfull, piece, out, sums, nb + 1);
+    k_text_finish<<<(unsigned) nb, WB, 0, stream>>>(dfa, buf, len, nfull, piece, out, sums, total, rc, max_lines);
     return cudaGetLastError();
 }
 
