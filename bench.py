@@ -448,7 +448,7 @@ def bench_c3(h, steps, warmup, dev, host):
                    "pike_tier": prog.last_pike_tier()},
         # 1 B per input byte (the gate reads every line once) + 8*(1+slots) B per matched line
         "roofline": h.roofline(bytes_per_step + 8 * (1 + ns) * matched, call_ms,
-                               "sre_cuda_pike_exec_lines: k_dfa_lines_hint + k_pike_compact + Pike kernel(s)",
+                               "sre_cuda_pike_exec_lines: k_dfa_lines_hint (packs the matching lines) + Pike kernel(s)",
                                note="whole call (3-4 launches); per-kernel shares in profiles/"),
         "gpu_launches": launches, "clocks": clocks,
     }
@@ -506,9 +506,9 @@ def bench_c4(h, steps, warmup):
                    "matched_fraction": matched / total_lines, "pike_tier": prog.last_pike_tier(),
                    "sharding": f"contiguous line ranges over {h.world} ranks, no data-path collective"},
         "roofline": h.roofline(n * PITCH + 4 * n + 8 * (1 + ns) * int((mrc >= 0).sum()), call_ms,
-                               "sre_cuda_pike_exec_lines: k_dfa_generic_hint (2107-state DFA) + k_pike_compact + "
-                               "k_pike_table", note="whole call on this rank's shard"),
-        "gate_roofline": h.roofline(n * PITCH + 4 * n, g_call, "k_dfa_generic<cls> (2107 states, table in L2)"),
+                               "sre_cuda_pike_exec_lines: k_dfa_lines_big<hint> (2107-state DFA, table through L1; packs "
+                               "the matching lines) + k_pike_lineage", note="whole call on this rank's shard"),
+        "gate_roofline": h.roofline(n * PITCH + 4 * n, g_call, "k_dfa_lines_big (2107 states, TMA-tiled lines, table through L1)"),
         "gpu_launches": launches, "clocks": clocks,
     }
     e2e_steps = 2
@@ -596,8 +596,8 @@ def bench_text(h, steps, warmup, dev):
                                "sre_vm_thompson_exec per line, regex " + REGEX_NAME,
                    "bytes_per_gpu": n, "lines": nl, "matched_lines": int((rc == 0).sum())},
         # 1 B per input byte + 4 B verdict per line (+ 8 B offset per line in the second form)
-        "roofline": h.roofline(n + 4 * nl, call_ms, "sre_cuda_thompson_exec_text: k_text_pieces + sums/scan/fill/scatter",
-                               note="whole call, verdict per line (5 launches + the read-back of the line count)"),
+        "roofline": h.roofline(n + 4 * nl, call_ms, "sre_cuda_thompson_exec_text: k_text_verdicts + tail + k_text_finish",
+                               note="whole call, verdict per line (3 launches + the read-back of the line count)"),
         "with_line_offsets_roofline": h.roofline(n + 12 * nl, off_call_ms,
                                                  "sre_cuda_thompson_exec_text: k_text_pieces + sums/scan/write"),
         "gpu_launches": launches, "clocks": clocks,

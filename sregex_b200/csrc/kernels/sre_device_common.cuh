@@ -47,26 +47,20 @@ struct step256_t {
  */
 constexpr uint32_t ROW260 = 260;
 struct step260_t {
-    uint32_t tab_s;             /* shared-window address of the table */
+    uint32_t tab_s;             /* shared-window address of the table; its low byte must be 0 */
     __device__ __forceinline__ static uint32_t lds_u8(uint32_t addr)
     {
         uint32_t v;
         asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
         return v;
     }
-    __device__ __forceinline__ uint32_t row0(uint32_t b) const
-    {
-        uint32_t a;
-        asm volatile("add.u32 %0, %1, %2;" : "=r"(a) : "r"(tab_s), "r"(b));
-        return a;
-    }
-    /* the byte's address within row 0 is computed off the state -> state chain,
-     * which is then one IMAD and one LDS per byte */
+    /* The byte's address within row 0 is ONE PRMT (the byte spliced under the upper three bytes of
+     * the table's address), off the state -> state chain, which is then one IMAD and one LDS per
+     * byte (the IMAD on the fma pipe, which these kernels leave idle). */
     __device__ __forceinline__ uint32_t word(uint32_t s, uint32_t w) const
     {
-        /* (opaque adds: the compiler would otherwise re-associate them into the chain) */
-        const uint32_t a0 = row0(__byte_perm(w, 0, 0x4440)), a1 = row0(__byte_perm(w, 0, 0x4441));
-        const uint32_t a2 = row0(__byte_perm(w, 0, 0x4442)), a3 = row0(__byte_perm(w, 0, 0x4443));
+        const uint32_t a0 = __byte_perm(w, tab_s, 0x7650), a1 = __byte_perm(w, tab_s, 0x7651);
+        const uint32_t a2 = __byte_perm(w, tab_s, 0x7652), a3 = __byte_perm(w, tab_s, 0x7653);
         s = lds_u8(s * ROW260 + a0);
         s = lds_u8(s * ROW260 + a1);
         s = lds_u8(s * ROW260 + a2);
@@ -132,7 +126,8 @@ constexpr int MAX_WARPS = 32, MAX_STAGES = 8;
 __host__ __device__ inline dfa_smem_plan_t dfa_smem_plan(uint32_t nstates, uint32_t nclasses, bool cls)
 {
     dfa_smem_plan_t p;
-    p.tab_bytes = align_up(cls ? (size_t) nstates * nclasses * 2 : (size_t) nstates * 256, 16);
+    /* (the [state][byte] tables: room for rows padded to ROW260 bytes) */
+    p.tab_bytes = align_up(cls ? (size_t) nstates * nclasses * 2 : (size_t) nstates * ROW260, 16);
     p.fin_ofs = p.tab_bytes;
     p.cls_ofs = p.fin_ofs + align_up(nstates, 16);
     p.bar_ofs = align_up(p.cls_ofs + (cls ? 256 : 0), 16);
