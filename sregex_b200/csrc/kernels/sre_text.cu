@@ -715,27 +715,44 @@ k_text_finish(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, si
     const uint32_t n = info & INFO_CNT;
     uint32_t total;
     const uint32_t before = block_exclusive(n, &total);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        /* warp 0 looks back 32 blocks at a time */
         volatile unsigned long long *st = status + 1;
+        const uint32_t lane = threadIdx.x;
         unsigned long long excl = 0;
         if (tile != 0) {
-            st[tile] = ((unsigned long long) total << 2) | 1ull;
-            __threadfence();
-            for (uint32_t j = tile; j-- > 0;) {
-                unsigned long long v;
-                while (((v = st[j]) & 3ull) == 0) {
+            if (lane == 0) {
+                st[tile] = ((unsigned long long) total << 2) | 1ull;
+                __threadfence();
+            }
+            for (int64_t hi = (int64_t) tile - 1; hi >= 0; hi -= 32) {
+                const int64_t j = hi - lane;            /* lane 0 = the nearest block */
+                unsigned long long v = 2ull;            /* (before block 0: a total of 0) */
+                if (j >= 0) {
+                    while (((v = st[j]) & 3ull) == 0) {
+                    }
                 }
-                excl += v >> 2;
-                if ((v & 3ull) == 2ull) {
+                /* the nearest block that knows the total up to itself ends the walk */
+                const uint32_t done = __ballot_sync(FULL, (v & 3ull) == 2ull);
+                const uint32_t upto = done ? (uint32_t) __ffs((int) done) - 1 : 31u;
+                unsigned long long part = lane <= upto ? v >> 2 : 0ull;
+#pragma unroll
+                for (uint32_t d = 16; d > 0; d >>= 1) {
+                    part += __shfl_xor_sync(FULL, part, d);
+                }
+                excl += part;
+                if (done) {
                     break;
                 }
             }
         }
-        st[tile] = ((excl + total) << 2) | 2ull;
-        __threadfence();
-        s_first = excl;
-        if ((size_t) tile == nfull / WB) {          /* the block that holds the tail piece */
-            *total_out = excl + total;
+        if (lane == 0) {
+            st[tile] = ((excl + total) << 2) | 2ull;
+            __threadfence();
+            s_first = excl;
+            if ((size_t) tile == nfull / WB) {      /* the block that holds the tail piece */
+                *total_out = excl + total;
+            }
         }
     }
     __syncthreads();
