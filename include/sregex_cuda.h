@@ -234,8 +234,12 @@ SRE_API int sre_cuda_index_lines(const uint8_t *dev_buf, size_t len,
  * '\n' ends at len.  *nlines = lines found (may exceed max_lines: then only the
  * first max_lines rows are written).  Programs whose DFA has a byte table of at
  * most 128 states take the one-pass kernel (dev_buf 16-byte aligned); the others
- * go through sre_cuda_index_lines + sre_cuda_thompson_exec_ragged.  Synchronises
- * the stream.
+ * go through sre_cuda_index_lines + sre_cuda_thompson_exec_ragged.  With
+ * dev_offsets == NULL and at most 64 states the verdict-only kernel runs (about
+ * twice as fast: no per-line records).  Synchronises the stream.
+ * Environment (tuning / tests): SRE_CUDA_TEXT_PIECE = bytes of text per CUDA
+ * thread in the verdict-only kernel (a multiple of 128 in [512, 4096]; default:
+ * fitted to the input).
  */
 SRE_API int sre_cuda_thompson_exec_text(sre_cuda_program_t *cp, const uint8_t *dev_buf,
     size_t len, int64_t *dev_offsets, int32_t *dev_rc, size_t max_lines, size_t *nlines,

@@ -804,19 +804,6 @@ k_text_finish(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, si
 
 }  // namespace
 
-size_t sre_text_workspace_bytes(size_t len)
-{
-    /* (the verdict path may cut pieces as small as MIN_PIECE) */
-    const size_t npieces = len / MIN_PIECE + 2, nb = (npieces + WB - 1) / WB;
-    return 256 + (nb + 2) * 8 + npieces * (CAP * 4 + 8) + 2048;
-}
-
-/* where in the workspace the number of lines is left (8 bytes) */
-size_t sre_text_count_offset(size_t)
-{
-    return 0;
-}
-
 /*
  * The piece size of the verdict path.  A thread walks its piece serially (~40 cycles per byte),
  * so below ~600 MB -- one 4 KB piece per resident thread -- the call takes the time of ONE piece
@@ -843,6 +830,20 @@ static uint32_t text_piece_bytes(size_t len, size_t threads_total)
         per *= 2;
     }
     return per;
+}
+
+size_t sre_text_workspace_bytes(size_t len)
+{
+    /* whichever path runs: the pieces the verdict path would cut, or 4 KB pieces */
+    const uint32_t piece = text_piece_bytes(len, (size_t) num_sms() * 1024);
+    const size_t npieces = len / piece + 2, nb = (npieces + WB - 1) / WB;
+    return 256 + (nb + 2) * 8 + npieces * (CAP * 4 + 8) + 2048;
+}
+
+/* where in the workspace the number of lines is left (8 bytes) */
+size_t sre_text_count_offset(size_t)
+{
+    return 0;
 }
 
 /* verdicts only, <= 64 states: count-only hot loop (k_text_verdicts) */
