@@ -649,8 +649,9 @@ def bench_nfa(h, steps, warmup, dev, host):
                                "1,048,576 x 1 KB log lines per GPU", "lines_per_gpu": n,
                    "nfa_states": prog.info.nfa_states, "dfa_states": prog.info.dfa_states,
                    "matched_lines": int((rc == 0).sum())},
-        "roofline": h.roofline(bytes_per_step + 4 * n, call_ms, "k_nfa64_lines",
-                               note="issue-bound by design: ~35 thread-instructions per byte"),
+        "roofline": h.roofline(bytes_per_step + 4 * n, call_ms, "k_nfa_packed<u32, K> (k_nfa64_lines beyond 4 non-shift movers)",
+                               note="ALU-pipe-bound by design: ~12 thread-instructions per byte, 7 of them on the "
+                                    "16-lane integer pipe"),
         "gpu_launches": launches, "clocks": clocks,
     }
     if h.rank == 0 and h.world == 1:

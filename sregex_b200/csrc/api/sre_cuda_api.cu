@@ -554,6 +554,18 @@ int upload(sre_cuda_program_t *cp)
         q.any_follow[0] = nfa64_any[0];
         q.any_follow[1] = nfa64_any[1];
         q.any_follow[2] = nfa64_any[2];
+        q.ncomplex = 0;
+        for (uint32_t st = 0; st < 64; st++) {
+            if ((nfa64_complex >> st) & 1) {
+                if (q.ncomplex < 4) {
+                    q.cidx[q.ncomplex] = (uint8_t) st;
+                }
+                q.ncomplex++;
+            }
+        }
+        if (q.ncomplex > 4) {
+            q.ncomplex = 0xffffffffu;
+        }
     }
 
     memset(&cp->pdfa, 0, sizeof(cp->pdfa));

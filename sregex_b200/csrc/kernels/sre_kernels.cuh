@@ -62,6 +62,11 @@ struct sre_dev_nfa64_t {
     const uint64_t   *mv, *mt;      /* [nclasses]                              */
     const uint64_t   *follow;       /* [nkinds][64] rows of the non-shift movers */
     uint64_t          init, mt_eof, shift_mask, complex_mask, any_follow[3];
+    /* the non-shift movers by number when there are at most 4 of them (the rule for regexes with
+     * bounded repetitions: one loop state and a run of shift states): the kernel then ORs their
+     * follow rows in under a mask instead of looping over set bits */
+    uint32_t          ncomplex;         /* 0xffffffff: more than 4 */
+    uint8_t           cidx[4];
 };
 cudaError_t sre_launch_nfa64_lines(const sre_dev_nfa64_t &nfa, const uint8_t *buf, size_t nlines, size_t pitch,
     size_t linelen, int32_t *rc, cudaStream_t stream, int *launches);

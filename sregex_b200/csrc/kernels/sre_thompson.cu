@@ -736,12 +736,16 @@ k_dfa_generic_hint(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, const int
  * S' = any_row | (M & shift) << 1 | OR of follow[s] over the other movers s.
  * The warp-per-line kernel below spends a whole warp on the same 64 bits.
  */
+/* K = number of non-shift movers handled without a loop (0..4), -1: any number (loop over the set
+ * bits: lanes diverge whenever some lane's byte moves such a state -- 20 of 32 lanes active on the
+ * bench regex; with the masked ORs all 32 are) */
+template <int K>
 struct nfa64_consumer_t {
     const uint64_t *mv, *mt, *follow;   /* shared memory: [nclasses], [nclasses], [nkinds][64] */
     const uint8_t  *cls, *kind;         /* shared memory: [256], [nclasses]                    */
     uint64_t        init, mt_eof, shiftm, complexm, anyrow[3];
     uint64_t        S, hit;
-    uint32_t        nkinds;
+    uint32_t        nkinds, cidx[4];
     size_t          nlines;
     int32_t        *rc;
 
@@ -757,16 +761,27 @@ struct nfa64_consumer_t {
             nxt = k == 0 ? anyrow[0] : k == 1 ? anyrow[1] : anyrow[2];
         }
         nxt |= (m & shiftm) << 1;
-        uint64_t cm = m & complexm;
-        while (cm) {
-            const uint32_t i = __ffsll((long long) cm) - 1;
-            cm &= cm - 1;
-            nxt |= follow[k * 64 + i];
+        if (K >= 0) {
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                const uint64_t on = 0ull - ((m >> cidx[j]) & 1ull);
+                nxt |= on & follow[k * 64 + cidx[j]];
+            }
+        } else {
+            uint64_t cm = m & complexm;
+            while (cm) {
+                const uint32_t i = __ffsll((long long) cm) - 1;
+                cm &= cm - 1;
+                nxt |= follow[k * 64 + i];
+            }
         }
         S = nxt;
     }
     __device__ __forceinline__ void chunk(const uint4 &v)
     {
+        if (hit != 0) {
+            return;             /* a step saw a live MATCH thread: the verdict is final */
+        }
         const uint32_t w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -785,6 +800,7 @@ struct nfa64_consumer_t {
     }
 };
 
+template <int K>
 __global__ void __launch_bounds__(1024, 1)
 k_nfa64_lines(sre_dev_nfa64_t nfa, const __grid_constant__ CUtensorMap tmap, size_t nlines, uint32_t linelen,
               int32_t *__restrict__ rc)
@@ -812,7 +828,10 @@ k_nfa64_lines(sre_dev_nfa64_t nfa, const __grid_constant__ CUtensorMap tmap, siz
     static_assert(BAR_OFS + MAX_WARPS * MAX_STAGES * 8 <= STAGE_OFS, "layout");
 
     const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
-    nfa64_consumer_t cons;
+    nfa64_consumer_t<K> cons;
+    for (int j = 0; j < 4; j++) {
+        cons.cidx[j] = nfa.cidx[j];
+    }
     cons.mv = s_mv;
     cons.mt = s_mt;
     cons.follow = s_follow;
@@ -1103,6 +1122,142 @@ cudaError_t launch_dfa_lines_early_t(const sre_dev_dfa_t &dfa, const uint8_t *bu
         grid = need;
     }
     kern<<<(unsigned) grid, THREADS, smem, stream>>>(dfa, tmap, nlines, (uint32_t) linelen, rc);
+    return cudaGetLastError();
+}
+
+
+/* ---- k_nfa_packed ----------------------------------------------------------- */
+
+/*
+ * The same step for programs with at most four non-shift movers (the rule for
+ * regexes whose bounded repetitions defeat determinisation: one loop state and a
+ * run of shift states), with everything a byte needs in ONE shared-memory entry
+ * per byte class: { mv, mt, the ".*?" row of the class's kind, the follow rows of
+ * the K movers for that kind }.  Per byte: the class (LDS.U8), the entry (one or
+ * two LDS.128, broadcast: text has few classes), and straight-line logic -- no
+ * kind look-up, no loop over set bits, no divergence.  W = uint32_t when the
+ * program has at most 32 lowered states (every 64-bit operation of k_nfa64_lines
+ * is two instructions), else uint64_t.
+ */
+template <typename W, int K>
+struct nfa_packed_consumer_t {
+    static constexpr int NW = 3 + K;                                   /* words per entry */
+    static constexpr int NV = (NW * (int) sizeof(W) + 15) / 16;         /* uint4 per entry */
+    uint32_t        ent_s, cls_s;       /* shared-window addresses: entries [nclasses], class map [256] */
+    W               init, mt_eof, shiftm, cbit[K > 0 ? K : 1];
+    W               S, hit;
+    size_t          nlines;
+    int32_t        *rc;
+
+    __device__ __forceinline__ void begin(size_t) { S = init; hit = 0; }
+    __device__ __forceinline__ void byte(uint32_t b)
+    {
+        uint32_t c;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(c) : "r"(cls_s + b));
+        union {
+            uint4 v[NV];
+            W     w[NV * 16 / sizeof(W)];
+        } e;
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                : "=r"(e.v[i].x), "=r"(e.v[i].y), "=r"(e.v[i].z), "=r"(e.v[i].w)
+                : "r"(ent_s + c * (uint32_t) (NV * 16) + (uint32_t) i * 16));
+        }
+        hit |= S & e.w[1];
+        const W m = S & e.w[0];
+        W nxt = e.w[2] | (W) ((m & shiftm) << 1);
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            nxt |= (m & cbit[j]) ? e.w[3 + j] : (W) 0;
+        }
+        S = nxt;
+    }
+    __device__ __forceinline__ void chunk(const uint4 &v)
+    {
+        if (hit != 0) {
+            return;             /* a step saw a live MATCH thread: the verdict is final */
+        }
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                byte(__byte_perm(w[i], 0, 0x4440 + q));
+            }
+        }
+    }
+    __device__ __forceinline__ void end(size_t group)
+    {
+        const size_t line = group * 32 + (threadIdx.x & 31);
+        if (line < nlines) {
+            rc[line] = (hit != 0 || (S & mt_eof) != 0) ? SRE_K_OK : SRE_K_DECLINED;
+        }
+    }
+};
+
+template <typename W, int K>
+__global__ void __launch_bounds__(1024, 1)
+k_nfa_packed(sre_dev_nfa64_t nfa, const __grid_constant__ CUtensorMap tmap, size_t nlines, uint32_t linelen,
+             int32_t *__restrict__ rc)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    using cons_t = nfa_packed_consumer_t<W, K>;
+    /* [entries 256 x NV x 16][cls 256][barriers][stages] */
+    constexpr size_t ENT_BYTES = (size_t) 256 * cons_t::NV * 16, CLS_OFS = ENT_BYTES, BAR_OFS = CLS_OFS + 256,
+                     STAGE_OFS = (BAR_OFS + MAX_WARPS * MAX_STAGES * 8 + 1023) / 1024 * 1024;
+    W *ent = reinterpret_cast<W *>(smem);
+    constexpr int EW = cons_t::NV * 16 / (int) sizeof(W);
+    for (uint32_t c = threadIdx.x; c < nfa.nclasses; c += blockDim.x) {
+        const uint32_t k = nfa.nkinds == 1 ? 0u : nfa.cls_kind[c];
+        W *e = ent + (size_t) c * EW;
+        e[0] = (W) nfa.mv[c];
+        e[1] = (W) nfa.mt[c];
+        e[2] = (W) nfa.any_follow[k];
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            e[3 + j] = (W) nfa.follow[k * 64 + nfa.cidx[j]];
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        smem[CLS_OFS + i] = nfa.clsmap[i];
+    }
+    __syncthreads();
+
+    const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    cons_t cons;
+    cons.ent_s = smem_u32(smem);
+    cons.cls_s = smem_u32(smem + CLS_OFS);
+    cons.init = (W) nfa.init;
+    cons.mt_eof = (W) nfa.mt_eof;
+    cons.shiftm = (W) nfa.shift_mask;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        cons.cbit[j] = (W) ((uint64_t) 1 << nfa.cidx[j]);
+    }
+    cons.nlines = nlines;
+    cons.rc = rc;
+    tile_pipeline_tma_early<1>(cons, &tmap, nlines, linelen, smem + STAGE_OFS + (size_t) warp * 32 * 128,
+                               reinterpret_cast<uint64_t *>(smem + BAR_OFS) + warp * MAX_STAGES,
+                               (size_t) blockIdx.x * warps_per_block + warp, (size_t) gridDim.x * warps_per_block);
+}
+
+template <typename W, int K>
+static cudaError_t launch_nfa_packed_t(const sre_dev_nfa64_t &nfa, const CUtensorMap &tmap, size_t nlines,
+    size_t linelen, int32_t *rc, size_t grid, cudaStream_t stream)
+{
+    constexpr size_t NV = nfa_packed_consumer_t<W, K>::NV;
+    const size_t smem = (256 * NV * 16 + 256 + MAX_WARPS * MAX_STAGES * 8 + 1023) / 1024 * 1024 + (size_t) 32 * 32 * 128;
+    auto kern = k_nfa_packed<W, K>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        const cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (err != cudaSuccess) {
+            return err;
+        }
+        attr_set = true;
+    }
+    kern<<<(unsigned) grid, 1024, smem, stream>>>(nfa, tmap, nlines, (uint32_t) linelen, rc);
     return cudaGetLastError();
 }
 
@@ -1404,13 +1559,40 @@ cudaError_t sre_launch_nfa64_lines(const sre_dev_nfa64_t &nfa, const uint8_t *bu
     if (err != cudaSuccess) {
         return err;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        err = cudaFuncSetAttribute(k_nfa64_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (nfa.ncomplex <= 4) {
+        const size_t ngroups = (nlines + 31) / 32;
+        size_t grid = (size_t) num_sms();
+        const size_t need = (ngroups + warps - 1) / warps;
+        if (grid > need) {
+            grid = need;
+        }
+        if (launches) {
+            ++*launches;
+        }
+        const bool w32 = nfa.nstates <= 32;
+        switch (nfa.ncomplex) {
+#define SRE_PACKED(KK)                                                                                       \
+        case KK: return w32 ? launch_nfa_packed_t<uint32_t, KK>(nfa, tmap, nlines, linelen, rc, grid, stream) \
+                            : launch_nfa_packed_t<uint64_t, KK>(nfa, tmap, nlines, linelen, rc, grid, stream);
+        SRE_PACKED(0)
+        SRE_PACKED(1)
+        SRE_PACKED(2)
+        SRE_PACKED(3)
+        SRE_PACKED(4)
+#undef SRE_PACKED
+        }
+    }
+    typedef void (*kern_t)(sre_dev_nfa64_t, const CUtensorMap, size_t, uint32_t, int32_t *);
+    static const kern_t kerns[6] = { k_nfa64_lines<-1>, k_nfa64_lines<0>, k_nfa64_lines<1>, k_nfa64_lines<2>,
+                                     k_nfa64_lines<3>, k_nfa64_lines<4> };
+    const int ki = nfa.ncomplex <= 4 ? (int) nfa.ncomplex + 1 : 0;
+    static bool attr_set[6];
+    if (!attr_set[ki]) {
+        err = cudaFuncSetAttribute(kerns[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (err != cudaSuccess) {
             return err;
         }
-        attr_set = true;
+        attr_set[ki] = true;
     }
     const size_t ngroups = (nlines + 31) / 32;
     size_t grid = (size_t) num_sms();
@@ -1421,7 +1603,7 @@ cudaError_t sre_launch_nfa64_lines(const sre_dev_nfa64_t &nfa, const uint8_t *bu
     if (launches) {
         ++*launches;
     }
-    k_nfa64_lines<<<(unsigned) grid, warps * 32, smem, stream>>>(nfa, tmap, nlines, (uint32_t) linelen, rc);
+    kerns[ki]<<<(unsigned) grid, warps * 32, smem, stream>>>(nfa, tmap, nlines, (uint32_t) linelen, rc);
     return cudaGetLastError();
 }
 

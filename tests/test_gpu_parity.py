@@ -940,6 +940,24 @@ def test_nfa_tier_on_a_regex_that_defeats_determinisation(cu):
                                     nthreads=8)
     got = prog.thompson_lines(log.cuda(), 2048, 1024, 1024).cpu().numpy()
     assert (got == want).all()
+    # the packed-entry kernel in its other shapes: 33..64 lowered states (64-bit sets), several loop
+    # states (non-shift movers), assertions (more than one kind of byte), more than four movers
+    # (the looping form); ragged line lengths exercise the byte-wise last tile
+    rs = np.random.RandomState(5)
+    sigma = np.frombuffer(b"abcde x\n", dtype=np.uint8)
+    n = 1500
+    for rx in (rb"[ab]*a[ab]{40}c", rb"(a|b)*x[ab]{35}(c|d)+e", rb"\b[ab]+ [ab]{20}\b", rb"^[ab]*a[ab]{12}c$",
+               rb"(a*b*c*d*e*x)+[ab]{30}", rb"[ab]*a[ab]{15}c|[cd]*c[cd]{15}a|x+e+x"):
+        prog = cu.CudaProgram(rx)
+        assert prog.info.nfa_states <= 64, (rx, prog.info.nfa_states)
+        for linelen in (16, 100, 256):
+            lines = sigma[rs.choice(len(sigma), size=(n, 256), p=[0.3, 0.3, 0.1, 0.08, 0.08, 0.06, 0.06, 0.02])].copy()
+            _, want, _ = baseline.run_lines("oracle", rx, None, lines, n, 256, linelen, baseline.ENGINE_THOMPSON,
+                                            nthreads=8)
+            dev = torch.from_numpy(lines).cuda()
+            for engine in (cu.ENGINE_NFA, cu.ENGINE_NFA_WARP):
+                got = prog.thompson_lines(dev, n, 256, linelen, engine=engine).cpu().numpy()
+                assert (got == want).all(), (rx, linelen, engine, int((got != want).sum()))
 
 
 def test_batched_streaming_pike_contexts(cu):
