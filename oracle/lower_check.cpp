@@ -507,7 +507,9 @@ extern "C" long lc_pdfa_pike(sre_program_t *prog, const uint8_t *input, long siz
     const uint32_t C = D.nclasses;
     const size_t nslots = T.max_slots;
     std::vector<uint16_t> hist((size_t) ring, 0);
-    uint32_t s = D.init;
+    /* the start list by look-behind context (sre_closure.h): offset 0 / after '\n' / elsewhere */
+    const uint32_t v0 = start <= 0 ? 0u : (input[start - 1] == '\n' ? 1u : 2u);
+    uint32_t s = D.init[v0];
     long pos = start, mpos = -1;
     bool have = false, at_eof = false;
     for (; pos < size && s != 0; pos++) {
@@ -561,7 +563,7 @@ extern "C" long lc_pdfa_pike(sre_program_t *prog, const uint8_t *input, long siz
             break;                          /* the ".*?" thread carries no captures */
         }
         if (u < start) {
-            assign(D.init_mask[j], start);  /* a thread of the start closure */
+            assign(D.init_mask[D.init_mask_ofs[v0] + j], start);    /* a thread of the start closure */
             break;
         }
         if (u <= oldest) return -1001;

@@ -309,6 +309,29 @@ struct sre_vm_pike_ctx_s {
 
 /* test statistic: longest Pike thread list seen (sizing of the GPU kernels) */
 static uint32_t oracle_max_list;
+/*
+ * The reference's first-byte prefilter (sre_vm_pike.c:256-309) is not result
+ * neutral: its "is the list the initial one?" test compares the thread COUNT and
+ * every pc but the LAST (:262-274, `t && t->next`).  Before a match the last
+ * thread is always the ".*?" one, so the test is exact; but once a match has cut
+ * that thread, a list of survivors that happens to have the initial list's
+ * length and leading pcs -- /a+b?/ after matching one 'a': [a-loop, b] against
+ * the initial [a-loop, .*?] -- passes for the initial list.  If that happens
+ * right after a prefilter jump (seen_start_state still set), the survivors are
+ * dropped and the search starts over at the next leading byte, a later match
+ * overwriting the leftmost one: /a+b?/ on ".a.a" reports (3, 4), on " ab" it
+ * reports (1, 2).  This oracle restates that faithfully (prefilter on, the
+ * default: equal to the reference on every input).  With the prefilter left out
+ * it computes what the Pike VM computes without the shortcut -- the leftmost-
+ * first match -- which is what libsregex_cuda implements.
+ */
+static int oracle_prefilter = 1;
+
+SRE_API void oracle_pike_prefilter(int on)
+{
+    oracle_prefilter = on;
+}
+
 SRE_API uint32_t oracle_pike_max_list(int reset)
 {
     uint32_t v = oracle_max_list;
@@ -632,8 +655,8 @@ sre_vm_pike_exec(sre_vm_pike_ctx_t *ctx, sre_char *input, size_t size,
             break;
         }
 
-        /* first-byte prefilter, :256-309 */
-        if (prog->nleading && ctx->seen_start_state) {
+        /* first-byte prefilter, :256-309 (oracle_pike_prefilter(0) leaves it out: see there) */
+        if (oracle_prefilter && prog->nleading && ctx->seen_start_state) {
             ctx->seen_start_state = 0;
             if (sp == last || clist->count != ctx->initial_states_count) {
                 goto run_cur_threads;

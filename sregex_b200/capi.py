@@ -185,6 +185,13 @@ class SreLib:
                 L.sre_vm_thompson_jit_free(code)
             L.sre_destroy_pool(pool)
 
+    def pike_prefilter(self, on: bool):
+        """checker libraries only (oracle): run the Pike VM with / without the reference's
+        first-byte prefilter (oracle/sre_oracle.c: oracle_pike_prefilter)"""
+        self.L.oracle_pike_prefilter.argtypes = [C.c_int]
+        self.L.oracle_pike_prefilter.restype = None
+        self.L.oracle_pike_prefilter(1 if on else 0)
+
     # -- Pike ----------------------------------------------------------------
     def pike(self, p: Program, data: bytes, chunks=None):
         """chunks=None: one exec(data, eof=1) -> (rc, ovector list).

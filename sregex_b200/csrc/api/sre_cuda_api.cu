@@ -402,7 +402,7 @@ int upload(sre_cuda_program_t *cp)
     sre_pdfa_t pd;
     const bool has_pd = has_clo && sre_build_pdfa(prog, clo, 4096, pd);
     size_t o_pcls = 0, o_ptrans = 0, o_peofs = 0, o_pent = 0, o_pmev = 0, o_peof = 0, o_pinit = 0;
-    uint32_t pd_nent = 0, pd_init_any = 0xff;
+    uint32_t pd_nent = 0, pd_init_any[3] = { 0xff, 0xff, 0xff };
     if (has_pd) {
         /* device form of the provenance records (see sre_dev_pdfa_t) */
         const uint32_t C = pd.nclasses;
@@ -421,7 +421,9 @@ int upload(sre_cuda_program_t *cp)
             eofv[st] = pd.eof_idx[st] | ((uint32_t) pd.eof_regex[st] << 16);
         }
         pd_nent = (uint32_t) pd.eparent.size();
-        pd_init_any = pd.any_idx[pd.init];
+        for (int v = 0; v < 3; v++) {
+            pd_init_any[v] = pd.any_idx[pd.init[v]];
+        }
         o_pcls = b.add(pd.clsmap, 256);
         o_ptrans = b.add(pd.trans.data(), pd.trans.size() * 2);
         o_peofs = b.add(pd.eofs.data(), pd.eofs.size() * 4);
@@ -573,10 +575,14 @@ int upload(sre_cuda_program_t *cp)
         sre_dev_pdfa_t &d = cp->pdfa;
         d.nstates = pd.nstates;
         d.nclasses = pd.nclasses;
-        d.init = pd.init;
+        for (int v = 0; v < 3; v++) {
+            d.init[v] = pd.init[v];
+            d.init_any[v] = pd_init_any[v];
+            d.init_mask_ofs[v] = pd.init_mask_ofs[v];
+        }
+        d.ctx_dep = pd.ctx_dep ? 1u : 0u;
         d.max_slots = pd.max_slots;
         d.nent = pd_nent;
-        d.init_any = pd_init_any;
         d.clsmap = base + o_pcls;
         d.trans = reinterpret_cast<const uint16_t *>(base + o_ptrans);
         d.eofs = reinterpret_cast<const uint32_t *>(base + o_peofs);

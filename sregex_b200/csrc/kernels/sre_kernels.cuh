@@ -236,9 +236,12 @@ cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf,
 /* the determinised Pike VM (lower/sre_pdfa.h; nstates == 0: none) and its capture kernel
  * (sre_pike_lineage.cu): same contract as sre_launch_pike_table, pass 0 */
 struct sre_dev_pdfa_t {
-    uint32_t         nstates, nclasses, init, max_slots;
+    uint32_t         nstates, nclasses, max_slots;
     uint32_t         nent;          /* provenance records                      */
-    uint32_t         init_any;      /* index of the ".*?" thread in the start closure, 0xff: none */
+    /* the start closure by look-behind context (0: at offset 0, 1: after a newline, 2: elsewhere;
+     * all alike unless ctx_dep): its state, the index of the ".*?" thread in it (0xff: none),
+     * where its slots begin in init_mask */
+    uint32_t         init[3], init_any[3], init_mask_ofs[3], ctx_dep;
     const uint8_t   *clsmap;        /* [256]                                   */
     const uint16_t  *trans;         /* [nstates][nclasses] next | 0x8000 match */
     /* provenance of the threads of a transition's next list: record eofs[t] + j =
@@ -249,7 +252,7 @@ struct sre_dev_pdfa_t {
     /* the thread that matched in a transition with bit 15: { slots, parent | 0x100 | regex << 16 } */
     const uint2     *mev;           /* [nstates * nclasses]                    */
     const uint32_t  *eof;           /* [nstates] first parked MATCH thread (EOF step): index | regex << 16, 0xff: none */
-    const uint32_t  *init_mask;     /* slots SAVEd by the start closure, per thread */
+    const uint32_t  *init_mask;     /* slots SAVEd by a start closure, per thread */
 };
 bool sre_pike_lineage_applicable(const sre_dev_pdfa_t &d, size_t linelen);
 cudaError_t sre_launch_pike_lineage(const sre_dev_pdfa_t &d, const uint8_t *buf, const int64_t *offsets,

@@ -142,7 +142,13 @@ k_pike_lineage(sre_dev_pdfa_t d, const uint8_t *__restrict__ buf, const int64_t 
         auto slot = [&](int32_t p) -> RT * { return ring_at((in_lo + (uint32_t) p) & (RING - 1)); };
 
         /* forward: the transition taken at every position, the last one that reported a match */
-        uint32_t s = d.init;
+        /* the start list by what lies before the first byte looked at (the look-behind context of
+         * `\A` / `^`): nothing, a newline, anything else */
+        uint32_t v0 = 0;
+        if (d.ctx_dep && start > 0) {
+            v0 = __ldg(input + start - 1) == '\n' ? 1u : 2u;
+        }
+        uint32_t s = d.init[v0];
         int32_t pos = start, mpos = -1;
         auto step = [&](uint32_t b, int32_t p, RT *where) {
             uint32_t e;
@@ -253,8 +259,8 @@ k_pike_lineage(sre_dev_pdfa_t d, const uint8_t *__restrict__ buf, const int64_t 
         }
         while (!lost && !stop) {
             if (u < start) {
-                if (j != d.init_any) {
-                    assign(__ldg(d.init_mask + j), start);      /* a thread of the start closure */
+                if (j != d.init_any[v0]) {
+                    assign(__ldg(d.init_mask + d.init_mask_ofs[v0] + j), start);   /* a thread of the start closure */
                 }
                 break;
             }

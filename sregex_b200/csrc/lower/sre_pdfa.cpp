@@ -14,9 +14,10 @@
 bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uint32_t max_states, sre_pdfa_t &out)
 {
     const uint32_t np = T.npark;
-    if (np == 0 || T.ctx_dep || max_states > 0x7fff) {
+    if (np == 0 || max_states > 0x7fff) {
         return false;
     }
+    out.ctx_dep = T.ctx_dep;
     for (uint32_t P = 0; P < np; P++) {
         if (T.kind[P] >= 2) {
             return false;           /* look-ahead assertions: not a function of the byte alone */
@@ -28,10 +29,12 @@ bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uin
     {
         std::map<std::vector<uint8_t>, uint32_t> sigs;
         for (uint32_t b = 0; b < 256; b++) {
-            std::vector<uint8_t> sig(T.nsets);
+            std::vector<uint8_t> sig(T.nsets + 1);
             for (uint32_t k = 0; k < T.nsets; k++) {
                 sig[k] = (T.accept[(size_t) k * 8 + (b >> 5)] >> (b & 31)) & 1;
             }
+            /* the look-behind context a byte leaves: '\n' apart when closures depend on it */
+            sig[T.nsets] = T.ctx_dep && b == '\n';
             std::map<std::vector<uint8_t>, uint32_t>::iterator it = sigs.find(sig);
             if (it == sigs.end()) {
                 it = sigs.insert(std::make_pair(sig, (uint32_t) sigs.size())).first;
@@ -55,11 +58,17 @@ bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uin
     lists.push_back(list_t());          /* state 0: the empty list */
     ids[list_t()] = 0;
 
-    /* the start closure (closure of "pc 0", number np), context 0 */
-    {
+    /* the start closures (closure of "pc 0", number np) by look-behind context */
+    for (uint32_t v = 0; v < 3; v++) {
+        if (v > 0 && !T.ctx_dep) {
+            out.init[v] = out.init[0];
+            out.init_mask_ofs[v] = out.init_mask_ofs[0];
+            continue;
+        }
         list_t init;
         std::vector<uint8_t> marks(np, 0);
-        for (uint32_t e = T.ofs[np]; e < T.ofs[np + 1]; e++) {
+        out.init_mask_ofs[v] = (uint32_t) out.init_mask.size();
+        for (uint32_t e = T.ofs[v * (np + 2) + np]; e < T.ofs[v * (np + 2) + np + 1]; e++) {
             const uint32_t fp = T.ent[e];
             if (marks[fp]) {
                 continue;
@@ -71,9 +80,14 @@ bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uin
         if (init.empty() || init.size() > 255) {
             return false;
         }
-        out.init = 1;
-        lists.push_back(init);
-        ids[init] = 1;
+        std::map<list_t, uint32_t>::iterator it = ids.find(init);
+        if (it == ids.end()) {
+            out.init[v] = (uint32_t) lists.size();
+            ids[init] = out.init[v];
+            lists.push_back(init);
+        } else {
+            out.init[v] = it->second;
+        }
     }
 
     std::vector<uint8_t> marks(np);
@@ -81,6 +95,8 @@ bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uin
         for (uint32_t c = 0; c < C; c++) {
             const list_t cur = lists[s];        /* copy: lists grows below */
             const uint32_t b = rep[c];
+            /* closures appended after this byte see it as their look-behind context */
+            const uint32_t vofs = (T.ctx_dep ? (b == '\n' ? 1u : 2u) : 0u) * (np + 2);
             list_t next;
             std::vector<uint8_t> parents;
             std::vector<uint32_t> masks;
@@ -102,7 +118,7 @@ bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uin
                 if (!accepts(P, b)) {
                     continue;
                 }
-                for (uint32_t e = T.ofs[P]; e < T.ofs[P + 1]; e++) {
+                for (uint32_t e = T.ofs[vofs + P]; e < T.ofs[vofs + P + 1]; e++) {
                     const uint32_t fp = T.ent[e];
                     if (marks[fp]) {
                         continue;

@@ -25,9 +25,14 @@
  * slot from the last step that SAVEd it.  Leftmost-first priority is the list
  * order, so the result is the Pike VM's, bit for bit.
  *
- * Built for programs without assertions (their closures depend on more than the
- * byte); sre_build_pdfa returns false for the others and when the automaton
- * exceeds max_states / lists of 255 threads: those stay on k_pike_table.
+ * Look-behind assertions (`\A`, `^`) are part of it: the closure a step appends
+ * depends on the consumed byte only through "was it a newline" (the look-behind
+ * context of sre_closure.h), so '\n' gets a byte class of its own and the search
+ * starts from one of three start lists (at offset 0 / after a newline /
+ * elsewhere).  Built for programs without look-AHEAD assertions (`$ \z \b \B`:
+ * their closures wait for the next byte); sre_build_pdfa returns false for those
+ * and when the automaton exceeds max_states / lists of 255 threads: they stay on
+ * k_pike_table.
  */
 #ifndef SRE_PDFA_H
 #define SRE_PDFA_H
@@ -40,7 +45,10 @@ struct sre_pdfa_t {
     uint32_t                nstates = 0;        /* state 0 = the empty list           */
     uint32_t                nclasses = 0;
     uint8_t                 clsmap[256];
-    uint32_t                init = 0;           /* the start closure                  */
+    uint32_t                init[3] = { 0, 0, 0 };      /* the start closure by look-behind context:
+                                                           at offset 0, after a newline, elsewhere */
+    uint32_t                init_mask_ofs[3] = { 0, 0, 0 };     /* ... where its init_mask begins */
+    bool                    ctx_dep = false;    /* the three differ (program has \A or ^) */
     uint32_t                max_slots = 0;      /* slots of the largest regex (<= 32) */
     std::vector<uint16_t>   trans;              /* [nstates][nclasses]                */
     std::vector<uint32_t>   eofs;               /* [nstates * nclasses + 1]           */
@@ -52,7 +60,7 @@ struct sre_pdfa_t {
     std::vector<uint8_t>    any_idx;            /* [nstates] index of the ".*?" thread, 0xff: none */
     std::vector<uint8_t>    eof_idx;            /* [nstates] first parked MATCH (EOF step), 0xff   */
     std::vector<uint16_t>   eof_regex;          /* [nstates]                          */
-    std::vector<uint32_t>   init_mask;          /* slots SAVEd by the start closure, per thread    */
+    std::vector<uint32_t>   init_mask;          /* slots SAVEd by a start closure, per thread (init_mask_ofs) */
     std::vector<uint32_t>   list_ofs;           /* [nstates + 1] the lists themselves */
     std::vector<uint16_t>   list_park;
 };

@@ -64,5 +64,18 @@ def cuda():
     return capi.load("cuda")
 
 
+@pytest.fixture(scope="module")
+def leftmost_first():
+    """For the module's comparisons of OUR Pike results with the oracle: the oracle without the
+    reference's first-byte prefilter, i.e. the leftmost-first match the Pike VM computes when that
+    shortcut does not misfire (oracle/sre_oracle.c: oracle_pike_prefilter).  The
+    oracle WITH the prefilter is pinned to the reference in tests/test_oracle.py."""
+    from sregex_b200 import capi
+    o = capi.load("oracle")
+    o.pike_prefilter(False)
+    yield o
+    o.pike_prefilter(True)
+
+
 def runnable(golden):
     return [b for b in golden["blocks"] if "skip" not in b and "error" not in b]

@@ -13,6 +13,15 @@ from sregex_b200 import capi, corpus
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _leftmost_first(leftmost_first):
+    """every Pike comparison with the oracle in this module is with the leftmost-first match (the
+    reference's prefilter misfire is pinned in test_oracle.py and shown below in
+    test_pike_is_leftmost_first_where_the_reference_prefilter_misfires)"""
+    yield leftmost_first
+
+
+
 @pytest.fixture(scope="module")
 def cu():
     from sregex_b200 import cuda
@@ -410,6 +419,22 @@ def test_pike_tier_selection(cu):
     rc, _ = prog.pike_lines(dev, n, 1024, 1024)
     assert prog.last_pike_tier() == 3
     assert int((rc == 0).sum()) == n
+    # look-behind assertions (^, \A) are part of the determinised Pike VM (the start list and the
+    # closures depend on "after a newline / at offset 0"); look-ahead ones ($ \b) stay on the
+    # closure-table kernel.  Same rows as the oracle either way, on lines with inner newlines.
+    o = capi.load("oracle")
+    lines = corpus.log_lines(n, 1024).numpy().copy()
+    lines[:, 200] = 10
+    lines[::2, 201:204] = np.frombuffer(b"GET", dtype=np.uint8)
+    dev = torch.from_numpy(lines).cuda()
+    for rx, tier in ((rb"^(\d+)\.(\d+)", 3), (rb"^(GET|\d+)(.)", 3), (rb"\A(\d+)", 3), (rb"(\w+)$", 0), (rb"\b(GET)\b", 0)):
+        prog = cu.CudaProgram(rx)
+        rc, ov = prog.pike_lines(dev, n, 1024, 1024)
+        assert prog.last_pike_tier() == tier, (rx, prog.last_pike_tier())
+        _, wrc, wov = baseline.run_lines("oracle", rx, None, lines, n, 1024, 1024, baseline.ENGINE_PIKE,
+                                         ovec_slots=prog.nslots)
+        assert (rc.cpu().numpy() == wrc).all() and (ov.cpu().numpy() == wov).all(), rx
+    assert o is not None
 
 
 def test_pike_lineage_long_matches_fall_through(cu):
@@ -958,6 +983,34 @@ def test_nfa_tier_on_a_regex_that_defeats_determinisation(cu):
             for engine in (cu.ENGINE_NFA, cu.ENGINE_NFA_WARP):
                 got = prog.thompson_lines(dev, n, 256, linelen, engine=engine).cpu().numpy()
                 assert (got == want).all(), (rx, linelen, engine, int((got != want).sum()))
+
+
+def test_pike_is_leftmost_first_where_the_reference_prefilter_misfires(cu):
+    """Every Pike tier (determinised, closure tables, shared-memory, general) and the classic
+    sre_vm_pike_exec return the leftmost-first match on the inputs where the reference's first-byte
+    prefilter misfires and reports a later one (sre_vm_pike.c:262-274; the cases and the
+    reference's own answers are in test_oracle.py::QUIRK_CASES)."""
+    from test_oracle import QUIRK_CASES
+    o = capi.load("oracle")
+    cuda_lib = capi.load("cuda")
+    pitch = 32
+    for rx, s, _want_ref, want in QUIRK_CASES:
+        prog = cu.CudaProgram(rx)
+        po = o.compile(rx, 0)
+        assert o.pike(po, s) == want            # (the module runs the oracle without the prefilter)
+        host = np.zeros((1, pitch), dtype=np.uint8)
+        host[0, : len(s)] = np.frombuffer(s, dtype=np.uint8)
+        dev = torch.from_numpy(host).cuda()
+        for tier in (0, 1, 2, 3):
+            prog.set_pike_tier(tier)
+            rc, ov = prog.pike_lines(dev, 1, pitch, len(s))
+            got = (int(rc[0]), ov[0].cpu().tolist() if int(rc[0]) >= 0 else None)
+            assert got == want, (rx, s, tier, got)
+        pc = cuda_lib.compile(rx, 0)
+        assert cuda_lib.pike(pc, s) == want, (rx, s, "classic")
+        pc.close()
+        po.close()
+        prog.program.close()
 
 
 def test_batched_streaming_pike_contexts(cu):

@@ -289,9 +289,9 @@ def _bind_pdfa(lc):
                                 C.POINTER(C.c_uint)]
 
 
-def test_pdfa_pike_against_golden(golden, oracle, lc):
+def test_pdfa_pike_against_golden(golden, oracle, lc, leftmost_first):
     """The determinised Pike VM (ordered thread lists as DFA states + lineage walk,
-    lower/sre_pdfa.cpp) on every golden block it applies to (no assertions): rc and
+    lower/sre_pdfa.cpp) on every golden block it applies to (no look-ahead assertions): rc and
     the whole ovector; with a short ring it either agrees or asks for the next tier."""
     _bind_pdfa(lc)
     n = short = 0
@@ -309,16 +309,17 @@ def test_pdfa_pike_against_golden(golden, oracle, lc):
     assert n > 1000 and short > 20, (n, short)
 
 
-def test_pdfa_pike_fuzz_vs_oracle(oracle, lc):
-    """random assertion-free regexes (nested groups, lazy and greedy repetition,
-    alternation, empty loops) and sets of them x random subjects, searched from
-    offset 0 and from a later start: rc + ovector == the oracle's Pike"""
+def test_pdfa_pike_fuzz_vs_oracle(oracle, lc, leftmost_first):
+    """random regexes without look-ahead assertions (nested groups, lazy and greedy
+    repetition, alternation, empty loops, `^` and `\\A` over subjects with newlines)
+    and sets of them x random subjects: rc + ovector == the oracle's Pike"""
     import random
     _bind_pdfa(lc)
     rng = random.Random(31337)
     atoms = ["a", "b", "ab", " ", "_", ".", "|", "(", ")", "(?:", "*", "+", "?", "*?", "+?", "??", "{2}", "{0,2}",
-             "{1,}", "[ab]", "[^a]", "\\w", "\\W", "\\s", "\\d", "1", "(a)", "(b*)", "(a|ab)", "(\\w+)"]
-    alphabet = b"ab _1."
+             "{1,}", "[ab]", "[^a]", "\\w", "\\W", "\\s", "\\d", "1", "(a)", "(b*)", "(a|ab)", "(\\w+)",
+             "^", "\\A", "\\n", "(^a)", "(?:^|b)"]
+    alphabet = b"ab _1.\n\n"
     done = applicable = 0
     while done < 1500:
         k = 1 if rng.random() < 0.7 else rng.randrange(2, 5)

@@ -88,3 +88,51 @@ def test_post_match_continuation_against_live_reference(golden, oracle, ref):
         po.close()
         pr.close()
     assert n > 900
+
+
+QUIRK_CASES = [
+    # regex, subject, the reference's answer, the leftmost-first answer
+    (rb"a+b?", b".a.a", (0, [3, 4]), (0, [1, 2])),
+    (rb"a+b?", b" ab cd", (0, [1, 2]), (0, [1, 3])),
+    (rb"\w+x?", b".b.a", (0, [3, 4]), (0, [1, 2])),
+    (rb"\d+\.?", b"-1-2", (0, [3, 4]), (0, [1, 2])),
+    (rb"\d+\.?", b"x.b.1.b a", (0, [4, 5]), (0, [4, 6])),
+    (rb"(\w+) ?", b".b.a", (0, [3, 4, 3, 4]), (0, [1, 2, 1, 2])),
+    (rb"(\w+)+(\w+)?", b".b.1.b a", (0, [7, 8, 7, 8, -1, -1]), (0, [1, 2, 1, 2, -1, -1])),
+    # ... and where it does not misfire both agree
+    (rb"a+b?", b"b.a", (0, [2, 3]), (0, [2, 3])),
+    (rb"\w+x?", b" ab cd", (0, [1, 3]), (0, [1, 3])),
+]
+
+
+def test_first_byte_prefilter_misfire_is_the_references(golden, oracle, ref):
+    """The reference's first-byte prefilter is not result neutral (sre_vm_pike.c:262-274 compares
+    the thread count and every pc but the last: after a match has cut the ".*?" thread, survivors
+    can pass for the initial list, get dropped, and a LATER match overwrites the leftmost one).
+    The oracle restates that bit for bit (== the live reference on these cases); with the
+    prefilter left out it gives the leftmost-first match, which is what the CUDA tiers implement
+    (tests/test_gpu_parity.py).  On the whole golden corpus the two coincide: the reference's own
+    test suite never meets the misfire."""
+    for rx, s, want_ref, want_clean in QUIRK_CASES:
+        po, pr = oracle.compile(rx, 0), ref.compile(rx, 0)
+        assert ref.pike(pr, s) == want_ref, (rx, s)
+        assert oracle.pike(po, s) == want_ref, (rx, s)
+        oracle.pike_prefilter(False)
+        try:
+            assert oracle.pike(po, s) == want_clean, (rx, s)
+        finally:
+            oracle.pike_prefilter(True)
+        po.close()
+        pr.close()
+    differ = 0
+    for b in runnable(golden):
+        p = oracle.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        on = oracle.pike(p, b["subject_b"])
+        oracle.pike_prefilter(False)
+        try:
+            off = oracle.pike(p, b["subject_b"])
+        finally:
+            oracle.pike_prefilter(True)
+        differ += on != off
+        p.close()
+    assert differ == 0
