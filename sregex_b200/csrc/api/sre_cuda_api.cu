@@ -25,6 +25,7 @@
 #include "../lower/sre_closure.h"
 #include "../lower/sre_image.h"
 #include "../lower/sre_pdfa.h"
+#include "../lower/sre_quirk.h"
 
 namespace {
 
@@ -631,6 +632,7 @@ int upload(sre_cuda_program_t *cp)
     pk.max_slots = max_slots;
     /* byte set of the leading instructions (sre_regex_compiler.c:123-241), for
      * the kernel's start-state shortcut */
+    pk.quirk_possible = sre_quirk_bytes(prog, pk.quirk_single) ? 1u : 0u;
     memset(pk.leadset, 0, sizeof(pk.leadset));
     for (uint32_t i = 0; i < prog->nleading; i++) {
         const sre_instruction_t &in = prog->insts[prog->leading[i]];
@@ -1289,6 +1291,19 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
                                     dev_rc, dev_ovec, (uint32_t) ovec_slots, pike_scratch.p, nctx, 0, st,
                                     &launches);
     }
+    /* the reference's first-byte prefilter can misfire on some (program, line) pairs and report a
+     * later match than the leftmost one (lower/sre_quirk.h): those lines are
+     * replayed to the letter, from offset 0, by the general kernel */
+    if (err == cudaSuccess && cp->pike.quirk_possible) {
+        uint32_t *qcount = reinterpret_cast<uint32_t *>(line_ws.p + 3 * half + 128);
+        err = sre_launch_pike_quirk_mark(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, dev_rc,
+                                         dev_ovec, (uint32_t) ovec_slots, qcount, st, &launches);
+        if (err == cudaSuccess) {
+            err = sre_launch_pike_lines(cp->pike, dev_buf, dev_offsets, nlines, pitch, linelen, lines, start,
+                                        dev_rc, dev_ovec, (uint32_t) ovec_slots, pike_scratch.p, nctx, 2, st,
+                                        &launches, qcount);
+        }
+    }
     count_launches(launches);
     if (err != cudaSuccess) {
         return fail("Pike kernel launch failed: %s", cudaGetErrorString(err));
@@ -1922,7 +1937,9 @@ sre_vm_pike_exec(sre_vm_pike_ctx_t *ctx, sre_char *input, size_t size, unsigned 
      * every thread is dead.
      */
     sre_cuda_program_t *cp = ctx->cp;
-    if (!ctx->started && eof && size >= (1u << 16) && cp->has_dfa && cp->has_image && cp->dfa.hcls != nullptr) {
+    /* (not when the reference's prefilter could misfire: that replay needs the whole buffer) */
+    if (!ctx->started && eof && size >= (1u << 16) && cp->has_dfa && cp->has_image && cp->dfa.hcls != nullptr
+        && !cp->pike.quirk_possible) {
         sre_cuda_stream_scan_t *sc = nullptr;
         if (stream_reduce(cp, ctx->d_in, size, nullptr, cp->dfa.start, CLASSIC_STREAM, &sc) != SRE_OK) {
             return SRE_ERROR;

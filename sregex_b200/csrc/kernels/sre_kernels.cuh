@@ -15,6 +15,8 @@
 #define SRE_K_AGAIN    (-2)
 #define SRE_K_DECLINED (-5)
 #define SRE_K_RETRY    (-100)  /* internal: line must be re-run by the general kernel */
+#define SRE_K_QUIRK    (-101)  /* internal: the reference's prefilter misfire is possible on this line:
+                                  re-run by the general kernel in faithful mode (k_pike_quirk_mark)   */
 
 /* ---- DFA tier ------------------------------------------------------------ */
 struct sre_dev_dfa_t {
@@ -102,6 +104,9 @@ struct sre_dev_pike_t {
     uint32_t                 stack_cap;     /* DFS stack entries per ctx      */
     uint64_t                 ctx_stride;    /* bytes of scratch per ctx       */
     uint32_t                 leadset[8];    /* bytes some leading inst takes  */
+    /* the reference's prefilter misfire (lower/sre_quirk.h): possible at all; the byte values a
+     * match must start with, right after a prefilter jump, to trigger it */
+    uint32_t                 quirk_possible, quirk_single[8];
     /* start closure by next byte: entries [start_ofs[b], start_ofs[b+1]) in
      * priority order; NULL when closure(pc 0) meets an assertion             */
     const uint32_t          *start_ofs;
@@ -258,6 +263,15 @@ bool sre_pike_lineage_applicable(const sre_dev_pdfa_t &d, size_t linelen);
 cudaError_t sre_launch_pike_lineage(const sre_dev_pdfa_t &d, const uint8_t *buf, const int64_t *offsets,
     size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines, const int32_t *start, int32_t *rc,
     int64_t *ovec, uint32_t ovec_slots, int prefilled, sre_pike_work_t *work, cudaStream_t stream, int *launches);
+
+/* Lines on which the reference's first-byte prefilter can misfire (sre_quirk.h) get rc =
+ * SRE_K_QUIRK and are counted in *count: matched lines whose match starts at offset s >= 1 with a
+ * quirk_single byte, a non-leading byte in front of it and a non-leading byte behind it.  With
+ * ovec == NULL (or no slots) every matched line is marked.  Re-run them with
+ * sre_launch_pike_lines(retry_only = 2): the reference to the letter, from offset 0. */
+cudaError_t sre_launch_pike_quirk_mark(const sre_dev_pike_t &pk, const uint8_t *buf, const int64_t *offsets,
+    size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines, int32_t *rc, const int64_t *ovec,
+    uint32_t ovec_slots, uint32_t *count, cudaStream_t stream, int *launches);
 
 /* all non-overlapping matches per line (post-match continuation, global scan)  */
 cudaError_t sre_launch_pike_lines_all(const sre_dev_pike_t &pk, const uint8_t *buf,

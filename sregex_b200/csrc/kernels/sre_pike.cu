@@ -59,7 +59,9 @@ struct pike_hdr_t {
     int32_t   has_matched, matched_id;
     int64_t   last_matched_pos;
     int64_t   pending[2];
-    uint8_t   first_buf, eof, empty_capture, seen_newline, seen_word, error, pad[2];
+    uint8_t   first_buf, eof, empty_capture, seen_newline, seen_word, error;
+    uint8_t   seen_start_state;             /* faithful mode: sre_vm_pike.c:796-800 */
+    uint8_t   pad;
     uint32_t  pad2[2];                      /* 26 words: 2-way bank conflicts at most as a shared array */
 };
 static_assert(sizeof(pike_hdr_t) == 104, "pike_hdr_t layout");
@@ -77,7 +79,7 @@ struct pike_ctx_t {
     pike_hdr_t   *h;            /* scalar state, in shared memory */
     uint32_t     *base;
     uint32_t      stride;
-    uint32_t      o_matched, o_thr, o_stk, o_hdr;
+    uint32_t      o_matched, o_thr, o_stk, o_init, o_hdr;
     uint32_t      max_slots, rec;       /* rec = words of one thread record */
     /* working capture: only the slots [cap_base, cap_base + max_slots) of one
      * regex can be set at any time (see header), so that window is all that
@@ -192,7 +194,7 @@ struct pike_ctx_t {
 
 /* words of one context block; the same walk gives the section offsets */
 struct pike_layout_t {
-    uint32_t o_tags, o_matched, o_cap, o_thr, o_stk, o_hdr, tagw, rec;
+    uint32_t o_tags, o_matched, o_cap, o_thr, o_stk, o_init, o_hdr, tagw, rec;
     size_t   words;
 };
 
@@ -208,6 +210,9 @@ __host__ __device__ inline pike_layout_t pike_layout(uint32_t len, uint32_t nslo
     L.o_cap = (uint32_t) o;      o += 2 * (size_t) max_slots;
     L.o_thr = (uint32_t) o;      o += (size_t) nthreads * L.rec;
     L.o_stk = (uint32_t) o;      o += 4 * (size_t) stack_cap;
+    /* faithful mode: the initial thread list as the reference records it (:217-228): its
+     * length, then the pcs of all its threads but the last */
+    L.o_init = (uint32_t) o;     o += (size_t) len + 2;
     L.o_hdr = (uint32_t) o;      o += (sizeof(pike_hdr_t) + 3) / 4;    /* streaming ctx only */
     L.words = o;
     return L;
@@ -249,6 +254,7 @@ __device__ __forceinline__ void pike_attach(pike_ctx_t &c, const sre_dev_pike_t 
     c.o_matched = L.o_matched;
     c.o_thr = L.o_thr;
     c.o_stk = L.o_stk;
+    c.o_init = L.o_init;
     c.o_hdr = L.o_hdr;
     c.tagw = L.tagw;
     c.cap_base = 0;
@@ -362,6 +368,7 @@ __device__ __forceinline__ void pike_reset(pike_ctx_t &c, bool first_time)
     h->seen_newline = 0;
     h->seen_word = 0;
     h->error = 0;
+    h->seen_start_state = 0;
 }
 
 __device__ __forceinline__ void list_clear(pike_ctx_t &c, int l)
@@ -467,7 +474,7 @@ __device__ __forceinline__ int32_t thread_append(const sre_dev_pike_t &pk, pike_
 enum { NB_END = -2, NB_UNKNOWN = -1 };
 
 __device__ __forceinline__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ctx_t &c, int l, tmp_list_t *tmp,
-    int32_t pc0, int64_t pos, const uint8_t *buffer, bool want_done, int nb)
+    int32_t pc0, int64_t pos, const uint8_t *buffer, bool want_done, int nb, bool faithful = false)
 {
     pike_hdr_t *h = c.h;
     const uint32_t tag = h->tag;
@@ -491,12 +498,18 @@ __device__ __forceinline__ int pike_add_thread(const sre_dev_pike_t &pk, pike_ct
             if (c.tag_test(pc, tag)) {
                 /* the revisited-SPLIT rule, :770-786 */
                 if (in.opcode == OP_SPLIT && !c.tag_test(in.y, tag)) {
+                    if (faithful && pc == 0) {
+                        h->seen_start_state = 1;        /* :775-778 */
+                    }
                     pc = in.y;
                     continue;
                 }
                 break;
             }
             c.tag_set(pc, tag);
+            if (faithful && pc == 0 && in.opcode == OP_SPLIT) {
+                h->seen_start_state = 1;                /* :797-800 */
+            }
 
             switch (in.opcode) {
             case OP_JMP:
@@ -673,8 +686,16 @@ __device__ __forceinline__ int prepare_matched(const sre_dev_pike_t &pk, pike_ct
  * One sre_vm_pike_exec call (:148-689).  ovector: caller's vector
  * (ovec_slots entries).  *pending_set: 1 when h->pending holds a pending match.
  */
+/*
+ * faithful: the reference's first-byte prefilter to the letter (:256-309) over complete thread
+ * lists (no next-byte pruning), including its misfire after a match (the "is this the initial
+ * list" test compares the count and every pc but the last, :262-274).  The batch
+ * tiers run without it (the prefilter below is result neutral) and hand the lines on which the
+ * misfire is possible to a faithful pass (k_pike_quirk_mark).
+ */
 __device__ __forceinline__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c, const uint8_t *input, int64_t size,
-    bool eof, int64_t *ovector, uint32_t ovec_slots, int *pending_set, int64_t start_pos = 0)
+    bool eof, int64_t *ovector, uint32_t ovec_slots, int *pending_set, int64_t start_pos = 0,
+    bool faithful = false)
 {
     pike_hdr_t *h = c.h;
     int64_t sp, last = size;
@@ -711,10 +732,19 @@ __device__ __forceinline__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c
         h->tag = h->prog_tag + 1;
         c.tag_open(h->tag);
         rc = pike_add_thread(pk, c, cl, nullptr, 0, sp, input, false,
-                             sp < last ? (int) input[sp] : (eof ? NB_END : NB_UNKNOWN));
+                             faithful ? NB_UNKNOWN : sp < last ? (int) input[sp] : (eof ? NB_END : NB_UNKNOWN),
+                             faithful);
         if (rc != SRE_K_OK) {
             h->prog_tag = h->tag;
             return SRE_K_ERROR;
+        }
+        if (faithful) {                             /* :217-228 */
+            c.W(c.o_init) = (uint32_t) h->count[cl];
+            uint32_t i = 0;
+            for (int32_t t = h->head[cl]; t >= 0 && c.t_next(t) >= 0; t = c.t_next(t)) {
+                c.W(c.o_init + 1 + i) = (uint32_t) c.t_pc(t);
+                i++;
+            }
         }
     } else {
         h->tag = h->prog_tag;
@@ -732,6 +762,40 @@ __device__ __forceinline__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c
          * scan can move to just before the next byte a leading instruction
          * takes: stepping the ".*?" thread there rebuilds the start closure.
          */
+        if (faithful) {
+            if (pk.nleading && h->seen_start_state) {
+                h->seen_start_state = 0;
+                bool initial = sp != last && (uint32_t) h->count[cl] == c.W(c.o_init);
+                if (initial) {
+                    uint32_t i = 0;
+                    for (int32_t t = h->head[cl]; t >= 0 && c.t_next(t) >= 0; t = c.t_next(t), i++) {
+                        if ((uint32_t) c.t_pc(t) != c.W(c.o_init + 1 + i)) {
+                            initial = false;
+                            break;
+                        }
+                    }
+                }
+                if (initial) {
+                    const int64_t p = find_first_byte(pk, input, sp, last);
+                    if (p > sp) {
+                        sp = p;
+                        list_clear(c, cl);
+                        c.cap_base = 0;
+                        c.cap_reset();
+                        h->tag++;
+                        c.tag_open(h->tag);
+                        rc = pike_add_thread(pk, c, cl, nullptr, 0, sp, input, false, NB_UNKNOWN, true);
+                        if (rc != SRE_K_OK) {
+                            h->prog_tag = h->tag;
+                            return SRE_K_ERROR;
+                        }
+                        if (sp == last) {
+                            break;
+                        }
+                    }
+                }
+            }
+        } else
         if (pk.nleading && h->count[cl] == 1 && sp + 1 < last && c.t_pc(h->head[cl]) == 1) {
             const int64_t p = find_first_byte(pk, input, sp + 1, last);
             if (p - 1 > sp) {
@@ -744,8 +808,8 @@ __device__ __forceinline__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c
         const bool at_end = (sp == last);
         const uint32_t byte = at_end ? 0 : input[sp];
         const bool cur_word = !at_end && isword(byte);
-        const int nb_cur = at_end ? NB_END : (int) byte;
-        const int nb_next = sp + 1 < last ? (int) input[sp + 1] : (eof ? NB_END : NB_UNKNOWN);
+        const int nb_cur = faithful ? NB_UNKNOWN : at_end ? NB_END : (int) byte;
+        const int nb_next = faithful ? NB_UNKNOWN : sp + 1 < last ? (int) input[sp + 1] : (eof ? NB_END : NB_UNKNOWN);
 
         while (h->head[cl] >= 0) {                  /* :314-567 */
             const int32_t t = h->head[cl];
@@ -774,7 +838,7 @@ __device__ __forceinline__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c
                     cap_load(pk, c, t, &cbase, &ccnt);
                     tmp_list_t tl = { -1, -1, 0 };
                     h->tag--;
-                    rc = pike_add_thread(pk, c, -1, &tl, pc + 1, sp, input, false, nb_cur);
+                    rc = pike_add_thread(pk, c, -1, &tl, pc + 1, sp, input, false, nb_cur, faithful);
                     if (rc != SRE_K_OK) {
                         h->prog_tag = h->tag + 1;
                         return SRE_K_ERROR;
@@ -801,7 +865,7 @@ __device__ __forceinline__ int pike_exec(const sre_dev_pike_t &pk, pike_ctx_t &c
                 cap_clear(c, cbase, ccnt);
             } else if (!at_end && consumes(pk, in, byte)) {
                 cap_load(pk, c, t, &cbase, &ccnt);
-                rc = pike_add_thread(pk, c, nl, nullptr, pc + 1, sp + 1, input, true, nb_next);
+                rc = pike_add_thread(pk, c, nl, nullptr, pc + 1, sp + 1, input, true, nb_next, faithful);
                 cap_clear(c, cbase, ccnt);
                 if (rc == RC_DONE) {
                     got_match = true;
@@ -920,6 +984,38 @@ k_pike_compact(const int32_t *__restrict__ select, size_t nlines, int32_t *__res
     }
 }
 
+/* see sre_launch_pike_quirk_mark (sre_kernels.cuh) */
+__global__ void __launch_bounds__(256)
+k_pike_quirk_mark(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
+                  size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines, int32_t *__restrict__ rc,
+                  const int64_t *__restrict__ ovec, uint32_t ovec_slots, uint32_t *__restrict__ count)
+{
+    const size_t nwork = lines.list ? (size_t) *lines.count : nlines;
+    auto bit = [](const uint32_t *set, uint32_t b) { return (set[b >> 5] >> (b & 31)) & 1u; };
+    uint32_t mine = 0;
+    for (size_t k = (size_t) blockIdx.x * blockDim.x + threadIdx.x; k < nwork; k += (size_t) gridDim.x * blockDim.x) {
+        const size_t line = lines.list ? (size_t) lines.list[k] : k;
+        if (rc[line] < 0) {
+            continue;
+        }
+        bool cand = true;
+        if (ovec != nullptr && ovec_slots >= 1) {
+            const size_t start = offsets ? (size_t) offsets[line] : line * pitch;
+            const int64_t size = (int64_t) (offsets ? (size_t) offsets[line + 1] - start : linelen);
+            const int64_t s = ovec[line * ovec_slots];
+            cand = s >= 1 && s + 1 < size && bit(pk.quirk_single, buf[start + s])
+                   && !bit(pk.leadset, buf[start + s - 1]) && !bit(pk.leadset, buf[start + s + 1]);
+        }
+        if (cand) {
+            rc[line] = SRE_K_QUIRK;
+            mine++;
+        }
+    }
+    if (mine) {
+        atomicAdd(count, mine);
+    }
+}
+
 __global__ void __launch_bounds__(128)
 k_pike_lines(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *__restrict__ offsets,
              size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines,
@@ -944,7 +1040,7 @@ k_pike_lines(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
         const size_t line = lines.list ? (size_t) lines.list[k] : k;
         int64_t *ov = ovec + line * ovec_slots;
         /* second pass after k_pike_small: only the lines it gave up on */
-        if (retry_only && rc[line] != SRE_K_RETRY) {
+        if (retry_only && rc[line] != (retry_only == 2 ? SRE_K_QUIRK : SRE_K_RETRY)) {
             continue;
         }
         const size_t start = offsets ? (size_t) offsets[line] : line * pitch;
@@ -952,8 +1048,9 @@ k_pike_lines(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64_t *
         pike_reset(c, first);
         first = false;
         int pending;
+        /* the quirk pass (retry_only 2) replays the reference to the letter from offset 0 */
         const int r = pike_exec(pk, c, buf + start, (int64_t) (end - start), true, ov, ovec_slots,
-                                &pending, start_hint ? start_hint[line] : 0);
+                                &pending, retry_only != 2 && start_hint ? start_hint[line] : 0, retry_only == 2);
         rc[line] = r;
         if (r < 0) {
             for (uint32_t i = 0; i < ovec_slots; i++) {
@@ -994,7 +1091,7 @@ k_pike_lines_all(sre_dev_pike_t pk, const uint8_t *__restrict__ buf, const int64
         int64_t at = 0, ov[2];
         while (m < max_matches) {
             int pending;
-            const int r = pike_exec(pk, c, buf + start + at, len - at, true, ov, 2, &pending);
+            const int r = pike_exec(pk, c, buf + start + at, len - at, true, ov, 2, &pending, 0, true);
             if (r < 0) {
                 break;
             }
@@ -1042,7 +1139,7 @@ __global__ void k_pike_stream(sre_dev_pike_t pk, uint8_t *ctx, const uint8_t *bu
         len -= skip;
     }
     int pending = 0;
-    const int r = pike_exec(pk, c, buf, (int64_t) len, eof != 0, out + 4, ovec_slots, &pending);
+    const int r = pike_exec(pk, c, buf, (int64_t) len, eof != 0, out + 4, ovec_slots, &pending, 0, true);
     pike_hdr_store(pk, c);
     out[0] = r;
     out[1] = pending;
@@ -1070,7 +1167,7 @@ k_pike_streams(sre_dev_pike_t pk, uint8_t *ctxs, size_t nstreams, const uint8_t 
     int64_t *o = out + i * (4 + (size_t) ovec_slots);
     int pending = 0;
     const bool eof = eof_all || (eofs != nullptr && eofs[i] != 0);
-    const int r = pike_exec(pk, c, buf + off[i], off[i + 1] - off[i], eof, o + 4, ovec_slots, &pending);
+    const int r = pike_exec(pk, c, buf + off[i], off[i + 1] - off[i], eof, o + 4, ovec_slots, &pending, 0, true);
     pike_hdr_store(pk, c);
     o[0] = r;
     o[1] = pending;
@@ -1150,6 +1247,29 @@ cudaError_t sre_launch_pike_compact(const int32_t *select, size_t nlines, int32_
         grid = 148 * 8;
     }
     k_pike_compact<<<(unsigned) grid, 256, 0, stream>>>(select, nlines, rc, list, count);
+    return cudaGetLastError();
+}
+
+cudaError_t sre_launch_pike_quirk_mark(const sre_dev_pike_t &pk, const uint8_t *buf, const int64_t *offsets,
+    size_t nlines, size_t pitch, size_t linelen, sre_line_list_t lines, int32_t *rc, const int64_t *ovec,
+    uint32_t ovec_slots, uint32_t *count, cudaStream_t stream, int *launches)
+{
+    if (nlines == 0) {
+        return cudaSuccess;
+    }
+    if (launches) {
+        ++*launches;
+    }
+    cudaError_t err = cudaMemsetAsync(count, 0, 4, stream);
+    if (err != cudaSuccess) {
+        return err;
+    }
+    size_t grid = (nlines + 255) / 256;
+    if (grid > 148 * 8) {
+        grid = 148 * 8;
+    }
+    k_pike_quirk_mark<<<(unsigned) grid, 256, 0, stream>>>(pk, buf, offsets, nlines, pitch, linelen, lines, rc, ovec,
+                                                          ovec_slots, count);
     return cudaGetLastError();
 }
 

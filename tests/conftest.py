@@ -66,10 +66,12 @@ def cuda():
 
 @pytest.fixture(scope="module")
 def leftmost_first():
-    """For the module's comparisons of OUR Pike results with the oracle: the oracle without the
-    reference's first-byte prefilter, i.e. the leftmost-first match the Pike VM computes when that
-    shortcut does not misfire (oracle/sre_oracle.c: oracle_pike_prefilter).  The
-    oracle WITH the prefilter is pinned to the reference in tests/test_oracle.py."""
+    """For the CPU models of the fast Pike tiers (closure tables, P-DFA), which compute the
+    leftmost-first match: the oracle without the reference's first-byte prefilter, i.e. what the
+    Pike VM computes when that shortcut does not misfire (oracle/sre_oracle.c:
+    oracle_pike_prefilter).  The product adds the misfire back in a separate pass
+    (k_pike_quirk_mark + the faithful general kernel); the GPU tests compare with the oracle WITH
+    the prefilter, which is pinned to the reference in tests/test_oracle.py."""
     from sregex_b200 import capi
     o = capi.load("oracle")
     o.pike_prefilter(False)

@@ -13,12 +13,6 @@ from sregex_b200 import capi, corpus
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", autouse=True)
-def _leftmost_first(leftmost_first):
-    """every Pike comparison with the oracle in this module is with the leftmost-first match (the
-    reference's prefilter misfire is pinned in test_oracle.py and shown below in
-    test_pike_is_leftmost_first_where_the_reference_prefilter_misfires)"""
-    yield leftmost_first
 
 
 
@@ -985,19 +979,23 @@ def test_nfa_tier_on_a_regex_that_defeats_determinisation(cu):
                 assert (got == want).all(), (rx, linelen, engine, int((got != want).sum()))
 
 
-def test_pike_is_leftmost_first_where_the_reference_prefilter_misfires(cu):
-    """Every Pike tier (determinised, closure tables, shared-memory, general) and the classic
-    sre_vm_pike_exec return the leftmost-first match on the inputs where the reference's first-byte
-    prefilter misfires and reports a later one (sre_vm_pike.c:262-274; the cases and the
-    reference's own answers are in test_oracle.py::QUIRK_CASES)."""
+def test_pike_reproduces_the_reference_prefilter_misfire(cu):
+    """The reference's first-byte prefilter is not result neutral: after a match reported in the
+    step a prefilter jump landed on, survivors that look like the initial list are dropped and a
+    LATER match overwrites the leftmost one (sre_vm_pike.c:262-274; tests/test_oracle.py pins the
+    oracle to the live reference on QUIRK_CASES).  Every Pike tier and the classic
+    sre_vm_pike_exec give the reference's answer: the fast tiers compute the leftmost-first match,
+    k_pike_quirk_mark finds the lines on which the misfire is possible, and the general kernel
+    replays those to the letter (pike_exec(faithful))."""
+    import random
     from test_oracle import QUIRK_CASES
     o = capi.load("oracle")
     cuda_lib = capi.load("cuda")
     pitch = 32
-    for rx, s, _want_ref, want in QUIRK_CASES:
+    for rx, s, want, _leftmost in QUIRK_CASES:
         prog = cu.CudaProgram(rx)
         po = o.compile(rx, 0)
-        assert o.pike(po, s) == want            # (the module runs the oracle without the prefilter)
+        assert o.pike(po, s) == want
         host = np.zeros((1, pitch), dtype=np.uint8)
         host[0, : len(s)] = np.frombuffer(s, dtype=np.uint8)
         dev = torch.from_numpy(host).cuda()
@@ -1011,6 +1009,36 @@ def test_pike_is_leftmost_first_where_the_reference_prefilter_misfires(cu):
         pc.close()
         po.close()
         prog.program.close()
+    # the family at large: regexes that can match one byte, lines full of isolated candidates
+    rng = random.Random(2718)
+    heads = [rb"a+", rb"\w+", rb"\d+", rb"[ab]+", rb"(a+)", rb"(\w)+", rb"(?:a|b)+", rb"^a+", rb"\ba+"]
+    tails = [rb"b?", rb"x?", rb"\.?", rb"(\d)?", rb" ?", rb"(?:ab)?", rb"b*", rb"$", rb""]
+    nlines, pitch = 512, 64
+    alphabet = list(b"ab1. x\n")
+    total = differ = 0
+    for _ in range(40):
+        rx = rng.choice(heads) + rng.choice(tails)
+        linelen = rng.choice([5, 16, 33, 64])
+        host = np.array([rng.choice(alphabet) for _ in range(nlines * pitch)], dtype=np.uint8).reshape(nlines, pitch)
+        prog = cu.CudaProgram(rx)
+        _, want_rc, want_ov = baseline.run_lines("oracle", rx, None, host, nlines, pitch, linelen,
+                                                 baseline.ENGINE_PIKE, ovec_slots=prog.nslots)
+        o.pike_prefilter(False)
+        try:
+            _, _, clean_ov = baseline.run_lines("oracle", rx, None, host, nlines, pitch, linelen,
+                                                baseline.ENGINE_PIKE, ovec_slots=prog.nslots)
+        finally:
+            o.pike_prefilter(True)
+        total += nlines
+        differ += int((clean_ov != want_ov).any(axis=1).sum())
+        dev = torch.from_numpy(host).cuda()
+        for tier in (0, 1, 2, 3):
+            prog.set_pike_tier(tier)
+            rc, ov = prog.pike_lines(dev, nlines, pitch, linelen)
+            assert (rc.cpu().numpy() == want_rc).all(), (rx, linelen, tier)
+            assert (ov.cpu().numpy() == want_ov).all(), (rx, linelen, tier)
+        prog.program.close()
+    assert differ > 50, (differ, total)     # the misfire really is exercised
 
 
 def test_batched_streaming_pike_contexts(cu):
