@@ -580,3 +580,37 @@ extern "C" long lc_pdfa_pike(sre_program_t *prog, const uint8_t *input, long siz
     }
     return (long) rid;
 }
+
+/*
+ * The bytes on which the reference's first-byte prefilter can misfire
+ * (lower/sre_quirk.h) and the leading-byte set, for the CPU test of the marking
+ * rule of k_pike_quirk_mark: single / lead = 256-bit sets; -> 1 when the misfire
+ * is possible at all for this program.
+ */
+#include "../sregex_b200/csrc/lower/sre_quirk.h"
+
+extern "C" int lc_quirk_bytes(sre_program_t *prog, uint32_t *single, uint32_t *lead)
+{
+    memset(lead, 0, 32);
+    for (uint32_t b = 0; b < 256; b++) {
+        for (uint32_t i = 0; i < prog->nleading; i++) {
+            const sre_instruction_t &in = prog->insts[prog->leading[i]];
+            bool t = false;
+            if (in.opcode == SRE_OPCODE_CHAR) {
+                t = b == in.ch;
+            } else if (in.opcode == SRE_OPCODE_ANY) {
+                t = true;
+            } else if (in.opcode == SRE_OPCODE_IN || in.opcode == SRE_OPCODE_NOTIN) {
+                bool inr = false;
+                for (uint32_t j = 0; j < in.nranges; j++) {
+                    inr |= b >= prog->ranges[in.v + j].from && b <= prog->ranges[in.v + j].to;
+                }
+                t = inr == (in.opcode == SRE_OPCODE_IN);
+            }
+            if (t) {
+                lead[b >> 5] |= 1u << (b & 31);
+            }
+        }
+    }
+    return sre_quirk_bytes(prog, single) ? 1 : 0;
+}

@@ -338,3 +338,55 @@ def test_pdfa_pike_fuzz_vs_oracle(oracle, lc, leftmost_first):
             assert got == oracle.pike(p, s), (rxs, s, got)
         p.close()
     assert applicable > 2000
+
+
+def test_prefilter_misfire_marking_rule(oracle, lc):
+    """k_pike_quirk_mark's rule is a superset of the lines on which the reference's first-byte
+    prefilter misfires (lower/sre_quirk.cpp): wherever the oracle with the prefilter (== the
+    reference) and without it (the leftmost-first match the fast tiers compute) disagree, the
+    leftmost-first match starts at offset s >= 1 on a byte of the program's `single` set with a
+    non-leading byte on either side.  Programs that cannot match one byte have an empty set."""
+    import random
+    from sregex_b200 import corpus
+    lc.lc_quirk_bytes.restype = C.c_int
+    lc.lc_quirk_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+
+    def sets(p):
+        single, lead = (C.c_uint32 * 8)(), (C.c_uint32 * 8)()
+        possible = lc.lc_quirk_bytes(p.prog, single, lead)
+        bit = lambda st, b: (st[b >> 5] >> (b & 31)) & 1
+        return possible, (lambda b: bit(single, b)), (lambda b: bit(lead, b))
+
+    for rx in (corpus.C2_REGEX, corpus.C3_REGEX, corpus.BENCH_REGEX):
+        p = oracle.compile(rx, 0)
+        assert sets(p)[0] == 0, rx
+        p.close()
+    p = oracle.compile(corpus.multi_pattern_set(64), 0)
+    assert sets(p)[0] == 0
+    p.close()
+
+    rng = random.Random(1618)
+    heads = [rb"a+", rb"\w+", rb"\d+", rb"[ab]+", rb"(a+)", rb"(\w)+", rb"(?:a|b)+", rb"^a+", rb"\ba+", rb"a", rb"(a|ab)+"]
+    tails = [rb"b?", rb"x?", rb"\.?", rb"(\d)?", rb" ?", rb"(?:ab)?", rb"b*", rb"$", rb"", rb"\b", rb"(b|c)?"]
+    alphabet = b"ab1. x\n"
+    differ = 0
+    for _ in range(300):
+        rx = rng.choice(heads) + rng.choice(tails)
+        p = oracle.compile(rx, 0)
+        possible, single, lead = sets(p)
+        for _ in range(40):
+            s = bytes(rng.choice(alphabet) for _ in range(rng.randrange(0, 24)))
+            on = oracle.pike(p, s)
+            oracle.pike_prefilter(False)
+            try:
+                off = oracle.pike(p, s)
+            finally:
+                oracle.pike_prefilter(True)
+            if on != off:
+                differ += 1
+                assert possible and off[0] >= 0, (rx, s, on, off)
+                st = off[1][0]
+                assert st >= 1 and st + 1 < len(s) and single(s[st]) and not lead(s[st - 1]) \
+                    and not lead(s[st + 1]), (rx, s, on, off)
+        p.close()
+    assert differ > 100, differ
