@@ -12,6 +12,7 @@ WANT = [
     ("dram__bytes_write.sum", "DRAM write"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput % of peak"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1/shared data pipe % (all wavefronts)"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "shared-memory pipe %"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared bank conflicts"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared wavefronts"),
