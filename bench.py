@@ -596,8 +596,8 @@ def bench_text(h, steps, warmup, dev):
                                "sre_vm_thompson_exec per line, regex " + REGEX_NAME,
                    "bytes_per_gpu": n, "lines": nl, "matched_lines": int((rc == 0).sum())},
         # 1 B per input byte + 4 B verdict per line (+ 8 B offset per line in the second form)
-        "roofline": h.roofline(n + 4 * nl, call_ms, "sre_cuda_thompson_exec_text: k_text_verdicts + tail + k_text_finish",
-                               note="whole call, verdict per line (3 launches + the read-back of the line count)"),
+        "roofline": h.roofline(n + 4 * nl, call_ms, "sre_cuda_thompson_exec_text: k_text_verdicts + k_text_finish",
+                               note="whole call, verdict per line (2 launches + the read-back of the line count)"),
         "with_line_offsets_roofline": h.roofline(n + 12 * nl, off_call_ms,
                                                  "sre_cuda_thompson_exec_text: k_text_pieces + sums/scan/write"),
         "gpu_launches": launches, "clocks": clocks,

@@ -435,6 +435,7 @@ k_text_write(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, siz
 constexpr uint32_t INFO_CNT = 0x1fffu;          /* newlines in the piece (<= 4097)            */
 constexpr uint32_t INFO_MSHIFT = 13;            /* matched ones among them                     */
 constexpr uint32_t INFO_FSHIFT = 26;            /* verdict of the line open at the piece's end */
+constexpr uint32_t INFO_BEGINS = 1u << 28;      /* a line begins at the first byte of the piece  */
 constexpr uint32_t FIX_NONE = 0, FIX_UNMATCHED = 1, FIX_MATCHED = 2;
 constexpr uint32_t NLBITS = 0x40404040u, MBITS = 0x80808080u;
 
@@ -451,7 +452,7 @@ struct verdict_consumer_t {
     size_t              len, nfull;
     verdict_out_t       out;
     uint32_t            piece_bytes, start, guess, acc;
-    uint32_t            s, cnt, mcnt;
+    uint32_t            s, cnt, mcnt, begins;
     uint32_t           *stage;
 
     __device__ __forceinline__ void begin(size_t group)
@@ -459,10 +460,12 @@ struct verdict_consumer_t {
         const size_t piece = group * 32 + (threadIdx.x & 31);
         cnt = 0;
         mcnt = 0;
+        begins = 0;
         s = guess;
         stage = out.stage;
         if (piece < nfull) {
-            s = (piece == 0 || __ldg(buf + piece * piece_bytes - 1) == '\n') ? start : guess;
+            begins = (piece == 0 || __ldg(buf + piece * piece_bytes - 1) == '\n') ? INFO_BEGINS : 0u;
+            s = begins ? start : guess;
             stage = out.stage + piece * CAP;
         }
     }
@@ -580,38 +583,9 @@ struct verdict_consumer_t {
                 }
             }
         }
-        out.info[piece] = cnt | (mcnt << INFO_MSHIFT) | (fix << INFO_FSHIFT);
+        out.info[piece] = cnt | (mcnt << INFO_MSHIFT) | (fix << INFO_FSHIFT) | begins;
     }
 };
-
-/* shared memory: [table 256 x ROW260][barriers][stages] */
-constexpr size_t VTAB_BYTES = align_up((size_t) 256 * ROW260, 1024);
-constexpr size_t VBAR_OFS = VTAB_BYTES, VSTAGE_OFS = VTAB_BYTES + 2048;
-
-__global__ void __launch_bounds__(1024, 1)
-k_text_verdicts(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ buf, size_t len,
-                size_t nfull, uint32_t piece_bytes, verdict_out_t out)
-{
-    extern __shared__ __align__(1024) uint8_t smem[];
-    load_table260(smem, dfa.x256m, 256);
-    __syncthreads();
-
-    const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
-    verdict_consumer_t cons;
-    cons.tab_s = smem_u32(smem);
-    cons.buf = buf;
-    cons.fin = dfa.fin;
-    cons.len = len;
-    cons.nfull = nfull;
-    cons.out = out;
-    cons.piece_bytes = piece_bytes;
-    cons.start = dfa.start;
-    cons.guess = dfa.xguess;
-    cons.acc = dfa.acc;
-    tile_pipeline_tma_early<1>(cons, &tmap, nfull, piece_bytes, smem + VSTAGE_OFS + (size_t) warp * 32 * 128,
-                               reinterpret_cast<uint64_t *>(smem + VBAR_OFS) + warp * MAX_STAGES,
-                               (size_t) warp * gridDim.x + blockIdx.x, (size_t) gridDim.x * warps_per_block);
-}
 
 /*
  * The same walk, serially, over the table in global memory: the newlines of
@@ -666,8 +640,66 @@ __device__ __forceinline__ uint32_t serial_marks(const sre_dev_dfa_t &dfa, const
     return n;
 }
 
-/* the tail piece [nfull * piece_bytes, len) (possibly empty) and the end of the buffer: thread 0;
- * the others clear the ticket and the look-back words of k_text_finish */
+/* the tail piece [nfull * piece_bytes, len) (possibly empty) and the end of the buffer: one thread */
+__device__ __forceinline__ void text_tail_piece(const sre_dev_dfa_t &dfa, const uint8_t *buf, size_t len, size_t nfull,
+                                                uint32_t piece_bytes, const verdict_out_t &out)
+{
+    uint32_t *stage = out.stage + nfull * CAP;
+    uint32_t m = 0;
+    const size_t begin = nfull * piece_bytes;
+    const uint32_t n = serial_marks(dfa, buf, len, begin, len, true, [&](uint32_t k) {
+        if (m < CAP) {
+            stage[m] = k;
+        }
+        m++;
+    });
+    const uint32_t begins = (begin == 0 || __ldg(buf + begin - 1) == '\n') ? INFO_BEGINS : 0u;
+    out.info[nfull] = n | (m << INFO_MSHIFT) | begins;
+}
+
+/* shared memory: [table 256 x ROW260][barriers][stages] */
+constexpr size_t VTAB_BYTES = align_up((size_t) 256 * ROW260, 1024);
+constexpr size_t VBAR_OFS = VTAB_BYTES, VSTAGE_OFS = VTAB_BYTES + 2048;
+
+__global__ void __launch_bounds__(1024, 1)
+k_text_verdicts(sre_dev_dfa_t dfa, const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ buf, size_t len,
+                size_t nfull, uint32_t piece_bytes, verdict_out_t out, unsigned long long *__restrict__ status,
+                size_t nstatus)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    load_table260(smem, dfa.x256m, 256);
+    if (blockIdx.x == 0) {
+        /* the ticket and the look-back words of k_text_finish */
+        for (size_t i = threadIdx.x; i < nstatus; i += blockDim.x) {
+            status[i] = 0;
+        }
+    }
+    __syncthreads();
+
+    const uint32_t warp = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    verdict_consumer_t cons;
+    cons.tab_s = smem_u32(smem);
+    cons.buf = buf;
+    cons.fin = dfa.fin;
+    cons.len = len;
+    cons.nfull = nfull;
+    cons.out = out;
+    cons.piece_bytes = piece_bytes;
+    cons.start = dfa.start;
+    cons.guess = dfa.xguess;
+    cons.acc = dfa.acc;
+    tile_pipeline_tma_early<1>(cons, &tmap, nfull, piece_bytes, smem + VSTAGE_OFS + (size_t) warp * 32 * 128,
+                               reinterpret_cast<uint64_t *>(smem + VBAR_OFS) + warp * MAX_STAGES,
+                               (size_t) warp * gridDim.x + blockIdx.x, (size_t) gridDim.x * warps_per_block);
+    /* the tail piece (shorter than a piece, not a row of the tensor): one lane of the warp that
+     * was handed the fewest pieces walks it when its own are done */
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == blockDim.x - 32) {
+        text_tail_piece(dfa, buf, len, nfull, piece_bytes, out);
+    }
+}
+
+/* inputs shorter than a piece: the tail piece and the ticket + look-back words of k_text_finish
+ * (otherwise k_text_verdicts does both) */
 __global__ void __launch_bounds__(256)
 k_text_verdicts_tail(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, size_t nfull,
                      uint32_t piece_bytes, verdict_out_t out, unsigned long long *__restrict__ status, size_t nstatus)
@@ -675,18 +707,9 @@ k_text_verdicts_tail(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t 
     for (size_t i = threadIdx.x; i < nstatus; i += blockDim.x) {
         status[i] = 0;
     }
-    if (threadIdx.x != 0) {
-        return;
+    if (threadIdx.x == 0) {
+        text_tail_piece(dfa, buf, len, nfull, piece_bytes, out);
     }
-    uint32_t *stage = out.stage + nfull * CAP;
-    uint32_t m = 0;
-    const uint32_t n = serial_marks(dfa, buf, len, nfull * piece_bytes, len, true, [&](uint32_t k) {
-        if (m < CAP) {
-            stage[m] = k;
-        }
-        m++;
-    });
-    out.info[nfull] = n | (m << INFO_MSHIFT);
 }
 
 /*
@@ -710,7 +733,6 @@ k_text_finish(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, si
     __syncthreads();
     const uint32_t tile = s_tile;
     const size_t piece = (size_t) tile * WB + threadIdx.x;
-    auto begins_line = [&](size_t pc) { return pc == 0 || __ldg(buf + pc * piece_bytes - 1) == '\n'; };
     const uint32_t info = piece <= nfull ? out.info[piece] : 0u;
     const uint32_t n = info & INFO_CNT;
     uint32_t total;
@@ -787,13 +809,13 @@ k_text_finish(sre_dev_dfa_t dfa, const uint8_t *__restrict__ buf, size_t len, si
     /* my first newline ends a line that an earlier piece began: the first correction left by the
      * pieces from its owner on (the owner = the nearest piece before me that holds a newline or
      * begins a line; the pieces between are all inside the line) decides; none: the guess held */
-    if (piece > 0 && first < max_lines && !begins_line(piece)) {
+    if (piece > 0 && first < max_lines && !(info & INFO_BEGINS)) {
         size_t k = piece - 1;
-        while (k > 0 && (out.info[k] & INFO_CNT) == 0 && !begins_line(k)) {
+        while (k > 0 && (out.info[k] & (INFO_CNT | INFO_BEGINS)) == 0) {
             k--;
         }
         for (; k < piece; k++) {
-            const uint32_t fix = out.info[k] >> INFO_FSHIFT;
+            const uint32_t fix = (out.info[k] >> INFO_FSHIFT) & 3u;
             if (fix != FIX_NONE) {
                 rc[first] = fix == FIX_MATCHED ? SRE_K_OK : SRE_K_DECLINED;
                 break;
@@ -878,12 +900,15 @@ static cudaError_t launch_text_verdicts(const sre_dev_dfa_t &dfa, const uint8_t 
             grid = need;
         }
         if (launches) ++*launches;
-        k_text_verdicts<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, piece, out);
+        /* (sums[] serves as the ticket + look-back words of k_text_finish) */
+        k_text_verdicts<<<(unsigned) grid, warps * 32, smem, stream>>>(dfa, tmap, buf, len, nfull, piece, out, sums,
+                                                                       nb + 1);
         if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    } else {
+        if (launches) ++*launches;
+        k_text_verdicts_tail<<<1, 256, 0, stream>>>(dfa, buf, len, nfull, piece, out, sums, nb + 1);
     }
-    if (launches) *launches += 2;
-    /* (sums[] serves as the ticket + look-back words of k_text_finish) */
-    k_text_verdicts_tail<<<1, 256, 0, stream>>>(dfa, buf, len, nfull, piece, out, sums, nb + 1);
+    if (launches) ++*launches;
     k_text_finish<<<(unsigned) nb, WB, 0, stream>>>(dfa, buf, len, nfull, piece, out, sums, total, rc, max_lines);
     return cudaGetLastError();
 }
