@@ -9,6 +9,8 @@
  * times at ~0.7 TB/s.  Here the text goes once through the TMA tile pipeline
  * of k_dfa_lines_tma_early, cut into PIECE-byte pieces (one CUDA thread each):
  *
+ * With line offsets wanted (rc[line] and offsets[line + 1]):
+ *
  *   k_text_pieces   The automaton table has the line structure folded in: on
  *                   '\n' every state goes to the START state, with bit 7 set
  *                   when the line that just ended matched (the verdict of the
@@ -18,15 +20,20 @@
  *                   first '\n' is thrown away (that line began in an earlier
  *                   piece and belongs to the thread of that piece), every later
  *                   line is exact, and the line that is still open at the end
- *                   of the piece is finished by reading on past it.  Per input
- *                   byte the loop is the PRMT + LDS.U8 of the line kernels plus
- *                   a newline test per word; the states after each byte of a
- *                   word stay in registers, so a word that holds a '\n' only
- *                   adds the bookkeeping.  Line ends and verdicts go to a small
- *                   per-piece staging area.
- *   k_text_scan     exclusive scan of the per-piece line counts.
+ *                   of the piece is finished by reading on past it.  Line ends
+ *                   and verdicts go to a small per-piece staging area.
+ *   k_text_sums / _scan   exclusive scan of the per-piece line counts.
  *   k_text_write    staging -> rc[line] and offsets[line + 1] (a piece with more
  *                   lines than its staging holds is scanned again, serially).
+ *
+ * Verdicts only (automata of at most 64 states; about twice as fast, see the
+ * comment at k_text_verdicts below):
+ *
+ *   k_text_verdicts newlines numbered by the piece they lie in, counted with one
+ *                   POPC per 16 bytes; the entry state of a piece that begins
+ *                   inside a line is GUESSED and checked by the piece in front,
+ *                   which leaves a correction when the guess was wrong.
+ *   k_text_finish   chained scan of the counts, rc <- DECLINED / OK, corrections.
  *
  * Line i = buf[offsets[i], offsets[i+1]) includes its terminator, as for
  * sre_cuda_index_lines; a last line without '\n' ends at len.

@@ -10,13 +10,21 @@
  *                  Input tiles (32 lines x 128 bytes per warp) are staged
  *                  through shared memory by the TMA unit (128-byte swizzle: the
  *                  per-lane 16-byte reads of "my row" are bank-conflict free).
- *                  Per input byte the inner loop is one PRMT (splice the byte
- *                  under the state) and one LDS.U8 into the [state][byte] table.
+ *                  Per input byte: one PRMT (the byte's address in row 0, off the
+ *                  chain), one IMAD and one LDS.U8 into the [state][byte] table,
+ *                  whose rows are padded to 260 bytes (bank conflicts).
  *   k_dfa_lines_skipw  the same with a warp-uniform word skip for automata whose
  *                  start state is left by few byte values.  HBM-bound.
- *   k_dfa_lines_hint[_skip]  verdict + Pike start hint.
+ *   k_dfa_lines_hint[_skip]  verdict + Pike start hint; packs the matching lines
+ *                  for the Pike pass.
+ *   k_dfa_lines_big  tiled lines, class table through L1 (automata beyond shared
+ *                  memory); bound by the L1/shared data pipe.
  *   k_dfa_generic  same automaton, any alignment / ragged offsets, any table
  *                  size, optional state carry (SRE_AGAIN) -- correctness tier.
+ *   k_nfa_packed   no DFA, <= 64 lowered states, <= 4 non-shift movers: thread per
+ *                  line, the thread set in a 32/64-bit register, one shared-
+ *                  memory entry per byte class.
+ *   k_nfa64_lines  the same for any number of non-shift movers (loop over bits).
  *   k_nfa_lines    the general tier: one warp per line, the NFA thread set is a
  *                  warp-wide bitmask (lane l owns words l, l+32, ... of it, up
  *                  to 4096 states), successor sets come from a shift for
