@@ -38,12 +38,23 @@ def allreduce_sum(value: int, device) -> int:
     return int(t.item())
 
 
+_gather_bufs = {}
+
+
 def allgather_bytes(mine: torch.Tensor):
-    """all-gather a small uint8 tensor (same size on every rank) -> list in rank order"""
-    if _world() == 1:
-        return [mine]
-    out = [torch.empty_like(mine) for _ in range(_world())]
-    dist.all_gather(out, mine)
+    """all-gather a small uint8 tensor (same size on every rank) -> [world, n] tensor, rows in rank
+    order (one collective into one cached buffer: the exchange sits inside the timed region)"""
+    world = _world()
+    if world == 1:
+        return mine.unsqueeze(0)
+    key = (mine.numel(), str(mine.device), world)
+    out = _gather_bufs.get(key)
+    if out is None:
+        out = _gather_bufs[key] = torch.empty((world, mine.numel()), dtype=torch.uint8, device=mine.device)
+    try:
+        dist.all_gather_into_tensor(out.view(-1), mine.contiguous().view(-1))
+    except (RuntimeError, NotImplementedError):
+        dist.all_gather(list(out.unbind(0)), mine.contiguous().view(-1))
     return out
 
 
@@ -92,8 +103,8 @@ def stream_match_sharded(prog, shard: torch.Tensor, shard_len: int, shard_base: 
     entry, off, final = None, -1, UNKNOWN
     for _ in range(world):
         mine = torch.frombuffer(bytearray(scan.fn), dtype=torch.uint8).to(shard.device, non_blocking=True)
-        gathered = torch.stack(allgather_bytes(mine)).cpu()         # one read-back for all ranks' records
-        fns = [bytes(row.numpy().tobytes()) for row in gathered]
+        gathered = allgather_bytes(mine).cpu().numpy()              # one read-back for all ranks' records
+        fns = [gathered[r].tobytes() for r in range(world)]
         entries, final = chain_entries(fns, start, apply)
         if entry is None and entries[rank] != UNKNOWN:
             entry = entries[rank]
