@@ -507,8 +507,8 @@ extern "C" long lc_pdfa_pike(sre_program_t *prog, const uint8_t *input, long siz
     const uint32_t C = D.nclasses;
     const size_t nslots = T.max_slots;
     std::vector<uint16_t> hist((size_t) ring, 0);
-    /* the start list by look-behind context (sre_closure.h): offset 0 / after '\n' / elsewhere */
-    const uint32_t v0 = start <= 0 ? 0u : (input[start - 1] == '\n' ? 1u : 2u);
+    /* the start list by what lies in front of the first byte: nothing / '\n' / a word byte / other */
+    const uint32_t v0 = start <= 0 ? 0u : input[start - 1] == '\n' ? 1u : tp_isword(input[start - 1]) ? 2u : 3u;
     uint32_t s = D.init[v0];
     long pos = start, mpos = -1;
     bool have = false, at_eof = false;
@@ -522,7 +522,8 @@ extern "C" long lc_pdfa_pike(sre_program_t *prog, const uint8_t *input, long siz
         }
         s = e & 0x7fff;
     }
-    if (s != 0 && D.eof_idx[s] != 0xff) {
+    /* the step at the end of the input (only when the input was walked to its end) */
+    if (s != 0 && pos == size && D.eof_idx[s] != 0xff) {
         have = true;
         at_eof = true;
     }
@@ -547,6 +548,7 @@ extern "C" long lc_pdfa_pike(sre_program_t *prog, const uint8_t *input, long siz
         cur = s;
         j = D.eof_idx[s];
         rid = D.eof_regex[s];
+        assign(D.eof_mask0[s], size);
         u = size - 1;
     } else {
         if (mpos <= oldest) return -1001;
@@ -555,6 +557,7 @@ extern "C" long lc_pdfa_pike(sre_program_t *prog, const uint8_t *input, long siz
         j = D.mparent[t];
         rid = D.mregex[t];
         assign(D.mmask[t], mpos + 1);
+        assign(D.mmask0[t], mpos);
         u = mpos - 1;
     }
     /* j indexes the list of state `cur`, the state before step u + 1 */
@@ -570,6 +573,7 @@ extern "C" long lc_pdfa_pike(sre_program_t *prog, const uint8_t *input, long siz
         const uint32_t before = hist[(size_t) (u % ring)];
         const size_t idx = D.eofs[(size_t) before * C + D.clsmap[input[u]]] + j;
         assign(D.emask[idx], u + 1);
+        assign(D.emask0[idx], u);
         j = D.eparent[idx];
         cur = before;
         u--;

@@ -403,7 +403,8 @@ int upload(sre_cuda_program_t *cp)
     sre_pdfa_t pd;
     const bool has_pd = has_clo && sre_build_pdfa(prog, clo, 4096, pd);
     size_t o_pcls = 0, o_ptrans = 0, o_peofs = 0, o_pent = 0, o_pmev = 0, o_peof = 0, o_pinit = 0;
-    uint32_t pd_nent = 0, pd_init_any[3] = { 0xff, 0xff, 0xff };
+    uint32_t pd_nent = 0, pd_init_any[4] = { 0xff, 0xff, 0xff, 0xff };
+    size_t o_pent0 = 0, o_pmev0 = 0, o_peof0 = 0;
     if (has_pd) {
         /* device form of the provenance records (see sre_dev_pdfa_t) */
         const uint32_t C = pd.nclasses;
@@ -422,8 +423,15 @@ int upload(sre_cuda_program_t *cp)
             eofv[st] = pd.eof_idx[st] | ((uint32_t) pd.eof_regex[st] << 16);
         }
         pd_nent = (uint32_t) pd.eparent.size();
-        for (int v = 0; v < 3; v++) {
+        for (int v = 0; v < 4; v++) {
             pd_init_any[v] = pd.any_idx[pd.init[v]];
+        }
+        if (pd.lookahead) {
+            std::vector<uint32_t> e0(pd.emask0);
+            e0.push_back(0);
+            o_pent0 = b.add(e0.data(), e0.size() * 4);
+            o_pmev0 = b.add(pd.mmask0.data(), pd.mmask0.size() * 4);
+            o_peof0 = b.add(pd.eof_mask0.data(), pd.eof_mask0.size() * 4);
         }
         o_pcls = b.add(pd.clsmap, 256);
         o_ptrans = b.add(pd.trans.data(), pd.trans.size() * 2);
@@ -576,12 +584,16 @@ int upload(sre_cuda_program_t *cp)
         sre_dev_pdfa_t &d = cp->pdfa;
         d.nstates = pd.nstates;
         d.nclasses = pd.nclasses;
-        for (int v = 0; v < 3; v++) {
+        d.ctx_dep = 0;
+        for (int v = 0; v < 4; v++) {
             d.init[v] = pd.init[v];
             d.init_any[v] = pd_init_any[v];
             d.init_mask_ofs[v] = pd.init_mask_ofs[v];
+            d.ctx_dep |= pd.init[v] != pd.init[0] ? 1u : 0u;   /* the start list depends on the byte in front */
         }
-        d.ctx_dep = pd.ctx_dep ? 1u : 0u;
+        d.ent0 = pd.lookahead ? reinterpret_cast<const uint32_t *>(base + o_pent0) : nullptr;
+        d.mev0 = pd.lookahead ? reinterpret_cast<const uint32_t *>(base + o_pmev0) : nullptr;
+        d.eof0 = pd.lookahead ? reinterpret_cast<const uint32_t *>(base + o_peof0) : nullptr;
         d.max_slots = pd.max_slots;
         d.nent = pd_nent;
         d.clsmap = base + o_pcls;
@@ -1232,7 +1244,14 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
                           && linelen < (1ull << 31);
     /* the determinised Pike VM first when the program has one; the closure-table
      * kernel (with its larger lists) re-runs the lines whose match outlives the ring */
-    const bool use_lineage = tier_mode == 0 && sre_pike_lineage_applicable(cp->pdfa, linelen) && table_ok;
+    /* (SRE_PDFA_LOOKAHEAD=0 keeps programs with look-ahead assertions on the closure-table kernel) */
+    static int la_ok = -1;
+    if (la_ok < 0) {
+        const char *e = getenv("SRE_PDFA_LOOKAHEAD");
+        la_ok = e ? atoi(e) : 0;
+    }
+    const bool use_lineage = tier_mode == 0 && sre_pike_lineage_applicable(cp->pdfa, linelen) && table_ok
+                             && (cp->pdfa.ent0 == nullptr || la_ok);
     const bool use_table = !use_lineage && table_ok && (tier_mode == 0 || tier_mode == 3);
     const bool use_small = !use_lineage && !use_table && sre_pike_small_applicable(cp->pike)
                            && linelen < (1ull << 31) && tier_mode != 1;

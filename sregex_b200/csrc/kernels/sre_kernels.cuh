@@ -243,10 +243,10 @@ cudaError_t sre_launch_pike_table(const sre_dev_pike_t &pk, const uint8_t *buf,
 struct sre_dev_pdfa_t {
     uint32_t         nstates, nclasses, max_slots;
     uint32_t         nent;          /* provenance records                      */
-    /* the start closure by look-behind context (0: at offset 0, 1: after a newline, 2: elsewhere;
-     * all alike unless ctx_dep): its state, the index of the ".*?" thread in it (0xff: none),
-     * where its slots begin in init_mask */
-    uint32_t         init[3], init_any[3], init_mask_ofs[3], ctx_dep;
+    /* the start closure by what lies in front of the first byte (0: nothing, 1: a newline, 2: a
+     * word byte, 3: anything else; all alike unless ctx_dep): its state, the index of the ".*?"
+     * thread in it (0xff: none), where its slots begin in init_mask */
+    uint32_t         init[4], init_any[4], init_mask_ofs[4], ctx_dep;
     const uint8_t   *clsmap;        /* [256]                                   */
     const uint16_t  *trans;         /* [nstates][nclasses] next | 0x8000 match */
     /* provenance of the threads of a transition's next list: record eofs[t] + j =
@@ -258,6 +258,10 @@ struct sre_dev_pdfa_t {
     const uint2     *mev;           /* [nstates * nclasses]                    */
     const uint32_t  *eof;           /* [nstates] first parked MATCH thread (EOF step): index | regex << 16, 0xff: none */
     const uint32_t  *init_mask;     /* slots SAVEd by a start closure, per thread */
+    /* programs with look-ahead assertions (NULL otherwise): the slots SAVEd at the position of
+     * the step itself, by assertions resolved on the way (lower/sre_pdfa.h: emask0 / mmask0 /
+     * eof_mask0), next to ent / mev / eof */
+    const uint32_t  *ent0, *mev0, *eof0;
 };
 bool sre_pike_lineage_applicable(const sre_dev_pdfa_t &d, size_t linelen);
 cudaError_t sre_launch_pike_lineage(const sre_dev_pdfa_t &d, const uint8_t *buf, const int64_t *offsets,

@@ -146,7 +146,9 @@ k_pike_lineage(sre_dev_pdfa_t d, const uint8_t *__restrict__ buf, const int64_t 
          * `\A` / `^`): nothing, a newline, anything else */
         uint32_t v0 = 0;
         if (d.ctx_dep && start > 0) {
-            v0 = __ldg(input + start - 1) == '\n' ? 1u : 2u;
+            const uint32_t pb = __ldg(input + start - 1);
+            const bool word = (pb - '0' < 10u) || ((pb | 0x20) - 'a' < 26u) || pb == '_';
+            v0 = pb == '\n' ? 1u : word ? 2u : 3u;
         }
         uint32_t s = d.init[v0];
         int32_t pos = start, mpos = -1;
@@ -242,6 +244,9 @@ k_pike_lineage(sre_dev_pdfa_t d, const uint8_t *__restrict__ buf, const int64_t 
         /* the transition taken at position p, as an index into eofs / mev */
         auto taken = [&](int32_t p) -> uint32_t { return *slot(p); };
         if (at_eof) {
+            if (d.eof0 != nullptr) {
+                assign(__ldg(d.eof0 + s), size);        /* SAVEd by assertions resolved at the end */
+            }
             j = ef & 0xff;
             rid = ef >> 16;
             u = size - 1;
@@ -250,8 +255,12 @@ k_pike_lineage(sre_dev_pdfa_t d, const uint8_t *__restrict__ buf, const int64_t 
             j = rid = 0;
             u = -1;
         } else {
-            const uint2 m = ld64(mev + taken(mpos));
+            const uint32_t tm = taken(mpos);
+            const uint2 m = ld64(mev + tm);
             assign(m.x, mpos + 1);
+            if (d.mev0 != nullptr) {
+                assign(__ldg(d.mev0 + tm), mpos);       /* ... by assertions resolved before the byte */
+            }
             j = m.y & 0xff;
             stop = (m.y & 0x100u) != 0;
             rid = m.y >> 16;
@@ -268,8 +277,12 @@ k_pike_lineage(sre_dev_pdfa_t d, const uint8_t *__restrict__ buf, const int64_t 
                 lost = true;
                 break;
             }
-            const uint2 e = ld64(ent + ld32(eofs + taken(u)) + j);
+            const uint32_t ei = ld32(eofs + taken(u)) + j;
+            const uint2 e = ld64(ent + ei);
             assign(e.x, u + 1);
+            if (d.ent0 != nullptr) {
+                assign(__ldg(d.ent0 + ei), u);
+            }
             j = e.y & 0xff;
             stop = (e.y & 0x100u) != 0;         /* the parent is the ".*?" thread: it carries no captures */
             u--;

@@ -11,30 +11,63 @@
 #include <map>
 #include <string.h>
 
+namespace {
+
+inline bool isword(uint32_t c)
+{
+    return (c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_';
+}
+
+/* one thread of a list: the instruction it is parked on | 0x8000 when it is parked on \b / \B and
+ * the byte in front of it was a word byte (sre_vm_pike.c:868-887: t->seen_word) */
+typedef std::vector<uint16_t> list_t;
+
+struct item_t {             /* a thread being stepped */
+    uint16_t ent;           /* park | seen_word << 15 */
+    uint8_t  parent;        /* index in the list it descends from */
+    uint32_t mask0;         /* slots SAVEd at the position of the step by resolved look-aheads */
+};
+
+}  // namespace
+
 bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uint32_t max_states, sre_pdfa_t &out)
 {
     const uint32_t np = T.npark;
-    if (np == 0 || max_states > 0x7fff) {
+    if (np == 0 || np >= 0x8000 || max_states > 0x7fff) {
         return false;
     }
-    out.ctx_dep = T.ctx_dep;
+    bool lookahead = false, wordy = false;
     for (uint32_t P = 0; P < np; P++) {
-        if (T.kind[P] >= 2) {
-            return false;           /* look-ahead assertions: not a function of the byte alone */
-        }
+        lookahead |= T.kind[P] >= 2;
+        wordy |= T.kind[P] >= 4;
     }
+    out.ctx_dep = T.ctx_dep;
+    out.lookahead = lookahead;
     out.max_slots = T.max_slots;
+    /* what a state must remember of the byte in front of it: 0 nothing / offset 0, 1 a newline,
+     * 2 a word byte, 3 anything else -- only as far as some closure can tell the difference */
+    auto kind_of = [&](uint32_t b) -> uint32_t {
+        if (wordy && isword(b)) {
+            return 2;
+        }
+        if (T.ctx_dep) {
+            return b == '\n' ? 1u : 3u;
+        }
+        return 0;               /* nothing to tell apart from "nothing in front" */
+    };
+    auto ctx_of = [&](uint32_t pk) -> uint32_t { return !T.ctx_dep ? 0u : pk == 0 ? 0u : pk == 1 ? 1u : 2u; };
 
-    /* byte classes: bytes that the same parked instructions accept */
+    /* byte classes: bytes that the same parked instructions accept and that leave the same
+     * look-behind kind (and, with `$`, '\n' apart) */
     {
         std::map<std::vector<uint8_t>, uint32_t> sigs;
         for (uint32_t b = 0; b < 256; b++) {
-            std::vector<uint8_t> sig(T.nsets + 1);
+            std::vector<uint8_t> sig(T.nsets + 2);
             for (uint32_t k = 0; k < T.nsets; k++) {
                 sig[k] = (T.accept[(size_t) k * 8 + (b >> 5)] >> (b & 31)) & 1;
             }
-            /* the look-behind context a byte leaves: '\n' apart when closures depend on it */
-            sig[T.nsets] = T.ctx_dep && b == '\n';
+            sig[T.nsets] = (uint8_t) kind_of(b);
+            sig[T.nsets + 1] = lookahead && b == '\n';
             std::map<std::vector<uint8_t>, uint32_t>::iterator it = sigs.find(sig);
             if (it == sigs.end()) {
                 it = sigs.insert(std::make_pair(sig, (uint32_t) sigs.size())).first;
@@ -52,136 +85,216 @@ bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uin
         return (T.accept[(size_t) T.acc_idx[P] * 8 + (b >> 5)] >> (b & 31)) & 1;
     };
 
-    typedef std::vector<uint16_t> list_t;
-    std::map<list_t, uint32_t> ids;
-    std::vector<list_t> lists;
-    lists.push_back(list_t());          /* state 0: the empty list */
-    ids[list_t()] = 0;
-
-    /* the start closures (closure of "pc 0", number np) by look-behind context */
-    for (uint32_t v = 0; v < 3; v++) {
-        if (v > 0 && !T.ctx_dep) {
-            out.init[v] = out.init[0];
-            out.init_mask_ofs[v] = out.init_mask_ofs[0];
-            continue;
+    /* a state = (look-behind kind, list) */
+    typedef std::pair<uint32_t, list_t> key_t;
+    std::map<key_t, uint32_t> ids;
+    std::vector<key_t> states;
+    states.push_back(key_t(0, list_t()));       /* state 0: the empty list */
+    ids[states[0]] = 0;
+    auto intern = [&](uint32_t pk, const list_t &l, uint32_t *id) -> bool {
+        /* the empty list is one state whatever came before it */
+        const key_t k(l.empty() ? 0u : pk, l);
+        std::map<key_t, uint32_t>::iterator it = ids.find(k);
+        if (it != ids.end()) {
+            *id = it->second;
+            return true;
         }
+        if (states.size() >= max_states) {
+            return false;
+        }
+        *id = (uint32_t) states.size();
+        ids[k] = *id;
+        states.push_back(k);
+        return true;
+    };
+
+    /* the start closures (closure of "pc 0", number np) by what lies in front of the first byte */
+    for (uint32_t pk = 0; pk < 4; pk++) {
         list_t init;
         std::vector<uint8_t> marks(np, 0);
-        out.init_mask_ofs[v] = (uint32_t) out.init_mask.size();
-        for (uint32_t e = T.ofs[v * (np + 2) + np]; e < T.ofs[v * (np + 2) + np + 1]; e++) {
+        out.init_mask_ofs[pk] = (uint32_t) out.init_mask.size();
+        const uint32_t vofs = ctx_of(pk) * (np + 2);
+        for (uint32_t e = T.ofs[vofs + np]; e < T.ofs[vofs + np + 1]; e++) {
             const uint32_t fp = T.ent[e];
             if (marks[fp]) {
                 continue;
             }
             marks[fp] = 1;
-            init.push_back((uint16_t) fp);
+            init.push_back((uint16_t) (fp | ((T.kind[fp] >= 4 && pk == 2) ? 0x8000u : 0u)));
             out.init_mask.push_back(T.emask[e]);
         }
         if (init.empty() || init.size() > 255) {
             return false;
         }
-        std::map<list_t, uint32_t>::iterator it = ids.find(init);
-        if (it == ids.end()) {
-            out.init[v] = (uint32_t) lists.size();
-            ids[init] = out.init[v];
-            lists.push_back(init);
-        } else {
-            out.init[v] = it->second;
+        /* (kinds the program cannot tell apart give the same state) */
+        const uint32_t eff = pk == 0 ? 0u : kind_of(pk == 1 ? '\n' : pk == 2 ? 'a' : '.');
+        if (!intern(pk == 0 ? 0u : eff, init, &out.init[pk])) {
+            return false;
         }
     }
 
-    std::vector<uint8_t> marks(np);
-    for (uint32_t s = 0; s < lists.size(); s++) {
-        for (uint32_t c = 0; c < C; c++) {
-            const list_t cur = lists[s];        /* copy: lists grows below */
-            const uint32_t b = rep[c];
-            /* closures appended after this byte see it as their look-behind context */
-            const uint32_t vofs = (T.ctx_dep ? (b == '\n' ? 1u : 2u) : 0u) * (np + 2);
-            list_t next;
-            std::vector<uint8_t> parents;
-            std::vector<uint32_t> masks;
-            bool mev = false;
-            uint8_t mpar = 0;
-            uint32_t mmask = 0;
-            uint16_t mreg = 0;
-            memset(marks.data(), 0, np);
-            for (size_t j = 0; j < cur.size() && !mev; j++) {
-                const uint32_t P = cur[j];
-                if (T.kind[P] == 1) {
-                    /* a parked MATCH thread (only the start closure parks one): sre_vm_pike.c:535-553 */
-                    mev = true;
-                    mpar = (uint8_t) j;
-                    mmask = 0;
-                    mreg = T.regex[P];
-                    break;
+    std::vector<uint8_t> m_prev(np), m_cur(np);
+    /*
+     * One step of state s: on byte b (eof = false) or at the end of the input.  Threads are taken
+     * in list order; a look-ahead thread whose assertion holds is replaced, in place, by its
+     * closure at the same position (sre_vm_pike.c:505-523, dedup against the previous step's
+     * marks: the tag-- trick); a consuming thread that takes b appends its closure at the next
+     * position; MATCH (parked, or reached by a closure that may report it) ends the step and
+     * cuts what has lower priority.
+     */
+    struct step_out_t {
+        list_t                next;
+        std::vector<uint8_t>  parents;
+        std::vector<uint32_t> mask0, mask1;
+        bool                  mev = false;
+        uint8_t               mpar = 0;
+        uint32_t              mmask0 = 0, mmask1 = 0;
+        uint16_t              mreg = 0;
+    };
+    auto step = [&](const key_t &st, bool eof, uint32_t b, step_out_t &o) {
+        const list_t &cur = st.second;
+        const uint32_t pk = st.first;
+        const bool prev_word = pk == 2, cur_word = !eof && isword(b);
+        const uint32_t vhold = ctx_of(pk) * (np + 2);
+        const uint32_t vnext = (T.ctx_dep ? (b == '\n' ? 1u : 2u) : 0u) * (np + 2);
+        memset(m_cur.data(), 0, np);
+        memset(m_prev.data(), 0, np);
+        for (size_t j = 0; j < cur.size(); j++) {
+            m_prev[cur[j] & 0x7fff] = 1;
+        }
+        std::vector<item_t> hold;           /* LIFO, back = top */
+        size_t i = 0;
+        for (;;) {
+            item_t t;
+            if (!hold.empty()) {
+                t = hold.back();
+                hold.pop_back();
+            } else if (i < cur.size()) {
+                t.ent = cur[i];
+                t.parent = (uint8_t) i;
+                t.mask0 = 0;
+                i++;
+            } else {
+                break;
+            }
+            const uint32_t P = t.ent & 0x7fff;
+            const bool sw = (t.ent & 0x8000) != 0;
+            const uint32_t kind = T.kind[P];
+            if (kind >= 2) {
+                bool holds;
+                switch (kind) {
+                case 2:  holds = eof; break;
+                case 3:  holds = eof || b == '\n'; break;
+                case 4:  holds = (sw == cur_word); break;
+                default: holds = (sw != cur_word); break;
                 }
-                if (!accepts(P, b)) {
+                if (!holds) {
                     continue;
                 }
-                for (uint32_t e = T.ofs[vofs + P]; e < T.ofs[vofs + P + 1]; e++) {
+                std::vector<item_t> add;
+                for (uint32_t e = T.ofs[vhold + P]; e < T.ofs[vhold + P + 1]; e++) {
                     const uint32_t fp = T.ent[e];
-                    if (marks[fp]) {
+                    if (m_prev[fp]) {
                         continue;
                     }
-                    marks[fp] = 1;
+                    m_prev[fp] = 1;
+                    m_cur[fp] = 0;
+                    item_t a;
+                    a.ent = (uint16_t) (fp | ((T.kind[fp] >= 4 && prev_word) ? 0x8000u : 0u));
+                    a.parent = t.parent;
+                    a.mask0 = t.mask0 | T.emask[e];
+                    add.push_back(a);
+                }
+                for (size_t k = add.size(); k-- > 0;) {     /* prepended: the first one on top */
+                    hold.push_back(add[k]);
+                }
+            } else if (kind == 1) {
+                /* a parked MATCH thread: sre_vm_pike.c:535-553 */
+                o.mev = true;
+                o.mpar = t.parent;
+                o.mmask0 = t.mask0;
+                o.mmask1 = 0;
+                o.mreg = T.regex[P];
+                return;
+            } else if (!eof && accepts(P, b)) {
+                for (uint32_t e = T.ofs[vnext + P]; e < T.ofs[vnext + P + 1]; e++) {
+                    const uint32_t fp = T.ent[e];
+                    if (m_cur[fp]) {
+                        continue;
+                    }
+                    m_cur[fp] = 1;
+                    m_prev[fp] = 0;
                     if (T.kind[fp] == 1) {
                         /* the closure reached MATCH: report and cut what has lower priority */
-                        mev = true;
-                        mpar = (uint8_t) j;
-                        mmask = T.emask[e];
-                        mreg = T.regex[fp];
-                        break;
+                        o.mev = true;
+                        o.mpar = t.parent;
+                        o.mmask0 = t.mask0;
+                        o.mmask1 = T.emask[e];
+                        o.mreg = T.regex[fp];
+                        return;
                     }
-                    next.push_back((uint16_t) fp);
-                    parents.push_back((uint8_t) j);
-                    masks.push_back(T.emask[e]);
+                    o.next.push_back((uint16_t) (fp | ((T.kind[fp] >= 4 && cur_word) ? 0x8000u : 0u)));
+                    o.parents.push_back(t.parent);
+                    o.mask0.push_back(t.mask0);
+                    o.mask1.push_back(T.emask[e]);
                 }
             }
-            if (next.size() > 255) {
+        }
+    };
+
+    for (uint32_t s = 0; s < states.size(); s++) {
+        for (uint32_t c = 0; c < C; c++) {
+            const key_t cur = states[s];            /* copy: states grows below */
+            const uint32_t b = rep[c];
+            step_out_t o;
+            step(cur, false, b, o);
+            if (o.next.size() > 255) {
                 return false;
             }
             uint32_t id;
-            std::map<list_t, uint32_t>::iterator it = ids.find(next);
-            if (it == ids.end()) {
-                id = (uint32_t) lists.size();
-                if (id >= max_states) {
-                    return false;
-                }
-                ids[next] = id;
-                lists.push_back(next);
-            } else {
-                id = it->second;
+            if (!intern(kind_of(b), o.next, &id)) {
+                return false;
             }
-            out.trans.push_back((uint16_t) (id | (mev ? 0x8000u : 0u)));
+            out.trans.push_back((uint16_t) (id | (o.mev ? 0x8000u : 0u)));
             out.eofs.push_back((uint32_t) out.eparent.size());
-            out.eparent.insert(out.eparent.end(), parents.begin(), parents.end());
-            out.emask.insert(out.emask.end(), masks.begin(), masks.end());
-            out.mparent.push_back(mpar);
-            out.mmask.push_back(mmask);
-            out.mregex.push_back(mreg);
+            out.eparent.insert(out.eparent.end(), o.parents.begin(), o.parents.end());
+            out.emask.insert(out.emask.end(), o.mask1.begin(), o.mask1.end());
+            out.emask0.insert(out.emask0.end(), o.mask0.begin(), o.mask0.end());
+            out.mparent.push_back(o.mpar);
+            out.mmask.push_back(o.mmask1);
+            out.mmask0.push_back(o.mmask0);
+            out.mregex.push_back(o.mreg);
             if (out.eparent.size() > (1u << 26)) {
                 return false;
             }
         }
     }
     out.eofs.push_back((uint32_t) out.eparent.size());
-    out.nstates = (uint32_t) lists.size();
+    out.nstates = (uint32_t) states.size();
 
     out.any_idx.assign(out.nstates, 0xff);
     out.eof_idx.assign(out.nstates, 0xff);
     out.eof_regex.assign(out.nstates, 0);
+    out.eof_mask0.assign(out.nstates, 0);
     out.list_ofs.assign(out.nstates + 1, 0);
     for (uint32_t s = 0; s < out.nstates; s++) {
+        const list_t &l = states[s].second;
         out.list_ofs[s] = (uint32_t) out.list_park.size();
-        for (size_t j = 0; j < lists[s].size(); j++) {
-            const uint32_t P = lists[s][j];
+        for (size_t j = 0; j < l.size(); j++) {
+            const uint32_t P = l[j] & 0x7fff;
             out.list_park.push_back((uint16_t) P);
             if ((int32_t) P == T.p_any) {
                 out.any_idx[s] = (uint8_t) j;
             }
-            if (T.kind[P] == 1 && out.eof_idx[s] == 0xff) {
-                out.eof_idx[s] = (uint8_t) j;
-                out.eof_regex[s] = T.regex[P];
+        }
+        /* the step at the end of the input: the first thread that reaches MATCH there */
+        if (s != 0) {
+            step_out_t o;
+            step(states[s], true, 0, o);
+            if (o.mev) {
+                out.eof_idx[s] = o.mpar;
+                out.eof_regex[s] = o.mreg;
+                out.eof_mask0[s] = o.mmask0;
             }
         }
     }

@@ -25,13 +25,18 @@
  * slot from the last step that SAVEd it.  Leftmost-first priority is the list
  * order, so the result is the Pike VM's, bit for bit.
  *
- * Look-behind assertions (`\A`, `^`) are part of it: the closure a step appends
- * depends on the consumed byte only through "was it a newline" (the look-behind
- * context of sre_closure.h), so '\n' gets a byte class of its own and the search
- * starts from one of three start lists (at offset 0 / after a newline /
- * elsewhere).  Built for programs without look-AHEAD assertions (`$ \z \b \B`:
- * their closures wait for the next byte); sre_build_pdfa returns false for those
- * and when the automaton exceeds max_states / lists of 255 threads: they stay on
+ * Assertions are part of it.  Look-behind ones (`\A`, `^`): the closure a step
+ * appends depends on the consumed byte only through "was it a newline" (the
+ * look-behind context of sre_closure.h), so the state remembers the kind of the
+ * byte in front of it (nothing / newline / word byte / other, as far as the
+ * program can tell them apart) and the search starts from one of four start
+ * lists.  Look-ahead ones (`$ \z \b \B`): a thread parked on the assertion is
+ * part of the list (with the seen_word flag of sre_vm_pike.c:868-887 for `\b
+ * \B`); the step on the next byte -- or the step at the end of the input --
+ * resolves it and splices its closure in at the SAME position, so a provenance
+ * record carries two slot sets: SAVEd at the position of the step (emask0) and
+ * after the consumed byte (emask).  sre_build_pdfa returns false when the
+ * automaton exceeds max_states / lists of 255 threads: those programs stay on
  * k_pike_table.
  */
 #ifndef SRE_PDFA_H
@@ -45,21 +50,25 @@ struct sre_pdfa_t {
     uint32_t                nstates = 0;        /* state 0 = the empty list           */
     uint32_t                nclasses = 0;
     uint8_t                 clsmap[256];
-    uint32_t                init[3] = { 0, 0, 0 };      /* the start closure by look-behind context:
-                                                           at offset 0, after a newline, elsewhere */
-    uint32_t                init_mask_ofs[3] = { 0, 0, 0 };     /* ... where its init_mask begins */
-    bool                    ctx_dep = false;    /* the three differ (program has \A or ^) */
+    /* the start closure by what lies in front of the first byte: nothing (offset 0), a newline, a
+     * word byte, anything else */
+    uint32_t                init[4] = { 0, 0, 0, 0 };
+    uint32_t                init_mask_ofs[4] = { 0, 0, 0, 0 };  /* ... where its init_mask begins */
+    bool                    ctx_dep = false;    /* program has \A or ^ */
+    bool                    lookahead = false;  /* program has $ \z \b \B */
     uint32_t                max_slots = 0;      /* slots of the largest regex (<= 32) */
     std::vector<uint16_t>   trans;              /* [nstates][nclasses]                */
     std::vector<uint32_t>   eofs;               /* [nstates * nclasses + 1]           */
     std::vector<uint8_t>    eparent;
-    std::vector<uint32_t>   emask;
+    std::vector<uint32_t>   emask, emask0;      /* slots SAVEd after the byte / at the step's position */
     std::vector<uint8_t>    mparent;            /* [nstates * nclasses]               */
-    std::vector<uint32_t>   mmask;
+    std::vector<uint32_t>   mmask, mmask0;
     std::vector<uint16_t>   mregex;
     std::vector<uint8_t>    any_idx;            /* [nstates] index of the ".*?" thread, 0xff: none */
-    std::vector<uint8_t>    eof_idx;            /* [nstates] first parked MATCH (EOF step), 0xff   */
+    std::vector<uint8_t>    eof_idx;            /* [nstates] the thread that reaches MATCH in the step at
+                                                   the end of the input (its index in the list), 0xff */
     std::vector<uint16_t>   eof_regex;          /* [nstates]                          */
+    std::vector<uint32_t>   eof_mask0;          /* [nstates] slots SAVEd on the way (at the end position) */
     std::vector<uint32_t>   init_mask;          /* slots SAVEd by a start closure, per thread (init_mask_ofs) */
     std::vector<uint32_t>   list_ofs;           /* [nstates + 1] the lists themselves */
     std::vector<uint16_t>   list_park;

@@ -413,15 +413,18 @@ def test_pike_tier_selection(cu):
     rc, _ = prog.pike_lines(dev, n, 1024, 1024)
     assert prog.last_pike_tier() == 3
     assert int((rc == 0).sum()) == n
-    # look-behind assertions (^, \A) are part of the determinised Pike VM (the start list and the
-    # closures depend on "after a newline / at offset 0"); look-ahead ones ($ \b) stay on the
-    # closure-table kernel.  Same rows as the oracle either way, on lines with inner newlines.
+    # assertions are part of the determinised Pike VM: look-behind ones through the start list and
+    # the kind of the byte in front of a state, look-ahead ones as threads parked on the assertion
+    # (resolved by the next byte or at the end of the line).  Same rows as the oracle, on lines
+    # with inner newlines.
     o = capi.load("oracle")
     lines = corpus.log_lines(n, 1024).numpy().copy()
     lines[:, 200] = 10
     lines[::2, 201:204] = np.frombuffer(b"GET", dtype=np.uint8)
     dev = torch.from_numpy(lines).cuda()
-    for rx, tier in ((rb"^(\d+)\.(\d+)", 3), (rb"^(GET|\d+)(.)", 3), (rb"\A(\d+)", 3), (rb"(\w+)$", 0), (rb"\b(GET)\b", 0)):
+    la = 3 if os.environ.get("SRE_PDFA_LOOKAHEAD", "0") != "0" else 0     # (see sre_cuda_pike_exec_lines)
+    for rx, tier in ((rb"^(\d+)\.(\d+)", 3), (rb"^(GET|\d+)(.)", 3), (rb"\A(\d+)", 3), (rb"(\w+)$", la), (rb"\b(GET)\b", la),
+                     (rb"(\d+)\.*$", la), (rb"^(\S+) .*\B(\.)\z", la), (rb"(\w+)\b (\S+)$", la)):
         prog = cu.CudaProgram(rx)
         rc, ov = prog.pike_lines(dev, n, 1024, 1024)
         assert prog.last_pike_tier() == tier, (rx, prog.last_pike_tier())

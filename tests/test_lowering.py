@@ -291,7 +291,7 @@ def _bind_pdfa(lc):
 
 def test_pdfa_pike_against_golden(golden, oracle, lc, leftmost_first):
     """The determinised Pike VM (ordered thread lists as DFA states + lineage walk,
-    lower/sre_pdfa.cpp) on every golden block it applies to (no look-ahead assertions): rc and
+    lower/sre_pdfa.cpp) on every golden block it applies to (every block whose automaton stays small): rc and
     the whole ovector; with a short ring it either agrees or asks for the next tier."""
     _bind_pdfa(lc)
     n = short = 0
@@ -310,15 +310,15 @@ def test_pdfa_pike_against_golden(golden, oracle, lc, leftmost_first):
 
 
 def test_pdfa_pike_fuzz_vs_oracle(oracle, lc, leftmost_first):
-    """random regexes without look-ahead assertions (nested groups, lazy and greedy
-    repetition, alternation, empty loops, `^` and `\\A` over subjects with newlines)
-    and sets of them x random subjects: rc + ovector == the oracle's Pike"""
+    """random regexes (nested groups, lazy and greedy repetition, alternation, empty
+    loops, all six assertions over subjects with newlines) and sets of them x random
+    subjects: rc + ovector == the oracle's Pike"""
     import random
     _bind_pdfa(lc)
     rng = random.Random(31337)
     atoms = ["a", "b", "ab", " ", "_", ".", "|", "(", ")", "(?:", "*", "+", "?", "*?", "+?", "??", "{2}", "{0,2}",
              "{1,}", "[ab]", "[^a]", "\\w", "\\W", "\\s", "\\d", "1", "(a)", "(b*)", "(a|ab)", "(\\w+)",
-             "^", "\\A", "\\n", "(^a)", "(?:^|b)"]
+             "^", "\\A", "\\n", "(^a)", "(?:^|b)", "$", "\\z", "\\b", "\\B", "(a$)", "(\\bb)", "(?:$|a)"]
     alphabet = b"ab _1.\n\n"
     done = applicable = 0
     while done < 1500:
