@@ -1108,3 +1108,42 @@ def test_batched_streaming_pike_contexts(cu):
             assert final[i] == (wrc, wov), (rx, subjects[i], final[i], wrc, wov)
             assert traces[i] == [tuple(t) for t in wt], (rx, subjects[i])
         assert sum(1 for f in final if f[0] >= 0) > 20
+
+
+def test_pike_lookahead_assertions_on_long_lines(cu):
+    """Programs with look-ahead assertions (`$ \\z \\b \\B`) over lines long enough for the start
+    hint to land anywhere (the search then begins from the start list of the byte in front: nothing
+    / newline / word byte / other): rc and the whole ovector against the oracle, through the
+    default tier (the determinised Pike VM when SRE_PDFA_LOOKAHEAD allows it, else the
+    closure-table kernel) and through the closure-table tier."""
+    import random
+    rng = random.Random(4242)
+    words = [b"GET", b"POST", b"a", b"ab", b"x1", b"_", b"77", b"index.html", b"b", b"."]
+    seps = [b" ", b" ", b" ", b"\n", b".", b"-", b"  ", b""]
+    regexes = [rb"(\w+)$", rb"\b(GET)\b (\w+)", rb"(\d+)\.*$", rb"(\w+)\b (\S+)$", rb"(a|ab)\b(.)", rb"(\w+)\B(\w)$",
+               rb"^(\w+)\b.*?(\w+)$", rb"(\S+)\z", rb"\B(\d)(\d)\b", rb"(x\d)?\b(\w+)\b\.$", rb"(?:(a)|b)+\b",
+               rb"(\w*)\b(\W+)\b(\w*)$", rb"\b(\w+) \1?$", rb"(a+)$|(b+)\b", rb"()\b(\w)"]
+    nlines, pitch = 384, 208
+    for rx in regexes:
+        try:
+            prog = cu.CudaProgram(rx)
+        except Exception:
+            continue            # (a back-reference: not in the reference's syntax either)
+        for linelen in (200, 61):
+            host = np.zeros((nlines, pitch), dtype=np.uint8)
+            for i in range(nlines):
+                row = bytearray()
+                # a head that cannot match most of the regexes, so that the hint moves into the line
+                row += b"-" * rng.randrange(0, 120)
+                while len(row) < pitch:
+                    row += rng.choice(words) + rng.choice(seps)
+                host[i] = np.frombuffer(bytes(row[:pitch]), dtype=np.uint8)
+            _, want_rc, want_ov = baseline.run_lines("oracle", rx, None, host, nlines, pitch, linelen,
+                                                     baseline.ENGINE_PIKE, ovec_slots=prog.nslots)
+            dev = torch.from_numpy(host).cuda()
+            for tier in (0, 3):
+                prog.set_pike_tier(tier)
+                rc, ov = prog.pike_lines(dev, nlines, pitch, linelen)
+                assert (rc.cpu().numpy() == want_rc).all(), (rx, linelen, tier)
+                assert (ov.cpu().numpy() == want_ov).all(), (rx, linelen, tier)
+        prog.program.close()

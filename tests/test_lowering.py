@@ -340,6 +340,55 @@ def test_pdfa_pike_fuzz_vs_oracle(oracle, lc, leftmost_first):
     assert applicable > 2000
 
 
+def test_pdfa_pike_from_the_start_hint(golden, oracle, lc, leftmost_first):
+    """k_pike_lineage begins at the 16-byte boundary below the DFA start hint, from the start list
+    of the byte in front (nothing / newline / word byte / other -- what `^ \\A` look back at and
+    what decides `\\b \\B` at the first byte).  Model: every start from the hint down to 16 bytes
+    below it gives the oracle's rc and ovector, on the golden blocks and on random regexes with all
+    six assertions over longer subjects."""
+    import random
+    _bind_pdfa(lc)
+
+    def check(p, s, want, tag):
+        if _pdfa_pike(lc, p, s) is None:
+            return 0
+        h = lc.lc_create(p.prog, 4096)
+        hint = lc.lc_hint_cls(h, s, len(s)) if h else -1
+        if h:
+            lc.lc_destroy(h)
+        if hint <= 0:
+            return 0
+        for start in range(max(0, hint - 16), hint + 1):
+            assert _pdfa_pike(lc, p, s, start) == want, (tag, s, hint, start)
+        return 1
+
+    hinted = 0
+    for b in runnable(golden)[::4]:
+        p = oracle.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        hinted += check(p, b["subject_b"], (b["pike"]["rc"], b["pike"]["ov"]), (b["file"], b["name"]))
+        p.close()
+    assert hinted > 20, hinted
+
+    rng = random.Random(777)
+    atoms = ["a", "b", "ab", " ", "_", ".", "|", "(", ")", "(?:", "*", "+", "?", "+?", "{2}", "[ab]", "[^a]", "\\w",
+             "\\W", "\\d", "1", "(a)", "(a|ab)", "(\\w+)", "^", "\\A", "\\n", "$", "\\z", "\\b", "\\B", "(a$)",
+             "(\\bb)", "(?:$|a)", "\\b", "$", "\\B"]
+    alphabet = b"ab _1.\n--"
+    done = fuzz_hinted = 0
+    while done < 400:
+        rx = "".join(rng.choice(atoms) for _ in range(rng.randrange(2, 8))).encode()
+        try:
+            p = oracle.compile(rx, 0)
+        except capi.SreSyntaxError:
+            continue
+        done += 1
+        for _ in range(2):
+            s = b"-" * rng.randrange(0, 30) + bytes(rng.choice(alphabet) for _ in range(rng.randrange(0, 40)))
+            fuzz_hinted += check(p, s, leftmost_first.pike(p, s), rx)
+        p.close()
+    assert fuzz_hinted > 100, fuzz_hinted
+
+
 def test_prefilter_misfire_marking_rule(oracle, lc):
     """k_pike_quirk_mark's rule is a superset of the lines on which the reference's first-byte
     prefilter misfires (lower/sre_quirk.cpp): wherever the oracle with the prefilter (== the
