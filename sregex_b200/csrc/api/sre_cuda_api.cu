@@ -399,7 +399,7 @@ int upload(sre_cuda_program_t *cp)
         o_cbent = b.add(clo.bent.data(), clo.bent.size() * 4);
         o_cbofs = b.add(clo.bofs.data(), clo.bofs.size() * 2);
     }
-    /* the determinised Pike VM (programs without assertions, up to 4096 thread lists) */
+    /* the determinised Pike VM (up to 4096 thread lists of <= 255 threads) */
     sre_pdfa_t pd;
     const bool has_pd = has_clo && sre_build_pdfa(prog, clo, 4096, pd);
     size_t o_pcls = 0, o_ptrans = 0, o_peofs = 0, o_pent = 0, o_pmev = 0, o_peof = 0, o_pinit = 0;
@@ -1248,7 +1248,7 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
     static int la_ok = -1;
     if (la_ok < 0) {
         const char *e = getenv("SRE_PDFA_LOOKAHEAD");
-        la_ok = e ? atoi(e) : 0;
+        la_ok = e ? atoi(e) : 1;
     }
     const bool use_lineage = tier_mode == 0 && sre_pike_lineage_applicable(cp->pdfa, linelen) && table_ok
                              && (cp->pdfa.ent0 == nullptr || la_ok);

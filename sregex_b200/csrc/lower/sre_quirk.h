@@ -20,8 +20,10 @@
 #include "../host/sre_internal.h"
 
 /* -> true when the misfire is possible at all; single[b >> 5] bit b & 31: a match that starts at
- * byte value b right after a prefilter jump may trigger it (a superset when the program has
- * assertions: every leading byte) */
+ * byte value b right after a prefilter jump may trigger it.  Programs with assertions are
+ * replayed in each look-behind context a landing offset can have (the byte in front a newline, a
+ * word byte, neither), with the look-ahead threads parked and resolved by the landing byte as
+ * the reference does (:452-509, :842-887): `\bGET\b`, `^\d+`, `\w+$` have an empty set. */
 bool sre_quirk_bytes(const sre_program_t *prog, uint32_t single[8]);
 
 #endif

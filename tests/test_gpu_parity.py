@@ -294,7 +294,7 @@ def test_big_regex_set_with_assertions_vs_oracle(cu):
     """a set of 40 random regexes rich in look-ahead / look-behind assertions
     (> 64 parked instructions: bit-set marks in shared memory, pending
     look-ahead closures, per-context closure tables) over random short lines:
-    matched id + ovector == the oracle's Pike, on the table tier"""
+    matched id + ovector == the oracle's Pike, on the default tier and on the table tier"""
     import random
     rng = random.Random(99)
     atoms = ["a", "b", "ab", " ", "_", "1", ".", "^", "$", "\\b", "\\B", "\\z", "\\A", "(a)", "(b+)", "(?:ab)*", "+", "?",
@@ -317,10 +317,15 @@ def test_big_regex_set_with_assertions_vs_oracle(cu):
     lines[:, :linelen] = alphabet[rs.randint(0, len(alphabet), size=(n, linelen))]
     _, want_rc, want_ov = baseline.run_lines("oracle", pats, None, lines, n, pitch, linelen,
                                              baseline.ENGINE_PIKE, nthreads=8, ovec_slots=prog.nslots)
-    rc, ov = prog.pike_lines(torch.from_numpy(lines).cuda(), n, pitch, linelen)
-    assert prog.last_pike_tier() == 0
-    assert (rc.cpu().numpy() == want_rc).all()
-    assert (ov.cpu().numpy() == want_ov).all()
+    dev = torch.from_numpy(lines).cuda()
+    # the default tier (the determinised Pike VM when the set has one, look-ahead threads parked
+    # in its lists) and the closure-table tier
+    for mode, tiers in ((0, (0, 3)), (3, (0,))):
+        prog.set_pike_tier(mode)
+        rc, ov = prog.pike_lines(dev, n, pitch, linelen)
+        assert prog.last_pike_tier() in tiers
+        assert (rc.cpu().numpy() == want_rc).all(), mode
+        assert (ov.cpu().numpy() == want_ov).all(), mode
     assert len(set(want_rc.tolist())) > 5
 
 
@@ -422,7 +427,7 @@ def test_pike_tier_selection(cu):
     lines[:, 200] = 10
     lines[::2, 201:204] = np.frombuffer(b"GET", dtype=np.uint8)
     dev = torch.from_numpy(lines).cuda()
-    la = 3 if os.environ.get("SRE_PDFA_LOOKAHEAD", "0") != "0" else 0     # (see sre_cuda_pike_exec_lines)
+    la = 3 if os.environ.get("SRE_PDFA_LOOKAHEAD", "1") != "0" else 0     # (see sre_cuda_pike_exec_lines)
     for rx, tier in ((rb"^(\d+)\.(\d+)", 3), (rb"^(GET|\d+)(.)", 3), (rb"\A(\d+)", 3), (rb"(\w+)$", la), (rb"\b(GET)\b", la),
                      (rb"(\d+)\.*$", la), (rb"^(\S+) .*\B(\.)\z", la), (rb"(\w+)\b (\S+)$", la)):
         prog = cu.CudaProgram(rx)
@@ -1014,8 +1019,9 @@ def test_pike_reproduces_the_reference_prefilter_misfire(cu):
         prog.program.close()
     # the family at large: regexes that can match one byte, lines full of isolated candidates
     rng = random.Random(2718)
-    heads = [rb"a+", rb"\w+", rb"\d+", rb"[ab]+", rb"(a+)", rb"(\w)+", rb"(?:a|b)+", rb"^a+", rb"\ba+"]
-    tails = [rb"b?", rb"x?", rb"\.?", rb"(\d)?", rb" ?", rb"(?:ab)?", rb"b*", rb"$", rb""]
+    heads = [rb"a+", rb"\w+", rb"\d+", rb"[ab]+", rb"(a+)", rb"(\w)+", rb"(?:a|b)+", rb"^a+", rb"\ba+", rb"(?:^|\b)a+",
+             rb"\B?a+", rb"^?[ab]+"]
+    tails = [rb"b?", rb"x?", rb"\.?", rb"(\d)?", rb" ?", rb"(?:ab)?", rb"b*", rb"$", rb"", rb"(?:b|$)?", rb"b?\b", rb"\B?x?"]
     nlines, pitch = 512, 64
     alphabet = list(b"ab1. x\n")
     total = differ = 0

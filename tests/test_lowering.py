@@ -439,3 +439,43 @@ def test_prefilter_misfire_marking_rule(oracle, lc):
                     and not lead(s[st + 1]), (rx, s, on, off)
         p.close()
     assert differ > 100, differ
+
+    # programs with assertions: the analysis replays the landing step in each look-behind context
+    # (the byte in front a newline / a word byte / neither) with the look-ahead threads parked as
+    # the reference parks them -- random regexes over all six assertions
+    pre = [rb"", rb"", rb"^", rb"\b", rb"\B", rb"(?:^|\b)", rb"\A|", rb"(?:\b|\B)", rb"^?"]
+    mid = [rb"", rb"", rb"\b", rb"\B", rb"$?", rb"(?:\b|x)"]
+    post = [rb"", rb"", rb"\b", rb"\B", rb"$", rb"\z", rb"(?:$|\b)", rb"|\bb"]
+    alphabet = b"ab1. x\n_"
+    tried = differ2 = flagged = 0
+    while tried < 1200:
+        rx = rng.choice(pre) + rng.choice(heads) + rng.choice(mid) + rng.choice(tails) + rng.choice(post)
+        try:
+            p = oracle.compile(rx, 0)
+        except capi.SreSyntaxError:
+            continue
+        tried += 1
+        possible, single, lead = sets(p)
+        flagged += possible
+        for _ in range(30):
+            s = bytes(rng.choice(alphabet) for _ in range(rng.randrange(0, 28)))
+            on = oracle.pike(p, s)
+            oracle.pike_prefilter(False)
+            try:
+                off = oracle.pike(p, s)
+            finally:
+                oracle.pike_prefilter(True)
+            if on != off:
+                differ2 += 1
+                assert possible and off[0] >= 0, (rx, s, on, off)
+                st = off[1][0]
+                assert st >= 1 and st + 1 < len(s) and single(s[st]) and not lead(s[st - 1]) \
+                    and not lead(s[st + 1]), (rx, s, on, off)
+        p.close()
+    assert differ2 > 100 and flagged < tried, (differ2, flagged, tried)
+    # the shapes real patterns have: a word boundary or an anchor around a literal does not make
+    # every matched line a candidate
+    for rx in (rb'\b(GET|HEAD|POST|PUT) (\S+) HTTP/(\d)\.(\d)\b', rb'(\w+)$', rb'^(\d+)\.(\d+)', rb'\bERROR\b', rb'\d+$'):
+        p = oracle.compile(rx, 0)
+        assert sets(p)[0] == 0, rx
+        p.close()

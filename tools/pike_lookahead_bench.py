@@ -31,7 +31,9 @@ def timed(fn, reps=10):
     return a.elapsed_time(b) / reps
 
 
-for rx in (rb'\b(GET|HEAD|POST|PUT) (\S+) HTTP/(\d)\.(\d)\b', rb'"\s(\d+)\b.*?(\.*)$', rb'(\w+) (\S+) HTTP/(\d)\.(\d)'):
+for rx in (rb'\b(GET|HEAD|POST|PUT) (\S+) HTTP/(\d)\.(\d)\b', rb'"\s(\d+)\b.*?(\.*)$', rb'(\w+) (\S+) HTTP/(\d)\.(\d)',
+           rb'^(\d+)\.(\d+)\.(\d+)\.(\d+)\b', rb'\b(\d\d\d)\b \.+$', rb'(\w+)\B(\d)" (5\d\d)\b',
+           rb'\[(\d+)/(\w+)/(\d+)\b', rb'(?:^|\s)(/x/\d+)\s'):
     prog = cuda.CudaProgram(rx)
     ns = prog.nslots
     rc = torch.empty(N, dtype=torch.int32, device="cuda")
