@@ -3,8 +3,9 @@
  * thread lists (../lower/sre_pdfa.h), one CUDA thread per line.
  *
  * What it replaces: sre_vm_pike_exec + sre_vm_pike_add_thread + the capture
- * copies (reference sre_vm_pike.c:148-689, :756-942, sre_capture.c) for
- * programs without assertions.  Instead of simulating the thread list (k_pike_table:
+ * copies (reference sre_vm_pike.c:148-689, :756-942, sre_capture.c), assertions
+ * included (look-behind ones pick the start list, look-ahead ones are threads
+ * parked in the lists).  Instead of simulating the thread list (k_pike_table:
  * ~500 instructions per byte, 10 of 32 lanes busy), a lane runs
  *
  *   forward   one look-up per byte in the P-DFA (state = the ordered thread

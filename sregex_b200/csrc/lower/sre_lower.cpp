@@ -411,10 +411,14 @@ bool build_dfa(const sre_nfa_t &nfa, uint32_t max_states, sre_dfa_t &dfa)
     std::vector<uint32_t> block(D0);
     uint32_t nblocks = 0;
     {
+        bool third = false;
         for (uint32_t d = 0; d < D0; d++) {
             block[d] = d == ACC ? 1 : (fin0[d] == fin0[0] ? 0 : 2);
+            third |= block[d] == 2;
         }
-        nblocks = 3;
+        /* (the number of blocks there really are: the refinement stops when a round adds none,
+         * and must not take a first round that ends with three for a stable one) */
+        nblocks = third ? 3 : 2;
         /* state 0 and ACC are visited first: their blocks keep the numbers 0 and 1 */
         std::vector<uint32_t> order;
         order.push_back(0);

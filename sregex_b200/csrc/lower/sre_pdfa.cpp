@@ -85,15 +85,33 @@ bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uin
         return (T.accept[(size_t) T.acc_idx[P] * 8 + (b >> 5)] >> (b & 31)) & 1;
     };
 
-    /* a state = (look-behind kind, list) */
-    typedef std::pair<uint32_t, list_t> key_t;
+    /*
+     * A state = (look-behind kind, list, odd marks).  The reference dedups closures by one tag
+     * word per instruction, and a look-ahead thread that holds appends its closure under the tag
+     * of the PREVIOUS step (sre_vm_pike.c:484-509: tag--), so what that step tagged is part of
+     * the state.  Mostly that is "the instructions of the list" -- but not quite: a MATCH
+     * reached by a closure is tagged and not parked (:889-899), and an instruction appended to
+     * the next list and then visited again by a held closure carries the older tag from then on.
+     * `odd` = the parked instructions whose mark differs from their membership in the list
+     * (programs with look-ahead assertions only; nothing else ever reads the older marks).
+     */
+    struct key_t {
+        uint32_t first;
+        list_t   second, odd;
+        key_t() : first(0) {}
+        key_t(uint32_t k, const list_t &l, const list_t &o) : first(k), second(l), odd(o) {}
+        bool operator<(const key_t &r) const
+        {
+            return first != r.first ? first < r.first : second != r.second ? second < r.second : odd < r.odd;
+        }
+    };
     std::map<key_t, uint32_t> ids;
     std::vector<key_t> states;
-    states.push_back(key_t(0, list_t()));       /* state 0: the empty list */
+    states.push_back(key_t(0, list_t(), list_t()));     /* state 0: the empty list */
     ids[states[0]] = 0;
-    auto intern = [&](uint32_t pk, const list_t &l, uint32_t *id) -> bool {
+    auto intern = [&](uint32_t pk, const list_t &l, const list_t &odd, uint32_t *id) -> bool {
         /* the empty list is one state whatever came before it */
-        const key_t k(l.empty() ? 0u : pk, l);
+        const key_t k(l.empty() ? 0u : pk, l, l.empty() ? list_t() : odd);
         std::map<key_t, uint32_t>::iterator it = ids.find(k);
         if (it != ids.end()) {
             *id = it->second;
@@ -128,7 +146,7 @@ bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uin
         }
         /* (kinds the program cannot tell apart give the same state) */
         const uint32_t eff = pk == 0 ? 0u : kind_of(pk == 1 ? '\n' : pk == 2 ? 'a' : '.');
-        if (!intern(pk == 0 ? 0u : eff, init, &out.init[pk])) {
+        if (!intern(pk == 0 ? 0u : eff, init, list_t(), &out.init[pk])) {
             return false;
         }
     }
@@ -143,7 +161,7 @@ bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uin
      * cuts what has lower priority.
      */
     struct step_out_t {
-        list_t                next;
+        list_t                next, odd;
         std::vector<uint8_t>  parents;
         std::vector<uint32_t> mask0, mask1;
         bool                  mev = false;
@@ -162,6 +180,24 @@ bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uin
         for (size_t j = 0; j < cur.size(); j++) {
             m_prev[cur[j] & 0x7fff] = 1;
         }
+        for (size_t j = 0; j < st.odd.size(); j++) {
+            m_prev[st.odd[j]] ^= 1;
+        }
+        /* what this step leaves tagged, against the list it leaves */
+        auto finish = [&]() {
+            if (!lookahead) {
+                return;
+            }
+            std::vector<uint8_t> in_list(np, 0);
+            for (size_t j = 0; j < o.next.size(); j++) {
+                in_list[o.next[j] & 0x7fff] = 1;
+            }
+            for (uint32_t P = 0; P < np; P++) {
+                if (m_cur[P] != in_list[P]) {
+                    o.odd.push_back((uint16_t) P);
+                }
+            }
+        };
         std::vector<item_t> hold;           /* LIFO, back = top */
         size_t i = 0;
         for (;;) {
@@ -215,6 +251,7 @@ bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uin
                 o.mmask0 = t.mask0;
                 o.mmask1 = 0;
                 o.mreg = T.regex[P];
+                finish();
                 return;
             } else if (!eof && accepts(P, b)) {
                 for (uint32_t e = T.ofs[vnext + P]; e < T.ofs[vnext + P + 1]; e++) {
@@ -231,6 +268,7 @@ bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uin
                         o.mmask0 = t.mask0;
                         o.mmask1 = T.emask[e];
                         o.mreg = T.regex[fp];
+                        finish();
                         return;
                     }
                     o.next.push_back((uint16_t) (fp | ((T.kind[fp] >= 4 && cur_word) ? 0x8000u : 0u)));
@@ -240,6 +278,7 @@ bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uin
                 }
             }
         }
+        finish();
     };
 
     for (uint32_t s = 0; s < states.size(); s++) {
@@ -252,7 +291,7 @@ bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uin
                 return false;
             }
             uint32_t id;
-            if (!intern(kind_of(b), o.next, &id)) {
+            if (!intern(kind_of(b), o.next, o.odd, &id)) {
                 return false;
             }
             out.trans.push_back((uint16_t) (id | (o.mev ? 0x8000u : 0u)));

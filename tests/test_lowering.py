@@ -318,10 +318,13 @@ def test_pdfa_pike_fuzz_vs_oracle(oracle, lc, leftmost_first):
     rng = random.Random(31337)
     atoms = ["a", "b", "ab", " ", "_", ".", "|", "(", ")", "(?:", "*", "+", "?", "*?", "+?", "??", "{2}", "{0,2}",
              "{1,}", "[ab]", "[^a]", "\\w", "\\W", "\\s", "\\d", "1", "(a)", "(b*)", "(a|ab)", "(\\w+)",
-             "^", "\\A", "\\n", "(^a)", "(?:^|b)", "$", "\\z", "\\b", "\\B", "(a$)", "(\\bb)", "(?:$|a)"]
-    alphabet = b"ab _1.\n\n"
+             "^", "\\A", "\\n", "(^a)", "(?:^|b)", "$", "\\z", "\\b", "\\B", "(a$)", "(\\bb)", "(?:$|a)",
+             # optional look-ahead assertions: a held closure meets what the previous step tagged
+             # without parking it (a MATCH already reported) -- the `odd` marks of a P-DFA state
+             "\\B?", "\\b?", "$?", "(?:\\b|)", "(\\B)?", "x?", "a+"]
+    alphabet = b"ab _1.\n\nx"
     done = applicable = 0
-    while done < 1500:
+    while done < 2500:
         k = 1 if rng.random() < 0.7 else rng.randrange(2, 5)
         rxs = ["".join(rng.choice(atoms) for _ in range(rng.randrange(1, 9))).encode() for _ in range(k)]
         try:
@@ -338,6 +341,51 @@ def test_pdfa_pike_fuzz_vs_oracle(oracle, lc, leftmost_first):
             assert got == oracle.pike(p, s), (rxs, s, got)
         p.close()
     assert applicable > 2000
+
+
+def test_pdfa_held_closures_see_the_previous_steps_tags(oracle, lc, leftmost_first):
+    """A look-ahead thread that holds appends its closure under the PREVIOUS step's tag
+    (sre_vm_pike.c:484-509), and that step tagged more than it parked: in /a\\B?x?/ on "ax" the
+    step on `a` reports a match (MATCH tagged, not parked) and parks [\\B, x]; on `x` the \\B
+    thread holds, its closure finds `x` and MATCH tagged already and adds nothing, and the `x`
+    thread goes on to the longer match.  A P-DFA state that forgot the MATCH tag reported (0, 1)."""
+    _bind_pdfa(lc)
+    for rx, s in [(rb"a\B?x?", b"ax"), (rb"a(?:\B|)x?", b"ax"), (rb"a+\B?x?", b".aax."), (rb"a\B?(x)?", b"ax"),
+                  (rb"a\B?x?", b"axx"), (rb"^a+\B?x?", b"\nax"), (rb"a\b?x?", b"a x"), (rb"a$?x?", b"ax")]:
+        p = oracle.compile(rx, 0)
+        got = _pdfa_pike(lc, p, s)
+        assert got is not None and got == leftmost_first.pike(p, s) == _table_pike(lc, p, s), (rx, s, got)
+        p.close()
+
+
+def test_dfa_minimisation_counts_its_initial_blocks(oracle, lc, leftmost_first):
+    """Moore refinement stops when a round adds no block.  When every state has the start state's
+    EOF verdict (a set with a member that always matches at the end, /$?$\\z/) there are two
+    initial blocks, not three; counted as three, a first round that ended with three blocks was
+    taken for stable and distinguishable states stayed merged: the DFA of this set never entered
+    ACC (late SRE_OK when streaming) and its restart flags let the Pike search begin behind the
+    match."""
+    rxs = [rb"(\B)?[^a] ", rb"$?$\z"]
+    s = b"x1 ax\n\n\n\nx\n .1x\nb_ "
+    p = oracle.compile(rxs, 0)
+    h = lc.lc_create(p.prog, 4096)
+    for n in range(len(s) + 1):
+        chunk = s[:n]
+        want = oracle.thompson(p, chunk, [(chunk, False)])[0]
+        for mode in (0, 1):
+            lc.lc_reset(h)
+            assert lc.lc_dfa_exec(h, chunk, n, 0, mode) == want, (n, mode)
+        lc.lc_reset(h)
+        assert lc.lc_nfa_exec(h, chunk, n, 0) == want, n
+    want = leftmost_first.pike(p, s)
+    assert want == (0, [1, 3, -1, -1])
+    hint = lc.lc_hint_cls(h, s, len(s))
+    assert 0 <= hint <= 1, hint
+    assert lc.lc_hint(h, s, len(s)) == hint
+    _bind_pdfa(lc)
+    assert _pdfa_pike(lc, p, s, hint) == want and _table_pike(lc, p, s, hint) == want
+    lc.lc_destroy(h)
+    p.close()
 
 
 def test_pdfa_pike_from_the_start_hint(golden, oracle, lc, leftmost_first):
