@@ -533,7 +533,23 @@ extern "C" long lc_pdfa_pike(sre_program_t *prog, const uint8_t *input, long siz
     if (!have) {
         return SRE_DECLINED;
     }
-    const long oldest = pos - ring;         /* positions > oldest are still in the ring */
+    long oldest = pos - ring;               /* positions > oldest are still in the ring */
+    /* positions the ring has lost: forward again from the start, up to and including `upto`
+     * (k_pike_lineage's refill; at most 64 times per input, then the next tier) */
+    int refills = 0;
+    auto refill = [&](long upto) -> bool {
+        if (refills == 64) {
+            return false;
+        }
+        refills++;
+        uint32_t r = D.init[v0];
+        for (long p = start; p <= upto; p++) {
+            hist[(size_t) (p % ring)] = (uint16_t) r;
+            r = D.trans[(size_t) r * C + D.clsmap[input[p]]] & 0x7fff;
+        }
+        oldest = upto - ring;
+        return true;
+    };
     uint32_t cur, j, rid;
     long u;
     uint32_t unset = nslots >= 32 ? 0xffffffffu : ((1u << nslots) - 1);
@@ -551,7 +567,7 @@ extern "C" long lc_pdfa_pike(sre_program_t *prog, const uint8_t *input, long siz
         assign(D.eof_mask0[s], size);
         u = size - 1;
     } else {
-        if (mpos <= oldest) return -1001;
+        if (mpos <= oldest && !refill(mpos)) return -1001;
         cur = hist[(size_t) (mpos % ring)];
         const size_t t = (size_t) cur * C + D.clsmap[input[mpos]];
         j = D.mparent[t];
@@ -569,7 +585,7 @@ extern "C" long lc_pdfa_pike(sre_program_t *prog, const uint8_t *input, long siz
             assign(D.init_mask[D.init_mask_ofs[v0] + j], start);    /* a thread of the start closure */
             break;
         }
-        if (u <= oldest) return -1001;
+        if (u <= oldest && !refill(u)) return -1001;
         const uint32_t before = hist[(size_t) (u % ring)];
         const size_t idx = D.eofs[(size_t) before * C + D.clsmap[input[u]]] + j;
         assign(D.emask[idx], u + 1);

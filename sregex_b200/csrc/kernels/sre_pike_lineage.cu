@@ -19,8 +19,12 @@
  *             reaches the ".*?" thread or the start closure.
  *
  * Every lane executes the same two loops: no per-lane thread lists, no
- * divergence beyond the span lengths.  A lineage older than the ring (a match
- * longer than ~60 bytes) is reported SRE_K_RETRY and re-run by k_pike_table.
+ * divergence beyond the span lengths.  When the walk back needs a position
+ * older than the ring (a match longer than ~60 bytes), the lane runs the
+ * automaton forward again from its start up to that position -- the P-DFA is
+ * deterministic, the ring then holds the 64 transitions in front of it -- and
+ * walks on; after REFILLS such passes (a lineage of several thousand bytes) the
+ * line is reported SRE_K_RETRY and re-run by k_pike_table.
  */
 #include "sre_device_common.cuh"
 
@@ -29,6 +33,7 @@ using namespace sre_dev;
 namespace {
 
 constexpr int RING = 64;            /* positions remembered per lane (power of two) */
+constexpr int REFILLS = 64;         /* forward re-runs per line before it is handed to the next tier */
 
 /* bytes of the tables a block keeps in shared memory next to the rings */
 __host__ __device__ inline size_t lineage_table_bytes(const sre_dev_pdfa_t &d)
@@ -222,7 +227,6 @@ k_pike_lineage(sre_dev_pdfa_t d, const uint8_t *__restrict__ buf, const int64_t 
 
         /* backward along the lineage of the thread that matched: j = its index in the list
          * before step u + 1; a slot keeps the position of the LAST step that SAVEd it */
-        const int32_t oldest = pos - RING;      /* positions > oldest are still in the ring */
         uint32_t j, rid, unset = 0xffffffffu;
         int32_t u;
         bool lost = false, stop = false;
@@ -244,6 +248,31 @@ k_pike_lineage(sre_dev_pdfa_t d, const uint8_t *__restrict__ buf, const int64_t 
         };
         /* the transition taken at position p, as an index into eofs / mev */
         auto taken = [&](int32_t p) -> uint32_t { return *slot(p); };
+        /* positions the ring has lost: forward again from the start of the search, up to and
+         * including position `upto` (same automaton, same bytes: the same transitions) */
+        int refills = 0;
+        auto refill = [&](int32_t upto) -> bool {
+            if (refills == REFILLS) {
+                return false;
+            }
+            refills++;
+            uint32_t r = d.init[v0];
+            for (int32_t p = start; p <= upto; p++) {
+                const uint32_t b = __ldg(input + p);
+                uint32_t e;
+                if (BYTE) {
+                    e = t256[(r << 8) | b];
+                    *slot(p) = (RT) (e >> 16);
+                } else {
+                    const uint32_t t = r * C + s_cls[b];
+                    *slot(p) = (RT) t;
+                    e = ld16(trans + t);
+                }
+                r = e & 0x7fffu;
+            }
+            return true;
+        };
+        int32_t oldest = pos - RING;            /* positions > oldest are in the ring */
         if (at_eof) {
             if (d.eof0 != nullptr) {
                 assign(__ldg(d.eof0 + s), size);        /* SAVEd by assertions resolved at the end */
@@ -251,11 +280,14 @@ k_pike_lineage(sre_dev_pdfa_t d, const uint8_t *__restrict__ buf, const int64_t 
             j = ef & 0xff;
             rid = ef >> 16;
             u = size - 1;
-        } else if (mpos <= oldest) {
+        } else if (mpos <= oldest && !refill(mpos)) {
             lost = true;
             j = rid = 0;
             u = -1;
         } else {
+            if (refills) {
+                oldest = mpos - RING;
+            }
             const uint32_t tm = taken(mpos);
             const uint2 m = ld64(mev + tm);
             assign(m.x, mpos + 1);
@@ -275,8 +307,11 @@ k_pike_lineage(sre_dev_pdfa_t d, const uint8_t *__restrict__ buf, const int64_t 
                 break;
             }
             if (u <= oldest) {
-                lost = true;
-                break;
+                if (!refill(u)) {
+                    lost = true;
+                    break;
+                }
+                oldest = u - RING;
             }
             const uint32_t ei = ld32(eofs + taken(u)) + j;
             const uint2 e = ld64(ent + ei);

@@ -292,7 +292,8 @@ def _bind_pdfa(lc):
 def test_pdfa_pike_against_golden(golden, oracle, lc, leftmost_first):
     """The determinised Pike VM (ordered thread lists as DFA states + lineage walk,
     lower/sre_pdfa.cpp) on every golden block it applies to (every block whose automaton stays small): rc and
-    the whole ovector; with a short ring it either agrees or asks for the next tier."""
+    the whole ovector; with a ring of 8 positions the walk back refills it by running forward again
+    (k_pike_lineage's answer to matches longer than its ring) and still agrees."""
     _bind_pdfa(lc)
     n = short = 0
     for b in runnable(golden):
@@ -303,8 +304,8 @@ def test_pdfa_pike_against_golden(golden, oracle, lc, leftmost_first):
             n += 1
             assert got == (b["pike"]["rc"], b["pike"]["ov"]), (b["file"], b["name"], got, b["pike"])
             got8 = _pdfa_pike(lc, p, s, ring=8)
-            assert got8 == "ring" or got8 == got, (b["file"], b["name"])
-            short += got8 == "ring"
+            assert got8 == got, (b["file"], b["name"])
+            short += got[0] >= 0 and got[1][1] - got[1][0] > 8
         p.close()
     assert n > 1000 and short > 20, (n, short)
 
