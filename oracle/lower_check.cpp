@@ -537,13 +537,26 @@ extern "C" long lc_pdfa_pike(sre_program_t *prog, const uint8_t *input, long siz
     /* positions the ring has lost: forward again from the start, up to and including `upto`
      * (k_pike_lineage's refill; at most 64 times per input, then the next tier) */
     int refills = 0;
+    std::vector<uint16_t> ckpt;
     auto refill = [&](long upto) -> bool {
         if (refills == 64) {
             return false;
         }
-        refills++;
         uint32_t r = D.init[v0];
-        for (long p = start; p <= upto; p++) {
+        long p = start;
+        if (refills > 0) {
+            /* from the last noted state that still covers the `ring` positions up to `upto` */
+            long i = (upto - (ring - 1) - start) / ring;
+            i = upto - (ring - 1) < start ? 0 : i >= (long) ckpt.size() ? (long) ckpt.size() - 1 : i;
+            r = ckpt[(size_t) i];
+            p = start + i * ring;
+        }
+        const bool note = refills == 0;
+        refills++;
+        for (; p <= upto; p++) {
+            if (note && (p - start) % ring == 0 && ckpt.size() < 32) {
+                ckpt.push_back((uint16_t) r);       /* the state in front of every ring-th position */
+            }
             hist[(size_t) (p % ring)] = (uint16_t) r;
             r = D.trans[(size_t) r * C + D.clsmap[input[p]]] & 0x7fff;
         }

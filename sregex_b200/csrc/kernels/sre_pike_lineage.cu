@@ -21,10 +21,11 @@
  * Every lane executes the same two loops: no per-lane thread lists, no
  * divergence beyond the span lengths.  When the walk back needs a position
  * older than the ring (a match longer than ~60 bytes), the lane runs the
- * automaton forward again from its start up to that position -- the P-DFA is
- * deterministic, the ring then holds the 64 transitions in front of it -- and
- * walks on; after REFILLS such passes (a lineage of several thousand bytes) the
- * line is reported SRE_K_RETRY and re-run by k_pike_table.
+ * automaton forward again up to that position -- the P-DFA is deterministic,
+ * the ring then holds the 64 transitions in front of it -- and walks on: the
+ * first such pass starts where the search started and notes the state at every
+ * 64th position, the later ones start from those; after REFILLS passes (a
+ * lineage of ~4 KB) the line is reported SRE_K_RETRY and re-run by k_pike_table.
  */
 #include "sre_device_common.cuh"
 
@@ -34,6 +35,7 @@ namespace {
 
 constexpr int RING = 64;            /* positions remembered per lane (power of two) */
 constexpr int REFILLS = 64;         /* forward re-runs per line before it is handed to the next tier */
+constexpr int CKPTS = 32;           /* states remembered by the first re-run, one per RING positions */
 
 /* bytes of the tables a block keeps in shared memory next to the rings */
 __host__ __device__ inline size_t lineage_table_bytes(const sre_dev_pdfa_t &d)
@@ -251,13 +253,29 @@ k_pike_lineage(sre_dev_pdfa_t d, const uint8_t *__restrict__ buf, const int64_t 
         /* positions the ring has lost: forward again from the start of the search, up to and
          * including position `upto` (same automaton, same bytes: the same transitions) */
         int refills = 0;
+        /* the first re-run starts at the start of the search and notes the state in front of every
+         * RING-th position; the later ones start from the last such state that still lets them
+         * cover the RING positions up to `upto` (<= 2 * RING - 1 steps) */
+        uint16_t ckpt[CKPTS];
+        int32_t nck = 0;
         auto refill = [&](int32_t upto) -> bool {
             if (refills == REFILLS) {
                 return false;
             }
-            refills++;
             uint32_t r = d.init[v0];
-            for (int32_t p = start; p <= upto; p++) {
+            int32_t p = start;
+            if (refills > 0) {
+                int32_t i = (upto - (RING - 1) - start) / RING;
+                i = upto - (RING - 1) < start ? 0 : i >= nck ? nck - 1 : i;
+                r = ckpt[i];
+                p = start + i * RING;
+            }
+            const bool note = refills == 0;
+            refills++;
+            for (; p <= upto; p++) {
+                if (note && ((p - start) & (RING - 1)) == 0 && nck < CKPTS) {
+                    ckpt[nck++] = (uint16_t) r;
+                }
                 const uint32_t b = __ldg(input + p);
                 uint32_t e;
                 if (BYTE) {
