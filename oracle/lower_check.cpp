@@ -647,3 +647,9 @@ extern "C" int lc_quirk_bytes(sre_program_t *prog, uint32_t *single, uint32_t *l
     }
     return sre_quirk_bytes(prog, single) ? 1 : 0;
 }
+
+/* lower/sre_quirk.h: can a held look-ahead closure and an ordinary one visit the same instruction */
+extern "C" int lc_lookahead_overlap(sre_program_t *prog)
+{
+    return sre_lookahead_overlap(prog);
+}

@@ -389,6 +389,72 @@ def test_dfa_minimisation_counts_its_initial_blocks(oracle, lc, leftmost_first):
     p.close()
 
 
+SKIPPABLE_LOOKAHEAD = [      # (regex, subject): the closure-table model or the P-DFA model differ from the reference
+    (rb"x?(?:\B|x)+", b"ax A\n A1B\n1BxB"),
+    (rb"(\w+)*?(\B)?(a)", b"1BBA1x \n.A\n Bbb Ba.x"),
+    (rb"(\B)?(a)?(\w+)(?:\B|x)+", b" A1aAx_ A\n \nB\n\n\n\na_B1"),
+    (rb"(a)??(\w+)(\B)?(a|ab)", b"xax \nbbA._1B.\n_a.Ba1"),
+    (rb"\b?(\w+)+(?:\b|)*(?:\B|x)+", b"\nabx .B.\na\n\nxbb"),
+    (rb"\s(?:\B|x)+B*?(?:\b|)", b"_\nxb\n.bBa_x"),
+]
+
+
+def test_lookahead_overlap_flags_every_program_the_tables_get_wrong(oracle, lc, leftmost_first):
+    """The closure tables and the P-DFA deduplicate closures by parked instruction, the reference
+    by one tag word per instruction, and a held look-ahead closure runs under the PREVIOUS step's
+    tag (sre_vm_pike.c:484-509).  The two can differ when one closure parks a look-ahead assertion
+    and also visits what lies behind it -- an assertion that can be skipped, /(\\B)?x/ -- which
+    lower/sre_quirk.cpp (sre_lookahead_overlap) reports as level 2; the batch Pike runs those
+    programs on the general kernel.  Here: wherever a CPU model of the fast tiers differs from the
+    oracle the program is level 2, and ordinary patterns are not."""
+    import random
+    from sregex_b200 import corpus
+    _bind_pdfa(lc)
+    lc.lc_lookahead_overlap.argtypes = [C.c_void_p]
+    for rx in (corpus.C2_REGEX, corpus.C3_REGEX, corpus.BENCH_REGEX, rb"\bGET\b", rb"(\w+)$", rb"^(\d+)\.(\d+)",
+               rb"foo\b|bar", rb"^$|^#", rb"(GET|POST)\b", rb'"\s(\d+)\b.*?(\.*)$', rb"(?:^|\s)foo\b", rb"\d+$"):
+        p = oracle.compile(rx, 0)
+        assert lc.lc_lookahead_overlap(p.prog) < 2, rx
+        p.close()
+    p = oracle.compile(corpus.multi_pattern_set(64), 0)
+    assert lc.lc_lookahead_overlap(p.prog) == 0
+    p.close()
+    wrong = 0
+    for rx, s in SKIPPABLE_LOOKAHEAD:
+        p = oracle.compile(rx, 0)
+        assert lc.lc_lookahead_overlap(p.prog) == 2, rx
+        want = leftmost_first.pike(p, s)
+        wrong += _table_pike(lc, p, s) != want or _pdfa_pike(lc, p, s) != want
+        p.close()
+    assert wrong >= 4, wrong
+    rng = random.Random(2024)
+    atoms = ["a", "b", "A", "ab", " ", "_", ".", "|", "(", ")", "(?:", "*", "+", "?", "*?", "+?", "{2}", "{0,2}", "[ab]",
+             "[^a]", "\\w", "\\W", "\\d", "\\s", "1", "(a)", "(b*)", "(a|ab)", "(\\w+)", "()", "^", "\\A", "\\n", "$",
+             "\\z", "\\b", "\\B", "\\b?", "\\B?", "$?", "^?", "(?:\\b|)", "(?:$|a)", "(\\B)?", "(?:\\B|x)+", "x?", "a+"]
+    alphabet = b"abAB _1.\n\nx"
+    done = differ = 0
+    levels = [0, 0, 0]
+    while done < 2000:
+        k = 1 if rng.random() < 0.8 else rng.randrange(2, 4)
+        rxs = ["".join(rng.choice(atoms) for _ in range(rng.randrange(1, 9))).encode() for _ in range(k)]
+        try:
+            p = oracle.compile(rxs if k > 1 else rxs[0], rng.random() < 0.25)
+        except capi.SreSyntaxError:
+            continue
+        done += 1
+        level = lc.lc_lookahead_overlap(p.prog)
+        levels[level] += 1
+        for _ in range(4):
+            s = bytes(rng.choice(alphabet) for _ in range(rng.randrange(0, 40)))
+            want = leftmost_first.pike(p, s)
+            for got in (_table_pike(lc, p, s), _pdfa_pike(lc, p, s, ring=16)):
+                if got is not None and got != "ring" and got != want:
+                    differ += 1
+                    assert level == 2, (rxs, s, got, want)
+        p.close()
+    assert differ >= 3 and levels[0] > 500, (differ, levels)
+
+
 def test_pdfa_pike_from_the_start_hint(golden, oracle, lc, leftmost_first):
     """k_pike_lineage begins at the 16-byte boundary below the DFA start hint, from the start list
     of the byte in front (nothing / newline / word byte / other -- what `^ \\A` look back at and
