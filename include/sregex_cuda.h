@@ -249,10 +249,8 @@ SRE_API int sre_cuda_thompson_exec_text(sre_cuda_program_t *cp, const uint8_t *d
 /* Pike tier sre_cuda_pike_exec_lines may use for this program (tests): 0 = best
  * available (default): the determinised Pike VM when the program has one, else
  * the closure-table kernel, each followed by the next tier for the lines it
- * gives up on (a program with a look-ahead assertion that can be skipped, such
- * as `(\B)?x`, runs on the general kernel: only that one keeps the reference's
- * per-instruction tags); 1 = general kernel only; 2 = walking shared-memory
- * kernel; 3 = closure-table kernel also when the program has a determinised form */
+ * gives up on; 1 = general kernel only; 2 = walking shared-memory kernel; 3 =
+ * closure-table kernel also when the program has a determinised form */
 SRE_API void sre_cuda_program_set_pike_tier(sre_cuda_program_t *cp, int mode);
 /* the first tier of the last sre_cuda_pike_exec_lines call on the program: 3 = determinised
  * Pike VM (k_pike_lineage), 0 = closure tables, 2 = walking, 1 = general; -1: none yet */

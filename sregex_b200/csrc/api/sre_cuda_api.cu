@@ -154,11 +154,6 @@ struct sre_cuda_program_s {
     /* byte values that leave the DFA start state (skip-scan tier), <= 4 kept */
     int                 nleave = 0;             /* -1: more than 4               */
     uint32_t            leave_pats[4] = { 0, 0, 0, 0 };
-    /* lower/sre_quirk.h sre_lookahead_overlap: 2 = a look-ahead assertion that can be skipped
-     * (`(\B)?x`): the closure tables and the P-DFA, which deduplicate by parked instruction, can
-     * differ from the reference's per-instruction tags; the batch Pike then runs on the general
-     * kernel by default */
-    int                 pike_overlap = 0;
     /* tests: which Pike tier sre_cuda_pike_exec_lines may use / used last */
     std::atomic<int>    pike_tier_mode{0};
     std::atomic<int>    pike_last_tier{-1};
@@ -650,7 +645,6 @@ int upload(sre_cuda_program_t *cp)
     /* byte set of the leading instructions (sre_regex_compiler.c:123-241), for
      * the kernel's start-state shortcut */
     pk.quirk_possible = sre_quirk_bytes(prog, pk.quirk_single) ? 1u : 0u;
-    cp->pike_overlap = sre_lookahead_overlap(prog);
     memset(pk.leadset, 0, sizeof(pk.leadset));
     for (uint32_t i = 0; i < prog->nleading; i++) {
         const sre_instruction_t &in = prog->insts[prog->leading[i]];
@@ -1245,8 +1239,7 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
     while (k2 > k1 && !sre_pike_table_applicable(cp->pike, dev_offsets, linelen, k2, h2)) {
         k2 = k2 - 4 > k1 ? k2 - 4 : k1;
     }
-    /* (a program whose look-ahead assertions can be skipped keeps the reference's tags: general kernel) */
-    const int tier_mode = (cp->pike_tier_mode.load() == 0 && cp->pike_overlap == 2) ? 1 : cp->pike_tier_mode.load();
+    const int tier_mode = cp->pike_tier_mode.load();
     const bool table_ok = sre_pike_table_applicable(cp->pike, dev_offsets, linelen, k2 > k1 ? k2 : k1, h2)
                           && linelen < (1ull << 31);
     /* the determinised Pike VM first when the program has one; the closure-table

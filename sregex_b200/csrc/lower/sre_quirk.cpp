@@ -192,122 +192,3 @@ bool sre_quirk_bytes(const sre_program_t *prog, uint32_t single[8])
     }
     return any;
 }
-
-/*
- * sre_lookahead_overlap -- see sre_quirk.h.
- *
- * reach(root): the instructions add_thread visits from `root` without consuming (JMP / SPLIT /
- * SAVE / look-behind assertions passed through; consuming instructions, MATCH and look-ahead
- * assertions visited and not passed).
- */
-namespace {
-
-void reach(const sre_program_t *prog, int32_t pc, std::vector<uint8_t> &seen)
-{
-    if (pc < 0 || (uint32_t) pc >= prog->len || seen[pc]) {
-        return;
-    }
-    seen[pc] = 1;
-    const sre_instruction_t &in = prog->insts[pc];
-    switch (in.opcode) {
-    case SRE_OPCODE_JMP:
-        reach(prog, in.x, seen);
-        break;
-    case SRE_OPCODE_SPLIT:
-        reach(prog, in.x, seen);
-        reach(prog, in.y, seen);
-        break;
-    case SRE_OPCODE_SAVE:
-        reach(prog, pc + 1, seen);
-        break;
-    case SRE_OPCODE_ASSERT:
-        if (in.v == SRE_REGEX_ASSERT_BIG_A || in.v == SRE_REGEX_ASSERT_CARET) {
-            reach(prog, pc + 1, seen);
-        }
-        break;
-    default:
-        break;
-    }
-}
-
-inline bool is_lookahead(const sre_instruction_t &in)
-{
-    return in.opcode == SRE_OPCODE_ASSERT && in.v != SRE_REGEX_ASSERT_BIG_A && in.v != SRE_REGEX_ASSERT_CARET;
-}
-
-inline bool consumes(const sre_instruction_t &in)
-{
-    return in.opcode == SRE_OPCODE_CHAR || in.opcode == SRE_OPCODE_ANY || in.opcode == SRE_OPCODE_IN
-           || in.opcode == SRE_OPCODE_NOTIN;
-}
-
-}  // namespace
-
-int sre_lookahead_overlap(const sre_program_t *prog)
-{
-    const uint32_t n = prog->len;
-    /* what the closures behind the look-ahead assertions visit (held closures, transitively) */
-    std::vector<std::vector<uint8_t> > held(n);
-    bool any = false;
-    for (uint32_t a = 0; a < n; a++) {
-        if (is_lookahead(prog->insts[a])) {
-            held[a].assign(n, 0);
-            reach(prog, (int32_t) a + 1, held[a]);
-            any = true;
-        }
-    }
-    if (!any) {
-        return 0;
-    }
-    /* a held closure can park another look-ahead assertion, which is resolved in the same step */
-    for (bool grown = true; grown;) {
-        grown = false;
-        for (uint32_t a = 0; a < n; a++) {
-            if (held[a].empty()) {
-                continue;
-            }
-            for (uint32_t b = 0; b < n; b++) {
-                if (b != a && held[a][b] && !held[b].empty()) {
-                    for (uint32_t k = 0; k < n; k++) {
-                        if (held[b][k] && !held[a][k]) {
-                            held[a][k] = 1;
-                            grown = true;
-                        }
-                    }
-                }
-            }
-        }
-    }
-    int level = 0;
-    std::vector<uint8_t> all_normal(n, 0), seen;
-    for (int32_t root = -1; root < (int32_t) n; root++) {
-        if (root >= 0 && !consumes(prog->insts[root])) {
-            continue;
-        }
-        /* the closure a step appends: of the start (root -1) or behind a consuming instruction */
-        seen.assign(n, 0);
-        reach(prog, root + 1, seen);
-        for (uint32_t k = 0; k < n; k++) {
-            all_normal[k] |= seen[k];
-        }
-        /* one closure that parks a look-ahead assertion AND visits what lies behind it */
-        for (uint32_t a = 0; a < n; a++) {
-            if (!held[a].empty() && seen[a]) {
-                for (uint32_t k = 0; k < n; k++) {
-                    if (held[a][k] && seen[k]) {
-                        return 2;
-                    }
-                }
-            }
-        }
-    }
-    /* anything visited both by a held closure and by an ordinary one */
-    for (uint32_t a = 0; a < n; a++) {
-        for (uint32_t k = 0; k < n && !held[a].empty(); k++) {
-            if (held[a][k] && all_normal[k]) {
-                level = 1;
-            }
-        }
-    }
-    return level;
-}

@@ -26,18 +26,4 @@
  * the reference does (:452-509, :842-887): `\bGET\b`, `^\d+`, `\w+$` have an empty set. */
 bool sre_quirk_bytes(const sre_program_t *prog, uint32_t single[8]);
 
-/*
- * The fast Pike tiers (closure tables, P-DFA) deduplicate closures by parked instruction; the
- * reference does it by one tag word per instruction (:770-792), and a look-ahead thread that
- * holds appends its closure under the tag of the PREVIOUS step (:484-509).  The two agree unless
- * an instruction can be visited both by such a held closure and by an ordinary one.
- * -> 0: no look-ahead assertion, or nothing behind one is visited by an ordinary closure;
- *    1: some instruction is visited both ways, but never by one closure that also parks the
- *       assertion (`foo\b|bar`: the tail after the alternation);
- *    2: one closure parks a look-ahead assertion and visits what lies behind it (an assertion
- *       that can be skipped: `(\B)?x`, `(?:\b|x)+`): the batch Pike runs such programs on the
- *       general kernel, which keeps the reference's tags.
- */
-int sre_lookahead_overlap(const sre_program_t *prog);
-
 #endif
