@@ -1245,11 +1245,10 @@ sre_cuda_pike_exec_lines(sre_cuda_program_t *cp, const uint8_t *dev_buf, const i
     /* the determinised Pike VM first when the program has one; the closure-table
      * kernel (with its larger lists) re-runs the lines whose match outlives the ring */
     /* (SRE_PDFA_LOOKAHEAD=0 keeps programs with look-ahead assertions on the closure-table kernel) */
-    static int la_ok = -1;
-    if (la_ok < 0) {
+    static const int la_ok = [] {
         const char *e = getenv("SRE_PDFA_LOOKAHEAD");
-        la_ok = e ? atoi(e) : 1;
-    }
+        return e ? atoi(e) : 1;
+    }();
     const bool use_lineage = tier_mode == 0 && sre_pike_lineage_applicable(cp->pdfa, linelen) && table_ok
                              && (cp->pdfa.ent0 == nullptr || la_ok);
     const bool use_table = !use_lineage && table_ok && (tier_mode == 0 || tier_mode == 3);
