@@ -75,6 +75,45 @@ def test_oracle_against_live_reference_fuzz(golden, oracle, ref):
         pr.close()
 
 
+def test_oracle_against_live_reference_on_random_regex_sets(oracle, ref):
+    """Random regexes and regex SETS -- assertions that can be skipped or looped ((\\B)?, (?:\\B|x)+,
+    $?), members that match the empty string, SRE_REGEX_CASELESS -- oracle vs the reference itself:
+    Pike rc + ovector (prefilter and all), Thompson rc, and both fed in 3-byte chunks.  The family
+    on which the fast Pike tiers were found to differ from the reference: the
+    oracle does not."""
+    from test_lowering import SKIPPABLE_LOOKAHEAD
+    for rx, s in SKIPPABLE_LOOKAHEAD:
+        po, pr = oracle.compile(rx, 0), ref.compile(rx, 0)
+        assert oracle.pike(po, s) == ref.pike(pr, s), rx
+        po.close()
+        pr.close()
+    rng = random.Random(31)
+    atoms = ["a", "b", "A", "ab", " ", "_", ".", "|", "(", ")", "(?:", "*", "+", "?", "*?", "+?", "{2}", "{0,2}", "[ab]",
+             "[^a]", "\\w", "\\W", "\\d", "\\s", "1", "(a)", "(b*)", "(a|ab)", "(\\w+)", "()", "^", "\\A", "\\n", "$",
+             "\\z", "\\b", "\\B", "\\b?", "\\B?", "$?", "^?", "(?:\\b|)", "(?:$|a)", "(\\B)?", "(?:\\B|x)+", "x?", "a+"]
+    alphabet = b"abAB _1.\n\nx"
+    done = 0
+    while done < 1500:
+        k = 1 if rng.random() < 0.8 else rng.randrange(2, 4)
+        rxs = ["".join(rng.choice(atoms) for _ in range(rng.randrange(1, 9))).encode() for _ in range(k)]
+        flags = capi.SRE_REGEX_CASELESS if rng.random() < 0.25 else 0
+        try:
+            pr = ref.compile(rxs if k > 1 else rxs[0], flags)
+        except capi.SreSyntaxError:
+            continue
+        po = oracle.compile(rxs if k > 1 else rxs[0], flags)
+        done += 1
+        for _ in range(4):
+            s = bytes(rng.choice(alphabet) for _ in range(rng.randrange(0, 40)))
+            assert oracle.pike(po, s) == ref.pike(pr, s), (rxs, flags, s)
+            assert oracle.thompson(po, s) == ref.thompson(pr, s), (rxs, flags, s)
+            chunks = [(s[i:i + 3], i + 3 >= len(s)) for i in range(0, len(s), 3)] or [(b"", True)]
+            assert oracle.thompson(po, s, chunks) == ref.thompson(pr, s, chunks), (rxs, flags, s)
+            assert oracle.pike(po, s, chunks) == ref.pike(pr, s, chunks), (rxs, flags, s)
+        po.close()
+        pr.close()
+
+
 def test_post_match_continuation_against_live_reference(golden, oracle, ref):
     """global scan through the classic API: after each match the ctx is given the
     rest of the data (sre_vm_pike.c:624-635, empty-match skip :179-193)"""
