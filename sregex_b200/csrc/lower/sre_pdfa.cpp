@@ -8,7 +8,9 @@
  */
 #include "sre_pdfa.h"
 
+#include <functional>
 #include <map>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -44,6 +46,89 @@ bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uin
     out.ctx_dep = T.ctx_dep;
     out.lookahead = lookahead;
     out.max_slots = T.max_slots;
+    /*
+     * SRE_PDFA_EXACT=1 (programs with look-ahead assertions; off by default: validated on the CPU
+     * model only, see DESIGN.md 3.3 "known divergence"): the step below walks the bytecode itself
+     * with the reference's one tag word per instruction, instead of combining the closure tables,
+     * and the instructions that carry the list's tag are part of the state.  Exact also where one
+     * closure parks a look-ahead assertion and visits what lies behind it (`(\B)?x`).
+     */
+    const char *exact_env = getenv("SRE_PDFA_EXACT");
+    const bool exact = lookahead && exact_env != nullptr && atoi(exact_env) != 0;
+    std::vector<int32_t> pc_park(prog->len, -1);
+    for (uint32_t P = 0; P < np; P++) {
+        pc_park[T.park_pc[P]] = (int32_t) P;
+    }
+    std::vector<uint32_t> slot_base(prog->len, 0);          /* first slot of the regex that owns a pc */
+    {
+        uint32_t r = 0, base = 0;
+        for (uint32_t pc = 0; pc < prog->len; pc++) {
+            slot_base[pc] = base;
+            if (prog->insts[pc].opcode == SRE_OPCODE_MATCH && r + 1 < prog->nregexes) {
+                base += 2 * (uint32_t) (prog->multi_ncaps[r] + 1);
+                r++;
+            }
+        }
+    }
+    /* tag words of the walk: 0 = older, 1 = the step the current list was built in, 2 = this step */
+    std::vector<uint8_t> tagw(prog->len, 0);
+    struct walked_t {
+        uint16_t ent;           /* parked number | seen_word << 15 */
+        uint32_t mask;          /* slots SAVEd on the way */
+    };
+    /* add_thread (sre_vm_pike.c:756-942) under tag word `tag`; prev: 0 offset 0, 1 after a newline,
+     * 2 after a word byte, 3 after anything else.  -> true when MATCH was reached with want_done
+     * (its slots in *done_mask, its instruction in *done_pc) */
+    std::function<bool(int32_t, uint32_t, uint8_t, uint32_t, bool, std::vector<walked_t> &, uint32_t *, int32_t *)> walk =
+        [&](int32_t pc, uint32_t mask, uint8_t tag, uint32_t prev, bool want_done, std::vector<walked_t> &outl,
+            uint32_t *done_mask, int32_t *done_pc) -> bool {
+        const sre_instruction_t &in = prog->insts[pc];
+        if (tagw[pc] == tag) {
+            if (in.opcode == SRE_OPCODE_SPLIT && tagw[in.y] != tag) {       /* the revisited-SPLIT rule */
+                return walk(in.y, mask, tag, prev, want_done, outl, done_mask, done_pc);
+            }
+            return false;
+        }
+        tagw[pc] = tag;
+        bool sw = false;
+        switch (in.opcode) {
+        case SRE_OPCODE_JMP:
+            return walk(in.x, mask, tag, prev, want_done, outl, done_mask, done_pc);
+        case SRE_OPCODE_SPLIT:
+            if (walk(in.x, mask, tag, prev, want_done, outl, done_mask, done_pc)) {
+                return true;
+            }
+            return walk(in.y, mask, tag, prev, want_done, outl, done_mask, done_pc);
+        case SRE_OPCODE_SAVE:
+            return walk(pc + 1, mask | (1u << ((uint32_t) in.v - slot_base[pc])), tag, prev, want_done, outl,
+                        done_mask, done_pc);
+        case SRE_OPCODE_ASSERT:
+            if (in.v == SRE_REGEX_ASSERT_BIG_A) {
+                return prev == 0 && T.ctx_dep ? walk(pc + 1, mask, tag, prev, want_done, outl, done_mask, done_pc)
+                                              : false;
+            }
+            if (in.v == SRE_REGEX_ASSERT_CARET) {
+                return (prev == 0 || prev == 1) ? walk(pc + 1, mask, tag, prev, want_done, outl, done_mask, done_pc)
+                                                : false;
+            }
+            sw = (in.v == SRE_REGEX_ASSERT_SMALL_B || in.v == SRE_REGEX_ASSERT_BIG_B) && prev == 2;
+            break;
+        case SRE_OPCODE_MATCH:
+            if (want_done) {
+                *done_mask = mask;
+                *done_pc = pc;
+                return true;
+            }
+            break;
+        default:
+            break;
+        }
+        walked_t w;
+        w.ent = (uint16_t) ((uint32_t) pc_park[pc] | (sw ? 0x8000u : 0u));
+        w.mask = mask;
+        outl.push_back(w);
+        return false;
+    };
     /* what a state must remember of the byte in front of it: 0 nothing / offset 0, 1 a newline,
      * 2 a word byte, 3 anything else -- only as far as some closure can tell the difference */
     auto kind_of = [&](uint32_t b) -> uint32_t {
@@ -132,6 +217,25 @@ bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uin
         std::vector<uint8_t> marks(np, 0);
         out.init_mask_ofs[pk] = (uint32_t) out.init_mask.size();
         const uint32_t vofs = ctx_of(pk) * (np + 2);
+        list_t tagged;          /* exact: the instructions the walk tagged */
+        if (exact) {
+            std::vector<walked_t> w;
+            uint32_t dm = 0;
+            int32_t dp = 0;
+            std::fill(tagw.begin(), tagw.end(), (uint8_t) 0);
+            /* (a context the program cannot tell from "elsewhere" is walked as the kind it collapses to) */
+            const uint32_t eff0 = pk == 0 ? 0u : kind_of(pk == 1 ? '\n' : pk == 2 ? 'a' : '.');
+            walk(0, 0, 1, pk == 0 ? 0u : (eff0 == 0 ? 3u : eff0), false, w, &dm, &dp);
+            for (size_t k = 0; k < w.size(); k++) {
+                init.push_back(w[k].ent);
+                out.init_mask.push_back(w[k].mask);
+            }
+            for (uint32_t pc = 0; pc < prog->len; pc++) {
+                if (tagw[pc] == 1) {
+                    tagged.push_back((uint16_t) pc);
+                }
+            }
+        } else
         for (uint32_t e = T.ofs[vofs + np]; e < T.ofs[vofs + np + 1]; e++) {
             const uint32_t fp = T.ent[e];
             if (marks[fp]) {
@@ -146,7 +250,7 @@ bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uin
         }
         /* (kinds the program cannot tell apart give the same state) */
         const uint32_t eff = pk == 0 ? 0u : kind_of(pk == 1 ? '\n' : pk == 2 ? 'a' : '.');
-        if (!intern(pk == 0 ? 0u : eff, init, list_t(), &out.init[pk])) {
+        if (!intern(pk == 0 ? 0u : eff, init, tagged, &out.init[pk])) {
             return false;
         }
     }
@@ -172,6 +276,98 @@ bool sre_build_pdfa(const sre_program_t *prog, const sre_closure_table_t &T, uin
     auto step = [&](const key_t &st, bool eof, uint32_t b, step_out_t &o) {
         const list_t &cur = st.second;
         const uint32_t pk = st.first;
+        if (exact) {
+            /* the reference's step on the bytecode: st.odd = the instructions tagged by the step
+             * that built the list */
+            std::fill(tagw.begin(), tagw.end(), (uint8_t) 0);
+            for (size_t j = 0; j < st.odd.size(); j++) {
+                tagw[st.odd[j]] = 1;
+            }
+            const bool word_b = !eof && isword(b);
+            const uint32_t next_prev = b == '\n' ? 1u : word_b ? 2u : 3u;
+            /* (the kind of the byte in front, as far as the program can tell: 0 stands for
+             * "elsewhere" too when nothing looks at offset 0 or at newlines) */
+            const uint32_t hold_prev = (pk == 0 && !T.ctx_dep) ? 3u : pk;
+            std::vector<item_t> holdx;
+            std::vector<walked_t> w;
+            size_t ix = 0;
+            auto done = [&]() {
+                for (uint32_t pc = 0; pc < prog->len; pc++) {
+                    if (tagw[pc] == 2) {
+                        o.odd.push_back((uint16_t) pc);
+                    }
+                }
+            };
+            for (;;) {
+                item_t t;
+                if (!holdx.empty()) {
+                    t = holdx.back();
+                    holdx.pop_back();
+                } else if (ix < cur.size()) {
+                    t.ent = cur[ix];
+                    t.parent = (uint8_t) ix;
+                    t.mask0 = 0;
+                    ix++;
+                } else {
+                    break;
+                }
+                const uint32_t P = t.ent & 0x7fff;
+                const bool sw = (t.ent & 0x8000) != 0;
+                const uint32_t kind = T.kind[P];
+                const int32_t pc = T.park_pc[P];
+                uint32_t dm = 0;
+                int32_t dp = 0;
+                if (kind >= 2) {
+                    bool holds;
+                    switch (kind) {
+                    case 2:  holds = eof; break;
+                    case 3:  holds = eof || b == '\n'; break;
+                    case 4:  holds = (sw == word_b); break;
+                    default: holds = (sw != word_b); break;
+                    }
+                    if (!holds) {
+                        continue;
+                    }
+                    w.clear();
+                    walk(pc + 1, t.mask0, 1, hold_prev, false, w, &dm, &dp);
+                    for (size_t k = w.size(); k-- > 0;) {       /* prepended: the first one on top */
+                        item_t a;
+                        a.ent = w[k].ent;
+                        a.parent = t.parent;
+                        a.mask0 = w[k].mask;
+                        holdx.push_back(a);
+                    }
+                } else if (kind == 1) {
+                    o.mev = true;
+                    o.mpar = t.parent;
+                    o.mmask0 = t.mask0;
+                    o.mmask1 = 0;
+                    o.mreg = T.regex[P];
+                    done();
+                    return;
+                } else if (!eof && accepts(P, b)) {
+                    w.clear();
+                    const bool hit = walk(pc + 1, 0, 2, next_prev, true, w, &dm, &dp);
+                    for (size_t k = 0; k < w.size(); k++) {
+                        o.next.push_back(w[k].ent);
+                        o.parents.push_back(t.parent);
+                        o.mask0.push_back(t.mask0);
+                        o.mask1.push_back(w[k].mask);
+                    }
+                    if (hit) {
+                        o.mev = true;
+                        o.mpar = t.parent;
+                        o.mmask0 = t.mask0;
+                        o.mmask1 = dm;
+                        o.mreg = T.regex[pc_park[dp]];
+                        done();
+                        return;
+                    }
+                }
+            }
+            done();
+            return;
+        }
         const bool prev_word = pk == 2, cur_word = !eof && isword(b);
         const uint32_t vhold = ctx_of(pk) * (np + 2);
         const uint32_t vnext = (T.ctx_dep ? (b == '\n' ? 1u : 2u) : 0u) * (np + 2);

@@ -521,6 +521,56 @@ def test_lowering_models_broad_fuzz(oracle, lc, leftmost_first):
     assert pike_checked > 8000 and hinted > 400, (pike_checked, hinted)
 
 
+def test_pdfa_built_from_the_bytecode_is_exact_on_skippable_lookahead(golden, oracle, lc, leftmost_first, monkeypatch):
+    """SRE_PDFA_EXACT=1: sre_build_pdfa steps the bytecode itself under the reference's tag words
+    (the tagged instructions are part of a state) instead of combining the closure tables.  On the
+    CPU model of k_pike_lineage that P-DFA gives the oracle's rc and ovector on the programs the
+    table-built one gets wrong (SKIPPABLE_LOOKAHEAD), on random regex sets full of such atoms from
+    offset 0 / the hint / the 16-byte boundary below it, and on a sample of the golden blocks.  Off
+    by default: the tables it emits have not been run on a GPU."""
+    import random
+    _bind_pdfa(lc)
+    lc.lc_lookahead_overlap.argtypes = [C.c_void_p]
+    monkeypatch.setenv("SRE_PDFA_EXACT", "1")
+    for rx, s in SKIPPABLE_LOOKAHEAD:
+        p = oracle.compile(rx, 0)
+        assert _pdfa_pike(lc, p, s) == leftmost_first.pike(p, s), rx
+        p.close()
+    rng = random.Random(77)
+    atoms = ["a", "b", "A", "ab", " ", "_", ".", "|", "(", ")", "(?:", "*", "+", "?", "*?", "+?", "{2}", "{0,2}", "[ab]",
+             "[^a]", "\\w", "\\W", "\\d", "\\s", "1", "(a)", "(b*)", "(a|ab)", "(\\w+)", "()", "^", "\\A", "\\n", "$",
+             "\\z", "\\b", "\\B", "\\b?", "\\B?", "$?", "^?", "(?:\\b|)", "(?:$|a)", "(\\B)?", "(?:\\B|x)+", "x?", "a+"]
+    alphabet = b"abAB _1.\n\nx"
+    done = skippable = checked = 0
+    while done < 1500:
+        k = 1 if rng.random() < 0.8 else rng.randrange(2, 4)
+        rxs = ["".join(rng.choice(atoms) for _ in range(rng.randrange(1, 9))).encode() for _ in range(k)]
+        try:
+            p = oracle.compile(rxs if k > 1 else rxs[0], rng.random() < 0.25)
+        except capi.SreSyntaxError:
+            continue
+        done += 1
+        skippable += lc.lc_lookahead_overlap(p.prog) == 2
+        h = lc.lc_create(p.prog, 4096)
+        for _ in range(3):
+            s = bytes(rng.choice(alphabet) for _ in range(rng.randrange(0, 40)))
+            want = leftmost_first.pike(p, s)
+            hint = max(0, lc.lc_hint_cls(h, s, len(s))) if h else 0
+            for start in {0, hint, hint & ~15}:
+                got = _pdfa_pike(lc, p, s, start, ring=16)
+                assert got is None or got == want, (rxs, s, start, got, want)
+                checked += got is not None
+        if h:
+            lc.lc_destroy(h)
+        p.close()
+    assert skippable > 300 and checked > 5000, (skippable, checked)
+    for b in runnable(golden)[::5]:
+        p = oracle.compile(b["regexes_b"], b["flags"], multi=b["multi"])
+        got = _pdfa_pike(lc, p, b["subject_b"])
+        assert got is None or got == (b["pike"]["rc"], b["pike"]["ov"]), (b["file"], b["name"])
+        p.close()
+
+
 def test_pdfa_pike_from_the_start_hint(golden, oracle, lc, leftmost_first):
     """k_pike_lineage begins at the 16-byte boundary below the DFA start hint, from the start list
     of the byte in front (nothing / newline / word byte / other -- what `^ \\A` look back at and
