@@ -114,6 +114,37 @@ def test_oracle_against_live_reference_on_random_regex_sets(oracle, ref):
         pr.close()
 
 
+def test_oracle_against_reference_answers_on_fuzzed_regex_sets(oracle):
+    """tests/golden/fuzz_sets.json.gz (tests/golden/gen_fuzz_sets.py): the unmodified reference's
+    answers on 4000 seeded (regex set, subject) cases outside its own t/ corpus -- assertions that
+    can be skipped or looped, members that match the empty string, SRE_REGEX_CASELESS, the
+    prefilter-misfire family -- Thompson rc, Pike rc + ovector, and both fed in 3-byte chunks
+    (Pike with its temp-capture / pending-match trace).  Runs wherever the fixture is, i.e. also on
+    the GPU box where the reference is not."""
+    import gzip
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fuzz_sets.json.gz")
+    with gzip.open(path) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) == 4000
+    plain = lambda x: json.loads(json.dumps(x))
+    multi = matched = 0
+    for c in cases:
+        rxs = [bytes.fromhex(r) for r in c["regexes"]]
+        s = bytes.fromhex(c["subject"])
+        p = oracle.compile(rxs if len(rxs) > 1 else rxs[0], c["flags"])
+        chunks = [(s[i:i + 3], i + 3 >= len(s)) for i in range(0, len(s), 3)] or [(b"", True)]
+        assert oracle.thompson(p, s) == c["thompson"], (rxs, s)
+        assert plain(oracle.pike(p, s)) == c["pike"], (rxs, s)
+        assert plain(oracle.thompson(p, s, chunks)) == c["thompson_chunked"], (rxs, s)
+        assert plain(oracle.pike(p, s, chunks)) == c["pike_chunked"], (rxs, s)
+        multi += len(rxs) > 1
+        matched += c["pike"][0] >= 0
+        p.close()
+    assert multi > 200 and 1000 < matched < 3900, (multi, matched)
+
+
 def test_post_match_continuation_against_live_reference(golden, oracle, ref):
     """global scan through the classic API: after each match the ctx is given the
     rest of the data (sre_vm_pike.c:624-635, empty-match skip :179-193)"""
